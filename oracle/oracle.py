@@ -1,0 +1,264 @@
+"""ctypes front-end of the CPU oracle (oracle/liboracle.so).
+
+TEST INFRASTRUCTURE ONLY: importable from tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs.  The product package (pyg_lib_b200) never imports this.
+
+The functions mirror the reference's Python API (pyg_lib/sampler/__init__.py:11-200,
+pyg_lib/ops/__init__.py:99-172) on CPU tensors and consume / advance torch's default CPU
+generator exactly like the reference does (whole 128-word blocks of at::randint, see
+pyg_lib/csrc/random/cpu/rand_engine.h:80-92), so `torch.manual_seed(s)` followed by the same
+call sequence gives the same outputs as the reference.
+"""
+import ctypes as C
+import os
+import os.path as osp
+import subprocess
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+import torch
+
+_HERE = osp.dirname(osp.abspath(__file__))
+_LIB = None
+
+
+class MTState(C.Structure):
+    _fields_ = [('state', C.c_uint32 * 624), ('left', C.c_int32), ('next', C.c_int32)]
+
+
+class HomoResult(C.Structure):
+    _fields_ = [('n_edges', C.c_int64), ('n_nodes', C.c_int64),
+                ('row', C.POINTER(C.c_int64)), ('col', C.POINTER(C.c_int64)),
+                ('edge_id', C.POINTER(C.c_int64)), ('node_id', C.POINTER(C.c_int64)),
+                ('node_batch', C.POINTER(C.c_int64)), ('nodes_per_hop', C.POINTER(C.c_int64)),
+                ('edges_per_hop', C.POINTER(C.c_int64)), ('rng_blocks', C.c_int64)]
+
+
+class HeteroResult(C.Structure):
+    _fields_ = [('T', C.c_int64), ('R', C.c_int64), ('L', C.c_int64),
+                ('n_nodes', C.POINTER(C.c_int64)),
+                ('node_id', C.POINTER(C.POINTER(C.c_int64))),
+                ('node_batch', C.POINTER(C.POINTER(C.c_int64))),
+                ('nodes_per_hop', C.POINTER(C.c_int64)),
+                ('n_edges', C.POINTER(C.c_int64)),
+                ('row', C.POINTER(C.POINTER(C.c_int64))),
+                ('col', C.POINTER(C.POINTER(C.c_int64))),
+                ('edge_id', C.POINTER(C.POINTER(C.c_int64))),
+                ('edges_per_hop', C.POINTER(C.c_int64)), ('rng_blocks', C.c_int64)]
+
+
+def build(force: bool = False) -> str:
+    path = osp.join(_HERE, 'liboracle.so')
+    srcs = [osp.join(_HERE, f) for f in ('sampler_oracle.c', 'matmul_oracle.c')]
+    if force or not osp.exists(path) or any(osp.getmtime(s) > osp.getmtime(path) for s in srcs):
+        subprocess.check_call(['make', '-C', _HERE, 'liboracle.so'], stdout=subprocess.DEVNULL,
+                              stderr=subprocess.DEVNULL)
+    return path
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = C.CDLL(build())
+        _LIB.oracle_mt_seed.argtypes = [C.POINTER(MTState), C.c_uint64]
+        _LIB.oracle_randint_words.argtypes = [C.POINTER(MTState), C.c_void_p, C.c_int64]
+        _LIB.oracle_neighbor_sample.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64,
+                                                C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                                C.POINTER(MTState), C.POINTER(HomoResult)]
+        _LIB.oracle_homo_free.argtypes = [C.POINTER(HomoResult)]
+        _LIB.oracle_hetero_neighbor_sample.argtypes = [
+            C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+            C.c_void_p, C.c_int64, C.c_int, C.c_int, C.POINTER(MTState), C.POINTER(HeteroResult)]
+        _LIB.oracle_hetero_free.argtypes = [C.POINTER(HeteroResult)]
+        _LIB.oracle_segment_matmul.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                               C.c_int64, C.c_int64, C.c_int]
+        _LIB.oracle_num_threads.restype = C.c_int
+    return _LIB
+
+
+# --------------------------------------------------------------------------- RNG state plumbing
+# torch.get_rng_state() layout (CPUGeneratorImplStateLegacy): u64 seed | i32 left | i32 seeded |
+# u64 next | u64 state[624] | normal cache ...   (torch/include/ATen/CPUGeneratorImpl.h)
+_OFF_LEFT, _OFF_NEXT, _OFF_STATE = 8, 16, 24
+
+
+def mt_from_torch(gen: Optional[torch.Generator] = None) -> MTState:
+    raw = (torch.get_rng_state() if gen is None else gen.get_state()).numpy()
+    mt = MTState()
+    st = np.frombuffer(raw[_OFF_STATE:_OFF_STATE + 624 * 8].tobytes(), dtype=np.uint64).astype(np.uint32)
+    C.memmove(mt.state, st.ctypes.data, 624 * 4)
+    mt.left = int(np.frombuffer(raw[_OFF_LEFT:_OFF_LEFT + 4].tobytes(), dtype=np.int32)[0])
+    mt.next = int(np.frombuffer(raw[_OFF_NEXT:_OFF_NEXT + 8].tobytes(), dtype=np.uint64)[0])
+    return mt
+
+
+def mt_to_torch(mt: MTState, gen: Optional[torch.Generator] = None) -> None:
+    raw = (torch.get_rng_state() if gen is None else gen.get_state()).clone()
+    arr = raw.numpy()
+    st = np.ctypeslib.as_array(mt.state).astype(np.uint64)
+    arr[_OFF_STATE:_OFF_STATE + 624 * 8] = np.frombuffer(st.tobytes(), dtype=np.uint8)
+    arr[_OFF_LEFT:_OFF_LEFT + 4] = np.frombuffer(np.int32(mt.left).tobytes(), dtype=np.uint8)
+    arr[_OFF_NEXT:_OFF_NEXT + 8] = np.frombuffer(np.uint64(mt.next).tobytes(), dtype=np.uint8)
+    if gen is None:
+        torch.set_rng_state(raw)
+    else:
+        gen.set_state(raw)
+
+
+def mt_seed(seed: int) -> MTState:
+    mt = MTState()
+    lib().oracle_mt_seed(C.byref(mt), seed)
+    return mt
+
+
+def randint_words(mt: MTState, n: int) -> np.ndarray:
+    out = np.empty(n, dtype=np.uint64)
+    lib().oracle_randint_words(C.byref(mt), out.ctypes.data, n)
+    return out
+
+
+def _i64(t: torch.Tensor) -> np.ndarray:
+    return np.ascontiguousarray(t.detach().cpu().numpy().astype(np.int64, copy=False))
+
+
+def _take(ptr, n: int, dtype: torch.dtype) -> torch.Tensor:
+    if n == 0:
+        return torch.empty(0, dtype=dtype)
+    return torch.from_numpy(np.ctypeslib.as_array(ptr, shape=(n,)).copy()).to(dtype)
+
+
+# --------------------------------------------------------------------------- sampler
+def neighbor_sample(rowptr, col, seed, num_neighbors: List[int], node_time=None, edge_time=None,
+                    seed_time=None, edge_weight=None, csc: bool = False, replace: bool = False,
+                    directed: bool = True, disjoint: bool = False, temporal_strategy: str = 'uniform',
+                    return_edge_id: bool = True, mt: Optional[MTState] = None):
+    """Oracle for pyg_lib.sampler.neighbor_sample (uniform; temporal/weighted not restated)."""
+    assert node_time is None and edge_time is None and seed_time is None and edge_weight is None
+    own_mt = mt is None
+    if own_mt:
+        mt = mt_from_torch()
+    dt = seed.dtype
+    rp, cl, sd = _i64(rowptr), _i64(col), _i64(seed)
+    nn = np.asarray(num_neighbors, dtype=np.int64)
+    res = HomoResult()
+    lib().oracle_neighbor_sample(rp.ctypes.data, rp.size - 1, cl.ctypes.data, sd.ctypes.data, sd.size,
+                                 nn.ctypes.data, len(num_neighbors), int(replace), int(disjoint),
+                                 C.byref(mt), C.byref(res))
+    L = len(num_neighbors)
+    row = _take(res.row, res.n_edges, dt)
+    colv = _take(res.col, res.n_edges, dt)
+    eid = _take(res.edge_id, res.n_edges, dt)
+    node = _take(res.node_id, res.n_nodes, dt)
+    if disjoint:
+        batch = _take(res.node_batch, res.n_nodes, dt)
+        node = torch.stack([batch, node], dim=1)
+    nph = [int(res.nodes_per_hop[i]) for i in range(L + 1)]
+    eph = [int(res.edges_per_hop[i]) for i in range(L)]
+    lib().oracle_homo_free(C.byref(res))
+    if own_mt:
+        mt_to_torch(mt)
+    if not directed:
+        raise RuntimeError('Undirected subgraphs not yet supported')
+    if csc:
+        row, colv = colv, row
+    return row, colv, node, (eid if return_edge_id else None), nph, eph
+
+
+def hetero_neighbor_sample(node_types: List[str], edge_types: List[Tuple[str, str, str]],
+                           rowptr_dict: Dict[str, torch.Tensor], col_dict: Dict[str, torch.Tensor],
+                           seed_dict: Dict[str, torch.Tensor], num_neighbors_dict: Dict[str, List[int]],
+                           csc: bool = False, replace: bool = False, directed: bool = True,
+                           disjoint: bool = False, return_edge_id: bool = True,
+                           mt: Optional[MTState] = None):
+    """Oracle for torch.ops.pyg.hetero_neighbor_sample with ONE ATen thread; dict keys are
+    'src__rel__dst' strings exactly like the operator (neighbor.cpp:137-147)."""
+    own_mt = mt is None
+    if own_mt:
+        mt = mt_from_torch()
+    rel = ['__'.join(k) for k in edge_types]
+    # node type order: seed_dict order first (batch ids in disjoint mode follow it), then the rest
+    types = list(seed_dict.keys()) + [t for t in node_types if t not in seed_dict]
+    tix = {t: i for i, t in enumerate(types)}
+    T, R = len(types), len(edge_types)
+    L = max(len(num_neighbors_dict[r]) for r in rel) if R else 0
+    dt = next(iter(seed_dict.values())).dtype
+    src = np.array([tix[k[0] if not csc else k[2]] for k in edge_types], dtype=np.int64)
+    dst = np.array([tix[k[2] if not csc else k[0]] for k in edge_types], dtype=np.int64)
+    rps = [_i64(rowptr_dict[r]) for r in rel]
+    cls = [_i64(col_dict[r]) for r in rel]
+    sds = [_i64(seed_dict[t]) if t in seed_dict else np.empty(0, dtype=np.int64) for t in types]
+    PP = C.c_void_p * max(R, 1)
+    PT = C.c_void_p * max(T, 1)
+    rp_arr = PP(*[a.ctypes.data for a in rps])
+    cl_arr = PP(*[a.ctypes.data for a in cls])
+    sd_arr = PT(*[a.ctypes.data for a in sds])
+    nsd = np.array([a.size for a in sds], dtype=np.int64)
+    nn = np.array([list(num_neighbors_dict[r]) for r in rel], dtype=np.int64).reshape(R, L)
+    res = HeteroResult()
+    lib().oracle_hetero_neighbor_sample(T, R, src.ctypes.data, dst.ctypes.data, rp_arr, cl_arr, sd_arr,
+                                        nsd.ctypes.data, nn.ctypes.data, L, int(replace), int(disjoint),
+                                        C.byref(mt), C.byref(res))
+    row_d, col_d, eid_d, node_d, nph_d, eph_d = {}, {}, {}, {}, {}, {}
+    for t in node_types:
+        i = tix[t]
+        n = int(res.n_nodes[i])
+        node = _take(res.node_id[i], n, dt)
+        if disjoint:
+            node = torch.stack([_take(res.node_batch[i], n, dt), node], dim=1) if n else node.view(0, 2)
+        node_d[t] = node
+        nph_d[t] = [int(res.nodes_per_hop[i * (L + 1) + j]) for j in range(L + 1)]
+    for k, r in enumerate(rel):
+        n = int(res.n_edges[k])
+        a, b = _take(res.row[k], n, dt), _take(res.col[k], n, dt)
+        row_d[r], col_d[r] = (a, b) if not csc else (b, a)
+        eid_d[r] = _take(res.edge_id[k], n, dt)
+        eph_d[r] = [int(res.edges_per_hop[k * L + j]) for j in range(L)]
+    lib().oracle_hetero_free(C.byref(res))
+    if own_mt:
+        mt_to_torch(mt)
+    if not directed:
+        raise RuntimeError('Undirected heterogeneous graphs not yet supported')
+    return row_d, col_d, node_d, (eid_d if return_edge_id else None), nph_d, eph_d
+
+
+# --------------------------------------------------------------------------- matmul
+_DT = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}
+
+
+def _raw(t: torch.Tensor) -> torch.Tensor:
+    t = t.detach().cpu().contiguous()
+    return t if t.dtype == torch.float32 else t.view(torch.int16)
+
+
+def segment_matmul(inputs: torch.Tensor, ptr: torch.Tensor, other: torch.Tensor,
+                   bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Oracle for pyg_lib.ops.segment_matmul (pyg_lib/ops/__init__.py:137-172)."""
+    x, w = _raw(inputs), _raw(other)
+    p = np.ascontiguousarray(ptr.detach().cpu().numpy().astype(np.int64))
+    N, K = inputs.shape
+    B, _, M = other.shape
+    out = torch.zeros(N, M, dtype=inputs.dtype)
+    o = out if out.dtype == torch.float32 else out.view(torch.int16)
+    lib().oracle_segment_matmul(x.data_ptr(), p.ctypes.data, w.data_ptr(), o.data_ptr(), K, M, B,
+                                _DT[inputs.dtype])
+    if bias is not None:
+        for i in range(B):
+            out[int(p[i]):int(p[i + 1])] += bias[i].cpu()
+    return out
+
+
+def grouped_matmul(inputs: List[torch.Tensor], others: List[torch.Tensor],
+                   biases: Optional[List[torch.Tensor]] = None) -> List[torch.Tensor]:
+    """Oracle for pyg_lib.ops.grouped_matmul (pyg_lib/ops/__init__.py:99-134)."""
+    outs = []
+    for i, (a, b) in enumerate(zip(inputs, others)):
+        ptr = torch.tensor([0, a.size(0)])
+        o = segment_matmul(a.contiguous(), ptr, b.contiguous().unsqueeze(0))
+        if biases is not None:
+            o = o + biases[i].cpu()
+        outs.append(o)
+    return outs
+
+
+def num_threads() -> int:
+    return int(lib().oracle_num_threads())

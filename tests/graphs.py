@@ -1,0 +1,191 @@
+"""Deterministic synthetic inputs shared by the golden generator, the oracle tests, the GPU parity
+tests and bench.py.  Everything is derived from integer seeds with CPU torch.Generator streams, so
+the GPU box regenerates bit-identical inputs (same image, same torch build)."""
+from typing import Dict, List, Tuple
+
+import torch
+
+
+def cycle_graph(n: int):
+    """test/csrc/graph.h:5-13 (note Python-style modulo: node 0's neighbours are [n-1, 1])."""
+    rowptr = torch.arange(0, 2 * n + 1, 2)
+    col = torch.stack([torch.arange(-1, n - 1) % n, torch.arange(1, n + 1) % n], dim=1).flatten()
+    return rowptr, col
+
+
+def random_csr(n: int, avg_deg: int, seed: int, big: List[Tuple[int, int]] = (), zero_frac: float = 0.1):
+    g = torch.Generator().manual_seed(seed)
+    deg = torch.randint(0, 2 * avg_deg + 1, (n,), generator=g)
+    deg[torch.rand(n, generator=g) < zero_frac] = 0
+    for i, d in big:
+        deg[i] = d
+    rowptr = torch.zeros(n + 1, dtype=torch.int64)
+    rowptr[1:] = deg.cumsum(0)
+    col = torch.randint(0, n, (int(rowptr[-1]),), generator=g)
+    return rowptr, col
+
+
+def lognormal_csr(n: int, e: int, seed: int, device='cpu', dtype=torch.int64, mean=3.0, std=1.2):
+    """SURVEY.md 8(d) C2 recipe: log-normal degrees scaled to sum E, uniform random targets."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    w = torch.empty(n, device=device, dtype=torch.float64).log_normal_(mean, std, generator=g)
+    deg = torch.floor(w * (e / w.sum())).to(torch.int64)
+    rem = int(e - int(deg.sum()))
+    if rem > 0:
+        deg[:rem] += 1
+    rowptr = torch.zeros(n + 1, dtype=torch.int64, device=device)
+    torch.cumsum(deg, 0, out=rowptr[1:])
+    col = torch.randint(0, n, (e,), generator=g, device=device, dtype=dtype)
+    return rowptr.to(dtype), col
+
+
+HOMO_CASES: Dict[str, dict] = {
+    # known-answer vectors of test/csrc/sampler/test_neighbor.cpp (cycle graph, seeds [2,3])
+    'cycle_full': dict(graph=('cycle', 6), seeds=[2, 3], num_neighbors=[-1, -1], rng_seed=0),
+    'cycle_norep': dict(graph=('cycle', 6), seeds=[2, 3], num_neighbors=[1, 1], rng_seed=123456),
+    'cycle_rep': dict(graph=('cycle', 6), seeds=[2, 3], num_neighbors=[1, 1], rng_seed=123456, replace=True),
+    'cycle_disjoint': dict(graph=('cycle', 6), seeds=[2, 3], num_neighbors=[2, 2], rng_seed=0, disjoint=True),
+    'zero_deg': dict(graph=('zero', 5), seeds=[0, 1, 2, 3, 4], num_neighbors=[-1, -1], rng_seed=0),
+    # random graphs
+    'rand_15_10': dict(graph=('rand', 2000, 20, 1), n_seeds=64, num_neighbors=[15, 10], rng_seed=12345),
+    'rand_15_10_rep': dict(graph=('rand', 2000, 20, 1), n_seeds=64, num_neighbors=[15, 10], rng_seed=12345,
+                           replace=True),
+    'rand_csc': dict(graph=('rand', 2000, 20, 2), n_seeds=32, num_neighbors=[10, 5], rng_seed=7, csc=True),
+    'rand_3hop': dict(graph=('rand', 3000, 8, 3), n_seeds=16, num_neighbors=[5, 5, 5], rng_seed=99),
+    'rand_full': dict(graph=('rand', 1500, 6, 4), n_seeds=8, num_neighbors=[-1, 4, -1], rng_seed=5),
+    'rand_k40': dict(graph=('rand', 1000, 60, 5), n_seeds=8, num_neighbors=[40, 3], rng_seed=11),
+    'rand_k40_rep': dict(graph=('rand', 1000, 60, 5), n_seeds=8, num_neighbors=[40, 3], rng_seed=11,
+                         replace=True),
+    'rand_k100': dict(graph=('rand', 600, 150, 6), n_seeds=4, num_neighbors=[100], rng_seed=13),
+    'rand_dupseeds': dict(graph=('rand', 2000, 20, 1), seeds=[4, 4, 9, 4, 9, 1, 1500, 4], num_neighbors=[5, 5],
+                          rng_seed=1),
+    'rand_zero_fanout': dict(graph=('rand', 2000, 20, 1), n_seeds=16, num_neighbors=[0, 3], rng_seed=3),
+    # degrees >= 65536 -> mixed 16/32-bit draws (rand_engine.h:43-61)
+    'bigdeg': dict(graph=('rand', 400, 10, 7, [(5, 70000), (77, 65540), (100, 65536), (101, 65535)]),
+                   seeds=[5, 3, 77, 100, 8, 101, 5], num_neighbors=[9, 4], rng_seed=21),
+    'bigdeg_rep': dict(graph=('rand', 400, 10, 7, [(5, 70000), (77, 65540), (100, 65536), (101, 65535)]),
+                       seeds=[5, 3, 77, 100, 8, 101], num_neighbors=[9, 4], rng_seed=21, replace=True),
+    'bigdeg_k40': dict(graph=('rand', 400, 10, 7, [(5, 70000), (77, 65540), (100, 65536), (101, 65535)]),
+                       seeds=[77, 100, 101, 5], num_neighbors=[40], rng_seed=22),
+    'rand_disjoint': dict(graph=('rand', 2000, 20, 1), n_seeds=24, num_neighbors=[6, 4], rng_seed=17,
+                          disjoint=True),
+    'rand_disjoint_rep': dict(graph=('rand', 2000, 20, 1), n_seeds=24, num_neighbors=[6, 4], rng_seed=17,
+                              disjoint=True, replace=True),
+}
+
+
+def build_homo(case: dict):
+    g = case['graph']
+    if g[0] == 'cycle':
+        rowptr, col = cycle_graph(g[1])
+        n = g[1]
+    elif g[0] == 'zero':
+        rowptr, col = torch.zeros(g[1] + 1, dtype=torch.int64), torch.zeros(0, dtype=torch.int64)
+        n = g[1]
+    else:
+        rowptr, col = random_csr(g[1], g[2], g[3], big=g[4] if len(g) > 4 else ())
+        n = g[1]
+    if 'seeds' in case:
+        seed = torch.tensor(case['seeds'], dtype=torch.int64)
+    else:
+        gg = torch.Generator().manual_seed(1000 + case['rng_seed'])
+        seed = torch.randperm(n, generator=gg)[:case['n_seeds']]
+    return rowptr, col, seed
+
+
+# ------------------------------------------------------------------------------------- hetero
+_MAG_TYPES = ['paper', 'author', 'institution']
+_MAG_RELS = [('paper', 'cites', 'paper'), ('author', 'writes', 'paper'), ('author', 'affiliated_with', 'institution'),
+             ('paper', 'rev_writes', 'author'), ('institution', 'rev_affiliated_with', 'author'),
+             ('paper', 'rev_cites', 'paper')]
+
+HETERO_CASES: Dict[str, dict] = {
+    'cycle_single_rel': dict(kind='cycle', num_neighbors=[2, 2], rng_seed=0),
+    'mag_small': dict(kind='mag', sizes=dict(paper=600, author=400, institution=20), avg_deg=6,
+                      n_seeds=dict(paper=16), num_neighbors=[5, 3], rng_seed=12345, gseed=31),
+    'mag_small_csc': dict(kind='mag', sizes=dict(paper=600, author=400, institution=20), avg_deg=6,
+                          n_seeds=dict(paper=16), num_neighbors=[5, 3], rng_seed=12345, gseed=31, csc=True),
+    'mag_25_15': dict(kind='mag', sizes=dict(paper=3000, author=2000, institution=40), avg_deg=30,
+                      n_seeds=dict(paper=4), num_neighbors=[25, 15], rng_seed=5, gseed=32),
+    'mag_two_seed_types_rep': dict(kind='mag', sizes=dict(paper=600, author=400, institution=20), avg_deg=6,
+                                   n_seeds=dict(author=8, paper=8), num_neighbors=[4, 4], rng_seed=77, gseed=33,
+                                   replace=True),
+    'mag_disjoint': dict(kind='mag', sizes=dict(paper=600, author=400, institution=20), avg_deg=6,
+                         n_seeds=dict(paper=6, author=5), num_neighbors=[4, 3], rng_seed=8, gseed=34,
+                         disjoint=True),
+}
+
+
+def build_hetero(case: dict):
+    """Returns (node_types, edge_types, rowptr_dict, col_dict, seed_dict, num_neighbors_dict) with
+    'src__rel__dst' string keys, i.e. the operator-level arguments (neighbor.cpp:137-147)."""
+    if case['kind'] == 'cycle':
+        rowptr, col = cycle_graph(6)
+        return (['paper'], [('paper', 'to', 'paper')], {'paper__to__paper': rowptr}, {'paper__to__paper': col},
+                {'paper': torch.arange(2, 4)}, {'paper__to__paper': list(case['num_neighbors'])})
+    sizes = case['sizes']
+    csc = case.get('csc', False)
+    rowptr_d, col_d, nn_d = {}, {}, {}
+    for i, (a, r, b) in enumerate(_MAG_RELS):
+        # CSR over the *source* side (rows) of the traversal: src = a (csr) or b (csc)
+        rows_t, cols_t = (a, b) if not csc else (b, a)
+        g = torch.Generator().manual_seed(case['gseed'] * 100 + i)
+        n_rows, n_cols = sizes[rows_t], sizes[cols_t]
+        avg = case['avg_deg'] if n_rows > 50 else case['avg_deg'] * 20
+        deg = torch.randint(0, 2 * avg + 1, (n_rows,), generator=g)
+        rowptr = torch.zeros(n_rows + 1, dtype=torch.int64)
+        rowptr[1:] = deg.cumsum(0)
+        col = torch.randint(0, n_cols, (int(rowptr[-1]),), generator=g)
+        key = '__'.join((a, r, b))
+        rowptr_d[key], col_d[key], nn_d[key] = rowptr, col, list(case['num_neighbors'])
+    seed_d = {}
+    for t, ns in case['n_seeds'].items():
+        g = torch.Generator().manual_seed(case['gseed'] * 7 + len(seed_d))
+        seed_d[t] = torch.randperm(sizes[t], generator=g)[:ns]
+    return list(_MAG_TYPES), list(_MAG_RELS), rowptr_d, col_d, seed_d, nn_d
+
+
+# ------------------------------------------------------------------------------------- matmul
+MATMUL_CASES: Dict[str, dict] = {
+    # test/ops/test_matmul.py:14-45
+    'ref_test_f32': dict(N=8, K=16, M=32, ptr=[0, 5, 8], dtype='float32', seed=0),
+    'ref_test_bf16': dict(N=8, K=16, M=32, ptr=[0, 5, 8], dtype='bfloat16', seed=0),
+    # BASELINE.json configs[0]
+    'c1_f32': dict(N=1024, K=64, M=64, ptr=[0, 256, 512, 768, 1024], dtype='float32', seed=0),
+    # ragged, one empty segment, not tile aligned (SURVEY 8d C3 recipe, scaled down)
+    'ragged_bf16': dict(N=3000, K=128, M=128, B=8, dtype='bfloat16', seed=1, ragged=True),
+    'ragged_f16': dict(N=1000, K=64, M=96, B=5, dtype='float16', seed=2, ragged=True),
+    'ragged_f32_odd': dict(N=777, K=40, M=24, B=6, dtype='float32', seed=3, ragged=True),
+}
+
+
+def ragged_ptr(N: int, B: int, seed: int, empty: int = 1) -> torch.Tensor:
+    """Segment lengths ~ log-normal(0,1) normalised to N (largest remainder), one forced empty."""
+    g = torch.Generator().manual_seed(seed)
+    w = torch.empty(B, dtype=torch.float64).log_normal_(0.0, 1.0, generator=g)
+    if B > 1 and empty is not None:
+        w[empty % B] = 0.0
+    ideal = w / w.sum() * N
+    ln = torch.floor(ideal).to(torch.int64)
+    rem = int(N - int(ln.sum()))
+    if rem > 0:
+        order = torch.argsort(ideal - ln.double(), descending=True)
+        order = order[w[order] > 0][:rem]
+        ln[order] += 1
+    ptr = torch.zeros(B + 1, dtype=torch.int64)
+    ptr[1:] = ln.cumsum(0)
+    assert int(ptr[-1]) == N
+    return ptr
+
+
+def build_matmul(case: dict, device='cpu'):
+    dt = getattr(torch, case['dtype'])
+    g = torch.Generator().manual_seed(case['seed'])
+    if 'ptr' in case:
+        ptr = torch.tensor(case['ptr'], dtype=torch.int64)
+    else:
+        ptr = ragged_ptr(case['N'], case['B'], case['seed'] + 100)
+    B = ptr.numel() - 1
+    x = torch.randn(case['N'], case['K'], generator=g).to(dt)
+    w = (torch.randn(B, case['K'], case['M'], generator=g) / case['K'] ** 0.5).to(dt)
+    return x.to(device), ptr, w.to(device)

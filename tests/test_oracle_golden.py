@@ -1,0 +1,137 @@
+"""CPU: pin the oracle restatement (oracle/*.c) to (1) the reference's own known-answer vectors and
+(2) outputs of the reference itself (tests/golden/reference_outputs.npz, made by make_golden.py)."""
+import numpy as np
+import pytest
+import torch
+
+from graphs import (HETERO_CASES, HOMO_CASES, MATMUL_CASES, build_hetero, build_homo, build_matmul, cycle_graph)
+from oracle import oracle as O
+
+
+def test_randint_stream_matches_torch():
+    """oracle mt19937 + randint transform == at::randint(INT64_MIN, INT64_MAX) (rand_engine.h:80-85)."""
+    torch.manual_seed(123456)
+    mt = O.mt_from_torch()
+    w = O.randint_words(mt, 1000)
+    t = torch.randint(-2 ** 63, 2 ** 63 - 1, (1000,), dtype=torch.int64).numpy().view(np.uint64)
+    assert (w == t).all()
+    mt2 = O.mt_from_torch()
+    assert mt.left == mt2.left and mt.next == mt2.next
+    assert (np.ctypeslib.as_array(mt.state) == np.ctypeslib.as_array(mt2.state)).all()
+
+
+def test_mt_seed_matches_manual_seed():
+    torch.manual_seed(987654321)
+    a, b = O.mt_from_torch(), O.mt_seed(987654321)
+    assert a.left == b.left and a.next == b.next
+    assert (np.ctypeslib.as_array(a.state) == np.ctypeslib.as_array(b.state)).all()
+
+
+# ---- reference known-answer vectors, test/csrc/sampler/test_neighbor.cpp -------------------------
+def test_kat_full_neighborhood():  # :8-31
+    rowptr, col = cycle_graph(6)
+    row, colv, node, eid, nph, eph = O.neighbor_sample(rowptr, col, torch.arange(2, 4), [-1, -1])
+    assert row.tolist() == [0, 0, 1, 1, 2, 2, 3, 3]
+    assert colv.tolist() == [2, 1, 0, 3, 4, 0, 1, 5]
+    assert node.tolist() == [2, 3, 1, 4, 0, 5]
+    assert eid.tolist() == [4, 5, 6, 7, 2, 3, 8, 9]
+    assert nph == [2, 2, 2] and eph == [4, 4]
+
+
+def test_kat_zero_degree():  # :33-57
+    rowptr, col = torch.zeros(6, dtype=torch.int64), torch.zeros(0, dtype=torch.int64)
+    row, colv, node, eid, nph, eph = O.neighbor_sample(rowptr, col, torch.arange(0, 5), [-1, -1])
+    assert row.numel() == 0 and colv.numel() == 0 and eid.numel() == 0
+    assert node.tolist() == [0, 1, 2, 3, 4] and nph == [5, 0, 0] and eph == [0, 0]
+
+
+@pytest.mark.parametrize('replace', [False, True])
+def test_kat_seeded(replace):  # :59-113
+    rowptr, col = cycle_graph(6)
+    torch.manual_seed(123456)
+    row, colv, node, eid, _, _ = O.neighbor_sample(rowptr, col, torch.arange(2, 4), [1, 1], replace=replace)
+    assert row.tolist() == [0, 1, 2, 3] and colv.tolist() == [2, 3, 0, 4]
+    assert node.tolist() == [2, 3, 1, 4, 5] and eid.tolist() == [4, 7, 3, 9]
+
+
+def test_kat_disjoint():  # :115-144
+    rowptr, col = cycle_graph(6)
+    row, colv, node, eid, _, _ = O.neighbor_sample(rowptr, col, torch.arange(2, 4), [2, 2], disjoint=True)
+    assert row.tolist() == [0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5]
+    assert colv.tolist() == [2, 3, 4, 5, 6, 0, 0, 7, 8, 1, 1, 9]
+    assert node.flatten().tolist() == [0, 2, 1, 3, 0, 1, 0, 3, 1, 2, 1, 4, 0, 0, 0, 4, 1, 1, 1, 5]
+    assert eid.tolist() == [4, 5, 6, 7, 2, 3, 6, 7, 4, 5, 8, 9]
+
+
+def test_kat_hetero_single_relation():  # :259-298
+    nt, et, rp, cl, sd, nn = build_hetero(HETERO_CASES['cycle_single_rel'])
+    row, colv, node, eid, nph, eph = O.hetero_neighbor_sample(nt, et, rp, cl, sd, nn)
+    k = 'paper__to__paper'
+    assert row[k].tolist() == [0, 0, 1, 1, 2, 2, 3, 3] and colv[k].tolist() == [2, 1, 0, 3, 4, 0, 1, 5]
+    assert node['paper'].tolist() == [2, 3, 1, 4, 0, 5] and eid[k].tolist() == [4, 5, 6, 7, 2, 3, 8, 9]
+    assert nph['paper'] == [2, 2, 2] and eph[k] == [4, 4]
+
+
+# ---- fixtures produced by the reference itself ---------------------------------------------------
+def _rng_prefix():
+    return torch.get_rng_state().numpy()[:24 + 624 * 8]
+
+
+@pytest.mark.parametrize('name', list(HOMO_CASES))
+def test_homo_matches_reference(name, golden):
+    case = HOMO_CASES[name]
+    rowptr, col, seed = build_homo(case)
+    torch.manual_seed(case['rng_seed'])
+    row, colv, node, eid, nph, eph = O.neighbor_sample(rowptr, col, seed, case['num_neighbors'],
+                                                        csc=case.get('csc', False),
+                                                        replace=case.get('replace', False),
+                                                        disjoint=case.get('disjoint', False))
+    p = f'homo/{name}/'
+    assert np.array_equal(row.numpy(), golden[p + 'row'])
+    assert np.array_equal(colv.numpy(), golden[p + 'col'])
+    assert np.array_equal(node.numpy(), golden[p + 'node'])
+    assert np.array_equal(eid.numpy(), golden[p + 'eid'])
+    assert nph == golden[p + 'nph'].tolist() and eph == golden[p + 'eph'].tolist()
+    # the default CPU generator must be left exactly where the reference leaves it
+    assert np.array_equal(_rng_prefix(), golden[p + 'rng_after'])
+
+
+@pytest.mark.parametrize('name', list(HETERO_CASES))
+def test_hetero_matches_reference(name, golden):
+    case = HETERO_CASES[name]
+    nt, et, rp, cl, sd, nn = build_hetero(case)
+    torch.manual_seed(case['rng_seed'])
+    row, colv, node, eid, nph, eph = O.hetero_neighbor_sample(nt, et, rp, cl, sd, nn,
+                                                               csc=case.get('csc', False),
+                                                               replace=case.get('replace', False),
+                                                               disjoint=case.get('disjoint', False))
+    p = f'hetero/{name}/'
+    for k in rp:
+        assert np.array_equal(row[k].numpy(), golden[p + 'row/' + k]), k
+        assert np.array_equal(colv[k].numpy(), golden[p + 'col/' + k]), k
+        assert np.array_equal(eid[k].numpy(), golden[p + 'eid/' + k]), k
+        assert eph[k] == golden[p + 'eph/' + k].tolist()
+    for t in nt:
+        assert np.array_equal(node[t].numpy(), golden[p + 'node/' + t]), t
+        assert nph[t] == golden[p + 'nph/' + t].tolist()
+    assert np.array_equal(_rng_prefix(), golden[p + 'rng_after'])
+
+
+@pytest.mark.parametrize('name', list(MATMUL_CASES))
+def test_matmul_matches_reference(name, golden):
+    case = MATMUL_CASES[name]
+    x, ptr, w = build_matmul(case)
+    out = O.segment_matmul(x, ptr, w).float().numpy()
+    ref = golden[f'matmul/{name}/out']
+    if case['dtype'] == 'float32':
+        assert np.allclose(out, ref, atol=1e-5, rtol=1e-5)
+    else:  # one storage-dtype ulp elementwise + 1e-3 relative Frobenius
+        assert np.linalg.norm(out - ref) <= 1e-3 * np.linalg.norm(ref)
+        ulp = 2.0 ** -7 if case['dtype'] == 'bfloat16' else 2.0 ** -10
+        assert (np.abs(out - ref) <= ulp * np.maximum(np.abs(ref), 2.0 ** -14) + 1e-30).all()
+    # and against a plain fp32 matmul (the reference's own test oracle, test_matmul.py:38-44)
+    for i in range(ptr.numel() - 1):
+        a, b = int(ptr[i]), int(ptr[i + 1])
+        exp = (x[a:b].float() @ w[i].float()).numpy()
+        tol = 1e-5 if case['dtype'] == 'float32' else 2e-2
+        assert np.allclose(out[a:b], exp, atol=tol, rtol=tol)
