@@ -1,0 +1,157 @@
+/*
+ * include/pyg_b200.h — C ABI of libpyg_b200.so: the B200 (sm_100a) implementation of pyg-lib's two
+ * data-parallel hot paths.  Plain pointers and sizes only; no torch types.  Everything that is a
+ * "const void* / void*" tensor argument is DEVICE memory on the current CUDA device unless it says
+ * "host".  `stream` is a cudaStream_t passed as void*.
+ *
+ * The reference has no FFI layer for these paths: its boundary is the PyTorch dispatcher registry
+ * (`TORCH_LIBRARY_FRAGMENT(pyg, m)`).  Each entry point below names the reference operator kernel
+ * it replaces (paths relative to the pyg-lib tree); libpyg.so (pyg_lib_b200/csrc/torch/) is the thin
+ * registration layer that binds those dispatcher ops to this ABI — see INTEGRATION.md.
+ *
+ * All functions return 0 on success and a negative code on failure; pygb200_last_error() gives a
+ * thread-local message.  There is no CPU fallback anywhere behind this ABI.
+ */
+#ifndef PYG_B200_H_
+#define PYG_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PYGB200_OK 0
+#define PYGB200_ERR_CUDA -1
+#define PYGB200_ERR_ARG -2
+#define PYGB200_ERR_UNSUPPORTED -3
+#define PYGB200_ERR_INTERNAL -4
+
+/* element types of matmul operands */
+#define PYGB200_F32 0
+#define PYGB200_BF16 1
+#define PYGB200_F16 2
+
+/* flags for the matmul entry points */
+#define PYGB200_MM_ALLOW_TF32 1u  /* fp32 inputs may use TF32 tensor-core math
+                                     (== torch.get_float32_matmul_precision() != 'highest',
+                                     pyg_lib/csrc/ops/cuda/matmul_kernel.cu:159-165) */
+#define PYGB200_MM_FORCE_SIMT 2u  /* debugging: never take the tcgen05 path */
+
+/* flags for the sampler entry points */
+#define PYGB200_S_REPLACE 1u
+#define PYGB200_S_DISJOINT 2u
+#define PYGB200_S_INDEX32 4u      /* rowptr/col/seed are int32 (else int64) */
+
+const char* pygb200_last_error(void);
+int pygb200_cuda_version(void);          /* CUDA_VERSION the library was built with
+                                            (pyg_lib/csrc/library.cpp:19-29 `pyg::cuda_version`) */
+int pygb200_kernel_launches(void);       /* number of kernels this library launched so far
+                                            (process-wide counter; bench.py reports deltas) */
+
+/* ------------------------------------------------------------------------------------ matmul
+ * out[ptr[b]:ptr[b+1], :] = x[ptr[b]:ptr[b+1], :] @ w[b]        (row-major, contiguous)
+ *   x [N,K], w [B,K,M], out [N,M] of `dtype`; ptr_dev [B+1] int64 on the DEVICE.
+ * Replaces segment_matmul_kernel / grouped_matmul_out_kernel / run_grouped_gemm
+ * (pyg_lib/csrc/ops/cuda/matmul_kernel.cu:304-319,121-287,21-100; CUTLASS 2.x sm80 GemmGrouped)
+ * with a persistent sm_100a kernel: TMA-staged tiles -> tcgen05.mma -> TMEM -> epilogue.
+ * bias (optional, [B,M], may be NULL) is fused into the epilogue — it replaces the Python loop of
+ * pyg_lib/ops/__init__.py:169-171.
+ */
+int pygb200_segment_matmul(const void* x, const int64_t* ptr_dev, const void* w, const void* bias,
+                           void* out, int64_t N, int64_t K, int64_t M, int64_t B, int dtype,
+                           unsigned flags, void* stream);
+
+/* dW[b] = x[ptr[b]:ptr[b+1], :]^T @ dy[ptr[b]:ptr[b+1], :]     x [N,K], dy [N,M], dw [B,K,M]
+ * Replaces the per-segment torch::matmul loop + at::stack of SegmentMatmul::backward
+ * (pyg_lib/csrc/ops/autograd/matmul_kernel.cpp:92-107). */
+int pygb200_segment_matmul_wgrad(const void* x, const int64_t* ptr_dev, const void* dy, void* dw,
+                                 int64_t N, int64_t K, int64_t M, int64_t B, int dtype,
+                                 unsigned flags, void* stream);
+
+/* Independent problems C_i[n_i,m_i] = A_i[n_i,k_i] @ B_i[k_i,m_i] with arbitrary row strides (so
+ * transposed views need no copy when their inner stride is 1).  All descriptor arrays are HOST
+ * arrays of length `count`; a/b/c are device pointers.  lda/ldb/ldc are ROW strides in elements;
+ * a_colmajor[i] / b_colmajor[i] != 0 means that operand is stored transposed (column stride ==
+ * ld, row stride == 1).  Replaces grouped_matmul_kernel (matmul_kernel.cu:289-302). */
+typedef struct {
+  const void* a; const void* b; void* c;
+  int64_t n, k, m;
+  int64_t lda, ldb, ldc;
+  int32_t a_colmajor, b_colmajor;
+} pygb200_gemm_problem;
+int pygb200_grouped_matmul(const pygb200_gemm_problem* problems_host, int64_t count, int dtype,
+                           unsigned flags, void* stream);
+
+/* ------------------------------------------------------------------------------------ sampler
+ * Bit-exact reproduction of NeighborSampler / sample<> / hetero sample<>
+ * (pyg_lib/csrc/sampler/cpu/neighbor_kernel.cpp:22-328,337-514,529-841) including the RNG stream
+ * of RandintEngine (pyg_lib/csrc/random/cpu/rand_engine.h:26-97) drawn from torch's CPU mt19937.
+ */
+
+/* torch mt19937 engine state (ATen/core/MT19937RNGEngine.h mt19937_data_pod: state_, left_, next_).
+ * Host struct, in/out: on success it is advanced exactly as the reference advances the default CPU
+ * generator (whole 128-word blocks of at::randint). */
+typedef struct {
+  uint32_t state[624];
+  int32_t left;
+  int32_t next;
+} pygb200_mt19937;
+
+typedef struct pygb200_sampler pygb200_sampler; /* opaque: persistent device workspace */
+
+int pygb200_sampler_create(pygb200_sampler** out);
+void pygb200_sampler_destroy(pygb200_sampler* s);
+
+/* One relation's CSR (device) plus its endpoints as indices into the node-type list. For csc=True
+ * callers pass src_type = the relation's dst and dst_type = its src (neighbor_kernel.cpp:718-719). */
+typedef struct {
+  const void* rowptr;   /* [num_src_nodes + 1] */
+  const void* col;      /* [num_edges] */
+  int64_t num_src_nodes;
+  int64_t num_edges;
+  int32_t src_type;
+  int32_t dst_type;
+} pygb200_relation;
+
+/* Runs all hops on `stream`, then synchronises the stream once and fills the host count arrays.
+ *   T node types, R relations (in the reference's `edge_types` order), L hops.
+ *   seeds[t] device pointer (or NULL), n_seeds[t] counts; seed order == seed_dict order only matters
+ *   for disjoint batch numbering, which follows type index order.
+ *   num_neighbors host [R*L] (row r = relation r; -1 == all neighbours).
+ * Outputs (host): nodes_per_hop [T*(L+1)], edges_per_hop [R*L], n_nodes [T], n_edges [R].
+ * The sampled subgraph stays in the workspace until the next run; copy it out with the export calls.
+ */
+int pygb200_sampler_run(pygb200_sampler* s, int32_t T, int32_t R, int32_t L,
+                        const pygb200_relation* rels_host, const void* const* seeds,
+                        const int64_t* n_seeds, const int64_t* num_neighbors, unsigned flags,
+                        pygb200_mt19937* mt_inout, int64_t* nodes_per_hop, int64_t* edges_per_hop,
+                        int64_t* n_nodes, int64_t* n_edges, void* stream);
+
+/* Asynchronous copies (cast to int32 when index32 != 0) of the last run's results into caller
+ * buffers of exactly n_edges[r] / n_nodes[t] elements.  row = local index of the source (frontier)
+ * node, col = local index of the sampled neighbour, edge_id = position in the relation's `col`
+ * (neighbor_kernel.cpp:309-315).  Pass NULL to skip an array.  node_batch is only valid for disjoint
+ * runs (node_id_out then receives [n,2] pairs (batch,node) like cpu/convert.h:17-24). */
+int pygb200_sampler_export_edges(pygb200_sampler* s, int32_t rel, void* row_out, void* col_out,
+                                 void* edge_id_out, int index32, void* stream);
+int pygb200_sampler_export_nodes(pygb200_sampler* s, int32_t type, void* node_id_out, int index32,
+                                 void* stream);
+
+/* Homogeneous convenience wrapper == T=1, R=1 (neighbor_sample_kernel, neighbor_kernel.cpp:899-926). */
+int pygb200_neighbor_sample_run(pygb200_sampler* s, const void* rowptr, const void* col,
+                                int64_t num_nodes, int64_t num_edges, const void* seed,
+                                int64_t n_seed, const int64_t* num_neighbors, int32_t L,
+                                unsigned flags, pygb200_mt19937* mt_inout, int64_t* nodes_per_hop,
+                                int64_t* edges_per_hop, int64_t* n_nodes, int64_t* n_edges,
+                                void* stream);
+
+/* ---- frontier-sharded multi-GPU building blocks (semantics of the reference's
+ * dist_neighbor_sample / relabel_neighborhood split, neighbor_kernel.cpp:296-303,957-978) ---------
+ * See pyg_lib_b200/sampler/dist.py for the orchestration over torch.distributed (NCCL). */
+int pygb200_mt_raw_words(const pygb200_mt19937* mt, int64_t n_words, uint64_t* out_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PYG_B200_H_ */

@@ -1,0 +1,151 @@
+// Device-side reproduction of the random stream pyg-lib's sampler consumes.
+//
+// Reference semantics (restated, not copied):
+//   * torch CPU generator = mt19937 (torch/include/ATen/core/MT19937RNGEngine.h:134-184); a 64-bit
+//     draw is two consecutive 32-bit outputs, first one in the high half (CPUGeneratorImpl::random64).
+//   * RandintEngine (pyg_lib/csrc/random/cpu/rand_engine.h:26-97) fetches blocks of 128 words
+//     w = (random64() % (2^64-1)) + INT64_MIN, reads block elements from index 127 down to 0 and
+//     slices each word into 16/32/64-bit fields from the low end.
+//
+// B200 design: the mt19937 *raw* (untempered) state stream is materialised in HBM by one CTA using
+// the linear recurrence  raw[m] = raw[m-227] ^ T(raw[m-624], raw[m-623])  unrolled KL times, so that
+// up to min(227*KL, 623) words are produced per barrier instead of one 624-word twist per three
+// barriers.  Tempering, 64-bit assembly and the randint transform happen at the point of use.
+#pragma once
+#include "common.cuh"
+
+namespace pygb200 {
+
+constexpr int MT_N = 624;
+constexpr int MT_M = 397;
+constexpr int MT_LAG = MT_N - MT_M;  // 227
+
+__host__ __device__ __forceinline__ u32 mt_twist(u32 u, u32 v) {
+  return (((u & 0x80000000u) | (v & 0x7fffffffu)) >> 1) ^ ((v & 1u) ? 0x9908b0dfu : 0u);
+}
+__host__ __device__ __forceinline__ u32 mt_temper(u32 y) {
+  y ^= (y >> 11);
+  y ^= (y << 7) & 0x9d2c5680u;
+  y ^= (y << 15) & 0xefc60000u;
+  y ^= (y >> 18);
+  return y;
+}
+
+// Raw index of the first not-yet-consumed output for an engine pod (left_, next_):
+// invariant left+next == 625 except right after seeding (left=1,next=0) where the whole state
+// array is "used up" and the next output is element 0 of the next generation.
+__host__ __device__ __forceinline__ i64 mt_next0(int left) { return 625 - (i64)left; }
+
+// Number of engine outputs the reference draws for `units` consumed 16-bit units: whole blocks of
+// 128 words, at least one (the constructor prefetches, rand_engine.h:28,80-85).
+__host__ __device__ __forceinline__ i64 rng_blocks_for_units(i64 units) {
+  i64 words = (units + 3) >> 2;
+  i64 blocks = (words + 127) >> 7;
+  return blocks < 1 ? 1 : blocks;
+}
+
+// Word W (0-based, in consumption order) of the RandintEngine stream.
+__device__ __forceinline__ u64 rng_word(const u32* __restrict__ raw, i64 out0, i64 W) {
+  const i64 b = W >> 7;
+  const int e = 127 - (int)(W & 127);
+  const i64 o = out0 + (b << 8) + 2 * e;
+  const u64 hi = mt_temper(raw[o]), lo = mt_temper(raw[o + 1]);
+  u64 v = (hi << 32) | lo;
+  if (v == ~0ull) v = 0;            // v % (2^64 - 1)
+  return v + 0x8000000000000000ull;  // + INT64_MIN, viewed as uint64
+}
+
+// width in 16-bit units of a draw with this range (rand_engine.h:43-50)
+__host__ __device__ __forceinline__ int rng_width_units(u64 range) {
+  return range < (1ull << 16) ? 1 : (range < (1ull << 32) ? 2 : 4);
+}
+// leftover bits too few -> skip to the next word (rand_engine.h:53-61)
+__host__ __device__ __forceinline__ i64 rng_align(i64 pos, int wu) {
+  const int ph = (int)(pos & 3);
+  return (ph + wu > 4) ? pos + (4 - ph) : pos;
+}
+// position after `n` consecutive draws of the same width starting at `pos`
+__host__ __device__ __forceinline__ i64 rng_run(i64 pos, int wu, i64 n) {
+  if (n <= 0) return pos;
+  if (wu == 1) return pos + n;
+  if (wu == 4) return rng_align(pos, 4) + 4 * n;
+  pos = rng_align(pos, 2) + 2;  // after one 32-bit draw the phase is 0, 2 or 3
+  if (--n == 0) return pos;
+  pos = rng_align(pos, 2) + 2;  // after two it is even
+  return pos + 2 * (n - 1);
+}
+// A node's draws come as n16 16-bit draws, then n32 32-bit, then n64 64-bit (ranges only grow).
+// Start position (aligned) of draw j (0-based) when the node's first draw may start at `pos`.
+__host__ __device__ __forceinline__ i64 rng_draw_start(i64 pos, i64 n16, i64 n32, i64 j, int* wu_out) {
+  if (j < n16) { *wu_out = 1; return pos + j; }
+  pos += n16;
+  if (j < n16 + n32) { *wu_out = 2; return rng_align(rng_run(pos, 2, j - n16), 2); }
+  pos = rng_run(pos, 2, n32);
+  *wu_out = 4;
+  return rng_align(rng_run(pos, 4, j - n16 - n32), 4);
+}
+__host__ __device__ __forceinline__ i64 rng_node_end(i64 pos, i64 n16, i64 n32, i64 n64) {
+  return rng_run(rng_run(pos + n16, 2, n32), 4, n64);
+}
+
+__device__ __forceinline__ u64 rng_draw(const u32* __restrict__ raw, i64 out0, i64 pos, int wu, u64 range) {
+  const u64 w = rng_word(raw, out0, pos >> 2);
+  const int sh = (int)(pos & 3) * 16;
+  if (wu == 1) return (u64)(((u32)(w >> sh) & 0xffffu) % (u32)range);
+  if (wu == 2) return (u64)((u32)(w >> sh) % (u32)range);
+  return w % range;
+}
+
+// ---------------------------------------------------------------------------------- generation
+struct MTPodParam {
+  u32 state[MT_N];
+};
+
+__global__ void k_mt_init(u32* __restrict__ raw, i64* generated, const __grid_constant__ MTPodParam pod) {
+  for (int i = threadIdx.x; i < MT_N; i += blockDim.x) raw[i] = pod.state[i];
+  if (threadIdx.x == 0) *generated = MT_N;
+}
+
+constexpr int MT_WIN = 4096;  // circular shared-memory window (words)
+
+// Extends raw[] so that it covers every engine output needed for `*units_ptr` consumed units plus
+// the generation holding the final state.  One CTA; `KL` = recurrence unroll.
+template <int KL>
+__global__ void __launch_bounds__(640) k_mt_extend(u32* __restrict__ raw, i64* generated, const i64* units_ptr,
+                                                    i64 next0, i64 cap_words, int* error) {
+  __shared__ u32 win[MT_WIN];
+  const i64 need = next0 + 256 * rng_blocks_for_units(*units_ptr);
+  i64 target = ((need + MT_N - 1) / MT_N) * MT_N;
+  i64 m = *generated;
+  if (target <= m) return;
+  if (target > cap_words) {
+    if (threadIdx.x == 0) *error = 1;
+    return;
+  }
+  constexpr int HIST = MT_N + MT_LAG * (KL - 1);
+  const i64 h0 = m > HIST ? m - HIST : 0;
+  for (i64 i = h0 + threadIdx.x; i < m; i += blockDim.x) win[i & (MT_WIN - 1)] = raw[i];
+  __syncthreads();
+  while (m < target) {
+    int k = (int)((m - MT_N) / MT_LAG) + 1;  // history available for this unroll factor
+    if (k > KL) k = KL;
+    i64 n = (i64)MT_LAG * k;
+    if (n > MT_N - 1) n = MT_N - 1;  // the T(raw[m-624], raw[m-623]) term caps the step at 623 words
+    if (n > target - m) n = target - m;
+    if ((i64)threadIdx.x < n) {
+      const i64 mm = m + threadIdx.x;
+      u32 x = win[(mm - (i64)MT_LAG * k) & (MT_WIN - 1)];
+#pragma unroll
+      for (int j = 0; j < KL; ++j)
+        if (j < k)
+          x ^= mt_twist(win[(mm - MT_N - MT_LAG * j) & (MT_WIN - 1)], win[(mm - MT_N + 1 - MT_LAG * j) & (MT_WIN - 1)]);
+      win[mm & (MT_WIN - 1)] = x;  // never aliases a word read in this step (window >> history + step)
+      raw[mm] = x;
+    }
+    __syncthreads();
+    m += n;
+  }
+  if (threadIdx.x == 0) *generated = m;
+}
+
+}  // namespace pygb200

@@ -1,0 +1,1086 @@
+// pyg_lib_b200/csrc/sampler.cu — neighbor_sample / hetero_neighbor_sample for sm_100a.
+//
+// Replaces the single-threaded CPU loops of pyg_lib/csrc/sampler/cpu/neighbor_kernel.cpp
+// (NeighborSampler :22-328, homogeneous sample<> :337-514, hetero sample<> :529-841) and reproduces
+// them bit-for-bit, including the order in which the sequential RandintEngine stream
+// (pyg_lib/csrc/random/cpu/rand_engine.h:26-97) is consumed.
+//
+// One "pass" = (hop, relation).  Sizes never leave the device while a pass runs:
+//   k_count   thread per frontier node: degree -> #edges emitted and the node's RNG "advance
+//             function" (phase-in -> units consumed), block-local ordered scans, per-node records;
+//             the LAST block to finish scans the tile aggregates (edge offsets + absolute RNG
+//             positions) and extends the mt19937 raw stream to cover the pass.
+//   k_sample  one group of G lanes per frontier node: draws (Robert Floyd / with replacement / full
+//             row), coalesced writes of (row, global dst, edge id), hash insert keyed by global id
+//             with atomicMin of the flat emission position (first-occurrence order).
+//   k_mark    edge is "first" iff its position won the atomicMin; tile-local ranks; last block scans.
+//   k_assign  new local ids = ids_base + rank, appended to the dst type's node list.
+//   k_lookup  every edge reads its final local id.
+// Host work per call: bounds, launches, ONE stream sync at the end (the API returns host counts).
+#include <algorithm>
+#include <atomic>
+#include <mutex>
+#include <vector>
+
+#include "common.cuh"
+#include "mt19937.cuh"
+
+namespace pygb200 {
+
+// ------------------------------------------------------------------------------- error plumbing
+static thread_local std::string g_err;
+static std::atomic<int> g_launches{0};
+void set_error(const std::string& msg) { g_err = msg; }
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+namespace {
+
+constexpr int NT = 256;              // threads per block everywhere in this file
+constexpr int ETILE = 1024;          // edges per mark/assign tile (NT x 4)
+constexpr u64 EMPTY = ~0ull;
+constexpr u64 POS_BASE = 1ull << 62; // vals >= POS_BASE are flat positions of the running pass
+constexpr u32 NO_SLOT = 0xffffffffu;
+constexpr int SCAN_NT = 1024;
+
+// state buffer (device, i64 words); a pinned mirror is read by the host after the final sync
+enum {
+  ST_CURSOR = 0,    // RNG units consumed so far (end of last scanned pass)
+  ST_GEN = 1,       // raw mt words generated
+  ST_PASS_F = 2,    // frontier size of the running pass
+  ST_PASS_E = 3,    // edges emitted by the running pass
+  ST_PASS_BASE = 4, // offset of the running pass inside its relation's edge arrays
+  ST_PASS_NEW = 5,  // new nodes found by the running pass
+  ST_LIST_BASE = 6, // dst list length before the running pass
+  ST_IDS_BASE = 7,  // dst id counter before the running pass
+  ST_ERROR = 8,
+  ST_MT_NEXT = 9, ST_MT_LEFT = 10, ST_BLOCKS = 11,
+  ST_TICKET_A = 12, ST_TICKET_B = 13,
+  ST_HDR = 16
+};
+
+struct NodeRec {   // per frontier node of the running pass (written by k_count, read by k_sample)
+  i64 rs;          // rowptr[v]
+  u32 deg;         // degree (clamped; degrees >= 2^32 are rejected on the host side)
+  u32 loc_off;     // edges emitted by earlier nodes of the same 256-node tile
+  u32 pf[4];       // RNG units consumed by earlier nodes of the tile, per entry phase
+};
+
+struct PassArgs {
+  const void* rowptr; const void* col;
+  const i64* src_nodes; const i64* src_batch;
+  i64* dst_nodes; i64* dst_batch; u32* dst_slot;
+  u64* keys; u64* vals; u64 mask;
+  i64* row; i64* colv; i64* eid;
+  u32* eslot; u32* erank;
+  NodeRec* rec; i64* tile_out; u32* tile_func; i64* tile_off; i64* tile_pos;
+  i64* mtile;      // per edge tile: count of firsts, then exclusive offset
+  i64* st;
+  int o_src_begin, o_src_end, o_dst_list, o_dst_ids, o_rel_edges, o_eph;
+  u32* raw; i64 next0; i64 raw_cap;
+  i64 fanout; int replace; int disjoint; int seed_mode;
+};
+
+// ------------------------------------------------------------------------------------- helpers
+__device__ __forceinline__ u64 hash64(u64 x) {
+  x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33;
+  return x;
+}
+
+// open addressing, linear probing; returns the slot holding `key`
+__device__ __forceinline__ u32 table_insert(u64* keys, u64 mask, u64 key) {
+  u64 s = hash64(key) & mask;
+  while (true) {
+    const u64 prev = atomicCAS(&keys[s], EMPTY, key);
+    if (prev == EMPTY || prev == key) return (u32)s;
+    s = (s + 1) & mask;
+  }
+}
+
+__device__ __forceinline__ u64 make_key(i64 node, i64 batch, int disjoint) {
+  return disjoint ? (((u64)batch << 40) | (u64)node) : (u64)node;
+}
+
+struct Func4 { u32 d[4]; };
+// apply a first, then b
+__device__ __forceinline__ Func4 compose(const Func4& a, const Func4& b) {
+  Func4 c;
+#pragma unroll
+  for (int p = 0; p < 4; ++p) c.d[p] = a.d[p] + b.d[(p + a.d[p]) & 3];
+  return c;
+}
+struct Func4L { u64 d[4]; };
+__device__ __forceinline__ Func4L composeL(const Func4L& a, const Func4L& b) {
+  Func4L c;
+#pragma unroll
+  for (int p = 0; p < 4; ++p) c.d[p] = a.d[p] + b.d[(p + a.d[p]) & 3];
+  return c;
+}
+
+// how a frontier node is sampled (neighbor_kernel.cpp:58-72,177-243)
+enum { MODE_NONE = 0, MODE_FULL = 1, MODE_REPLACE = 2, MODE_FLOYD = 3 };
+__device__ __forceinline__ int classify(i64 deg, i64 k, int replace, i64* n_out, i64* n16, i64* n32, i64* n64) {
+  *n16 = *n32 = *n64 = 0;
+  if (deg == 0 || k == 0) { *n_out = 0; return MODE_NONE; }
+  if (k < 0 || (!replace && k >= deg)) { *n_out = deg; return MODE_FULL; }
+  *n_out = k;
+  if (replace) {
+    const int wu = rng_width_units((u64)deg);
+    if (wu == 1) *n16 = k; else if (wu == 2) *n32 = k; else *n64 = k;
+    return MODE_REPLACE;
+  }
+  // Floyd: ranges deg-k+1 .. deg, increasing
+  const i64 lo = deg - k;  // range_j = lo + 1 + j
+  i64 a = 65535 - lo; a = a < 0 ? 0 : (a > k ? k : a);
+  i64 b = 4294967295ll - lo; b = b < 0 ? 0 : (b > k ? k : b);
+  *n16 = a; *n32 = b - a; *n64 = k - b;
+  return MODE_FLOYD;
+}
+
+// ordered exclusive scan of (u32 sum, Func4) over the NT threads of a block
+__device__ __forceinline__ void block_scan_pair(u32 v, Func4 f, u32* ex_v, Func4* ex_f, u32* tot_v, Func4* tot_f) {
+  __shared__ u32 s_v[NT / 32];
+  __shared__ Func4 s_f[NT / 32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  u32 iv = v; Func4 iff = f;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const u32 ov = __shfl_up_sync(0xffffffffu, iv, d);
+    Func4 of;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) of.d[p] = __shfl_up_sync(0xffffffffu, iff.d[p], d);
+    if (lane >= d) { iv += ov; iff = compose(of, iff); }
+  }
+  if (lane == 31) { s_v[wid] = iv; s_f[wid] = iff; }
+  __syncthreads();
+  u32 pv = 0; Func4 pfx = {{0, 0, 0, 0}};
+  for (int w = 0; w < wid; ++w) { pv += s_v[w]; pfx = compose(pfx, s_f[w]); }
+  // exclusive = prefix of earlier warps, then inclusive of the previous lane
+  u32 ev = __shfl_up_sync(0xffffffffu, iv, 1);
+  Func4 ef;
+#pragma unroll
+  for (int p = 0; p < 4; ++p) ef.d[p] = __shfl_up_sync(0xffffffffu, iff.d[p], 1);
+  if (lane == 0) { ev = 0; ef = {{0, 0, 0, 0}}; }
+  *ex_v = pv + ev;
+  *ex_f = compose(pfx, ef);
+  u32 tv = 0; Func4 tf = {{0, 0, 0, 0}};
+  for (int w = 0; w < NT / 32; ++w) { tv += s_v[w]; tf = compose(tf, s_f[w]); }
+  *tot_v = tv; *tot_f = tf;
+  __syncthreads();
+}
+
+// Single-block ordered scan of the frontier tile aggregates: edge offsets and absolute RNG positions.
+// Runs in the last block of k_count.  blockDim.x == NT.
+__device__ void scan_frontier_tiles(const PassArgs& a, i64 ntiles) {
+  __shared__ i64 s_sum[NT / 32];
+  __shared__ Func4L s_fun[NT / 32];
+  __shared__ i64 c_off, c_pos;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (threadIdx.x == 0) { c_off = 0; c_pos = a.st[ST_CURSOR]; }
+  __syncthreads();
+  for (i64 base = 0; base < ntiles; base += NT) {
+    const i64 t = base + threadIdx.x;
+    i64 v = 0; Func4L f = {{0, 0, 0, 0}};
+    if (t < ntiles) {
+      v = __ldcg(&a.tile_out[t]);
+#pragma unroll
+      for (int p = 0; p < 4; ++p) f.d[p] = __ldcg(&a.tile_func[4 * t + p]);
+    }
+    i64 iv = v; Func4L iff = f;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const i64 ov = __shfl_up_sync(0xffffffffu, iv, d);
+      Func4L of;
+#pragma unroll
+      for (int p = 0; p < 4; ++p) of.d[p] = __shfl_up_sync(0xffffffffu, iff.d[p], d);
+      if (lane >= d) { iv += ov; iff = composeL(of, iff); }
+    }
+    if (lane == 31) { s_sum[wid] = iv; s_fun[wid] = iff; }
+    __syncthreads();
+    i64 pv = 0; Func4L pfx = {{0, 0, 0, 0}};
+    for (int w = 0; w < wid; ++w) { pv += s_sum[w]; pfx = composeL(pfx, s_fun[w]); }
+    i64 ev = __shfl_up_sync(0xffffffffu, iv, 1);
+    Func4L ef;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) ef.d[p] = __shfl_up_sync(0xffffffffu, iff.d[p], 1);
+    if (lane == 0) { ev = 0; ef = {{0, 0, 0, 0}}; }
+    const Func4L exf = composeL(pfx, ef);
+    const i64 off0 = c_off, pos0 = c_pos;
+    if (t < ntiles) {
+      a.tile_off[t] = off0 + pv + ev;
+      a.tile_pos[t] = pos0 + (i64)exf.d[pos0 & 3];
+    }
+    i64 tv = 0; Func4L tf = {{0, 0, 0, 0}};
+    for (int w = 0; w < NT / 32; ++w) { tv += s_sum[w]; tf = composeL(tf, s_fun[w]); }
+    __syncthreads();
+    if (threadIdx.x == 0) { c_off = off0 + tv; c_pos = pos0 + (i64)tf.d[pos0 & 3]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const i64 E = c_off;
+    a.st[ST_PASS_E] = E;
+    a.st[ST_CURSOR] = c_pos;
+    if (!a.seed_mode) {
+      a.st[ST_PASS_BASE] = a.st[a.o_rel_edges];
+      a.st[a.o_rel_edges] += E;
+      a.st[a.o_eph] = E;
+    }
+  }
+  __syncthreads();
+}
+
+// mt19937 raw-stream extension by the calling block (blockDim.x == NT): same recurrence as
+// k_mt_extend but with NT threads per step (several words per thread).
+template <int KL>
+__device__ void mt_extend_block(u32* __restrict__ raw, i64* st, i64 next0, i64 cap_words, u32* win) {
+  const i64 need = next0 + 256 * rng_blocks_for_units(st[ST_CURSOR]);
+  const i64 target = ((need + MT_N - 1) / MT_N) * MT_N;
+  i64 m = st[ST_GEN];
+  if (target <= m) return;
+  if (target > cap_words) {
+    if (threadIdx.x == 0) st[ST_ERROR] = 1;
+    return;
+  }
+  constexpr int HIST = MT_N + MT_LAG * (KL - 1);
+  const i64 h0 = m > HIST ? m - HIST : 0;
+  for (i64 i = h0 + threadIdx.x; i < m; i += blockDim.x) win[i & (MT_WIN - 1)] = __ldcg(&raw[i]);
+  __syncthreads();
+  while (m < target) {
+    int k = (int)((m - MT_N) / MT_LAG) + 1;
+    if (k > KL) k = KL;
+    i64 n = (i64)MT_LAG * k;
+    if (n > MT_N - 1) n = MT_N - 1;
+    if (n > target - m) n = target - m;
+    for (i64 idx = threadIdx.x; idx < n; idx += blockDim.x) {
+      const i64 mm = m + idx;
+      u32 x = win[(mm - (i64)MT_LAG * k) & (MT_WIN - 1)];
+#pragma unroll
+      for (int j = 0; j < KL; ++j)
+        if (j < k)
+          x ^= mt_twist(win[(mm - MT_N - MT_LAG * j) & (MT_WIN - 1)], win[(mm - MT_N + 1 - MT_LAG * j) & (MT_WIN - 1)]);
+      win[mm & (MT_WIN - 1)] = x;
+      raw[mm] = x;
+    }
+    __syncthreads();
+    m += n;
+  }
+  if (threadIdx.x == 0) st[ST_GEN] = m;
+  __syncthreads();
+}
+
+// "last block done" ticket: returns true in exactly one block, after all other blocks' global
+// writes issued before their call are visible.
+__device__ __forceinline__ bool last_block(i64* ticket) {
+  __shared__ int s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const u64 t = atomicAdd((u64*)ticket, 1ull);
+    s_last = (t == (u64)gridDim.x - 1);
+    if (s_last) *ticket = 0;
+  }
+  __syncthreads();
+  if (s_last) __threadfence();
+  return s_last != 0;
+}
+
+// ------------------------------------------------------------------------------------ kernels
+template <typename idx_t>
+__global__ void __launch_bounds__(NT) k_count(const PassArgs a) {
+  __shared__ u32 s_win[MT_WIN];
+  const i64 begin = a.st[a.o_src_begin], end = a.st[a.o_src_end];
+  const i64 F = end - begin;
+  const i64 ntiles = ceil_div(F, NT);
+  const idx_t* __restrict__ rowptr = (const idx_t*)a.rowptr;
+  for (i64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const i64 i = tile * NT + threadIdx.x;
+    i64 rs = 0, deg = 0, n_out = 0, n16 = 0, n32 = 0, n64 = 0;
+    Func4 f = {{0, 0, 0, 0}};
+    if (i < F) {
+      const i64 v = a.src_nodes[begin + i];
+      rs = (i64)rowptr[v];
+      deg = (i64)rowptr[v + 1] - rs;
+      classify(deg, a.fanout, a.replace, &n_out, &n16, &n32, &n64);
+      if (n32 == 0 && n64 == 0) {
+        f.d[0] = f.d[1] = f.d[2] = f.d[3] = (u32)n16;
+      } else {
+#pragma unroll
+        for (int p = 0; p < 4; ++p) f.d[p] = (u32)(rng_node_end(p, n16, n32, n64) - p);
+      }
+    }
+    u32 ex_v, tot_v; Func4 ex_f, tot_f;
+    block_scan_pair((u32)n_out, f, &ex_v, &ex_f, &tot_v, &tot_f);
+    if (i < F) {
+      NodeRec r;
+      r.rs = rs; r.deg = (u32)deg; r.loc_off = ex_v;
+      r.pf[0] = ex_f.d[0]; r.pf[1] = ex_f.d[1]; r.pf[2] = ex_f.d[2]; r.pf[3] = ex_f.d[3];
+      a.rec[i] = r;
+    }
+    if (threadIdx.x == 0) {
+      a.tile_out[tile] = tot_v;
+#pragma unroll
+      for (int p = 0; p < 4; ++p) a.tile_func[4 * tile + p] = tot_f.d[p];
+    }
+  }
+  if (last_block(&a.st[ST_TICKET_A])) {
+    if (threadIdx.x == 0) a.st[ST_PASS_F] = F;
+    scan_frontier_tiles(a, ntiles);
+    mt_extend_block<3>(a.raw, a.st, a.next0, a.raw_cap, s_win);
+  }
+}
+
+// One group of G lanes per frontier node.
+template <typename idx_t, int G>
+__global__ void __launch_bounds__(NT) k_sample(const PassArgs a) {
+  const i64 F = a.st[ST_PASS_F];
+  const i64 begin = a.st[a.o_src_begin];
+  const i64 pbase = a.st[ST_PASS_BASE];
+  const i64 out0 = a.next0;
+  const idx_t* __restrict__ col = (const idx_t*)a.col;
+  const u32* __restrict__ raw = a.raw;
+  const int gl = threadIdx.x & (G - 1);
+  const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) & ~(G - 1)));
+  const i64 groups_per_grid = (i64)gridDim.x * (NT / G);
+  for (i64 i = (i64)blockIdx.x * (NT / G) + threadIdx.x / G; i < F; i += groups_per_grid) {
+    const NodeRec r = a.rec[i];
+    const i64 tile = i / NT;
+    const i64 tpos = a.tile_pos[tile];
+    const i64 off = a.tile_off[tile] + r.loc_off;    // pass-local flat position of the node's first edge
+    const i64 pos0 = tpos + r.pf[tpos & 3];           // RNG position (16-bit units) of its first draw
+    const i64 deg = r.deg, rs = r.rs, k = a.fanout;
+    const i64 src_pos = begin + i;                    // == local id of the source node (neighbor_kernel.cpp:453)
+    const i64 sbatch = a.disjoint ? a.src_batch[src_pos] : 0;
+    i64 n_out, n16, n32, n64;
+    const int mode = classify(deg, k, a.replace, &n_out, &n16, &n32, &n64);
+    auto emit = [&](i64 j, i64 e) {
+      const i64 p = off + j;
+      const i64 d = (i64)col[e];
+      a.row[pbase + p] = src_pos;
+      a.eid[pbase + p] = e;
+      a.colv[pbase + p] = d;  // global id for now; k_lookup overwrites it with the local id
+      const u32 s = table_insert(a.keys, a.mask, make_key(d, sbatch, a.disjoint));
+      atomicMin(&a.vals[s], POS_BASE + (u64)p);
+      a.eslot[p] = s;
+    };
+    if (mode == MODE_FULL) {
+      for (i64 j = gl; j < deg; j += G) emit(j, rs + j);
+    } else if (mode == MODE_REPLACE) {
+      const int wu = rng_width_units((u64)deg);
+      for (i64 j = gl; j < k; j += G) {
+        const i64 pos = (wu == 1) ? pos0 + j : rng_align(rng_run(pos0, wu, j), wu);
+        emit(j, rs + (i64)rng_draw(raw, out0, pos, wu, (u64)deg));
+      }
+    } else if (mode == MODE_FLOYD) {
+      const i64 lo = deg - k;  // draw j: range lo+1+j, fallback value lo+j (neighbor_kernel.cpp:231-241)
+      for (i64 c0 = 0; c0 < k; c0 += G) {
+        const i64 j = c0 + gl;
+        const bool act = j < k;
+        i64 rnd = -1, c = -1;
+        if (act) {
+          int wu;
+          const i64 pos = (n32 == 0 && n64 == 0) ? (wu = 1, pos0 + j) : rng_draw_start(pos0, n16, n32, j, &wu);
+          rnd = (i64)rng_draw(raw, out0, pos, wu, (u64)(lo + 1 + j));
+          c = rnd;
+          // already chosen in an earlier chunk of this node? (only when fanout > G == 32)
+          for (i64 t = 0; t < c0; ++t)
+            if (__ldcg(&a.eid[pbase + off + t]) - rs == rnd) { c = lo + j; break; }
+        }
+        const int lim = (int)((k - c0) < G ? (k - c0) : G);
+        for (int jj = 0; jj < lim; ++jj) {
+          const i64 cj = __shfl_sync(gmask, c, jj, G);
+          if (act && gl > jj && rnd == cj) c = lo + j;
+        }
+        if (act) emit(j, rs + c);
+        if (c0 + G < k) __syncwarp(gmask);
+      }
+    }
+  }
+}
+
+// seeds: list them, insert them (first-occurrence order == seed order)
+template <typename idx_t>
+__global__ void __launch_bounds__(NT) k_seed(const PassArgs a, const idx_t* __restrict__ seeds, i64 n, i64 batch0) {
+  for (i64 i = (i64)blockIdx.x * NT + threadIdx.x; i < n; i += (i64)gridDim.x * NT) {
+    const i64 v = (i64)seeds[i];
+    a.dst_nodes[i] = v;
+    if (a.disjoint) a.dst_batch[i] = batch0 + i;
+    const u32 s = table_insert(a.keys, a.mask, make_key(v, batch0 + i, a.disjoint));
+    atomicMin(&a.vals[s], POS_BASE + (u64)i);
+    a.eslot[i] = s;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    a.st[ST_PASS_E] = n;
+    a.st[ST_PASS_BASE] = 0;
+  }
+}
+
+// first occurrences of the running pass + tile-local ranks; last block scans the tile counts and
+// updates the dst type's counters.
+__global__ void __launch_bounds__(NT) k_mark(const PassArgs a) {
+  __shared__ u32 s_w[NT / 32];
+  const i64 E = a.st[ST_PASS_E];
+  const i64 ntiles = ceil_div(E, ETILE);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (i64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const i64 p0 = tile * ETILE + threadIdx.x * 4;
+    u32 fl[4]; u32 cnt = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const i64 p = p0 + q;
+      fl[q] = 0;
+      if (p < E) fl[q] = (a.vals[a.eslot[p]] == POS_BASE + (u64)p) ? 1u : 0u;
+      cnt += fl[q];
+    }
+    u32 inc = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const u32 o = __shfl_up_sync(0xffffffffu, inc, d);
+      if (lane >= d) inc += o;
+    }
+    if (lane == 31) s_w[wid] = inc;
+    __syncthreads();
+    u32 pre = 0, tot = 0;
+    for (int w = 0; w < NT / 32; ++w) { if (w < wid) pre += s_w[w]; tot += s_w[w]; }
+    u32 ex = pre + inc - cnt;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const i64 p = p0 + q;
+      if (p < E) a.erank[p] = fl[q] ? (0x80000000u | ex) : 0u;
+      ex += fl[q];
+    }
+    if (threadIdx.x == 0) a.mtile[tile] = tot;
+    __syncthreads();
+  }
+  if (last_block(&a.st[ST_TICKET_B])) {
+    // ordered exclusive scan of tile counts by one block
+    __shared__ i64 s_s[NT / 32];
+    __shared__ i64 carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (i64 base = 0; base < ntiles; base += NT) {
+      const i64 t = base + threadIdx.x;
+      const i64 v = t < ntiles ? __ldcg(&a.mtile[t]) : 0;
+      i64 inc = v;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const i64 o = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += o;
+      }
+      if (lane == 31) s_s[wid] = inc;
+      __syncthreads();
+      i64 pre = 0, tot = 0;
+      for (int w = 0; w < NT / 32; ++w) { if (w < wid) pre += s_s[w]; tot += s_s[w]; }
+      const i64 c0 = carry;
+      if (t < ntiles) a.mtile[t] = c0 + pre + inc - v;
+      __syncthreads();
+      if (threadIdx.x == 0) carry = c0 + tot;
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+      const i64 nnew = carry;
+      a.st[ST_PASS_NEW] = nnew;
+      if (a.seed_mode) {
+        a.st[ST_LIST_BASE] = 0;
+        a.st[ST_IDS_BASE] = 0;
+        a.st[a.o_dst_list] = E;      // every seed is listed, duplicates included (neighbor_kernel.cpp:410)
+        a.st[a.o_dst_ids] = nnew;    // ... but ids only count distinct ones (mapper.h:29-46)
+      } else {
+        a.st[ST_LIST_BASE] = a.st[a.o_dst_list];
+        a.st[ST_IDS_BASE] = a.st[a.o_dst_ids];
+        a.st[a.o_dst_list] += nnew;
+        a.st[a.o_dst_ids] += nnew;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(NT) k_assign(const PassArgs a) {
+  const i64 E = a.st[ST_PASS_E];
+  const i64 pbase = a.st[ST_PASS_BASE];
+  const i64 list_base = a.st[ST_LIST_BASE], ids_base = a.st[ST_IDS_BASE];
+  for (i64 p = (i64)blockIdx.x * NT + threadIdx.x; p < E; p += (i64)gridDim.x * NT) {
+    const u32 er = a.erank[p];
+    if (a.seed_mode) {
+      if (er & 0x80000000u) {
+        const i64 rank = a.mtile[p / ETILE] + (er & 0x7fffffffu);
+        a.vals[a.eslot[p]] = (u64)rank;
+        a.dst_slot[p] = a.eslot[p];
+      } else {
+        a.dst_slot[p] = NO_SLOT;
+      }
+    } else if (er & 0x80000000u) {
+      const i64 rank = a.mtile[p / ETILE] + (er & 0x7fffffffu);
+      const u32 s = a.eslot[p];
+      a.vals[s] = (u64)(ids_base + rank);
+      a.dst_nodes[list_base + rank] = a.colv[pbase + p];
+      if (a.disjoint) a.dst_batch[list_base + rank] = a.src_batch[a.row[pbase + p]];
+      a.dst_slot[list_base + rank] = s;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(NT) k_lookup(const PassArgs a) {
+  const i64 E = a.st[ST_PASS_E];
+  const i64 pbase = a.st[ST_PASS_BASE];
+  for (i64 p = (i64)blockIdx.x * NT + threadIdx.x; p < E; p += (i64)gridDim.x * NT)
+    a.colv[pbase + p] = (i64)a.vals[a.eslot[p]];
+}
+
+// end of hop: advance every type's frontier slice and record nodes-per-hop (neighbor_kernel.cpp:807-812)
+__global__ void k_hop_end(i64* st, int T, int L, int hop, int o_list, int o_begin, int o_end, int o_nph) {
+  const int t = threadIdx.x;
+  if (t < T) {
+    const i64 n = st[o_list + t], e = st[o_end + t];
+    st[o_nph + t * (L + 1) + hop + 1] = n - e;
+    st[o_begin + t] = e;
+    st[o_end + t] = n;
+  }
+}
+
+__global__ void k_seed_end(i64* st, int t, int L, int o_list, int o_begin, int o_end, int o_nph) {
+  st[o_begin + t] = 0;
+  st[o_end + t] = st[o_list + t];
+  st[o_nph + t * (L + 1)] = st[o_list + t];
+}
+
+// final engine state: generation holding the last consumed output (see mt19937.cuh)
+__global__ void k_finalize(i64* st, const u32* __restrict__ raw, i64 next0, int o_mt) {
+  const i64 blocks = rng_blocks_for_units(st[ST_CURSOR]);
+  const i64 q = next0 + 256 * blocks;
+  const i64 g = (q - 1) / MT_N;
+  u32* out = reinterpret_cast<u32*>(st + o_mt);
+  for (int i = threadIdx.x; i < MT_N; i += blockDim.x) out[i] = raw[g * MT_N + i];
+  if (threadIdx.x == 0) {
+    const i64 nxt = q - g * MT_N;
+    st[ST_MT_NEXT] = nxt;
+    st[ST_MT_LEFT] = 625 - nxt;
+    st[ST_BLOCKS] = blocks;
+  }
+}
+
+__global__ void __launch_bounds__(NT) k_cleanup(u64* keys, u64* vals, const u32* __restrict__ slots, const i64* n_ptr) {
+  const i64 n = *n_ptr;
+  for (i64 i = (i64)blockIdx.x * NT + threadIdx.x; i < n; i += (i64)gridDim.x * NT) {
+    const u32 s = slots[i];
+    if (s != NO_SLOT) { keys[s] = EMPTY; vals[s] = EMPTY; }
+  }
+}
+
+// table growth (only the synced path): move every listed node's entry into the new table
+__global__ void __launch_bounds__(NT) k_rehash(const u64* __restrict__ old_keys, const u64* __restrict__ old_vals,
+                                               u64* new_keys, u64* new_vals, u64 new_mask, u32* slots, i64 n) {
+  for (i64 i = (i64)blockIdx.x * NT + threadIdx.x; i < n; i += (i64)gridDim.x * NT) {
+    const u32 s = slots[i];
+    if (s == NO_SLOT) continue;
+    const u32 ns = table_insert(new_keys, new_mask, old_keys[s]);
+    new_vals[ns] = old_vals[s];
+    slots[i] = ns;
+  }
+}
+
+template <typename out_t>
+__global__ void __launch_bounds__(NT) k_export(const i64* __restrict__ src, out_t* __restrict__ dst, i64 n) {
+  for (i64 i = (i64)blockIdx.x * NT + threadIdx.x; i < n; i += (i64)gridDim.x * NT) dst[i] = (out_t)src[i];
+}
+template <typename out_t>
+__global__ void __launch_bounds__(NT) k_export_pairs(const i64* __restrict__ batch, const i64* __restrict__ node,
+                                                      out_t* __restrict__ dst, i64 n) {
+  for (i64 i = (i64)blockIdx.x * NT + threadIdx.x; i < n; i += (i64)gridDim.x * NT) {
+    dst[2 * i] = (out_t)batch[i];
+    dst[2 * i + 1] = (out_t)node[i];
+  }
+}
+
+inline int grid_for(i64 work_items, int per_block, int sm_count) {
+  i64 b = ceil_div(work_items > 0 ? work_items : 1, per_block);
+  const i64 cap = (i64)sm_count * 8;
+  return (int)(b < cap ? b : cap);
+}
+
+inline i64 sat_mul(i64 a, i64 b) {
+  if (a == 0 || b == 0) return 0;
+  const i64 LIM = (i64)1 << 60;
+  if (a > LIM / b) return LIM;
+  return a * b;
+}
+inline i64 sat_add(i64 a, i64 b) {
+  const i64 LIM = (i64)1 << 60;
+  return (a + b > LIM) ? LIM : a + b;
+}
+inline u64 pow2_ge(u64 x) { u64 p = 1024; while (p < x) p <<= 1; return p; }
+
+}  // namespace
+}  // namespace pygb200
+
+using namespace pygb200;
+
+// ------------------------------------------------------------------------------------- handle
+struct pygb200_sampler {
+  int device = -1;
+  int sm_count = 148;
+  struct TypeBuf {
+    DevBuf nodes, batch, slot, keys, vals;
+    u64 tcap = 0;       // table capacity (slots, power of two); table is all-EMPTY between runs
+    i64 n_nodes = 0;    // result of the last run
+  };
+  struct RelBuf { DevBuf row, colv, eid; i64 n_edges = 0; };
+  std::vector<TypeBuf> types;
+  std::vector<RelBuf> rels;
+  DevBuf eslot, erank, rec, tile_out, tile_func, tile_off, tile_pos, mtile, raw, st;
+  i64* st_host = nullptr;   // pinned mirror of the state buffer
+  size_t st_words = 0;
+  bool disjoint = false;
+  bool dirty = false;       // a run failed mid-way: tables must be wiped before reuse
+  int T = 0, R = 0, L = 0;
+  std::mutex mu;
+};
+
+extern "C" const char* pygb200_last_error(void) { return g_err.c_str(); }
+extern "C" int pygb200_cuda_version(void) { return CUDART_VERSION; }
+extern "C" int pygb200_kernel_launches(void) { return g_launches.load(); }
+
+extern "C" int pygb200_sampler_create(pygb200_sampler** out) {
+  PYGB_CHECK(out != nullptr, PYGB200_ERR_ARG, "pygb200_sampler_create: null out");
+  int dev = 0;
+  PYGB_CUDA(cudaGetDevice(&dev));
+  auto* s = new pygb200_sampler();
+  s->device = dev;
+  cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, dev);
+  *out = s;
+  return PYGB200_OK;
+}
+
+extern "C" void pygb200_sampler_destroy(pygb200_sampler* s) {
+  if (!s) return;
+  for (auto& t : s->types) { t.nodes.release(); t.batch.release(); t.slot.release(); t.keys.release(); t.vals.release(); }
+  for (auto& r : s->rels) { r.row.release(); r.colv.release(); r.eid.release(); }
+  DevBuf* all[] = {&s->eslot, &s->erank, &s->rec, &s->tile_out, &s->tile_func,
+                   &s->tile_off, &s->tile_pos, &s->mtile, &s->raw, &s->st};
+  for (auto* b : all) b->release();
+  if (s->st_host) cudaFreeHost(s->st_host);
+  delete s;
+}
+
+namespace {
+
+struct Layout { int o_list, o_ids, o_begin, o_end, o_rel, o_nph, o_eph, o_mt; size_t words; };
+Layout make_layout(int T, int R, int L) {
+  Layout l;
+  int o = ST_HDR;
+  l.o_list = o; o += T; l.o_ids = o; o += T; l.o_begin = o; o += T; l.o_end = o; o += T;
+  l.o_rel = o; o += R; l.o_nph = o; o += T * (L + 1); l.o_eph = o; o += R * (L > 0 ? L : 1);
+  l.o_mt = o; o += MT_N / 2;
+  l.words = (size_t)o;
+  return l;
+}
+
+// node list / slot list / batch list of one type: capacity for `need` entries, keeping `keep`
+int ensure_type(pygb200_sampler* s, int t, i64 need, i64 keep, bool disjoint, cudaStream_t st) {
+  auto& tb = s->types[t];
+  if (int e = tb.nodes.ensure((size_t)need * 8, (size_t)keep * 8, st)) return e;
+  if (int e = tb.slot.ensure((size_t)need * 4, (size_t)keep * 4, st)) return e;
+  if (disjoint) if (int e = tb.batch.ensure((size_t)need * 8, (size_t)keep * 8, st)) return e;
+  return PYGB200_OK;
+}
+
+// hash table of one type: room for `need_nodes` distinct keys at load factor <= 0.5.
+// `listed` = entries currently in the table (0 between runs) -> rehash when it has to grow.
+int ensure_table(pygb200_sampler* s, int t, i64 need_nodes, i64 listed, cudaStream_t st) {
+  auto& tb = s->types[t];
+  const u64 cap = pow2_ge(2 * (u64)(need_nodes > 0 ? need_nodes : 1));
+  if (cap <= tb.tcap) return PYGB200_OK;
+  PYGB_CHECK(cap <= (1ull << 32), PYGB200_ERR_UNSUPPORTED, "sampler hash table would exceed 2^32 slots");
+  if (listed == 0) {
+    if (int e = tb.keys.ensure(cap * 8, 0, st)) return e;
+    if (int e = tb.vals.ensure(cap * 8, 0, st)) return e;
+    PYGB_CUDA(cudaMemsetAsync(tb.keys.p, 0xff, cap * 8, st));
+    PYGB_CUDA(cudaMemsetAsync(tb.vals.p, 0xff, cap * 8, st));
+  } else {
+    DevBuf nk, nv;
+    if (int e = nk.ensure(cap * 8, 0, st)) return e;
+    if (int e = nv.ensure(cap * 8, 0, st)) return e;
+    PYGB_CUDA(cudaMemsetAsync(nk.p, 0xff, nk.cap, st));
+    PYGB_CUDA(cudaMemsetAsync(nv.p, 0xff, nv.cap, st));
+    k_rehash<<<grid_for(listed, NT, s->sm_count), NT, 0, st>>>(tb.keys.as<u64>(), tb.vals.as<u64>(), nk.as<u64>(),
+                                                              nv.as<u64>(), cap - 1, tb.slot.as<u32>(), listed);
+    PYGB_LAUNCH_CHECK();
+    PYGB_CUDA(cudaStreamSynchronize(st));
+    tb.keys.release(); tb.vals.release();
+    tb.keys = nk; tb.vals = nv;
+  }
+  tb.tcap = cap;
+  return PYGB200_OK;
+}
+
+int ensure_rel(pygb200_sampler* s, int r, i64 need, i64 keep, cudaStream_t st) {
+  auto& rb = s->rels[r];
+  if (int e = rb.row.ensure((size_t)need * 8, (size_t)keep * 8, st)) return e;
+  if (int e = rb.colv.ensure((size_t)need * 8, (size_t)keep * 8, st)) return e;
+  if (int e = rb.eid.ensure((size_t)need * 8, (size_t)keep * 8, st)) return e;
+  return PYGB200_OK;
+}
+
+int ensure_frontier_scratch(pygb200_sampler* s, i64 F, cudaStream_t st) {
+  const i64 tiles = ceil_div(F > 0 ? F : 1, NT);
+  if (int e = s->rec.ensure((size_t)(F > 0 ? F : 1) * sizeof(NodeRec), 0, st)) return e;
+  if (int e = s->tile_out.ensure((size_t)tiles * 8, 0, st)) return e;
+  if (int e = s->tile_func.ensure((size_t)tiles * 16, 0, st)) return e;
+  if (int e = s->tile_off.ensure((size_t)tiles * 8, 0, st)) return e;
+  if (int e = s->tile_pos.ensure((size_t)tiles * 8, 0, st)) return e;
+  return PYGB200_OK;
+}
+int ensure_edge_scratch(pygb200_sampler* s, i64 E, cudaStream_t st) {
+  const i64 e_ = E > 0 ? E : 1;
+  if (int e = s->eslot.ensure((size_t)e_ * 4, 0, st)) return e;
+  if (int e = s->erank.ensure((size_t)e_ * 4, 0, st)) return e;
+  if (int e = s->mtile.ensure((size_t)ceil_div(e_, ETILE) * 8, 0, st)) return e;
+  return PYGB200_OK;
+}
+
+template <typename idx_t>
+int launch_count(pygb200_sampler* s, const PassArgs& a, i64 F, cudaStream_t st) {
+  k_count<idx_t><<<grid_for(F, NT, s->sm_count), NT, 0, st>>>(a);
+  PYGB_LAUNCH_CHECK();
+  return PYGB200_OK;
+}
+
+template <typename idx_t>
+int launch_rest(pygb200_sampler* s, const PassArgs& a, i64 F, i64 E, cudaStream_t st) {
+  const i64 k = a.fanout;
+  const int G = (k < 0 || k > 16) ? 32 : (k > 8 ? 16 : (k > 4 ? 8 : 4));
+  const int gs = grid_for(F, NT / G, s->sm_count);
+  switch (G) {
+    case 4: k_sample<idx_t, 4><<<gs, NT, 0, st>>>(a); break;
+    case 8: k_sample<idx_t, 8><<<gs, NT, 0, st>>>(a); break;
+    case 16: k_sample<idx_t, 16><<<gs, NT, 0, st>>>(a); break;
+    default: k_sample<idx_t, 32><<<gs, NT, 0, st>>>(a); break;
+  }
+  PYGB_LAUNCH_CHECK();
+  k_mark<<<grid_for(E, ETILE, s->sm_count), NT, 0, st>>>(a);
+  PYGB_LAUNCH_CHECK();
+  k_assign<<<grid_for(E, NT, s->sm_count), NT, 0, st>>>(a);
+  PYGB_LAUNCH_CHECK();
+  k_lookup<<<grid_for(E, NT, s->sm_count), NT, 0, st>>>(a);
+  PYGB_LAUNCH_CHECK();
+  return PYGB200_OK;
+}
+
+int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const pygb200_relation* rels,
+                     const void* const* seeds, const int64_t* n_seeds, const int64_t* num_neighbors,
+                     unsigned flags, pygb200_mt19937* mt, int64_t* nodes_per_hop, int64_t* edges_per_hop,
+                     int64_t* n_nodes_out, int64_t* n_edges_out, cudaStream_t st) {
+  const bool replace = flags & PYGB200_S_REPLACE, disjoint = flags & PYGB200_S_DISJOINT, idx32 = flags & PYGB200_S_INDEX32;
+  i64 total_seeds = 0;
+  for (int t = 0; t < T; ++t) {
+    PYGB_CHECK(n_seeds[t] >= 0, PYGB200_ERR_ARG, "negative seed count");
+    PYGB_CHECK(n_seeds[t] == 0 || seeds[t] != nullptr, PYGB200_ERR_ARG, "null seed pointer");
+    total_seeds += n_seeds[t];
+  }
+  for (int r = 0; r < R; ++r) {
+    PYGB_CHECK(rels[r].src_type >= 0 && rels[r].src_type < T && rels[r].dst_type >= 0 && rels[r].dst_type < T,
+               PYGB200_ERR_ARG, "relation endpoint out of range");
+    PYGB_CHECK(rels[r].num_edges >= 0 && rels[r].num_edges < ((i64)1 << 40), PYGB200_ERR_UNSUPPORTED,
+               "relations with >= 2^40 edges are not supported");
+    PYGB_CHECK(rels[r].rowptr != nullptr && (rels[r].col != nullptr || rels[r].num_edges == 0), PYGB200_ERR_ARG,
+               "null CSR pointer");
+  }
+  if (disjoint) PYGB_CHECK(total_seeds < ((i64)1 << 23), PYGB200_ERR_UNSUPPORTED,
+                           "disjoint sampling supports < 2^23 seeds and node ids < 2^40 on this path");
+  const i64 next0 = mt_next0(mt->left);
+  PYGB_CHECK(mt->left >= 1 && mt->left <= MT_N && mt->next >= 0 && mt->next <= MT_N, PYGB200_ERR_ARG,
+             "invalid mt19937 state");
+
+  // ---- static worst-case bounds: frontier per (type, hop), edges per (relation, hop)
+  const int Lz = L > 0 ? L : 1;
+  std::vector<i64> fb((size_t)T * (L + 1), 0), eb((size_t)R * Lz, 0);
+  for (int t = 0; t < T; ++t) fb[(size_t)t * (L + 1)] = n_seeds[t];
+  bool synced = false;  // true: sync after every count kernel and size buffers from actual numbers
+  for (int h = 0; h < L; ++h)
+    for (int r = 0; r < R; ++r) {
+      const i64 k = num_neighbors[(size_t)r * L + h];
+      const i64 F = fb[(size_t)rels[r].src_type * (L + 1) + h];
+      if (k < 0) synced = true;
+      const i64 e = k >= 0 ? sat_mul(F, k) : 0;
+      eb[(size_t)r * L + h] = e;
+      i64& nf = fb[(size_t)rels[r].dst_type * (L + 1) + h + 1];
+      nf = sat_add(nf, e);
+    }
+  std::vector<i64> node_cap(T, 0), rel_cap(R, 0);
+  i64 max_F = 1, max_E = std::max<i64>(total_seeds, 1), draw_units = 0, total_elems = 0;
+  for (int t = 0; t < T; ++t) {
+    i64 c = 0;
+    for (int h = 0; h <= L; ++h) { c = sat_add(c, fb[(size_t)t * (L + 1) + h]); max_F = std::max(max_F, fb[(size_t)t * (L + 1) + h]); }
+    node_cap[t] = std::max<i64>(c, 1);
+    total_elems = sat_add(total_elems, c);
+  }
+  for (int r = 0; r < R; ++r) {
+    i64 c = 0;
+    for (int h = 0; h < L; ++h) {
+      const i64 e = eb[(size_t)r * L + h];
+      c = sat_add(c, e); max_E = std::max(max_E, e);
+      // units per draw: 1 when every range < 2^16, else at most 2 + 1 skipped (32-bit) / 4 + 3 (64-bit)
+      draw_units = sat_add(draw_units, sat_mul(e, rels[r].num_edges < 65536 ? 1 : (rels[r].num_edges < ((i64)1 << 32) ? 3 : 7)));
+    }
+    rel_cap[r] = std::max<i64>(c, 1);
+    total_elems = sat_add(total_elems, sat_mul(c, 3));
+  }
+  if (total_elems > ((i64)1 << 30)) synced = true;  // > 8 GiB of worst-case int64 results: size from actuals
+
+  // ---- workspace
+  if ((int)s->types.size() < T) s->types.resize(T);
+  if ((int)s->rels.size() < R) s->rels.resize(R);
+  s->T = T; s->R = R; s->L = L; s->disjoint = disjoint;
+  const Layout lay = make_layout(T, R, L);
+  if (lay.words > s->st_words) {
+    if (s->st_host) cudaFreeHost(s->st_host);
+    s->st_host = nullptr; s->st_words = 0;
+    PYGB_CUDA(cudaHostAlloc((void**)&s->st_host, lay.words * 8, cudaHostAllocDefault));
+    s->st_words = lay.words;
+  }
+  if (int e = s->st.ensure(lay.words * 8, 0, st)) return e;
+  if (s->dirty) {  // previous run aborted: wipe tables
+    for (auto& tb : s->types) if (tb.tcap) {
+      PYGB_CUDA(cudaMemsetAsync(tb.keys.p, 0xff, tb.tcap * 8, st));
+      PYGB_CUDA(cudaMemsetAsync(tb.vals.p, 0xff, tb.tcap * 8, st));
+    }
+    s->dirty = false;
+  }
+  s->dirty = true;
+  i64 raw_cap;
+  if (!synced) {
+    for (int t = 0; t < T; ++t) {
+      if (int e = ensure_type(s, t, node_cap[t], 0, disjoint, st)) return e;
+      if (int e = ensure_table(s, t, node_cap[t], 0, st)) return e;
+    }
+    for (int r = 0; r < R; ++r) if (int e = ensure_rel(s, r, rel_cap[r], 0, st)) return e;
+    if (int e = ensure_frontier_scratch(s, max_F, st)) return e;
+    if (int e = ensure_edge_scratch(s, max_E, st)) return e;
+    raw_cap = next0 + 256 * (rng_blocks_for_units(draw_units) + 1) + 2 * MT_N;
+  } else {
+    for (int t = 0; t < T; ++t) {
+      if (int e = ensure_type(s, t, std::max<i64>(n_seeds[t], 1), 0, disjoint, st)) return e;
+      if (int e = ensure_table(s, t, std::max<i64>(n_seeds[t], 1), 0, st)) return e;
+    }
+    for (int r = 0; r < R; ++r) if (int e = ensure_rel(s, r, 1, 0, st)) return e;
+    if (int e = ensure_edge_scratch(s, total_seeds, st)) return e;
+    raw_cap = next0 + 256 * 2 + 2 * MT_N;
+  }
+  if (int e = s->raw.ensure((size_t)raw_cap * 4, 0, st)) return e;
+
+  // ---- init: zero state, upload the engine state
+  i64* dst = s->st.as<i64>();
+  PYGB_CUDA(cudaMemsetAsync(dst, 0, lay.words * 8, st));
+  {
+    MTPodParam pod;
+    memcpy(pod.state, mt->state, sizeof(pod.state));
+    k_mt_init<<<1, NT, 0, st>>>(s->raw.as<u32>(), dst + ST_GEN, pod);
+    PYGB_LAUNCH_CHECK();
+  }
+  auto make_args = [&](int src_t, int dst_t, int rel) {
+    PassArgs a;
+    memset(&a, 0, sizeof(a));
+    auto& td = s->types[dst_t];
+    a.dst_nodes = td.nodes.as<i64>(); a.dst_batch = td.batch.as<i64>(); a.dst_slot = td.slot.as<u32>();
+    a.keys = td.keys.as<u64>(); a.vals = td.vals.as<u64>(); a.mask = td.tcap - 1;
+    if (src_t >= 0) { a.src_nodes = s->types[src_t].nodes.as<i64>(); a.src_batch = s->types[src_t].batch.as<i64>(); }
+    if (rel >= 0) {
+      a.rowptr = rels[rel].rowptr; a.col = rels[rel].col;
+      a.row = s->rels[rel].row.as<i64>(); a.colv = s->rels[rel].colv.as<i64>(); a.eid = s->rels[rel].eid.as<i64>();
+      a.o_rel_edges = lay.o_rel + rel;
+    }
+    a.eslot = s->eslot.as<u32>(); a.erank = s->erank.as<u32>(); a.rec = s->rec.as<NodeRec>();
+    a.tile_out = s->tile_out.as<i64>(); a.tile_func = s->tile_func.as<u32>();
+    a.tile_off = s->tile_off.as<i64>(); a.tile_pos = s->tile_pos.as<i64>(); a.mtile = s->mtile.as<i64>();
+    a.st = dst;
+    a.o_src_begin = lay.o_begin + (src_t >= 0 ? src_t : 0); a.o_src_end = lay.o_end + (src_t >= 0 ? src_t : 0);
+    a.o_dst_list = lay.o_list + dst_t; a.o_dst_ids = lay.o_ids + dst_t;
+    a.raw = s->raw.as<u32>(); a.next0 = next0; a.raw_cap = raw_cap;
+    a.replace = replace; a.disjoint = disjoint;
+    return a;
+  };
+  auto read_state = [&]() -> int {
+    PYGB_CUDA(cudaMemcpyAsync(s->st_host, dst, lay.words * 8, cudaMemcpyDeviceToHost, st));
+    PYGB_CUDA(cudaStreamSynchronize(st));
+    return PYGB200_OK;
+  };
+
+  // ---- seeds (neighbor_kernel.cpp:409-416, :669-704)
+  i64 batch0 = 0;
+  for (int t = 0; t < T; ++t) {
+    if (n_seeds[t] > 0) {
+      PassArgs a = make_args(-1, t, -1);
+      a.seed_mode = 1;
+      const int g = grid_for(n_seeds[t], NT, s->sm_count);
+      if (idx32) k_seed<int32_t><<<g, NT, 0, st>>>(a, (const int32_t*)seeds[t], n_seeds[t], batch0);
+      else k_seed<int64_t><<<g, NT, 0, st>>>(a, (const int64_t*)seeds[t], n_seeds[t], batch0);
+      PYGB_LAUNCH_CHECK();
+      k_mark<<<grid_for(n_seeds[t], ETILE, s->sm_count), NT, 0, st>>>(a);
+      PYGB_LAUNCH_CHECK();
+      k_assign<<<g, NT, 0, st>>>(a);
+      PYGB_LAUNCH_CHECK();
+      if (disjoint) batch0 += n_seeds[t];
+    }
+    k_seed_end<<<1, 1, 0, st>>>(dst, t, L, lay.o_list, lay.o_begin, lay.o_end, lay.o_nph);
+    PYGB_LAUNCH_CHECK();
+  }
+
+  // ---- hops
+  for (int h = 0; h < L; ++h) {
+    if (synced) if (int e = read_state()) return e;  // actual frontier slices of this hop
+    for (int r = 0; r < R; ++r) {
+      const i64 k = num_neighbors[(size_t)r * L + h];
+      const int src_t = rels[r].src_type, dst_t = rels[r].dst_type;
+      if (k == 0) continue;  // nothing emitted, no RNG consumed (neighbor_kernel.cpp:67-68)
+      if (!synced) {
+        const i64 Fb = fb[(size_t)src_t * (L + 1) + h], Eb = eb[(size_t)r * L + h];
+        if (Fb == 0 || Eb == 0) continue;
+        PassArgs a = make_args(src_t, dst_t, r);
+        a.fanout = k;
+        a.o_eph = lay.o_eph + r * L + h;
+        if (int e = idx32 ? launch_count<int32_t>(s, a, Fb, st) : launch_count<int64_t>(s, a, Fb, st)) return e;
+        if (int e = idx32 ? launch_rest<int32_t>(s, a, Fb, Eb, st) : launch_rest<int64_t>(s, a, Fb, Eb, st)) return e;
+      } else {
+        const i64 F = s->st_host[lay.o_end + src_t] - s->st_host[lay.o_begin + src_t];
+        if (F == 0) continue;
+        if (int e = ensure_frontier_scratch(s, F, st)) return e;
+        if (k > 0) {  // draws possible: make sure the raw stream buffer can hold this pass
+          const i64 upu = rels[r].num_edges < 65536 ? 1 : (rels[r].num_edges < ((i64)1 << 32) ? 3 : 7);
+          if (int e = read_state()) return e;
+          const i64 need = next0 + 256 * (rng_blocks_for_units(s->st_host[ST_CURSOR] + sat_mul(sat_mul(F, k), upu)) + 1) + 2 * MT_N;
+          if (need > raw_cap) {
+            if (int e = s->raw.ensure((size_t)need * 4, (size_t)s->st_host[ST_GEN] * 4, st)) return e;
+            raw_cap = need;
+          }
+        }
+        PassArgs a = make_args(src_t, dst_t, r);
+        a.fanout = k;
+        a.o_eph = lay.o_eph + r * L + h;
+        if (int e = idx32 ? launch_count<int32_t>(s, a, F, st) : launch_count<int64_t>(s, a, F, st)) return e;
+        if (int e = read_state()) return e;
+        const i64 E = s->st_host[ST_PASS_E];
+        if (E == 0) continue;
+        const i64 rel_before = s->st_host[ST_PASS_BASE], list_now = s->st_host[lay.o_list + dst_t];
+        if (int e = ensure_rel(s, r, rel_before + E, rel_before, st)) return e;
+        if (int e = ensure_edge_scratch(s, E, st)) return e;
+        if (int e = ensure_type(s, dst_t, list_now + E, list_now, disjoint, st)) return e;
+        if (int e = ensure_table(s, dst_t, list_now + E, list_now, st)) return e;
+        a = make_args(src_t, dst_t, r);  // pointers may have moved
+        a.fanout = k;
+        a.o_eph = lay.o_eph + r * L + h;
+        if (int e = idx32 ? launch_rest<int32_t>(s, a, F, E, st) : launch_rest<int64_t>(s, a, F, E, st)) return e;
+      }
+    }
+    k_hop_end<<<1, 1024, 0, st>>>(dst, T, L, h, lay.o_list, lay.o_begin, lay.o_end, lay.o_nph);
+    PYGB_LAUNCH_CHECK();
+  }
+
+  // ---- final engine state (at least one 128-word block is always consumed), counts to the host
+  k_mt_extend<3><<<1, 640, 0, st>>>(s->raw.as<u32>(), dst + ST_GEN, dst + ST_CURSOR, next0, raw_cap,
+                                    reinterpret_cast<int*>(dst + ST_ERROR));
+  PYGB_LAUNCH_CHECK();
+  k_finalize<<<1, NT, 0, st>>>(dst, s->raw.as<u32>(), next0, lay.o_mt);
+  PYGB_LAUNCH_CHECK();
+  PYGB_CUDA(cudaMemcpyAsync(s->st_host, dst, lay.words * 8, cudaMemcpyDeviceToHost, st));
+  // table cleanup is stream-ordered after the copy; the host does not wait for it
+  cudaEvent_t copied;
+  PYGB_CUDA(cudaEventCreateWithFlags(&copied, cudaEventDisableTiming));
+  PYGB_CUDA(cudaEventRecord(copied, st));
+  for (int t = 0; t < T; ++t) {
+    auto& tb = s->types[t];
+    const i64 cap_nodes = (i64)(tb.slot.cap / 4);
+    k_cleanup<<<grid_for(synced ? cap_nodes : node_cap[t], NT, s->sm_count), NT, 0, st>>>(
+        tb.keys.as<u64>(), tb.vals.as<u64>(), tb.slot.as<u32>(), dst + lay.o_list + t);
+    PYGB_LAUNCH_CHECK();
+  }
+  cudaError_t werr = cudaEventSynchronize(copied);
+  cudaEventDestroy(copied);
+  PYGB_CUDA(werr);
+  const i64* hs = s->st_host;
+  PYGB_CHECK(hs[ST_ERROR] == 0, PYGB200_ERR_INTERNAL, "sampler: mt19937 stream buffer too small (internal bound violated)");
+  s->dirty = false;
+  for (int t = 0; t < T; ++t) {
+    s->types[t].n_nodes = hs[lay.o_list + t];
+    if (n_nodes_out) n_nodes_out[t] = hs[lay.o_list + t];
+    if (nodes_per_hop) for (int j = 0; j <= L; ++j) nodes_per_hop[(size_t)t * (L + 1) + j] = hs[lay.o_nph + t * (L + 1) + j];
+  }
+  for (int r = 0; r < R; ++r) {
+    s->rels[r].n_edges = hs[lay.o_rel + r];
+    if (n_edges_out) n_edges_out[r] = hs[lay.o_rel + r];
+    if (edges_per_hop) for (int j = 0; j < L; ++j) edges_per_hop[(size_t)r * L + j] = hs[lay.o_eph + r * L + j];
+  }
+  memcpy(mt->state, hs + lay.o_mt, sizeof(mt->state));
+  mt->next = (int32_t)hs[ST_MT_NEXT];
+  mt->left = (int32_t)hs[ST_MT_LEFT];
+  return PYGB200_OK;
+}
+
+}  // namespace
+
+extern "C" int pygb200_sampler_run(pygb200_sampler* s, int32_t T, int32_t R, int32_t L,
+                                   const pygb200_relation* rels, const void* const* seeds,
+                                   const int64_t* n_seeds, const int64_t* num_neighbors, unsigned flags,
+                                   pygb200_mt19937* mt, int64_t* nodes_per_hop, int64_t* edges_per_hop,
+                                   int64_t* n_nodes_out, int64_t* n_edges_out, void* stream) {
+  PYGB_CHECK(s && seeds && n_seeds && mt && (rels || R == 0) && (num_neighbors || L == 0 || R == 0), PYGB200_ERR_ARG,
+             "pygb200_sampler_run: null argument");
+  PYGB_CHECK(T >= 1 && T <= 1024 && R >= 0 && L >= 0, PYGB200_ERR_ARG, "pygb200_sampler_run: bad T/R/L");
+  std::lock_guard<std::mutex> lock(s->mu);
+  return sampler_run_impl(s, T, R, L, rels, seeds, n_seeds, num_neighbors, flags, mt, nodes_per_hop, edges_per_hop,
+                          n_nodes_out, n_edges_out, (cudaStream_t)stream);
+}
+
+extern "C" int pygb200_sampler_export_edges(pygb200_sampler* s, int32_t rel, void* row_out, void* col_out,
+                                            void* edge_id_out, int index32, void* stream) {
+  PYGB_CHECK(s && rel >= 0 && rel < s->R, PYGB200_ERR_ARG, "export_edges: bad relation");
+  cudaStream_t st = (cudaStream_t)stream;
+  const i64 n = s->rels[rel].n_edges;
+  if (n == 0) return PYGB200_OK;
+  const int g = grid_for(n, NT, s->sm_count);
+  const i64* srcs[3] = {s->rels[rel].row.as<i64>(), s->rels[rel].colv.as<i64>(), s->rels[rel].eid.as<i64>()};
+  void* dsts[3] = {row_out, col_out, edge_id_out};
+  for (int i = 0; i < 3; ++i) {
+    if (!dsts[i]) continue;
+    if (index32) {
+      k_export<int32_t><<<g, NT, 0, st>>>(srcs[i], (int32_t*)dsts[i], n);
+      PYGB_LAUNCH_CHECK();
+    } else {
+      PYGB_CUDA(cudaMemcpyAsync(dsts[i], srcs[i], (size_t)n * 8, cudaMemcpyDeviceToDevice, st));
+    }
+  }
+  return PYGB200_OK;
+}
+
+extern "C" int pygb200_sampler_export_nodes(pygb200_sampler* s, int32_t type, void* node_id_out, int index32,
+                                            void* stream) {
+  PYGB_CHECK(s && type >= 0 && type < s->T, PYGB200_ERR_ARG, "export_nodes: bad node type");
+  cudaStream_t st = (cudaStream_t)stream;
+  const i64 n = s->types[type].n_nodes;
+  if (n == 0 || !node_id_out) return PYGB200_OK;
+  const int g = grid_for(n, NT, s->sm_count);
+  const i64* node = s->types[type].nodes.as<i64>();
+  if (s->disjoint) {
+    const i64* batch = s->types[type].batch.as<i64>();
+    if (index32) k_export_pairs<int32_t><<<g, NT, 0, st>>>(batch, node, (int32_t*)node_id_out, n);
+    else k_export_pairs<int64_t><<<g, NT, 0, st>>>(batch, node, (int64_t*)node_id_out, n);
+    PYGB_LAUNCH_CHECK();
+  } else if (index32) {
+    k_export<int32_t><<<g, NT, 0, st>>>(node, (int32_t*)node_id_out, n);
+    PYGB_LAUNCH_CHECK();
+  } else {
+    PYGB_CUDA(cudaMemcpyAsync(node_id_out, node, (size_t)n * 8, cudaMemcpyDeviceToDevice, st));
+  }
+  return PYGB200_OK;
+}
+
+extern "C" int pygb200_neighbor_sample_run(pygb200_sampler* s, const void* rowptr, const void* col,
+                                           int64_t num_nodes, int64_t num_edges, const void* seed,
+                                           int64_t n_seed, const int64_t* num_neighbors, int32_t L,
+                                           unsigned flags, pygb200_mt19937* mt, int64_t* nodes_per_hop,
+                                           int64_t* edges_per_hop, int64_t* n_nodes, int64_t* n_edges,
+                                           void* stream) {
+  pygb200_relation rel;
+  rel.rowptr = rowptr; rel.col = col; rel.num_src_nodes = num_nodes; rel.num_edges = num_edges;
+  rel.src_type = 0; rel.dst_type = 0;
+  const void* seeds[1] = {seed};
+  return pygb200_sampler_run(s, 1, 1, L, &rel, seeds, &n_seed, num_neighbors, flags, mt, nodes_per_hop,
+                             edges_per_hop, n_nodes, n_edges, stream);
+}

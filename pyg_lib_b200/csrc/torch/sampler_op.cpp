@@ -1,0 +1,269 @@
+// torch.ops.pyg.neighbor_sample / hetero_neighbor_sample on CUDA tensors.
+//
+// Schemas are the reference's, verbatim (pyg_lib/csrc/sampler/neighbor.cpp:129-147); PyG feature-
+// detects optional arguments by inspecting them.  Dispatch keys follow SURVEY.md 8(b):
+//   pyg::neighbor_sample         -> CUDA key   (reference: CPU only, neighbor_kernel.cpp:980-983)
+//   pyg::hetero_neighbor_sample  -> BackendSelect (dict arguments carry no backend key,
+//                                   neighbor_kernel.cpp:985-991); the kernel checks devices itself.
+// There is no CPU kernel: CPU tensors raise.
+#include <ATen/CPUGeneratorImpl.h>
+
+#include <map>
+#include <mutex>
+
+#include "common.h"
+
+namespace pyg {
+namespace sampler {
+namespace {
+
+typedef std::string node_type;
+typedef std::string rel_type;
+typedef std::tuple<std::string, std::string, std::string> edge_type;
+
+inline rel_type to_rel_type(const edge_type& k) {  // pyg_lib/csrc/utils/types.h:10-12
+  return std::get<0>(k) + "__" + std::get<1>(k) + "__" + std::get<2>(k);
+}
+
+// one persistent workspace per (device, stream)
+pygb200_sampler* get_sampler(int device, cudaStream_t stream) {
+  static std::mutex mu;
+  static std::map<std::pair<int, cudaStream_t>, pygb200_sampler*> cache;
+  std::lock_guard<std::mutex> lock(mu);
+  auto key = std::make_pair(device, stream);
+  auto it = cache.find(key);
+  if (it != cache.end()) return it->second;
+  pygb200_sampler* s = nullptr;
+  PYGB_TORCH_CALL(pygb200_sampler_create(&s));
+  cache[key] = s;
+  return s;
+}
+
+// RAII view of torch's default CPU generator as the ABI's engine struct.  The reference draws its
+// random words from exactly this generator (rand_engine.h:80-92), so it is read before and written
+// back after the run, under the generator's mutex.
+struct CpuEngine {
+  at::CPUGeneratorImpl* gen;
+  std::unique_lock<std::mutex> lock;
+  pygb200_mt19937 mt;
+  CpuEngine()
+      : gen(at::get_generator_or_default<at::CPUGeneratorImpl>(std::nullopt, at::detail::getDefaultCPUGenerator())),
+        lock(gen->mutex_) {
+    const at::mt19937_data_pod pod = gen->engine().data();
+    for (int i = 0; i < 624; ++i) mt.state[i] = pod.state_[i];
+    mt.left = pod.left_;
+    mt.next = (int32_t)pod.next_;
+  }
+  void commit() {
+    at::mt19937 eng = gen->engine();
+    at::mt19937_data_pod pod = eng.data();
+    for (int i = 0; i < 624; ++i) pod.state_[i] = mt.state[i];
+    pod.left_ = mt.left;
+    pod.next_ = (uint32_t)mt.next;
+    eng.set_data(pod);
+    gen->set_engine(eng);
+  }
+};
+
+void check_index_tensor(const at::Tensor& t, const char* name, at::ScalarType st, const at::Device& dev) {
+  TORCH_CHECK(t.is_contiguous(), "Non-contiguous '", name, "'");  // neighbor_kernel.cpp:361-363
+  TORCH_CHECK(t.scalar_type() == st, "'", name, "' must have the same dtype as the seed tensor");
+  TORCH_CHECK(t.device() == dev, "'", name, "' must live on ", dev, " (pyg_lib_b200 has no CPU fallback)");
+  TORCH_CHECK(t.dim() == 1, "'", name, "' must be one-dimensional");
+}
+
+void reject_unsupported(bool has_node_time, bool has_edge_time, bool has_seed_time, bool has_weight, bool disjoint) {
+  // reference argument checks first (neighbor_kernel.cpp:354-359), then what this path does not do
+  TORCH_CHECK(!has_node_time || disjoint, "Temporal sampling needs to create disjoint subgraphs");
+  TORCH_CHECK(!has_edge_time || disjoint, "Temporal sampling needs to create disjoint subgraphs");
+  TORCH_CHECK(!(has_node_time && has_edge_time), "Only one of node-level or edge-level sampling is supported ");
+  TORCH_CHECK(!has_node_time && !has_edge_time && !has_seed_time,
+              "pyg_lib_b200: temporal neighbor sampling is not implemented on the B200 path");
+  TORCH_CHECK(!has_weight, "pyg_lib_b200: biased (edge_weight) neighbor sampling is not implemented on the B200 path");
+}
+
+std::tuple<at::Tensor, at::Tensor, at::Tensor, std::optional<at::Tensor>, std::vector<int64_t>, std::vector<int64_t>>
+neighbor_sample_cuda(const at::Tensor& rowptr, const at::Tensor& col, const at::Tensor& seed,
+                     const std::vector<int64_t>& num_neighbors, const std::optional<at::Tensor>& node_time,
+                     const std::optional<at::Tensor>& edge_time, const std::optional<at::Tensor>& seed_time,
+                     const std::optional<at::Tensor>& edge_weight, bool csc, bool replace, bool directed,
+                     bool disjoint, std::string temporal_strategy, bool return_edge_id) {
+  TORCH_CHECK(temporal_strategy == "uniform" || temporal_strategy == "last", "No valid temporal strategy found");
+  reject_unsupported(node_time.has_value(), edge_time.has_value(), seed_time.has_value(), edge_weight.has_value(), disjoint);
+  TORCH_CHECK(seed.is_cuda(), "pyg_lib_b200: neighbor_sample expects CUDA tensors (no CPU fallback)");
+  const auto st = seed.scalar_type();
+  TORCH_CHECK(st == at::kLong || st == at::kInt, "neighbor_sample: index tensors must be int64 or int32");
+  check_index_tensor(rowptr, "rowptr", st, seed.device());
+  check_index_tensor(col, "col", st, seed.device());
+  check_index_tensor(seed, "seed", st, seed.device());
+  TORCH_CHECK(rowptr.numel() >= 1, "'rowptr' must have at least one element");
+
+  c10::cuda::CUDAGuard guard(seed.device());
+  cudaStream_t stream = at::cuda::getCurrentCUDAStream();
+  pygb200_sampler* s = get_sampler(seed.device().index(), stream);
+  const int L = (int)num_neighbors.size();
+  const bool idx32 = st == at::kInt;
+  unsigned flags = (replace ? PYGB200_S_REPLACE : 0u) | (disjoint ? PYGB200_S_DISJOINT : 0u) | (idx32 ? PYGB200_S_INDEX32 : 0u);
+  std::vector<int64_t> nph(L + 1, 0), eph(L, 0);
+  int64_t n_nodes = 0, n_edges = 0;
+  {
+    CpuEngine eng;
+    PYGB_TORCH_CALL(pygb200_neighbor_sample_run(s, rowptr.data_ptr(), col.data_ptr(), rowptr.numel() - 1, col.numel(),
+                                                seed.data_ptr(), seed.numel(), num_neighbors.data(), L, flags, &eng.mt,
+                                                nph.data(), eph.data(), &n_nodes, &n_edges, stream));
+    eng.commit();
+  }
+  TORCH_CHECK(directed, "Undirected subgraphs not yet supported");  // raised after sampling, neighbor_kernel.cpp:501
+  const auto opt = seed.options();
+  at::Tensor row = at::empty({n_edges}, opt), colv = at::empty({n_edges}, opt);
+  at::Tensor node = disjoint ? at::empty({n_nodes, 2}, opt) : at::empty({n_nodes}, opt);
+  std::optional<at::Tensor> eid = std::nullopt;
+  if (return_edge_id) eid = at::empty({n_edges}, opt);
+  PYGB_TORCH_CALL(pygb200_sampler_export_edges(s, 0, row.data_ptr(), colv.data_ptr(),
+                                               return_edge_id ? eid->data_ptr() : nullptr, idx32, stream));
+  PYGB_TORCH_CALL(pygb200_sampler_export_nodes(s, 0, node.data_ptr(), idx32, stream));
+  if (csc) std::swap(row, colv);  // neighbor_kernel.cpp:155-159
+  return std::make_tuple(row, colv, node, eid, nph, eph);
+}
+
+std::tuple<c10::Dict<rel_type, at::Tensor>, c10::Dict<rel_type, at::Tensor>, c10::Dict<node_type, at::Tensor>,
+           std::optional<c10::Dict<rel_type, at::Tensor>>, c10::Dict<node_type, std::vector<int64_t>>,
+           c10::Dict<rel_type, std::vector<int64_t>>>
+hetero_neighbor_sample_cuda(const std::vector<node_type>& node_types, const std::vector<edge_type>& edge_types,
+                            const c10::Dict<rel_type, at::Tensor>& rowptr_dict,
+                            const c10::Dict<rel_type, at::Tensor>& col_dict,
+                            const c10::Dict<node_type, at::Tensor>& seed_dict,
+                            const c10::Dict<rel_type, std::vector<int64_t>>& num_neighbors_dict,
+                            const std::optional<c10::Dict<node_type, at::Tensor>>& node_time_dict,
+                            const std::optional<c10::Dict<rel_type, at::Tensor>>& edge_time_dict,
+                            const std::optional<c10::Dict<node_type, at::Tensor>>& seed_time_dict,
+                            const std::optional<c10::Dict<rel_type, at::Tensor>>& edge_weight_dict, bool csc,
+                            bool replace, bool directed, bool disjoint, std::string temporal_strategy,
+                            bool return_edge_id) {
+  TORCH_CHECK(temporal_strategy == "uniform" || temporal_strategy == "last", "No valid temporal strategy found");
+  reject_unsupported(node_time_dict.has_value(), edge_time_dict.has_value(), seed_time_dict.has_value(),
+                     edge_weight_dict.has_value(), disjoint);
+  TORCH_CHECK(seed_dict.size() > 0, "hetero_neighbor_sample: empty 'seed_dict'");
+  const at::Tensor& first_seed = seed_dict.begin()->value();
+  TORCH_CHECK(first_seed.is_cuda(), "pyg_lib_b200: hetero_neighbor_sample expects CUDA tensors (no CPU fallback)");
+  const auto st = first_seed.scalar_type();
+  const auto dev = first_seed.device();
+  TORCH_CHECK(st == at::kLong || st == at::kInt, "hetero_neighbor_sample: index tensors must be int64 or int32");
+  const bool idx32 = st == at::kInt;
+
+  // node type indices: seed_dict order first (disjoint batch ids follow it, neighbor_kernel.cpp:669-684)
+  std::vector<node_type> types;
+  std::map<node_type, int> tix;
+  auto add_type = [&](const node_type& t) { if (!tix.count(t)) { tix[t] = (int)types.size(); types.push_back(t); } };
+  for (const auto& kv : seed_dict) {
+    TORCH_CHECK(std::find(node_types.begin(), node_types.end(), kv.key()) != node_types.end(),
+                "seed node type '", kv.key(), "' is not in 'node_types'");
+    add_type(kv.key());
+  }
+  for (const auto& t : node_types) add_type(t);
+  const int T = (int)types.size(), R = (int)edge_types.size();
+
+  size_t L = 0;
+  for (const auto& k : edge_types) L = std::max(L, num_neighbors_dict.at(to_rel_type(k)).size());
+  std::vector<pygb200_relation> rels(R);
+  std::vector<int64_t> nn((size_t)R * std::max<size_t>(L, 1), 0);
+  for (int r = 0; r < R; ++r) {
+    const auto& k = edge_types[r];
+    const rel_type rk = to_rel_type(k);
+    const at::Tensor& rowptr = rowptr_dict.at(rk);
+    const at::Tensor& col = col_dict.at(rk);
+    check_index_tensor(rowptr, "rowptr", st, dev);
+    check_index_tensor(col, "col", st, dev);
+    const node_type& src = !csc ? std::get<0>(k) : std::get<2>(k);  // roles swap for csc (neighbor_kernel.cpp:718-719)
+    const node_type& dst = !csc ? std::get<2>(k) : std::get<0>(k);
+    TORCH_CHECK(tix.count(src) && tix.count(dst), "edge type '", rk, "' uses a node type missing from 'node_types'");
+    rels[r].rowptr = rowptr.data_ptr(); rels[r].col = col.data_ptr();
+    rels[r].num_src_nodes = rowptr.numel() - 1; rels[r].num_edges = col.numel();
+    rels[r].src_type = tix[src]; rels[r].dst_type = tix[dst];
+    const auto& v = num_neighbors_dict.at(rk);
+    TORCH_CHECK(v.size() == L, "all entries of 'num_neighbors_dict' must have the same number of hops");
+    for (size_t h = 0; h < L; ++h) nn[(size_t)r * L + h] = v[h];
+  }
+  std::vector<const void*> seeds(T, nullptr);
+  std::vector<int64_t> n_seeds(T, 0);
+  for (const auto& kv : seed_dict) {
+    check_index_tensor(kv.value(), "seed", st, dev);
+    seeds[tix[kv.key()]] = kv.value().data_ptr();
+    n_seeds[tix[kv.key()]] = kv.value().numel();
+  }
+
+  c10::cuda::CUDAGuard guard(dev);
+  cudaStream_t stream = at::cuda::getCurrentCUDAStream();
+  pygb200_sampler* s = get_sampler(dev.index(), stream);
+  unsigned flags = (replace ? PYGB200_S_REPLACE : 0u) | (disjoint ? PYGB200_S_DISJOINT : 0u) | (idx32 ? PYGB200_S_INDEX32 : 0u);
+  std::vector<int64_t> nph((size_t)T * (L + 1), 0), eph((size_t)R * std::max<size_t>(L, 1), 0), n_nodes(T, 0), n_edges(std::max(R, 1), 0);
+  {
+    CpuEngine eng;
+    PYGB_TORCH_CALL(pygb200_sampler_run(s, T, R, (int)L, rels.data(), seeds.data(), n_seeds.data(), nn.data(), flags,
+                                        &eng.mt, nph.data(), eph.data(), n_nodes.data(), n_edges.data(), stream));
+    eng.commit();
+  }
+  TORCH_CHECK(directed, "Undirected heterogeneous graphs not yet supported");  // neighbor_kernel.cpp:824
+
+  const auto opt = first_seed.options();
+  c10::Dict<rel_type, at::Tensor> out_row, out_col;
+  c10::Dict<node_type, at::Tensor> out_node;
+  std::optional<c10::Dict<rel_type, at::Tensor>> out_eid = std::nullopt;
+  if (return_edge_id) out_eid = c10::Dict<rel_type, at::Tensor>();
+  c10::Dict<node_type, std::vector<int64_t>> out_nph;
+  c10::Dict<rel_type, std::vector<int64_t>> out_eph;
+  for (const auto& t : node_types) {
+    const int i = tix[t];
+    at::Tensor node = disjoint ? at::empty({n_nodes[i], 2}, opt) : at::empty({n_nodes[i]}, opt);
+    PYGB_TORCH_CALL(pygb200_sampler_export_nodes(s, i, node.data_ptr(), idx32, stream));
+    out_node.insert(t, node);
+    out_nph.insert(t, std::vector<int64_t>(nph.begin() + (size_t)i * (L + 1), nph.begin() + (size_t)(i + 1) * (L + 1)));
+  }
+  for (int r = 0; r < R; ++r) {
+    const rel_type rk = to_rel_type(edge_types[r]);
+    at::Tensor row = at::empty({n_edges[r]}, opt), colv = at::empty({n_edges[r]}, opt), eid;
+    if (return_edge_id) eid = at::empty({n_edges[r]}, opt);
+    PYGB_TORCH_CALL(pygb200_sampler_export_edges(s, r, row.data_ptr(), colv.data_ptr(),
+                                                 return_edge_id ? eid.data_ptr() : nullptr, idx32, stream));
+    if (csc) std::swap(row, colv);
+    out_row.insert(rk, row);
+    out_col.insert(rk, colv);
+    if (return_edge_id) out_eid->insert(rk, eid);
+    out_eph.insert(rk, std::vector<int64_t>(eph.begin() + (size_t)r * L, eph.begin() + (size_t)(r + 1) * L));
+  }
+  return std::make_tuple(out_row, out_col, out_node, out_eid, out_nph, out_eph);
+}
+
+}  // namespace
+
+TORCH_LIBRARY_FRAGMENT(pyg, m) {
+  m.def(TORCH_SELECTIVE_SCHEMA(
+      "pyg::neighbor_sample(Tensor rowptr, Tensor col, Tensor seed, int[] "
+      "num_neighbors, Tensor? node_time = None, Tensor? edge_time = None, "
+      "Tensor? seed_time = None, Tensor? edge_weight = None, bool csc = False, "
+      "bool replace = False, bool directed = True, bool disjoint = False, "
+      "str temporal_strategy = 'uniform', bool return_edge_id = True) -> "
+      "(Tensor, Tensor, Tensor, Tensor?, int[], int[])"));
+  m.def(TORCH_SELECTIVE_SCHEMA(
+      "pyg::hetero_neighbor_sample(str[] node_types, (str, str, str)[] "
+      "edge_types, Dict(str, Tensor) rowptr_dict, Dict(str, Tensor) col_dict, "
+      "Dict(str, Tensor) seed_dict, Dict(str, int[]) num_neighbors_dict, "
+      "Dict(str, Tensor)? node_time_dict = None, Dict(str, Tensor)? "
+      "edge_time_dict = None, Dict(str, Tensor)? seed_time_dict = None, "
+      "Dict(str, Tensor)? edge_weight_dict = None, bool csc = False, "
+      "bool replace = False, bool directed = True, bool disjoint = False, "
+      "str temporal_strategy = 'uniform', bool return_edge_id = True) -> "
+      "(Dict(str, Tensor), Dict(str, Tensor), Dict(str, Tensor), "
+      "Dict(str, Tensor)?, Dict(str, int[]), Dict(str, int[]))"));
+}
+
+TORCH_LIBRARY_IMPL(pyg, CUDA, m) {
+  m.impl(TORCH_SELECTIVE_NAME("pyg::neighbor_sample"), TORCH_FN(neighbor_sample_cuda));
+}
+
+TORCH_LIBRARY_IMPL(pyg, BackendSelect, m) {
+  m.impl(TORCH_SELECTIVE_NAME("pyg::hetero_neighbor_sample"), TORCH_FN(hetero_neighbor_sample_cuda));
+}
+
+}  // namespace sampler
+}  // namespace pyg

@@ -1,0 +1,116 @@
+"""GPU parity: segment_matmul / grouped_matmul (torch.ops.pyg.* -> C ABI -> sm_100a kernels) vs the CPU
+oracle, the reference-generated fixtures and a plain fp32 torch matmul.
+
+Tolerances: fp32 'highest' atol 1e-5 (reference test: 1e-6 on 8x16 inputs,
+test/ops/test_matmul.py:38-44); bf16/fp16: relative Frobenius error <= 1e-3 against the reference's
+own low-precision output and max elementwise difference <= 1 storage ulp."""
+import numpy as np
+import pytest
+import torch
+
+from graphs import MATMUL_CASES, build_matmul, ragged_ptr
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+
+
+@pytest.fixture(scope='module')
+def lib():
+    import pyg_lib_b200
+    torch.backends.cuda.matmul.allow_tf32 = False  # like the reference tests (test_matmul.py:9-11)
+    return pyg_lib_b200
+
+
+def _check_lowp(out, ref, dtype):
+    out, ref = out.float().cpu().numpy(), np.asarray(ref, dtype=np.float32)
+    assert np.linalg.norm(out - ref) <= 1e-3 * max(np.linalg.norm(ref), 1e-30)
+    ulp = 2.0 ** -7 if dtype == torch.bfloat16 else 2.0 ** -10
+    assert (np.abs(out - ref) <= ulp * np.maximum(np.abs(ref), 2.0 ** -14) + 1e-30).all()
+
+
+@pytest.mark.parametrize('name', list(MATMUL_CASES))
+@pytest.mark.parametrize('ptr_on_device', [False, True])
+def test_segment_matmul_golden(lib, golden, name, ptr_on_device):
+    case = MATMUL_CASES[name]
+    x, ptr, w = build_matmul(case)
+    out = lib.ops.segment_matmul(x.to(DEV), ptr.to(DEV) if ptr_on_device else ptr, w.to(DEV))
+    assert out.shape == (x.size(0), w.size(2)) and out.dtype == x.dtype and out.is_cuda
+    ref = golden[f'matmul/{name}/out']
+    if x.dtype == torch.float32:
+        assert np.allclose(out.cpu().numpy(), ref, atol=1e-5, rtol=1e-5)
+    else:
+        _check_lowp(out, ref, x.dtype)
+        _check_lowp(out, O.segment_matmul(x, ptr, w).float().numpy(), x.dtype)
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16, torch.float16])
+def test_segment_matmul_bias_and_reference_test_shape(lib, dtype):
+    """test/ops/test_matmul.py:14-45 restated: [8,16] x [2,16,32], ptr [0,5,8], with bias."""
+    g = torch.Generator().manual_seed(0)
+    x, w, b = torch.randn(8, 16, generator=g).to(dtype), torch.randn(2, 16, 32, generator=g).to(dtype), \
+        torch.randn(2, 32, generator=g).to(dtype)
+    ptr = torch.tensor([0, 5, 8])
+    out = lib.ops.segment_matmul(x.to(DEV), ptr, w.to(DEV), bias=b.to(DEV)).cpu()
+    tol = 1e-5 if dtype == torch.float32 else 3e-2
+    assert torch.allclose(out[0:5].float(), x[0:5].float() @ w[0].float() + b[0].float(), atol=tol, rtol=tol)
+    assert torch.allclose(out[5:8].float(), x[5:8].float() @ w[1].float() + b[1].float(), atol=tol, rtol=tol)
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_segment_matmul_backward(lib, dtype):
+    """Autograd kernel (ops/autograd/matmul_kernel.cpp:68-117): dX = dY W^T per segment, dW[b] = X_b^T dY_b."""
+    g = torch.Generator().manual_seed(1)
+    N, K, M, B = 300, 48, 40, 5
+    ptr = ragged_ptr(N, B, 7)
+    x = torch.randn(N, K, generator=g).to(dtype).to(DEV).requires_grad_()
+    w = (torch.randn(B, K, M, generator=g) / K ** 0.5).to(dtype).to(DEV).requires_grad_()
+    bias = torch.randn(B, M, generator=g).to(dtype).to(DEV).requires_grad_()
+    out = lib.ops.segment_matmul(x, ptr, w, bias=bias)
+    gy = torch.randn(N, M, generator=g).to(dtype).to(DEV)
+    out.backward(gy)
+    xr, wr, br = x.detach().float().requires_grad_(), w.detach().float().requires_grad_(), bias.detach().float().requires_grad_()
+    ref = torch.cat([xr[ptr[i]:ptr[i + 1]] @ wr[i] + br[i] for i in range(B)])
+    ref.backward(gy.float())
+    tol = 1e-4 if dtype == torch.float32 else 5e-2
+    assert torch.allclose(out.float(), ref, atol=tol, rtol=tol)
+    assert torch.allclose(x.grad.float(), xr.grad, atol=tol, rtol=tol)
+    assert torch.allclose(w.grad.float(), wr.grad, atol=tol * 4, rtol=tol)
+    assert torch.allclose(bias.grad.float(), br.grad, atol=tol * 4, rtol=tol)
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize('transposed', [False, True])
+def test_grouped_matmul(lib, dtype, transposed):
+    """test/ops/test_matmul.py:48-93 restated: different shapes per group, transposed `others`, biases, grads."""
+    g = torch.Generator().manual_seed(2)
+    shapes = [(5, 16, 32), (6, 9, 64), (0, 8, 8), (130, 70, 33)]
+    inputs = [torch.randn(n, k, generator=g).to(dtype).to(DEV).requires_grad_() for n, k, m in shapes]
+    if transposed:
+        others_raw = [torch.randn(m, k, generator=g).to(dtype).to(DEV).requires_grad_() for n, k, m in shapes]
+        others = [o.t() for o in others_raw]
+    else:
+        others_raw = [torch.randn(k, m, generator=g).to(dtype).to(DEV).requires_grad_() for n, k, m in shapes]
+        others = others_raw
+    biases = [torch.randn(m, generator=g).to(dtype).to(DEV) for n, k, m in shapes]
+    outs = lib.ops.grouped_matmul(inputs, others, biases)
+    tol = 1e-4 if dtype == torch.float32 else 1e-1
+    for (n, k, m), x, o, b, out in zip(shapes, inputs, others, biases, outs):
+        assert out.shape == (n, m)
+        assert torch.allclose(out.float(), x.float() @ o.float() + b.float(), atol=tol, rtol=5e-2)
+    sum(o.float().sum() for o in outs).backward()
+    for (n, k, m), x, o_raw, o in zip(shapes, inputs, others_raw, others):
+        gx = torch.ones(n, m, device=DEV) @ o.detach().float().t()
+        assert torch.allclose(x.grad.float(), gx, atol=tol, rtol=5e-2)
+        go = x.detach().float().t() @ torch.ones(n, m, device=DEV)
+        assert torch.allclose(o_raw.grad.float(), go.t() if transposed else go, atol=tol, rtol=5e-2)
+
+
+def test_segment_matmul_errors(lib):
+    x, w = torch.randn(8, 16, device=DEV), torch.randn(2, 16, 32, device=DEV)
+    with pytest.raises(RuntimeError, match='expected scalar type Long'):
+        lib.ops.segment_matmul(x, torch.tensor([0, 5, 8], dtype=torch.int32), w)
+    with pytest.raises(RuntimeError):
+        lib.ops.segment_matmul(x, torch.tensor([0, 5, 8]), w[:, :8])
+    with pytest.raises((RuntimeError, NotImplementedError)):
+        lib.ops.segment_matmul(x.cpu(), torch.tensor([0, 5, 8]), w.cpu())  # no CPU fallback

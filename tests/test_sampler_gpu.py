@@ -1,0 +1,195 @@
+"""GPU parity: CUDA sampler (through torch.ops.pyg.* -> C ABI) vs the CPU oracle and the committed
+reference fixtures.  Bit-exact for every index tensor, every count, and the CPU generator state."""
+import ctypes as C
+import os.path as osp
+
+import numpy as np
+import pytest
+import torch
+
+from graphs import HETERO_CASES, HOMO_CASES, build_hetero, build_homo, lognormal_csr, random_csr
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+
+
+@pytest.fixture(scope='module')
+def lib():
+    import pyg_lib_b200  # noqa: F401  (registers torch.ops.pyg.*)
+    return pyg_lib_b200
+
+
+def _rng_prefix():
+    return torch.get_rng_state().numpy()[:24 + 624 * 8].copy()
+
+
+def _cmp(out, exp):
+    row, col, node, eid, nph, eph = out
+    erow, ecol, enode, eeid, enph, eeph = exp
+    assert nph == enph and eph == eeph
+    assert torch.equal(node.cpu(), enode)
+    assert torch.equal(row.cpu(), erow)
+    assert torch.equal(col.cpu(), ecol)
+    if eeid is None:
+        assert eid is None
+    else:
+        assert torch.equal(eid.cpu(), eeid)
+
+
+@pytest.mark.parametrize('name', list(HOMO_CASES))
+@pytest.mark.parametrize('dtype', [torch.int64, torch.int32])
+def test_homo_golden(lib, golden, name, dtype):
+    case = HOMO_CASES[name]
+    rowptr, col, seed = build_homo(case)
+    torch.manual_seed(case['rng_seed'])
+    out = lib.sampler.neighbor_sample(rowptr.to(DEV, dtype), col.to(DEV, dtype), seed.to(DEV, dtype),
+                                      case['num_neighbors'], csc=case.get('csc', False),
+                                      replace=case.get('replace', False), disjoint=case.get('disjoint', False))
+    p = f'homo/{name}/'
+    assert out[0].dtype == dtype and out[2].dtype == dtype
+    assert out[4] == golden[p + 'nph'].tolist() and out[5] == golden[p + 'eph'].tolist()
+    assert np.array_equal(out[2].cpu().numpy(), golden[p + 'node'])
+    assert np.array_equal(out[0].cpu().numpy(), golden[p + 'row'])
+    assert np.array_equal(out[1].cpu().numpy(), golden[p + 'col'])
+    assert np.array_equal(out[3].cpu().numpy(), golden[p + 'eid'])
+    assert np.array_equal(_rng_prefix(), golden[p + 'rng_after'])
+
+
+@pytest.mark.parametrize('name', list(HETERO_CASES))
+def test_hetero_golden(lib, golden, name):
+    case = HETERO_CASES[name]
+    nt, et, rp, cl, sd, nn = build_hetero(case)
+    torch.manual_seed(case['rng_seed'])
+    out = torch.ops.pyg.hetero_neighbor_sample(nt, et, {k: v.to(DEV) for k, v in rp.items()},
+                                               {k: v.to(DEV) for k, v in cl.items()},
+                                               {k: v.to(DEV) for k, v in sd.items()}, nn, None, None, None, None,
+                                               case.get('csc', False), case.get('replace', False), True,
+                                               case.get('disjoint', False), 'uniform', True)
+    p = f'hetero/{name}/'
+    for k in rp:
+        assert out[5][k] == golden[p + 'eph/' + k].tolist(), k
+        assert np.array_equal(out[0][k].cpu().numpy(), golden[p + 'row/' + k]), k
+        assert np.array_equal(out[1][k].cpu().numpy(), golden[p + 'col/' + k]), k
+        assert np.array_equal(out[3][k].cpu().numpy(), golden[p + 'eid/' + k]), k
+    for t in nt:
+        assert out[4][t] == golden[p + 'nph/' + t].tolist(), t
+        assert np.array_equal(out[2][t].cpu().numpy(), golden[p + 'node/' + t]), t
+    assert np.array_equal(_rng_prefix(), golden[p + 'rng_after'])
+
+
+def test_hetero_python_wrapper(lib):
+    """EdgeType-tuple API of pyg_lib.sampler.hetero_neighbor_sample (pyg_lib/sampler/__init__.py:135-200)."""
+    case = HETERO_CASES['mag_small']
+    nt, et, rp, cl, sd, nn = build_hetero(case)
+    key = {'__'.join(k): k for k in et}
+    torch.manual_seed(3)
+    exp = O.hetero_neighbor_sample(nt, et, rp, cl, sd, nn)
+    torch.manual_seed(3)
+    out = lib.sampler.hetero_neighbor_sample({key[k]: v.to(DEV) for k, v in rp.items()},
+                                             {key[k]: v.to(DEV) for k, v in cl.items()},
+                                             {k: v.to(DEV) for k, v in sd.items()}, {key[k]: v for k, v in nn.items()})
+    for k in rp:
+        assert torch.equal(out[0][key[k]].cpu(), exp[0][k]) and torch.equal(out[1][key[k]].cpu(), exp[1][k])
+        assert torch.equal(out[3][key[k]].cpu(), exp[3][k]) and out[5][key[k]] == exp[5][k]
+    for t in nt:
+        assert torch.equal(out[2][t].cpu(), exp[2][t]) and out[4][t] == exp[4][t]
+
+
+@pytest.mark.parametrize('replace', [False, True])
+@pytest.mark.parametrize('nn', [[15, 10], [25, 15], [3, 2, 2], [33, 4], [-1], [10, -1]])
+def test_homo_vs_oracle_medium(lib, replace, nn):
+    """20k-node graph with a few >= 2^16-degree hubs: mixed 16/32-bit draws; call sequence shares one
+    generator so RNG hand-over between calls is covered too."""
+    rowptr, col = random_csr(20000, 30, 0, big=[(5, 70000), (77, 65540), (100, 65536)])
+    seed = torch.randperm(20000, generator=torch.Generator().manual_seed(5))[:256]
+    seed[3], seed[9], seed[11] = 5, 77, 100
+    d = [t.to(DEV) for t in (rowptr, col, seed)]
+    torch.manual_seed(7)
+    exp = [O.neighbor_sample(rowptr, col, seed, nn, replace=replace) for _ in range(3)]
+    s_exp = _rng_prefix()
+    torch.manual_seed(7)
+    for i in range(3):
+        _cmp(lib.sampler.neighbor_sample(d[0], d[1], d[2], nn, replace=replace), exp[i])
+    assert np.array_equal(_rng_prefix(), s_exp)
+
+
+def test_no_edge_id_and_csc(lib):
+    rowptr, col = random_csr(5000, 12, 3)
+    seed = torch.arange(100, 164)
+    torch.manual_seed(1)
+    exp = O.neighbor_sample(rowptr, col, seed, [8, 4], csc=True, return_edge_id=False)
+    torch.manual_seed(1)
+    out = lib.sampler.neighbor_sample(rowptr.to(DEV), col.to(DEV), seed.to(DEV), [8, 4], csc=True,
+                                      return_edge_id=False)
+    _cmp(out, exp)
+
+
+def test_products_shaped_slice(lib):
+    """Scaled-down C2 (log-normal degrees, SURVEY 8d recipe): 200k nodes / 10M edges, 1024 seeds, [15,10]."""
+    rowptr, col = lognormal_csr(200_000, 10_000_000, seed=1)
+    seed = torch.randperm(200_000, generator=torch.Generator().manual_seed(2))[:1024]
+    torch.manual_seed(12345)
+    exp = O.neighbor_sample(rowptr, col, seed, [15, 10])
+    torch.manual_seed(12345)
+    out = lib.sampler.neighbor_sample(rowptr.to(DEV), col.to(DEV), seed.to(DEV), [15, 10])
+    _cmp(out, exp)
+    assert out[0].numel() > 100_000
+
+
+def test_errors(lib):
+    rowptr, col = random_csr(100, 4, 0)
+    r, c, s = rowptr.to(DEV), col.to(DEV), torch.arange(4, device=DEV)
+    with pytest.raises(RuntimeError, match='Undirected subgraphs not yet supported'):
+        lib.sampler.neighbor_sample(r, c, s, [2], directed=False)
+    with pytest.raises(RuntimeError, match='disjoint'):
+        lib.sampler.neighbor_sample(r, c, s, [2], node_time=torch.zeros(100, dtype=torch.long, device=DEV))
+    with pytest.raises(RuntimeError, match='not implemented on the B200 path'):
+        lib.sampler.neighbor_sample(r, c, s, [2], edge_weight=torch.ones(col.numel(), device=DEV))
+    with pytest.raises(RuntimeError, match='Non-contiguous'):
+        lib.sampler.neighbor_sample(r, torch.stack([c, c], 1)[:, 0], s, [2])
+    with pytest.raises((RuntimeError, NotImplementedError)):
+        lib.sampler.neighbor_sample(rowptr, col, torch.arange(4), [2])  # CPU tensors: no fallback
+
+
+def test_c_abi_direct(lib):
+    """Call libpyg_b200.so through ctypes with raw device pointers (no torch op layer)."""
+    path = osp.join(osp.dirname(lib.__file__), 'libpyg_b200.so')
+    abi = C.CDLL(path)
+    abi.pygb200_last_error.restype = C.c_char_p
+
+    class MT(C.Structure):
+        _fields_ = [('state', C.c_uint32 * 624), ('left', C.c_int32), ('next', C.c_int32)]
+
+    case = HOMO_CASES['rand_15_10']
+    rowptr, col, seed = build_homo(case)
+    d = [t.to(DEV) for t in (rowptr, col, seed)]
+    omt = O.mt_seed(case['rng_seed'])
+    exp = O.neighbor_sample(rowptr, col, seed, case['num_neighbors'], mt=omt)
+    mt = MT()
+    src = O.mt_seed(case['rng_seed'])
+    C.memmove(C.byref(mt), C.byref(src), C.sizeof(MT))
+    h = C.c_void_p()
+    assert abi.pygb200_sampler_create(C.byref(h)) == 0, abi.pygb200_last_error()
+    nn = (C.c_int64 * 2)(*case['num_neighbors'])
+    nph, eph = (C.c_int64 * 3)(), (C.c_int64 * 2)()
+    n_nodes, n_edges = C.c_int64(), C.c_int64()
+    torch.cuda.synchronize()
+    rc = abi.pygb200_neighbor_sample_run(h, C.c_void_p(d[0].data_ptr()), C.c_void_p(d[1].data_ptr()),
+                                         C.c_int64(rowptr.numel() - 1), C.c_int64(col.numel()),
+                                         C.c_void_p(d[2].data_ptr()), C.c_int64(seed.numel()), nn, 2, 0, C.byref(mt), nph,
+                                         eph, C.byref(n_nodes), C.byref(n_edges), None)
+    assert rc == 0, abi.pygb200_last_error()
+    assert list(nph) == exp[4] and list(eph) == exp[5]
+    row = torch.empty(n_edges.value, dtype=torch.int64, device=DEV)
+    colv, eid = torch.empty_like(row), torch.empty_like(row)
+    node = torch.empty(n_nodes.value, dtype=torch.int64, device=DEV)
+    assert abi.pygb200_sampler_export_edges(h, 0, C.c_void_p(row.data_ptr()), C.c_void_p(colv.data_ptr()),
+                                            C.c_void_p(eid.data_ptr()), 0, None) == 0
+    assert abi.pygb200_sampler_export_nodes(h, 0, C.c_void_p(node.data_ptr()), 0, None) == 0
+    torch.cuda.synchronize()
+    assert torch.equal(row.cpu(), exp[0]) and torch.equal(colv.cpu(), exp[1])
+    assert torch.equal(node.cpu(), exp[2]) and torch.equal(eid.cpu(), exp[3])
+    assert mt.left == omt.left and mt.next == omt.next
+    assert (np.ctypeslib.as_array(mt.state) == np.ctypeslib.as_array(omt.state)).all()
+    abi.pygb200_sampler_destroy(h)
