@@ -49,6 +49,14 @@ int pygb200_cuda_version(void);          /* CUDA_VERSION the library was built w
 int pygb200_kernel_launches(void);       /* number of kernels this library launched so far
                                             (process-wide counter; bench.py reports deltas) */
 
+/* Per-kernel device timing for bench.py's roofline: when enabled, selected kernels are bracketed with
+ * CUDA events on their launching stream.  `pygb200_profile_read` synchronises the pending events and
+ * returns accumulated milliseconds, launch count and work units (sampler kernels: edges; matmul: rows)
+ * for `name` in {"sample","count","mark","assign","lookup","segment_matmul","grouped_gemm"}, then
+ * resets that accumulator.  Returns 0, or PYGB200_ERR_ARG for an unknown name. */
+void pygb200_profile_enable(int on);
+int pygb200_profile_read(const char* name, double* ms, int64_t* launches, int64_t* work);
+
 /* ------------------------------------------------------------------------------------ matmul
  * out[ptr[b]:ptr[b+1], :] = x[ptr[b]:ptr[b+1], :] @ w[b]        (row-major, contiguous)
  *   x [N,K], w [B,K,M], out [N,M] of `dtype`; ptr_dev [B+1] int64 on the DEVICE.
@@ -145,11 +153,6 @@ int pygb200_neighbor_sample_run(pygb200_sampler* s, const void* rowptr, const vo
                                 unsigned flags, pygb200_mt19937* mt_inout, int64_t* nodes_per_hop,
                                 int64_t* edges_per_hop, int64_t* n_nodes, int64_t* n_edges,
                                 void* stream);
-
-/* ---- frontier-sharded multi-GPU building blocks (semantics of the reference's
- * dist_neighbor_sample / relabel_neighborhood split, neighbor_kernel.cpp:296-303,957-978) ---------
- * See pyg_lib_b200/sampler/dist.py for the orchestration over torch.distributed (NCCL). */
-int pygb200_mt_raw_words(const pygb200_mt19937* mt, int64_t n_words, uint64_t* out_dev, void* stream);
 
 #ifdef __cplusplus
 }

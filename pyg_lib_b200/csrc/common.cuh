@@ -16,6 +16,12 @@ namespace pygb200 {
 void set_error(const std::string& msg);  // thread-local, read by pygb200_last_error()
 void count_launch(int n = 1);            // process-wide kernel launch counter
 
+// Optional per-kernel device timing (pygb200_profile_enable): CUDA events on the launching stream
+// around selected launches, accumulated per name.  Off by default (zero overhead besides a branch).
+bool prof_enabled();
+void* prof_begin(cudaStream_t st);                                   // returns an opaque token (or null)
+void prof_end(void* token, const char* name, cudaStream_t st, long long work);
+
 #define PYGB_CUDA(expr)                                                                          \
   do {                                                                                           \
     cudaError_t _e = (expr);                                                                     \

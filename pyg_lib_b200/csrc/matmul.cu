@@ -166,12 +166,14 @@ int launch_grouped(const Problem* probs_dev, i64 P, const i64* total_dev, i64 ti
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   i64 g = tiles_bound < 1 ? 1 : tiles_bound;
   if (g > (i64)sms * 8) g = (i64)sms * 8;
+  void* tk = prof_begin(st);
   switch (dtype) {
     case PYGB200_F32: k_grouped_gemm<float><<<(int)g, MM_NT, 0, st>>>(probs_dev, P, total_dev); break;
     case PYGB200_BF16: k_grouped_gemm<__nv_bfloat16><<<(int)g, MM_NT, 0, st>>>(probs_dev, P, total_dev); break;
     case PYGB200_F16: k_grouped_gemm<__half><<<(int)g, MM_NT, 0, st>>>(probs_dev, P, total_dev); break;
     default: set_error("matmul: unknown dtype"); return PYGB200_ERR_ARG;
   }
+  prof_end(tk, "grouped_gemm", st, tiles_bound);
   PYGB_LAUNCH_CHECK();
   return PYGB200_OK;
 }

@@ -17,6 +17,8 @@
 //   k_assign  new local ids = ids_base + rank, appended to the dst type's node list.
 //   k_lookup  every edge reads its final local id.
 // Host work per call: bounds, launches, ONE stream sync at the end (the API returns host counts).
+#include <string.h>
+
 #include <algorithm>
 #include <atomic>
 #include <mutex>
@@ -32,6 +34,49 @@ static thread_local std::string g_err;
 static std::atomic<int> g_launches{0};
 void set_error(const std::string& msg) { g_err = msg; }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// ---- optional per-kernel timing
+namespace {
+struct ProfPending { cudaEvent_t a, b; int slot; long long work; };
+struct ProfAcc { const char* name; double ms; long long launches, work; };
+std::mutex g_prof_mu;
+std::atomic<bool> g_prof_on{false};
+std::vector<ProfPending> g_prof_pending;
+ProfAcc g_prof_acc[] = {{"sample", 0, 0, 0}, {"count", 0, 0, 0}, {"mark", 0, 0, 0}, {"assign", 0, 0, 0},
+                        {"lookup", 0, 0, 0}, {"segment_matmul", 0, 0, 0}, {"grouped_gemm", 0, 0, 0}};
+constexpr int N_PROF = sizeof(g_prof_acc) / sizeof(g_prof_acc[0]);
+int prof_slot(const char* name) {
+  for (int i = 0; i < N_PROF; ++i) if (strcmp(g_prof_acc[i].name, name) == 0) return i;
+  return -1;
+}
+void prof_drain_locked() {
+  for (auto& p : g_prof_pending) {
+    float ms = 0.f;
+    if (cudaEventSynchronize(p.b) == cudaSuccess && cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) {
+      g_prof_acc[p.slot].ms += ms; g_prof_acc[p.slot].launches += 1; g_prof_acc[p.slot].work += p.work;
+    }
+    cudaEventDestroy(p.a); cudaEventDestroy(p.b);
+  }
+  g_prof_pending.clear();
+}
+}  // namespace
+bool prof_enabled() { return g_prof_on.load(std::memory_order_relaxed); }
+void* prof_begin(cudaStream_t st) {
+  if (!prof_enabled()) return nullptr;
+  auto* p = new ProfPending();
+  cudaEventCreate(&p->a); cudaEventCreate(&p->b);
+  cudaEventRecord(p->a, st);
+  return p;
+}
+void prof_end(void* token, const char* name, cudaStream_t st, long long work) {
+  if (!token) return;
+  auto* p = static_cast<ProfPending*>(token);
+  cudaEventRecord(p->b, st);
+  p->slot = prof_slot(name); p->work = work;
+  std::lock_guard<std::mutex> lock(g_prof_mu);
+  if (p->slot >= 0) g_prof_pending.push_back(*p); else { cudaEventDestroy(p->a); cudaEventDestroy(p->b); }
+  delete p;
+}
 
 namespace {
 
@@ -637,6 +682,18 @@ struct pygb200_sampler {
 extern "C" const char* pygb200_last_error(void) { return g_err.c_str(); }
 extern "C" int pygb200_cuda_version(void) { return CUDART_VERSION; }
 extern "C" int pygb200_kernel_launches(void) { return g_launches.load(); }
+extern "C" void pygb200_profile_enable(int on) { g_prof_on.store(on != 0); }
+extern "C" int pygb200_profile_read(const char* name, double* ms, int64_t* launches, int64_t* work) {
+  std::lock_guard<std::mutex> lock(g_prof_mu);
+  prof_drain_locked();
+  const int i = name ? prof_slot(name) : -1;
+  if (i < 0) { set_error("pygb200_profile_read: unknown kernel name"); return PYGB200_ERR_ARG; }
+  if (ms) *ms = g_prof_acc[i].ms;
+  if (launches) *launches = g_prof_acc[i].launches;
+  if (work) *work = g_prof_acc[i].work;
+  g_prof_acc[i].ms = 0; g_prof_acc[i].launches = 0; g_prof_acc[i].work = 0;
+  return PYGB200_OK;
+}
 
 extern "C" int pygb200_sampler_create(pygb200_sampler** out) {
   PYGB_CHECK(out != nullptr, PYGB200_ERR_ARG, "pygb200_sampler_create: null out");
@@ -738,7 +795,9 @@ int ensure_edge_scratch(pygb200_sampler* s, i64 E, cudaStream_t st) {
 
 template <typename idx_t>
 int launch_count(pygb200_sampler* s, const PassArgs& a, i64 F, cudaStream_t st) {
+  void* tk = prof_begin(st);
   k_count<idx_t><<<grid_for(F, NT, s->sm_count), NT, 0, st>>>(a);
+  prof_end(tk, "count", st, F);
   PYGB_LAUNCH_CHECK();
   return PYGB200_OK;
 }
@@ -748,18 +807,26 @@ int launch_rest(pygb200_sampler* s, const PassArgs& a, i64 F, i64 E, cudaStream_
   const i64 k = a.fanout;
   const int G = (k < 0 || k > 16) ? 32 : (k > 8 ? 16 : (k > 4 ? 8 : 4));
   const int gs = grid_for(F, NT / G, s->sm_count);
+  void* tk = prof_begin(st);
   switch (G) {
     case 4: k_sample<idx_t, 4><<<gs, NT, 0, st>>>(a); break;
     case 8: k_sample<idx_t, 8><<<gs, NT, 0, st>>>(a); break;
     case 16: k_sample<idx_t, 16><<<gs, NT, 0, st>>>(a); break;
     default: k_sample<idx_t, 32><<<gs, NT, 0, st>>>(a); break;
   }
+  prof_end(tk, "sample", st, E);
   PYGB_LAUNCH_CHECK();
+  tk = prof_begin(st);
   k_mark<<<grid_for(E, ETILE, s->sm_count), NT, 0, st>>>(a);
+  prof_end(tk, "mark", st, E);
   PYGB_LAUNCH_CHECK();
+  tk = prof_begin(st);
   k_assign<<<grid_for(E, NT, s->sm_count), NT, 0, st>>>(a);
+  prof_end(tk, "assign", st, E);
   PYGB_LAUNCH_CHECK();
+  tk = prof_begin(st);
   k_lookup<<<grid_for(E, NT, s->sm_count), NT, 0, st>>>(a);
+  prof_end(tk, "lookup", st, E);
   PYGB_LAUNCH_CHECK();
   return PYGB200_OK;
 }
