@@ -1,9 +1,456 @@
-// placeholder until the tcgen05 kernel lands (next commit): nothing is routed here yet.
+// pyg_lib_b200/csrc/matmul_tcgen05.cu — segment_matmul for bf16/fp16 on Blackwell tensor cores.
+//
+// Replaces the reference's CUTLASS 2.x sm80 grouped GEMM (pyg_lib/csrc/ops/cuda/matmul_kernel.cu:167-190,
+// mma.sync TF32, fp32 storage only) with a hand-written persistent sm_100a kernel:
+//
+//   * one CTA per SM, warp-specialised: warp 0 = TMA producer, warp 1 = tcgen05.mma issuer,
+//     warp 2 = TMEM allocator, warps 4-7 = epilogue (TMEM -> registers -> bf16 -> smem -> TMA store);
+//   * the flat tile list (ceil(len_b / 128) row tiles per segment) is derived on the device from `ptr`
+//     (no host sync); every CTA takes a contiguous chunk so consecutive tiles share W[b];
+//   * A row tiles [128 x K] stream through a 3-stage TMA ring (SWIZZLE_128B, K-major);
+//     W[b] ([K x M], M contiguous == "MN-major" B operand) is TMA-loaded once per segment into a
+//     double-buffered slot and consumed in place — no transpose pass;
+//   * accumulators live in TMEM (two [128 x M] fp32 buffers) so the epilogue of tile t overlaps the
+//     MMAs of tile t+1; bias is fused in the epilogue;
+//   * ragged tails: a tile never crosses a segment end; TMA loads may over-read rows of the next
+//     segment (harmless), full tiles leave through TMA stores, partial tiles through predicated
+//     16-byte row stores.
+//
+// The shape is HBM-bound (AI = 63.75 FLOP/B at K=M=128), so the design goal is bytes in flight per SM,
+// not MMA issue rate: 3 x 32 KB of A loads are outstanding while one tile computes.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
 #include "common.cuh"
+
 namespace pygb200 {
-bool tcgen05_supported(i64, i64, i64, i64, int, const void*, const void*, const void*) { return false; }
-int segment_matmul_tcgen05(const void*, const i64*, const void*, const void*, void*, i64, i64, i64, i64, int, cudaStream_t) {
-  set_error("tcgen05 path not built");
-  return PYGB200_ERR_UNSUPPORTED;
+namespace {
+
+constexpr int TM = 128;            // rows per tile == UMMA M == TMEM lanes
+constexpr int A_STAGES = 3;
+constexpr int MAX_SEG = 1024;      // segments handled by the in-kernel tile prefix (else generic path)
+constexpr int NTHREADS = 256;
+
+// ---------------------------------------------------------------------------------- PTX helpers
+__device__ __forceinline__ u32 smem_u32(const void* p) { return (u32)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(u32 bar, u32 count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
+__device__ __forceinline__ void mbar_expect_tx(u32 bar, u32 bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(u32 bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u32 bar, u32 parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "DONE:\n"
+      "}\n" ::"r"(bar), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(u32 dst, const CUtensorMap* map, int c0, int c1, u32 bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+      "l"(map), "r"(c0), "r"(c1), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, u32 src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src), "r"(c0),
+               "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(u32 bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(u32 tmem_d, u64 adesc, u64 bdesc, u32 idesc, u32 accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld_32x32(u32 taddr, u32* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp SmemDescriptor bit layout):
+// [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version=1 | [61,64) layout (2 = SWIZZLE_128B)
+__device__ __forceinline__ u64 make_desc(u32 saddr, u32 lbo_bytes, u32 sbo_bytes) {
+  u64 d = 0;
+  d |= (u64)((saddr & 0x3ffffu) >> 4);
+  d |= (u64)((lbo_bytes >> 4) & 0x3fffu) << 16;
+  d |= (u64)((sbo_bytes >> 4) & 0x3fffu) << 32;
+  d |= (u64)1 << 46;
+  d |= (u64)2 << 61;
+  return d;
+}
+
+template <bool BF16>
+__device__ __forceinline__ u32 pack2(float a, float b) {
+  if (BF16) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<u32*>(&h);
+  } else {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<u32*>(&h);
+  }
+}
+template <bool BF16>
+__device__ __forceinline__ float ld_bias(const void* bias, i64 idx) {
+  if (BF16) return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(bias)[idx]);
+  return __half2float(reinterpret_cast<const __half*>(bias)[idx]);
+}
+
+struct SegParams {
+  const i64* ptr;
+  const void* bias;   // [B, M] or null
+  void* out;          // [N, M]
+  i64 N;
+  int K, M, B;
+};
+
+// dynamic smem layout (1024-aligned): A ring | W double buffer | out staging | barriers | tile prefix
+template <bool BF16>
+__global__ void __launch_bounds__(NTHREADS, 1)
+k_segment_matmul_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
+                    const __grid_constant__ CUtensorMap map_o, const SegParams P) {
+  extern __shared__ unsigned char smem_raw[];
+  const u32 raw = smem_u32(smem_raw);
+  const u32 base = (raw + 1023u) & ~1023u;
+  unsigned char* sm = smem_raw + (base - raw);
+  const int K = P.K, M = P.M, KH = K / 64, NH = M / 64;
+  const u32 a_bytes = TM * K * 2, w_bytes = K * M * 2, o_bytes = TM * M * 2;
+  const u32 off_a = 0, off_w = off_a + A_STAGES * a_bytes, off_o = off_w + 2 * w_bytes, off_bar = off_o + o_bytes;
+  u64* bars = reinterpret_cast<u64*>(sm + off_bar);
+  // barrier indices
+  const u32 bar0 = base + off_bar;
+  auto A_FULL = [&](int s) { return bar0 + 8u * (u32)s; };
+  auto A_EMPTY = [&](int s) { return bar0 + 8u * (u32)(A_STAGES + s); };
+  auto W_FULL = [&](int s) { return bar0 + 8u * (u32)(2 * A_STAGES + s); };
+  auto W_EMPTY = [&](int s) { return bar0 + 8u * (u32)(2 * A_STAGES + 2 + s); };
+  auto T_FULL = [&](int s) { return bar0 + 8u * (u32)(2 * A_STAGES + 4 + s); };
+  auto T_EMPTY = [&](int s) { return bar0 + 8u * (u32)(2 * A_STAGES + 6 + s); };
+  constexpr int NBARS = 2 * A_STAGES + 8;
+  u32* tmem_slot = reinterpret_cast<u32*>(bars + NBARS);
+  int* tile_pre = reinterpret_cast<int*>(tmem_slot + 2);  // [B + 1] exclusive prefix of tiles per segment
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const u32 tmem_cols = (2 * M <= 32) ? 32 : (2 * M <= 64) ? 64 : (2 * M <= 128) ? 128 : (2 * M <= 256) ? 256 : 512;
+
+  // ---- prologue: tile prefix over segments (all threads), barriers, TMEM
+  {
+    // serial-in-chunks prefix: B <= MAX_SEG, 256 threads
+    __shared__ int s_part[NTHREADS];
+    const int per = (P.B + NTHREADS - 1) / NTHREADS;
+    int loc = 0;
+    for (int j = 0; j < per; ++j) {
+      const int b = threadIdx.x * per + j;
+      if (b < P.B) loc += (int)((P.ptr[b + 1] - P.ptr[b] + TM - 1) / TM);
+    }
+    s_part[threadIdx.x] = loc;
+    __syncthreads();
+    int pre = 0;
+    for (int t = 0; t < (int)threadIdx.x; ++t) pre += s_part[t];
+    for (int j = 0; j < per; ++j) {
+      const int b = threadIdx.x * per + j;
+      if (b < P.B) {
+        tile_pre[b] = pre;
+        pre += (int)((P.ptr[b + 1] - P.ptr[b] + TM - 1) / TM);
+      }
+    }
+    if (threadIdx.x == 0) {
+      int tot = 0;
+      for (int t = 0; t < NTHREADS; ++t) tot += s_part[t];
+      tile_pre[P.B] = tot;
+    }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < A_STAGES; ++s) { mbar_init(A_FULL(s), 1); mbar_init(A_EMPTY(s), 1); }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(W_FULL(s), 1); mbar_init(W_EMPTY(s), 1);
+      mbar_init(T_FULL(s), 1); mbar_init(T_EMPTY(s), 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    fence_proxy_async();
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_o) : "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const u32 tmem_base = *tmem_slot;
+
+  const int total_tiles = tile_pre[P.B];
+  const int per_cta = (total_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int t_begin = (int)blockIdx.x * per_cta;
+  const int t_end = min(total_tiles, t_begin + per_cta);
+
+  // segment lookup: largest b with tile_pre[b] <= t and a non-empty segment (tile_pre[b+1] > t)
+  auto seg_of = [&](int t) {
+    int lo = 0, hi = P.B - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (tile_pre[mid] <= t) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+  };
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (lane == 0 && t_begin < t_end) {
+      int seg = seg_of(t_begin), cur_seg = -1, wbuf = 1, a_stage = 0;
+      u32 a_phase = 0, w_phase[2] = {0, 0};
+      for (int t = t_begin; t < t_end; ++t) {
+        while (tile_pre[seg + 1] <= t) ++seg;
+        if (seg != cur_seg) {
+          cur_seg = seg;
+          wbuf ^= 1;
+          mbar_wait(W_EMPTY(wbuf), w_phase[wbuf] ^ 1);
+          w_phase[wbuf] ^= 1;
+          mbar_expect_tx(W_FULL(wbuf), w_bytes);
+          for (int h = 0; h < NH; ++h)  // box [64 cols of M x K rows] -> [K][128 B], MN-major SW128 atoms
+            tma_load_2d(base + off_w + wbuf * w_bytes + h * (K * 128), &map_w, h * 64, seg * K, W_FULL(wbuf));
+        }
+        const i64 row0 = P.ptr[seg] + (i64)(t - tile_pre[seg]) * TM;
+        mbar_wait(A_EMPTY(a_stage), a_phase ^ 1);
+        mbar_expect_tx(A_FULL(a_stage), a_bytes);
+        for (int h = 0; h < KH; ++h)  // box [64 cols of K x 128 rows] -> [128][128 B], K-major SW128 atoms
+          tma_load_2d(base + off_a + a_stage * a_bytes + h * (TM * 128), &map_a, h * 64, (int)row0, A_FULL(a_stage));
+        if (++a_stage == A_STAGES) { a_stage = 0; a_phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ================================
+    if (t_begin < t_end) {
+      // instruction descriptor: D=f32 (bit 4), A/B format (bits 7-9, 10-12: 1 = bf16, 0 = f16),
+      // A K-major (bit 15 = 0), B MN-major (bit 16 = 1), N>>3 at bit 17, M>>4 at bit 24
+      const u32 fmt = BF16 ? 1u : 0u;
+      const u32 idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (1u << 16) | ((u32)(M >> 3) << 17) | ((u32)(TM >> 4) << 24);
+      int seg = seg_of(t_begin), cur_seg = -1, wbuf = 1, a_stage = 0, acc = 0;
+      u32 a_phase = 0, w_phase[2] = {0, 0}, t_phase[2] = {0, 0};
+      for (int t = t_begin; t < t_end; ++t) {
+        while (tile_pre[seg + 1] <= t) ++seg;
+        if (seg != cur_seg) {
+          cur_seg = seg;
+          wbuf ^= 1;
+          mbar_wait(W_FULL(wbuf), w_phase[wbuf]);
+          w_phase[wbuf] ^= 1;
+        }
+        mbar_wait(T_EMPTY(acc), t_phase[acc] ^ 1);
+        mbar_wait(A_FULL(a_stage), a_phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const u32 a_base = base + off_a + a_stage * a_bytes, w_base = base + off_w + wbuf * w_bytes;
+          const u32 d_tmem = tmem_base + (u32)(acc * M);
+          for (int kk = 0; kk < K / 16; ++kk) {
+            // A: half (kk/4) of 64 K-elements, 32 bytes per 16-element step inside the 128 B swizzle row
+            const u64 adesc = make_desc(a_base + (kk >> 2) * (TM * 128) + (kk & 3) * 32, 16, 1024);
+            // B: 16 K-rows = 2 atoms of 8 rows x 128 B; LBO = stride between 64-column groups of N
+            const u64 bdesc = make_desc(w_base + kk * 2048, (u32)(K * 128), 1024);
+            tc_mma_f16(d_tmem, adesc, bdesc, idesc, kk > 0 ? 1u : 0u);
+          }
+          tc_commit(A_EMPTY(a_stage));   // smem A stage reusable once these MMAs retire
+          tc_commit(T_FULL(acc));        // accumulator ready for the epilogue
+          const bool last_of_seg = (t + 1 >= t_end) || (tile_pre[seg + 1] <= t + 1);
+          if (last_of_seg) tc_commit(W_EMPTY(wbuf));
+        }
+        __syncwarp();
+        if (++a_stage == A_STAGES) { a_stage = 0; a_phase ^= 1; }
+        t_phase[acc] ^= 1;
+        acc ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    // ================================ epilogue (128 threads) ================================
+    const int q = warp & 3;                 // TMEM lane quarter owned by this warp
+    const int r = q * 32 + lane;            // row inside the tile == TMEM lane
+    const int et = threadIdx.x - 128;
+    unsigned char* stage = sm + off_o;
+    if (t_begin < t_end) {
+      int seg = seg_of(t_begin), acc = 0;
+      u32 t_phase[2] = {0, 0};
+      bool store_pending = false;
+      for (int t = t_begin; t < t_end; ++t) {
+        while (tile_pre[seg + 1] <= t) ++seg;
+        const i64 row0 = P.ptr[seg] + (i64)(t - tile_pre[seg]) * TM;
+        const i64 rem = P.ptr[seg + 1] - row0;
+        const int valid = rem < TM ? (int)rem : TM;
+        mbar_wait(T_FULL(acc), t_phase[acc]);
+        t_phase[acc] ^= 1;
+        tc_fence_after();
+        if (valid == TM && store_pending) {  // staging buffer still being read by the previous TMA store?
+          if (et == 0) tma_store_wait_read();
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          store_pending = false;
+        }
+        for (int c0 = 0; c0 < M; c0 += 32) {
+          u32 v[32];
+          tc_ld_32x32(tmem_base + (u32)(acc * M + c0) + ((u32)(q * 32) << 16), v);
+          tc_wait_ld();
+          u32 pk[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float f0 = __uint_as_float(v[2 * j]), f1 = __uint_as_float(v[2 * j + 1]);
+            if (P.bias) {
+              f0 += ld_bias<BF16>(P.bias, (i64)seg * M + c0 + 2 * j);
+              f1 += ld_bias<BF16>(P.bias, (i64)seg * M + c0 + 2 * j + 1);
+            }
+            pk[j] = pack2<BF16>(f0, f1);
+          }
+          if (valid == TM) {
+            // staging layout == TMA SWIZZLE_128B box [64 cols x 128 rows]: row pitch 128 B, 16 B chunk ^ (row & 7)
+            const int h = c0 >> 6, chunk0 = (c0 & 63) >> 3;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int ch = (chunk0 + j) ^ (r & 7);
+              *reinterpret_cast<uint4*>(stage + h * (TM * 128) + r * 128 + ch * 16) =
+                  make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+            }
+          } else if (r < valid) {
+            uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(P.out) + ((row0 + r) * M + c0) * 2);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) dst[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+          }
+        }
+        // accumulator drained -> MMA warp may overwrite it
+        tc_fence_before();
+        mbar_arrive(T_EMPTY(acc));
+        if (valid == TM) {
+          fence_proxy_async();
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (et == 0) {
+            for (int h = 0; h < NH; ++h) tma_store_2d(&map_o, base + off_o + h * (TM * 128), h * 64, (int)row0);
+            tma_store_commit();
+          }
+          store_pending = true;
+        }
+        acc ^= 1;
+      }
+      if (et == 0) tma_store_wait_all();
+    }
+  }
+
+  // ---- teardown
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// 2-D row-major [rows, cols] tensor of 16-bit elements, box [box_rows x 64 cols], 128 B swizzle
+int make_map(CUtensorMap* m, const void* ptr, i64 rows, i64 cols, int box_rows, bool bf16) {
+  EncodeTiledFn enc = get_encode();
+  PYGB_CHECK(enc != nullptr, PYGB200_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims,
+                   strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
+    return PYGB200_ERR_CUDA;
+  }
+  return PYGB200_OK;
+}
+
+size_t smem_needed(i64 K, i64 M, i64 B) {
+  return 1024 + (size_t)A_STAGES * TM * K * 2 + 2 * (size_t)K * M * 2 + (size_t)TM * M * 2 + (2 * A_STAGES + 8) * 8 + 16 +
+         (size_t)(B + 2) * 4;
+}
+
+}  // namespace
+
+bool tcgen05_supported(i64 N, i64 K, i64 M, i64 B, int dtype, const void* x, const void* w, const void* out) {
+  if (dtype != PYGB200_BF16 && dtype != PYGB200_F16) return false;
+  if (K < 64 || K > 256 || K % 64 != 0) return false;
+  if (M < 64 || M > 256 || M % 64 != 0) return false;
+  if (B < 1 || B > MAX_SEG || N < 1 || N >= ((i64)1 << 31) || B * K >= ((i64)1 << 31)) return false;
+  if (((uintptr_t)x | (uintptr_t)w | (uintptr_t)out) & 15) return false;
+  if (smem_needed(K, M, B) > 227 * 1024) return false;
+  return true;
+}
+
+int segment_matmul_tcgen05(const void* x, const i64* ptr_dev, const void* w, const void* bias, void* out, i64 N, i64 K,
+                           i64 M, i64 B, int dtype, cudaStream_t st) {
+  const bool bf16 = dtype == PYGB200_BF16;
+  CUtensorMap ma, mw, mo;
+  if (int e = make_map(&ma, x, N, K, TM, bf16)) return e;
+  if (int e = make_map(&mw, w, B * K, M, (int)K, bf16)) return e;
+  if (int e = make_map(&mo, out, N, M, TM, bf16)) return e;
+  SegParams P;
+  P.ptr = ptr_dev; P.bias = bias; P.out = out; P.N = N; P.K = (int)K; P.M = (int)M; P.B = (int)B;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const size_t smem = smem_needed(K, M, B);
+  i64 max_tiles = N / TM + B;
+  int grid = (int)(max_tiles < sms ? (max_tiles < 1 ? 1 : max_tiles) : sms);
+  void* tk = prof_begin(st);
+  if (bf16) {
+    PYGB_CUDA(cudaFuncSetAttribute(k_segment_matmul_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_segment_matmul_tc<true><<<grid, NTHREADS, smem, st>>>(ma, mw, mo, P);
+  } else {
+    PYGB_CUDA(cudaFuncSetAttribute(k_segment_matmul_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_segment_matmul_tc<false><<<grid, NTHREADS, smem, st>>>(ma, mw, mo, P);
+  }
+  prof_end(tk, "segment_matmul", st, N);
+  PYGB_LAUNCH_CHECK();
+  return PYGB200_OK;
+}
+
 }  // namespace pygb200

@@ -114,3 +114,38 @@ def test_segment_matmul_errors(lib):
         lib.ops.segment_matmul(x, torch.tensor([0, 5, 8]), w[:, :8])
     with pytest.raises((RuntimeError, NotImplementedError)):
         lib.ops.segment_matmul(x.cpu(), torch.tensor([0, 5, 8]), w.cpu())  # no CPU fallback
+
+
+@pytest.mark.parametrize('dtype', [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize('K,M', [(128, 128), (64, 64), (64, 128), (128, 64), (192, 64)])
+@pytest.mark.parametrize('with_bias', [False, True])
+def test_tcgen05_path(lib, dtype, K, M, with_bias):
+    """Shapes that take the tcgen05/TMA kernel (K, M multiples of 64): ragged segments incl. empty and
+    1-row ones, tiles that end mid-segment, more tiles than SMs."""
+    g = torch.Generator().manual_seed(K * 1000 + M)
+    lens = [0, 1, 127, 128, 129, 300, 0, 1000, 5, 4096, 77, 20000]
+    ptr = torch.tensor([0] + lens).cumsum(0)
+    N, B = int(ptr[-1]), len(lens)
+    x = torch.randn(N, K, generator=g).to(dtype)
+    w = (torch.randn(B, K, M, generator=g) / K ** 0.5).to(dtype)
+    b = torch.randn(B, M, generator=g).to(dtype) if with_bias else None
+    out = lib.ops.segment_matmul(x.to(DEV), ptr.to(DEV), w.to(DEV), bias=None if b is None else b.to(DEV)).cpu()
+    ref = torch.cat([x[ptr[i]:ptr[i + 1]].float() @ w[i].float() + (b[i].float() if with_bias else 0) for i in range(B)])
+    err = (out.float() - ref).norm() / ref.norm()
+    assert err <= 3e-3, float(err)   # one bf16 rounding of an fp32-accumulated result
+    assert torch.allclose(out.float(), ref, atol=3e-2, rtol=2e-2)
+
+
+def test_tcgen05_c3_shape_uniform_and_ragged(lib):
+    """BASELINE configs[2] geometry (scaled to N=2^17): uniform split and log-normal ragged split."""
+    N, K, M, B = 1 << 17, 128, 128, 64
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(N, K, generator=g).to(torch.bfloat16).to(DEV)
+    w = (torch.randn(B, K, M, generator=g) / K ** 0.5).to(torch.bfloat16).to(DEV)
+    for ptr in (torch.arange(0, N + 1, N // B), ragged_ptr(N, B, 100)):
+        out = lib.ops.segment_matmul(x, ptr.to(DEV), w)
+        for i in (0, 1, 17, 63):
+            a, b = int(ptr[i]), int(ptr[i + 1])
+            ref = x[a:b].float() @ w[i].float()
+            if b > a:
+                assert (out[a:b].float() - ref).norm() <= 3e-3 * ref.norm()
