@@ -108,20 +108,15 @@ __global__ void k_mt_init(u32* __restrict__ raw, i64* generated, const __grid_co
 
 constexpr int MT_WIN = 4096;  // circular shared-memory window (words)
 
-// Extends raw[] so that it covers every engine output needed for `*units_ptr` consumed units plus
-// the generation holding the final state.  One CTA; `KL` = recurrence unroll.
+// Extends raw[] up to (at least) raw index `target`, rounded up to a whole 624-word generation.
+// One CTA (640 threads: one word per thread per step); `KL` = recurrence unroll.
 template <int KL>
-__global__ void __launch_bounds__(640) k_mt_extend(u32* __restrict__ raw, i64* generated, const i64* units_ptr,
-                                                    i64 next0, i64 cap_words, int* error) {
+__global__ void __launch_bounds__(640) k_mt_extend_to(u32* __restrict__ raw, i64* generated, i64 target_in, i64 cap_words) {
   __shared__ u32 win[MT_WIN];
-  const i64 need = next0 + 256 * rng_blocks_for_units(*units_ptr);
-  i64 target = ((need + MT_N - 1) / MT_N) * MT_N;
+  i64 target = ((target_in + MT_N - 1) / MT_N) * MT_N;
+  if (target > cap_words) target = (cap_words / MT_N) * MT_N;
   i64 m = *generated;
   if (target <= m) return;
-  if (target > cap_words) {
-    if (threadIdx.x == 0) *error = 1;
-    return;
-  }
   constexpr int HIST = MT_N + MT_LAG * (KL - 1);
   const i64 h0 = m > HIST ? m - HIST : 0;
   for (i64 i = h0 + threadIdx.x; i < m; i += blockDim.x) win[i & (MT_WIN - 1)] = raw[i];

@@ -90,7 +90,7 @@ constexpr int SCAN_NT = 1024;
 // state buffer (device, i64 words); a pinned mirror is read by the host after the final sync
 enum {
   ST_CURSOR = 0,    // RNG units consumed so far (end of last scanned pass)
-  ST_GEN = 1,       // raw mt words generated
+  ST_SPARE = 1,
   ST_PASS_F = 2,    // frontier size of the running pass
   ST_PASS_E = 3,    // edges emitted by the running pass
   ST_PASS_BASE = 4, // offset of the running pass inside its relation's edge arrays
@@ -121,8 +121,12 @@ struct PassArgs {
   i64* mtile;      // per edge tile: count of firsts, then exclusive offset
   i64* st;
   int o_src_begin, o_src_end, o_dst_list, o_dst_ids, o_rel_edges, o_eph;
-  u32* raw; i64 next0; i64 raw_cap;
+  u32* raw; i64* gen; i64 out0; i64 raw_cap;   // mt19937 raw stream, #words generated, raw index of this call's output 0
   i64 fanout; int replace; int disjoint; int seed_mode;
+  // lookup of the PREVIOUS pass, deferred into this pass's k_count / the final kernel (null = none)
+  i64* lk_colv; const u64* lk_vals;
+  // end-of-hop bookkeeping folded into the last pass's k_mark (he_T == 0: not the last pass of its hop)
+  int he_T, he_L, he_hop, he_list, he_begin, he_end, he_nph;
 };
 
 // ------------------------------------------------------------------------------------- helpers
@@ -276,10 +280,9 @@ __device__ void scan_frontier_tiles(const PassArgs& a, i64 ntiles) {
 // mt19937 raw-stream extension by the calling block (blockDim.x == NT): same recurrence as
 // k_mt_extend but with NT threads per step (several words per thread).
 template <int KL>
-__device__ void mt_extend_block(u32* __restrict__ raw, i64* st, i64 next0, i64 cap_words, u32* win) {
-  const i64 need = next0 + 256 * rng_blocks_for_units(st[ST_CURSOR]);
+__device__ void mt_extend_block(u32* __restrict__ raw, i64* gen, i64 need, i64 cap_words, i64* st, u32* win) {
   const i64 target = ((need + MT_N - 1) / MT_N) * MT_N;
-  i64 m = st[ST_GEN];
+  i64 m = *gen;
   if (target <= m) return;
   if (target > cap_words) {
     if (threadIdx.x == 0) st[ST_ERROR] = 1;
@@ -308,7 +311,7 @@ __device__ void mt_extend_block(u32* __restrict__ raw, i64* st, i64 next0, i64 c
     __syncthreads();
     m += n;
   }
-  if (threadIdx.x == 0) st[ST_GEN] = m;
+  if (threadIdx.x == 0) *gen = m;
   __syncthreads();
 }
 
@@ -329,9 +332,18 @@ __device__ __forceinline__ bool last_block(i64* ticket) {
 }
 
 // ------------------------------------------------------------------------------------ kernels
+// local ids of the previous pass's edges (its k_assign has completed: kernel boundary)
+__device__ __forceinline__ void deferred_lookup(const PassArgs& a) {
+  if (a.lk_colv == nullptr) return;
+  const i64 E = a.st[ST_PASS_E], pbase = a.st[ST_PASS_BASE];
+  for (i64 p = (i64)blockIdx.x * NT + threadIdx.x; p < E; p += (i64)gridDim.x * NT)
+    a.lk_colv[pbase + p] = (i64)a.lk_vals[a.eslot[p]];
+}
+
 template <typename idx_t>
 __global__ void __launch_bounds__(NT) k_count(const PassArgs a) {
   __shared__ u32 s_win[MT_WIN];
+  deferred_lookup(a);  // must precede the ticket: the last block overwrites ST_PASS_E / ST_PASS_BASE
   const i64 begin = a.st[a.o_src_begin], end = a.st[a.o_src_end];
   const i64 F = end - begin;
   const i64 ntiles = ceil_div(F, NT);
@@ -369,7 +381,7 @@ __global__ void __launch_bounds__(NT) k_count(const PassArgs a) {
   if (last_block(&a.st[ST_TICKET_A])) {
     if (threadIdx.x == 0) a.st[ST_PASS_F] = F;
     scan_frontier_tiles(a, ntiles);
-    mt_extend_block<3>(a.raw, a.st, a.next0, a.raw_cap, s_win);
+    mt_extend_block<3>(a.raw, a.gen, a.out0 + 256 * rng_blocks_for_units(a.st[ST_CURSOR]), a.raw_cap, a.st, s_win);
   }
 }
 
@@ -379,7 +391,7 @@ __global__ void __launch_bounds__(NT) k_sample(const PassArgs a) {
   const i64 F = a.st[ST_PASS_F];
   const i64 begin = a.st[a.o_src_begin];
   const i64 pbase = a.st[ST_PASS_BASE];
-  const i64 out0 = a.next0;
+  const i64 out0 = a.out0;
   const idx_t* __restrict__ col = (const idx_t*)a.col;
   const u32* __restrict__ raw = a.raw;
   const int gl = threadIdx.x & (G - 1);
@@ -535,6 +547,14 @@ __global__ void __launch_bounds__(NT) k_mark(const PassArgs a) {
         a.st[a.o_dst_ids] += nnew;
       }
     }
+    __syncthreads();
+    // last pass of the hop: advance every type's frontier slice (neighbor_kernel.cpp:807-812)
+    for (int t = threadIdx.x; t < a.he_T; t += NT) {
+      const i64 n = a.st[a.he_list + t], e = a.st[a.he_end + t];
+      a.st[a.he_nph + t * (a.he_L + 1) + a.he_hop + 1] = n - e;
+      a.st[a.he_begin + t] = e;
+      a.st[a.he_end + t] = n;
+    }
   }
 }
 
@@ -587,18 +607,74 @@ __global__ void k_seed_end(i64* st, int t, int L, int o_list, int o_begin, int o
   st[o_nph + t * (L + 1)] = st[o_list + t];
 }
 
-// final engine state: generation holding the last consumed output (see mt19937.cuh)
-__global__ void k_finalize(i64* st, const u32* __restrict__ raw, i64 next0, int o_mt) {
-  const i64 blocks = rng_blocks_for_units(st[ST_CURSOR]);
-  const i64 q = next0 + 256 * blocks;
+// Last kernel of a run: deferred lookup of the last pass + (block 0) final engine state = the
+// generation holding the last consumed output (see mt19937.cuh); at least one 128-word block is
+// always consumed (rand_engine.h:28).
+__global__ void __launch_bounds__(NT) k_final(const PassArgs a, int o_mt) {
+  __shared__ u32 s_win[MT_WIN];
+  deferred_lookup(a);
+  if (blockIdx.x != 0) return;
+  const i64 blocks = rng_blocks_for_units(a.st[ST_CURSOR]);
+  const i64 q = a.out0 + 256 * blocks;
+  mt_extend_block<3>(a.raw, a.gen, q, a.raw_cap, a.st, s_win);
   const i64 g = (q - 1) / MT_N;
-  u32* out = reinterpret_cast<u32*>(st + o_mt);
-  for (int i = threadIdx.x; i < MT_N; i += blockDim.x) out[i] = raw[g * MT_N + i];
+  u32* out = reinterpret_cast<u32*>(a.st + o_mt);
+  for (int i = threadIdx.x; i < MT_N; i += blockDim.x) out[i] = __ldcg(&a.raw[g * MT_N + i]);
   if (threadIdx.x == 0) {
     const i64 nxt = q - g * MT_N;
-    st[ST_MT_NEXT] = nxt;
-    st[ST_MT_LEFT] = 625 - nxt;
-    st[ST_BLOCKS] = blocks;
+    a.st[ST_MT_NEXT] = nxt;
+    a.st[ST_MT_LEFT] = 625 - nxt;
+    a.st[ST_BLOCKS] = blocks;
+  }
+}
+
+// Seeds of one node type in ONE block (n <= SEED_FUSED_MAX): list, insert, first-occurrence ranks, ids.
+// Equivalent to k_seed + k_mark + k_assign + k_seed_end (neighbor_kernel.cpp:409-416, mapper.h:29-46).
+constexpr int SEED_NT = 1024;
+constexpr int SEED_FUSED_MAX = 16384;
+template <typename idx_t>
+__global__ void __launch_bounds__(SEED_NT) k_seed_fused(const PassArgs a, const idx_t* __restrict__ seeds, int n, i64 batch0,
+                                                         int L, int o_begin, int o_end, int o_nph) {
+  __shared__ int s_w[SEED_NT / 32];
+  __shared__ int s_carry;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < n; i += SEED_NT) {
+    const i64 v = (i64)seeds[i];
+    a.dst_nodes[i] = v;
+    if (a.disjoint) a.dst_batch[i] = batch0 + i;
+    const u32 s = table_insert(a.keys, a.mask, make_key(v, batch0 + i, a.disjoint));
+    atomicMin(&a.vals[s], POS_BASE + (u64)i);
+    a.eslot[i] = s;
+  }
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();   // block-scope: all atomicMin of this block are visible
+  for (int base = 0; base < n; base += SEED_NT) {
+    const int i = base + threadIdx.x;
+    u32 s = 0; int first = 0;
+    if (i < n) { s = a.eslot[i]; first = (a.vals[s] == POS_BASE + (u64)i) ? 1 : 0; }
+    int inc = first;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int o = __shfl_up_sync(0xffffffffu, inc, d);
+      if (lane >= d) inc += o;
+    }
+    if (lane == 31) s_w[wid] = inc;
+    __syncthreads();
+    int pre = 0, tot = 0;
+    for (int w = 0; w < SEED_NT / 32; ++w) { if (w < wid) pre += s_w[w]; tot += s_w[w]; }
+    const int c0 = s_carry;
+    if (i < n) a.dst_slot[i] = first ? s : NO_SLOT;
+    __syncthreads();   // every thread has read vals[] of this chunk before ranks overwrite them
+    if (first) a.vals[s] = (u64)(c0 + pre + inc - 1);
+    if (threadIdx.x == 0) s_carry = c0 + tot;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    a.st[a.o_dst_list] = n;        // every seed is listed, duplicates included
+    a.st[a.o_dst_ids] = s_carry;   // ids count distinct seeds only
+    a.st[o_begin] = 0;
+    a.st[o_end] = n;
+    a.st[o_nph] = n;
   }
 }
 
@@ -625,6 +701,16 @@ __global__ void __launch_bounds__(NT) k_rehash(const u64* __restrict__ old_keys,
 template <typename out_t>
 __global__ void __launch_bounds__(NT) k_export(const i64* __restrict__ src, out_t* __restrict__ dst, i64 n) {
   for (i64 i = (i64)blockIdx.x * NT + threadIdx.x; i < n; i += (i64)gridDim.x * NT) dst[i] = (out_t)src[i];
+}
+// row / col / edge_id of one relation in one launch (null dst = skip)
+template <typename out_t>
+__global__ void __launch_bounds__(NT) k_export3(const i64* __restrict__ s0, const i64* __restrict__ s1, const i64* __restrict__ s2,
+                                                 out_t* __restrict__ d0, out_t* __restrict__ d1, out_t* __restrict__ d2, i64 n) {
+  for (i64 i = (i64)blockIdx.x * NT + threadIdx.x; i < n; i += (i64)gridDim.x * NT) {
+    if (d0) d0[i] = (out_t)s0[i];
+    if (d1) d1[i] = (out_t)s1[i];
+    if (d2) d2[i] = (out_t)s2[i];
+  }
 }
 template <typename out_t>
 __global__ void __launch_bounds__(NT) k_export_pairs(const i64* __restrict__ batch, const i64* __restrict__ node,
@@ -670,8 +756,18 @@ struct pygb200_sampler {
   struct RelBuf { DevBuf row, colv, eid; i64 n_edges = 0; };
   std::vector<TypeBuf> types;
   std::vector<RelBuf> rels;
-  DevBuf eslot, erank, rec, tile_out, tile_func, tile_off, tile_pos, mtile, raw, st;
+  DevBuf eslot, erank, rec, tile_out, tile_func, tile_off, tile_pos, mtile, raw, st, gen;
   i64* st_host = nullptr;   // pinned mirror of the state buffer
+  // persistent mt19937 raw stream: survives between runs while torch's CPU generator is exactly where
+  // the previous run left it (the common case in a sampling loop) and is extended ahead of time on a
+  // side stream, so that generation stays off the critical path of the next run.
+  bool mt_valid = false;          // raw[] continues the stream of `mt_expected`
+  pygb200_mt19937 mt_expected;    // engine state written back by the previous run
+  i64 mt_q = 0;                   // raw index of the next output
+  i64 raw_cap_words = 0;
+  cudaStream_t mt_stream = nullptr;
+  cudaEvent_t mt_ready = nullptr; // pre-generation finished
+  bool mt_pending = false;
   size_t st_words = 0;
   bool disjoint = false;
   bool dirty = false;       // a run failed mid-way: tables must be wiped before reuse
@@ -710,8 +806,10 @@ extern "C" void pygb200_sampler_destroy(pygb200_sampler* s) {
   if (!s) return;
   for (auto& t : s->types) { t.nodes.release(); t.batch.release(); t.slot.release(); t.keys.release(); t.vals.release(); }
   for (auto& r : s->rels) { r.row.release(); r.colv.release(); r.eid.release(); }
+  if (s->mt_stream) { cudaStreamSynchronize(s->mt_stream); cudaStreamDestroy(s->mt_stream); }
+  if (s->mt_ready) cudaEventDestroy(s->mt_ready);
   DevBuf* all[] = {&s->eslot, &s->erank, &s->rec, &s->tile_out, &s->tile_func,
-                   &s->tile_off, &s->tile_pos, &s->mtile, &s->raw, &s->st};
+                   &s->tile_off, &s->tile_pos, &s->mtile, &s->raw, &s->st, &s->gen};
   for (auto* b : all) b->release();
   if (s->st_host) cudaFreeHost(s->st_host);
   delete s;
@@ -794,16 +892,18 @@ int ensure_edge_scratch(pygb200_sampler* s, i64 E, cudaStream_t st) {
 }
 
 template <typename idx_t>
-int launch_count(pygb200_sampler* s, const PassArgs& a, i64 F, cudaStream_t st) {
+int launch_count(pygb200_sampler* s, const PassArgs& a, i64 F, i64 E_prev, cudaStream_t st) {
+  // the grid also has to cover the deferred lookup of the previous pass (E_prev edges)
+  const int g = std::max(grid_for(F, NT, s->sm_count), a.lk_colv ? grid_for(E_prev, NT, s->sm_count) : 1);
   void* tk = prof_begin(st);
-  k_count<idx_t><<<grid_for(F, NT, s->sm_count), NT, 0, st>>>(a);
+  k_count<idx_t><<<g, NT, 0, st>>>(a);
   prof_end(tk, "count", st, F);
   PYGB_LAUNCH_CHECK();
   return PYGB200_OK;
 }
 
 template <typename idx_t>
-int launch_rest(pygb200_sampler* s, const PassArgs& a, i64 F, i64 E, cudaStream_t st) {
+int launch_rest(pygb200_sampler* s, const PassArgs& a, i64 F, i64 E, bool lookup_now, cudaStream_t st) {
   const i64 k = a.fanout;
   const int G = (k < 0 || k > 16) ? 32 : (k > 8 ? 16 : (k > 4 ? 8 : 4));
   const int gs = grid_for(F, NT / G, s->sm_count);
@@ -824,10 +924,12 @@ int launch_rest(pygb200_sampler* s, const PassArgs& a, i64 F, i64 E, cudaStream_
   k_assign<<<grid_for(E, NT, s->sm_count), NT, 0, st>>>(a);
   prof_end(tk, "assign", st, E);
   PYGB_LAUNCH_CHECK();
-  tk = prof_begin(st);
-  k_lookup<<<grid_for(E, NT, s->sm_count), NT, 0, st>>>(a);
-  prof_end(tk, "lookup", st, E);
-  PYGB_LAUNCH_CHECK();
+  if (lookup_now) {
+    tk = prof_begin(st);
+    k_lookup<<<grid_for(E, NT, s->sm_count), NT, 0, st>>>(a);
+    prof_end(tk, "lookup", st, E);
+    PYGB_LAUNCH_CHECK();
+  }
   return PYGB200_OK;
 }
 
@@ -852,7 +954,6 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
   }
   if (disjoint) PYGB_CHECK(total_seeds < ((i64)1 << 23), PYGB200_ERR_UNSUPPORTED,
                            "disjoint sampling supports < 2^23 seeds and node ids < 2^40 on this path");
-  const i64 next0 = mt_next0(mt->left);
   PYGB_CHECK(mt->left >= 1 && mt->left <= MT_N && mt->next >= 0 && mt->next <= MT_N, PYGB200_ERR_ARG,
              "invalid mt19937 state");
 
@@ -904,15 +1005,19 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
     s->st_words = lay.words;
   }
   if (int e = s->st.ensure(lay.words * 8, 0, st)) return e;
-  if (s->dirty) {  // previous run aborted: wipe tables
+  if (int e = s->gen.ensure(64, 0, st)) return e;
+  if (!s->mt_stream) {
+    PYGB_CUDA(cudaStreamCreateWithFlags(&s->mt_stream, cudaStreamNonBlocking));
+    PYGB_CUDA(cudaEventCreateWithFlags(&s->mt_ready, cudaEventDisableTiming));
+  }
+  if (s->dirty) {  // previous run aborted: wipe tables, forget the stream
     for (auto& tb : s->types) if (tb.tcap) {
       PYGB_CUDA(cudaMemsetAsync(tb.keys.p, 0xff, tb.tcap * 8, st));
       PYGB_CUDA(cudaMemsetAsync(tb.vals.p, 0xff, tb.tcap * 8, st));
     }
-    s->dirty = false;
+    s->mt_valid = false;
   }
   s->dirty = true;
-  i64 raw_cap;
   if (!synced) {
     for (int t = 0; t < T; ++t) {
       if (int e = ensure_type(s, t, node_cap[t], 0, disjoint, st)) return e;
@@ -921,7 +1026,6 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
     for (int r = 0; r < R; ++r) if (int e = ensure_rel(s, r, rel_cap[r], 0, st)) return e;
     if (int e = ensure_frontier_scratch(s, max_F, st)) return e;
     if (int e = ensure_edge_scratch(s, max_E, st)) return e;
-    raw_cap = next0 + 256 * (rng_blocks_for_units(draw_units) + 1) + 2 * MT_N;
   } else {
     for (int t = 0; t < T; ++t) {
       if (int e = ensure_type(s, t, std::max<i64>(n_seeds[t], 1), 0, disjoint, st)) return e;
@@ -929,19 +1033,39 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
     }
     for (int r = 0; r < R; ++r) if (int e = ensure_rel(s, r, 1, 0, st)) return e;
     if (int e = ensure_edge_scratch(s, total_seeds, st)) return e;
-    raw_cap = next0 + 256 * 2 + 2 * MT_N;
   }
-  if (int e = s->raw.ensure((size_t)raw_cap * 4, 0, st)) return e;
 
-  // ---- init: zero state, upload the engine state
-  i64* dst = s->st.as<i64>();
-  PYGB_CUDA(cudaMemsetAsync(dst, 0, lay.words * 8, st));
-  {
+  // ---- mt19937 raw stream: continue the persistent one or (re)start from the caller's engine state
+  if (s->mt_pending) {  // pre-generation of the previous run must be complete before anything touches raw/gen
+    PYGB_CUDA(cudaStreamWaitEvent(st, s->mt_ready, 0));
+    s->mt_pending = false;
+  }
+  // outputs this run may consume (bounded mode), rounded to whole blocks, plus the final-state generation
+  const i64 run_outputs = synced ? 256 * 2 : 256 * (rng_blocks_for_units(draw_units) + 1);
+  const i64 min_cap = (i64)MT_N + run_outputs + 3 * MT_N;
+  i64 out0;
+  bool cont = s->mt_valid && memcmp(&s->mt_expected, mt, sizeof(*mt)) == 0 &&
+              s->mt_q + run_outputs + 2 * MT_N <= s->raw_cap_words;
+  if (!cont) {
+    const i64 want = std::max<i64>(min_cap, (i64)1 << 23);  // 32 MB of raw words: ~100 runs of C2 between restarts
+    if (want > s->raw_cap_words) {
+      if (int e = s->raw.ensure((size_t)want * 4, 0, st)) return e;
+      s->raw_cap_words = want;
+    }
     MTPodParam pod;
     memcpy(pod.state, mt->state, sizeof(pod.state));
-    k_mt_init<<<1, NT, 0, st>>>(s->raw.as<u32>(), dst + ST_GEN, pod);
+    k_mt_init<<<1, NT, 0, st>>>(s->raw.as<u32>(), s->gen.as<i64>(), pod);
     PYGB_LAUNCH_CHECK();
+    out0 = mt_next0(mt->left);
+  } else {
+    out0 = s->mt_q;
   }
+  s->mt_valid = false;  // until this run completes
+  i64 raw_cap = s->raw_cap_words;
+
+  // ---- init: zero state
+  i64* dst = s->st.as<i64>();
+  PYGB_CUDA(cudaMemsetAsync(dst, 0, lay.words * 8, st));
   auto make_args = [&](int src_t, int dst_t, int rel) {
     PassArgs a;
     memset(&a, 0, sizeof(a));
@@ -960,7 +1084,7 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
     a.st = dst;
     a.o_src_begin = lay.o_begin + (src_t >= 0 ? src_t : 0); a.o_src_end = lay.o_end + (src_t >= 0 ? src_t : 0);
     a.o_dst_list = lay.o_list + dst_t; a.o_dst_ids = lay.o_ids + dst_t;
-    a.raw = s->raw.as<u32>(); a.next0 = next0; a.raw_cap = raw_cap;
+    a.raw = s->raw.as<u32>(); a.gen = s->gen.as<i64>(); a.out0 = out0; a.raw_cap = raw_cap;
     a.replace = replace; a.disjoint = disjoint;
     return a;
   };
@@ -973,9 +1097,15 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
   // ---- seeds (neighbor_kernel.cpp:409-416, :669-704)
   i64 batch0 = 0;
   for (int t = 0; t < T; ++t) {
-    if (n_seeds[t] > 0) {
-      PassArgs a = make_args(-1, t, -1);
-      a.seed_mode = 1;
+    PassArgs a = make_args(-1, t, -1);
+    a.seed_mode = 1;
+    if (n_seeds[t] > 0 && n_seeds[t] <= SEED_FUSED_MAX) {
+      if (idx32) k_seed_fused<int32_t><<<1, SEED_NT, 0, st>>>(a, (const int32_t*)seeds[t], (int)n_seeds[t], batch0, L,
+                                                              lay.o_begin + t, lay.o_end + t, lay.o_nph + t * (L + 1));
+      else k_seed_fused<int64_t><<<1, SEED_NT, 0, st>>>(a, (const int64_t*)seeds[t], (int)n_seeds[t], batch0, L,
+                                                        lay.o_begin + t, lay.o_end + t, lay.o_nph + t * (L + 1));
+      PYGB_LAUNCH_CHECK();
+    } else if (n_seeds[t] > 0) {
       const int g = grid_for(n_seeds[t], NT, s->sm_count);
       if (idx32) k_seed<int32_t><<<g, NT, 0, st>>>(a, (const int32_t*)seeds[t], n_seeds[t], batch0);
       else k_seed<int64_t><<<g, NT, 0, st>>>(a, (const int64_t*)seeds[t], n_seeds[t], batch0);
@@ -984,27 +1114,47 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
       PYGB_LAUNCH_CHECK();
       k_assign<<<g, NT, 0, st>>>(a);
       PYGB_LAUNCH_CHECK();
-      if (disjoint) batch0 += n_seeds[t];
-    }
-    k_seed_end<<<1, 1, 0, st>>>(dst, t, L, lay.o_list, lay.o_begin, lay.o_end, lay.o_nph);
-    PYGB_LAUNCH_CHECK();
+      k_seed_end<<<1, 1, 0, st>>>(dst, t, L, lay.o_list, lay.o_begin, lay.o_end, lay.o_nph);
+      PYGB_LAUNCH_CHECK();
+    }  // n == 0: the zeroed state already says "empty list, empty slice"
+    if (disjoint) batch0 += n_seeds[t];
   }
 
-  // ---- hops
+  // ---- hops.  Bounded mode defers every pass's lookup into the next k_count / the final kernel.
+  i64* lk_colv = nullptr; const u64* lk_vals = nullptr; i64 lk_E = 0;
   for (int h = 0; h < L; ++h) {
     if (synced) if (int e = read_state()) return e;  // actual frontier slices of this hop
+    // last pass of this hop that will actually be launched (it also does the end-of-hop bookkeeping)
+    int last_r = -1;
+    for (int r = 0; r < R; ++r) {
+      const i64 k = num_neighbors[(size_t)r * L + h];
+      if (k == 0) continue;
+      if (!synced && (fb[(size_t)rels[r].src_type * (L + 1) + h] == 0 || eb[(size_t)r * L + h] == 0)) continue;
+      if (synced && s->st_host[lay.o_end + rels[r].src_type] - s->st_host[lay.o_begin + rels[r].src_type] == 0) continue;
+      last_r = r;
+    }
+    bool hop_closed = false;
     for (int r = 0; r < R; ++r) {
       const i64 k = num_neighbors[(size_t)r * L + h];
       const int src_t = rels[r].src_type, dst_t = rels[r].dst_type;
       if (k == 0) continue;  // nothing emitted, no RNG consumed (neighbor_kernel.cpp:67-68)
+      auto with_hop_end = [&](PassArgs& a) {
+        if (r != last_r) return;
+        a.he_T = T; a.he_L = L; a.he_hop = h; a.he_list = lay.o_list; a.he_begin = lay.o_begin; a.he_end = lay.o_end;
+        a.he_nph = lay.o_nph;
+      };
       if (!synced) {
         const i64 Fb = fb[(size_t)src_t * (L + 1) + h], Eb = eb[(size_t)r * L + h];
         if (Fb == 0 || Eb == 0) continue;
         PassArgs a = make_args(src_t, dst_t, r);
         a.fanout = k;
         a.o_eph = lay.o_eph + r * L + h;
-        if (int e = idx32 ? launch_count<int32_t>(s, a, Fb, st) : launch_count<int64_t>(s, a, Fb, st)) return e;
-        if (int e = idx32 ? launch_rest<int32_t>(s, a, Fb, Eb, st) : launch_rest<int64_t>(s, a, Fb, Eb, st)) return e;
+        a.lk_colv = lk_colv; a.lk_vals = lk_vals;
+        with_hop_end(a);
+        if (int e = idx32 ? launch_count<int32_t>(s, a, Fb, lk_E, st) : launch_count<int64_t>(s, a, Fb, lk_E, st)) return e;
+        if (int e = idx32 ? launch_rest<int32_t>(s, a, Fb, Eb, false, st) : launch_rest<int64_t>(s, a, Fb, Eb, false, st)) return e;
+        lk_colv = a.colv; lk_vals = a.vals; lk_E = Eb;
+        if (r == last_r) hop_closed = true;
       } else {
         const i64 F = s->st_host[lay.o_end + src_t] - s->st_host[lay.o_begin + src_t];
         if (F == 0) continue;
@@ -1012,19 +1162,22 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
         if (k > 0) {  // draws possible: make sure the raw stream buffer can hold this pass
           const i64 upu = rels[r].num_edges < 65536 ? 1 : (rels[r].num_edges < ((i64)1 << 32) ? 3 : 7);
           if (int e = read_state()) return e;
-          const i64 need = next0 + 256 * (rng_blocks_for_units(s->st_host[ST_CURSOR] + sat_mul(sat_mul(F, k), upu)) + 1) + 2 * MT_N;
+          const i64 need = out0 + 256 * (rng_blocks_for_units(s->st_host[ST_CURSOR] + sat_mul(sat_mul(F, k), upu)) + 1) + 3 * MT_N;
           if (need > raw_cap) {
-            if (int e = s->raw.ensure((size_t)need * 4, (size_t)s->st_host[ST_GEN] * 4, st)) return e;
-            raw_cap = need;
+            i64 gen_now = 0;
+            PYGB_CUDA(cudaMemcpyAsync(&gen_now, s->gen.p, 8, cudaMemcpyDeviceToHost, st));
+            PYGB_CUDA(cudaStreamSynchronize(st));
+            if (int e = s->raw.ensure((size_t)need * 4, (size_t)gen_now * 4, st)) return e;
+            raw_cap = need; s->raw_cap_words = need;
           }
         }
         PassArgs a = make_args(src_t, dst_t, r);
         a.fanout = k;
         a.o_eph = lay.o_eph + r * L + h;
-        if (int e = idx32 ? launch_count<int32_t>(s, a, F, st) : launch_count<int64_t>(s, a, F, st)) return e;
+        if (int e = idx32 ? launch_count<int32_t>(s, a, F, 0, st) : launch_count<int64_t>(s, a, F, 0, st)) return e;
         if (int e = read_state()) return e;
         const i64 E = s->st_host[ST_PASS_E];
-        if (E == 0) continue;
+        if (E == 0) continue;  // (a hop whose last pass emits nothing is closed by the standalone kernel below)
         const i64 rel_before = s->st_host[ST_PASS_BASE], list_now = s->st_host[lay.o_list + dst_t];
         if (int e = ensure_rel(s, r, rel_before + E, rel_before, st)) return e;
         if (int e = ensure_edge_scratch(s, E, st)) return e;
@@ -1033,19 +1186,24 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
         a = make_args(src_t, dst_t, r);  // pointers may have moved
         a.fanout = k;
         a.o_eph = lay.o_eph + r * L + h;
-        if (int e = idx32 ? launch_rest<int32_t>(s, a, F, E, st) : launch_rest<int64_t>(s, a, F, E, st)) return e;
+        with_hop_end(a);
+        if (int e = idx32 ? launch_rest<int32_t>(s, a, F, E, true, st) : launch_rest<int64_t>(s, a, F, E, true, st)) return e;
+        if (r == last_r) hop_closed = true;
       }
     }
-    k_hop_end<<<1, 1024, 0, st>>>(dst, T, L, h, lay.o_list, lay.o_begin, lay.o_end, lay.o_nph);
-    PYGB_LAUNCH_CHECK();
+    if (!hop_closed) {
+      k_hop_end<<<1, 1024, 0, st>>>(dst, T, L, h, lay.o_list, lay.o_begin, lay.o_end, lay.o_nph);
+      PYGB_LAUNCH_CHECK();
+    }
   }
 
-  // ---- final engine state (at least one 128-word block is always consumed), counts to the host
-  k_mt_extend<3><<<1, 640, 0, st>>>(s->raw.as<u32>(), dst + ST_GEN, dst + ST_CURSOR, next0, raw_cap,
-                                    reinterpret_cast<int*>(dst + ST_ERROR));
-  PYGB_LAUNCH_CHECK();
-  k_finalize<<<1, NT, 0, st>>>(dst, s->raw.as<u32>(), next0, lay.o_mt);
-  PYGB_LAUNCH_CHECK();
+  // ---- final kernel (deferred lookup of the last pass + engine state), counts to the host
+  {
+    PassArgs a = make_args(-1, 0, -1);
+    a.lk_colv = lk_colv; a.lk_vals = lk_vals;
+    k_final<<<lk_colv ? grid_for(lk_E, NT, s->sm_count) : 1, NT, 0, st>>>(a, lay.o_mt);
+    PYGB_LAUNCH_CHECK();
+  }
   PYGB_CUDA(cudaMemcpyAsync(s->st_host, dst, lay.words * 8, cudaMemcpyDeviceToHost, st));
   // table cleanup is stream-ordered after the copy; the host does not wait for it
   cudaEvent_t copied;
@@ -1077,6 +1235,19 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
   memcpy(mt->state, hs + lay.o_mt, sizeof(mt->state));
   mt->next = (int32_t)hs[ST_MT_NEXT];
   mt->left = (int32_t)hs[ST_MT_LEFT];
+  // the stream persists: remember where it is and pre-generate what a run like this one will need,
+  // on the side stream (one CTA, overlaps the caller's work and the next run's first kernels)
+  s->mt_expected = *mt;
+  s->mt_q = out0 + 256 * hs[ST_BLOCKS];
+  s->mt_valid = true;
+  {
+    const i64 target = std::min<i64>(s->raw_cap_words - 2 * MT_N, s->mt_q + run_outputs + MT_N);
+    if (target > s->mt_q) {
+      k_mt_extend_to<3><<<1, 640, 0, s->mt_stream>>>(s->raw.as<u32>(), s->gen.as<i64>(), target, s->raw_cap_words);
+      count_launch();
+      if (cudaGetLastError() == cudaSuccess && cudaEventRecord(s->mt_ready, s->mt_stream) == cudaSuccess) s->mt_pending = true;
+    }
+  }
   return PYGB200_OK;
 }
 
@@ -1102,17 +1273,10 @@ extern "C" int pygb200_sampler_export_edges(pygb200_sampler* s, int32_t rel, voi
   const i64 n = s->rels[rel].n_edges;
   if (n == 0) return PYGB200_OK;
   const int g = grid_for(n, NT, s->sm_count);
-  const i64* srcs[3] = {s->rels[rel].row.as<i64>(), s->rels[rel].colv.as<i64>(), s->rels[rel].eid.as<i64>()};
-  void* dsts[3] = {row_out, col_out, edge_id_out};
-  for (int i = 0; i < 3; ++i) {
-    if (!dsts[i]) continue;
-    if (index32) {
-      k_export<int32_t><<<g, NT, 0, st>>>(srcs[i], (int32_t*)dsts[i], n);
-      PYGB_LAUNCH_CHECK();
-    } else {
-      PYGB_CUDA(cudaMemcpyAsync(dsts[i], srcs[i], (size_t)n * 8, cudaMemcpyDeviceToDevice, st));
-    }
-  }
+  const i64 *s0 = s->rels[rel].row.as<i64>(), *s1 = s->rels[rel].colv.as<i64>(), *s2 = s->rels[rel].eid.as<i64>();
+  if (index32) k_export3<int32_t><<<g, NT, 0, st>>>(s0, s1, s2, (int32_t*)row_out, (int32_t*)col_out, (int32_t*)edge_id_out, n);
+  else k_export3<int64_t><<<g, NT, 0, st>>>(s0, s1, s2, (int64_t*)row_out, (int64_t*)col_out, (int64_t*)edge_id_out, n);
+  PYGB_LAUNCH_CHECK();
   return PYGB200_OK;
 }
 
