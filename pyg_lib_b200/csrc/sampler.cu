@@ -17,6 +17,7 @@
 //   k_assign  new local ids = ids_base + rank, appended to the dst type's node list.
 //   k_lookup  every edge reads its final local id.
 // Host work per call: bounds, launches, ONE stream sync at the end (the API returns host counts).
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -85,7 +86,6 @@ constexpr int ETILE = 1024;          // edges per mark/assign tile (NT x 4)
 constexpr u64 EMPTY = ~0ull;
 constexpr u64 POS_BASE = 1ull << 62; // vals >= POS_BASE are flat positions of the running pass
 constexpr u32 NO_SLOT = 0xffffffffu;
-constexpr int SCAN_NT = 1024;
 
 // state buffer (device, i64 words); a pinned mirror is read by the host after the final sync
 enum {
@@ -1047,7 +1047,8 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
   bool cont = s->mt_valid && memcmp(&s->mt_expected, mt, sizeof(*mt)) == 0 &&
               s->mt_q + run_outputs + 2 * MT_N <= s->raw_cap_words;
   if (!cont) {
-    const i64 want = std::max<i64>(min_cap, (i64)1 << 23);  // 32 MB of raw words: ~100 runs of C2 between restarts
+    static const i64 pref_cap = [] { const char* e = getenv("PYGB200_MT_CAP_WORDS"); return e ? (i64)atoll(e) : (i64)1 << 23; }();
+    const i64 want = std::max<i64>(min_cap, pref_cap);  // default 32 MB of raw words: ~100 runs of C2 between restarts
     if (want > s->raw_cap_words) {
       if (int e = s->raw.ensure((size_t)want * 4, 0, st)) return e;
       s->raw_cap_words = want;

@@ -193,3 +193,63 @@ def test_c_abi_direct(lib):
     assert mt.left == omt.left and mt.next == omt.next
     assert (np.ctypeslib.as_array(mt.state) == np.ctypeslib.as_array(omt.state)).all()
     abi.pygb200_sampler_destroy(h)
+
+
+def test_rng_stream_persistence_and_restart(lib):
+    """The device keeps the mt19937 stream between calls.  Interleave calls with foreign draws from the
+    CPU generator (forces a restart from the new engine state)."""
+    rowptr, col = random_csr(5000, 20, 9)
+    d = [rowptr.to(DEV), col.to(DEV)]
+    perm = torch.randperm(5000, generator=torch.Generator().manual_seed(4))
+    torch.manual_seed(99)
+    exp = []
+    for i in range(12):
+        if i in (3, 7):
+            torch.rand(5)  # somebody else consumes the default CPU generator
+        exp.append(O.neighbor_sample(rowptr, col, perm[i * 64:(i + 1) * 64], [12, 6]))
+    s_exp = _rng_prefix()
+    torch.manual_seed(99)
+    for i in range(12):
+        if i in (3, 7):
+            torch.rand(5)
+        _cmp(lib.sampler.neighbor_sample(d[0], d[1], perm[i * 64:(i + 1) * 64].to(DEV), [12, 6]), exp[i])
+    assert np.array_equal(_rng_prefix(), s_exp)
+
+
+def test_rng_small_cap_subprocess():
+    """Same call loop in a child process whose raw-stream buffer is tiny, so the stream restarts from
+    the host engine state every few calls."""
+    import os
+    import subprocess
+    import sys
+    code = r"""
+import sys, os, torch
+sys.path.insert(0, os.getcwd()); sys.path.insert(0, os.path.join(os.getcwd(), 'tests'))
+import pyg_lib_b200 as P
+from graphs import random_csr
+from oracle import oracle as O
+rowptr, col = random_csr(5000, 20, 9)
+perm = torch.randperm(5000, generator=torch.Generator().manual_seed(4))
+torch.manual_seed(5)
+exp = [O.neighbor_sample(rowptr, col, perm[i*64:(i+1)*64], [12, 6]) for i in range(40)]
+torch.manual_seed(5)
+r, c = rowptr.cuda(), col.cuda()
+for i in range(40):
+    out = P.sampler.neighbor_sample(r, c, perm[i*64:(i+1)*64].cuda(), [12, 6])
+    assert all(torch.equal(a.cpu(), b) for a, b in zip(out[:4], exp[i][:4])), i
+print('OK')
+"""
+    env = dict(os.environ, PYGB200_MT_CAP_WORDS='20000')
+    out = subprocess.run([sys.executable, '-c', code], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True,
+                         timeout=300, cwd=osp.dirname(osp.dirname(osp.abspath(__file__))))
+    assert out.returncode == 0 and 'OK' in out.stdout, out.stderr[-2000:]
+
+
+def test_many_seeds_multi_kernel_seed_path(lib):
+    """> 16384 seeds take the multi-kernel seed path; duplicates included."""
+    rowptr, col = random_csr(50000, 8, 12)
+    seed = torch.randint(0, 50000, (40000,), generator=torch.Generator().manual_seed(8))
+    torch.manual_seed(2)
+    exp = O.neighbor_sample(rowptr, col, seed, [3, 2])
+    torch.manual_seed(2)
+    _cmp(lib.sampler.neighbor_sample(rowptr.to(DEV), col.to(DEV), seed.to(DEV), [3, 2]), exp)
