@@ -94,7 +94,7 @@ def reference_arm(a):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    workers = max(1, min(cores, 64))
+    workers = max(1, cores)  # every host thread: one single-threaded worker process per core (how PyG deploys it)
     per_step_calls = 2  # each "step" = a bounded sample: `workers` processes x 2 calls of 1024 seeds
     total_calls = per_step_calls * (a.steps + a.warmup)
     total_calls = max(2, min(total_calls, 40))  # keep the whole run within a few minutes

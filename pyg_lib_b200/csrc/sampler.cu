@@ -764,10 +764,14 @@ struct pygb200_sampler {
   bool mt_valid = false;          // raw[] continues the stream of `mt_expected`
   pygb200_mt19937 mt_expected;    // engine state written back by the previous run
   i64 mt_q = 0;                   // raw index of the next output
+  i64 mt_gen_known = 0;           // raw words known (to the host) to be generated and visible to the main stream
   i64 raw_cap_words = 0;
   cudaStream_t mt_stream = nullptr;
-  cudaEvent_t mt_ready = nullptr; // pre-generation finished
-  bool mt_pending = false;
+  // the last two pre-generation launches (side stream, in launch order): event + raw index they cover
+  cudaEvent_t mt_ev[2] = {nullptr, nullptr};
+  i64 mt_ev_target[2] = {0, 0};
+  bool mt_ev_pending[2] = {false, false};
+  int mt_ev_next = 0;
   size_t st_words = 0;
   bool disjoint = false;
   bool dirty = false;       // a run failed mid-way: tables must be wiped before reuse
@@ -807,7 +811,7 @@ extern "C" void pygb200_sampler_destroy(pygb200_sampler* s) {
   for (auto& t : s->types) { t.nodes.release(); t.batch.release(); t.slot.release(); t.keys.release(); t.vals.release(); }
   for (auto& r : s->rels) { r.row.release(); r.colv.release(); r.eid.release(); }
   if (s->mt_stream) { cudaStreamSynchronize(s->mt_stream); cudaStreamDestroy(s->mt_stream); }
-  if (s->mt_ready) cudaEventDestroy(s->mt_ready);
+  for (int i = 0; i < 2; ++i) if (s->mt_ev[i]) cudaEventDestroy(s->mt_ev[i]);
   DevBuf* all[] = {&s->eslot, &s->erank, &s->rec, &s->tile_out, &s->tile_func,
                    &s->tile_off, &s->tile_pos, &s->mtile, &s->raw, &s->st, &s->gen};
   for (auto* b : all) b->release();
@@ -1008,7 +1012,7 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
   if (int e = s->gen.ensure(64, 0, st)) return e;
   if (!s->mt_stream) {
     PYGB_CUDA(cudaStreamCreateWithFlags(&s->mt_stream, cudaStreamNonBlocking));
-    PYGB_CUDA(cudaEventCreateWithFlags(&s->mt_ready, cudaEventDisableTiming));
+    for (int i = 0; i < 2; ++i) PYGB_CUDA(cudaEventCreateWithFlags(&s->mt_ev[i], cudaEventDisableTiming));
   }
   if (s->dirty) {  // previous run aborted: wipe tables, forget the stream
     for (auto& tb : s->types) if (tb.tcap) {
@@ -1035,20 +1039,49 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
     if (int e = ensure_edge_scratch(s, total_seeds, st)) return e;
   }
 
-  // ---- mt19937 raw stream: continue the persistent one or (re)start from the caller's engine state
-  if (s->mt_pending) {  // pre-generation of the previous run must be complete before anything touches raw/gen
-    PYGB_CUDA(cudaStreamWaitEvent(st, s->mt_ready, 0));
-    s->mt_pending = false;
-  }
-  // outputs this run may consume (bounded mode), rounded to whole blocks, plus the final-state generation
+  // ---- mt19937 raw stream: continue the persistent one or (re)start from the caller's engine state.
+  // Pre-generation runs TWO runs ahead on the side stream: the launch made at the end of run i-1 already
+  // covers run i+1, so in a steady loop this run only waits for an event that completed long ago while
+  // the launch made at the end of run i (for run i+2) overlaps run i+1.
   const i64 run_outputs = synced ? 256 * 2 : 256 * (rng_blocks_for_units(draw_units) + 1);
-  const i64 min_cap = (i64)MT_N + run_outputs + 3 * MT_N;
+  auto wait_all_pregen = [&]() -> int {
+    for (int i = 0; i < 2; ++i) if (s->mt_ev_pending[i]) { PYGB_CUDA(cudaStreamWaitEvent(st, s->mt_ev[i], 0)); s->mt_ev_pending[i] = false; }
+    return PYGB200_OK;
+  };
   i64 out0;
   bool cont = s->mt_valid && memcmp(&s->mt_expected, mt, sizeof(*mt)) == 0 &&
-              s->mt_q + run_outputs + 2 * MT_N <= s->raw_cap_words;
-  if (!cont) {
+              s->mt_q + 2 * run_outputs + 6 * MT_N <= s->raw_cap_words;
+  if (synced) {  // synced runs extend the stream from inside k_count: nothing may run beside them
+    if (int e = wait_all_pregen()) return e;
+    s->mt_gen_known = 0;
+  }
+  if (cont) {
+    out0 = s->mt_q;
+    const i64 need = out0 + run_outputs + MT_N;
+    // oldest pending launch that covers this run (mt_ev_next is the older slot)
+    const int older = s->mt_ev_next, newer = s->mt_ev_next ^ 1;
+    if (s->mt_gen_known >= need) {
+      // covered by a launch this stream has already waited for; newer launches keep running beside us
+    } else if (s->mt_ev_pending[older] && s->mt_ev_target[older] >= need) {
+      PYGB_CUDA(cudaStreamWaitEvent(st, s->mt_ev[older], 0));
+      s->mt_ev_pending[older] = false;
+      s->mt_gen_known = std::max(s->mt_gen_known, s->mt_ev_target[older]);
+    } else if (s->mt_ev_pending[newer] && s->mt_ev_target[newer] >= need) {
+      // same side stream: once the newer launch is complete so is the older one
+      PYGB_CUDA(cudaStreamWaitEvent(st, s->mt_ev[newer], 0));
+      s->mt_ev_pending[older] = s->mt_ev_pending[newer] = false;
+      s->mt_gen_known = std::max(s->mt_gen_known, s->mt_ev_target[newer]);
+    } else {
+      // not covered ahead of time (first continued run, or a run larger than the previous one): extend here
+      if (int e = wait_all_pregen()) return e;
+      k_mt_extend_to<3><<<1, 640, 0, st>>>(s->raw.as<u32>(), s->gen.as<i64>(), need, s->raw_cap_words);
+      PYGB_LAUNCH_CHECK();
+      s->mt_gen_known = need;
+    }
+  } else {
+    if (int e = wait_all_pregen()) return e;
     static const i64 pref_cap = [] { const char* e = getenv("PYGB200_MT_CAP_WORDS"); return e ? (i64)atoll(e) : (i64)1 << 23; }();
-    const i64 want = std::max<i64>(min_cap, pref_cap);  // default 32 MB of raw words: ~100 runs of C2 between restarts
+    const i64 want = std::max<i64>((i64)MT_N + 2 * run_outputs + 8 * MT_N, pref_cap);  // default 32 MB of raw words
     if (want > s->raw_cap_words) {
       if (int e = s->raw.ensure((size_t)want * 4, 0, st)) return e;
       s->raw_cap_words = want;
@@ -1058,8 +1091,12 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
     k_mt_init<<<1, NT, 0, st>>>(s->raw.as<u32>(), s->gen.as<i64>(), pod);
     PYGB_LAUNCH_CHECK();
     out0 = mt_next0(mt->left);
-  } else {
-    out0 = s->mt_q;
+    s->mt_gen_known = MT_N;
+    if (!synced) {  // cover this run's worst case up front so that no pass has to extend the stream itself
+      k_mt_extend_to<3><<<1, 640, 0, st>>>(s->raw.as<u32>(), s->gen.as<i64>(), out0 + run_outputs + MT_N, s->raw_cap_words);
+      PYGB_LAUNCH_CHECK();
+      s->mt_gen_known = out0 + run_outputs + MT_N;
+    }
   }
   s->mt_valid = false;  // until this run completes
   i64 raw_cap = s->raw_cap_words;
@@ -1241,12 +1278,19 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
   s->mt_expected = *mt;
   s->mt_q = out0 + 256 * hs[ST_BLOCKS];
   s->mt_valid = true;
-  {
-    const i64 target = std::min<i64>(s->raw_cap_words - 2 * MT_N, s->mt_q + run_outputs + MT_N);
-    if (target > s->mt_q) {
+  if (!synced) {
+    const i64 target = std::min<i64>(s->raw_cap_words - 2 * MT_N, s->mt_q + 2 * run_outputs + 2 * MT_N);
+    const int slot = s->mt_ev_next;
+    if (target > s->mt_q && !s->mt_ev_pending[slot]) {
+      // this run's kernels (which may extend the stream themselves) are done: the D2H copy we just waited
+      // for is ordered after k_final
       k_mt_extend_to<3><<<1, 640, 0, s->mt_stream>>>(s->raw.as<u32>(), s->gen.as<i64>(), target, s->raw_cap_words);
       count_launch();
-      if (cudaGetLastError() == cudaSuccess && cudaEventRecord(s->mt_ready, s->mt_stream) == cudaSuccess) s->mt_pending = true;
+      if (cudaGetLastError() == cudaSuccess && cudaEventRecord(s->mt_ev[slot], s->mt_stream) == cudaSuccess) {
+        s->mt_ev_pending[slot] = true;
+        s->mt_ev_target[slot] = target;
+        s->mt_ev_next = slot ^ 1;
+      }
     }
   }
   return PYGB200_OK;
