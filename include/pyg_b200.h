@@ -136,6 +136,30 @@ int pygb200_sampler_run(pygb200_sampler* s, int32_t T, int32_t R, int32_t L,
                         pygb200_mt19937* mt_inout, int64_t* nodes_per_hop, int64_t* edges_per_hop,
                         int64_t* n_nodes, int64_t* n_edges, void* stream);
 
+/* Frontier-sharded run for multi-GPU sampling of ONE batch (the reference's own split of
+ * the work is dist_neighbor_sample -> merge -> relabel, neighbor_kernel.cpp:296-303,957-978).
+ * Every rank holds the full CSR and calls this with identical arguments and identical engine state.
+ * Per pass each rank counts the whole frontier (edge offsets and bit-stream positions are global),
+ * draws only its contiguous slice of frontier nodes, and the callback all-gathers the drawn EDGE IDS
+ * in place:  on return buf[seg_begin[q] .. seg_begin[q+1]) must hold rank q's elements for every q
+ * (int64 elements, offsets relative to buf; seg_begin is a HOST array of world+1 entries; the call is
+ * made on `stream`'s timeline: enqueue the collective on / synchronise it with that stream).
+ * Dedup / relabel then run replicated, so every rank ends with the identical, reference-exact result.
+ * Restrictions: fan-outs >= 0, world <= 64. */
+typedef int (*pygb200_allgather_fn)(void* user, void* buf_dev, const int64_t* seg_begin, int32_t world,
+                                    void* stream);
+typedef struct {
+  int32_t rank, world;
+  pygb200_allgather_fn allgather;
+  void* user;
+} pygb200_shard;
+int pygb200_sampler_run_sharded(pygb200_sampler* s, int32_t T, int32_t R, int32_t L,
+                                const pygb200_relation* rels_host, const void* const* seeds,
+                                const int64_t* n_seeds, const int64_t* num_neighbors, unsigned flags,
+                                pygb200_mt19937* mt_inout, int64_t* nodes_per_hop,
+                                int64_t* edges_per_hop, int64_t* n_nodes, int64_t* n_edges, void* stream,
+                                const pygb200_shard* shard);
+
 /* Asynchronous copies (cast to int32 when index32 != 0) of the last run's results into caller
  * buffers of exactly n_edges[r] / n_nodes[t] elements.  row = local index of the source (frontier)
  * node, col = local index of the sampled neighbour, edge_id = position in the relation's `col`

@@ -127,6 +127,9 @@ struct PassArgs {
   i64* lk_colv; const u64* lk_vals;
   // end-of-hop bookkeeping folded into the last pass's k_mark (he_T == 0: not the last pass of its hop)
   int he_T, he_L, he_hop, he_list, he_begin, he_end, he_nph;
+  // frontier sharding (multi-GPU): phase 0 = normal; 1 = draw only, frontier nodes [shard_lo, shard_hi),
+  // writes edge ids; 2 = expand ALL nodes from the (all-gathered) edge ids: gather col, rows, hash insert
+  int phase; i64 shard_lo, shard_hi;
 };
 
 // ------------------------------------------------------------------------------------- helpers
@@ -397,7 +400,9 @@ __global__ void __launch_bounds__(NT) k_sample(const PassArgs a) {
   const int gl = threadIdx.x & (G - 1);
   const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) & ~(G - 1)));
   const i64 groups_per_grid = (i64)gridDim.x * (NT / G);
-  for (i64 i = (i64)blockIdx.x * (NT / G) + threadIdx.x / G; i < F; i += groups_per_grid) {
+  const i64 i_lo = a.phase == 1 ? a.shard_lo : 0;
+  const i64 i_hi = a.phase == 1 ? (a.shard_hi < F ? a.shard_hi : F) : F;
+  for (i64 i = i_lo + (i64)blockIdx.x * (NT / G) + threadIdx.x / G; i < i_hi; i += groups_per_grid) {
     const NodeRec r = a.rec[i];
     const i64 tile = i / NT;
     const i64 tpos = a.tile_pos[tile];
@@ -410,6 +415,7 @@ __global__ void __launch_bounds__(NT) k_sample(const PassArgs a) {
     const int mode = classify(deg, k, a.replace, &n_out, &n16, &n32, &n64);
     auto emit = [&](i64 j, i64 e) {
       const i64 p = off + j;
+      if (a.phase == 1) { a.eid[pbase + p] = e; return; }
       const i64 d = (i64)col[e];
       a.row[pbase + p] = src_pos;
       a.eid[pbase + p] = e;
@@ -418,7 +424,9 @@ __global__ void __launch_bounds__(NT) k_sample(const PassArgs a) {
       atomicMin(&a.vals[s], POS_BASE + (u64)p);
       a.eslot[p] = s;
     };
-    if (mode == MODE_FULL) {
+    if (a.phase == 2) {
+      for (i64 j = gl; j < n_out; j += G) emit(j, a.eid[pbase + off + j]);
+    } else if (mode == MODE_FULL) {
       for (i64 j = gl; j < deg; j += G) emit(j, rs + j);
     } else if (mode == MODE_REPLACE) {
       const int wu = rng_width_units((u64)deg);
@@ -451,6 +459,15 @@ __global__ void __launch_bounds__(NT) k_sample(const PassArgs a) {
       }
     }
   }
+}
+
+// flat edge offset of the first frontier node of every shard (frontier split evenly by node index)
+__global__ void k_shard_bounds(const PassArgs a, int W, int o_shard) {
+  const int q = threadIdx.x;
+  if (q > W) return;
+  const i64 F = a.st[ST_PASS_F], E = a.st[ST_PASS_E];
+  const i64 i = (i64)((__int128)F * q / W);
+  a.st[o_shard + q] = (i < F) ? a.tile_off[i / NT] + a.rec[i].loc_off : E;
 }
 
 // seeds: list them, insert them (first-occurrence order == seed order)
@@ -821,13 +838,15 @@ extern "C" void pygb200_sampler_destroy(pygb200_sampler* s) {
 
 namespace {
 
-struct Layout { int o_list, o_ids, o_begin, o_end, o_rel, o_nph, o_eph, o_mt; size_t words; };
+constexpr int MAX_SHARDS = 64;
+struct Layout { int o_list, o_ids, o_begin, o_end, o_rel, o_nph, o_eph, o_mt, o_shard; size_t words; };
 Layout make_layout(int T, int R, int L) {
   Layout l;
   int o = ST_HDR;
   l.o_list = o; o += T; l.o_ids = o; o += T; l.o_begin = o; o += T; l.o_end = o; o += T;
   l.o_rel = o; o += R; l.o_nph = o; o += T * (L + 1); l.o_eph = o; o += R * (L > 0 ? L : 1);
   l.o_mt = o; o += MT_N / 2;
+  l.o_shard = o; o += MAX_SHARDS + 2;
   l.words = (size_t)o;
   return l;
 }
@@ -907,7 +926,7 @@ int launch_count(pygb200_sampler* s, const PassArgs& a, i64 F, i64 E_prev, cudaS
 }
 
 template <typename idx_t>
-int launch_rest(pygb200_sampler* s, const PassArgs& a, i64 F, i64 E, bool lookup_now, cudaStream_t st) {
+int launch_sample(pygb200_sampler* s, const PassArgs& a, i64 F, i64 E, cudaStream_t st) {
   const i64 k = a.fanout;
   const int G = (k < 0 || k > 16) ? 32 : (k > 8 ? 16 : (k > 4 ? 8 : 4));
   const int gs = grid_for(F, NT / G, s->sm_count);
@@ -920,7 +939,13 @@ int launch_rest(pygb200_sampler* s, const PassArgs& a, i64 F, i64 E, bool lookup
   }
   prof_end(tk, "sample", st, E);
   PYGB_LAUNCH_CHECK();
-  tk = prof_begin(st);
+  return PYGB200_OK;
+}
+
+template <typename idx_t>
+int launch_rest(pygb200_sampler* s, const PassArgs& a, i64 F, i64 E, bool lookup_now, cudaStream_t st, bool with_sample = true) {
+  if (with_sample) if (int e = launch_sample<idx_t>(s, a, F, E, st)) return e;
+  void* tk = prof_begin(st);
   k_mark<<<grid_for(E, ETILE, s->sm_count), NT, 0, st>>>(a);
   prof_end(tk, "mark", st, E);
   PYGB_LAUNCH_CHECK();
@@ -940,7 +965,7 @@ int launch_rest(pygb200_sampler* s, const PassArgs& a, i64 F, i64 E, bool lookup
 int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const pygb200_relation* rels,
                      const void* const* seeds, const int64_t* n_seeds, const int64_t* num_neighbors,
                      unsigned flags, pygb200_mt19937* mt, int64_t* nodes_per_hop, int64_t* edges_per_hop,
-                     int64_t* n_nodes_out, int64_t* n_edges_out, cudaStream_t st) {
+                     int64_t* n_nodes_out, int64_t* n_edges_out, cudaStream_t st, const pygb200_shard* shard) {
   const bool replace = flags & PYGB200_S_REPLACE, disjoint = flags & PYGB200_S_DISJOINT, idx32 = flags & PYGB200_S_INDEX32;
   i64 total_seeds = 0;
   for (int t = 0; t < T; ++t) {
@@ -996,6 +1021,12 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
     total_elems = sat_add(total_elems, sat_mul(c, 3));
   }
   if (total_elems > ((i64)1 << 30)) synced = true;  // > 8 GiB of worst-case int64 results: size from actuals
+  const bool sharded = shard != nullptr && shard->world > 1;
+  if (sharded) {
+    PYGB_CHECK(!synced, PYGB200_ERR_UNSUPPORTED, "frontier-sharded sampling needs bounded fan-outs (no -1, < 8 GiB worst case)");
+    PYGB_CHECK(shard->world <= MAX_SHARDS && shard->rank >= 0 && shard->rank < shard->world && shard->allgather,
+               PYGB200_ERR_ARG, "bad shard descriptor");
+  }
 
   // ---- workspace
   if ((int)s->types.size() < T) s->types.resize(T);
@@ -1190,7 +1221,30 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
         a.lk_colv = lk_colv; a.lk_vals = lk_vals;
         with_hop_end(a);
         if (int e = idx32 ? launch_count<int32_t>(s, a, Fb, lk_E, st) : launch_count<int64_t>(s, a, Fb, lk_E, st)) return e;
-        if (int e = idx32 ? launch_rest<int32_t>(s, a, Fb, Eb, false, st) : launch_rest<int64_t>(s, a, Fb, Eb, false, st)) return e;
+        if (!sharded) {
+          if (int e = idx32 ? launch_rest<int32_t>(s, a, Fb, Eb, false, st) : launch_rest<int64_t>(s, a, Fb, Eb, false, st)) return e;
+        } else {
+          // every rank counted the whole frontier (offsets and bit-stream positions are global); draw only
+          // this rank's slice, all-gather the edge ids, then expand/dedup everything (replicated)
+          const int W = shard->world;
+          k_shard_bounds<<<1, 128, 0, st>>>(a, W, lay.o_shard);
+          PYGB_LAUNCH_CHECK();
+          if (int e = read_state()) return e;
+          const i64 F = s->st_host[ST_PASS_F], E = s->st_host[ST_PASS_E], pbase = s->st_host[ST_PASS_BASE];
+          PassArgs d = a;
+          d.phase = 1;
+          d.shard_lo = (i64)((__int128)F * shard->rank / W);
+          d.shard_hi = (i64)((__int128)F * (shard->rank + 1) / W);
+          if (d.shard_hi > d.shard_lo)
+            if (int e = idx32 ? launch_sample<int32_t>(s, d, d.shard_hi - d.shard_lo, E, st) : launch_sample<int64_t>(s, d, d.shard_hi - d.shard_lo, E, st)) return e;
+          if (E > 0) {
+            const int rc = shard->allgather(shard->user, a.eid + pbase, reinterpret_cast<const int64_t*>(s->st_host + lay.o_shard), W, (void*)st);
+            PYGB_CHECK(rc == 0, PYGB200_ERR_INTERNAL, "frontier-sharded sampling: all-gather callback failed");
+          }
+          d.phase = 2;
+          if (int e = idx32 ? launch_sample<int32_t>(s, d, Fb, Eb, st) : launch_sample<int64_t>(s, d, Fb, Eb, st)) return e;
+          if (int e = idx32 ? launch_rest<int32_t>(s, a, Fb, Eb, false, st, false) : launch_rest<int64_t>(s, a, Fb, Eb, false, st, false)) return e;
+        }
         lk_colv = a.colv; lk_vals = a.vals; lk_E = Eb;
         if (r == last_r) hop_closed = true;
       } else {
@@ -1308,7 +1362,21 @@ extern "C" int pygb200_sampler_run(pygb200_sampler* s, int32_t T, int32_t R, int
   PYGB_CHECK(T >= 1 && T <= 1024 && R >= 0 && L >= 0, PYGB200_ERR_ARG, "pygb200_sampler_run: bad T/R/L");
   std::lock_guard<std::mutex> lock(s->mu);
   return sampler_run_impl(s, T, R, L, rels, seeds, n_seeds, num_neighbors, flags, mt, nodes_per_hop, edges_per_hop,
-                          n_nodes_out, n_edges_out, (cudaStream_t)stream);
+                          n_nodes_out, n_edges_out, (cudaStream_t)stream, nullptr);
+}
+
+extern "C" int pygb200_sampler_run_sharded(pygb200_sampler* s, int32_t T, int32_t R, int32_t L,
+                                           const pygb200_relation* rels, const void* const* seeds,
+                                           const int64_t* n_seeds, const int64_t* num_neighbors, unsigned flags,
+                                           pygb200_mt19937* mt, int64_t* nodes_per_hop, int64_t* edges_per_hop,
+                                           int64_t* n_nodes_out, int64_t* n_edges_out, void* stream,
+                                           const pygb200_shard* shard) {
+  PYGB_CHECK(s && seeds && n_seeds && mt && (rels || R == 0) && (num_neighbors || L == 0 || R == 0), PYGB200_ERR_ARG,
+             "pygb200_sampler_run_sharded: null argument");
+  PYGB_CHECK(T >= 1 && T <= 1024 && R >= 0 && L >= 0, PYGB200_ERR_ARG, "pygb200_sampler_run_sharded: bad T/R/L");
+  std::lock_guard<std::mutex> lock(s->mu);
+  return sampler_run_impl(s, T, R, L, rels, seeds, n_seeds, num_neighbors, flags, mt, nodes_per_hop, edges_per_hop,
+                          n_nodes_out, n_edges_out, (cudaStream_t)stream, shard);
 }
 
 extern "C" int pygb200_sampler_export_edges(pygb200_sampler* s, int32_t rel, void* row_out, void* col_out,

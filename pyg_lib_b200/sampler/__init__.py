@@ -87,4 +87,6 @@ def hetero_neighbor_sample(
     return row_dict, col_dict, node_id_dict, edge_id_dict, num_nodes_per_hop_dict, num_edges_per_hop_dict
 
 
-__all__ = ['neighbor_sample', 'hetero_neighbor_sample']
+from .dist import dist_neighbor_sample  # noqa: E402  (multi-GPU, frontier-sharded)
+
+__all__ = ['neighbor_sample', 'hetero_neighbor_sample', 'dist_neighbor_sample']
