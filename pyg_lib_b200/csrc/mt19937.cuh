@@ -108,21 +108,18 @@ __global__ void k_mt_init(u32* __restrict__ raw, i64* generated, const __grid_co
 
 constexpr int MT_WIN = 4096;  // circular shared-memory window (words)
 
-// Extends raw[] up to (at least) raw index `target`, rounded up to a whole 624-word generation.
-// One CTA (640 threads: one word per thread per step); `KL` = recurrence unroll.
+// Generates raw[m .. target) with one 640-thread CTA.  `hist_lo` = lowest raw index that holds valid
+// history (0 for the stream's start; the window base after a jump).  `KL` = recurrence unroll: with
+// history >= 624 + 227*(KL-1) words a step yields min(227*KL, 623) words per barrier.
 template <int KL>
-__global__ void __launch_bounds__(640) k_mt_extend_to(u32* __restrict__ raw, i64* generated, i64 target_in, i64 cap_words) {
-  __shared__ u32 win[MT_WIN];
-  i64 target = ((target_in + MT_N - 1) / MT_N) * MT_N;
-  if (target > cap_words) target = (cap_words / MT_N) * MT_N;
-  i64 m = *generated;
+__device__ void mt_gen_range(u32* __restrict__ raw, i64 hist_lo, i64 m, i64 target, u32* win) {
   if (target <= m) return;
   constexpr int HIST = MT_N + MT_LAG * (KL - 1);
-  const i64 h0 = m > HIST ? m - HIST : 0;
-  for (i64 i = h0 + threadIdx.x; i < m; i += blockDim.x) win[i & (MT_WIN - 1)] = raw[i];
+  const i64 h0 = (m - hist_lo) > HIST ? m - HIST : hist_lo;
+  for (i64 i = h0 + threadIdx.x; i < m; i += blockDim.x) win[i & (MT_WIN - 1)] = __ldcg(&raw[i]);
   __syncthreads();
   while (m < target) {
-    int k = (int)((m - MT_N) / MT_LAG) + 1;  // history available for this unroll factor
+    int k = (int)((m - hist_lo - MT_N) / MT_LAG) + 1;  // unroll factor the available history allows
     if (k > KL) k = KL;
     i64 n = (i64)MT_LAG * k;
     if (n > MT_N - 1) n = MT_N - 1;  // the T(raw[m-624], raw[m-623]) term caps the step at 623 words
@@ -140,7 +137,92 @@ __global__ void __launch_bounds__(640) k_mt_extend_to(u32* __restrict__ raw, i64
     __syncthreads();
     m += n;
   }
-  if (threadIdx.x == 0) *generated = m;
+}
+
+// Extends raw[] up to (at least) raw index `target`, rounded up to a whole 624-word generation.
+template <int KL>
+__global__ void __launch_bounds__(640) k_mt_extend_to(u32* __restrict__ raw, i64* generated, i64 target_in, i64 cap_words) {
+  __shared__ u32 win[MT_WIN];
+  i64 target = ((target_in + MT_N - 1) / MT_N) * MT_N;
+  if (target > cap_words) target = (cap_words / MT_N) * MT_N;
+  const i64 m = *generated;
+  if (target <= m) return;
+  mt_gen_range<KL>(raw, 0, m, target, win);
+  if (threadIdx.x == 0) *generated = target;
+}
+
+// ---- parallel generation by jump-ahead (tools/mt19937_jump.py builds the polynomial table) -------------
+// raw[] is linear over GF(2): raw[t + p*S + j] = XOR_{i in g_p} raw[t + i + j] (j = 0..623) with
+// g_p = x^(p*S) mod x*phi(x), deg < 19938.  So after a serial pre-step of ~20.6k words every CTA p can
+// compute the 624-word window that starts its chunk and generate S words independently.
+constexpr int MT_POLY_WORDS = 624;                       // 19968 bits >= degree bound 19938
+constexpr i64 MT_JUMP_PRESTEP = 19938 + MT_N + MT_N;     // history the jumps read, rounded up below
+
+// pre-step: remember where the jump base is and extend by the history the polynomials read
+template <int KL>
+__global__ void __launch_bounds__(640) k_mt_jump_prestep(u32* __restrict__ raw, i64* generated, i64* jump_base, i64 cap_words) {
+  __shared__ u32 win[MT_WIN];
+  const i64 m = *generated;
+  i64 target = ((m + MT_JUMP_PRESTEP + MT_N - 1) / MT_N) * MT_N;
+  if (target > cap_words) target = (cap_words / MT_N) * MT_N;
+  if (threadIdx.x == 0) *jump_base = m;
+  if (target <= m) return;
+  mt_gen_range<KL>(raw, 0, m, target, win);
+  if (threadIdx.x == 0) *generated = target;
+}
+
+// CTA p generates raw[b0 + p*S + 624 .. b0 + (p+1)*S + 624), b0 = jump_base - 624 (CTA 0 continues after the
+// pre-step).  The last CTA to finish publishes the new length.
+template <int KL>
+__global__ void __launch_bounds__(640) k_mt_jump_generate(u32* __restrict__ raw, i64* generated, const i64* jump_base,
+                                                           const u32* __restrict__ polys, int S, i64 cap_words,
+                                                           unsigned long long* ticket) {
+  __shared__ u32 win[MT_WIN];
+  __shared__ int s_last;
+  const i64 b0 = *jump_base - MT_N;
+  const int p = blockIdx.x, P = gridDim.x;
+  i64 end_all = b0 + (i64)P * S + MT_N;
+  if (end_all > cap_words) end_all = (cap_words / MT_N) * MT_N;
+  i64 m, hist_lo, target = b0 + (i64)(p + 1) * S + MT_N;
+  if (target > end_all) target = end_all;
+  if (p == 0) {
+    m = *generated;   // end of the pre-step
+    hist_lo = 0;
+  } else {
+    const i64 w0 = b0 + (i64)p * S;   // window base of this chunk
+    if (w0 + MT_N <= end_all) {
+      const u32* __restrict__ g = polys + (size_t)(p - 1) * MT_POLY_WORDS;
+      const u32* src = raw + b0;
+      if (threadIdx.x < MT_N) {
+        u32 acc = 0;
+        for (int w = 0; w < MT_POLY_WORDS; ++w) {
+          u32 bits = g[w];
+          while (bits) {
+            const int i = w * 32 + __ffs(bits) - 1;
+            bits &= bits - 1;
+            acc ^= __ldcg(&src[i + threadIdx.x]);
+          }
+        }
+        raw[w0 + threadIdx.x] = acc;
+      }
+    }
+    __syncthreads();
+    m = w0 + MT_N;
+    hist_lo = w0;
+  }
+  if (m < target) mt_gen_range<KL>(raw, hist_lo, m, target, win);
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned long long t = atomicAdd(ticket, 1ull);
+    s_last = (t == (unsigned long long)P - 1);
+    if (s_last) *ticket = 0;
+  }
+  __syncthreads();
+  if (s_last && threadIdx.x == 0) {
+    __threadfence();
+    if (end_all > *generated) *generated = end_all;
+  }
 }
 
 }  // namespace pygb200

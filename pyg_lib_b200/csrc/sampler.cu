@@ -17,6 +17,8 @@
 //   k_assign  new local ids = ids_base + rank, appended to the dst type's node list.
 //   k_lookup  every edge reads its final local id.
 // Host work per call: bounds, launches, ONE stream sync at the end (the API returns host counts).
+#include <dlfcn.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -782,6 +784,10 @@ struct pygb200_sampler {
   pygb200_mt19937 mt_expected;    // engine state written back by the previous run
   i64 mt_q = 0;                   // raw index of the next output
   i64 mt_gen_known = 0;           // raw words known (to the host) to be generated and visible to the main stream
+  i64 mt_requested = 0;           // lower bound of the stream length once every queued generation kernel has run
+  DevBuf jump_polys, jump_scratch; // jump-ahead table (tools/mt19937_jump.py) and {jump_base, ticket}
+  int jump_S = 0, jump_P = 0;     // 0 = table not available: serial generation only
+  bool jump_tried = false;
   i64 raw_cap_words = 0;
   cudaStream_t mt_stream = nullptr;
   // the last two pre-generation launches (side stream, in launch order): event + raw index they cover
@@ -830,7 +836,7 @@ extern "C" void pygb200_sampler_destroy(pygb200_sampler* s) {
   if (s->mt_stream) { cudaStreamSynchronize(s->mt_stream); cudaStreamDestroy(s->mt_stream); }
   for (int i = 0; i < 2; ++i) if (s->mt_ev[i]) cudaEventDestroy(s->mt_ev[i]);
   DevBuf* all[] = {&s->eslot, &s->erank, &s->rec, &s->tile_out, &s->tile_func,
-                   &s->tile_off, &s->tile_pos, &s->mtile, &s->raw, &s->st, &s->gen};
+                   &s->tile_off, &s->tile_pos, &s->mtile, &s->raw, &s->st, &s->gen, &s->jump_polys, &s->jump_scratch};
   for (auto* b : all) b->release();
   if (s->st_host) cudaFreeHost(s->st_host);
   delete s;
@@ -911,6 +917,64 @@ int ensure_edge_scratch(pygb200_sampler* s, i64 E, cudaStream_t st) {
   if (int e = s->eslot.ensure((size_t)e_ * 4, 0, st)) return e;
   if (int e = s->erank.ensure((size_t)e_ * 4, 0, st)) return e;
   if (int e = s->mtile.ensure((size_t)ceil_div(e_, ETILE) * 8, 0, st)) return e;
+  return PYGB200_OK;
+}
+
+// jump-ahead table: mt19937_jump.bin next to this shared library (optional; without it generation is serial)
+void load_jump_table(pygb200_sampler* s, cudaStream_t st) {
+  if (s->jump_tried) return;
+  s->jump_tried = true;
+  Dl_info info;
+  if (!dladdr((void*)&pygb200_sampler_create, &info) || !info.dli_fname) return;
+  std::string dir(info.dli_fname);
+  const size_t slash = dir.find_last_of('/');
+  dir = slash == std::string::npos ? std::string(".") : dir.substr(0, slash);
+  const char* cands[] = {"/mt19937_jump.bin", "/csrc/mt19937_jump.bin"};
+  for (const char* c : cands) {
+    FILE* f = fopen((dir + c).c_str(), "rb");
+    if (!f) continue;
+    uint32_t hdr[4];
+    std::vector<uint32_t> data;
+    bool ok = fread(hdr, 4, 4, f) == 4 && hdr[0] == 0x4a54364du && hdr[3] == (uint32_t)MT_POLY_WORDS && hdr[2] >= 2 && hdr[2] <= 1024 &&
+              hdr[1] >= 65536;
+    if (ok) {
+      data.resize((size_t)(hdr[2] - 1) * MT_POLY_WORDS);
+      ok = fread(data.data(), 4, data.size(), f) == data.size();
+    }
+    fclose(f);
+    if (!ok) continue;
+    if (s->jump_polys.ensure(data.size() * 4, 0, st) != PYGB200_OK || s->jump_scratch.ensure(64, 0, st) != PYGB200_OK) return;
+    if (cudaMemcpyAsync(s->jump_polys.p, data.data(), data.size() * 4, cudaMemcpyHostToDevice, st) != cudaSuccess) return;
+    if (cudaMemsetAsync(s->jump_scratch.p, 0, 64, st) != cudaSuccess) return;
+    if (cudaStreamSynchronize(st) != cudaSuccess) return;   // `data` is pageable and dies here
+    s->jump_S = (int)hdr[1];
+    s->jump_P = (int)hdr[2];
+    return;
+  }
+}
+
+// Queue generation of the raw stream up to (at least) `target` on `st`.  Large requests are split over
+// CTAs by jump-ahead (~20k-word serial pre-step + one pass over it per chunk), small ones run on one CTA.
+int mt_request(pygb200_sampler* s, cudaStream_t st, i64 target) {
+  target = std::min<i64>(target, s->raw_cap_words - MT_N);
+  while (target > s->mt_requested) {
+    const i64 amount = target - s->mt_requested;
+    if (s->jump_P >= 2 && amount >= 2 * (i64)s->jump_S) {
+      const int P_used = (int)std::min<i64>(s->jump_P, (amount + s->jump_S - 1) / s->jump_S);
+      i64* jb = s->jump_scratch.as<i64>();
+      k_mt_jump_prestep<3><<<1, 640, 0, st>>>(s->raw.as<u32>(), s->gen.as<i64>(), jb, s->raw_cap_words);
+      PYGB_LAUNCH_CHECK();
+      k_mt_jump_generate<3><<<P_used, 640, 0, st>>>(s->raw.as<u32>(), s->gen.as<i64>(), jb, s->jump_polys.as<u32>(), s->jump_S,
+                                                   s->raw_cap_words, reinterpret_cast<unsigned long long*>(jb + 1));
+      PYGB_LAUNCH_CHECK();
+      s->mt_requested += (i64)P_used * s->jump_S;
+      if (s->mt_requested > s->raw_cap_words - MT_N) { s->mt_requested = s->raw_cap_words - MT_N; break; }
+    } else {
+      k_mt_extend_to<3><<<1, 640, 0, st>>>(s->raw.as<u32>(), s->gen.as<i64>(), target, s->raw_cap_words);
+      PYGB_LAUNCH_CHECK();
+      s->mt_requested = target;
+    }
+  }
   return PYGB200_OK;
 }
 
@@ -1002,7 +1066,7 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
       nf = sat_add(nf, e);
     }
   std::vector<i64> node_cap(T, 0), rel_cap(R, 0);
-  i64 max_F = 1, max_E = std::max<i64>(total_seeds, 1), draw_units = 0, total_elems = 0;
+  i64 max_F = 1, max_E = std::max<i64>(total_seeds, 1), draw_units = 0, draw_count = 0, total_elems = 0;
   for (int t = 0; t < T; ++t) {
     i64 c = 0;
     for (int h = 0; h <= L; ++h) { c = sat_add(c, fb[(size_t)t * (L + 1) + h]); max_F = std::max(max_F, fb[(size_t)t * (L + 1) + h]); }
@@ -1016,6 +1080,7 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
       c = sat_add(c, e); max_E = std::max(max_E, e);
       // units per draw: 1 when every range < 2^16, else at most 2 + 1 skipped (32-bit) / 4 + 3 (64-bit)
       draw_units = sat_add(draw_units, sat_mul(e, rels[r].num_edges < 65536 ? 1 : (rels[r].num_edges < ((i64)1 << 32) ? 3 : 7)));
+      draw_count = sat_add(draw_count, e);
     }
     rel_cap[r] = std::max<i64>(c, 1);
     total_elems = sat_add(total_elems, sat_mul(c, 3));
@@ -1074,14 +1139,19 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
   // Pre-generation runs TWO runs ahead on the side stream: the launch made at the end of run i-1 already
   // covers run i+1, so in a steady loop this run only waits for an event that completed long ago while
   // the launch made at the end of run i (for run i+2) overlaps run i+1.
-  const i64 run_outputs = synced ? 256 * 2 : 256 * (rng_blocks_for_units(draw_units) + 1);
+  // run_outputs     : what a run is EXPECTED to consume at most (one 16-bit unit per draw — exact unless a
+  //                   frontier node has >= 2^16 neighbours); pre-generation targets use it, a shortfall is
+  //                   extended by the last block of k_count;
+  // run_outputs_max : the worst case (32/64-bit draws incl. skipped units), used only for capacity.
+  const i64 run_outputs = synced ? 256 * 2 : 256 * (rng_blocks_for_units(draw_count) + 1);
+  const i64 run_outputs_max = synced ? 256 * 2 : 256 * (rng_blocks_for_units(draw_units) + 1);
   auto wait_all_pregen = [&]() -> int {
     for (int i = 0; i < 2; ++i) if (s->mt_ev_pending[i]) { PYGB_CUDA(cudaStreamWaitEvent(st, s->mt_ev[i], 0)); s->mt_ev_pending[i] = false; }
     return PYGB200_OK;
   };
   i64 out0;
   bool cont = s->mt_valid && memcmp(&s->mt_expected, mt, sizeof(*mt)) == 0 &&
-              s->mt_q + 2 * run_outputs + 6 * MT_N <= s->raw_cap_words;
+              s->mt_q + run_outputs_max + run_outputs + 6 * MT_N <= s->raw_cap_words;
   if (synced) {  // synced runs extend the stream from inside k_count: nothing may run beside them
     if (int e = wait_all_pregen()) return e;
     s->mt_gen_known = 0;
@@ -1105,14 +1175,14 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
     } else {
       // not covered ahead of time (first continued run, or a run larger than the previous one): extend here
       if (int e = wait_all_pregen()) return e;
-      k_mt_extend_to<3><<<1, 640, 0, st>>>(s->raw.as<u32>(), s->gen.as<i64>(), need, s->raw_cap_words);
-      PYGB_LAUNCH_CHECK();
+      if (int e = mt_request(s, st, need)) return e;
       s->mt_gen_known = need;
     }
   } else {
     if (int e = wait_all_pregen()) return e;
     static const i64 pref_cap = [] { const char* e = getenv("PYGB200_MT_CAP_WORDS"); return e ? (i64)atoll(e) : (i64)1 << 23; }();
-    const i64 want = std::max<i64>((i64)MT_N + 2 * run_outputs + 8 * MT_N, pref_cap);  // default 32 MB of raw words
+    load_jump_table(s, st);
+    const i64 want = std::max<i64>((i64)MT_N + 4 * (run_outputs_max + run_outputs) + 8 * MT_N + 2 * (i64)s->jump_S, pref_cap);  // default 32 MB of raw words
     if (want > s->raw_cap_words) {
       if (int e = s->raw.ensure((size_t)want * 4, 0, st)) return e;
       s->raw_cap_words = want;
@@ -1123,9 +1193,9 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
     PYGB_LAUNCH_CHECK();
     out0 = mt_next0(mt->left);
     s->mt_gen_known = MT_N;
-    if (!synced) {  // cover this run's worst case up front so that no pass has to extend the stream itself
-      k_mt_extend_to<3><<<1, 640, 0, st>>>(s->raw.as<u32>(), s->gen.as<i64>(), out0 + run_outputs + MT_N, s->raw_cap_words);
-      PYGB_LAUNCH_CHECK();
+    s->mt_requested = MT_N;
+    if (!synced) {  // cover this run's expected need up front so that no pass has to extend the stream itself
+      if (int e = mt_request(s, st, out0 + run_outputs + MT_N)) return e;
       s->mt_gen_known = out0 + run_outputs + MT_N;
     }
   }
@@ -1338,9 +1408,7 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
     if (target > s->mt_q && !s->mt_ev_pending[slot]) {
       // this run's kernels (which may extend the stream themselves) are done: the D2H copy we just waited
       // for is ordered after k_final
-      k_mt_extend_to<3><<<1, 640, 0, s->mt_stream>>>(s->raw.as<u32>(), s->gen.as<i64>(), target, s->raw_cap_words);
-      count_launch();
-      if (cudaGetLastError() == cudaSuccess && cudaEventRecord(s->mt_ev[slot], s->mt_stream) == cudaSuccess) {
+      if (mt_request(s, s->mt_stream, target) == PYGB200_OK && cudaEventRecord(s->mt_ev[slot], s->mt_stream) == cudaSuccess) {
         s->mt_ev_pending[slot] = true;
         s->mt_ev_target[slot] = target;
         s->mt_ev_next = slot ^ 1;

@@ -253,3 +253,19 @@ def test_many_seeds_multi_kernel_seed_path(lib):
     exp = O.neighbor_sample(rowptr, col, seed, [3, 2])
     torch.manual_seed(2)
     _cmp(lib.sampler.neighbor_sample(rowptr.to(DEV), col.to(DEV), seed.to(DEV), [3, 2]), exp)
+
+
+def test_large_batch_jump_ahead(lib):
+    """Enough draws (~2.5 M) that the mt19937 stream is generated by jump-ahead across CTAs
+    (mt19937_jump.bin); three calls so that restart, continuation and pre-generation are all exercised."""
+    rowptr, col = lognormal_csr(200_000, 10_000_000, seed=3)
+    seed = torch.randperm(200_000, generator=torch.Generator().manual_seed(6))[:30000]
+    d = [t.to(DEV) for t in (rowptr, col, seed)]
+    torch.manual_seed(2024)
+    exp = [O.neighbor_sample(rowptr, col, seed, [10, 8]) for _ in range(3)]
+    s_exp = _rng_prefix()
+    torch.manual_seed(2024)
+    for i in range(3):
+        _cmp(lib.sampler.neighbor_sample(d[0], d[1], d[2], [10, 8]), exp[i])
+    assert np.array_equal(_rng_prefix(), s_exp)
+    assert exp[0][0].numel() > 2_000_000
