@@ -268,4 +268,4 @@ def test_large_batch_jump_ahead(lib):
     for i in range(3):
         _cmp(lib.sampler.neighbor_sample(d[0], d[1], d[2], [10, 8]), exp[i])
     assert np.array_equal(_rng_prefix(), s_exp)
-    assert exp[0][0].numel() > 2_000_000
+    assert exp[0][0].numel() > 1_000_000
