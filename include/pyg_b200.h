@@ -136,6 +136,26 @@ int pygb200_sampler_run(pygb200_sampler* s, int32_t T, int32_t R, int32_t L,
                         pygb200_mt19937* mt_inout, int64_t* nodes_per_hop, int64_t* edges_per_hop,
                         int64_t* n_nodes, int64_t* n_edges, void* stream);
 
+/* Temporal sampling (node_temporal_sample / edge_temporal_sample, neighbor_kernel.cpp:74-144,417-428,
+ * 742-787): neighbourhoods must be sorted by time; only neighbours with time <= the seed time of the
+ * frontier node's subgraph are candidates (`strategy_last`: the latest `fan-out` of them).  Requires
+ * PYGB200_S_DISJOINT.  All arrays are int64 on the device; any pointer / entry may be NULL:
+ *   node_time[t]  time of the nodes of type t (applies to relations whose DST type is t)
+ *   edge_time[r]  time of relation r's edges (wins over node_time)
+ *   seed_time[t]  per seed of type t; default node_time[t][seed]. */
+typedef struct {
+  const int64_t* const* node_time;   /* [T] */
+  const int64_t* const* edge_time;   /* [R] */
+  const int64_t* const* seed_time;   /* [T] */
+  int32_t strategy_last;
+} pygb200_temporal;
+int pygb200_sampler_run_temporal(pygb200_sampler* s, int32_t T, int32_t R, int32_t L,
+                                 const pygb200_relation* rels_host, const void* const* seeds,
+                                 const int64_t* n_seeds, const int64_t* num_neighbors, unsigned flags,
+                                 pygb200_mt19937* mt_inout, int64_t* nodes_per_hop,
+                                 int64_t* edges_per_hop, int64_t* n_nodes, int64_t* n_edges, void* stream,
+                                 const pygb200_temporal* temporal);
+
 /* Frontier-sharded run for multi-GPU sampling of ONE batch (the reference's own split of
  * the work is dist_neighbor_sample -> merge -> relabel, neighbor_kernel.cpp:296-303,957-978).
  * Every rank holds the full CSR and calls this with identical arguments and identical engine state.

@@ -65,6 +65,13 @@ def lib():
         _LIB.oracle_neighbor_sample.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64,
                                                 C.c_void_p, C.c_int, C.c_int, C.c_int,
                                                 C.POINTER(MTState), C.POINTER(HomoResult)]
+        _LIB.oracle_neighbor_sample_temporal.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64,
+                                                         C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(MTState),
+                                                         C.POINTER(HomoResult), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        _LIB.oracle_hetero_neighbor_sample_temporal.argtypes = [
+            C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+            C.c_void_p, C.c_int64, C.c_int, C.c_int, C.POINTER(MTState), C.POINTER(HeteroResult),
+            C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         _LIB.oracle_homo_free.argtypes = [C.POINTER(HomoResult)]
         _LIB.oracle_hetero_neighbor_sample.argtypes = [
             C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
@@ -132,8 +139,13 @@ def neighbor_sample(rowptr, col, seed, num_neighbors: List[int], node_time=None,
                     seed_time=None, edge_weight=None, csc: bool = False, replace: bool = False,
                     directed: bool = True, disjoint: bool = False, temporal_strategy: str = 'uniform',
                     return_edge_id: bool = True, mt: Optional[MTState] = None):
-    """Oracle for pyg_lib.sampler.neighbor_sample (uniform; temporal/weighted not restated)."""
-    assert node_time is None and edge_time is None and seed_time is None and edge_weight is None
+    """Oracle for pyg_lib.sampler.neighbor_sample (uniform and temporal; weighted not restated)."""
+    assert edge_weight is None
+    if node_time is not None or edge_time is not None:
+        if not disjoint:
+            raise RuntimeError('Temporal sampling needs to create disjoint subgraphs')
+        if edge_time is not None and seed_time is None:
+            raise RuntimeError('Seed time needs to be specified')
     own_mt = mt is None
     if own_mt:
         mt = mt_from_torch()
@@ -141,9 +153,14 @@ def neighbor_sample(rowptr, col, seed, num_neighbors: List[int], node_time=None,
     rp, cl, sd = _i64(rowptr), _i64(col), _i64(seed)
     nn = np.asarray(num_neighbors, dtype=np.int64)
     res = HomoResult()
-    lib().oracle_neighbor_sample(rp.ctypes.data, rp.size - 1, cl.ctypes.data, sd.ctypes.data, sd.size,
-                                 nn.ctypes.data, len(num_neighbors), int(replace), int(disjoint),
-                                 C.byref(mt), C.byref(res))
+    nt = _i64(node_time) if node_time is not None else None
+    et = _i64(edge_time) if edge_time is not None else None
+    stt = _i64(seed_time) if seed_time is not None else None
+    lib().oracle_neighbor_sample_temporal(rp.ctypes.data, rp.size - 1, cl.ctypes.data, sd.ctypes.data, sd.size,
+                                          nn.ctypes.data, len(num_neighbors), int(replace), int(disjoint),
+                                          C.byref(mt), C.byref(res), nt.ctypes.data if nt is not None else None,
+                                          et.ctypes.data if et is not None else None,
+                                          stt.ctypes.data if stt is not None else None, int(temporal_strategy == 'last'))
     L = len(num_neighbors)
     row = _take(res.row, res.n_edges, dt)
     colv = _take(res.col, res.n_edges, dt)
@@ -169,7 +186,8 @@ def hetero_neighbor_sample(node_types: List[str], edge_types: List[Tuple[str, st
                            seed_dict: Dict[str, torch.Tensor], num_neighbors_dict: Dict[str, List[int]],
                            csc: bool = False, replace: bool = False, directed: bool = True,
                            disjoint: bool = False, return_edge_id: bool = True,
-                           mt: Optional[MTState] = None):
+                           mt: Optional[MTState] = None, node_time_dict=None, edge_time_dict=None, seed_time_dict=None,
+                           temporal_strategy: str = 'uniform'):
     """Oracle for torch.ops.pyg.hetero_neighbor_sample with ONE ATen thread; dict keys are
     'src__rel__dst' strings exactly like the operator (neighbor.cpp:137-147)."""
     own_mt = mt is None
@@ -195,9 +213,21 @@ def hetero_neighbor_sample(node_types: List[str], edge_types: List[Tuple[str, st
     nsd = np.array([a.size for a in sds], dtype=np.int64)
     nn = np.array([list(num_neighbors_dict[r]) for r in rel], dtype=np.int64).reshape(R, L)
     res = HeteroResult()
-    lib().oracle_hetero_neighbor_sample(T, R, src.ctypes.data, dst.ctypes.data, rp_arr, cl_arr, sd_arr,
-                                        nsd.ctypes.data, nn.ctypes.data, L, int(replace), int(disjoint),
-                                        C.byref(mt), C.byref(res))
+    keep = []
+
+    def ptr_array(d, keys, n):
+        if d is None:
+            return None
+        arrs = [(_i64(d[k]) if k in d else None) for k in keys]
+        keep.append(arrs)
+        return (C.c_void_p * max(n, 1))(*[(a.ctypes.data if a is not None else None) for a in arrs])
+    nt_arr = ptr_array(node_time_dict, types, T)
+    et_arr = ptr_array(edge_time_dict, rel, R)
+    st_arr = ptr_array(seed_time_dict, types, T)
+    lib().oracle_hetero_neighbor_sample_temporal(T, R, src.ctypes.data, dst.ctypes.data, rp_arr, cl_arr, sd_arr,
+                                                 nsd.ctypes.data, nn.ctypes.data, L, int(replace), int(disjoint),
+                                                 C.byref(mt), C.byref(res), nt_arr, et_arr, st_arr,
+                                                 int(temporal_strategy == 'last'))
     row_d, col_d, eid_d, node_d, nph_d, eph_d = {}, {}, {}, {}, {}, {}
     for t in node_types:
         i = tix[t]

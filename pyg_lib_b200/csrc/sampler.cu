@@ -132,6 +132,9 @@ struct PassArgs {
   // frontier sharding (multi-GPU): phase 0 = normal; 1 = draw only, frontier nodes [shard_lo, shard_hi),
   // writes edge ids; 2 = expand ALL nodes from the (all-gathered) edge ids: gather col, rows, hash insert
   int phase; i64 shard_lo, shard_hi;
+  // temporal sampling (neighbor_kernel.cpp:74-144): time_mode 1 = node time of the neighbour (time[col[e]]),
+  // 2 = edge time (time[e]); seed_times indexed by the frontier node's batch id; time_last = strategy 'last'
+  const i64* time; const i64* seed_times; int time_mode, time_last;
 };
 
 // ------------------------------------------------------------------------------------- helpers
@@ -360,7 +363,21 @@ __global__ void __launch_bounds__(NT) k_count(const PassArgs a) {
     if (i < F) {
       const i64 v = a.src_nodes[begin + i];
       rs = (i64)rowptr[v];
-      deg = (i64)rowptr[v + 1] - rs;
+      i64 re = (i64)rowptr[v + 1];
+      if (a.time_mode && re > rs && a.fanout != 0) {
+        // neighbours that fulfil the temporal constraint: std::upper_bound on the (time-sorted) row
+        const i64 st = a.seed_times[a.src_batch[begin + i]];
+        const idx_t* __restrict__ colp = (const idx_t*)a.col;
+        i64 lo = rs, hi = re;
+        while (lo < hi) {
+          const i64 mid = lo + ((hi - lo) >> 1);
+          const i64 key = a.time_mode == 1 ? a.time[(i64)colp[mid]] : a.time[mid];
+          if (st < key) hi = mid; else lo = mid + 1;
+        }
+        re = lo;
+        if (a.time_last && a.fanout >= 0 && re - a.fanout > rs) rs = re - a.fanout;
+      }
+      deg = re - rs;
       classify(deg, a.fanout, a.replace, &n_out, &n16, &n32, &n64);
       if (n32 == 0 && n64 == 0) {
         f.d[0] = f.d[1] = f.d[2] = f.d[3] = (u32)n16;
@@ -461,6 +478,14 @@ __global__ void __launch_bounds__(NT) k_sample(const PassArgs a) {
       }
     }
   }
+}
+
+// seed time per batch id (neighbor_kernel.cpp:417-428): explicit seed_time wins, else node_time[seed]
+template <typename idx_t>
+__global__ void __launch_bounds__(NT) k_seed_times(i64* __restrict__ out, const idx_t* __restrict__ seeds, i64 n, i64 batch0,
+                                                    const i64* __restrict__ seed_time, const i64* __restrict__ node_time) {
+  for (i64 i = (i64)blockIdx.x * NT + threadIdx.x; i < n; i += (i64)gridDim.x * NT)
+    out[batch0 + i] = seed_time ? seed_time[i] : node_time[(i64)seeds[i]];
 }
 
 // flat edge offset of the first frontier node of every shard (frontier split evenly by node index)
@@ -785,6 +810,7 @@ struct pygb200_sampler {
   i64 mt_q = 0;                   // raw index of the next output
   i64 mt_gen_known = 0;           // raw words known (to the host) to be generated and visible to the main stream
   i64 mt_requested = 0;           // lower bound of the stream length once every queued generation kernel has run
+  DevBuf seed_times;              // temporal sampling: seed time per batch id
   DevBuf jump_polys, jump_scratch; // jump-ahead table (tools/mt19937_jump.py) and {jump_base, ticket}
   int jump_S = 0, jump_P = 0;     // 0 = table not available: serial generation only
   bool jump_tried = false;
@@ -836,7 +862,7 @@ extern "C" void pygb200_sampler_destroy(pygb200_sampler* s) {
   if (s->mt_stream) { cudaStreamSynchronize(s->mt_stream); cudaStreamDestroy(s->mt_stream); }
   for (int i = 0; i < 2; ++i) if (s->mt_ev[i]) cudaEventDestroy(s->mt_ev[i]);
   DevBuf* all[] = {&s->eslot, &s->erank, &s->rec, &s->tile_out, &s->tile_func,
-                   &s->tile_off, &s->tile_pos, &s->mtile, &s->raw, &s->st, &s->gen, &s->jump_polys, &s->jump_scratch};
+                   &s->tile_off, &s->tile_pos, &s->mtile, &s->raw, &s->st, &s->gen, &s->jump_polys, &s->jump_scratch, &s->seed_times};
   for (auto* b : all) b->release();
   if (s->st_host) cudaFreeHost(s->st_host);
   delete s;
@@ -1029,7 +1055,8 @@ int launch_rest(pygb200_sampler* s, const PassArgs& a, i64 F, i64 E, bool lookup
 int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const pygb200_relation* rels,
                      const void* const* seeds, const int64_t* n_seeds, const int64_t* num_neighbors,
                      unsigned flags, pygb200_mt19937* mt, int64_t* nodes_per_hop, int64_t* edges_per_hop,
-                     int64_t* n_nodes_out, int64_t* n_edges_out, cudaStream_t st, const pygb200_shard* shard) {
+                     int64_t* n_nodes_out, int64_t* n_edges_out, cudaStream_t st, const pygb200_shard* shard,
+                     const pygb200_temporal* temporal) {
   const bool replace = flags & PYGB200_S_REPLACE, disjoint = flags & PYGB200_S_DISJOINT, idx32 = flags & PYGB200_S_INDEX32;
   i64 total_seeds = 0;
   for (int t = 0; t < T; ++t) {
@@ -1086,6 +1113,17 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
     total_elems = sat_add(total_elems, sat_mul(c, 3));
   }
   if (total_elems > ((i64)1 << 30)) synced = true;  // > 8 GiB of worst-case int64 results: size from actuals
+  bool any_time = false;
+  if (temporal) {
+    for (int t = 0; t < T && temporal->node_time; ++t) any_time |= temporal->node_time[t] != nullptr;
+    for (int r = 0; r < R && temporal->edge_time; ++r) any_time |= temporal->edge_time[r] != nullptr;
+  }
+  if (any_time) {
+    PYGB_CHECK(disjoint, PYGB200_ERR_ARG, "Temporal sampling needs to create disjoint subgraphs");
+    for (int t = 0; t < T; ++t)
+      PYGB_CHECK(n_seeds[t] == 0 || (temporal->seed_time && temporal->seed_time[t]) || (temporal->node_time && temporal->node_time[t]),
+                 PYGB200_ERR_ARG, "Seed time needs to be specified");
+  }
   const bool sharded = shard != nullptr && shard->world > 1;
   if (sharded) {
     PYGB_CHECK(!synced, PYGB200_ERR_UNSUPPORTED, "frontier-sharded sampling needs bounded fan-outs (no -1, < 8 GiB worst case)");
@@ -1225,6 +1263,12 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
     a.o_dst_list = lay.o_list + dst_t; a.o_dst_ids = lay.o_ids + dst_t;
     a.raw = s->raw.as<u32>(); a.gen = s->gen.as<i64>(); a.out0 = out0; a.raw_cap = raw_cap;
     a.replace = replace; a.disjoint = disjoint;
+    if (any_time && rel >= 0) {  // edge time of the relation wins over node time of its dst type (:742-787)
+      if (temporal->edge_time && temporal->edge_time[rel]) { a.time_mode = 2; a.time = reinterpret_cast<const i64*>(temporal->edge_time[rel]); }
+      else if (temporal->node_time && temporal->node_time[dst_t]) { a.time_mode = 1; a.time = reinterpret_cast<const i64*>(temporal->node_time[dst_t]); }
+      a.seed_times = s->seed_times.as<i64>();
+      a.time_last = temporal->strategy_last;
+    }
     return a;
   };
   auto read_state = [&]() -> int {
@@ -1234,10 +1278,19 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
   };
 
   // ---- seeds (neighbor_kernel.cpp:409-416, :669-704)
+  if (any_time) if (int e = s->seed_times.ensure((size_t)std::max<i64>(total_seeds, 1) * 8, 0, st)) return e;
   i64 batch0 = 0;
   for (int t = 0; t < T; ++t) {
     PassArgs a = make_args(-1, t, -1);
     a.seed_mode = 1;
+    if (any_time && n_seeds[t] > 0) {
+      const i64* stt = temporal->seed_time ? reinterpret_cast<const i64*>(temporal->seed_time[t]) : nullptr;
+      const i64* ntt = temporal->node_time ? reinterpret_cast<const i64*>(temporal->node_time[t]) : nullptr;
+      const int g = grid_for(n_seeds[t], NT, s->sm_count);
+      if (idx32) k_seed_times<int32_t><<<g, NT, 0, st>>>(s->seed_times.as<i64>(), (const int32_t*)seeds[t], n_seeds[t], batch0, stt, ntt);
+      else k_seed_times<int64_t><<<g, NT, 0, st>>>(s->seed_times.as<i64>(), (const int64_t*)seeds[t], n_seeds[t], batch0, stt, ntt);
+      PYGB_LAUNCH_CHECK();
+    }
     if (n_seeds[t] > 0 && n_seeds[t] <= SEED_FUSED_MAX) {
       if (idx32) k_seed_fused<int32_t><<<1, SEED_NT, 0, st>>>(a, (const int32_t*)seeds[t], (int)n_seeds[t], batch0, L,
                                                               lay.o_begin + t, lay.o_end + t, lay.o_nph + t * (L + 1));
@@ -1430,7 +1483,21 @@ extern "C" int pygb200_sampler_run(pygb200_sampler* s, int32_t T, int32_t R, int
   PYGB_CHECK(T >= 1 && T <= 1024 && R >= 0 && L >= 0, PYGB200_ERR_ARG, "pygb200_sampler_run: bad T/R/L");
   std::lock_guard<std::mutex> lock(s->mu);
   return sampler_run_impl(s, T, R, L, rels, seeds, n_seeds, num_neighbors, flags, mt, nodes_per_hop, edges_per_hop,
-                          n_nodes_out, n_edges_out, (cudaStream_t)stream, nullptr);
+                          n_nodes_out, n_edges_out, (cudaStream_t)stream, nullptr, nullptr);
+}
+
+extern "C" int pygb200_sampler_run_temporal(pygb200_sampler* s, int32_t T, int32_t R, int32_t L,
+                                            const pygb200_relation* rels, const void* const* seeds,
+                                            const int64_t* n_seeds, const int64_t* num_neighbors, unsigned flags,
+                                            pygb200_mt19937* mt, int64_t* nodes_per_hop, int64_t* edges_per_hop,
+                                            int64_t* n_nodes_out, int64_t* n_edges_out, void* stream,
+                                            const pygb200_temporal* temporal) {
+  PYGB_CHECK(s && seeds && n_seeds && mt && (rels || R == 0) && (num_neighbors || L == 0 || R == 0), PYGB200_ERR_ARG,
+             "pygb200_sampler_run_temporal: null argument");
+  PYGB_CHECK(T >= 1 && T <= 1024 && R >= 0 && L >= 0, PYGB200_ERR_ARG, "pygb200_sampler_run_temporal: bad T/R/L");
+  std::lock_guard<std::mutex> lock(s->mu);
+  return sampler_run_impl(s, T, R, L, rels, seeds, n_seeds, num_neighbors, flags, mt, nodes_per_hop, edges_per_hop,
+                          n_nodes_out, n_edges_out, (cudaStream_t)stream, nullptr, temporal);
 }
 
 extern "C" int pygb200_sampler_run_sharded(pygb200_sampler* s, int32_t T, int32_t R, int32_t L,
@@ -1444,7 +1511,7 @@ extern "C" int pygb200_sampler_run_sharded(pygb200_sampler* s, int32_t T, int32_
   PYGB_CHECK(T >= 1 && T <= 1024 && R >= 0 && L >= 0, PYGB200_ERR_ARG, "pygb200_sampler_run_sharded: bad T/R/L");
   std::lock_guard<std::mutex> lock(s->mu);
   return sampler_run_impl(s, T, R, L, rels, seeds, n_seeds, num_neighbors, flags, mt, nodes_per_hop, edges_per_hop,
-                          n_nodes_out, n_edges_out, (cudaStream_t)stream, shard);
+                          n_nodes_out, n_edges_out, (cudaStream_t)stream, shard, nullptr);
 }
 
 extern "C" int pygb200_sampler_export_edges(pygb200_sampler* s, int32_t rel, void* row_out, void* col_out,

@@ -72,14 +72,20 @@ void check_index_tensor(const at::Tensor& t, const char* name, at::ScalarType st
   TORCH_CHECK(t.dim() == 1, "'", name, "' must be one-dimensional");
 }
 
-void reject_unsupported(bool has_node_time, bool has_edge_time, bool has_seed_time, bool has_weight, bool disjoint) {
-  // reference argument checks first (neighbor_kernel.cpp:354-359), then what this path does not do
+void check_arguments(bool has_node_time, bool has_edge_time, bool has_seed_time, bool has_weight, bool disjoint) {
+  // reference argument checks (neighbor_kernel.cpp:354-380), then what this path does not do
   TORCH_CHECK(!has_node_time || disjoint, "Temporal sampling needs to create disjoint subgraphs");
   TORCH_CHECK(!has_edge_time || disjoint, "Temporal sampling needs to create disjoint subgraphs");
   TORCH_CHECK(!(has_node_time && has_edge_time), "Only one of node-level or edge-level sampling is supported ");
-  TORCH_CHECK(!has_node_time && !has_edge_time && !has_seed_time,
-              "pyg_lib_b200: temporal neighbor sampling is not implemented on the B200 path");
+  TORCH_CHECK(!has_edge_time || has_seed_time, "Seed time needs to be specified");
   TORCH_CHECK(!has_weight, "pyg_lib_b200: biased (edge_weight) neighbor sampling is not implemented on the B200 path");
+}
+
+const int64_t* time_ptr(const at::Tensor& t, const char* name, const at::Device& dev) {
+  TORCH_CHECK(t.is_contiguous(), "Non-contiguous '", name, "'");
+  TORCH_CHECK(t.scalar_type() == at::kLong, "'", name, "' must be int64 (the reference reads temporal_t = int64_t)");
+  TORCH_CHECK(t.device() == dev, "'", name, "' must live on ", dev);
+  return t.data_ptr<int64_t>();
 }
 
 std::tuple<at::Tensor, at::Tensor, at::Tensor, std::optional<at::Tensor>, std::vector<int64_t>, std::vector<int64_t>>
@@ -89,7 +95,7 @@ neighbor_sample_cuda(const at::Tensor& rowptr, const at::Tensor& col, const at::
                      const std::optional<at::Tensor>& edge_weight, bool csc, bool replace, bool directed,
                      bool disjoint, std::string temporal_strategy, bool return_edge_id) {
   TORCH_CHECK(temporal_strategy == "uniform" || temporal_strategy == "last", "No valid temporal strategy found");
-  reject_unsupported(node_time.has_value(), edge_time.has_value(), seed_time.has_value(), edge_weight.has_value(), disjoint);
+  check_arguments(node_time.has_value(), edge_time.has_value(), seed_time.has_value(), edge_weight.has_value(), disjoint);
   TORCH_CHECK(seed.is_cuda(), "pyg_lib_b200: neighbor_sample expects CUDA tensors (no CPU fallback)");
   const auto st = seed.scalar_type();
   TORCH_CHECK(st == at::kLong || st == at::kInt, "neighbor_sample: index tensors must be int64 or int32");
@@ -107,10 +113,19 @@ neighbor_sample_cuda(const at::Tensor& rowptr, const at::Tensor& col, const at::
   std::vector<int64_t> nph(L + 1, 0), eph(L, 0);
   int64_t n_nodes = 0, n_edges = 0;
   {
+    const int64_t* nt = node_time.has_value() ? time_ptr(*node_time, "node_time", seed.device()) : nullptr;
+    const int64_t* et = edge_time.has_value() ? time_ptr(*edge_time, "edge_time", seed.device()) : nullptr;
+    const int64_t* stt = seed_time.has_value() ? time_ptr(*seed_time, "seed_time", seed.device()) : nullptr;
+    if (stt) TORCH_CHECK(seed_time->numel() == seed.numel(), "'seed_time' must have one entry per seed");
+    if (et) TORCH_CHECK(edge_time->numel() == col.numel(), "'edge_time' must have one entry per edge");
+    pygb200_temporal tmp{&nt, &et, &stt, temporal_strategy == "last" ? 1 : 0};
+    pygb200_relation rel{rowptr.data_ptr(), col.data_ptr(), rowptr.numel() - 1, col.numel(), 0, 0};
+    const void* seeds[1] = {seed.data_ptr()};
+    const int64_t n_seed = seed.numel();
     CpuEngine eng;
-    PYGB_TORCH_CALL(pygb200_neighbor_sample_run(s, rowptr.data_ptr(), col.data_ptr(), rowptr.numel() - 1, col.numel(),
-                                                seed.data_ptr(), seed.numel(), num_neighbors.data(), L, flags, &eng.mt,
-                                                nph.data(), eph.data(), &n_nodes, &n_edges, stream));
+    PYGB_TORCH_CALL(pygb200_sampler_run_temporal(s, 1, 1, L, &rel, seeds, &n_seed, num_neighbors.data(), flags, &eng.mt,
+                                                 nph.data(), eph.data(), &n_nodes, &n_edges, stream,
+                                                 (nt || et) ? &tmp : nullptr));
     eng.commit();
   }
   TORCH_CHECK(directed, "Undirected subgraphs not yet supported");  // raised after sampling, neighbor_kernel.cpp:501
@@ -141,8 +156,8 @@ hetero_neighbor_sample_cuda(const std::vector<node_type>& node_types, const std:
                             bool replace, bool directed, bool disjoint, std::string temporal_strategy,
                             bool return_edge_id) {
   TORCH_CHECK(temporal_strategy == "uniform" || temporal_strategy == "last", "No valid temporal strategy found");
-  reject_unsupported(node_time_dict.has_value(), edge_time_dict.has_value(), seed_time_dict.has_value(),
-                     edge_weight_dict.has_value(), disjoint);
+  check_arguments(node_time_dict.has_value(), edge_time_dict.has_value(), seed_time_dict.has_value(),
+                  edge_weight_dict.has_value(), disjoint);
   TORCH_CHECK(seed_dict.size() > 0, "hetero_neighbor_sample: empty 'seed_dict'");
   const at::Tensor& first_seed = seed_dict.begin()->value();
   TORCH_CHECK(first_seed.is_cuda(), "pyg_lib_b200: hetero_neighbor_sample expects CUDA tensors (no CPU fallback)");
@@ -198,9 +213,24 @@ hetero_neighbor_sample_cuda(const std::vector<node_type>& node_types, const std:
   unsigned flags = (replace ? PYGB200_S_REPLACE : 0u) | (disjoint ? PYGB200_S_DISJOINT : 0u) | (idx32 ? PYGB200_S_INDEX32 : 0u);
   std::vector<int64_t> nph((size_t)T * (L + 1), 0), eph((size_t)R * std::max<size_t>(L, 1), 0), n_nodes(T, 0), n_edges(std::max(R, 1), 0);
   {
+    std::vector<const int64_t*> nt(T, nullptr), et(std::max(R, 1), nullptr), stt(T, nullptr);
+    bool any = false;
+    if (node_time_dict.has_value())
+      for (const auto& kv : *node_time_dict)
+        if (tix.count(kv.key())) { nt[tix[kv.key()]] = time_ptr(kv.value(), "node_time", dev); any = true; }
+    if (edge_time_dict.has_value())
+      for (int r = 0; r < R; ++r) {
+        const rel_type rk = to_rel_type(edge_types[r]);
+        if (edge_time_dict->contains(rk)) { et[r] = time_ptr(edge_time_dict->at(rk), "edge_time", dev); any = true; }
+      }
+    if (seed_time_dict.has_value())
+      for (const auto& kv : *seed_time_dict)
+        if (tix.count(kv.key())) stt[tix[kv.key()]] = time_ptr(kv.value(), "seed_time", dev);
+    pygb200_temporal tmp{nt.data(), et.data(), stt.data(), temporal_strategy == "last" ? 1 : 0};
     CpuEngine eng;
-    PYGB_TORCH_CALL(pygb200_sampler_run(s, T, R, (int)L, rels.data(), seeds.data(), n_seeds.data(), nn.data(), flags,
-                                        &eng.mt, nph.data(), eph.data(), n_nodes.data(), n_edges.data(), stream));
+    PYGB_TORCH_CALL(pygb200_sampler_run_temporal(s, T, R, (int)L, rels.data(), seeds.data(), n_seeds.data(), nn.data(), flags,
+                                                 &eng.mt, nph.data(), eph.data(), n_nodes.data(), n_edges.data(), stream,
+                                                 any ? &tmp : nullptr));
     eng.commit();
   }
   TORCH_CHECK(directed, "Undirected heterogeneous graphs not yet supported");  // neighbor_kernel.cpp:824

@@ -22,7 +22,7 @@ sys.path.insert(0, osp.join(ROOT, 'tests'))
 torch.ops.load_library(osp.join(ROOT, 'oracle', '_ref', 'libpyg_ref.so'))
 torch.set_num_threads(1)  # hetero reference is only deterministic single-threaded (neighbor_kernel.cpp:635)
 
-from graphs import HOMO_CASES, HETERO_CASES, MATMUL_CASES, build_homo, build_hetero, build_matmul  # noqa
+from graphs import HOMO_CASES, HETERO_CASES, MATMUL_CASES, build_homo, build_hetero, build_matmul, build_temporal  # noqa
 
 
 def np_(t):
@@ -33,10 +33,13 @@ def main():
     out = {}
     for name, case in HOMO_CASES.items():
         rowptr, col, seed = build_homo(case)
+        nt = et = stt = None
+        if 'temporal' in case:
+            col, nt, et, stt = build_temporal(case, rowptr, col, seed)
         torch.manual_seed(case['rng_seed'])
-        r = torch.ops.pyg.neighbor_sample(rowptr, col, seed, case['num_neighbors'], None, None, None, None,
+        r = torch.ops.pyg.neighbor_sample(rowptr, col, seed, case['num_neighbors'], nt, et, stt, None,
                                           case.get('csc', False), case.get('replace', False), True,
-                                          case.get('disjoint', False), 'uniform', True)
+                                          case.get('disjoint', False), case.get('strategy', 'uniform'), True)
         out[f'homo/{name}/row'] = np_(r[0]); out[f'homo/{name}/col'] = np_(r[1])
         out[f'homo/{name}/node'] = np_(r[2]); out[f'homo/{name}/eid'] = np_(r[3])
         out[f'homo/{name}/nph'] = np_(r[4]); out[f'homo/{name}/eph'] = np_(r[5])

@@ -74,6 +74,43 @@ HOMO_CASES: Dict[str, dict] = {
 }
 
 
+# temporal cases: neighbourhoods sorted by time (node time of the neighbour, or edge time); need disjoint
+HOMO_CASES.update({
+    'temporal_node': dict(graph=('rand', 1500, 14, 41), n_seeds=40, num_neighbors=[5, 4], rng_seed=31, disjoint=True,
+                          temporal='node'),
+    'temporal_node_last': dict(graph=('rand', 1500, 14, 41), n_seeds=40, num_neighbors=[5, 4], rng_seed=31, disjoint=True,
+                               temporal='node', strategy='last'),
+    'temporal_node_seedtime_rep': dict(graph=('rand', 1500, 14, 42), n_seeds=40, num_neighbors=[6, 3], rng_seed=32,
+                                       disjoint=True, temporal='node', seed_time=True, replace=True),
+    'temporal_edge': dict(graph=('rand', 1500, 14, 43), n_seeds=40, num_neighbors=[5, 4], rng_seed=33, disjoint=True,
+                          temporal='edge', seed_time=True),
+    'temporal_edge_last': dict(graph=('rand', 1500, 14, 43), n_seeds=40, num_neighbors=[-1, 3], rng_seed=33, disjoint=True,
+                               temporal='edge', seed_time=True, strategy='last'),
+})
+
+
+def build_temporal(case: dict, rowptr, col, seed):
+    """(col', node_time, edge_time, seed_time) for a temporal case; col' has time-sorted neighbourhoods."""
+    n = rowptr.numel() - 1
+    g = torch.Generator().manual_seed(5000 + case['rng_seed'])
+    node_time = edge_time = seed_time = None
+    deg = rowptr[1:] - rowptr[:-1]
+    row_of_edge = torch.repeat_interleave(torch.arange(n), deg)
+    if case['temporal'] == 'node':
+        node_time = torch.randint(0, 50, (n,), generator=g)
+        key = row_of_edge * 1000 + node_time[col]          # sort each neighbourhood by neighbour time (stable)
+        order = torch.sort(key, stable=True).indices
+        col = col[order]
+    else:
+        et = torch.randint(0, 50, (col.numel(),), generator=g)
+        key = row_of_edge * 1000 + et
+        order = torch.sort(key, stable=True).indices
+        col, edge_time = col[order], et[order]
+    if case.get('seed_time'):
+        seed_time = torch.randint(5, 60, (seed.numel(),), generator=g)
+    return col.contiguous(), node_time, edge_time, seed_time
+
+
 def build_homo(case: dict):
     g = case['graph']
     if g[0] == 'cycle':

@@ -4,7 +4,8 @@ import numpy as np
 import pytest
 import torch
 
-from graphs import (HETERO_CASES, HOMO_CASES, MATMUL_CASES, build_hetero, build_homo, build_matmul, cycle_graph)
+from graphs import (HETERO_CASES, HOMO_CASES, MATMUL_CASES, build_hetero, build_homo, build_matmul, build_temporal,
+                    cycle_graph)
 from oracle import oracle as O
 
 
@@ -81,11 +82,15 @@ def _rng_prefix():
 def test_homo_matches_reference(name, golden):
     case = HOMO_CASES[name]
     rowptr, col, seed = build_homo(case)
+    nt = et = stt = None
+    if 'temporal' in case:
+        col, nt, et, stt = build_temporal(case, rowptr, col, seed)
     torch.manual_seed(case['rng_seed'])
-    row, colv, node, eid, nph, eph = O.neighbor_sample(rowptr, col, seed, case['num_neighbors'],
-                                                        csc=case.get('csc', False),
+    row, colv, node, eid, nph, eph = O.neighbor_sample(rowptr, col, seed, case['num_neighbors'], node_time=nt,
+                                                        edge_time=et, seed_time=stt, csc=case.get('csc', False),
                                                         replace=case.get('replace', False),
-                                                        disjoint=case.get('disjoint', False))
+                                                        disjoint=case.get('disjoint', False),
+                                                        temporal_strategy=case.get('strategy', 'uniform'))
     p = f'homo/{name}/'
     assert np.array_equal(row.numpy(), golden[p + 'row'])
     assert np.array_equal(colv.numpy(), golden[p + 'col'])
@@ -135,3 +140,31 @@ def test_matmul_matches_reference(name, golden):
         exp = (x[a:b].float() @ w[i].float()).numpy()
         tol = 1e-5 if case['dtype'] == 'float32' else 2e-2
         assert np.allclose(out[a:b], exp, atol=tol, rtol=tol)
+
+
+# ---- temporal known-answer vectors, test/csrc/sampler/test_neighbor.cpp:146-257 --------------------------
+def test_kat_node_temporal():
+    rowptr, col = cycle_graph(6)
+    node_time = torch.arange(6)
+    col = torch.sort(col.view(-1, 2), dim=1).values.flatten()
+    out1 = O.neighbor_sample(rowptr, col, torch.arange(2, 4), [2, 2], node_time=node_time, disjoint=True)
+    assert out1[0].tolist() == [0, 1, 2, 2, 3, 3] and out1[1].tolist() == [2, 3, 4, 0, 5, 1]
+    assert out1[2].flatten().tolist() == [0, 2, 1, 3, 0, 1, 1, 2, 0, 0, 1, 1]
+    assert out1[3].tolist() == [4, 6, 2, 3, 4, 5]
+    out2 = O.neighbor_sample(rowptr, col, torch.arange(2, 4), [1, 2], node_time=node_time, disjoint=True,
+                             temporal_strategy='last')
+    for a, b in zip(out1[:4], out2[:4]):
+        assert torch.equal(a, b)
+
+
+def test_kat_edge_temporal():
+    rowptr, col = cycle_graph(6)
+    edge_time = torch.arange(col.numel())
+    out = O.neighbor_sample(rowptr, col, torch.arange(2, 4), [2, 2], edge_time=edge_time, seed_time=torch.arange(5, 7),
+                            disjoint=True)
+    assert out[0].tolist() == [0, 0, 1, 2, 2, 4, 4] and out[1].tolist() == [2, 3, 4, 5, 0, 6, 1]
+    assert out[2].flatten().tolist() == [0, 2, 1, 3, 0, 1, 0, 3, 1, 2, 0, 0, 1, 1]
+    assert out[3].tolist() == [4, 5, 6, 2, 3, 4, 5]
+    out2 = O.neighbor_sample(rowptr, col, torch.arange(2, 4), [1, 1], edge_time=edge_time,
+                             seed_time=torch.tensor([-1, -1]), disjoint=True, replace=True)
+    assert out2[0].numel() == 0 and out2[2].flatten().tolist() == [0, 2, 1, 3]

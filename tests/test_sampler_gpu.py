@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 import torch
 
-from graphs import HETERO_CASES, HOMO_CASES, build_hetero, build_homo, lognormal_csr, random_csr
+from graphs import HETERO_CASES, HOMO_CASES, build_hetero, build_homo, build_temporal, lognormal_csr, random_csr
 from oracle import oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -42,10 +42,16 @@ def _cmp(out, exp):
 def test_homo_golden(lib, golden, name, dtype):
     case = HOMO_CASES[name]
     rowptr, col, seed = build_homo(case)
+    nt = et = stt = None
+    if 'temporal' in case:
+        col, nt, et, stt = build_temporal(case, rowptr, col, seed)
+    dv = lambda t: None if t is None else t.to(DEV)  # noqa: E731  (times stay int64)
     torch.manual_seed(case['rng_seed'])
     out = lib.sampler.neighbor_sample(rowptr.to(DEV, dtype), col.to(DEV, dtype), seed.to(DEV, dtype),
-                                      case['num_neighbors'], csc=case.get('csc', False),
-                                      replace=case.get('replace', False), disjoint=case.get('disjoint', False))
+                                      case['num_neighbors'], node_time=dv(nt), edge_time=dv(et), seed_time=dv(stt),
+                                      csc=case.get('csc', False), replace=case.get('replace', False),
+                                      disjoint=case.get('disjoint', False),
+                                      temporal_strategy=case.get('strategy', 'uniform'))
     p = f'homo/{name}/'
     assert out[0].dtype == dtype and out[2].dtype == dtype
     assert out[4] == golden[p + 'nph'].tolist() and out[5] == golden[p + 'eph'].tolist()
@@ -146,6 +152,8 @@ def test_errors(lib):
         lib.sampler.neighbor_sample(r, c, s, [2], node_time=torch.zeros(100, dtype=torch.long, device=DEV))
     with pytest.raises(RuntimeError, match='not implemented on the B200 path'):
         lib.sampler.neighbor_sample(r, c, s, [2], edge_weight=torch.ones(col.numel(), device=DEV))
+    with pytest.raises(RuntimeError, match='Seed time needs to be specified'):
+        lib.sampler.neighbor_sample(r, c, s, [2], edge_time=torch.zeros(col.numel(), dtype=torch.long, device=DEV), disjoint=True)
     with pytest.raises(RuntimeError, match='Non-contiguous'):
         lib.sampler.neighbor_sample(r, torch.stack([c, c], 1)[:, 0], s, [2])
     with pytest.raises((RuntimeError, NotImplementedError)):
@@ -269,3 +277,48 @@ def test_large_batch_jump_ahead(lib):
         _cmp(lib.sampler.neighbor_sample(d[0], d[1], d[2], [10, 8]), exp[i])
     assert np.array_equal(_rng_prefix(), s_exp)
     assert exp[0][0].numel() > 1_000_000
+
+
+def test_temporal_kat_and_hetero(lib):
+    """test/csrc/sampler/test_neighbor.cpp:146-257 on the GPU + a hetero temporal run vs the oracle."""
+    from graphs import cycle_graph
+    rowptr, col = cycle_graph(6)
+    node_time = torch.arange(6)
+    colS = torch.sort(col.view(-1, 2), dim=1).values.flatten()
+    out1 = lib.sampler.neighbor_sample(rowptr.to(DEV), colS.to(DEV), torch.arange(2, 4, device=DEV), [2, 2],
+                                       node_time=node_time.to(DEV), disjoint=True)
+    assert out1[0].tolist() == [0, 1, 2, 2, 3, 3] and out1[1].tolist() == [2, 3, 4, 0, 5, 1]
+    assert out1[2].flatten().tolist() == [0, 2, 1, 3, 0, 1, 1, 2, 0, 0, 1, 1] and out1[3].tolist() == [4, 6, 2, 3, 4, 5]
+    out2 = lib.sampler.neighbor_sample(rowptr.to(DEV), colS.to(DEV), torch.arange(2, 4, device=DEV), [1, 2],
+                                       node_time=node_time.to(DEV), disjoint=True, temporal_strategy='last')
+    assert all(torch.equal(a, b) for a, b in zip(out1[:4], out2[:4]))
+    et = torch.arange(col.numel())
+    out = lib.sampler.neighbor_sample(rowptr.to(DEV), col.to(DEV), torch.arange(2, 4, device=DEV), [2, 2],
+                                      edge_time=et.to(DEV), seed_time=torch.arange(5, 7, device=DEV), disjoint=True)
+    assert out[0].tolist() == [0, 0, 1, 2, 2, 4, 4] and out[1].tolist() == [2, 3, 4, 5, 0, 6, 1]
+    assert out[3].tolist() == [4, 5, 6, 2, 3, 4, 5]
+    # hetero: node times on every type, neighbourhoods sorted by neighbour time
+    case = HETERO_CASES['mag_disjoint']
+    nt, etypes, rp, cl, sd, nn = build_hetero(case)
+    g = torch.Generator().manual_seed(77)
+    times = {t: torch.randint(0, 30, (case['sizes'][t],), generator=g) for t in nt}
+    for k in etypes:
+        rk = '__'.join(k)
+        deg = rp[rk][1:] - rp[rk][:-1]
+        rows = torch.repeat_interleave(torch.arange(deg.numel()), deg)
+        order = torch.sort(rows * 1000 + times[k[2]][cl[rk]], stable=True).indices
+        cl[rk] = cl[rk][order].contiguous()
+    for strategy in ('uniform', 'last'):
+        torch.manual_seed(5)
+        exp = O.hetero_neighbor_sample(nt, etypes, rp, cl, sd, nn, disjoint=True, node_time_dict=times,
+                                       temporal_strategy=strategy)
+        torch.manual_seed(5)
+        out = torch.ops.pyg.hetero_neighbor_sample(nt, etypes, {k: v.to(DEV) for k, v in rp.items()},
+                                                   {k: v.to(DEV) for k, v in cl.items()}, {k: v.to(DEV) for k, v in sd.items()},
+                                                   nn, {k: v.to(DEV) for k, v in times.items()}, None, None, None, False, False,
+                                                   True, True, strategy, True)
+        for k in rp:
+            assert torch.equal(out[0][k].cpu(), exp[0][k]) and torch.equal(out[1][k].cpu(), exp[1][k]), k
+            assert torch.equal(out[3][k].cpu(), exp[3][k]) and out[5][k] == exp[5][k]
+        for t in nt:
+            assert torch.equal(out[2][t].cpu(), exp[2][t]) and out[4][t] == exp[4][t]
