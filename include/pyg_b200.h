@@ -190,6 +190,11 @@ int pygb200_sampler_export_edges(pygb200_sampler* s, int32_t rel, void* row_out,
 int pygb200_sampler_export_nodes(pygb200_sampler* s, int32_t type, void* node_id_out, int index32,
                                  void* stream);
 
+/* Both of the above for one relation and one node type in a single launch (homogeneous fast path). */
+int pygb200_sampler_export_all(pygb200_sampler* s, int32_t rel, void* row_out, void* col_out,
+                               void* edge_id_out, int32_t type, void* node_id_out, int index32,
+                               void* stream);
+
 /* Homogeneous convenience wrapper == T=1, R=1 (neighbor_sample_kernel, neighbor_kernel.cpp:899-926). */
 int pygb200_neighbor_sample_run(pygb200_sampler* s, const void* rowptr, const void* col,
                                 int64_t num_nodes, int64_t num_edges, const void* seed,

@@ -138,6 +138,14 @@ struct PassArgs {
 };
 
 // ------------------------------------------------------------------------------------- helpers
+// Programmatic dependent launch: the kernels of a run form a chain on one stream.  Each waits for its
+// predecessor's completion + memory flush here, then lets its successor's blocks be scheduled early
+// (they park in their own pdl_enter), which hides launch latency and the block-scheduling ramp.
+__device__ __forceinline__ void pdl_enter() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 __device__ __forceinline__ u64 hash64(u64 x) {
   x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33;
   return x;
@@ -351,6 +359,7 @@ __device__ __forceinline__ void deferred_lookup(const PassArgs& a) {
 template <typename idx_t>
 __global__ void __launch_bounds__(NT) k_count(const PassArgs a) {
   __shared__ u32 s_win[MT_WIN];
+  pdl_enter();
   deferred_lookup(a);  // must precede the ticket: the last block overwrites ST_PASS_E / ST_PASS_BASE
   const i64 begin = a.st[a.o_src_begin], end = a.st[a.o_src_end];
   const i64 F = end - begin;
@@ -410,6 +419,7 @@ __global__ void __launch_bounds__(NT) k_count(const PassArgs a) {
 // One group of G lanes per frontier node.
 template <typename idx_t, int G>
 __global__ void __launch_bounds__(NT) k_sample(const PassArgs a) {
+  pdl_enter();
   const i64 F = a.st[ST_PASS_F];
   const i64 begin = a.st[a.o_src_begin];
   const i64 pbase = a.st[ST_PASS_BASE];
@@ -518,6 +528,7 @@ __global__ void __launch_bounds__(NT) k_seed(const PassArgs a, const idx_t* __re
 // updates the dst type's counters.
 __global__ void __launch_bounds__(NT) k_mark(const PassArgs a) {
   __shared__ u32 s_w[NT / 32];
+  pdl_enter();
   const i64 E = a.st[ST_PASS_E];
   const i64 ntiles = ceil_div(E, ETILE);
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -602,7 +613,135 @@ __global__ void __launch_bounds__(NT) k_mark(const PassArgs a) {
   }
 }
 
+// k_mark + k_assign in one launch (bounded, non-seed passes): tiles of 1024 edges are claimed in order
+// through a ticket; every tile publishes {epoch | status | value} — first its count of first occurrences
+// (status 1), then, after a decoupled look-back over the preceding tiles (warp 0, 32 tiles per step), its
+// inclusive prefix (status 2) — and assigns ids straight away.  The epoch makes stale words from earlier
+// launches invisible, so the tile array never needs clearing.  The block that finishes the last tile does
+// the counter / end-of-hop bookkeeping; ids_base / list_base are read before a block takes its first
+// ticket, i.e. strictly before the last tile can complete, so they are stable for every reader.
+__device__ __forceinline__ u64 tile_word(u32 epoch, u32 status, u32 value) {
+  return ((u64)epoch << 32) | ((u64)status << 30) | (u64)value;
+}
+__global__ void __launch_bounds__(NT) k_mark_assign(const PassArgs a, u32 epoch) {
+  __shared__ u32 s_w[NT / 32];
+  __shared__ i64 s_ticket;
+  __shared__ u32 s_excl;
+  pdl_enter();
+  const i64 E = a.st[ST_PASS_E], pbase = a.st[ST_PASS_BASE];
+  const i64 ids_base = a.st[a.o_dst_ids], list_base = a.st[a.o_dst_list];
+  const i64 ntiles = ceil_div(E, ETILE);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  volatile u64* tiles = reinterpret_cast<volatile u64*>(a.mtile);
+  u64* ticket = reinterpret_cast<u64*>(&a.st[ST_TICKET_B]);
+  while (true) {
+    __syncthreads();
+    if (threadIdx.x == 0) s_ticket = (i64)atomicAdd(ticket, 1ull);
+    __syncthreads();
+    const i64 tile = s_ticket;
+    if (tile >= ntiles) {
+      if (threadIdx.x == 0) {
+        if (tile == ntiles + (i64)gridDim.x - 1) *ticket = 0;   // the very last draw of this launch
+        if (ntiles == 0 && tile == 0) {                          // nothing emitted: only the bookkeeping remains
+          a.st[ST_PASS_NEW] = 0;
+          a.st[ST_LIST_BASE] = list_base; a.st[ST_IDS_BASE] = ids_base;
+        }
+      }
+      if (ntiles == 0 && tile == 0) {
+        __syncthreads();
+        for (int t = threadIdx.x; t < a.he_T; t += NT) {
+          const i64 n = a.st[a.he_list + t], e = a.st[a.he_end + t];
+          a.st[a.he_nph + t * (a.he_L + 1) + a.he_hop + 1] = n - e;
+          a.st[a.he_begin + t] = e;
+          a.st[a.he_end + t] = n;
+        }
+      }
+      break;
+    }
+    const i64 p0 = tile * ETILE + threadIdx.x * 4;
+    u32 fl[4], sl[4]; u32 cnt = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const i64 p = p0 + q;
+      fl[q] = 0; sl[q] = 0;
+      if (p < E) { sl[q] = a.eslot[p]; fl[q] = (a.vals[sl[q]] == POS_BASE + (u64)p) ? 1u : 0u; }
+      cnt += fl[q];
+    }
+    u32 inc = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const u32 o = __shfl_up_sync(0xffffffffu, inc, d);
+      if (lane >= d) inc += o;
+    }
+    if (lane == 31) s_w[wid] = inc;
+    __syncthreads();
+    u32 pre = 0, tot = 0;
+    for (int w = 0; w < NT / 32; ++w) { if (w < wid) pre += s_w[w]; tot += s_w[w]; }
+    if (wid == 0) {
+      u32 excl = 0;
+      if (tile > 0) {
+        if (lane == 0) tiles[tile] = tile_word(epoch, 1, tot);
+        i64 base = tile - 1;
+        while (true) {
+          const i64 idx = base - lane;
+          u64 w = idx >= 0 ? tiles[idx] : tile_word(epoch, 2, 0);   // virtual tile -1: prefix 0
+          const bool valid = (u32)(w >> 32) == epoch && ((w >> 30) & 3u) != 0;
+          const bool is_pre = valid && ((w >> 30) & 3u) == 2;
+          const unsigned bv = __ballot_sync(0xffffffffu, valid), bp = __ballot_sync(0xffffffffu, is_pre);
+          const int first_pre = bp ? (__ffs(bp) - 1) : 32;          // nearest tile that already knows its prefix
+          const unsigned need = first_pre >= 31 ? 0xffffffffu : ((2u << first_pre) - 1u);
+          if ((bv & need) != need) continue;                        // somebody in range has not published yet: poll again
+          u32 v = (lane <= first_pre) ? (u32)(w & 0x3fffffffu) : 0u;
+#pragma unroll
+          for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+          excl += v;
+          if (bp) break;
+          base -= 32;
+        }
+      }
+      if (lane == 0) {
+        __threadfence();
+        tiles[tile] = tile_word(epoch, 2, excl + tot);
+        s_excl = excl;
+      }
+    }
+    __syncthreads();
+    const u32 excl = s_excl;
+    u32 ex = excl + pre + inc - cnt;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (fl[q]) {
+        const i64 p = p0 + q;
+        const i64 rank = ex;
+        a.vals[sl[q]] = (u64)(ids_base + rank);
+        a.dst_nodes[list_base + rank] = a.colv[pbase + p];
+        if (a.disjoint) a.dst_batch[list_base + rank] = a.src_batch[a.row[pbase + p]];
+        a.dst_slot[list_base + rank] = sl[q];
+      }
+      ex += fl[q];
+    }
+    if (tile == ntiles - 1) {   // last tile: excl + tot == number of new nodes of the pass
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        const i64 nnew = (i64)excl + tot;
+        a.st[ST_PASS_NEW] = nnew;
+        a.st[ST_LIST_BASE] = list_base; a.st[ST_IDS_BASE] = ids_base;
+        a.st[a.o_dst_list] = list_base + nnew;
+        a.st[a.o_dst_ids] = ids_base + nnew;
+      }
+      __syncthreads();
+      for (int t = threadIdx.x; t < a.he_T; t += NT) {
+        const i64 n = a.st[a.he_list + t], e = a.st[a.he_end + t];
+        a.st[a.he_nph + t * (a.he_L + 1) + a.he_hop + 1] = n - e;
+        a.st[a.he_begin + t] = e;
+        a.st[a.he_end + t] = n;
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(NT) k_assign(const PassArgs a) {
+  pdl_enter();
   const i64 E = a.st[ST_PASS_E];
   const i64 pbase = a.st[ST_PASS_BASE];
   const i64 list_base = a.st[ST_LIST_BASE], ids_base = a.st[ST_IDS_BASE];
@@ -654,8 +793,9 @@ __global__ void k_seed_end(i64* st, int t, int L, int o_list, int o_begin, int o
 // Last kernel of a run: deferred lookup of the last pass + (block 0) final engine state = the
 // generation holding the last consumed output (see mt19937.cuh); at least one 128-word block is
 // always consumed (rand_engine.h:28).
-__global__ void __launch_bounds__(NT) k_final(const PassArgs a, int o_mt) {
+__global__ void __launch_bounds__(NT) k_final(const PassArgs a, int o_mt, i64* host_st, int n_words, i64 serial) {
   __shared__ u32 s_win[MT_WIN];
+  pdl_enter();
   deferred_lookup(a);
   if (blockIdx.x != 0) return;
   const i64 blocks = rng_blocks_for_units(a.st[ST_CURSOR]);
@@ -670,6 +810,16 @@ __global__ void __launch_bounds__(NT) k_final(const PassArgs a, int o_mt) {
     a.st[ST_MT_LEFT] = 625 - nxt;
     a.st[ST_BLOCKS] = blocks;
   }
+  // publish the counters + engine state straight into mapped host memory; the host polls the flag word
+  // (no DMA copy, no event round trip).  Other blocks may still be doing the deferred lookup — the host
+  // only needs the counters, everything else it does is stream-ordered behind this kernel.
+  __syncthreads();
+  if (host_st) {
+    for (int i = threadIdx.x; i < n_words; i += blockDim.x) host_st[i] = a.st[i];
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) { *reinterpret_cast<volatile i64*>(host_st + n_words) = serial; __threadfence_system(); }
+  }
 }
 
 // Seeds of one node type in ONE block (n <= SEED_FUSED_MAX): list, insert, first-occurrence ranks, ids.
@@ -681,6 +831,7 @@ __global__ void __launch_bounds__(SEED_NT) k_seed_fused(const PassArgs a, const 
                                                          int L, int o_begin, int o_end, int o_nph) {
   __shared__ int s_w[SEED_NT / 32];
   __shared__ int s_carry;
+  pdl_enter();
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   for (int i = threadIdx.x; i < n; i += SEED_NT) {
     const i64 v = (i64)seeds[i];
@@ -723,6 +874,7 @@ __global__ void __launch_bounds__(SEED_NT) k_seed_fused(const PassArgs a, const 
 }
 
 __global__ void __launch_bounds__(NT) k_cleanup(u64* keys, u64* vals, const u32* __restrict__ slots, const i64* n_ptr) {
+  pdl_enter();
   const i64 n = *n_ptr;
   for (i64 i = (i64)blockIdx.x * NT + threadIdx.x; i < n; i += (i64)gridDim.x * NT) {
     const u32 s = slots[i];
@@ -754,6 +906,26 @@ __global__ void __launch_bounds__(NT) k_export3(const i64* __restrict__ s0, cons
     if (d0) d0[i] = (out_t)s0[i];
     if (d1) d1[i] = (out_t)s1[i];
     if (d2) d2[i] = (out_t)s2[i];
+  }
+}
+// one relation's edges + one type's node list in a single launch (homogeneous fast path)
+template <typename out_t>
+__global__ void __launch_bounds__(NT) k_export4(const i64* __restrict__ s0, const i64* __restrict__ s1, const i64* __restrict__ s2,
+                                                 out_t* __restrict__ d0, out_t* __restrict__ d1, out_t* __restrict__ d2, i64 n_edges,
+                                                 const i64* __restrict__ node, const i64* __restrict__ batch, out_t* __restrict__ dn,
+                                                 i64 n_nodes) {
+  pdl_enter();
+  const i64 n = n_edges > n_nodes ? n_edges : n_nodes;
+  for (i64 i = (i64)blockIdx.x * NT + threadIdx.x; i < n; i += (i64)gridDim.x * NT) {
+    if (i < n_edges) {
+      if (d0) d0[i] = (out_t)s0[i];
+      if (d1) d1[i] = (out_t)s1[i];
+      if (d2) d2[i] = (out_t)s2[i];
+    }
+    if (i < n_nodes && dn) {
+      if (batch) { dn[2 * i] = (out_t)batch[i]; dn[2 * i + 1] = (out_t)node[i]; }
+      else dn[i] = (out_t)node[i];
+    }
   }
 }
 template <typename out_t>
@@ -801,7 +973,10 @@ struct pygb200_sampler {
   std::vector<TypeBuf> types;
   std::vector<RelBuf> rels;
   DevBuf eslot, erank, rec, tile_out, tile_func, tile_off, tile_pos, mtile, raw, st, gen;
-  i64* st_host = nullptr;   // pinned mirror of the state buffer
+  i64* st_host = nullptr;   // pinned + mapped mirror of the state buffer (k_final writes it directly)
+  i64* st_host_dev = nullptr;   // device-side address of st_host
+  i64 run_serial = 0;       // completion flag value of the current run
+  unsigned epoch = 0;       // tag of the tile words of k_mark_assign launches
   // persistent mt19937 raw stream: survives between runs while torch's CPU generator is exactly where
   // the previous run left it (the common case in a sampling loop) and is extended ahead of time on a
   // side stream, so that generation stays off the critical path of the next run.
@@ -946,6 +1121,19 @@ int ensure_edge_scratch(pygb200_sampler* s, i64 E, cudaStream_t st) {
   return PYGB200_OK;
 }
 
+// launch with the programmatic-stream-serialization attribute (see pdl_enter)
+template <typename... KP, typename... A>
+cudaError_t launch_pdl(void (*kernel)(KP...), int grid, int block, cudaStream_t st, A... args) {
+  static const bool off = getenv("PYGB200_NO_PDL") != nullptr;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = off ? 0 : 1;
+  return cudaLaunchKernelEx(&cfg, kernel, KP(args)...);
+}
+
 // jump-ahead table: mt19937_jump.bin next to this shared library (optional; without it generation is serial)
 void load_jump_table(pygb200_sampler* s, cudaStream_t st) {
   if (s->jump_tried) return;
@@ -1009,7 +1197,7 @@ int launch_count(pygb200_sampler* s, const PassArgs& a, i64 F, i64 E_prev, cudaS
   // the grid also has to cover the deferred lookup of the previous pass (E_prev edges)
   const int g = std::max(grid_for(F, NT, s->sm_count), a.lk_colv ? grid_for(E_prev, NT, s->sm_count) : 1);
   void* tk = prof_begin(st);
-  k_count<idx_t><<<g, NT, 0, st>>>(a);
+  launch_pdl(k_count<idx_t>, g, NT, st, a);
   prof_end(tk, "count", st, F);
   PYGB_LAUNCH_CHECK();
   return PYGB200_OK;
@@ -1022,10 +1210,10 @@ int launch_sample(pygb200_sampler* s, const PassArgs& a, i64 F, i64 E, cudaStrea
   const int gs = grid_for(F, NT / G, s->sm_count);
   void* tk = prof_begin(st);
   switch (G) {
-    case 4: k_sample<idx_t, 4><<<gs, NT, 0, st>>>(a); break;
-    case 8: k_sample<idx_t, 8><<<gs, NT, 0, st>>>(a); break;
-    case 16: k_sample<idx_t, 16><<<gs, NT, 0, st>>>(a); break;
-    default: k_sample<idx_t, 32><<<gs, NT, 0, st>>>(a); break;
+    case 4: launch_pdl(k_sample<idx_t, 4>, gs, NT, st, a); break;
+    case 8: launch_pdl(k_sample<idx_t, 8>, gs, NT, st, a); break;
+    case 16: launch_pdl(k_sample<idx_t, 16>, gs, NT, st, a); break;
+    default: launch_pdl(k_sample<idx_t, 32>, gs, NT, st, a); break;
   }
   prof_end(tk, "sample", st, E);
   PYGB_LAUNCH_CHECK();
@@ -1035,12 +1223,20 @@ int launch_sample(pygb200_sampler* s, const PassArgs& a, i64 F, i64 E, cudaStrea
 template <typename idx_t>
 int launch_rest(pygb200_sampler* s, const PassArgs& a, i64 F, i64 E, bool lookup_now, cudaStream_t st, bool with_sample = true) {
   if (with_sample) if (int e = launch_sample<idx_t>(s, a, F, E, st)) return e;
+  static const bool no_fuse = getenv("PYGB200_NO_FUSE") != nullptr;
+  if (!lookup_now && !a.seed_mode && E < ((i64)1 << 30) && !no_fuse) {   // bounded path: mark + assign in one launch
+    void* tk2 = prof_begin(st);
+    launch_pdl(k_mark_assign, grid_for(E, ETILE, s->sm_count), NT, st, a, (u32)(++s->epoch));
+    prof_end(tk2, "mark", st, E);
+    PYGB_LAUNCH_CHECK();
+    return PYGB200_OK;
+  }
   void* tk = prof_begin(st);
-  k_mark<<<grid_for(E, ETILE, s->sm_count), NT, 0, st>>>(a);
+  launch_pdl(k_mark, grid_for(E, ETILE, s->sm_count), NT, st, a);
   prof_end(tk, "mark", st, E);
   PYGB_LAUNCH_CHECK();
   tk = prof_begin(st);
-  k_assign<<<grid_for(E, NT, s->sm_count), NT, 0, st>>>(a);
+  launch_pdl(k_assign, grid_for(E, NT, s->sm_count), NT, st, a);
   prof_end(tk, "assign", st, E);
   PYGB_LAUNCH_CHECK();
   if (lookup_now) {
@@ -1139,7 +1335,9 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
   if (lay.words > s->st_words) {
     if (s->st_host) cudaFreeHost(s->st_host);
     s->st_host = nullptr; s->st_words = 0;
-    PYGB_CUDA(cudaHostAlloc((void**)&s->st_host, lay.words * 8, cudaHostAllocDefault));
+    PYGB_CUDA(cudaHostAlloc((void**)&s->st_host, (lay.words + 8) * 8, cudaHostAllocMapped));
+    PYGB_CUDA(cudaHostGetDevicePointer((void**)&s->st_host_dev, s->st_host, 0));
+    memset(s->st_host, 0, (lay.words + 8) * 8);
     s->st_words = lay.words;
   }
   if (int e = s->st.ensure(lay.words * 8, 0, st)) return e;
@@ -1292,19 +1490,19 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
       PYGB_LAUNCH_CHECK();
     }
     if (n_seeds[t] > 0 && n_seeds[t] <= SEED_FUSED_MAX) {
-      if (idx32) k_seed_fused<int32_t><<<1, SEED_NT, 0, st>>>(a, (const int32_t*)seeds[t], (int)n_seeds[t], batch0, L,
-                                                              lay.o_begin + t, lay.o_end + t, lay.o_nph + t * (L + 1));
-      else k_seed_fused<int64_t><<<1, SEED_NT, 0, st>>>(a, (const int64_t*)seeds[t], (int)n_seeds[t], batch0, L,
-                                                        lay.o_begin + t, lay.o_end + t, lay.o_nph + t * (L + 1));
+      if (idx32) launch_pdl(k_seed_fused<int32_t>, 1, SEED_NT, st, a, (const int32_t*)seeds[t], (int)n_seeds[t], batch0, (int)L,
+                            lay.o_begin + t, lay.o_end + t, lay.o_nph + t * (L + 1));
+      else launch_pdl(k_seed_fused<int64_t>, 1, SEED_NT, st, a, (const int64_t*)seeds[t], (int)n_seeds[t], batch0, (int)L,
+                      lay.o_begin + t, lay.o_end + t, lay.o_nph + t * (L + 1));
       PYGB_LAUNCH_CHECK();
     } else if (n_seeds[t] > 0) {
       const int g = grid_for(n_seeds[t], NT, s->sm_count);
       if (idx32) k_seed<int32_t><<<g, NT, 0, st>>>(a, (const int32_t*)seeds[t], n_seeds[t], batch0);
       else k_seed<int64_t><<<g, NT, 0, st>>>(a, (const int64_t*)seeds[t], n_seeds[t], batch0);
       PYGB_LAUNCH_CHECK();
-      k_mark<<<grid_for(n_seeds[t], ETILE, s->sm_count), NT, 0, st>>>(a);
+      launch_pdl(k_mark, grid_for(n_seeds[t], ETILE, s->sm_count), NT, st, a);
       PYGB_LAUNCH_CHECK();
-      k_assign<<<g, NT, 0, st>>>(a);
+      launch_pdl(k_assign, g, NT, st, a);
       PYGB_LAUNCH_CHECK();
       k_seed_end<<<1, 1, 0, st>>>(dst, t, L, lay.o_list, lay.o_begin, lay.o_end, lay.o_nph);
       PYGB_LAUNCH_CHECK();
@@ -1416,24 +1614,37 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
   {
     PassArgs a = make_args(-1, 0, -1);
     a.lk_colv = lk_colv; a.lk_vals = lk_vals;
-    k_final<<<lk_colv ? grid_for(lk_E, NT, s->sm_count) : 1, NT, 0, st>>>(a, lay.o_mt);
+    s->run_serial += 1;
+    launch_pdl(k_final, lk_colv ? grid_for(lk_E, NT, s->sm_count) : 1, NT, st, a, lay.o_mt, s->st_host_dev, (int)lay.words,
+               s->run_serial);
     PYGB_LAUNCH_CHECK();
   }
-  PYGB_CUDA(cudaMemcpyAsync(s->st_host, dst, lay.words * 8, cudaMemcpyDeviceToHost, st));
-  // table cleanup is stream-ordered after the copy; the host does not wait for it
-  cudaEvent_t copied;
-  PYGB_CUDA(cudaEventCreateWithFlags(&copied, cudaEventDisableTiming));
-  PYGB_CUDA(cudaEventRecord(copied, st));
+  // table cleanup is stream-ordered after k_final; the host does not wait for it
   for (int t = 0; t < T; ++t) {
     auto& tb = s->types[t];
     const i64 cap_nodes = (i64)(tb.slot.cap / 4);
-    k_cleanup<<<grid_for(synced ? cap_nodes : node_cap[t], NT, s->sm_count), NT, 0, st>>>(
-        tb.keys.as<u64>(), tb.vals.as<u64>(), tb.slot.as<u32>(), dst + lay.o_list + t);
+    launch_pdl(k_cleanup, grid_for(synced ? cap_nodes : node_cap[t], NT, s->sm_count), NT, st, tb.keys.as<u64>(), tb.vals.as<u64>(),
+               (const u32*)tb.slot.as<u32>(), (const i64*)(dst + lay.o_list + t));
     PYGB_LAUNCH_CHECK();
   }
-  cudaError_t werr = cudaEventSynchronize(copied);
-  cudaEventDestroy(copied);
-  PYGB_CUDA(werr);
+  {  // wait for k_final's flag (spin on mapped memory; keep an eye on the stream in case the run died)
+    volatile i64* flag = s->st_host + lay.words;
+    unsigned long long spins = 0;
+    while (*flag != s->run_serial) {
+      if ((++spins & 0xfffff) == 0) {
+        const cudaError_t q = cudaStreamQuery(st);
+        if (q != cudaErrorNotReady) {
+          if (q == cudaSuccess && *flag == s->run_serial) break;
+          set_error(std::string("sampler: run did not complete: ") + cudaGetErrorString(q == cudaSuccess ? cudaErrorUnknown : q));
+          return PYGB200_ERR_CUDA;
+        }
+      }
+#if defined(__x86_64__)
+      __builtin_ia32_pause();
+#endif
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+  }
   const i64* hs = s->st_host;
   PYGB_CHECK(hs[ST_ERROR] == 0, PYGB200_ERR_INTERNAL, "sampler: mt19937 stream buffer too small (internal bound violated)");
   s->dirty = false;
@@ -1524,6 +1735,26 @@ extern "C" int pygb200_sampler_export_edges(pygb200_sampler* s, int32_t rel, voi
   const i64 *s0 = s->rels[rel].row.as<i64>(), *s1 = s->rels[rel].colv.as<i64>(), *s2 = s->rels[rel].eid.as<i64>();
   if (index32) k_export3<int32_t><<<g, NT, 0, st>>>(s0, s1, s2, (int32_t*)row_out, (int32_t*)col_out, (int32_t*)edge_id_out, n);
   else k_export3<int64_t><<<g, NT, 0, st>>>(s0, s1, s2, (int64_t*)row_out, (int64_t*)col_out, (int64_t*)edge_id_out, n);
+  PYGB_LAUNCH_CHECK();
+  return PYGB200_OK;
+}
+
+extern "C" int pygb200_sampler_export_all(pygb200_sampler* s, int32_t rel, void* row_out, void* col_out, void* edge_id_out,
+                                          int32_t type, void* node_id_out, int index32, void* stream) {
+  PYGB_CHECK(s && rel >= 0 && rel < s->R && type >= 0 && type < s->T, PYGB200_ERR_ARG, "export_all: bad relation / node type");
+  cudaStream_t st = (cudaStream_t)stream;
+  const i64 ne = s->rels[rel].n_edges, nn = s->types[type].n_nodes;
+  if (ne == 0 && nn == 0) return PYGB200_OK;
+  const int g = grid_for(std::max(ne, nn), NT, s->sm_count);
+  const i64 *s0 = s->rels[rel].row.as<i64>(), *s1 = s->rels[rel].colv.as<i64>(), *s2 = s->rels[rel].eid.as<i64>();
+  const i64* node = s->types[type].nodes.as<i64>();
+  const i64* batch = s->disjoint ? s->types[type].batch.as<i64>() : nullptr;
+  if (index32)
+    launch_pdl(k_export4<int32_t>, g, NT, st, s0, s1, s2, (int32_t*)row_out, (int32_t*)col_out, (int32_t*)edge_id_out, ne, node,
+               batch, (int32_t*)node_id_out, nn);
+  else
+    launch_pdl(k_export4<int64_t>, g, NT, st, s0, s1, s2, (int64_t*)row_out, (int64_t*)col_out, (int64_t*)edge_id_out, ne, node,
+               batch, (int64_t*)node_id_out, nn);
   PYGB_LAUNCH_CHECK();
   return PYGB200_OK;
 }

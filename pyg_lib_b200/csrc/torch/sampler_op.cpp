@@ -134,9 +134,8 @@ neighbor_sample_cuda(const at::Tensor& rowptr, const at::Tensor& col, const at::
   at::Tensor node = disjoint ? at::empty({n_nodes, 2}, opt) : at::empty({n_nodes}, opt);
   std::optional<at::Tensor> eid = std::nullopt;
   if (return_edge_id) eid = at::empty({n_edges}, opt);
-  PYGB_TORCH_CALL(pygb200_sampler_export_edges(s, 0, row.data_ptr(), colv.data_ptr(),
-                                               return_edge_id ? eid->data_ptr() : nullptr, idx32, stream));
-  PYGB_TORCH_CALL(pygb200_sampler_export_nodes(s, 0, node.data_ptr(), idx32, stream));
+  PYGB_TORCH_CALL(pygb200_sampler_export_all(s, 0, row.data_ptr(), colv.data_ptr(), return_edge_id ? eid->data_ptr() : nullptr, 0,
+                                             node.data_ptr(), idx32, stream));
   if (csc) std::swap(row, colv);  // neighbor_kernel.cpp:155-159
   return std::make_tuple(row, colv, node, eid, nph, eph);
 }
