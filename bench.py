@@ -158,9 +158,11 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(step_fn):
+    def timed(step_fn, finish=None):
         for i in range(a.warmup):
             step_fn(i)
+        if finish is not None:
+            finish()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = P.kernel_launches()
@@ -169,6 +171,8 @@ def main():
             e0.record()
             for i in range(a.warmup, a.warmup + a.steps):
                 edges += step_fn(i)
+            if finish is not None:
+                finish()   # e.g. make the timed stream wait for outstanding result copies
             e1.record()
             torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
@@ -188,20 +192,35 @@ def main():
     ms, edges, launches, clocks = timed(step_dev)
     value = edges / (ms * 1e-3)
 
-    # ---- e2e: host seeds in, host results out, every step
+    # ---- e2e: host seeds in (pinned -> device) and host results out (device -> pinned) EVERY step, through the
+    # public API.  Like a double-buffered loader, the result copy of step i runs on a copy stream while step
+    # i+1 samples (the calls themselves cannot overlap: each consumes the CPU generator where the previous one
+    # left it); the timed region ends only after the last copy has landed.
     cap = BATCH * (FANOUT[0] + FANOUT[0] * FANOUT[1]) + BATCH
-    host_out = [torch.empty(cap, dtype=torch.int64).pin_memory() for _ in range(4)]
+    host_out = [[torch.empty(cap, dtype=torch.int64).pin_memory() for _ in range(4)] for _ in range(2)]
+    copy_stream = torch.cuda.Stream(device=dev)
+    copied = [torch.cuda.Event(), torch.cuda.Event()]
     d2h = [0]
 
     def step_e2e(i):
         s = seeds_host[i].to(dev, non_blocking=True)
-        row, colv, node, eid, _, _ = P.sampler.neighbor_sample(rowptr, col, s, FANOUT)
-        for h, t in zip(host_out, (row, colv, node, eid)):
-            h[:t.numel()].copy_(t, non_blocking=True)
-        torch.cuda.synchronize()
-        d2h[0] += 8 * (3 * row.numel() + node.numel())
-        return row.numel()
-    ms_e, edges_e, _, _ = timed(step_e2e)
+        outs = P.sampler.neighbor_sample(rowptr, col, s, FANOUT)[:4]
+        ready = torch.cuda.Event()
+        ready.record()
+        slot = i & 1
+        copied[slot].synchronize()          # host buffers of step i-2 are free again
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(ready)
+            for h, t in zip(host_out[slot], outs):
+                t.record_stream(copy_stream)
+                h[:t.numel()].copy_(t, non_blocking=True)
+            copied[slot].record()
+        d2h[0] += 8 * sum(t.numel() for t in outs)
+        return outs[0].numel()
+
+    def finish_e2e():
+        torch.cuda.current_stream().wait_stream(copy_stream)
+    ms_e, edges_e, _, _ = timed(step_e2e, finish_e2e)
     # (d2h counter also ran during warm-up; per-step figure from the timed steps only)
     e2e = {'value': edges_e / (ms_e * 1e-3), 'unit': 'edges/s', 'h2d_bytes_per_step': BATCH * 8,
            'd2h_bytes_per_step': int(d2h[0] / max(a.steps + a.warmup, 1))}
