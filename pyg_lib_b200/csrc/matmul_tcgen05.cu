@@ -487,6 +487,220 @@ int launch_any(int v, const CUtensorMap& ma, const CUtensorMap& mw, const CUtens
   }
 }
 
+
+// ===================================================================================== weight gradient
+// dW[b] = X_b^T @ dY_b  (X [N,K], dY [N,M], dW [B,K,M]).  Replaces the B torch::matmul calls + at::stack of
+// SegmentMatmul::backward (pyg_lib/csrc/ops/autograd/matmul_kernel.cpp:92-107).
+//   * UMMA shape: D[K=128 x M] += A[128 x 16] * B[16 x M], contraction over the ROWS of the segment.
+//     Both operands are consumed in place as MN-major tiles: a TMA box [64 cols x 128 rows] of X (or dY) is
+//     exactly the canonical SW128 MN-major layout with the row index as the K dimension.
+//   * Row tiles are dealt to the CTAs as contiguous ranges; a CTA accumulates in TMEM while consecutive tiles
+//     stay in one segment and flushes at a segment change with fp32 atomics into a zeroed [B,K,M] scratch
+//     (two accumulators, so the flush overlaps the next run's MMAs).  A final pass rounds to bf16/fp16.
+//   * Tails: rows of the tile past the segment end belong to the next segment -> the MMA warp zeroes them in
+//     shared memory (both operands) before issuing, then fences towards the async proxy.
+constexpr int WG_STAGES = 3;
+
+struct WgradParams {
+  const i64* ptr;
+  float* acc;    // [B, K, M] fp32, zero-initialised
+  i64 N;
+  int K, M, B;
+};
+
+template <bool BF16>
+__global__ void __launch_bounds__(NTHREADS, 1)
+k_segment_wgrad_tc(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_dy, const WgradParams P) {
+  extern __shared__ unsigned char smem_raw[];
+  const u32 raw = smem_u32(smem_raw);
+  const u32 base = (raw + 1023u) & ~1023u;
+  unsigned char* sm = smem_raw + (base - raw);
+  const int K = P.K, M = P.M, KH = K / 64, NH = M / 64;
+  const u32 x_bytes = TM * K * 2, y_bytes = TM * M * 2, st_bytes = x_bytes + y_bytes;
+  const u32 off_bar = WG_STAGES * st_bytes;
+  const u32 bar0 = base + off_bar;
+  auto FULL = [&](int s) { return bar0 + 8u * (u32)s; };
+  auto EMPTY = [&](int s) { return bar0 + 8u * (u32)(WG_STAGES + s); };
+  auto T_FULL = [&](int s) { return bar0 + 8u * (u32)(2 * WG_STAGES + s); };
+  auto T_EMPTY = [&](int s) { return bar0 + 8u * (u32)(2 * WG_STAGES + 2 + s); };
+  constexpr int NBARS = 2 * WG_STAGES + 4;
+  u64* bars = reinterpret_cast<u64*>(sm + off_bar);
+  u32* tmem_slot = reinterpret_cast<u32*>(bars + NBARS);
+  int* tile_pre = reinterpret_cast<int*>(tmem_slot + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const u32 tmem_cols = (2 * M <= 32) ? 32 : (2 * M <= 64) ? 64 : (2 * M <= 128) ? 128 : (2 * M <= 256) ? 256 : 512;
+  {
+    __shared__ int s_part[NTHREADS];
+    const int per = (P.B + NTHREADS - 1) / NTHREADS;
+    int loc = 0;
+    for (int j = 0; j < per; ++j) {
+      const int b = threadIdx.x * per + j;
+      if (b < P.B) loc += (int)((P.ptr[b + 1] - P.ptr[b] + TM - 1) / TM);
+    }
+    s_part[threadIdx.x] = loc;
+    __syncthreads();
+    int pre = 0;
+    for (int t = 0; t < (int)threadIdx.x; ++t) pre += s_part[t];
+    for (int j = 0; j < per; ++j) {
+      const int b = threadIdx.x * per + j;
+      if (b < P.B) {
+        tile_pre[b] = pre;
+        pre += (int)((P.ptr[b + 1] - P.ptr[b] + TM - 1) / TM);
+      }
+    }
+    if (threadIdx.x == 0) {
+      int tot = 0;
+      for (int t = 0; t < NTHREADS; ++t) tot += s_part[t];
+      tile_pre[P.B] = tot;
+    }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < WG_STAGES; ++s) { mbar_init(FULL(s), 1); mbar_init(EMPTY(s), 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(T_FULL(s), 1); mbar_init(T_EMPTY(s), 128); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    fence_proxy_async();
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_dy) : "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const u32 tmem_base = *tmem_slot;
+
+  const int total_tiles = tile_pre[P.B];
+  const int per_cta = (total_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int t_begin = (int)blockIdx.x * per_cta;
+  const int t_end = min(total_tiles, t_begin + per_cta);
+  auto seg_of = [&](int t) {
+    int lo = 0, hi = P.B - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (tile_pre[mid] <= t) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+  };
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (lane == 0 && t_begin < t_end) {
+      int seg = seg_of(t_begin), stage = 0;
+      u32 phase = 0;
+      for (int t = t_begin; t < t_end; ++t) {
+        while (tile_pre[seg + 1] <= t) ++seg;
+        const i64 row0 = P.ptr[seg] + (i64)(t - tile_pre[seg]) * TM;
+        mbar_wait(EMPTY(stage), phase ^ 1);
+        mbar_expect_tx(FULL(stage), st_bytes);
+        const u32 xs = base + stage * st_bytes, ys = xs + x_bytes;
+        for (int h = 0; h < KH; ++h) tma_load_2d(xs + h * (TM * 128), &map_x, h * 64, (int)row0, FULL(stage));
+        for (int h = 0; h < NH; ++h) tma_load_2d(ys + h * (TM * 128), &map_dy, h * 64, (int)row0, FULL(stage));
+        if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ================================
+    if (t_begin < t_end) {
+      // D = f32, A and B both MN-major (bits 15 and 16), N = M(out cols) >> 3, M = K(=128) >> 4
+      const u32 fmt = BF16 ? 1u : 0u;
+      const u32 idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (1u << 15) | (1u << 16) | ((u32)(M >> 3) << 17) | ((u32)(K >> 4) << 24);
+      int seg = seg_of(t_begin), stage = 0, acc = 0;
+      u32 phase = 0, t_phase = 0;
+      bool run_open = false;   // an accumulation run (consecutive tiles of one segment) is in progress
+      for (int t = t_begin; t < t_end; ++t) {
+        while (tile_pre[seg + 1] <= t) ++seg;
+        const i64 row0 = P.ptr[seg] + (i64)(t - tile_pre[seg]) * TM;
+        const i64 rem = P.ptr[seg + 1] - row0;
+        const int valid = rem < TM ? (int)rem : TM;
+        if (!run_open) mbar_wait(T_EMPTY(acc), ((t_phase >> acc) & 1u) ^ 1u);
+        mbar_wait(FULL(stage), phase);
+        const u32 xs = base + stage * st_bytes, ys = xs + x_bytes;
+        if (valid < TM) {
+          // rows [valid, 128) belong to the next segment: zero them in both operand tiles (each row is one
+          // 128-byte line per 64-column half, whatever the swizzle)
+          unsigned char* xp = sm + stage * st_bytes;
+          const int halves = KH + NH, chunks = (TM - valid) * 8;
+          for (int h = 0; h < halves; ++h)
+            for (int c = lane; c < chunks; c += 32)
+              *reinterpret_cast<uint4*>(xp + h * (TM * 128) + (valid + (c >> 3)) * 128 + (c & 7) * 16) = make_uint4(0, 0, 0, 0);
+          fence_proxy_async();
+          __syncwarp();
+        }
+        tc_fence_after();
+        if (lane == 0) {
+          const u32 d_tmem = tmem_base + (u32)(acc * M);
+          for (int kk = 0; kk < TM / 16; ++kk) {
+            const u64 adesc = make_desc(xs + kk * 2048, (u32)(TM * 128), 1024);
+            const u64 bdesc = make_desc(ys + kk * 2048, (u32)(TM * 128), 1024);
+            tc_mma_f16(d_tmem, adesc, bdesc, idesc, (run_open || kk > 0) ? 1u : 0u);
+          }
+          tc_commit(EMPTY(stage));
+        }
+        run_open = true;
+        const bool last_of_run = (t + 1 >= t_end) || (tile_pre[seg + 1] <= t + 1);
+        if (last_of_run) {
+          if (lane == 0) tc_commit(T_FULL(acc));
+          t_phase ^= 1u << acc;
+          acc ^= 1;
+          run_open = false;
+        }
+        __syncwarp();
+        if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ================================ epilogue: flush finished runs ================================
+    const int q = warp & 3;
+    const int r = q * 32 + lane;   // accumulator lane == column of X == row of dW[b]
+    if (t_begin < t_end) {
+      int seg = seg_of(t_begin), acc = 0;
+      u32 t_phase = 0;
+      for (int t = t_begin; t < t_end; ++t) {
+        while (tile_pre[seg + 1] <= t) ++seg;
+        const bool last_of_run = (t + 1 >= t_end) || (tile_pre[seg + 1] <= t + 1);
+        if (!last_of_run) continue;
+        mbar_wait(T_FULL(acc), (t_phase >> acc) & 1u);
+        t_phase ^= 1u << acc;
+        tc_fence_after();
+        float* dst = P.acc + ((i64)seg * K + r) * M;
+        for (int c0 = 0; c0 < M; c0 += 32) {
+          u32 v[32];
+          tc_ld_32x32(tmem_base + (u32)(acc * M + c0) + ((u32)(q * 32) << 16), v);
+          tc_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) atomicAdd(dst + c0 + j, __uint_as_float(v[j]));
+        }
+        tc_fence_before();
+        mbar_arrive(T_EMPTY(acc));
+        acc ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+  }
+}
+
+template <bool BF16>
+__global__ void k_wgrad_finish(const float* __restrict__ acc, void* __restrict__ dw, i64 n) {
+  for (i64 i = ((i64)blockIdx.x * blockDim.x + threadIdx.x) * 2; i < n; i += (i64)gridDim.x * blockDim.x * 2)
+    reinterpret_cast<u32*>(dw)[i >> 1] = pack2<BF16>(acc[i], acc[i + 1]);
+}
+
+size_t wgrad_smem(i64 K, i64 M, i64 B) {
+  return 1024 + (size_t)WG_STAGES * (TM * K * 2 + TM * M * 2) + (2 * WG_STAGES + 4) * 8 + 16 + (size_t)(B + 2) * 4;
+}
+
 }  // namespace
 
 bool tcgen05_supported(i64 N, i64 K, i64 M, i64 B, int dtype, const void* x, const void* w, const void* out) {
@@ -529,6 +743,53 @@ int segment_matmul_tcgen05(const void* x, const i64* ptr_dev, const void* w, con
   if (int e = bf16 ? launch_any<true>(v, ma, mw, mo, P, grid, smem, st) : launch_any<false>(v, ma, mw, mo, P, grid, smem, st)) return e;
   prof_end(tk, "segment_matmul", st, N);
   PYGB_LAUNCH_CHECK();
+  return PYGB200_OK;
+}
+
+bool wgrad_tcgen05_supported(i64 N, i64 K, i64 M, i64 B, int dtype, const void* x, const void* dy, const void* dw) {
+  if (dtype != PYGB200_BF16 && dtype != PYGB200_F16) return false;
+  if (K != 128) return false;                                  // UMMA M dimension (rows of dW[b])
+  if (M < 64 || M > 256 || M % 64 != 0) return false;
+  if (B < 1 || B > MAX_SEG || N < 1 || N >= ((i64)1 << 31)) return false;
+  if (((uintptr_t)x | (uintptr_t)dy | (uintptr_t)dw) & 15) return false;
+  if (wgrad_smem(K, M, B) > SMEM_LIMIT) return false;
+  return true;
+}
+
+int segment_wgrad_tcgen05(const void* x, const i64* ptr_dev, const void* dy, void* dw, i64 N, i64 K, i64 M, i64 B, int dtype,
+                          cudaStream_t st) {
+  const bool bf16 = dtype == PYGB200_BF16;
+  CUtensorMap mx, my;
+  if (int e = make_map(&mx, x, N, K, TM, bf16)) return e;
+  if (int e = make_map(&my, dy, N, M, TM, bf16)) return e;
+  float* acc = nullptr;
+  const size_t acc_bytes = (size_t)B * K * M * sizeof(float);
+  PYGB_CUDA(cudaMallocAsync((void**)&acc, acc_bytes, st));
+  PYGB_CUDA(cudaMemsetAsync(acc, 0, acc_bytes, st));
+  WgradParams P;
+  P.ptr = ptr_dev; P.acc = acc; P.N = N; P.K = (int)K; P.M = (int)M; P.B = (int)B;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const i64 max_tiles = N / TM + B;
+  const int grid = (int)(max_tiles < sms ? (max_tiles < 1 ? 1 : max_tiles) : sms);
+  const size_t smem = wgrad_smem(K, M, B);
+  void* tk = prof_begin(st);
+  if (bf16) {
+    PYGB_CUDA(cudaFuncSetAttribute(k_segment_wgrad_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_segment_wgrad_tc<true><<<grid, NTHREADS, smem, st>>>(mx, my, P);
+  } else {
+    PYGB_CUDA(cudaFuncSetAttribute(k_segment_wgrad_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_segment_wgrad_tc<false><<<grid, NTHREADS, smem, st>>>(mx, my, P);
+  }
+  prof_end(tk, "segment_matmul", st, N);
+  PYGB_LAUNCH_CHECK();
+  const i64 n = B * K * M;
+  const int fg = (int)std::min<i64>((n / 2 + 255) / 256, (i64)sms * 8);
+  if (bf16) k_wgrad_finish<true><<<fg, 256, 0, st>>>(acc, dw, n);
+  else k_wgrad_finish<false><<<fg, 256, 0, st>>>(acc, dw, n);
+  PYGB_LAUNCH_CHECK();
+  cudaFreeAsync(acc, st);
   return PYGB200_OK;
 }
 

@@ -150,3 +150,33 @@ def test_tcgen05_c3_shape_uniform_and_ragged(lib):
             ref = x[a:b].float() @ w[i].float()
             if b > a:
                 assert (out[a:b].float() - ref).norm() <= 3e-3 * ref.norm()
+
+
+@pytest.mark.parametrize('dtype', [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize('M', [64, 128, 256])
+def test_wgrad_tcgen05(lib, dtype, M):
+    """dW[b] = X_b^T dY_b on the tensor-core path (K = 128): empty / 1-row / tail segments, more row tiles
+    than SMs, and the autograd wiring (dX through the forward kernel with W^T)."""
+    K = 128
+    g = torch.Generator().manual_seed(M)
+    lens = [0, 1, 127, 128, 129, 300, 0, 1000, 5, 4096, 77, 30000]
+    ptr = torch.tensor([0] + lens).cumsum(0)
+    N, B = int(ptr[-1]), len(lens)
+    x = (torch.randn(N, K, generator=g) * 0.5).to(dtype)
+    gy = (torch.randn(N, M, generator=g) * 0.5).to(dtype)
+    dw = torch.ops.pyg.segment_matmul_wgrad(x.to(DEV), ptr.to(DEV), gy.to(DEV)).float().cpu()
+    ref = torch.stack([x[ptr[i]:ptr[i + 1]].float().t() @ gy[ptr[i]:ptr[i + 1]].float() for i in range(B)])
+    assert dw.shape == (B, K, M)
+    for i in range(B):
+        if lens[i] == 0:
+            assert torch.count_nonzero(dw[i]) == 0
+        else:
+            assert (dw[i] - ref[i]).norm() <= 4e-3 * ref[i].norm() + 1e-3, (i, lens[i])
+    # end to end through autograd
+    xg = x.to(DEV).requires_grad_()
+    w = (torch.randn(B, K, M, generator=g) / K ** 0.5).to(dtype).to(DEV).requires_grad_()
+    out = lib.ops.segment_matmul(xg, ptr, w)
+    out.backward(gy.to(DEV))
+    assert (w.grad.float().cpu() - ref).norm() <= 4e-3 * ref.norm()
+    gx_ref = torch.cat([gy[ptr[i]:ptr[i + 1]].float() @ w[i].detach().float().cpu().t() for i in range(B)])
+    assert (xg.grad.float().cpu() - gx_ref).norm() <= 4e-3 * gx_ref.norm()
