@@ -42,29 +42,45 @@ class ClockMonitor:
         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
 
     def __init__(self, index: int):
-        self.index, self.proc, self.lines = index, None, []
+        self.index, self.proc, self.lines, self.lo, self.hi = index, None, [], 0, None
 
-    def __enter__(self):
+    def start(self):
+        """Launch nvidia-smi and wait for its first sample: NVML start-up takes ~100 ms and holds driver locks,
+        so it must not overlap the timed region."""
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
-                                          '--format=csv,noheader,nounits', '-lms', '100'], stdout=subprocess.PIPE,
+                                          '--format=csv,noheader,nounits', '-lms', '50'], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
+
+            def pump():
+                for ln in self.proc.stdout:
+                    self.lines.append(ln)
+            self.t = threading.Thread(target=pump, daemon=True)
             self.t.start()
+            t0 = time.time()
+            while not self.lines and time.time() - t0 < 3.0:
+                time.sleep(0.01)
         except Exception:  # noqa
             self.proc = None
         return self
 
-    def __exit__(self, *a):
+    def __enter__(self):   # marks the start of the timed region
+        self.lo = len(self.lines)
+        return self
+
+    def __exit__(self, *a):  # marks its end
+        time.sleep(0.06)       # one more sample so that short regions are covered
+        self.hi = len(self.lines)
+
+    def stop(self):
         if self.proc is not None:
-            time.sleep(0.15)
             self.proc.terminate()
             self.t.join(timeout=2)
 
     def summary(self):
         sm, mx, reasons = [], 0, set()
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        for ln in self.lines:
+        for ln in self.lines[max(self.lo - 1, 0):self.hi]:
             f = [x.strip() for x in ln.split(',')]
             if len(f) < 6:
                 continue
@@ -120,8 +136,8 @@ def config_dict(n_gpus):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=200)
-    ap.add_argument('--warmup', type=int, default=10)
+    ap.add_argument('--steps', type=int, default=1000)
+    ap.add_argument('--warmup', type=int, default=20)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-matmul', action='store_true')
@@ -158,6 +174,8 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    mon = ClockMonitor(local).start()
+
     def timed(step_fn, finish=None):
         for i in range(a.warmup):
             step_fn(i)
@@ -167,7 +185,7 @@ def main():
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = P.kernel_launches()
         edges = 0
-        with ClockMonitor(local) as mon:
+        with mon:
             e0.record()
             for i in range(a.warmup, a.warmup + a.steps):
                 edges += step_fn(i)
@@ -304,6 +322,7 @@ def main():
             except Exception as ex:  # noqa
                 line['cpu_baseline'] = {'value': None, 'unit': 'edges/s', 'cores': 0, 'kind': 'failed', 'sample': str(ex)[:300]}
         print(json.dumps(line), flush=True)
+    mon.stop()
     if world > 1:
         dist.destroy_process_group()
 
