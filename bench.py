@@ -255,6 +255,19 @@ def main():
             peaks = json.load(open(osp.join(ROOT, 'MEASURED_PEAKS.json')))
         except Exception:  # noqa
             pass
+        # DRAM traffic per launch of the dominant kernels, from the committed `ncu --set full` capture
+        # (profiles/ncu_summary_r1.json: dram__bytes_read.sum + dram__bytes_write.sum, MB)
+        traffic = {}
+        try:
+            summ = json.load(open(osp.join(ROOT, 'profiles', 'ncu_summary_r1.json')))
+            for grp in summ.values():
+                for d in grp:
+                    nm = 'k_sample' if 'k_sample' in d['Kernel Name'] else ('k_segment_matmul_tc' if 'k_segment_matmul_tc' in d['Kernel Name'] else None)
+                    if nm:
+                        traffic.setdefault(nm, []).append(1e6 * (float(d['dram__bytes_read.sum']) + float(d['dram__bytes_write.sum'])))
+            traffic = {k: sum(v) / len(v) for k, v in traffic.items()}
+        except Exception:  # noqa
+            traffic = {}
         hbm_peak = float(peaks.get('hbm_gbs', 6650.0))
         peak_src = 'measured (MEASURED_PEAKS.json)' if 'hbm_gbs' in peaks else 'fallback 6.65 TB/s'
         abi.pygb200_profile_enable(1)
@@ -274,7 +287,7 @@ def main():
         bytes_per_launch = BYTES_PER_EDGE * d_work / max(d_launches, 1)
         achieved = bytes_per_launch / (d_ms / max(d_launches, 1) * 1e-3) / 1e9 if d_ms > 0 else 0.0
         line['roofline'] = {'bound': 'hbm', 'kernel': 'k_' + dom, 'achieved': achieved, 'peak': hbm_peak, 'unit': 'GB/s',
-                            'frac': achieved / hbm_peak, 'traffic': None, 'peak_source': peak_src,
+                            'frac': achieved / hbm_peak, 'traffic': traffic.get('k_' + dom), 'peak_source': peak_src,
                             'avg_launch_us': 1e3 * d_ms / max(d_launches, 1),
                             'bytes_per_launch': bytes_per_launch,
                             'kernel_ms_share': {k: v[0] for k, v in prof.items()},
@@ -304,7 +317,7 @@ def main():
                 'config': '64 relations, N=2^20 ragged rows (log-normal lengths, one empty), 128->128 bf16, ptr on device',
                 'ms': mm_ms, 'tflops': flops / (mm_ms * 1e-3) / 1e12, 'algorithmic_bytes': byts,
                 'roofline': {'bound': 'hbm', 'achieved': byts / (mm_ms * 1e-3) / 1e9, 'peak': hbm_peak, 'unit': 'GB/s',
-                             'frac': byts / (mm_ms * 1e-3) / 1e9 / hbm_peak, 'traffic': None,
+                             'frac': byts / (mm_ms * 1e-3) / 1e9 / hbm_peak, 'traffic': traffic.get('k_segment_matmul_tc'),
                              'tensor_frac_of_bf16_peak': flops / (mm_ms * 1e-3) / 1e12 / tf_peak},
                 'note': 'x (256 MiB) + out (256 MiB) > L2; arithmetic intensity 63.75 FLOP/B => HBM-bound'}
             del x, w, y
