@@ -27,6 +27,9 @@ bool tcgen05_supported(i64 N, i64 K, i64 M, i64 B, int dtype, const void* x, con
 int segment_wgrad_tcgen05(const void* x, const i64* ptr_dev, const void* dy, void* dw, i64 N, i64 K, i64 M, i64 B, int dtype,
                           cudaStream_t st);
 bool wgrad_tcgen05_supported(i64 N, i64 K, i64 M, i64 B, int dtype, const void* x, const void* dy, const void* dw);
+int segment_matmul_tf32(const void* x, const i64* ptr_dev, const void* w, const void* bias, void* out, i64 N, i64 K, i64 M,
+                        i64 B, cudaStream_t st);
+bool tf32_supported(i64 N, i64 K, i64 M, i64 B, const void* x, const void* w, const void* out);
 
 namespace {
 
@@ -312,6 +315,9 @@ extern "C" int pygb200_segment_matmul(const void* x, const int64_t* ptr_dev, con
   }
   if (!(flags & PYGB200_MM_FORCE_SIMT) && tcgen05_supported(N, K, M, B, dtype, x, w, out))
     return segment_matmul_tcgen05(x, (const i64*)ptr_dev, w, bias, out, N, K, M, B, dtype, st);
+  if (!(flags & PYGB200_MM_FORCE_SIMT) && (flags & PYGB200_MM_ALLOW_TF32) && dtype == PYGB200_F32 &&
+      tf32_supported(N, K, M, B, x, w, out))
+    return segment_matmul_tf32(x, (const i64*)ptr_dev, w, bias, out, N, K, M, B, st);
   return segment_generic(x, (const i64*)ptr_dev, w, bias, out, N, K, M, B, dtype, 0, st);
 }
 

@@ -746,6 +746,307 @@ int segment_matmul_tcgen05(const void* x, const i64* ptr_dev, const void* w, con
   return PYGB200_OK;
 }
 
+// ===================================================================================== TF32 forward
+// fp32 storage, TF32 tensor-core math (tcgen05.mma kind::tf32) — taken when the caller allows TF32
+// (torch.get_float32_matmul_precision() != 'highest', like the reference's TensorOp kernel,
+// pyg_lib/csrc/ops/cuda/matmul_kernel.cu:159-190).  Same structure as the 16-bit kernel with 4-byte elements:
+// a 128-byte swizzle row holds 32 elements, one MMA covers K = 8.  A streams in [128 rows x 64 cols] stages
+// (two TMA boxes each), W[b] (K*M*4 <= 64 KB) is resident as an MN-major operand, the fp32 result leaves in
+// 32-column groups through a double-buffered 16 KB staging tile.
+namespace {
+
+constexpr int TF_A_STAGES = 4;
+constexpr u32 TF_A_BYTES = TM * 64 * 4;    // one stage
+constexpr u32 TF_O_BYTES = TM * 32 * 4;    // one staging tile
+
+__device__ __forceinline__ void tc_mma_tf32(u32 tmem_d, u64 adesc, u64 bdesc, u32 idesc, u32 accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+struct Tf32Params {
+  const i64* ptr;
+  const float* bias;
+  float* out;
+  i64 N;
+  int K, M, B, G;
+};
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+k_segment_matmul_tf32(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
+                      const __grid_constant__ CUtensorMap map_o, const Tf32Params P) {
+  extern __shared__ unsigned char smem_raw[];
+  const u32 raw = smem_u32(smem_raw);
+  const u32 base = (raw + 1023u) & ~1023u;
+  unsigned char* sm = smem_raw + (base - raw);
+  const int K = P.K, M = P.M, KC = K / 64, NG = M / 32;
+  const u32 w_bytes = (u32)K * M * 4;
+  const u32 off_w = TF_A_STAGES * TF_A_BYTES, off_o = off_w + w_bytes, off_bar = off_o + 2 * TF_O_BYTES;
+  const u32 bar0 = base + off_bar;
+  auto A_FULL = [&](int s) { return bar0 + 8u * (u32)s; };
+  auto A_EMPTY = [&](int s) { return bar0 + 8u * (u32)(TF_A_STAGES + s); };
+  const u32 W_FULL = bar0 + 8u * (2 * TF_A_STAGES), W_EMPTY = W_FULL + 8;
+  auto T_FULL = [&](int s) { return bar0 + 8u * (u32)(2 * TF_A_STAGES + 2 + s); };
+  auto T_EMPTY = [&](int s) { return bar0 + 8u * (u32)(2 * TF_A_STAGES + 4 + s); };
+  constexpr int NBARS = 2 * TF_A_STAGES + 6;
+  u64* bars = reinterpret_cast<u64*>(sm + off_bar);
+  u32* tmem_slot = reinterpret_cast<u32*>(bars + NBARS);
+  int* tile_pre = reinterpret_cast<int*>(tmem_slot + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const u32 tmem_cols = (2 * M <= 32) ? 32 : (2 * M <= 64) ? 64 : (2 * M <= 128) ? 128 : (2 * M <= 256) ? 256 : 512;
+  {
+    __shared__ int s_part[NTHREADS];
+    const int per = (P.B + NTHREADS - 1) / NTHREADS;
+    int loc = 0;
+    for (int j = 0; j < per; ++j) {
+      const int b = threadIdx.x * per + j;
+      if (b < P.B) loc += (int)((P.ptr[b + 1] - P.ptr[b] + TM - 1) / TM);
+    }
+    s_part[threadIdx.x] = loc;
+    __syncthreads();
+    int pre = 0;
+    for (int t = 0; t < (int)threadIdx.x; ++t) pre += s_part[t];
+    for (int j = 0; j < per; ++j) {
+      const int b = threadIdx.x * per + j;
+      if (b < P.B) {
+        tile_pre[b] = pre;
+        pre += (int)((P.ptr[b + 1] - P.ptr[b] + TM - 1) / TM);
+      }
+    }
+    if (threadIdx.x == 0) {
+      int tot = 0;
+      for (int t = 0; t < NTHREADS; ++t) tot += s_part[t];
+      tile_pre[P.B] = tot;
+    }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < TF_A_STAGES; ++s) { mbar_init(A_FULL(s), 1); mbar_init(A_EMPTY(s), 1); }
+    mbar_init(W_FULL, 1); mbar_init(W_EMPTY, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(T_FULL(s), 1); mbar_init(T_EMPTY(s), 128); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    fence_proxy_async();
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_o) : "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const u32 tmem_base = *tmem_slot;
+  const int total_tiles = tile_pre[P.B];
+  const int per_cta = (total_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int G = P.G > 0 ? P.G : max(per_cta, 1);
+  const bool has_work = (long long)blockIdx.x * G < total_tiles;
+  auto seg_of = [&](int t) {
+    int lo = 0, hi = P.B - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (tile_pre[mid] <= t) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+  };
+
+  if (warp == 0) {
+    if (lane == 0 && has_work) {
+      TileIter it(G, (int)gridDim.x, total_tiles, (int)blockIdx.x);
+      int seg = seg_of(it.t), cur_seg = -1, stage = 0;
+      u32 a_phase = 0, w_phase = 0;
+      for (; it.valid(); it.next()) {
+        const int t = it.t;
+        while (tile_pre[seg + 1] <= t) ++seg;
+        if (seg != cur_seg) {
+          cur_seg = seg;
+          mbar_wait(W_EMPTY, w_phase ^ 1);
+          w_phase ^= 1;
+          mbar_expect_tx(W_FULL, w_bytes);
+          for (int g = 0; g < NG; ++g)   // box [32 cols of M x K rows] -> [K][128 B]: MN-major SW128 atoms
+            tma_load_2d(base + off_w + g * (K * 128), &map_w, g * 32, seg * K, W_FULL);
+        }
+        const i64 row0 = P.ptr[seg] + (i64)(t - tile_pre[seg]) * TM;
+        for (int c = 0; c < KC; ++c) {
+          mbar_wait(A_EMPTY(stage), a_phase ^ 1);
+          mbar_expect_tx(A_FULL(stage), TF_A_BYTES);
+          for (int h = 0; h < 2; ++h)     // box [32 cols of K x 128 rows] -> [128][128 B]: K-major SW128 atoms
+            tma_load_2d(base + stage * TF_A_BYTES + h * (TM * 128), &map_a, c * 64 + h * 32, (int)row0, A_FULL(stage));
+          if (++stage == TF_A_STAGES) { stage = 0; a_phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (has_work) {
+      // D = f32 (bit 4), A/B = TF32 (format 2 at bits 7 and 10), B MN-major (bit 16), N >> 3, M >> 4
+      const u32 idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) | ((u32)(M >> 3) << 17) | ((u32)(TM >> 4) << 24);
+      TileIter it(G, (int)gridDim.x, total_tiles, (int)blockIdx.x);
+      int seg = seg_of(it.t), cur_seg = -1, stage = 0, acc = 0;
+      u32 a_phase = 0, w_phase = 0, t_phase = 0;
+      for (; it.valid(); it.next()) {
+        const int t = it.t;
+        while (tile_pre[seg + 1] <= t) ++seg;
+        if (seg != cur_seg) {
+          cur_seg = seg;
+          mbar_wait(W_FULL, w_phase);
+          w_phase ^= 1;
+        }
+        mbar_wait(T_EMPTY(acc), ((t_phase >> acc) & 1u) ^ 1u);
+        const u32 d_tmem = tmem_base + (u32)(acc * M);
+        for (int c = 0; c < KC; ++c) {
+          mbar_wait(A_FULL(stage), a_phase);
+          tc_fence_after();
+          if (lane == 0) {
+            const u32 a_base = base + stage * TF_A_BYTES, w_base = base + off_w;
+            for (int kk = 0; kk < 8; ++kk) {   // K = 8 per instruction: 32 bytes inside the 128 B swizzle row
+              const u64 adesc = make_desc(a_base + (kk >> 2) * (TM * 128) + (kk & 3) * 32, 16, 1024);
+              const u64 bdesc = make_desc(w_base + (c * 8 + kk) * 1024, (u32)(K * 128), 1024);
+              tc_mma_tf32(d_tmem, adesc, bdesc, idesc, (c > 0 || kk > 0) ? 1u : 0u);
+            }
+            tc_commit(A_EMPTY(stage));
+          }
+          __syncwarp();
+          if (++stage == TF_A_STAGES) { stage = 0; a_phase ^= 1; }
+        }
+        if (lane == 0) {
+          tc_commit(T_FULL(acc));
+          const int tn = it.peek_next();
+          if ((tn >= total_tiles) || (tile_pre[seg + 1] <= tn)) tc_commit(W_EMPTY);
+        }
+        __syncwarp();
+        t_phase ^= 1u << acc;
+        acc ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    const int q = warp & 3, r = q * 32 + lane, et = threadIdx.x - 128;
+    if (has_work) {
+      TileIter it(G, (int)gridDim.x, total_tiles, (int)blockIdx.x);
+      int seg = seg_of(it.t), acc = 0, obuf = 0;
+      u32 t_phase = 0;
+      for (; it.valid(); it.next()) {
+        const int t = it.t;
+        while (tile_pre[seg + 1] <= t) ++seg;
+        const i64 row0 = P.ptr[seg] + (i64)(t - tile_pre[seg]) * TM;
+        const i64 rem = P.ptr[seg + 1] - row0;
+        const int valid = rem < TM ? (int)rem : TM;
+        mbar_wait(T_FULL(acc), (t_phase >> acc) & 1u);
+        t_phase ^= 1u << acc;
+        tc_fence_after();
+        for (int g = 0; g < NG; ++g) {
+          u32 v[32];
+          tc_ld_32x32(tmem_base + (u32)(acc * M + g * 32) + ((u32)(q * 32) << 16), v);
+          tc_wait_ld();
+          if (P.bias) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + P.bias[(i64)seg * M + g * 32 + j]);
+          }
+          if (valid == TM) {
+            unsigned char* stage_o = sm + off_o + obuf * TF_O_BYTES;
+            if (et == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the store that last read this buffer
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int ch = j ^ (r & 7);
+              *reinterpret_cast<uint4*>(stage_o + r * 128 + ch * 16) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            }
+            fence_proxy_async();
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (et == 0) {
+              tma_store_2d(&map_o, base + off_o + obuf * TF_O_BYTES, g * 32, (int)row0);
+              tma_store_commit();
+            }
+            obuf ^= 1;
+          } else if (r < valid) {
+            uint4* dst = reinterpret_cast<uint4*>(P.out + (row0 + r) * M + g * 32);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) dst[j] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(T_EMPTY(acc));
+        acc ^= 1;
+      }
+      if (et == 0) tma_store_wait_all();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+  }
+}
+
+// 2-D row-major fp32 tensor, box [box_rows x 32 cols] (128 bytes), 128 B swizzle
+int make_map_f32(CUtensorMap* m, const void* ptr, i64 rows, i64 cols, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  PYGB_CHECK(enc != nullptr, PYGB200_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * 4};
+  cuuint32_t box[2] = {32, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(f32) failed with code " + std::to_string((int)r));
+    return PYGB200_ERR_CUDA;
+  }
+  return PYGB200_OK;
+}
+
+size_t tf32_smem(i64 K, i64 M, i64 B) {
+  return 1024 + (size_t)TF_A_STAGES * TF_A_BYTES + (size_t)K * M * 4 + 2 * TF_O_BYTES + (2 * TF_A_STAGES + 6) * 8 + 16 +
+         (size_t)(B + 2) * 4;
+}
+
+}  // namespace
+
+bool tf32_supported(i64 N, i64 K, i64 M, i64 B, const void* x, const void* w, const void* out) {
+  if (K < 64 || K > 256 || K % 64 != 0) return false;
+  if (M < 32 || M > 256 || M % 32 != 0) return false;
+  if (B < 1 || B > MAX_SEG || N < 1 || N >= ((i64)1 << 31) || B * K >= ((i64)1 << 31)) return false;
+  if (((uintptr_t)x | (uintptr_t)w | (uintptr_t)out) & 15) return false;
+  return tf32_smem(K, M, B) <= SMEM_LIMIT;
+}
+
+int segment_matmul_tf32(const void* x, const i64* ptr_dev, const void* w, const void* bias, void* out, i64 N, i64 K, i64 M,
+                        i64 B, cudaStream_t st) {
+  CUtensorMap ma, mw, mo;
+  if (int e = make_map_f32(&ma, x, N, K, TM)) return e;
+  if (int e = make_map_f32(&mw, w, B * K, M, (int)K)) return e;
+  if (int e = make_map_f32(&mo, out, N, M, TM)) return e;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const i64 max_tiles = N / TM + B;
+  Tf32Params P;
+  P.ptr = ptr_dev; P.bias = (const float*)bias; P.out = (float*)out; P.N = N; P.K = (int)K; P.M = (int)M; P.B = (int)B;
+  {
+    const i64 per_cta = (max_tiles + sms - 1) / sms;
+    const i64 rounds = std::max<i64>(1, (per_cta + 2) / 4);
+    P.G = (int)std::max<i64>(1, (per_cta + rounds - 1) / rounds);
+  }
+  const size_t smem = tf32_smem(K, M, B);
+  const int grid = (int)(max_tiles < sms ? (max_tiles < 1 ? 1 : max_tiles) : sms);
+  PYGB_CUDA(cudaFuncSetAttribute(k_segment_matmul_tf32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  void* tk = prof_begin(st);
+  k_segment_matmul_tf32<<<grid, NTHREADS, smem, st>>>(ma, mw, mo, P);
+  prof_end(tk, "segment_matmul", st, N);
+  PYGB_LAUNCH_CHECK();
+  return PYGB200_OK;
+}
+
 bool wgrad_tcgen05_supported(i64 N, i64 K, i64 M, i64 B, int dtype, const void* x, const void* dy, const void* dw) {
   if (dtype != PYGB200_BF16 && dtype != PYGB200_F16) return false;
   if (K != 128) return false;                                  // UMMA M dimension (rows of dW[b])

@@ -180,3 +180,27 @@ def test_wgrad_tcgen05(lib, dtype, M):
     assert (w.grad.float().cpu() - ref).norm() <= 4e-3 * ref.norm()
     gx_ref = torch.cat([gy[ptr[i]:ptr[i + 1]].float() @ w[i].detach().float().cpu().t() for i in range(B)])
     assert (xg.grad.float().cpu() - gx_ref).norm() <= 4e-3 * gx_ref.norm()
+
+
+@pytest.mark.parametrize('K,M', [(128, 128), (64, 256), (256, 64), (64, 32), (192, 64)])
+@pytest.mark.parametrize('with_bias', [False, True])
+def test_tf32_path(lib, K, M, with_bias):
+    """fp32 storage with TF32 tensor-core math when the caller allows it
+    (torch.set_float32_matmul_precision('high'), cf. matmul_kernel.cu:159-165); 'highest' stays exact fp32."""
+    g = torch.Generator().manual_seed(K + M)
+    lens = [0, 1, 127, 128, 129, 300, 0, 1000, 5, 4096, 77, 20000]
+    ptr = torch.tensor([0] + lens).cumsum(0)
+    N, B = int(ptr[-1]), len(lens)
+    x = torch.randn(N, K, generator=g)
+    w = torch.randn(B, K, M, generator=g) / K ** 0.5
+    b = torch.randn(B, M, generator=g) if with_bias else None
+    ref = torch.cat([x[ptr[i]:ptr[i + 1]].double() @ w[i].double() + (b[i].double() if with_bias else 0) for i in range(B)])
+    try:
+        torch.set_float32_matmul_precision('high')
+        out = lib.ops.segment_matmul(x.to(DEV), ptr.to(DEV), w.to(DEV), bias=None if b is None else b.to(DEV)).cpu()
+    finally:
+        torch.set_float32_matmul_precision('highest')
+    err = (out.double() - ref).norm() / ref.norm()
+    assert 1e-6 < err <= 2e-3, float(err)   # TF32 (10-bit mantissa) accuracy: not exact, not garbage
+    exact = lib.ops.segment_matmul(x.to(DEV), ptr.to(DEV), w.to(DEV), bias=None if b is None else b.to(DEV)).cpu()
+    assert (exact.double() - ref).norm() / ref.norm() <= 1e-6

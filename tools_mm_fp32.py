@@ -6,7 +6,8 @@ dev='cuda:0'
 N,K,M,B = 1<<20,128,128,64
 g = torch.Generator().manual_seed(0)
 res={}
-for dt in (torch.float32, torch.bfloat16):
+for dt, prec in ((torch.float32, 'highest'), (torch.float32, 'high'), (torch.bfloat16, 'highest')):
+    torch.set_float32_matmul_precision(prec)
     x = torch.randn(N,K,generator=g).to(dt).to(dev); w = (torch.randn(B,K,M,generator=g)/K**0.5).to(dt).to(dev)
     ptr = ragged_ptr(N,B,100).to(dev)
     x.requires_grad_(); w.requires_grad_()
@@ -29,5 +30,5 @@ for dt in (torch.float32, torch.bfloat16):
     torch.cuda.synchronize(); e0.record()
     for _ in range(5): r = ref()
     e1.record(); torch.cuda.synchronize(); ref_ms = e0.elapsed_time(e1)/5
-    res[str(dt)] = dict(fwd_ms=f_ms, fwd_tflops=2*N*K*M/f_ms/1e9, fwd_bwd_ms=fb_ms, torch_loop_fwd_ms=ref_ms)
+    res[str(dt) + '/' + prec] = dict(fwd_ms=f_ms, fwd_tflops=2*N*K*M/f_ms/1e9, fwd_bwd_ms=fb_ms, torch_loop_fwd_ms=ref_ms)
 print(json.dumps(res))
