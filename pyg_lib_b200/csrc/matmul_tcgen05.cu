@@ -751,8 +751,11 @@ int segment_matmul_tcgen05(const void* x, const i64* ptr_dev, const void* w, con
 // (torch.get_float32_matmul_precision() != 'highest', like the reference's TensorOp kernel,
 // pyg_lib/csrc/ops/cuda/matmul_kernel.cu:159-190).  Same structure as the 16-bit kernel with 4-byte elements:
 // a 128-byte swizzle row holds 32 elements, one MMA covers K = 8.  A streams in [128 rows x 64 cols] stages
-// (two TMA boxes each), W[b] (K*M*4 <= 64 KB) is resident as an MN-major operand, the fp32 result leaves in
-// 32-column groups through a double-buffered 16 KB staging tile.
+// (two TMA boxes each); the fp32 result leaves in 32-column groups through a double-buffered 16 KB staging
+// tile.  Unlike the 16-bit kernel W is NOT consumed in place: MN-major 32-bit operands need the special
+// 128B_BASE32B swizzle (the first version with plain SWIZZLE_128B produced zeros), so W is transposed once per
+// call into a [B, M, K] scratch (4 MB at C3, ~3 us) and enters as an ordinary K-major operand (K*M*4 <= 64 KB
+// resident per segment).
 namespace {
 
 constexpr int TF_A_STAGES = 4;
@@ -872,8 +875,8 @@ k_segment_matmul_tf32(const __grid_constant__ CUtensorMap map_a, const __grid_co
           mbar_wait(W_EMPTY, w_phase ^ 1);
           w_phase ^= 1;
           mbar_expect_tx(W_FULL, w_bytes);
-          for (int g = 0; g < NG; ++g)   // box [32 cols of M x K rows] -> [K][128 B]: MN-major SW128 atoms
-            tma_load_2d(base + off_w + g * (K * 128), &map_w, g * 32, seg * K, W_FULL);
+          for (int bx = 0; bx < K / 32; ++bx)   // W^T[b]: box [32 cols of K x M rows] -> [M][128 B], K-major SW128 atoms
+            tma_load_2d(base + off_w + bx * (M * 128), &map_w, bx * 32, seg * M, W_FULL);
         }
         const i64 row0 = P.ptr[seg] + (i64)(t - tile_pre[seg]) * TM;
         for (int c = 0; c < KC; ++c) {
@@ -887,8 +890,8 @@ k_segment_matmul_tf32(const __grid_constant__ CUtensorMap map_a, const __grid_co
     }
   } else if (warp == 1) {
     if (has_work) {
-      // D = f32 (bit 4), A/B = TF32 (format 2 at bits 7 and 10), B MN-major (bit 16), N >> 3, M >> 4
-      const u32 idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) | ((u32)(M >> 3) << 17) | ((u32)(TM >> 4) << 24);
+      // D = f32 (bit 4), A/B = TF32 (format 2 at bits 7 and 10), both K-major, N >> 3, M >> 4
+      const u32 idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((u32)(M >> 3) << 17) | ((u32)(TM >> 4) << 24);
       TileIter it(G, (int)gridDim.x, total_tiles, (int)blockIdx.x);
       int seg = seg_of(it.t), cur_seg = -1, stage = 0, acc = 0;
       u32 a_phase = 0, w_phase = 0, t_phase = 0;
@@ -909,7 +912,8 @@ k_segment_matmul_tf32(const __grid_constant__ CUtensorMap map_a, const __grid_co
             const u32 a_base = base + stage * TF_A_BYTES, w_base = base + off_w;
             for (int kk = 0; kk < 8; ++kk) {   // K = 8 per instruction: 32 bytes inside the 128 B swizzle row
               const u64 adesc = make_desc(a_base + (kk >> 2) * (TM * 128) + (kk & 3) * 32, 16, 1024);
-              const u64 bdesc = make_desc(w_base + (c * 8 + kk) * 1024, (u32)(K * 128), 1024);
+              const int kg = c * 8 + kk;   // K step of 8 inside the whole K: box kg/4, 32 bytes per step inside the row
+              const u64 bdesc = make_desc(w_base + (kg >> 2) * (M * 128) + (kg & 3) * 32, 16, 1024);
               tc_mma_tf32(d_tmem, adesc, bdesc, idesc, (c > 0 || kk > 0) ? 1u : 0u);
             }
             tc_commit(A_EMPTY(stage));
@@ -987,6 +991,23 @@ k_segment_matmul_tf32(const __grid_constant__ CUtensorMap map_a, const __grid_co
   }
 }
 
+// W[b] [K, M] -> Wt[b] [M, K]
+__global__ void k_transpose_w_f32(const float* __restrict__ w, float* __restrict__ wt, int K, int M) {
+  __shared__ float tile[32][33];
+  const float* src = w + (size_t)blockIdx.z * K * M;
+  float* dst = wt + (size_t)blockIdx.z * K * M;
+  const int k0 = blockIdx.y * 32, m0 = blockIdx.x * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int k = k0 + i, m = m0 + threadIdx.x;
+    tile[i][threadIdx.x] = (k < K && m < M) ? src[(size_t)k * M + m] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int m = m0 + i, k = k0 + threadIdx.x;
+    if (m < M && k < K) dst[(size_t)m * K + k] = tile[threadIdx.x][i];
+  }
+}
+
 // 2-D row-major fp32 tensor, box [box_rows x 32 cols] (128 bytes), 128 B swizzle
 int make_map_f32(CUtensorMap* m, const void* ptr, i64 rows, i64 cols, int box_rows) {
   EncodeTiledFn enc = get_encode();
@@ -1022,9 +1043,14 @@ bool tf32_supported(i64 N, i64 K, i64 M, i64 B, const void* x, const void* w, co
 
 int segment_matmul_tf32(const void* x, const i64* ptr_dev, const void* w, const void* bias, void* out, i64 N, i64 K, i64 M,
                         i64 B, cudaStream_t st) {
+  float* wt = nullptr;
+  PYGB_CUDA(cudaMallocAsync((void**)&wt, (size_t)B * K * M * 4, st));
+  k_transpose_w_f32<<<dim3((unsigned)((M + 31) / 32), (unsigned)((K + 31) / 32), (unsigned)B), dim3(32, 8), 0, st>>>(
+      (const float*)w, wt, (int)K, (int)M);
+  PYGB_LAUNCH_CHECK();
   CUtensorMap ma, mw, mo;
   if (int e = make_map_f32(&ma, x, N, K, TM)) return e;
-  if (int e = make_map_f32(&mw, w, B * K, M, (int)K)) return e;
+  if (int e = make_map_f32(&mw, wt, B * M, K, (int)M)) return e;
   if (int e = make_map_f32(&mo, out, N, M, TM)) return e;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
@@ -1044,6 +1070,7 @@ int segment_matmul_tf32(const void* x, const i64* ptr_dev, const void* w, const 
   k_segment_matmul_tf32<<<grid, NTHREADS, smem, st>>>(ma, mw, mo, P);
   prof_end(tk, "segment_matmul", st, N);
   PYGB_LAUNCH_CHECK();
+  cudaFreeAsync(wt, st);
   return PYGB200_OK;
 }
 
