@@ -1,9 +1,9 @@
 """hetero_neighbor_sample on a MAG240M-shaped graph (BASELINE configs[3]): 3 node types / 6 edge types,
 fan-out [25,15] for every relation, 1024 paper seeds.  `--scale` multiplies all node/edge counts
 (1.0 = 121.7M papers, 122.4M authors, 25.7k institutions; 1.30G cites, 386M writes, 44.6M affiliated + reverses)."""
-import argparse, json, sys, time
+import argparse, json, os, sys, time
 import torch
-sys.path.insert(0, 'tests')
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), '..')); sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), '..', 'tests'))
 import pyg_lib_b200 as P
 from graphs import lognormal_csr
 

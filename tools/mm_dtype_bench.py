@@ -1,5 +1,5 @@
-import sys, json, torch
-sys.path.insert(0, 'tests')
+import os, sys, json, torch
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), '..')); sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), '..', 'tests'))
 import pyg_lib_b200 as P
 from graphs import ragged_ptr
 dev='cuda:0'
