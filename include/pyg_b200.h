@@ -42,6 +42,8 @@ extern "C" {
 #define PYGB200_S_REPLACE 1u
 #define PYGB200_S_DISJOINT 2u
 #define PYGB200_S_INDEX32 4u      /* rowptr/col/seed are int32 (else int64) */
+#define PYGB200_S_DEFER_CLEANUP 8u /* single node type only: the hash-table reset is done by the following
+                                     pygb200_sampler_export_all (or by the next run) instead of its own launch */
 
 const char* pygb200_last_error(void);
 int pygb200_cuda_version(void);          /* CUDA_VERSION the library was built with

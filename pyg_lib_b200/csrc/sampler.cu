@@ -913,10 +913,14 @@ template <typename out_t>
 __global__ void __launch_bounds__(NT) k_export4(const i64* __restrict__ s0, const i64* __restrict__ s1, const i64* __restrict__ s2,
                                                  out_t* __restrict__ d0, out_t* __restrict__ d1, out_t* __restrict__ d2, i64 n_edges,
                                                  const i64* __restrict__ node, const i64* __restrict__ batch, out_t* __restrict__ dn,
-                                                 i64 n_nodes) {
+                                                 i64 n_nodes, u64* keys, u64* vals, const u32* __restrict__ slots) {
   pdl_enter();
   const i64 n = n_edges > n_nodes ? n_edges : n_nodes;
   for (i64 i = (i64)blockIdx.x * NT + threadIdx.x; i < n; i += (i64)gridDim.x * NT) {
+    if (keys && i < n_nodes) {   // deferred table reset (PYGB200_S_DEFER_CLEANUP)
+      const u32 sl = slots[i];
+      if (sl != NO_SLOT) { keys[sl] = EMPTY; vals[sl] = EMPTY; }
+    }
     if (i < n_edges) {
       if (d0) d0[i] = (out_t)s0[i];
       if (d1) d1[i] = (out_t)s1[i];
@@ -977,6 +981,8 @@ struct pygb200_sampler {
   i64* st_host_dev = nullptr;   // device-side address of st_host
   i64 run_serial = 0;       // completion flag value of the current run
   unsigned epoch = 0;       // tag of the tile words of k_mark_assign launches
+  bool cleanup_pending = false;   // the last run left its table reset to pygb200_sampler_export_all
+  int st_o_list = 0;        // offset of the node-list counters inside `st` (for the deferred cleanup)
   // persistent mt19937 raw stream: survives between runs while torch's CPU generator is exactly where
   // the previous run left it (the common case in a sampling loop) and is extended ahead of time on a
   // side stream, so that generation stays off the critical path of the next run.
@@ -1330,6 +1336,13 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
   }
 
   // ---- workspace
+  if (s->cleanup_pending && !s->types.empty() && s->types[0].tcap) {   // nobody exported the previous run: reset its table now
+    auto& tb = s->types[0];
+    launch_pdl(k_cleanup, grid_for((i64)(tb.slot.cap / 4), NT, s->sm_count), NT, st, tb.keys.as<u64>(), tb.vals.as<u64>(),
+               (const u32*)tb.slot.as<u32>(), (const i64*)(s->st.as<i64>() + s->st_o_list));
+    PYGB_LAUNCH_CHECK();
+    s->cleanup_pending = false;
+  }
   if ((int)s->types.size() < T) s->types.resize(T);
   if ((int)s->rels.size() < R) s->rels.resize(R);
   s->T = T; s->R = R; s->L = L; s->disjoint = disjoint;
@@ -1621,8 +1634,10 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
                s->run_serial);
     PYGB_LAUNCH_CHECK();
   }
-  // table cleanup is stream-ordered after k_final; the host does not wait for it
-  for (int t = 0; t < T; ++t) {
+  // table cleanup is stream-ordered after k_final; the host does not wait for it.  With
+  // PYGB200_S_DEFER_CLEANUP (homogeneous fast path) it rides along with pygb200_sampler_export_all instead.
+  s->cleanup_pending = (flags & PYGB200_S_DEFER_CLEANUP) && T == 1;
+  for (int t = 0; t < T && !s->cleanup_pending; ++t) {
     auto& tb = s->types[t];
     const i64 cap_nodes = (i64)(tb.slot.cap / 4);
     launch_pdl(k_cleanup, grid_for(synced ? cap_nodes : node_cap[t], NT, s->sm_count), NT, st, tb.keys.as<u64>(), tb.vals.as<u64>(),
@@ -1665,6 +1680,7 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
   mt->left = (int32_t)hs[ST_MT_LEFT];
   // the stream persists: remember where it is and pre-generate what a run like this one will need,
   // on the side stream (one CTA, overlaps the caller's work and the next run's first kernels)
+  s->st_o_list = lay.o_list;
   s->mt_expected = *mt;
   s->mt_q = out0 + 256 * hs[ST_BLOCKS];
   s->mt_valid = true;
@@ -1746,17 +1762,22 @@ extern "C" int pygb200_sampler_export_all(pygb200_sampler* s, int32_t rel, void*
   PYGB_CHECK(s && rel >= 0 && rel < s->R && type >= 0 && type < s->T, PYGB200_ERR_ARG, "export_all: bad relation / node type");
   cudaStream_t st = (cudaStream_t)stream;
   const i64 ne = s->rels[rel].n_edges, nn = s->types[type].n_nodes;
-  if (ne == 0 && nn == 0) return PYGB200_OK;
+  const bool clean = s->cleanup_pending && type == 0;
+  if (ne == 0 && nn == 0) { if (clean) s->cleanup_pending = false; return PYGB200_OK; }
+  u64* ck = clean ? s->types[0].keys.as<u64>() : nullptr;
+  u64* cv = clean ? s->types[0].vals.as<u64>() : nullptr;
+  const u32* cs = clean ? s->types[0].slot.as<u32>() : nullptr;
+  if (clean) s->cleanup_pending = false;
   const int g = grid_for(std::max(ne, nn), NT, s->sm_count);
   const i64 *s0 = s->rels[rel].row.as<i64>(), *s1 = s->rels[rel].colv.as<i64>(), *s2 = s->rels[rel].eid.as<i64>();
   const i64* node = s->types[type].nodes.as<i64>();
   const i64* batch = s->disjoint ? s->types[type].batch.as<i64>() : nullptr;
   if (index32)
     launch_pdl(k_export4<int32_t>, g, NT, st, s0, s1, s2, (int32_t*)row_out, (int32_t*)col_out, (int32_t*)edge_id_out, ne, node,
-               batch, (int32_t*)node_id_out, nn);
+               batch, (int32_t*)node_id_out, nn, ck, cv, cs);
   else
     launch_pdl(k_export4<int64_t>, g, NT, st, s0, s1, s2, (int64_t*)row_out, (int64_t*)col_out, (int64_t*)edge_id_out, ne, node,
-               batch, (int64_t*)node_id_out, nn);
+               batch, (int64_t*)node_id_out, nn, ck, cv, cs);
   PYGB_LAUNCH_CHECK();
   return PYGB200_OK;
 }

@@ -109,7 +109,8 @@ neighbor_sample_cuda(const at::Tensor& rowptr, const at::Tensor& col, const at::
   pygb200_sampler* s = get_sampler(seed.device().index(), stream);
   const int L = (int)num_neighbors.size();
   const bool idx32 = st == at::kInt;
-  unsigned flags = (replace ? PYGB200_S_REPLACE : 0u) | (disjoint ? PYGB200_S_DISJOINT : 0u) | (idx32 ? PYGB200_S_INDEX32 : 0u);
+  unsigned flags = (replace ? PYGB200_S_REPLACE : 0u) | (disjoint ? PYGB200_S_DISJOINT : 0u) | (idx32 ? PYGB200_S_INDEX32 : 0u) |
+                   PYGB200_S_DEFER_CLEANUP;   // export_all below resets the table in the same launch
   std::vector<int64_t> nph(L + 1, 0), eph(L, 0);
   int64_t n_nodes = 0, n_edges = 0;
   {
