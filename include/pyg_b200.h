@@ -59,6 +59,14 @@ int pygb200_kernel_launches(void);       /* number of kernels this library launc
 void pygb200_profile_enable(int on);
 int pygb200_profile_read(const char* name, double* ms, int64_t* launches, int64_t* work);
 
+/* Debug timeline of the sampler's kernel chain: when enabled, every sampler kernel stamps %globaltimer (ns)
+ * when its block 0 starts working / finishes, and when its serial "last block" section starts / ends.
+ * Each word is (id << 56) | (smid << 48) | (time & 2^48-1); id = kernel (1 seed, 2 count, 3 sample, 4 mark, 5 assign, 6 final,
+ * 7 export) | 8 for the last-block section | 16 for an end stamp.  `pygb200_timeline_read` synchronises the
+ * device, copies up to `cap` words (in stamping order) and clears the buffer; returns the word count. */
+int pygb200_timeline_enable(int on);
+int64_t pygb200_timeline_read(uint64_t* out, int64_t cap);
+
 /* ------------------------------------------------------------------------------------ matmul
  * out[ptr[b]:ptr[b+1], :] = x[ptr[b]:ptr[b+1], :] @ w[b]        (row-major, contiguous)
  *   x [N,K], w [B,K,M], out [N,M] of `dtype`; ptr_dev [B+1] int64 on the DEVICE.
@@ -181,6 +189,24 @@ int pygb200_sampler_run_sharded(pygb200_sampler* s, int32_t T, int32_t R, int32_
                                 pygb200_mt19937* mt_inout, int64_t* nodes_per_hop,
                                 int64_t* edges_per_hop, int64_t* n_nodes, int64_t* n_edges, void* stream,
                                 const pygb200_shard* shard);
+
+/* Results without an export pass (latency path).  `pygb200_sampler_bounds` gives the static upper bounds of a
+ * run — nodes per type, edges per relation — from the seed counts and fan-outs alone (the recurrence of
+ * neighbor_kernel.cpp:430-475: every frontier node emits at most `k` edges, every edge at most one new node);
+ * PYGB200_ERR_UNSUPPORTED if a fan-out is -1 or the worst case exceeds 8 GiB.  `pygb200_sampler_bind_outputs`
+ * hands the sampler caller-owned int64 device arrays of at least those capacities (edge_id may be NULL, or hold
+ * NULL entries, when edge ids are not wanted) for the NEXT run only: that run's kernels then write rows, local
+ * column ids, edge ids and the per-type node lists straight into them — the first n_edges_out[r] /
+ * n_nodes_out[t] entries are the result, there is nothing to export, and the hash tables are reset behind the
+ * run.  The binding is honoured for bounded, int64, non-disjoint, non-sharded runs whose bounds fit the
+ * capacities; `pygb200_sampler_outputs_direct` says whether the last run used it (1) or the caller has to
+ * export as usual (0).  After a direct run the export functions fail with PYGB200_ERR_ARG. */
+int pygb200_sampler_bounds(int32_t T, int32_t R, int32_t L, const pygb200_relation* rels, const int64_t* n_seeds,
+                           const int64_t* num_neighbors, int64_t* node_cap, int64_t* edge_cap);
+int pygb200_sampler_bind_outputs(pygb200_sampler* s, int32_t T, int32_t R, void* const* row, void* const* col,
+                                 void* const* edge_id, void* const* node, const int64_t* edge_cap,
+                                 const int64_t* node_cap);
+int pygb200_sampler_outputs_direct(pygb200_sampler* s);
 
 /* Asynchronous copies (cast to int32 when index32 != 0) of the last run's results into caller
  * buffers of exactly n_edges[r] / n_nodes[t] elements.  row = local index of the source (frontier)

@@ -24,6 +24,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <mutex>
 #include <vector>
 
@@ -141,9 +142,27 @@ struct PassArgs {
 // Programmatic dependent launch: the kernels of a run form a chain on one stream.  Each waits for its
 // predecessor's completion + memory flush here, then lets its successor's blocks be scheduled early
 // (they park in their own pdl_enter), which hides launch latency and the block-scheduling ramp.
-__device__ __forceinline__ void pdl_enter() {
+// Debug timeline (pygb200_timeline_enable): %globaltimer stamps by thread 0 of block 0 (or of the calling
+// block for tl_mark_any), word 0 of the buffer counts the stamps.  Off: one constant-bank load per mark.
+__constant__ u64* g_tl = nullptr;
+constexpr int TL_CAP = 8192;
+__device__ __forceinline__ void tl_mark_any(int id) {
+  u64* tl = g_tl;
+  if (tl == nullptr || threadIdx.x != 0) return;
+  u64 t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  const u64 i = atomicAdd(tl, 1ull);
+  u32 smid;
+  asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+  if (i < TL_CAP) tl[1 + i] = ((u64)id << 56) | ((u64)(smid & 0xff) << 48) | (t & ((1ull << 48) - 1));
+}
+__device__ __forceinline__ void tl_mark(int id) { if (blockIdx.x == 0) tl_mark_any(id); }
+enum { TL_SEED = 1, TL_COUNT = 2, TL_SAMPLE = 3, TL_MARK = 4, TL_ASSIGN = 5, TL_FINAL = 6, TL_EXPORT = 7, TL_LAST = 8, TL_END = 16 };
+
+__device__ __forceinline__ void pdl_enter(int id = 0) {
   asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if (id) tl_mark(id);
 }
 
 __device__ __forceinline__ u64 hash64(u64 x) {
@@ -359,7 +378,7 @@ __device__ __forceinline__ void deferred_lookup(const PassArgs& a) {
 template <typename idx_t>
 __global__ void __launch_bounds__(NT) k_count(const PassArgs a) {
   __shared__ u32 s_win[MT_WIN];
-  pdl_enter();
+  pdl_enter(TL_COUNT);
   deferred_lookup(a);  // must precede the ticket: the last block overwrites ST_PASS_E / ST_PASS_BASE
   const i64 begin = a.st[a.o_src_begin], end = a.st[a.o_src_end];
   const i64 F = end - begin;
@@ -409,17 +428,20 @@ __global__ void __launch_bounds__(NT) k_count(const PassArgs a) {
       for (int p = 0; p < 4; ++p) a.tile_func[4 * tile + p] = tot_f.d[p];
     }
   }
+  tl_mark(TL_COUNT | TL_END);
   if (last_block(&a.st[ST_TICKET_A])) {
+    tl_mark_any(TL_COUNT | TL_LAST);
     if (threadIdx.x == 0) a.st[ST_PASS_F] = F;
     scan_frontier_tiles(a, ntiles);
     mt_extend_block<3>(a.raw, a.gen, a.out0 + 256 * rng_blocks_for_units(a.st[ST_CURSOR]), a.raw_cap, a.st, s_win);
+    tl_mark_any(TL_COUNT | TL_LAST | TL_END);
   }
 }
 
 // One group of G lanes per frontier node.
 template <typename idx_t, int G>
-__global__ void __launch_bounds__(NT) k_sample(const PassArgs a) {
-  pdl_enter();
+__global__ void __launch_bounds__(NT, SAMPLE_MIN_BLOCKS) k_sample(const PassArgs a) {
+  pdl_enter(TL_SAMPLE);
   const i64 F = a.st[ST_PASS_F];
   const i64 begin = a.st[a.o_src_begin];
   const i64 pbase = a.st[ST_PASS_BASE];
@@ -488,6 +510,7 @@ __global__ void __launch_bounds__(NT) k_sample(const PassArgs a) {
       }
     }
   }
+  tl_mark(TL_SAMPLE | TL_END);
 }
 
 // seed time per batch id (neighbor_kernel.cpp:417-428): explicit seed_time wins, else node_time[seed]
@@ -528,7 +551,7 @@ __global__ void __launch_bounds__(NT) k_seed(const PassArgs a, const idx_t* __re
 // updates the dst type's counters.
 __global__ void __launch_bounds__(NT) k_mark(const PassArgs a) {
   __shared__ u32 s_w[NT / 32];
-  pdl_enter();
+  pdl_enter(TL_MARK);
   const i64 E = a.st[ST_PASS_E];
   const i64 ntiles = ceil_div(E, ETILE);
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -562,7 +585,9 @@ __global__ void __launch_bounds__(NT) k_mark(const PassArgs a) {
     if (threadIdx.x == 0) a.mtile[tile] = tot;
     __syncthreads();
   }
+  tl_mark(TL_MARK | TL_END);
   if (last_block(&a.st[ST_TICKET_B])) {
+    tl_mark_any(TL_MARK | TL_LAST);
     // ordered exclusive scan of tile counts by one block
     __shared__ i64 s_s[NT / 32];
     __shared__ i64 carry;
@@ -610,6 +635,7 @@ __global__ void __launch_bounds__(NT) k_mark(const PassArgs a) {
       a.st[a.he_begin + t] = e;
       a.st[a.he_end + t] = n;
     }
+    tl_mark_any(TL_MARK | TL_LAST | TL_END);
   }
 }
 
@@ -741,7 +767,7 @@ __global__ void __launch_bounds__(NT) k_mark_assign(const PassArgs a, u32 epoch)
 }
 
 __global__ void __launch_bounds__(NT) k_assign(const PassArgs a) {
-  pdl_enter();
+  pdl_enter(TL_ASSIGN);
   const i64 E = a.st[ST_PASS_E];
   const i64 pbase = a.st[ST_PASS_BASE];
   const i64 list_base = a.st[ST_LIST_BASE], ids_base = a.st[ST_IDS_BASE];
@@ -795,7 +821,7 @@ __global__ void k_seed_end(i64* st, int t, int L, int o_list, int o_begin, int o
 // always consumed (rand_engine.h:28).
 __global__ void __launch_bounds__(NT) k_final(const PassArgs a, int o_mt, i64* host_st, int n_words, i64 serial) {
   __shared__ u32 s_win[MT_WIN];
-  pdl_enter();
+  pdl_enter(TL_FINAL);
   deferred_lookup(a);
   if (blockIdx.x != 0) return;
   const i64 blocks = rng_blocks_for_units(a.st[ST_CURSOR]);
@@ -820,6 +846,7 @@ __global__ void __launch_bounds__(NT) k_final(const PassArgs a, int o_mt, i64* h
     __syncthreads();
     if (threadIdx.x == 0) { *reinterpret_cast<volatile i64*>(host_st + n_words) = serial; __threadfence_system(); }
   }
+  tl_mark(TL_FINAL | TL_END);
 }
 
 // Seeds of one node type in ONE block (n <= SEED_FUSED_MAX): list, insert, first-occurrence ranks, ids.
@@ -828,10 +855,10 @@ constexpr int SEED_NT = 1024;
 constexpr int SEED_FUSED_MAX = 16384;
 template <typename idx_t>
 __global__ void __launch_bounds__(SEED_NT) k_seed_fused(const PassArgs a, const idx_t* __restrict__ seeds, int n, i64 batch0,
-                                                         int L, int o_begin, int o_end, int o_nph) {
+                                                         int L, int o_begin, int o_end, int o_nph, const PassArgs c, int do_count) {
   __shared__ int s_w[SEED_NT / 32];
   __shared__ int s_carry;
-  pdl_enter();
+  pdl_enter(TL_SEED);
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   for (int i = threadIdx.x; i < n; i += SEED_NT) {
     const i64 v = (i64)seeds[i];
@@ -871,6 +898,88 @@ __global__ void __launch_bounds__(SEED_NT) k_seed_fused(const PassArgs a, const 
     a.st[o_end] = n;
     a.st[o_nph] = n;
   }
+  tl_mark(TL_SEED | TL_END);
+  if (!do_count) return;
+  // ---- the first pass's k_count, done here: its frontier is exactly this seed list and one block holds it
+  // (n <= SEED_FUSED_MAX), so degrees, in-tile scans (256-node tiles, same records as k_count) and the scan
+  // over the <= 64 tiles need no second launch and no last-block protocol.
+  __shared__ u32 s_win[MT_WIN];
+  __shared__ u32 s_tv[SEED_NT / 32];
+  __shared__ Func4 s_tf[SEED_NT / 32];
+  __shared__ u32 s_tile_v[SEED_FUSED_MAX / NT];
+  __shared__ Func4 s_tile_f[SEED_FUSED_MAX / NT];
+  const idx_t* __restrict__ rowptr = (const idx_t*)c.rowptr;
+  __syncthreads();
+  for (int base = 0; base < n; base += SEED_NT) {
+    const int i = base + threadIdx.x;
+    i64 rs = 0, deg = 0, n_out = 0, n16 = 0, n32 = 0, n64 = 0;
+    Func4 f = {{0, 0, 0, 0}};
+    if (i < n) {
+      const i64 v = (i64)seeds[i];
+      rs = (i64)rowptr[v];
+      deg = (i64)rowptr[v + 1] - rs;
+      classify(deg, c.fanout, c.replace, &n_out, &n16, &n32, &n64);
+      if (n32 == 0 && n64 == 0) {
+        f.d[0] = f.d[1] = f.d[2] = f.d[3] = (u32)n16;
+      } else {
+#pragma unroll
+        for (int p = 0; p < 4; ++p) f.d[p] = (u32)(rng_node_end(p, n16, n32, n64) - p);
+      }
+    }
+    u32 iv = (u32)n_out; Func4 iff = f;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const u32 ov = __shfl_up_sync(0xffffffffu, iv, d);
+      Func4 of;
+#pragma unroll
+      for (int p = 0; p < 4; ++p) of.d[p] = __shfl_up_sync(0xffffffffu, iff.d[p], d);
+      if (lane >= d) { iv += ov; iff = compose(of, iff); }
+    }
+    if (lane == 31) { s_tv[wid] = iv; s_tf[wid] = iff; }
+    __syncthreads();
+    const int w0 = wid & ~7;   // first warp of this thread's 256-node tile
+    u32 pv = 0; Func4 pfx = {{0, 0, 0, 0}};
+    for (int w = w0; w < wid; ++w) { pv += s_tv[w]; pfx = compose(pfx, s_tf[w]); }
+    u32 ev = __shfl_up_sync(0xffffffffu, iv, 1);
+    Func4 ef;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) ef.d[p] = __shfl_up_sync(0xffffffffu, iff.d[p], 1);
+    if (lane == 0) { ev = 0; ef = {{0, 0, 0, 0}}; }
+    const Func4 exf = compose(pfx, ef);
+    if (i < n) {
+      NodeRec r;
+      r.rs = rs; r.deg = (u32)deg; r.loc_off = pv + ev;
+      r.pf[0] = exf.d[0]; r.pf[1] = exf.d[1]; r.pf[2] = exf.d[2]; r.pf[3] = exf.d[3];
+      c.rec[i] = r;
+    }
+    if (lane == 31 && (wid & 7) == 7) {   // last thread of a tile: the tile's totals
+      const int tile = (base >> 8) + (wid >> 3);
+      s_tile_v[tile] = pv + iv;
+      s_tile_f[tile] = compose(pfx, iff);
+    }
+    __syncthreads();
+  }
+  tl_mark(TL_COUNT | TL_END);
+  if (threadIdx.x == 0) {
+    const int ntiles = (n + NT - 1) / NT;
+    i64 off = 0, pos = c.st[ST_CURSOR];
+    for (int t = 0; t < ntiles; ++t) {
+      c.tile_off[t] = off;
+      c.tile_pos[t] = pos;
+      off += s_tile_v[t];
+      pos += s_tile_f[t].d[pos & 3];
+    }
+    c.st[ST_PASS_F] = n;
+    c.st[ST_PASS_E] = off;
+    c.st[ST_CURSOR] = pos;
+    c.st[ST_PASS_BASE] = c.st[c.o_rel_edges];
+    c.st[c.o_rel_edges] += off;
+    c.st[c.o_eph] = off;
+  }
+  tl_mark(TL_COUNT | TL_LAST);
+  __syncthreads();
+  mt_extend_block<3>(c.raw, c.gen, c.out0 + 256 * rng_blocks_for_units(c.st[ST_CURSOR]), c.raw_cap, c.st, s_win);
+  tl_mark(TL_COUNT | TL_LAST | TL_END);
 }
 
 __global__ void __launch_bounds__(NT) k_cleanup(u64* keys, u64* vals, const u32* __restrict__ slots, const i64* n_ptr) {
@@ -914,7 +1023,7 @@ __global__ void __launch_bounds__(NT) k_export4(const i64* __restrict__ s0, cons
                                                  out_t* __restrict__ d0, out_t* __restrict__ d1, out_t* __restrict__ d2, i64 n_edges,
                                                  const i64* __restrict__ node, const i64* __restrict__ batch, out_t* __restrict__ dn,
                                                  i64 n_nodes, u64* keys, u64* vals, const u32* __restrict__ slots) {
-  pdl_enter();
+  pdl_enter(TL_EXPORT);
   const i64 n = n_edges > n_nodes ? n_edges : n_nodes;
   for (i64 i = (i64)blockIdx.x * NT + threadIdx.x; i < n; i += (i64)gridDim.x * NT) {
     if (keys && i < n_nodes) {   // deferred table reset (PYGB200_S_DEFER_CLEANUP)
@@ -931,6 +1040,7 @@ __global__ void __launch_bounds__(NT) k_export4(const i64* __restrict__ s0, cons
       else dn[i] = (out_t)node[i];
     }
   }
+  tl_mark(TL_EXPORT | TL_END);
 }
 template <typename out_t>
 __global__ void __launch_bounds__(NT) k_export_pairs(const i64* __restrict__ batch, const i64* __restrict__ node,
@@ -976,6 +1086,10 @@ struct pygb200_sampler {
   struct RelBuf { DevBuf row, colv, eid; i64 n_edges = 0; };
   std::vector<TypeBuf> types;
   std::vector<RelBuf> rels;
+  // caller-owned result arrays for the NEXT run (pygb200_sampler_bind_outputs): the run's kernels write rows /
+  // local cols / edge ids / node lists straight into them, so no export pass follows
+  struct Bound { std::vector<i64*> row, col, eid, node; std::vector<i64> ecap, ncap; bool armed = false; } bound;
+  bool last_direct = false;   // the last run wrote into the bound arrays (exports are refused)
   DevBuf eslot, erank, rec, tile_out, tile_func, tile_off, tile_pos, mtile, raw, st, gen;
   i64* st_host = nullptr;   // pinned + mapped mirror of the state buffer (k_final writes it directly)
   i64* st_host_dev = nullptr;   // device-side address of st_host
@@ -1009,10 +1123,47 @@ struct pygb200_sampler {
   std::mutex mu;
 };
 
+// Debug: host-side time per segment of a run (PYGB200_HOST_TIMING=1, printed at exit)
+struct HostTimes {
+  bool on = getenv("PYGB200_HOST_TIMING") != nullptr;
+  double acc[6] = {0, 0, 0, 0, 0, 0};
+  long runs = 0;
+  static double now() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+  ~HostTimes() {
+    if (on && runs)
+      fprintf(stderr, "[pygb200 host us/run over %ld runs] setup %.2f  mt+memset %.2f  seeds %.2f  hops+final %.2f  spin %.2f  post %.2f\n",
+              runs, acc[0] / runs, acc[1] / runs, acc[2] / runs, acc[3] / runs, acc[4] / runs, acc[5] / runs);
+  }
+};
+static HostTimes g_ht;
+
 extern "C" const char* pygb200_last_error(void) { return g_err.c_str(); }
 extern "C" int pygb200_cuda_version(void) { return CUDART_VERSION; }
 extern "C" int pygb200_kernel_launches(void) { return g_launches.load(); }
 extern "C" void pygb200_profile_enable(int on) { g_prof_on.store(on != 0); }
+static u64* g_tl_buf = nullptr;
+extern "C" int pygb200_timeline_enable(int on) {
+  u64* p = nullptr;
+  if (on) {
+    if (!g_tl_buf) PYGB_CUDA(cudaMalloc(&g_tl_buf, (size_t)(TL_CAP + 1) * 8));
+    PYGB_CUDA(cudaMemset(g_tl_buf, 0, (size_t)(TL_CAP + 1) * 8));
+    p = g_tl_buf;
+  }
+  PYGB_CUDA(cudaDeviceSynchronize());
+  PYGB_CUDA(cudaMemcpyToSymbol(g_tl, &p, sizeof(p)));
+  return PYGB200_OK;
+}
+extern "C" int64_t pygb200_timeline_read(uint64_t* out, int64_t cap) {
+  if (!g_tl_buf || !out || cap <= 0) return 0;
+  if (cudaDeviceSynchronize() != cudaSuccess) return 0;
+  u64 n = 0;
+  if (cudaMemcpy(&n, g_tl_buf, 8, cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
+  if (n > (u64)TL_CAP) n = TL_CAP;
+  if ((i64)n > cap) n = (u64)cap;
+  if (n && cudaMemcpy(out, g_tl_buf + 1, (size_t)n * 8, cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
+  cudaMemset(g_tl_buf, 0, 8);
+  return (int64_t)n;
+}
 extern "C" int pygb200_profile_read(const char* name, double* ms, int64_t* launches, int64_t* work) {
   std::lock_guard<std::mutex> lock(g_prof_mu);
   prof_drain_locked();
@@ -1262,6 +1413,8 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
                      int64_t* n_nodes_out, int64_t* n_edges_out, cudaStream_t st, const pygb200_shard* shard,
                      const pygb200_temporal* temporal) {
   const bool replace = flags & PYGB200_S_REPLACE, disjoint = flags & PYGB200_S_DISJOINT, idx32 = flags & PYGB200_S_INDEX32;
+  double ht_last = g_ht.on ? HostTimes::now() : 0;
+  auto ht_lap = [&](int seg) { if (g_ht.on) { const double t = HostTimes::now(); g_ht.acc[seg] += t - ht_last; ht_last = t; } };
   i64 total_seeds = 0;
   for (int t = 0; t < T; ++t) {
     PYGB_CHECK(n_seeds[t] >= 0, PYGB200_ERR_ARG, "negative seed count");
@@ -1335,6 +1488,15 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
                PYGB200_ERR_ARG, "bad shard descriptor");
   }
 
+  // ---- results straight into the caller's arrays?  (bounded int64 non-disjoint runs only; the binding is one-shot)
+  bool direct = s->bound.armed && !synced && !sharded && !idx32 && !disjoint && (int)s->bound.node.size() == T &&
+                (int)s->bound.row.size() == R;
+  s->bound.armed = false;
+  s->last_direct = false;
+  for (int t = 0; t < T && direct; ++t) direct = s->bound.node[t] != nullptr && s->bound.ncap[t] >= node_cap[t];
+  for (int r = 0; r < R && direct; ++r)
+    direct = s->bound.row[r] != nullptr && s->bound.col[r] != nullptr && s->bound.ecap[r] >= rel_cap[r];
+
   // ---- workspace
   if (s->cleanup_pending && !s->types.empty() && s->types[0].tcap) {   // nobody exported the previous run: reset its table now
     auto& tb = s->types[0];
@@ -1386,6 +1548,7 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
     if (int e = ensure_edge_scratch(s, total_seeds, st)) return e;
   }
 
+  ht_lap(0);
   // ---- mt19937 raw stream: continue the persistent one or (re)start from the caller's engine state.
   // Pre-generation runs TWO runs ahead on the side stream: the launch made at the end of run i-1 already
   // covers run i+1, so in a steady loop this run only waits for an event that completed long ago while
@@ -1468,6 +1631,14 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
       a.row = s->rels[rel].row.as<i64>(); a.colv = s->rels[rel].colv.as<i64>(); a.eid = s->rels[rel].eid.as<i64>();
       a.o_rel_edges = lay.o_rel + rel;
     }
+    if (direct) {
+      a.dst_nodes = s->bound.node[dst_t];
+      if (src_t >= 0) a.src_nodes = s->bound.node[src_t];
+      if (rel >= 0) {
+        a.row = s->bound.row[rel]; a.colv = s->bound.col[rel];
+        if (s->bound.eid[rel]) a.eid = s->bound.eid[rel];
+      }
+    }
     a.eslot = s->eslot.as<u32>(); a.erank = s->erank.as<u32>(); a.rec = s->rec.as<NodeRec>();
     a.tile_out = s->tile_out.as<i64>(); a.tile_func = s->tile_func.as<u32>();
     a.tile_off = s->tile_off.as<i64>(); a.tile_pos = s->tile_pos.as<i64>(); a.mtile = s->mtile.as<i64>();
@@ -1490,12 +1661,38 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
     return PYGB200_OK;
   };
 
+  ht_lap(1);
   // ---- seeds (neighbor_kernel.cpp:409-416, :669-704)
   if (any_time) if (int e = s->seed_times.ensure((size_t)std::max<i64>(total_seeds, 1) * 8, 0, st)) return e;
-  i64 batch0 = 0;
-  for (int t = 0; t < T; ++t) {
+  // The first pass that will run (hop 0) has its k_count folded into the seed kernel of its source type when
+  // that seed list fits one block: one launch less on the critical path.  That seed kernel goes last, because
+  // the multi-kernel seed path of another type would overwrite the pass header it leaves behind.
+  int fuse_r = -1, fuse_t = -1;
+  if (!synced && !sharded && !any_time && L > 0 && !getenv("PYGB200_NO_FUSE_COUNT")) {
+    for (int r = 0; r < R; ++r) {
+      if (num_neighbors[(size_t)r * L] == 0) continue;
+      if (fb[(size_t)rels[r].src_type * (L + 1)] == 0 || eb[(size_t)r * L] == 0) continue;
+      const int t0 = rels[r].src_type;
+      if (n_seeds[t0] > 0 && n_seeds[t0] <= SEED_FUSED_MAX) { fuse_r = r; fuse_t = t0; }
+      break;
+    }
+  }
+  std::vector<i64> batch_base((size_t)T, 0);
+  if (disjoint) for (int t = 1; t < T; ++t) batch_base[t] = batch_base[t - 1] + n_seeds[t - 1];
+  for (int ti = 0; ti < T; ++ti) {
+    // order: every type but fuse_t, then fuse_t
+    int t = ti;
+    if (fuse_t >= 0) t = ti == T - 1 ? fuse_t : (ti >= fuse_t ? ti + 1 : ti);
+    const i64 batch0 = batch_base[t];
     PassArgs a = make_args(-1, t, -1);
     a.seed_mode = 1;
+    PassArgs c = a;
+    const int do_count = t == fuse_t;
+    if (do_count) {
+      c = make_args(rels[fuse_r].src_type, rels[fuse_r].dst_type, fuse_r);
+      c.fanout = num_neighbors[(size_t)fuse_r * L];
+      c.o_eph = lay.o_eph + fuse_r * L;
+    }
     if (any_time && n_seeds[t] > 0) {
       const i64* stt = temporal->seed_time ? reinterpret_cast<const i64*>(temporal->seed_time[t]) : nullptr;
       const i64* ntt = temporal->node_time ? reinterpret_cast<const i64*>(temporal->node_time[t]) : nullptr;
@@ -1506,9 +1703,9 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
     }
     if (n_seeds[t] > 0 && n_seeds[t] <= SEED_FUSED_MAX) {
       if (idx32) launch_pdl(k_seed_fused<int32_t>, 1, SEED_NT, st, a, (const int32_t*)seeds[t], (int)n_seeds[t], batch0, (int)L,
-                            lay.o_begin + t, lay.o_end + t, lay.o_nph + t * (L + 1));
+                            lay.o_begin + t, lay.o_end + t, lay.o_nph + t * (L + 1), c, do_count);
       else launch_pdl(k_seed_fused<int64_t>, 1, SEED_NT, st, a, (const int64_t*)seeds[t], (int)n_seeds[t], batch0, (int)L,
-                      lay.o_begin + t, lay.o_end + t, lay.o_nph + t * (L + 1));
+                      lay.o_begin + t, lay.o_end + t, lay.o_nph + t * (L + 1), c, do_count);
       PYGB_LAUNCH_CHECK();
     } else if (n_seeds[t] > 0) {
       const int g = grid_for(n_seeds[t], NT, s->sm_count);
@@ -1522,9 +1719,9 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
       k_seed_end<<<1, 1, 0, st>>>(dst, t, L, lay.o_list, lay.o_begin, lay.o_end, lay.o_nph);
       PYGB_LAUNCH_CHECK();
     }  // n == 0: the zeroed state already says "empty list, empty slice"
-    if (disjoint) batch0 += n_seeds[t];
   }
 
+  ht_lap(2);
   // ---- hops.  Bounded mode defers every pass's lookup into the next k_count / the final kernel.
   i64* lk_colv = nullptr; const u64* lk_vals = nullptr; i64 lk_E = 0;
   for (int h = 0; h < L; ++h) {
@@ -1556,7 +1753,8 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
         a.o_eph = lay.o_eph + r * L + h;
         a.lk_colv = lk_colv; a.lk_vals = lk_vals;
         with_hop_end(a);
-        if (int e = idx32 ? launch_count<int32_t>(s, a, Fb, lk_E, st) : launch_count<int64_t>(s, a, Fb, lk_E, st)) return e;
+        if (!(h == 0 && r == fuse_r))  // (counted by the seed kernel)
+          if (int e = idx32 ? launch_count<int32_t>(s, a, Fb, lk_E, st) : launch_count<int64_t>(s, a, Fb, lk_E, st)) return e;
         if (!sharded) {
           if (int e = idx32 ? launch_rest<int32_t>(s, a, Fb, Eb, false, st) : launch_rest<int64_t>(s, a, Fb, Eb, false, st)) return e;
         } else {
@@ -1636,7 +1834,8 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
   }
   // table cleanup is stream-ordered after k_final; the host does not wait for it.  With
   // PYGB200_S_DEFER_CLEANUP (homogeneous fast path) it rides along with pygb200_sampler_export_all instead.
-  s->cleanup_pending = (flags & PYGB200_S_DEFER_CLEANUP) && T == 1;
+  s->cleanup_pending = (flags & PYGB200_S_DEFER_CLEANUP) && T == 1 && !direct;
+  s->last_direct = direct;
   for (int t = 0; t < T && !s->cleanup_pending; ++t) {
     auto& tb = s->types[t];
     const i64 cap_nodes = (i64)(tb.slot.cap / 4);
@@ -1644,6 +1843,7 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
                (const u32*)tb.slot.as<u32>(), (const i64*)(dst + lay.o_list + t));
     PYGB_LAUNCH_CHECK();
   }
+  ht_lap(3);
   {  // wait for k_final's flag (spin on mapped memory; keep an eye on the stream in case the run died)
     volatile i64* flag = s->st_host + lay.words;
     unsigned long long spins = 0;
@@ -1662,6 +1862,7 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
     }
     std::atomic_thread_fence(std::memory_order_acquire);
   }
+  ht_lap(4);
   const i64* hs = s->st_host;
   PYGB_CHECK(hs[ST_ERROR] == 0, PYGB200_ERR_INTERNAL, "sampler: mt19937 stream buffer too small (internal bound violated)");
   s->dirty = false;
@@ -1697,6 +1898,8 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
       }
     }
   }
+  ht_lap(5);
+  if (g_ht.on) g_ht.runs += 1;
   return PYGB200_OK;
 }
 
@@ -1743,9 +1946,68 @@ extern "C" int pygb200_sampler_run_sharded(pygb200_sampler* s, int32_t T, int32_
                           n_nodes_out, n_edges_out, (cudaStream_t)stream, shard, nullptr);
 }
 
+extern "C" int pygb200_sampler_bounds(int32_t T, int32_t R, int32_t L, const pygb200_relation* rels,
+                                      const int64_t* n_seeds, const int64_t* num_neighbors, int64_t* node_cap,
+                                      int64_t* edge_cap) {
+  PYGB_CHECK(n_seeds && node_cap && (rels || R == 0) && (edge_cap || R == 0) && (num_neighbors || L == 0 || R == 0),
+             PYGB200_ERR_ARG, "pygb200_sampler_bounds: null argument");
+  PYGB_CHECK(T >= 1 && T <= 1024 && R >= 0 && L >= 0, PYGB200_ERR_ARG, "pygb200_sampler_bounds: bad T/R/L");
+  // same recurrence as the run's static bounds: frontier per (type, hop) -> edges per (relation, hop)
+  std::vector<i64> fb((size_t)T * (L + 1), 0);
+  for (int t = 0; t < T; ++t) fb[(size_t)t * (L + 1)] = n_seeds[t];
+  for (int r = 0; r < R; ++r) {
+    PYGB_CHECK(rels[r].src_type >= 0 && rels[r].src_type < T && rels[r].dst_type >= 0 && rels[r].dst_type < T,
+               PYGB200_ERR_ARG, "pygb200_sampler_bounds: relation node type out of range");
+    edge_cap[r] = 0;
+  }
+  i64 total = 0;
+  for (int h = 0; h < L; ++h)
+    for (int r = 0; r < R; ++r) {
+      const i64 k = num_neighbors[(size_t)r * L + h];
+      PYGB_CHECK(k >= 0, PYGB200_ERR_UNSUPPORTED, "pygb200_sampler_bounds: a fan-out of -1 has no static bound");
+      const i64 e = sat_mul(fb[(size_t)rels[r].src_type * (L + 1) + h], k);
+      edge_cap[r] = sat_add(edge_cap[r], e);
+      i64& nf = fb[(size_t)rels[r].dst_type * (L + 1) + h + 1];
+      nf = sat_add(nf, e);
+      total = sat_add(total, sat_mul(e, 4));
+    }
+  for (int t = 0; t < T; ++t) {
+    i64 c = 0;
+    for (int h = 0; h <= L; ++h) c = sat_add(c, fb[(size_t)t * (L + 1) + h]);
+    node_cap[t] = c;
+  }
+  PYGB_CHECK(total <= ((i64)1 << 30), PYGB200_ERR_UNSUPPORTED, "pygb200_sampler_bounds: worst case too large for static sizing");
+  return PYGB200_OK;
+}
+
+extern "C" int pygb200_sampler_bind_outputs(pygb200_sampler* s, int32_t T, int32_t R, void* const* row, void* const* col,
+                                            void* const* edge_id, void* const* node, const int64_t* edge_cap,
+                                            const int64_t* node_cap) {
+  PYGB_CHECK(s && node && node_cap && (R == 0 || (row && col && edge_cap)) && T >= 1 && R >= 0, PYGB200_ERR_ARG,
+             "pygb200_sampler_bind_outputs: null argument");
+  std::lock_guard<std::mutex> lock(s->mu);
+  auto& b = s->bound;
+  b.row.assign(R, nullptr); b.col.assign(R, nullptr); b.eid.assign(R, nullptr); b.ecap.assign(R, 0);
+  b.node.assign(T, nullptr); b.ncap.assign(T, 0);
+  for (int r = 0; r < R; ++r) {
+    b.row[r] = (i64*)row[r]; b.col[r] = (i64*)col[r]; b.eid[r] = edge_id ? (i64*)edge_id[r] : nullptr;
+    b.ecap[r] = edge_cap[r];
+  }
+  for (int t = 0; t < T; ++t) { b.node[t] = (i64*)node[t]; b.ncap[t] = node_cap[t]; }
+  b.armed = true;
+  return PYGB200_OK;
+}
+
+extern "C" int pygb200_sampler_outputs_direct(pygb200_sampler* s) {
+  if (!s) return 0;
+  std::lock_guard<std::mutex> lock(s->mu);
+  return s->last_direct ? 1 : 0;
+}
+
 extern "C" int pygb200_sampler_export_edges(pygb200_sampler* s, int32_t rel, void* row_out, void* col_out,
                                             void* edge_id_out, int index32, void* stream) {
   PYGB_CHECK(s && rel >= 0 && rel < s->R, PYGB200_ERR_ARG, "export_edges: bad relation");
+  PYGB_CHECK(!s->last_direct, PYGB200_ERR_ARG, "export: the last run wrote its results into the bound output arrays");
   cudaStream_t st = (cudaStream_t)stream;
   const i64 n = s->rels[rel].n_edges;
   if (n == 0) return PYGB200_OK;
@@ -1760,6 +2022,7 @@ extern "C" int pygb200_sampler_export_edges(pygb200_sampler* s, int32_t rel, voi
 extern "C" int pygb200_sampler_export_all(pygb200_sampler* s, int32_t rel, void* row_out, void* col_out, void* edge_id_out,
                                           int32_t type, void* node_id_out, int index32, void* stream) {
   PYGB_CHECK(s && rel >= 0 && rel < s->R && type >= 0 && type < s->T, PYGB200_ERR_ARG, "export_all: bad relation / node type");
+  PYGB_CHECK(!s->last_direct, PYGB200_ERR_ARG, "export: the last run wrote its results into the bound output arrays");
   cudaStream_t st = (cudaStream_t)stream;
   const i64 ne = s->rels[rel].n_edges, nn = s->types[type].n_nodes;
   const bool clean = s->cleanup_pending && type == 0;
@@ -1785,6 +2048,7 @@ extern "C" int pygb200_sampler_export_all(pygb200_sampler* s, int32_t rel, void*
 extern "C" int pygb200_sampler_export_nodes(pygb200_sampler* s, int32_t type, void* node_id_out, int index32,
                                             void* stream) {
   PYGB_CHECK(s && type >= 0 && type < s->T, PYGB200_ERR_ARG, "export_nodes: bad node type");
+  PYGB_CHECK(!s->last_direct, PYGB200_ERR_ARG, "export: the last run wrote its results into the bound output arrays");
   cudaStream_t st = (cudaStream_t)stream;
   const i64 n = s->types[type].n_nodes;
   if (n == 0 || !node_id_out) return PYGB200_OK;

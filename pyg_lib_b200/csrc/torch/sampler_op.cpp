@@ -11,6 +11,7 @@
 #include <map>
 #include <mutex>
 
+#include <chrono>
 #include "common.h"
 
 namespace pyg {
@@ -24,6 +25,20 @@ typedef std::tuple<std::string, std::string, std::string> edge_type;
 inline rel_type to_rel_type(const edge_type& k) {  // pyg_lib/csrc/utils/types.h:10-12
   return std::get<0>(k) + "__" + std::get<1>(k) + "__" + std::get<2>(k);
 }
+
+// Debug: host time of the homogeneous op outside the ABI run (PYGB200_HOST_TIMING=1, printed at exit)
+struct OpTimes {
+  bool on = getenv("PYGB200_HOST_TIMING") != nullptr;
+  double pre = 0, run = 0, post = 0, between = 0, last_exit = 0;
+  long calls = 0;
+  static double now() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+  ~OpTimes() {
+    if (on && calls)
+      fprintf(stderr, "[pygb200 op us/call over %ld calls] before run %.2f  run %.2f  after run %.2f  between calls (python+dispatcher) %.2f\n",
+              calls, pre / calls, run / calls, post / calls, between / (calls > 1 ? calls - 1 : 1));
+  }
+};
+static OpTimes g_ot;
 
 // one persistent workspace per (device, stream)
 pygb200_sampler* get_sampler(int device, cudaStream_t stream) {
@@ -65,6 +80,9 @@ struct CpuEngine {
   }
 };
 
+// results of at most this many worst-case bytes are written in place (views of bound-sized tensors are returned)
+constexpr int64_t kDirectOutputBytes = 64ll << 20;
+
 void check_index_tensor(const at::Tensor& t, const char* name, at::ScalarType st, const at::Device& dev) {
   TORCH_CHECK(t.is_contiguous(), "Non-contiguous '", name, "'");  // neighbor_kernel.cpp:361-363
   TORCH_CHECK(t.scalar_type() == st, "'", name, "' must have the same dtype as the seed tensor");
@@ -94,6 +112,9 @@ neighbor_sample_cuda(const at::Tensor& rowptr, const at::Tensor& col, const at::
                      const std::optional<at::Tensor>& edge_time, const std::optional<at::Tensor>& seed_time,
                      const std::optional<at::Tensor>& edge_weight, bool csc, bool replace, bool directed,
                      bool disjoint, std::string temporal_strategy, bool return_edge_id) {
+  const double ot0 = g_ot.on ? OpTimes::now() : 0;
+  double ot1 = 0, ot2 = 0;
+  if (g_ot.on && g_ot.calls) g_ot.between += ot0 - g_ot.last_exit;
   TORCH_CHECK(temporal_strategy == "uniform" || temporal_strategy == "last", "No valid temporal strategy found");
   check_arguments(node_time.has_value(), edge_time.has_value(), seed_time.has_value(), edge_weight.has_value(), disjoint);
   TORCH_CHECK(seed.is_cuda(), "pyg_lib_b200: neighbor_sample expects CUDA tensors (no CPU fallback)");
@@ -113,6 +134,9 @@ neighbor_sample_cuda(const at::Tensor& rowptr, const at::Tensor& col, const at::
                    PYGB200_S_DEFER_CLEANUP;   // export_all below resets the table in the same launch
   std::vector<int64_t> nph(L + 1, 0), eph(L, 0);
   int64_t n_nodes = 0, n_edges = 0;
+  const auto opt = seed.options();
+  at::Tensor row, colv, node;
+  std::optional<at::Tensor> eid = std::nullopt;
   {
     const int64_t* nt = node_time.has_value() ? time_ptr(*node_time, "node_time", seed.device()) : nullptr;
     const int64_t* et = edge_time.has_value() ? time_ptr(*edge_time, "edge_time", seed.device()) : nullptr;
@@ -123,21 +147,43 @@ neighbor_sample_cuda(const at::Tensor& rowptr, const at::Tensor& col, const at::
     pygb200_relation rel{rowptr.data_ptr(), col.data_ptr(), rowptr.numel() - 1, col.numel(), 0, 0};
     const void* seeds[1] = {seed.data_ptr()};
     const int64_t n_seed = seed.numel();
+    // Latency path: result tensors sized by the static bounds and written by the sampling kernels themselves
+    // (no export launch, no second host round trip); the caller gets views of their first n entries.
+    int64_t ncap = 0, ecap = 0;
+    if (!idx32 && !disjoint && L > 0 &&
+        pygb200_sampler_bounds(1, 1, L, &rel, &n_seed, num_neighbors.data(), &ncap, &ecap) == PYGB200_OK && ecap > 0 &&
+        (3 * ecap + ncap) * 8 <= kDirectOutputBytes) {
+      row = at::empty({ecap}, opt); colv = at::empty({ecap}, opt); node = at::empty({ncap}, opt);
+      if (return_edge_id) eid = at::empty({ecap}, opt);
+      void* rp = row.data_ptr(); void* cp = colv.data_ptr(); void* np = node.data_ptr();
+      void* ep = return_edge_id ? eid->data_ptr() : nullptr;
+      PYGB_TORCH_CALL(pygb200_sampler_bind_outputs(s, 1, 1, &rp, &cp, &ep, &np, &ecap, &ncap));
+    }
     CpuEngine eng;
+    if (g_ot.on) ot1 = OpTimes::now();
     PYGB_TORCH_CALL(pygb200_sampler_run_temporal(s, 1, 1, L, &rel, seeds, &n_seed, num_neighbors.data(), flags, &eng.mt,
                                                  nph.data(), eph.data(), &n_nodes, &n_edges, stream,
                                                  (nt || et) ? &tmp : nullptr));
+    if (g_ot.on) ot2 = OpTimes::now();
     eng.commit();
   }
   TORCH_CHECK(directed, "Undirected subgraphs not yet supported");  // raised after sampling, neighbor_kernel.cpp:501
-  const auto opt = seed.options();
-  at::Tensor row = at::empty({n_edges}, opt), colv = at::empty({n_edges}, opt);
-  at::Tensor node = disjoint ? at::empty({n_nodes, 2}, opt) : at::empty({n_nodes}, opt);
-  std::optional<at::Tensor> eid = std::nullopt;
-  if (return_edge_id) eid = at::empty({n_edges}, opt);
-  PYGB_TORCH_CALL(pygb200_sampler_export_all(s, 0, row.data_ptr(), colv.data_ptr(), return_edge_id ? eid->data_ptr() : nullptr, 0,
-                                             node.data_ptr(), idx32, stream));
+  if (pygb200_sampler_outputs_direct(s)) {
+    row = row.narrow(0, 0, n_edges); colv = colv.narrow(0, 0, n_edges); node = node.narrow(0, 0, n_nodes);
+    if (return_edge_id) eid = eid->narrow(0, 0, n_edges);
+  } else {
+    row = at::empty({n_edges}, opt); colv = at::empty({n_edges}, opt);
+    node = disjoint ? at::empty({n_nodes, 2}, opt) : at::empty({n_nodes}, opt);
+    eid = std::nullopt;
+    if (return_edge_id) eid = at::empty({n_edges}, opt);
+    PYGB_TORCH_CALL(pygb200_sampler_export_all(s, 0, row.data_ptr(), colv.data_ptr(), return_edge_id ? eid->data_ptr() : nullptr, 0,
+                                               node.data_ptr(), idx32, stream));
+  }
   if (csc) std::swap(row, colv);  // neighbor_kernel.cpp:155-159
+  if (g_ot.on) {
+    const double t = OpTimes::now();
+    g_ot.pre += ot1 - ot0; g_ot.run += ot2 - ot1; g_ot.post += t - ot2; g_ot.last_exit = t; g_ot.calls += 1;
+  }
   return std::make_tuple(row, colv, node, eid, nph, eph);
 }
 

@@ -203,6 +203,82 @@ def test_c_abi_direct(lib):
     abi.pygb200_sampler_destroy(h)
 
 
+def test_c_abi_bound_outputs(lib):
+    """pygb200_sampler_bounds + pygb200_sampler_bind_outputs: the run writes its results into caller-owned arrays
+    (no export); the binding is one-shot and exports are refused after a direct run."""
+    abi = C.CDLL(osp.join(osp.dirname(lib.__file__), 'libpyg_b200.so'))
+    abi.pygb200_last_error.restype = C.c_char_p
+
+    class MT(C.Structure):
+        _fields_ = [('state', C.c_uint32 * 624), ('left', C.c_int32), ('next', C.c_int32)]
+
+    class REL(C.Structure):
+        _fields_ = [('rowptr', C.c_void_p), ('col', C.c_void_p), ('num_src_nodes', C.c_int64), ('num_edges', C.c_int64),
+                    ('src_type', C.c_int32), ('dst_type', C.c_int32)]
+
+    case = HOMO_CASES['rand_15_10']
+    rowptr, col, seed = build_homo(case)
+    d = [t.to(DEV) for t in (rowptr, col, seed)]
+    omt = O.mt_seed(case['rng_seed'])
+    exp = O.neighbor_sample(rowptr, col, seed, case['num_neighbors'], mt=omt)
+    mt = MT()
+    src = O.mt_seed(case['rng_seed'])
+    C.memmove(C.byref(mt), C.byref(src), C.sizeof(MT))
+    h = C.c_void_p()
+    assert abi.pygb200_sampler_create(C.byref(h)) == 0, abi.pygb200_last_error()
+    rel = REL(d[0].data_ptr(), d[1].data_ptr(), rowptr.numel() - 1, col.numel(), 0, 0)
+    nn = (C.c_int64 * 2)(*case['num_neighbors'])
+    n_seed = C.c_int64(seed.numel())
+    ncap, ecap = C.c_int64(), C.c_int64()
+    assert abi.pygb200_sampler_bounds(1, 1, 2, C.byref(rel), C.byref(n_seed), nn, C.byref(ncap), C.byref(ecap)) == 0
+    k0, k1 = case['num_neighbors']
+    assert ecap.value == seed.numel() * k0 * (1 + k1) and ncap.value == seed.numel() + ecap.value
+    assert len(exp[0]) <= ecap.value and len(exp[2]) <= ncap.value
+    nn_bad = (C.c_int64 * 2)(5, -1)
+    assert abi.pygb200_sampler_bounds(1, 1, 2, C.byref(rel), C.byref(n_seed), nn_bad, C.byref(ncap), C.byref(ecap)) != 0
+    assert abi.pygb200_sampler_bounds(1, 1, 2, C.byref(rel), C.byref(n_seed), nn, C.byref(ncap), C.byref(ecap)) == 0
+    row = torch.full((ecap.value,), -7, dtype=torch.int64, device=DEV)
+    colv, eid = row.clone(), row.clone()
+    node = torch.full((ncap.value,), -7, dtype=torch.int64, device=DEV)
+    ptr = lambda t: (C.c_void_p * 1)(t.data_ptr())
+    assert abi.pygb200_sampler_bind_outputs(h, 1, 1, ptr(row), ptr(colv), ptr(eid), ptr(node), C.byref(ecap), C.byref(ncap)) == 0
+    nph, eph = (C.c_int64 * 3)(), (C.c_int64 * 2)()
+    n_nodes, n_edges = C.c_int64(), C.c_int64()
+    seeds = (C.c_void_p * 1)(d[2].data_ptr())
+    torch.cuda.synchronize()
+    rc = abi.pygb200_sampler_run(h, 1, 1, 2, C.byref(rel), seeds, C.byref(n_seed), nn, 0, C.byref(mt), nph, eph,
+                                 C.byref(n_nodes), C.byref(n_edges), None)
+    assert rc == 0, abi.pygb200_last_error()
+    assert abi.pygb200_sampler_outputs_direct(h) == 1
+    torch.cuda.synchronize()
+    ne, nv = n_edges.value, n_nodes.value
+    assert list(nph) == exp[4] and list(eph) == exp[5]
+    assert torch.equal(row[:ne].cpu(), exp[0]) and torch.equal(colv[:ne].cpu(), exp[1])
+    assert torch.equal(node[:nv].cpu(), exp[2]) and torch.equal(eid[:ne].cpu(), exp[3])
+    assert (row[ne:] == -7).all() and (node[nv:] == -7).all()          # nothing written past the results
+    assert (np.ctypeslib.as_array(mt.state) == np.ctypeslib.as_array(omt.state)).all()
+    tmp = torch.empty(max(ne, 1), dtype=torch.int64, device=DEV)
+    assert abi.pygb200_sampler_export_edges(h, 0, C.c_void_p(tmp.data_ptr()), C.c_void_p(tmp.data_ptr()), None, 0, None) != 0
+    # one-shot: the next run (same engine state continues the stream) goes back to its own buffers + export
+    exp2 = O.neighbor_sample(rowptr, col, seed, case['num_neighbors'], mt=omt)
+    rc = abi.pygb200_sampler_run(h, 1, 1, 2, C.byref(rel), seeds, C.byref(n_seed), nn, 0, C.byref(mt), nph, eph,
+                                 C.byref(n_nodes), C.byref(n_edges), None)
+    assert rc == 0 and abi.pygb200_sampler_outputs_direct(h) == 0
+    r2 = torch.empty(n_edges.value, dtype=torch.int64, device=DEV)
+    c2, e2 = torch.empty_like(r2), torch.empty_like(r2)
+    assert abi.pygb200_sampler_export_edges(h, 0, C.c_void_p(r2.data_ptr()), C.c_void_p(c2.data_ptr()),
+                                            C.c_void_p(e2.data_ptr()), 0, None) == 0
+    torch.cuda.synchronize()
+    assert torch.equal(r2.cpu(), exp2[0]) and torch.equal(c2.cpu(), exp2[1]) and torch.equal(e2.cpu(), exp2[3])
+    # too small a binding is ignored (falls back to export), never overrun
+    small = C.c_int64(8)
+    assert abi.pygb200_sampler_bind_outputs(h, 1, 1, ptr(row), ptr(colv), ptr(eid), ptr(node), C.byref(small), C.byref(ncap)) == 0
+    rc = abi.pygb200_sampler_run(h, 1, 1, 2, C.byref(rel), seeds, C.byref(n_seed), nn, 0, C.byref(mt), nph, eph,
+                                 C.byref(n_nodes), C.byref(n_edges), None)
+    assert rc == 0 and abi.pygb200_sampler_outputs_direct(h) == 0
+    abi.pygb200_sampler_destroy(h)
+
+
 def test_rng_stream_persistence_and_restart(lib):
     """The device keeps the mt19937 stream between calls.  Interleave calls with foreign draws from the
     CPU generator (forces a restart from the new engine state)."""
