@@ -439,6 +439,9 @@ __global__ void __launch_bounds__(NT) k_count(const PassArgs a) {
 }
 
 // One group of G lanes per frontier node.
+#ifndef SAMPLE_MIN_BLOCKS
+#define SAMPLE_MIN_BLOCKS 4   // resident CTAs per SM the register allocation aims for
+#endif
 template <typename idx_t, int G>
 __global__ void __launch_bounds__(NT, SAMPLE_MIN_BLOCKS) k_sample(const PassArgs a) {
   pdl_enter(TL_SAMPLE);
@@ -458,7 +461,9 @@ __global__ void __launch_bounds__(NT, SAMPLE_MIN_BLOCKS) k_sample(const PassArgs
     const i64 tile = i / NT;
     const i64 tpos = a.tile_pos[tile];
     const i64 off = a.tile_off[tile] + r.loc_off;    // pass-local flat position of the node's first edge
-    const i64 pos0 = tpos + r.pf[tpos & 3];           // RNG position (16-bit units) of its first draw
+    const int ph = (int)(tpos & 3);
+    const u32 pfv = ph == 0 ? r.pf[0] : (ph == 1 ? r.pf[1] : (ph == 2 ? r.pf[2] : r.pf[3]));
+    const i64 pos0 = tpos + pfv;                      // RNG position (16-bit units) of its first draw
     const i64 deg = r.deg, rs = r.rs, k = a.fanout;
     const i64 src_pos = begin + i;                    // == local id of the source node (neighbor_kernel.cpp:453)
     const i64 sbatch = a.disjoint ? a.src_batch[src_pos] : 0;
@@ -819,29 +824,43 @@ __global__ void k_seed_end(i64* st, int t, int L, int o_list, int o_begin, int o
 // Last kernel of a run: deferred lookup of the last pass + (block 0) final engine state = the
 // generation holding the last consumed output (see mt19937.cuh); at least one 128-word block is
 // always consumed (rand_engine.h:28).
-__global__ void __launch_bounds__(NT) k_final(const PassArgs a, int o_mt, i64* host_st, int n_words, i64 serial) {
+__global__ void __launch_bounds__(NT) k_final(const PassArgs a, int o_mt, i64* host_st, int n_words, i64 serial, i64* zero_st) {
   __shared__ u32 s_win[MT_WIN];
   pdl_enter(TL_FINAL);
   deferred_lookup(a);
   if (blockIdx.x != 0) return;
+  // The counters + engine state go straight into mapped host memory; the host polls the flag word (no DMA copy,
+  // no event round trip).  Other blocks may still be doing the deferred lookup — the host only needs the
+  // counters, everything else it does is stream-ordered behind this kernel.
+  // Counters first: these loads overlap the cursor -> stream -> engine-state chain below.
+  if (host_st) {
+    for (int i = threadIdx.x; i < n_words; i += blockDim.x)
+      if ((i < o_mt || i >= o_mt + MT_N / 2) && (i < ST_ERROR || i > ST_BLOCKS)) host_st[i] = a.st[i];
+  }
+  // the state buffer is double-buffered: the half the NEXT run uses is cleared here (nobody reads it any more)
+  if (zero_st) for (int i = threadIdx.x; i < n_words; i += blockDim.x) zero_st[i] = 0;
   const i64 blocks = rng_blocks_for_units(a.st[ST_CURSOR]);
   const i64 q = a.out0 + 256 * blocks;
   mt_extend_block<3>(a.raw, a.gen, q, a.raw_cap, a.st, s_win);
   const i64 g = (q - 1) / MT_N;
   u32* out = reinterpret_cast<u32*>(a.st + o_mt);
-  for (int i = threadIdx.x; i < MT_N; i += blockDim.x) out[i] = __ldcg(&a.raw[g * MT_N + i]);
+  u32* hout = host_st ? reinterpret_cast<u32*>(host_st + o_mt) : nullptr;
+  for (int i = threadIdx.x; i < MT_N; i += blockDim.x) {
+    const u32 w = __ldcg(&a.raw[g * MT_N + i]);
+    out[i] = w;
+    if (hout) hout[i] = w;
+  }
   if (threadIdx.x == 0) {
     const i64 nxt = q - g * MT_N;
     a.st[ST_MT_NEXT] = nxt;
     a.st[ST_MT_LEFT] = 625 - nxt;
     a.st[ST_BLOCKS] = blocks;
+    if (host_st) {
+      host_st[ST_MT_NEXT] = nxt; host_st[ST_MT_LEFT] = 625 - nxt; host_st[ST_BLOCKS] = blocks;
+      host_st[ST_ERROR] = a.st[ST_ERROR];   // (mt_extend_block may have raised it)
+    }
   }
-  // publish the counters + engine state straight into mapped host memory; the host polls the flag word
-  // (no DMA copy, no event round trip).  Other blocks may still be doing the deferred lookup — the host
-  // only needs the counters, everything else it does is stream-ordered behind this kernel.
-  __syncthreads();
   if (host_st) {
-    for (int i = threadIdx.x; i < n_words; i += blockDim.x) host_st[i] = a.st[i];
     __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) { *reinterpret_cast<volatile i64*>(host_st + n_words) = serial; __threadfence_system(); }
@@ -1113,10 +1132,15 @@ struct pygb200_sampler {
   cudaStream_t mt_stream = nullptr;
   // the last two pre-generation launches (side stream, in launch order): event + raw index they cover
   cudaEvent_t mt_ev[2] = {nullptr, nullptr};
+  cudaEvent_t mt_order_ev = nullptr;   // main stream -> side stream ordering after an in-run extension
   i64 mt_ev_target[2] = {0, 0};
   bool mt_ev_pending[2] = {false, false};
   int mt_ev_next = 0;
   size_t st_words = 0;
+  size_t st_dev_words = 0;  // layout size the device state halves were cleared for (0 = both halves need a memset)
+  int st_cur = 0;           // half of `st` the last run used (k_final clears the other one for the next run)
+  i64* st_last = nullptr;   // device state of the last run
+  i64 mt_defer_target = 0;  // pre-generation decided at the end of the last run, launched inside the next one
   bool disjoint = false;
   bool dirty = false;       // a run failed mid-way: tables must be wiped before reuse
   int T = 0, R = 0, L = 0;
@@ -1128,11 +1152,15 @@ struct HostTimes {
   bool on = getenv("PYGB200_HOST_TIMING") != nullptr;
   double acc[6] = {0, 0, 0, 0, 0, 0};
   long runs = 0;
+  long branch[5] = {0, 0, 0, 0, 0};   // stream coverage at run start: known / older event / newer event / extend here / restart
   static double now() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
   ~HostTimes() {
     if (on && runs)
       fprintf(stderr, "[pygb200 host us/run over %ld runs] setup %.2f  mt+memset %.2f  seeds %.2f  hops+final %.2f  spin %.2f  post %.2f\n",
               runs, acc[0] / runs, acc[1] / runs, acc[2] / runs, acc[3] / runs, acc[4] / runs, acc[5] / runs);
+    if (on && runs)
+      fprintf(stderr, "[pygb200 mt19937 stream at run start] covered %ld  older event %ld  newer event %ld  extended here %ld  restarted %ld\n",
+              branch[0], branch[1], branch[2], branch[3], branch[4]);
   }
 };
 static HostTimes g_ht;
@@ -1193,6 +1221,7 @@ extern "C" void pygb200_sampler_destroy(pygb200_sampler* s) {
   for (auto& r : s->rels) { r.row.release(); r.colv.release(); r.eid.release(); }
   if (s->mt_stream) { cudaStreamSynchronize(s->mt_stream); cudaStreamDestroy(s->mt_stream); }
   for (int i = 0; i < 2; ++i) if (s->mt_ev[i]) cudaEventDestroy(s->mt_ev[i]);
+  if (s->mt_order_ev) cudaEventDestroy(s->mt_order_ev);
   DevBuf* all[] = {&s->eslot, &s->erank, &s->rec, &s->tile_out, &s->tile_func,
                    &s->tile_off, &s->tile_pos, &s->mtile, &s->raw, &s->st, &s->gen, &s->jump_polys, &s->jump_scratch, &s->seed_times};
   for (auto* b : all) b->release();
@@ -1501,7 +1530,7 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
   if (s->cleanup_pending && !s->types.empty() && s->types[0].tcap) {   // nobody exported the previous run: reset its table now
     auto& tb = s->types[0];
     launch_pdl(k_cleanup, grid_for((i64)(tb.slot.cap / 4), NT, s->sm_count), NT, st, tb.keys.as<u64>(), tb.vals.as<u64>(),
-               (const u32*)tb.slot.as<u32>(), (const i64*)(s->st.as<i64>() + s->st_o_list));
+               (const u32*)tb.slot.as<u32>(), (const i64*)(s->st_last + s->st_o_list));
     PYGB_LAUNCH_CHECK();
     s->cleanup_pending = false;
   }
@@ -1517,11 +1546,12 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
     memset(s->st_host, 0, (lay.words + 8) * 8);
     s->st_words = lay.words;
   }
-  if (int e = s->st.ensure(lay.words * 8, 0, st)) return e;
+  if (int e = s->st.ensure(2 * lay.words * 8, 0, st)) return e;
   if (int e = s->gen.ensure(64, 0, st)) return e;
   if (!s->mt_stream) {
     PYGB_CUDA(cudaStreamCreateWithFlags(&s->mt_stream, cudaStreamNonBlocking));
     for (int i = 0; i < 2; ++i) PYGB_CUDA(cudaEventCreateWithFlags(&s->mt_ev[i], cudaEventDisableTiming));
+    PYGB_CUDA(cudaEventCreateWithFlags(&s->mt_order_ev, cudaEventDisableTiming));
   }
   if (s->dirty) {  // previous run aborted: wipe tables, forget the stream
     for (auto& tb : s->types) if (tb.tcap) {
@@ -1529,6 +1559,7 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
       PYGB_CUDA(cudaMemsetAsync(tb.vals.p, 0xff, tb.tcap * 8, st));
     }
     s->mt_valid = false;
+    s->st_dev_words = 0;
   }
   s->dirty = true;
   if (!synced) {
@@ -1570,6 +1601,7 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
     if (int e = wait_all_pregen()) return e;
     s->mt_gen_known = 0;
   }
+  if (!cont || synced) s->mt_defer_target = 0;
   if (cont) {
     out0 = s->mt_q;
     const i64 need = out0 + run_outputs + MT_N;
@@ -1577,22 +1609,30 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
     const int older = s->mt_ev_next, newer = s->mt_ev_next ^ 1;
     if (s->mt_gen_known >= need) {
       // covered by a launch this stream has already waited for; newer launches keep running beside us
+      g_ht.branch[0]++;
     } else if (s->mt_ev_pending[older] && s->mt_ev_target[older] >= need) {
+      g_ht.branch[1]++;
       PYGB_CUDA(cudaStreamWaitEvent(st, s->mt_ev[older], 0));
       s->mt_ev_pending[older] = false;
       s->mt_gen_known = std::max(s->mt_gen_known, s->mt_ev_target[older]);
     } else if (s->mt_ev_pending[newer] && s->mt_ev_target[newer] >= need) {
+      g_ht.branch[2]++;
       // same side stream: once the newer launch is complete so is the older one
       PYGB_CUDA(cudaStreamWaitEvent(st, s->mt_ev[newer], 0));
       s->mt_ev_pending[older] = s->mt_ev_pending[newer] = false;
       s->mt_gen_known = std::max(s->mt_gen_known, s->mt_ev_target[newer]);
     } else {
       // not covered ahead of time (first continued run, or a run larger than the previous one): extend here
+      g_ht.branch[3]++;
       if (int e = wait_all_pregen()) return e;
       if (int e = mt_request(s, st, need)) return e;
       s->mt_gen_known = need;
+      // the side stream continues from here: order its next launch behind this one
+      PYGB_CUDA(cudaEventRecord(s->mt_order_ev, st));
+      PYGB_CUDA(cudaStreamWaitEvent(s->mt_stream, s->mt_order_ev, 0));
     }
   } else {
+    g_ht.branch[4]++;
     if (int e = wait_all_pregen()) return e;
     static const i64 pref_cap = [] { const char* e = getenv("PYGB200_MT_CAP_WORDS"); return e ? (i64)atoll(e) : (i64)1 << 23; }();
     load_jump_table(s, st);
@@ -1616,9 +1656,17 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
   s->mt_valid = false;  // until this run completes
   i64 raw_cap = s->raw_cap_words;
 
-  // ---- init: zero state
-  i64* dst = s->st.as<i64>();
-  PYGB_CUDA(cudaMemsetAsync(dst, 0, lay.words * 8, st));
+  // ---- init: zero state.  Two halves: the previous run's k_final already cleared the one this run uses.
+  if (s->st_dev_words != lay.words) {
+    PYGB_CUDA(cudaMemsetAsync(s->st.p, 0, 2 * lay.words * 8, st));
+    s->st_dev_words = lay.words;
+    s->st_cur = 0;
+  } else {
+    s->st_cur ^= 1;
+  }
+  i64* dst = s->st.as<i64>() + (size_t)s->st_cur * lay.words;
+  i64* dst_other = s->st.as<i64>() + (size_t)(s->st_cur ^ 1) * lay.words;
+  s->st_last = dst;
   auto make_args = [&](int src_t, int dst_t, int rel) {
     PassArgs a;
     memset(&a, 0, sizeof(a));
@@ -1829,7 +1877,7 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
     a.lk_colv = lk_colv; a.lk_vals = lk_vals;
     s->run_serial += 1;
     launch_pdl(k_final, lk_colv ? grid_for(lk_E, NT, s->sm_count) : 1, NT, st, a, lay.o_mt, s->st_host_dev, (int)lay.words,
-               s->run_serial);
+               s->run_serial, dst_other);
     PYGB_LAUNCH_CHECK();
   }
   // table cleanup is stream-ordered after k_final; the host does not wait for it.  With
@@ -1842,6 +1890,18 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
     launch_pdl(k_cleanup, grid_for(synced ? cap_nodes : node_cap[t], NT, s->sm_count), NT, st, tb.keys.as<u64>(), tb.vals.as<u64>(),
                (const u32*)tb.slot.as<u32>(), (const i64*)(dst + lay.o_list + t));
     PYGB_LAUNCH_CHECK();
+  }
+  // pre-generation for the run after this one (decided when the previous run ended): launched now, on the side
+  // stream, while the GPU is busy with this run and the host has nothing to do but wait
+  if (s->mt_defer_target > 0) {
+    const int slot = s->mt_ev_next;
+    if (!s->mt_ev_pending[slot] && mt_request(s, s->mt_stream, s->mt_defer_target) == PYGB200_OK &&
+        cudaEventRecord(s->mt_ev[slot], s->mt_stream) == cudaSuccess) {
+      s->mt_ev_pending[slot] = true;
+      s->mt_ev_target[slot] = s->mt_defer_target;
+      s->mt_ev_next = slot ^ 1;
+    }
+    s->mt_defer_target = 0;
   }
   ht_lap(3);
   {  // wait for k_final's flag (spin on mapped memory; keep an eye on the stream in case the run died)
@@ -1887,16 +1947,9 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
   s->mt_valid = true;
   if (!synced) {
     const i64 target = std::min<i64>(s->raw_cap_words - 2 * MT_N, s->mt_q + 2 * run_outputs + 2 * MT_N);
-    const int slot = s->mt_ev_next;
-    if (target > s->mt_q && !s->mt_ev_pending[slot]) {
-      // this run's kernels (which may extend the stream themselves) are done: the D2H copy we just waited
-      // for is ordered after k_final
-      if (mt_request(s, s->mt_stream, target) == PYGB200_OK && cudaEventRecord(s->mt_ev[slot], s->mt_stream) == cudaSuccess) {
-        s->mt_ev_pending[slot] = true;
-        s->mt_ev_target[slot] = target;
-        s->mt_ev_next = slot ^ 1;
-      }
-    }
+    // this run's kernels (which may extend the stream themselves) are done; the launch itself is left to the
+    // next run (see above) so that it costs no host time between two runs
+    s->mt_defer_target = target > s->mt_q ? target : 0;
   }
   ht_lap(5);
   if (g_ht.on) g_ht.runs += 1;

@@ -11,6 +11,21 @@ RelType = str
 EdgeType = Tuple[str, str, str]
 
 
+class _LazyOp:
+    """`torch.ops.pyg.<name>.default` resolved on first use (the library is loaded by the package import) and
+    called directly afterwards: skips the per-call namespace lookup and overload resolution."""
+    def __init__(self, name):
+        self.name, self.op = name, None
+
+    def __call__(self, *args):
+        if self.op is None:
+            self.op = getattr(torch.ops.pyg, self.name).default
+        return self.op(*args)
+
+
+_neighbor_sample_op = _LazyOp('neighbor_sample')
+
+
 def neighbor_sample(
     rowptr: Tensor,
     col: Tensor,
@@ -33,9 +48,8 @@ def neighbor_sample(
 
     Temporal (`node_time`/`edge_time`/`seed_time`) and biased (`edge_weight`) sampling raise: they are
     not implemented on the B200 path and there is no CPU fallback."""
-    return torch.ops.pyg.neighbor_sample(rowptr, col, seed, num_neighbors, node_time, edge_time, seed_time,
-                                         edge_weight, csc, replace, directed, disjoint, temporal_strategy,
-                                         return_edge_id)
+    return _neighbor_sample_op(rowptr, col, seed, num_neighbors, node_time, edge_time, seed_time, edge_weight, csc,
+                               replace, directed, disjoint, temporal_strategy, return_edge_id)
 
 
 def hetero_neighbor_sample(
