@@ -139,6 +139,15 @@ __device__ void mt_gen_range(u32* __restrict__ raw, i64 hist_lo, i64 m, i64 targ
   }
 }
 
+// Publication of a new stream length by the block that generated it: the length only ever grows (a main-stream
+// kernel and the side stream may extend the same stream concurrently — they write identical words) and a
+// reader that polls it (k_sample_s) must find the words behind it.
+__device__ __forceinline__ void mt_publish(i64* generated, i64 m) {
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) atomicMax(reinterpret_cast<unsigned long long*>(generated), (unsigned long long)m);
+}
+
 // Extends raw[] up to (at least) raw index `target`, rounded up to a whole 624-word generation.
 template <int KL>
 __global__ void __launch_bounds__(640) k_mt_extend_to(u32* __restrict__ raw, i64* generated, i64 target_in, i64 cap_words) {
@@ -148,7 +157,7 @@ __global__ void __launch_bounds__(640) k_mt_extend_to(u32* __restrict__ raw, i64
   const i64 m = *generated;
   if (target <= m) return;
   mt_gen_range<KL>(raw, 0, m, target, win);
-  if (threadIdx.x == 0) *generated = target;
+  mt_publish(generated, target);
 }
 
 // ---- parallel generation by jump-ahead (tools/mt19937_jump.py builds the polynomial table) -------------
@@ -168,7 +177,7 @@ __global__ void __launch_bounds__(640) k_mt_jump_prestep(u32* __restrict__ raw, 
   if (threadIdx.x == 0) *jump_base = m;
   if (target <= m) return;
   mt_gen_range<KL>(raw, 0, m, target, win);
-  if (threadIdx.x == 0) *generated = target;
+  mt_publish(generated, target);
 }
 
 // CTA p generates raw[b0 + p*S + 624 .. b0 + (p+1)*S + 624), b0 = jump_base - 624 (CTA 0 continues after the
@@ -221,7 +230,7 @@ __global__ void __launch_bounds__(640) k_mt_jump_generate(u32* __restrict__ raw,
   __syncthreads();
   if (s_last && threadIdx.x == 0) {
     __threadfence();
-    if (end_all > *generated) *generated = end_all;
+    atomicMax(reinterpret_cast<unsigned long long*>(generated), (unsigned long long)end_all);
   }
 }
 

@@ -133,10 +133,21 @@ struct PassArgs {
   // frontier sharding (multi-GPU): phase 0 = normal; 1 = draw only, frontier nodes [shard_lo, shard_hi),
   // writes edge ids; 2 = expand ALL nodes from the (all-gathered) edge ids: gather col, rows, hash insert
   int phase; i64 shard_lo, shard_hi;
+  int group;       // k_sample: lanes per frontier node (sample_group_lanes)
   // temporal sampling (neighbor_kernel.cpp:74-144): time_mode 1 = node time of the neighbour (time[col[e]]),
   // 2 = edge time (time[e]); seed_times indexed by the frontier node's batch id; time_last = strategy 'last'
   const i64* time; const i64* seed_times; int time_mode, time_last;
+  // Latency path (k_*_s kernels): the counters of a run are WRITE-ONCE words of `st` whose indices the host
+  // fixes from its static pass schedule, so no kernel updates a word another block of the same launch reads and
+  // no pass needs a serial "last block" section.  A value is st[w_x] when w_x >= 0, else the constant c_x.
+  int ssa;
+  int w_begin, w_end, w_list_in, w_pbase, w_cur_in;      // frontier slice, dst list length, relation offset, RNG cursor
+  i64 c_begin, c_end, c_list_in;                          // (pbase / cursor constants are 0)
+  int w_E, w_cur_out, w_relcum_out, w_list_out;          // written by this pass (block 0 of k_sample_s / k_assign_s)
+  int w_seed_list, w_seed_ids;                            // dst type: seeds listed / distinct seeds (ids = list - dups)
+  int lk_w_E, lk_w_pbase;                                 // previous pass (deferred lookup)
 };
+__device__ __forceinline__ i64 ldw(const i64* st, int w, i64 c) { return w >= 0 ? st[w] : c; }
 
 // ------------------------------------------------------------------------------------- helpers
 // Programmatic dependent launch: the kernels of a run form a chain on one stream.  Each waits for its
@@ -252,6 +263,45 @@ __device__ __forceinline__ void block_scan_pair(u32 v, Func4 f, u32* ex_v, Func4
   __syncthreads();
 }
 
+// Ordered exclusive scan of two u32 sums over the NT threads of a block.
+__device__ __forceinline__ void block_scan_sums(u32 v, u32 u, u32* ex_v, u32* ex_u, u32* tot_v, u32* tot_u) {
+  __shared__ u32 s_a[NT / 32], s_b[NT / 32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  u32 iv = v, iu = u;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const u32 ov = __shfl_up_sync(0xffffffffu, iv, d), ou = __shfl_up_sync(0xffffffffu, iu, d);
+    if (lane >= d) { iv += ov; iu += ou; }
+  }
+  if (lane == 31) { s_a[wid] = iv; s_b[wid] = iu; }
+  __syncthreads();
+  u32 pv = 0, pu = 0, tv = 0, tu = 0;
+#pragma unroll
+  for (int w = 0; w < NT / 32; ++w) {
+    const u32 xa = s_a[w], xb = s_b[w];
+    if (w < wid) { pv += xa; pu += xb; }
+    tv += xa; tu += xb;
+  }
+  *ex_v = pv + iv - v; *ex_u = pu + iu - u;
+  *tot_v = tv; *tot_u = tu;
+  __syncthreads();
+}
+
+// block_scan_pair for advance functions that are almost always plain additions: a draw from a range below 2^16
+// takes one 16-bit unit whatever the phase, so f is uniform (d[0..3] equal) unless a node has >= 2^16 candidate
+// neighbours, and uniform functions compose by adding.  One block-wide vote picks the cheap scan.
+__device__ __forceinline__ void block_scan_nodes(u32 v, Func4 f, u32* ex_v, Func4* ex_f, u32* tot_v, Func4* tot_f) {
+  const int uni = f.d[0] == f.d[1] && f.d[1] == f.d[2] && f.d[2] == f.d[3];
+  if (__syncthreads_and(uni)) {
+    u32 eu, tu;
+    block_scan_sums(v, f.d[0], ex_v, &eu, tot_v, &tu);
+    ex_f->d[0] = ex_f->d[1] = ex_f->d[2] = ex_f->d[3] = eu;
+    tot_f->d[0] = tot_f->d[1] = tot_f->d[2] = tot_f->d[3] = tu;
+  } else {
+    block_scan_pair(v, f, ex_v, ex_f, tot_v, tot_f);
+  }
+}
+
 // Single-block ordered scan of the frontier tile aggregates: edge offsets and absolute RNG positions.
 // Runs in the last block of k_count.  blockDim.x == NT.
 __device__ void scan_frontier_tiles(const PassArgs& a, i64 ntiles) {
@@ -346,7 +396,7 @@ __device__ void mt_extend_block(u32* __restrict__ raw, i64* gen, i64 need, i64 c
     __syncthreads();
     m += n;
   }
-  if (threadIdx.x == 0) *gen = m;
+  mt_publish(gen, m);
   __syncthreads();
 }
 
@@ -370,9 +420,65 @@ __device__ __forceinline__ bool last_block(i64* ticket) {
 // local ids of the previous pass's edges (its k_assign has completed: kernel boundary)
 __device__ __forceinline__ void deferred_lookup(const PassArgs& a) {
   if (a.lk_colv == nullptr) return;
-  const i64 E = a.st[ST_PASS_E], pbase = a.st[ST_PASS_BASE];
+  const i64 E = a.ssa ? a.st[a.lk_w_E] : a.st[ST_PASS_E];
+  const i64 pbase = a.ssa ? ldw(a.st, a.lk_w_pbase, 0) : a.st[ST_PASS_BASE];
   for (i64 p = (i64)blockIdx.x * NT + threadIdx.x; p < E; p += (i64)gridDim.x * NT)
     a.lk_colv[pbase + p] = (i64)a.lk_vals[a.eslot[p]];
+}
+
+// What frontier node v (batch id `batch`, only read for temporal sampling) contributes to a pass: its (possibly
+// time-windowed) row, the number of edges it emits and its RNG advance function (neighbor_kernel.cpp:58-144).
+template <typename idx_t>
+__device__ __forceinline__ void node_degree(const PassArgs& a, i64 v, i64 batch, i64* rs_out, i64* deg_out, u32* n_out_out, Func4* f_out) {
+  const idx_t* __restrict__ rowptr = (const idx_t*)a.rowptr;
+  i64 rs = (i64)rowptr[v];
+  i64 re = (i64)rowptr[v + 1];
+  if (a.time_mode && re > rs && a.fanout != 0) {
+    // neighbours that fulfil the temporal constraint: std::upper_bound on the (time-sorted) row
+    const i64 st = a.seed_times[batch];
+    const idx_t* __restrict__ colp = (const idx_t*)a.col;
+    i64 lo = rs, hi = re;
+    while (lo < hi) {
+      const i64 mid = lo + ((hi - lo) >> 1);
+      const i64 key = a.time_mode == 1 ? a.time[(i64)colp[mid]] : a.time[mid];
+      if (st < key) hi = mid; else lo = mid + 1;
+    }
+    re = lo;
+    if (a.time_last && a.fanout >= 0 && re - a.fanout > rs) rs = re - a.fanout;
+  }
+  const i64 deg = re - rs;
+  i64 n_out, n16, n32, n64;
+  classify(deg, a.fanout, a.replace, &n_out, &n16, &n32, &n64);
+  Func4 f;
+  if (n32 == 0 && n64 == 0) {
+    f.d[0] = f.d[1] = f.d[2] = f.d[3] = (u32)n16;
+  } else {
+#pragma unroll
+    for (int p = 0; p < 4; ++p) f.d[p] = (u32)(rng_node_end(p, n16, n32, n64) - p);
+  }
+  *rs_out = rs; *deg_out = deg; *n_out_out = (u32)n_out; *f_out = f;
+}
+
+// one 256-node frontier tile: per-node records + the tile's aggregate (blockDim.x == NT)
+template <typename idx_t>
+__device__ __forceinline__ void count_tile(const PassArgs& a, i64 begin, i64 F, i64 tile) {
+  const i64 i = tile * NT + threadIdx.x;
+  i64 rs = 0, deg = 0; u32 n_out = 0;
+  Func4 f = {{0, 0, 0, 0}};
+  if (i < F) node_degree<idx_t>(a, a.src_nodes[begin + i], a.time_mode ? a.src_batch[begin + i] : 0, &rs, &deg, &n_out, &f);
+  u32 ex_v, tot_v; Func4 ex_f, tot_f;
+  block_scan_nodes(n_out, f, &ex_v, &ex_f, &tot_v, &tot_f);
+  if (i < F) {
+    NodeRec r;
+    r.rs = rs; r.deg = (u32)deg; r.loc_off = ex_v;
+    r.pf[0] = ex_f.d[0]; r.pf[1] = ex_f.d[1]; r.pf[2] = ex_f.d[2]; r.pf[3] = ex_f.d[3];
+    a.rec[i] = r;
+  }
+  if (threadIdx.x == 0) {
+    a.tile_out[tile] = tot_v;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) a.tile_func[4 * tile + p] = tot_f.d[p];
+  }
 }
 
 template <typename idx_t>
@@ -383,51 +489,7 @@ __global__ void __launch_bounds__(NT) k_count(const PassArgs a) {
   const i64 begin = a.st[a.o_src_begin], end = a.st[a.o_src_end];
   const i64 F = end - begin;
   const i64 ntiles = ceil_div(F, NT);
-  const idx_t* __restrict__ rowptr = (const idx_t*)a.rowptr;
-  for (i64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const i64 i = tile * NT + threadIdx.x;
-    i64 rs = 0, deg = 0, n_out = 0, n16 = 0, n32 = 0, n64 = 0;
-    Func4 f = {{0, 0, 0, 0}};
-    if (i < F) {
-      const i64 v = a.src_nodes[begin + i];
-      rs = (i64)rowptr[v];
-      i64 re = (i64)rowptr[v + 1];
-      if (a.time_mode && re > rs && a.fanout != 0) {
-        // neighbours that fulfil the temporal constraint: std::upper_bound on the (time-sorted) row
-        const i64 st = a.seed_times[a.src_batch[begin + i]];
-        const idx_t* __restrict__ colp = (const idx_t*)a.col;
-        i64 lo = rs, hi = re;
-        while (lo < hi) {
-          const i64 mid = lo + ((hi - lo) >> 1);
-          const i64 key = a.time_mode == 1 ? a.time[(i64)colp[mid]] : a.time[mid];
-          if (st < key) hi = mid; else lo = mid + 1;
-        }
-        re = lo;
-        if (a.time_last && a.fanout >= 0 && re - a.fanout > rs) rs = re - a.fanout;
-      }
-      deg = re - rs;
-      classify(deg, a.fanout, a.replace, &n_out, &n16, &n32, &n64);
-      if (n32 == 0 && n64 == 0) {
-        f.d[0] = f.d[1] = f.d[2] = f.d[3] = (u32)n16;
-      } else {
-#pragma unroll
-        for (int p = 0; p < 4; ++p) f.d[p] = (u32)(rng_node_end(p, n16, n32, n64) - p);
-      }
-    }
-    u32 ex_v, tot_v; Func4 ex_f, tot_f;
-    block_scan_pair((u32)n_out, f, &ex_v, &ex_f, &tot_v, &tot_f);
-    if (i < F) {
-      NodeRec r;
-      r.rs = rs; r.deg = (u32)deg; r.loc_off = ex_v;
-      r.pf[0] = ex_f.d[0]; r.pf[1] = ex_f.d[1]; r.pf[2] = ex_f.d[2]; r.pf[3] = ex_f.d[3];
-      a.rec[i] = r;
-    }
-    if (threadIdx.x == 0) {
-      a.tile_out[tile] = tot_v;
-#pragma unroll
-      for (int p = 0; p < 4; ++p) a.tile_func[4 * tile + p] = tot_f.d[p];
-    }
-  }
+  for (i64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) count_tile<idx_t>(a, begin, F, tile);
   tl_mark(TL_COUNT | TL_END);
   if (last_block(&a.st[ST_TICKET_A])) {
     tl_mark_any(TL_COUNT | TL_LAST);
@@ -438,82 +500,108 @@ __global__ void __launch_bounds__(NT) k_count(const PassArgs a) {
   }
 }
 
-// One group of G lanes per frontier node.
+// Sampling of ONE frontier node by a group of `g` consecutive lanes of a warp (g = min(fan-out, 32): a warp
+// takes 32 / g nodes, so a fan-out of 10 keeps 30 of its 32 lanes busy).  `r` = the node's record, `off` =
+// pass-local flat position of its first edge, `pos0` = RNG position (16-bit units) of its first draw, `gl` = lane
+// within the group, `gbase` = the group's first lane, `gmask` = its lanes.
+// Robert Floyd's algorithm (neighbor_kernel.cpp:231-241) is sequential in the draws — draw j falls back to lo + j
+// when its random value was already CHOSEN by an earlier draw — but only through the chosen values: every lane
+// takes one draw and the conflicts are settled with g shuffles.  Fan-outs beyond 32 go in rounds of 32 and
+// re-read what earlier rounds emitted.
+template <typename idx_t>
+__device__ __forceinline__ void sample_node(const PassArgs& a, const NodeRec& r, i64 off, i64 pos0, i64 src_pos, i64 pbase,
+                                            int g, int gl, int gbase, unsigned gmask) {
+  const idx_t* __restrict__ col = (const idx_t*)a.col;
+  const u32* __restrict__ raw = a.raw;
+  const i64 out0 = a.out0;
+  const i64 deg = r.deg, rs = r.rs, k = a.fanout;
+  const i64 sbatch = a.disjoint ? a.src_batch[src_pos] : 0;
+  i64 n_out, n16, n32, n64;
+  const int mode = classify(deg, k, a.replace, &n_out, &n16, &n32, &n64);
+  auto emit = [&](i64 j, i64 e) {
+    const i64 p = off + j;
+    if (a.phase == 1) { a.eid[pbase + p] = e; return; }
+    const i64 d = (i64)col[e];
+    a.row[pbase + p] = src_pos;
+    a.eid[pbase + p] = e;
+    a.colv[pbase + p] = d;  // global id for now; the (deferred) lookup overwrites it with the local id
+    const u32 s = table_insert(a.keys, a.mask, make_key(d, sbatch, a.disjoint));
+    atomicMin(&a.vals[s], POS_BASE + (u64)p);
+    a.eslot[p] = s;
+  };
+  if (a.phase == 2) {
+    for (i64 j = gl; j < n_out; j += g) emit(j, a.eid[pbase + off + j]);
+  } else if (mode == MODE_FULL) {
+    for (i64 j = gl; j < deg; j += g) emit(j, rs + j);
+  } else if (mode == MODE_REPLACE) {
+    const int wu = rng_width_units((u64)deg);
+    for (i64 j = gl; j < k; j += g) {
+      const i64 pos = (wu == 1) ? pos0 + j : rng_align(rng_run(pos0, wu, j), wu);
+      emit(j, rs + (i64)rng_draw(raw, out0, pos, wu, (u64)deg));
+    }
+  } else if (mode == MODE_FLOYD) {
+    const i64 lo = deg - k;  // draw j: range lo+1+j, fallback value lo+j
+    for (i64 c0 = 0; c0 < k; c0 += g) {
+      const i64 j = c0 + gl;
+      const bool act = j < k;
+      i64 rnd = -1, c = -1;
+      if (act) {
+        int wu;
+        const i64 pos = (n32 == 0 && n64 == 0) ? (wu = 1, pos0 + j) : rng_draw_start(pos0, n16, n32, j, &wu);
+        rnd = (i64)rng_draw(raw, out0, pos, wu, (u64)(lo + 1 + j));
+        c = rnd;
+        // already chosen in an earlier round of this node? (only when fanout > 32)
+        for (i64 t = 0; t < c0; ++t)
+          if (__ldcg(&a.eid[pbase + off + t]) - rs == rnd) { c = lo + j; break; }
+      }
+      const int lim = (int)((k - c0) < g ? (k - c0) : g);
+      for (int jj = 0; jj < lim; ++jj) {
+        const i64 cj = __shfl_sync(gmask, c, gbase + jj);
+        if (act && gl > jj && rnd == cj) c = lo + j;
+      }
+      if (act) emit(j, rs + c);
+      if (c0 + g < k) __syncwarp(gmask);
+    }
+  }
+}
+
+// Lanes per frontier node: the power of two that holds the fan-out, 4..32 (full neighbourhoods: a warp per node).
+// Measured on C2's second hop (15k nodes x 10): 16 lanes, 960 CTAs in two waves 24 us; exact groups of 10 (three
+// nodes per warp, one wave) 33 us; 8 lanes with two draws per lane 34 us — more nodes in flight per SM lengthen
+// every gather / table insert more than the saved wave is worth, so the kernel stays with one draw per lane.
+inline int sample_group_lanes(i64 k) {
+  static const int exact = getenv("PYGB200_SAMPLE_EXACT_GROUPS") != nullptr;
+  if (k < 0 || k > 16) return 32;
+  if (exact) return (int)(k < 1 ? 1 : k);
+  return k > 8 ? 16 : (k > 4 ? 8 : 4);
+}
+inline int sample_nodes_per_block(int g) { return (NT / 32) * (32 / g); }
+
 #ifndef SAMPLE_MIN_BLOCKS
 #define SAMPLE_MIN_BLOCKS 4   // resident CTAs per SM the register allocation aims for
 #endif
-template <typename idx_t, int G>
+template <typename idx_t>
 __global__ void __launch_bounds__(NT, SAMPLE_MIN_BLOCKS) k_sample(const PassArgs a) {
   pdl_enter(TL_SAMPLE);
   const i64 F = a.st[ST_PASS_F];
   const i64 begin = a.st[a.o_src_begin];
   const i64 pbase = a.st[ST_PASS_BASE];
-  const i64 out0 = a.out0;
-  const idx_t* __restrict__ col = (const idx_t*)a.col;
-  const u32* __restrict__ raw = a.raw;
-  const int gl = threadIdx.x & (G - 1);
-  const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) & ~(G - 1)));
-  const i64 groups_per_grid = (i64)gridDim.x * (NT / G);
+  const int g = a.group, lane = threadIdx.x & 31, per_warp = 32 / g;
+  const int gi = lane / g, gl = lane - gi * g, gbase = gi * g;
+  const unsigned gmask = (g == 32) ? 0xffffffffu : (((1u << g) - 1u) << gbase);
+  const int npb = (NT / 32) * per_warp;
   const i64 i_lo = a.phase == 1 ? a.shard_lo : 0;
   const i64 i_hi = a.phase == 1 ? (a.shard_hi < F ? a.shard_hi : F) : F;
-  for (i64 i = i_lo + (i64)blockIdx.x * (NT / G) + threadIdx.x / G; i < i_hi; i += groups_per_grid) {
+  if (gi >= per_warp) return;   // (lanes beyond the last whole group of the warp)
+  for (i64 i = i_lo + (i64)blockIdx.x * npb + (threadIdx.x >> 5) * per_warp + gi; i < i_hi; i += (i64)gridDim.x * npb) {
     const NodeRec r = a.rec[i];
     const i64 tile = i / NT;
     const i64 tpos = a.tile_pos[tile];
     const i64 off = a.tile_off[tile] + r.loc_off;    // pass-local flat position of the node's first edge
     const int ph = (int)(tpos & 3);
     const u32 pfv = ph == 0 ? r.pf[0] : (ph == 1 ? r.pf[1] : (ph == 2 ? r.pf[2] : r.pf[3]));
-    const i64 pos0 = tpos + pfv;                      // RNG position (16-bit units) of its first draw
-    const i64 deg = r.deg, rs = r.rs, k = a.fanout;
-    const i64 src_pos = begin + i;                    // == local id of the source node (neighbor_kernel.cpp:453)
-    const i64 sbatch = a.disjoint ? a.src_batch[src_pos] : 0;
-    i64 n_out, n16, n32, n64;
-    const int mode = classify(deg, k, a.replace, &n_out, &n16, &n32, &n64);
-    auto emit = [&](i64 j, i64 e) {
-      const i64 p = off + j;
-      if (a.phase == 1) { a.eid[pbase + p] = e; return; }
-      const i64 d = (i64)col[e];
-      a.row[pbase + p] = src_pos;
-      a.eid[pbase + p] = e;
-      a.colv[pbase + p] = d;  // global id for now; k_lookup overwrites it with the local id
-      const u32 s = table_insert(a.keys, a.mask, make_key(d, sbatch, a.disjoint));
-      atomicMin(&a.vals[s], POS_BASE + (u64)p);
-      a.eslot[p] = s;
-    };
-    if (a.phase == 2) {
-      for (i64 j = gl; j < n_out; j += G) emit(j, a.eid[pbase + off + j]);
-    } else if (mode == MODE_FULL) {
-      for (i64 j = gl; j < deg; j += G) emit(j, rs + j);
-    } else if (mode == MODE_REPLACE) {
-      const int wu = rng_width_units((u64)deg);
-      for (i64 j = gl; j < k; j += G) {
-        const i64 pos = (wu == 1) ? pos0 + j : rng_align(rng_run(pos0, wu, j), wu);
-        emit(j, rs + (i64)rng_draw(raw, out0, pos, wu, (u64)deg));
-      }
-    } else if (mode == MODE_FLOYD) {
-      const i64 lo = deg - k;  // draw j: range lo+1+j, fallback value lo+j (neighbor_kernel.cpp:231-241)
-      for (i64 c0 = 0; c0 < k; c0 += G) {
-        const i64 j = c0 + gl;
-        const bool act = j < k;
-        i64 rnd = -1, c = -1;
-        if (act) {
-          int wu;
-          const i64 pos = (n32 == 0 && n64 == 0) ? (wu = 1, pos0 + j) : rng_draw_start(pos0, n16, n32, j, &wu);
-          rnd = (i64)rng_draw(raw, out0, pos, wu, (u64)(lo + 1 + j));
-          c = rnd;
-          // already chosen in an earlier chunk of this node? (only when fanout > G == 32)
-          for (i64 t = 0; t < c0; ++t)
-            if (__ldcg(&a.eid[pbase + off + t]) - rs == rnd) { c = lo + j; break; }
-        }
-        const int lim = (int)((k - c0) < G ? (k - c0) : G);
-        for (int jj = 0; jj < lim; ++jj) {
-          const i64 cj = __shfl_sync(gmask, c, jj, G);
-          if (act && gl > jj && rnd == cj) c = lo + j;
-        }
-        if (act) emit(j, rs + c);
-        if (c0 + G < k) __syncwarp(gmask);
-      }
-    }
+    // RNG position of the first draw; begin + i == local id of the source node (neighbor_kernel.cpp:453)
+    sample_node<idx_t>(a, r, off, tpos + pfv, begin + i, pbase, g, gl, gbase, gmask);
   }
   tl_mark(TL_SAMPLE | TL_END);
 }
@@ -554,42 +642,46 @@ __global__ void __launch_bounds__(NT) k_seed(const PassArgs a, const idx_t* __re
 
 // first occurrences of the running pass + tile-local ranks; last block scans the tile counts and
 // updates the dst type's counters.
+// one 1024-edge tile: first-occurrence flags + tile-local ranks, count of firsts -> mtile[tile]
+__device__ __forceinline__ void mark_tile(const PassArgs& a, i64 E, i64 tile, u32* s_w) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const i64 p0 = tile * ETILE + threadIdx.x * 4;
+  u32 fl[4]; u32 cnt = 0;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const i64 p = p0 + q;
+    fl[q] = 0;
+    if (p < E) fl[q] = (a.vals[a.eslot[p]] == POS_BASE + (u64)p) ? 1u : 0u;
+    cnt += fl[q];
+  }
+  u32 inc = cnt;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const u32 o = __shfl_up_sync(0xffffffffu, inc, d);
+    if (lane >= d) inc += o;
+  }
+  if (lane == 31) s_w[wid] = inc;
+  __syncthreads();
+  u32 pre = 0, tot = 0;
+  for (int w = 0; w < NT / 32; ++w) { if (w < wid) pre += s_w[w]; tot += s_w[w]; }
+  u32 ex = pre + inc - cnt;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const i64 p = p0 + q;
+    if (p < E) a.erank[p] = fl[q] ? (0x80000000u | ex) : 0u;
+    ex += fl[q];
+  }
+  if (threadIdx.x == 0) a.mtile[tile] = tot;
+  __syncthreads();
+}
+
 __global__ void __launch_bounds__(NT) k_mark(const PassArgs a) {
   __shared__ u32 s_w[NT / 32];
   pdl_enter(TL_MARK);
   const i64 E = a.st[ST_PASS_E];
   const i64 ntiles = ceil_div(E, ETILE);
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  for (i64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const i64 p0 = tile * ETILE + threadIdx.x * 4;
-    u32 fl[4]; u32 cnt = 0;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const i64 p = p0 + q;
-      fl[q] = 0;
-      if (p < E) fl[q] = (a.vals[a.eslot[p]] == POS_BASE + (u64)p) ? 1u : 0u;
-      cnt += fl[q];
-    }
-    u32 inc = cnt;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const u32 o = __shfl_up_sync(0xffffffffu, inc, d);
-      if (lane >= d) inc += o;
-    }
-    if (lane == 31) s_w[wid] = inc;
-    __syncthreads();
-    u32 pre = 0, tot = 0;
-    for (int w = 0; w < NT / 32; ++w) { if (w < wid) pre += s_w[w]; tot += s_w[w]; }
-    u32 ex = pre + inc - cnt;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const i64 p = p0 + q;
-      if (p < E) a.erank[p] = fl[q] ? (0x80000000u | ex) : 0u;
-      ex += fl[q];
-    }
-    if (threadIdx.x == 0) a.mtile[tile] = tot;
-    __syncthreads();
-  }
+  for (i64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) mark_tile(a, E, tile, s_w);
   tl_mark(TL_MARK | TL_END);
   if (last_block(&a.st[ST_TICKET_B])) {
     tl_mark_any(TL_MARK | TL_LAST);
@@ -797,6 +889,186 @@ __global__ void __launch_bounds__(NT) k_assign(const PassArgs a) {
   }
 }
 
+// ============================================================================ latency path
+// Small bounded runs (every pass <= LAT_TILES frontier tiles and edge tiles, seeds <= SEED_FUSED_MAX per type)
+// are a chain of tiny kernels whose cost is the length of their dependent-latency chains, not their work.  The
+// k_*_s kernels cut the two serial sections of a pass (the "last block" tile scans of k_count and k_mark and
+// the tickets in front of them): the producer only writes per-tile aggregates, and EVERY block of the consumer
+// scans them for itself (<= 1024 aggregates, 4 per thread).  The run's counters become write-once words (see
+// PassArgs), written by block 0 of the consumer for later kernels only.
+constexpr int LAT_TILES = 1024;
+
+__device__ __forceinline__ u32 pick4(const Func4& f, int ph) {
+  return ph == 0 ? f.d[0] : (ph == 1 ? f.d[1] : (ph == 2 ? f.d[2] : f.d[3]));
+}
+
+template <typename idx_t>
+__global__ void __launch_bounds__(NT) k_count_s(const PassArgs a) {
+  pdl_enter(TL_COUNT);
+  deferred_lookup(a);
+  const i64 begin = ldw(a.st, a.w_begin, a.c_begin), end = ldw(a.st, a.w_end, a.c_end);
+  const i64 F = end - begin;
+  const i64 ntiles = ceil_div(F, NT);
+  for (i64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) count_tile<idx_t>(a, begin, F, tile);
+  tl_mark(TL_COUNT | TL_END);
+}
+
+template <typename idx_t>
+__global__ void __launch_bounds__(NT, SAMPLE_MIN_BLOCKS) k_sample_s(const PassArgs a) {
+  __shared__ u32 s_off[LAT_TILES], s_pos[LAT_TILES];
+  __shared__ u32 s_win[MT_WIN];   // (block 0, stream shortfall only)
+  pdl_enter(TL_SAMPLE);
+  const i64 gen0 = *reinterpret_cast<volatile i64*>(a.gen);
+  const i64 begin = ldw(a.st, a.w_begin, a.c_begin), end = ldw(a.st, a.w_end, a.c_end);
+  const i64 cur_in = ldw(a.st, a.w_cur_in, 0), pbase = ldw(a.st, a.w_pbase, 0);
+  const i64 F = end - begin;
+  const int ntiles = (int)ceil_div(F, NT);
+  const int ph0 = (int)(cur_in & 3);
+  const int g = a.group, lane = threadIdx.x & 31, per_warp = 32 / g;
+  const int gi = lane / g, gl = lane - gi * g, gbase = gi * g;
+  const unsigned gmask = (g == 32) ? 0xffffffffu : (((1u << g) - 1u) << gbase);
+  const int npb = (NT / 32) * per_warp;
+  // this group's first node: its record is fetched now, beside the tile aggregates (rec[] is sized for the bound)
+  const i64 i_first = (i64)blockIdx.x * npb + (threadIdx.x >> 5) * per_warp + (gi < per_warp ? gi : 0);
+  NodeRec r_first = {};
+  if (i_first < F) r_first = a.rec[i_first];
+  // ---- every block: exclusive scan of the tile aggregates (edge offsets, RNG positions relative to cur_in)
+  u32 E, adv;
+  {
+    const int t0 = threadIdx.x * 4;
+    auto tile_agg = [&](int t, u32* v, Func4* f) {
+      *v = (u32)a.tile_out[t];
+      const uint4 w = *reinterpret_cast<const uint4*>(a.tile_func + 4 * (size_t)t);
+      f->d[0] = w.x; f->d[1] = w.y; f->d[2] = w.z; f->d[3] = w.w;
+    };
+    u32 lv = 0; Func4 lf = {{0, 0, 0, 0}};
+    int uni = 1;
+    for (int q = 0; q < 4 && t0 + q < ntiles; ++q) {
+      u32 v; Func4 f;
+      tile_agg(t0 + q, &v, &f);
+      uni &= f.d[0] == f.d[1] && f.d[1] == f.d[2] && f.d[2] == f.d[3];
+      lv += v; lf = compose(lf, f);
+    }
+    if (__syncthreads_and(uni)) {   // (the rule: no multi-word draw in this pass) advances just add up
+      u32 ex_v, ex_u, tot_v, tot_u;
+      block_scan_sums(lv, lf.d[0], &ex_v, &ex_u, &tot_v, &tot_u);
+      for (int q = 0; q < 4 && t0 + q < ntiles; ++q) {   // (second look at the aggregates: L1 hits)
+        s_off[t0 + q] = ex_v; s_pos[t0 + q] = ex_u;
+        ex_v += (u32)a.tile_out[t0 + q]; ex_u += a.tile_func[4 * (size_t)(t0 + q)];
+      }
+      E = tot_v; adv = tot_u;
+    } else {
+      u32 ex_v, tot_v; Func4 ex_f, tot_f;
+      block_scan_pair(lv, lf, &ex_v, &ex_f, &tot_v, &tot_f);
+      for (int q = 0; q < 4 && t0 + q < ntiles; ++q) {
+        u32 v; Func4 f;
+        tile_agg(t0 + q, &v, &f);
+        s_off[t0 + q] = ex_v; s_pos[t0 + q] = pick4(ex_f, ph0);
+        ex_v += v; ex_f = compose(ex_f, f);
+      }
+      E = tot_v; adv = pick4(tot_f, ph0);
+    }
+    __syncthreads();
+  }
+  const i64 cur_out = cur_in + adv;
+  // ---- the stream must cover this pass; it does unless a node drew multi-word values (deg >= 2^16)
+  const i64 need = a.out0 + 256 * rng_blocks_for_units(cur_out);
+  const i64 target = ((need + MT_N - 1) / MT_N) * MT_N;
+  if (blockIdx.x == 0) {
+    if (threadIdx.x == 0) {
+      a.st[a.w_E] = E;
+      a.st[a.w_cur_out] = cur_out;
+      a.st[a.w_relcum_out] = pbase + E;
+    }
+    if (gen0 < target) mt_extend_block<3>(a.raw, a.gen, need, a.raw_cap, a.st, s_win);
+  } else if (gen0 < target) {
+    if (threadIdx.x == 0) {
+      while (*reinterpret_cast<volatile i64*>(a.gen) < target && *reinterpret_cast<volatile i64*>(a.st + ST_ERROR) == 0) { }
+      __threadfence();
+    }
+    __syncthreads();
+  }
+  // ---- one group of g lanes per frontier node
+  if (gi >= per_warp) return;   // (lanes beyond the last whole group of the warp; no block-wide sync below)
+  for (i64 i = i_first; i < F; i += (i64)gridDim.x * npb) {
+    const NodeRec r = i == i_first ? r_first : a.rec[i];
+    const int tile = (int)(i / NT);
+    const i64 tpos = cur_in + s_pos[tile];
+    const i64 off = (i64)s_off[tile] + r.loc_off;
+    const int ph = (int)(tpos & 3);
+    const u32 pfv = ph == 0 ? r.pf[0] : (ph == 1 ? r.pf[1] : (ph == 2 ? r.pf[2] : r.pf[3]));
+    sample_node<idx_t>(a, r, off, tpos + pfv, begin + i, pbase, g, gl, gbase, gmask);
+  }
+  tl_mark(TL_SAMPLE | TL_END);
+}
+
+__global__ void __launch_bounds__(NT) k_mark_s(const PassArgs a) {
+  __shared__ u32 s_w[NT / 32];
+  pdl_enter(TL_MARK);
+  const i64 E = a.st[a.w_E];
+  const i64 ntiles = ceil_div(E, ETILE);
+  for (i64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) mark_tile(a, E, tile, s_w);
+  tl_mark(TL_MARK | TL_END);
+}
+
+__global__ void __launch_bounds__(NT) k_assign_s(const PassArgs a) {
+  __shared__ u32 s_excl[LAT_TILES];
+  __shared__ u32 s_w[NT / 32];
+  pdl_enter(TL_ASSIGN);
+  const i64 E = a.st[a.w_E];
+  const i64 pbase = ldw(a.st, a.w_pbase, 0);
+  const i64 list_base = ldw(a.st, a.w_list_in, a.c_list_in);
+  const i64 ids_base = list_base - (a.st[a.w_seed_list] - a.st[a.w_seed_ids]);   // duplicate seeds are listed, not numbered
+  const int ntiles = (int)ceil_div(E, ETILE);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  // this thread's first edge: fetched now, beside the tile counts
+  const i64 p_first = (i64)blockIdx.x * NT + threadIdx.x;
+  u32 er_first = 0, sl_first = 0;
+  if (p_first < E) { er_first = a.erank[p_first]; sl_first = a.eslot[p_first]; }
+  // ---- every block: exclusive scan of the per-tile counts of first occurrences
+  u32 nnew;
+  {
+    const int t0 = threadIdx.x * 4;
+    u32 pv[4]; u32 lv = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int t = t0 + q;
+      pv[q] = lv;
+      if (t < ntiles) lv += (u32)a.mtile[t];
+    }
+    u32 inc = lv;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const u32 o = __shfl_up_sync(0xffffffffu, inc, d);
+      if (lane >= d) inc += o;
+    }
+    if (lane == 31) s_w[wid] = inc;
+    __syncthreads();
+    u32 pre = 0, tot = 0;
+    for (int w = 0; w < NT / 32; ++w) { if (w < wid) pre += s_w[w]; tot += s_w[w]; }
+    const u32 ex = pre + inc - lv;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int t = t0 + q;
+      if (t < ntiles) s_excl[t] = ex + pv[q];
+    }
+    nnew = tot;
+    __syncthreads();
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) a.st[a.w_list_out] = list_base + nnew;
+  for (i64 p = p_first; p < E; p += (i64)gridDim.x * NT) {
+    const u32 er = p == p_first ? er_first : a.erank[p];
+    if (er & 0x80000000u) {
+      const i64 rank = (i64)s_excl[p / ETILE] + (er & 0x7fffffffu);
+      const u32 s = p == p_first ? sl_first : a.eslot[p];
+      a.vals[s] = (u64)(ids_base + rank);
+      a.dst_nodes[list_base + rank] = a.colv[pbase + p];
+      if (a.disjoint) a.dst_batch[list_base + rank] = a.src_batch[a.row[pbase + p]];
+      a.dst_slot[list_base + rank] = s;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(NT) k_lookup(const PassArgs a) {
   const i64 E = a.st[ST_PASS_E];
   const i64 pbase = a.st[ST_PASS_BASE];
@@ -839,7 +1111,7 @@ __global__ void __launch_bounds__(NT) k_final(const PassArgs a, int o_mt, i64* h
   }
   // the state buffer is double-buffered: the half the NEXT run uses is cleared here (nobody reads it any more)
   if (zero_st) for (int i = threadIdx.x; i < n_words; i += blockDim.x) zero_st[i] = 0;
-  const i64 blocks = rng_blocks_for_units(a.st[ST_CURSOR]);
+  const i64 blocks = rng_blocks_for_units(a.ssa ? ldw(a.st, a.w_cur_in, 0) : a.st[ST_CURSOR]);
   const i64 q = a.out0 + 256 * blocks;
   mt_extend_block<3>(a.raw, a.gen, q, a.raw_cap, a.st, s_win);
   const i64 g = (q - 1) / MT_N;
@@ -874,11 +1146,60 @@ constexpr int SEED_NT = 1024;
 constexpr int SEED_FUSED_MAX = 16384;
 template <typename idx_t>
 __global__ void __launch_bounds__(SEED_NT) k_seed_fused(const PassArgs a, const idx_t* __restrict__ seeds, int n, i64 batch0,
-                                                         int L, int o_begin, int o_end, int o_nph, const PassArgs c, int do_count) {
+                                                         int L, int o_begin, int o_end, int o_nph, const PassArgs c) {
   __shared__ int s_w[SEED_NT / 32];
   __shared__ int s_carry;
   pdl_enter(TL_SEED);
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (blockIdx.x > 0) {
+    // ---- latency path: blocks 1.. do the k_count of the run's first pass `c` beside the dedup of block 0.  Its
+    // frontier is this seed list as given (duplicates included) and nothing it needs comes out of the hash
+    // table, so one launch covers both.  Each block takes 1024 seeds = four 256-node tiles (same records and
+    // tile aggregates as count_tile).
+    __shared__ u32 s_tv[SEED_NT / 32];
+    __shared__ Func4 s_tf[SEED_NT / 32];
+    const int base = ((int)blockIdx.x - 1) * SEED_NT;
+    const int i = base + threadIdx.x;
+    i64 rs = 0, deg = 0; u32 n_out = 0;
+    Func4 f = {{0, 0, 0, 0}};
+    if (i < n) node_degree<idx_t>(c, (i64)seeds[i], batch0 + i, &rs, &deg, &n_out, &f);
+    u32 iv = n_out; Func4 iff = f;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const u32 ov = __shfl_up_sync(0xffffffffu, iv, d);
+      Func4 of;
+#pragma unroll
+      for (int p = 0; p < 4; ++p) of.d[p] = __shfl_up_sync(0xffffffffu, iff.d[p], d);
+      if (lane >= d) { iv += ov; iff = compose(of, iff); }
+    }
+    if (lane == 31) { s_tv[wid] = iv; s_tf[wid] = iff; }
+    __syncthreads();
+    const int w0 = wid & ~7;   // first warp of this thread's 256-node tile
+    u32 pv = 0; Func4 pfx = {{0, 0, 0, 0}};
+    for (int w = w0; w < wid; ++w) { pv += s_tv[w]; pfx = compose(pfx, s_tf[w]); }
+    u32 ev = __shfl_up_sync(0xffffffffu, iv, 1);
+    Func4 ef;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) ef.d[p] = __shfl_up_sync(0xffffffffu, iff.d[p], 1);
+    if (lane == 0) { ev = 0; ef = {{0, 0, 0, 0}}; }
+    const Func4 exf = compose(pfx, ef);
+    if (i < n) {
+      NodeRec r;
+      r.rs = rs; r.deg = (u32)deg; r.loc_off = pv + ev;
+      r.pf[0] = exf.d[0]; r.pf[1] = exf.d[1]; r.pf[2] = exf.d[2]; r.pf[3] = exf.d[3];
+      c.rec[i] = r;
+    }
+    if (lane == 31 && (wid & 7) == 7) {   // last thread of a tile: the tile's totals
+      const int tile = (base >> 8) + (wid >> 3);
+      if (tile * NT < n) {
+        const Func4 tf = compose(pfx, iff);
+        c.tile_out[tile] = pv + iv;
+#pragma unroll
+        for (int p = 0; p < 4; ++p) c.tile_func[4 * tile + p] = tf.d[p];
+      }
+    }
+    return;
+  }
   for (int i = threadIdx.x; i < n; i += SEED_NT) {
     const i64 v = (i64)seeds[i];
     a.dst_nodes[i] = v;
@@ -918,87 +1239,6 @@ __global__ void __launch_bounds__(SEED_NT) k_seed_fused(const PassArgs a, const 
     a.st[o_nph] = n;
   }
   tl_mark(TL_SEED | TL_END);
-  if (!do_count) return;
-  // ---- the first pass's k_count, done here: its frontier is exactly this seed list and one block holds it
-  // (n <= SEED_FUSED_MAX), so degrees, in-tile scans (256-node tiles, same records as k_count) and the scan
-  // over the <= 64 tiles need no second launch and no last-block protocol.
-  __shared__ u32 s_win[MT_WIN];
-  __shared__ u32 s_tv[SEED_NT / 32];
-  __shared__ Func4 s_tf[SEED_NT / 32];
-  __shared__ u32 s_tile_v[SEED_FUSED_MAX / NT];
-  __shared__ Func4 s_tile_f[SEED_FUSED_MAX / NT];
-  const idx_t* __restrict__ rowptr = (const idx_t*)c.rowptr;
-  __syncthreads();
-  for (int base = 0; base < n; base += SEED_NT) {
-    const int i = base + threadIdx.x;
-    i64 rs = 0, deg = 0, n_out = 0, n16 = 0, n32 = 0, n64 = 0;
-    Func4 f = {{0, 0, 0, 0}};
-    if (i < n) {
-      const i64 v = (i64)seeds[i];
-      rs = (i64)rowptr[v];
-      deg = (i64)rowptr[v + 1] - rs;
-      classify(deg, c.fanout, c.replace, &n_out, &n16, &n32, &n64);
-      if (n32 == 0 && n64 == 0) {
-        f.d[0] = f.d[1] = f.d[2] = f.d[3] = (u32)n16;
-      } else {
-#pragma unroll
-        for (int p = 0; p < 4; ++p) f.d[p] = (u32)(rng_node_end(p, n16, n32, n64) - p);
-      }
-    }
-    u32 iv = (u32)n_out; Func4 iff = f;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const u32 ov = __shfl_up_sync(0xffffffffu, iv, d);
-      Func4 of;
-#pragma unroll
-      for (int p = 0; p < 4; ++p) of.d[p] = __shfl_up_sync(0xffffffffu, iff.d[p], d);
-      if (lane >= d) { iv += ov; iff = compose(of, iff); }
-    }
-    if (lane == 31) { s_tv[wid] = iv; s_tf[wid] = iff; }
-    __syncthreads();
-    const int w0 = wid & ~7;   // first warp of this thread's 256-node tile
-    u32 pv = 0; Func4 pfx = {{0, 0, 0, 0}};
-    for (int w = w0; w < wid; ++w) { pv += s_tv[w]; pfx = compose(pfx, s_tf[w]); }
-    u32 ev = __shfl_up_sync(0xffffffffu, iv, 1);
-    Func4 ef;
-#pragma unroll
-    for (int p = 0; p < 4; ++p) ef.d[p] = __shfl_up_sync(0xffffffffu, iff.d[p], 1);
-    if (lane == 0) { ev = 0; ef = {{0, 0, 0, 0}}; }
-    const Func4 exf = compose(pfx, ef);
-    if (i < n) {
-      NodeRec r;
-      r.rs = rs; r.deg = (u32)deg; r.loc_off = pv + ev;
-      r.pf[0] = exf.d[0]; r.pf[1] = exf.d[1]; r.pf[2] = exf.d[2]; r.pf[3] = exf.d[3];
-      c.rec[i] = r;
-    }
-    if (lane == 31 && (wid & 7) == 7) {   // last thread of a tile: the tile's totals
-      const int tile = (base >> 8) + (wid >> 3);
-      s_tile_v[tile] = pv + iv;
-      s_tile_f[tile] = compose(pfx, iff);
-    }
-    __syncthreads();
-  }
-  tl_mark(TL_COUNT | TL_END);
-  if (threadIdx.x == 0) {
-    const int ntiles = (n + NT - 1) / NT;
-    i64 off = 0, pos = c.st[ST_CURSOR];
-    for (int t = 0; t < ntiles; ++t) {
-      c.tile_off[t] = off;
-      c.tile_pos[t] = pos;
-      off += s_tile_v[t];
-      pos += s_tile_f[t].d[pos & 3];
-    }
-    c.st[ST_PASS_F] = n;
-    c.st[ST_PASS_E] = off;
-    c.st[ST_CURSOR] = pos;
-    c.st[ST_PASS_BASE] = c.st[c.o_rel_edges];
-    c.st[c.o_rel_edges] += off;
-    c.st[c.o_eph] = off;
-  }
-  tl_mark(TL_COUNT | TL_LAST);
-  __syncthreads();
-  mt_extend_block<3>(c.raw, c.gen, c.out0 + 256 * rng_blocks_for_units(c.st[ST_CURSOR]), c.raw_cap, c.st, s_win);
-  tl_mark(TL_COUNT | TL_LAST | TL_END);
 }
 
 __global__ void __launch_bounds__(NT) k_cleanup(u64* keys, u64* vals, const u32* __restrict__ slots, const i64* n_ptr) {
@@ -1232,7 +1472,7 @@ extern "C" void pygb200_sampler_destroy(pygb200_sampler* s) {
 namespace {
 
 constexpr int MAX_SHARDS = 64;
-struct Layout { int o_list, o_ids, o_begin, o_end, o_rel, o_nph, o_eph, o_mt, o_shard; size_t words; };
+struct Layout { int o_list, o_ids, o_begin, o_end, o_rel, o_nph, o_eph, o_mt, o_shard, o_ssa; size_t words; };
 Layout make_layout(int T, int R, int L) {
   Layout l;
   int o = ST_HDR;
@@ -1240,6 +1480,7 @@ Layout make_layout(int T, int R, int L) {
   l.o_rel = o; o += R; l.o_nph = o; o += T * (L + 1); l.o_eph = o; o += R * (L > 0 ? L : 1);
   l.o_mt = o; o += MT_N / 2;
   l.o_shard = o; o += MAX_SHARDS + 2;
+  l.o_ssa = o; o += 4 * R * (L > 0 ? L : 1);   // latency path: {E, cursor, relation total, dst list length} per pass
   l.words = (size_t)o;
   return l;
 }
@@ -1390,17 +1631,12 @@ int launch_count(pygb200_sampler* s, const PassArgs& a, i64 F, i64 E_prev, cudaS
 }
 
 template <typename idx_t>
-int launch_sample(pygb200_sampler* s, const PassArgs& a, i64 F, i64 E, cudaStream_t st) {
-  const i64 k = a.fanout;
-  const int G = (k < 0 || k > 16) ? 32 : (k > 8 ? 16 : (k > 4 ? 8 : 4));
-  const int gs = grid_for(F, NT / G, s->sm_count);
+int launch_sample(pygb200_sampler* s, const PassArgs& a_in, i64 F, i64 E, cudaStream_t st) {
+  PassArgs a = a_in;
+  a.group = sample_group_lanes(a.fanout);
+  const int gs = grid_for(F, sample_nodes_per_block(a.group), s->sm_count);
   void* tk = prof_begin(st);
-  switch (G) {
-    case 4: launch_pdl(k_sample<idx_t, 4>, gs, NT, st, a); break;
-    case 8: launch_pdl(k_sample<idx_t, 8>, gs, NT, st, a); break;
-    case 16: launch_pdl(k_sample<idx_t, 16>, gs, NT, st, a); break;
-    default: launch_pdl(k_sample<idx_t, 32>, gs, NT, st, a); break;
-  }
+  launch_pdl(k_sample<idx_t>, gs, NT, st, a);
   prof_end(tk, "sample", st, E);
   PYGB_LAUNCH_CHECK();
   return PYGB200_OK;
@@ -1712,34 +1948,36 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
   ht_lap(1);
   // ---- seeds (neighbor_kernel.cpp:409-416, :669-704)
   if (any_time) if (int e = s->seed_times.ensure((size_t)std::max<i64>(total_seeds, 1) * 8, 0, st)) return e;
-  // The first pass that will run (hop 0) has its k_count folded into the seed kernel of its source type when
-  // that seed list fits one block: one launch less on the critical path.  That seed kernel goes last, because
-  // the multi-kernel seed path of another type would overwrite the pass header it leaves behind.
+  // ---- latency path?  (k_*_s kernels: write-once counters, no serial sections; see above k_count_s)
+  bool lat = !synced && !sharded && L > 0 && !getenv("PYGB200_NO_LATENCY_PATH");
+  for (int t = 0; t < T && lat; ++t) lat = n_seeds[t] <= SEED_FUSED_MAX;
+  for (int h = 0; h < L && lat; ++h)
+    for (int r = 0; r < R && lat; ++r) {
+      if (num_neighbors[(size_t)r * L + h] == 0) continue;
+      lat = fb[(size_t)rels[r].src_type * (L + 1) + h] <= (i64)LAT_TILES * NT && eb[(size_t)r * L + h] <= (i64)LAT_TILES * ETILE;
+    }
+  // The first pass that will run (hop 0) is counted inside the seed launch of its source type (extra blocks)
   int fuse_r = -1, fuse_t = -1;
-  if (!synced && !sharded && !any_time && L > 0 && !getenv("PYGB200_NO_FUSE_COUNT")) {
+  if (lat) {
     for (int r = 0; r < R; ++r) {
       if (num_neighbors[(size_t)r * L] == 0) continue;
       if (fb[(size_t)rels[r].src_type * (L + 1)] == 0 || eb[(size_t)r * L] == 0) continue;
-      const int t0 = rels[r].src_type;
-      if (n_seeds[t0] > 0 && n_seeds[t0] <= SEED_FUSED_MAX) { fuse_r = r; fuse_t = t0; }
+      fuse_r = r; fuse_t = rels[r].src_type;
       break;
     }
   }
   std::vector<i64> batch_base((size_t)T, 0);
   if (disjoint) for (int t = 1; t < T; ++t) batch_base[t] = batch_base[t - 1] + n_seeds[t - 1];
-  for (int ti = 0; ti < T; ++ti) {
-    // order: every type but fuse_t, then fuse_t
-    int t = ti;
-    if (fuse_t >= 0) t = ti == T - 1 ? fuse_t : (ti >= fuse_t ? ti + 1 : ti);
+  for (int t = 0; t < T; ++t) {
     const i64 batch0 = batch_base[t];
     PassArgs a = make_args(-1, t, -1);
     a.seed_mode = 1;
     PassArgs c = a;
-    const int do_count = t == fuse_t;
-    if (do_count) {
+    int count_blocks = 0;
+    if (t == fuse_t) {
       c = make_args(rels[fuse_r].src_type, rels[fuse_r].dst_type, fuse_r);
       c.fanout = num_neighbors[(size_t)fuse_r * L];
-      c.o_eph = lay.o_eph + fuse_r * L;
+      count_blocks = (int)ceil_div(n_seeds[t], SEED_NT);
     }
     if (any_time && n_seeds[t] > 0) {
       const i64* stt = temporal->seed_time ? reinterpret_cast<const i64*>(temporal->seed_time[t]) : nullptr;
@@ -1750,10 +1988,10 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
       PYGB_LAUNCH_CHECK();
     }
     if (n_seeds[t] > 0 && n_seeds[t] <= SEED_FUSED_MAX) {
-      if (idx32) launch_pdl(k_seed_fused<int32_t>, 1, SEED_NT, st, a, (const int32_t*)seeds[t], (int)n_seeds[t], batch0, (int)L,
-                            lay.o_begin + t, lay.o_end + t, lay.o_nph + t * (L + 1), c, do_count);
-      else launch_pdl(k_seed_fused<int64_t>, 1, SEED_NT, st, a, (const int64_t*)seeds[t], (int)n_seeds[t], batch0, (int)L,
-                      lay.o_begin + t, lay.o_end + t, lay.o_nph + t * (L + 1), c, do_count);
+      if (idx32) launch_pdl(k_seed_fused<int32_t>, 1 + count_blocks, SEED_NT, st, a, (const int32_t*)seeds[t], (int)n_seeds[t], batch0, (int)L,
+                            lay.o_begin + t, lay.o_end + t, lay.o_nph + t * (L + 1), c);
+      else launch_pdl(k_seed_fused<int64_t>, 1 + count_blocks, SEED_NT, st, a, (const int64_t*)seeds[t], (int)n_seeds[t], batch0, (int)L,
+                      lay.o_begin + t, lay.o_end + t, lay.o_nph + t * (L + 1), c);
       PYGB_LAUNCH_CHECK();
     } else if (n_seeds[t] > 0) {
       const int g = grid_for(n_seeds[t], NT, s->sm_count);
@@ -1772,7 +2010,72 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
   ht_lap(2);
   // ---- hops.  Bounded mode defers every pass's lookup into the next k_count / the final kernel.
   i64* lk_colv = nullptr; const u64* lk_vals = nullptr; i64 lk_E = 0;
-  for (int h = 0; h < L; ++h) {
+  // latency path: the static schedule decides which write-once word holds what
+  struct Wd { int w; i64 c; };
+  std::vector<Wd> cur_list, sl_begin, sl_end, relcum, list_end;
+  std::vector<int> eph_w;
+  Wd cursor{-1, 0};
+  int lk_w_E = -1, lk_w_pbase = -1;
+  if (lat) {
+    cur_list.resize(T); sl_begin.resize(T); sl_end.resize(T); relcum.assign(R, Wd{-1, 0});
+    list_end.resize((size_t)T * (L + 1)); eph_w.assign((size_t)R * L, -1);
+    for (int t = 0; t < T; ++t) {
+      cur_list[t] = Wd{-1, n_seeds[t]}; sl_begin[t] = Wd{-1, 0}; sl_end[t] = Wd{-1, n_seeds[t]};
+      list_end[(size_t)t * (L + 1)] = cur_list[t];
+    }
+    int P = 0;
+    for (int h = 0; h < L; ++h) {
+      for (int r = 0; r < R; ++r) {
+        const i64 k = num_neighbors[(size_t)r * L + h];
+        const int src_t = rels[r].src_type, dst_t = rels[r].dst_type;
+        if (k == 0) continue;  // nothing emitted, no RNG consumed (neighbor_kernel.cpp:67-68)
+        const i64 Fb = fb[(size_t)src_t * (L + 1) + h], Eb = eb[(size_t)r * L + h];
+        if (Fb == 0 || Eb == 0) continue;
+        PassArgs a = make_args(src_t, dst_t, r);
+        const int base = lay.o_ssa + 4 * P++;
+        a.fanout = k;
+        a.ssa = 1;
+        a.w_begin = sl_begin[src_t].w; a.c_begin = sl_begin[src_t].c;
+        a.w_end = sl_end[src_t].w; a.c_end = sl_end[src_t].c;
+        a.w_list_in = cur_list[dst_t].w; a.c_list_in = cur_list[dst_t].c;
+        a.w_pbase = relcum[r].w;
+        a.w_cur_in = cursor.w;
+        a.w_E = base; a.w_cur_out = base + 1; a.w_relcum_out = base + 2; a.w_list_out = base + 3;
+        a.w_seed_list = lay.o_list + dst_t; a.w_seed_ids = lay.o_ids + dst_t;
+        a.lk_colv = lk_colv; a.lk_vals = lk_vals; a.lk_w_E = lk_w_E; a.lk_w_pbase = lk_w_pbase;
+        void* tk;
+        if (!(h == 0 && r == fuse_r)) {   // (else: counted inside the seed launch)
+          const int g = std::max(grid_for(Fb, NT, s->sm_count), lk_colv ? grid_for(lk_E, NT, s->sm_count) : 1);
+          tk = prof_begin(st);
+          if (idx32) launch_pdl(k_count_s<int32_t>, g, NT, st, a); else launch_pdl(k_count_s<int64_t>, g, NT, st, a);
+          prof_end(tk, "count", st, Fb);
+          PYGB_LAUNCH_CHECK();
+        }
+        a.group = sample_group_lanes(k);
+        const int gs = grid_for(Fb, sample_nodes_per_block(a.group), s->sm_count);
+        tk = prof_begin(st);
+        if (idx32) launch_pdl(k_sample_s<int32_t>, gs, NT, st, a); else launch_pdl(k_sample_s<int64_t>, gs, NT, st, a);
+        prof_end(tk, "sample", st, Eb);
+        PYGB_LAUNCH_CHECK();
+        tk = prof_begin(st);
+        launch_pdl(k_mark_s, grid_for(Eb, ETILE, s->sm_count), NT, st, a);
+        prof_end(tk, "mark", st, Eb);
+        PYGB_LAUNCH_CHECK();
+        tk = prof_begin(st);
+        launch_pdl(k_assign_s, grid_for(Eb, NT, s->sm_count), NT, st, a);
+        prof_end(tk, "assign", st, Eb);
+        PYGB_LAUNCH_CHECK();
+        lk_colv = a.colv; lk_vals = a.vals; lk_E = Eb; lk_w_E = base; lk_w_pbase = relcum[r].w;
+        cursor = Wd{base + 1, 0}; relcum[r] = Wd{base + 2, 0}; cur_list[dst_t] = Wd{base + 3, 0};
+        eph_w[(size_t)r * L + h] = base;
+      }
+      for (int t = 0; t < T; ++t) {   // end of hop: next frontier = what the hop added (neighbor_kernel.cpp:807-812)
+        sl_begin[t] = sl_end[t]; sl_end[t] = cur_list[t];
+        list_end[(size_t)t * (L + 1) + h + 1] = cur_list[t];
+      }
+    }
+  }
+  for (int h = 0; h < L && !lat; ++h) {
     if (synced) if (int e = read_state()) return e;  // actual frontier slices of this hop
     // last pass of this hop that will actually be launched (it also does the end-of-hop bookkeeping)
     int last_r = -1;
@@ -1801,8 +2104,7 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
         a.o_eph = lay.o_eph + r * L + h;
         a.lk_colv = lk_colv; a.lk_vals = lk_vals;
         with_hop_end(a);
-        if (!(h == 0 && r == fuse_r))  // (counted by the seed kernel)
-          if (int e = idx32 ? launch_count<int32_t>(s, a, Fb, lk_E, st) : launch_count<int64_t>(s, a, Fb, lk_E, st)) return e;
+        if (int e = idx32 ? launch_count<int32_t>(s, a, Fb, lk_E, st) : launch_count<int64_t>(s, a, Fb, lk_E, st)) return e;
         if (!sharded) {
           if (int e = idx32 ? launch_rest<int32_t>(s, a, Fb, Eb, false, st) : launch_rest<int64_t>(s, a, Fb, Eb, false, st)) return e;
         } else {
@@ -1875,6 +2177,7 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
   {
     PassArgs a = make_args(-1, 0, -1);
     a.lk_colv = lk_colv; a.lk_vals = lk_vals;
+    if (lat) { a.ssa = 1; a.lk_w_E = lk_w_E; a.lk_w_pbase = lk_w_pbase; a.w_cur_in = cursor.w; }
     s->run_serial += 1;
     launch_pdl(k_final, lk_colv ? grid_for(lk_E, NT, s->sm_count) : 1, NT, st, a, lay.o_mt, s->st_host_dev, (int)lay.words,
                s->run_serial, dst_other);
@@ -1888,7 +2191,7 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
     auto& tb = s->types[t];
     const i64 cap_nodes = (i64)(tb.slot.cap / 4);
     launch_pdl(k_cleanup, grid_for(synced ? cap_nodes : node_cap[t], NT, s->sm_count), NT, st, tb.keys.as<u64>(), tb.vals.as<u64>(),
-               (const u32*)tb.slot.as<u32>(), (const i64*)(dst + lay.o_list + t));
+               (const u32*)tb.slot.as<u32>(), (const i64*)(dst + (lat && cur_list[t].w >= 0 ? cur_list[t].w : lay.o_list + t)));
     PYGB_LAUNCH_CHECK();
   }
   // pre-generation for the run after this one (decided when the previous run ended): launched now, on the side
@@ -1926,22 +2229,42 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
   const i64* hs = s->st_host;
   PYGB_CHECK(hs[ST_ERROR] == 0, PYGB200_ERR_INTERNAL, "sampler: mt19937 stream buffer too small (internal bound violated)");
   s->dirty = false;
-  for (int t = 0; t < T; ++t) {
-    s->types[t].n_nodes = hs[lay.o_list + t];
-    if (n_nodes_out) n_nodes_out[t] = hs[lay.o_list + t];
-    if (nodes_per_hop) for (int j = 0; j <= L; ++j) nodes_per_hop[(size_t)t * (L + 1) + j] = hs[lay.o_nph + t * (L + 1) + j];
-  }
-  for (int r = 0; r < R; ++r) {
-    s->rels[r].n_edges = hs[lay.o_rel + r];
-    if (n_edges_out) n_edges_out[r] = hs[lay.o_rel + r];
-    if (edges_per_hop) for (int j = 0; j < L; ++j) edges_per_hop[(size_t)r * L + j] = hs[lay.o_eph + r * L + j];
+  if (lat) {   // counters from the write-once words of the schedule
+    auto val = [&](const Wd& x) { return x.w >= 0 ? hs[x.w] : x.c; };
+    for (int t = 0; t < T; ++t) {
+      const i64 n = val(cur_list[t]);
+      s->types[t].n_nodes = n;
+      if (n_nodes_out) n_nodes_out[t] = n;
+      if (nodes_per_hop) {
+        nodes_per_hop[(size_t)t * (L + 1)] = n_seeds[t];
+        for (int j = 1; j <= L; ++j)
+          nodes_per_hop[(size_t)t * (L + 1) + j] = val(list_end[(size_t)t * (L + 1) + j]) - val(list_end[(size_t)t * (L + 1) + j - 1]);
+      }
+    }
+    for (int r = 0; r < R; ++r) {
+      const i64 n = val(relcum[r]);
+      s->rels[r].n_edges = n;
+      if (n_edges_out) n_edges_out[r] = n;
+      if (edges_per_hop) for (int j = 0; j < L; ++j) edges_per_hop[(size_t)r * L + j] = eph_w[(size_t)r * L + j] >= 0 ? hs[eph_w[(size_t)r * L + j]] : 0;
+    }
+  } else {
+    for (int t = 0; t < T; ++t) {
+      s->types[t].n_nodes = hs[lay.o_list + t];
+      if (n_nodes_out) n_nodes_out[t] = hs[lay.o_list + t];
+      if (nodes_per_hop) for (int j = 0; j <= L; ++j) nodes_per_hop[(size_t)t * (L + 1) + j] = hs[lay.o_nph + t * (L + 1) + j];
+    }
+    for (int r = 0; r < R; ++r) {
+      s->rels[r].n_edges = hs[lay.o_rel + r];
+      if (n_edges_out) n_edges_out[r] = hs[lay.o_rel + r];
+      if (edges_per_hop) for (int j = 0; j < L; ++j) edges_per_hop[(size_t)r * L + j] = hs[lay.o_eph + r * L + j];
+    }
   }
   memcpy(mt->state, hs + lay.o_mt, sizeof(mt->state));
   mt->next = (int32_t)hs[ST_MT_NEXT];
   mt->left = (int32_t)hs[ST_MT_LEFT];
   // the stream persists: remember where it is and pre-generate what a run like this one will need,
   // on the side stream (one CTA, overlaps the caller's work and the next run's first kernels)
-  s->st_o_list = lay.o_list;
+  s->st_o_list = lat && cur_list[0].w >= 0 ? cur_list[0].w : lay.o_list;
   s->mt_expected = *mt;
   s->mt_q = out0 + 256 * hs[ST_BLOCKS];
   s->mt_valid = true;
