@@ -146,6 +146,9 @@ struct PassArgs {
   int w_E, w_cur_out, w_relcum_out, w_list_out;          // written by this pass (block 0 of k_sample_s / k_assign_s)
   int w_seed_list, w_seed_ids;                            // dst type: seeds listed / distinct seeds (ids = list - dups)
   int lk_w_E, lk_w_pbase;                                 // previous pass (deferred lookup)
+  // publication of the run's counters + final engine state to the host (publish_run): by k_final, or — latency
+  // path — already by the last pass's k_assign_s, as soon as the last counter is known
+  i64* pub_host; i64* pub_zero; i64 pub_serial; int pub_words, pub_o_mt;
 };
 __device__ __forceinline__ i64 ldw(const i64* st, int w, i64 c) { return w >= 0 ? st[w] : c; }
 
@@ -889,6 +892,42 @@ __global__ void __launch_bounds__(NT) k_assign(const PassArgs a) {
   }
 }
 
+// The run's counters and the final engine state go straight into mapped host memory; the host polls the flag
+// word behind them (no DMA copy, no event round trip) and everything else it does is stream-ordered behind the
+// run's remaining kernels, so this may happen as soon as the last counter exists.  Called by one whole block.
+// Engine state = the generation holding the last consumed output (see mt19937.cuh); at least one 128-word block
+// is always consumed (rand_engine.h:28).  The stream must already cover it.
+__device__ void publish_run(const PassArgs& a, i64 cursor, bool with_flag) {
+  i64* host_st = a.pub_host;
+  const int n_words = a.pub_words, o_mt = a.pub_o_mt;
+  // counters first: these loads overlap the stream -> engine-state chain below
+  for (int i = threadIdx.x; i < n_words; i += blockDim.x)
+    if ((i < o_mt || i >= o_mt + MT_N / 2) && (i < ST_ERROR || i > ST_BLOCKS)) host_st[i] = a.st[i];
+  // the state buffer is double-buffered: the half the NEXT run uses is cleared here (nobody reads it any more)
+  if (a.pub_zero) for (int i = threadIdx.x; i < n_words; i += blockDim.x) a.pub_zero[i] = 0;
+  const i64 blocks = rng_blocks_for_units(cursor);
+  const i64 q = a.out0 + 256 * blocks;
+  const i64 g = (q - 1) / MT_N;
+  u32* hout = reinterpret_cast<u32*>(host_st + o_mt);
+  for (int i = threadIdx.x; i < MT_N; i += blockDim.x) hout[i] = __ldcg(&a.raw[g * MT_N + i]);
+  if (threadIdx.x == 0) {
+    const i64 nxt = q - g * MT_N;
+    host_st[ST_MT_NEXT] = nxt; host_st[ST_MT_LEFT] = 625 - nxt; host_st[ST_BLOCKS] = blocks;
+    host_st[ST_ERROR] = a.st[ST_ERROR];
+  }
+  if (!with_flag) return;   // (the caller's successor adds the last counter and raises the flag: publish_last)
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) { *reinterpret_cast<volatile i64*>(host_st + n_words) = a.pub_serial; __threadfence_system(); }
+}
+// thread 0 of one block: the one counter that was still missing, then the flag
+__device__ __forceinline__ void publish_last(const PassArgs& a, int w, i64 value) {
+  a.pub_host[w] = value;
+  __threadfence_system();
+  *reinterpret_cast<volatile i64*>(a.pub_host + a.pub_words) = a.pub_serial;
+  __threadfence_system();
+}
+
 // ============================================================================ latency path
 // Small bounded runs (every pass <= LAT_TILES frontier tiles and edge tiles, seeds <= SEED_FUSED_MAX per type)
 // are a chain of tiny kernels whose cost is the length of their dependent-latency chains, not their work.  The
@@ -981,6 +1020,10 @@ __global__ void __launch_bounds__(NT, SAMPLE_MIN_BLOCKS) k_sample_s(const PassAr
       a.st[a.w_relcum_out] = pbase + E;
     }
     if (gen0 < target) mt_extend_block<3>(a.raw, a.gen, need, a.raw_cap, a.st, s_win);
+    if (a.pub_words) {   // last pass of the run: everything but the final length of its dst list is known now
+      __syncthreads();
+      publish_run(a, cur_out, false);
+    }
   } else if (gen0 < target) {
     if (threadIdx.x == 0) {
       while (*reinterpret_cast<volatile i64*>(a.gen) < target && *reinterpret_cast<volatile i64*>(a.st + ST_ERROR) == 0) { }
@@ -1055,7 +1098,15 @@ __global__ void __launch_bounds__(NT) k_assign_s(const PassArgs a) {
     nnew = tot;
     __syncthreads();
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) a.st[a.w_list_out] = list_base + nnew;
+  if (blockIdx.x == 0) {
+    if (threadIdx.x == 0) {
+      a.st[a.w_list_out] = list_base + nnew;
+      if (a.pub_words) {   // last pass of the run: that was the last counter (the rest went out with k_sample_s)
+        publish_last(a, a.w_list_out, list_base + nnew);
+        tl_mark(TL_FINAL);
+      }
+    }
+  }
   for (i64 p = p_first; p < E; p += (i64)gridDim.x * NT) {
     const u32 er = p == p_first ? er_first : a.erank[p];
     if (er & 0x80000000u) {
@@ -1093,50 +1144,16 @@ __global__ void k_seed_end(i64* st, int t, int L, int o_list, int o_begin, int o
   st[o_nph + t * (L + 1)] = st[o_list + t];
 }
 
-// Last kernel of a run: deferred lookup of the last pass + (block 0) final engine state = the
-// generation holding the last consumed output (see mt19937.cuh); at least one 128-word block is
-// always consumed (rand_engine.h:28).
-__global__ void __launch_bounds__(NT) k_final(const PassArgs a, int o_mt, i64* host_st, int n_words, i64 serial, i64* zero_st) {
+// Last kernel of a run: deferred lookup of the last pass; block 0 publishes the run unless that has happened.
+__global__ void __launch_bounds__(NT) k_final(const PassArgs a) {
   __shared__ u32 s_win[MT_WIN];
   pdl_enter(TL_FINAL);
+  if (blockIdx.x == 0 && a.pub_words) {
+    const i64 cursor = a.ssa ? ldw(a.st, a.w_cur_in, 0) : a.st[ST_CURSOR];
+    mt_extend_block<3>(a.raw, a.gen, a.out0 + 256 * rng_blocks_for_units(cursor), a.raw_cap, a.st, s_win);
+    publish_run(a, cursor, true);
+  }
   deferred_lookup(a);
-  if (blockIdx.x != 0) return;
-  // The counters + engine state go straight into mapped host memory; the host polls the flag word (no DMA copy,
-  // no event round trip).  Other blocks may still be doing the deferred lookup — the host only needs the
-  // counters, everything else it does is stream-ordered behind this kernel.
-  // Counters first: these loads overlap the cursor -> stream -> engine-state chain below.
-  if (host_st) {
-    for (int i = threadIdx.x; i < n_words; i += blockDim.x)
-      if ((i < o_mt || i >= o_mt + MT_N / 2) && (i < ST_ERROR || i > ST_BLOCKS)) host_st[i] = a.st[i];
-  }
-  // the state buffer is double-buffered: the half the NEXT run uses is cleared here (nobody reads it any more)
-  if (zero_st) for (int i = threadIdx.x; i < n_words; i += blockDim.x) zero_st[i] = 0;
-  const i64 blocks = rng_blocks_for_units(a.ssa ? ldw(a.st, a.w_cur_in, 0) : a.st[ST_CURSOR]);
-  const i64 q = a.out0 + 256 * blocks;
-  mt_extend_block<3>(a.raw, a.gen, q, a.raw_cap, a.st, s_win);
-  const i64 g = (q - 1) / MT_N;
-  u32* out = reinterpret_cast<u32*>(a.st + o_mt);
-  u32* hout = host_st ? reinterpret_cast<u32*>(host_st + o_mt) : nullptr;
-  for (int i = threadIdx.x; i < MT_N; i += blockDim.x) {
-    const u32 w = __ldcg(&a.raw[g * MT_N + i]);
-    out[i] = w;
-    if (hout) hout[i] = w;
-  }
-  if (threadIdx.x == 0) {
-    const i64 nxt = q - g * MT_N;
-    a.st[ST_MT_NEXT] = nxt;
-    a.st[ST_MT_LEFT] = 625 - nxt;
-    a.st[ST_BLOCKS] = blocks;
-    if (host_st) {
-      host_st[ST_MT_NEXT] = nxt; host_st[ST_MT_LEFT] = 625 - nxt; host_st[ST_BLOCKS] = blocks;
-      host_st[ST_ERROR] = a.st[ST_ERROR];   // (mt_extend_block may have raised it)
-    }
-  }
-  if (host_st) {
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x == 0) { *reinterpret_cast<volatile i64*>(host_st + n_words) = serial; __threadfence_system(); }
-  }
   tl_mark(TL_FINAL | TL_END);
 }
 
@@ -1949,7 +1966,8 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
   // ---- seeds (neighbor_kernel.cpp:409-416, :669-704)
   if (any_time) if (int e = s->seed_times.ensure((size_t)std::max<i64>(total_seeds, 1) * 8, 0, st)) return e;
   // ---- latency path?  (k_*_s kernels: write-once counters, no serial sections; see above k_count_s)
-  bool lat = !synced && !sharded && L > 0 && !getenv("PYGB200_NO_LATENCY_PATH");
+  static const bool no_lat = getenv("PYGB200_NO_LATENCY_PATH") != nullptr;
+  bool lat = !synced && !sharded && L > 0 && !no_lat;
   for (int t = 0; t < T && lat; ++t) lat = n_seeds[t] <= SEED_FUSED_MAX;
   for (int h = 0; h < L && lat; ++h)
     for (int r = 0; r < R && lat; ++r) {
@@ -2010,6 +2028,8 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
   ht_lap(2);
   // ---- hops.  Bounded mode defers every pass's lookup into the next k_count / the final kernel.
   i64* lk_colv = nullptr; const u64* lk_vals = nullptr; i64 lk_E = 0;
+  s->run_serial += 1;
+  bool published = false;
   // latency path: the static schedule decides which write-once word holds what
   struct Wd { int w; i64 c; };
   std::vector<Wd> cur_list, sl_begin, sl_end, relcum, list_end;
@@ -2023,7 +2043,10 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
       cur_list[t] = Wd{-1, n_seeds[t]}; sl_begin[t] = Wd{-1, 0}; sl_end[t] = Wd{-1, n_seeds[t]};
       list_end[(size_t)t * (L + 1)] = cur_list[t];
     }
-    int P = 0;
+    int P = 0, P_total = 0;
+    for (int h = 0; h < L; ++h)
+      for (int r = 0; r < R; ++r)
+        P_total += num_neighbors[(size_t)r * L + h] != 0 && fb[(size_t)rels[r].src_type * (L + 1) + h] != 0 && eb[(size_t)r * L + h] != 0;
     for (int h = 0; h < L; ++h) {
       for (int r = 0; r < R; ++r) {
         const i64 k = num_neighbors[(size_t)r * L + h];
@@ -2032,6 +2055,11 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
         const i64 Fb = fb[(size_t)src_t * (L + 1) + h], Eb = eb[(size_t)r * L + h];
         if (Fb == 0 || Eb == 0) continue;
         PassArgs a = make_args(src_t, dst_t, r);
+        if (P == P_total - 1) {   // the last pass publishes the run from its k_assign_s
+          a.pub_host = s->st_host_dev; a.pub_zero = dst_other; a.pub_serial = s->run_serial; a.pub_words = (int)lay.words;
+          a.pub_o_mt = lay.o_mt;
+          published = true;
+        }
         const int base = lay.o_ssa + 4 * P++;
         a.fanout = k;
         a.ssa = 1;
@@ -2178,9 +2206,11 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
     PassArgs a = make_args(-1, 0, -1);
     a.lk_colv = lk_colv; a.lk_vals = lk_vals;
     if (lat) { a.ssa = 1; a.lk_w_E = lk_w_E; a.lk_w_pbase = lk_w_pbase; a.w_cur_in = cursor.w; }
-    s->run_serial += 1;
-    launch_pdl(k_final, lk_colv ? grid_for(lk_E, NT, s->sm_count) : 1, NT, st, a, lay.o_mt, s->st_host_dev, (int)lay.words,
-               s->run_serial, dst_other);
+    if (!published) {
+      a.pub_host = s->st_host_dev; a.pub_zero = dst_other; a.pub_serial = s->run_serial; a.pub_words = (int)lay.words;
+      a.pub_o_mt = lay.o_mt;
+    }
+    launch_pdl(k_final, lk_colv ? grid_for(lk_E, NT, s->sm_count) : 1, NT, st, a);
     PYGB_LAUNCH_CHECK();
   }
   // table cleanup is stream-ordered after k_final; the host does not wait for it.  With
