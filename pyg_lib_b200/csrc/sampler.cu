@@ -144,6 +144,7 @@ struct PassArgs {
   int w_begin, w_end, w_list_in, w_pbase, w_cur_in;      // frontier slice, dst list length, relation offset, RNG cursor
   i64 c_begin, c_end, c_list_in;                          // (pbase / cursor constants are 0)
   int w_E, w_cur_out, w_relcum_out, w_list_out;          // written by this pass (block 0 of k_sample_s / k_assign_s)
+  int w_new;                                              // new nodes of this pass (summed up by k_mark_s)
   int w_seed_list, w_seed_ids;                            // dst type: seeds listed / distinct seeds (ids = list - dups)
   int lk_w_E, lk_w_pbase;                                 // previous pass (deferred lookup)
   // publication of the run's counters + final engine state to the host (publish_run): by k_final, or — latency
@@ -897,6 +898,10 @@ __global__ void __launch_bounds__(NT) k_assign(const PassArgs a) {
 // run's remaining kernels, so this may happen as soon as the last counter exists.  Called by one whole block.
 // Engine state = the generation holding the last consumed output (see mt19937.cuh); at least one 128-word block
 // is always consumed (rand_engine.h:28).  The stream must already cover it.
+// flag word = run serial (24 bits) above a 40-bit payload
+__host__ __device__ __forceinline__ i64 flag_word(i64 serial, i64 payload) {
+  return (i64)((((u64)serial & 0xffffffull) << 40) | ((u64)payload & 0xffffffffffull));
+}
 __device__ void publish_run(const PassArgs& a, i64 cursor, bool with_flag) {
   i64* host_st = a.pub_host;
   const int n_words = a.pub_words, o_mt = a.pub_o_mt;
@@ -915,16 +920,15 @@ __device__ void publish_run(const PassArgs& a, i64 cursor, bool with_flag) {
     host_st[ST_MT_NEXT] = nxt; host_st[ST_MT_LEFT] = 625 - nxt; host_st[ST_BLOCKS] = blocks;
     host_st[ST_ERROR] = a.st[ST_ERROR];
   }
-  if (!with_flag) return;   // (the caller's successor adds the last counter and raises the flag: publish_last)
+  if (!with_flag) return;   // (a later kernel adds the last counter and raises the flag: publish_last)
   __threadfence_system();
   __syncthreads();
-  if (threadIdx.x == 0) { *reinterpret_cast<volatile i64*>(host_st + n_words) = a.pub_serial; __threadfence_system(); }
+  if (threadIdx.x == 0) { *reinterpret_cast<volatile i64*>(host_st + n_words) = flag_word(a.pub_serial, 0); __threadfence_system(); }
 }
-// thread 0 of one block: the one counter that was still missing, then the flag
-__device__ __forceinline__ void publish_last(const PassArgs& a, int w, i64 value) {
-  a.pub_host[w] = value;
-  __threadfence_system();
-  *reinterpret_cast<volatile i64*>(a.pub_host + a.pub_words) = a.pub_serial;
+// One thread of a LATER kernel (everything publish_run wrote is visible by then): the flag word carries the one
+// counter that was still missing, so a single 8-byte store completes the run for the host.
+__device__ __forceinline__ void publish_last(const PassArgs& a, i64 value) {
+  *reinterpret_cast<volatile i64*>(a.pub_host + a.pub_words) = flag_word(a.pub_serial, value);
   __threadfence_system();
 }
 
@@ -1050,7 +1054,13 @@ __global__ void __launch_bounds__(NT) k_mark_s(const PassArgs a) {
   pdl_enter(TL_MARK);
   const i64 E = a.st[a.w_E];
   const i64 ntiles = ceil_div(E, ETILE);
-  for (i64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) mark_tile(a, E, tile, s_w);
+  u32 mine = 0;
+  for (i64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    mark_tile(a, E, tile, s_w);
+    if (threadIdx.x == 0) mine += (u32)a.mtile[tile];
+  }
+  // the pass's total of new nodes: the host-facing counter of the run's last pass is published from it
+  if (threadIdx.x == 0 && mine) atomicAdd(reinterpret_cast<unsigned long long*>(a.st + a.w_new), (unsigned long long)mine);
   tl_mark(TL_MARK | TL_END);
 }
 
@@ -1064,6 +1074,10 @@ __global__ void __launch_bounds__(NT) k_assign_s(const PassArgs a) {
   const i64 ids_base = list_base - (a.st[a.w_seed_list] - a.st[a.w_seed_ids]);   // duplicate seeds are listed, not numbered
   const int ntiles = (int)ceil_div(E, ETILE);
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (a.pub_words && blockIdx.x == 0 && threadIdx.x == 0) {   // last pass of the run: its dst list length was the last counter
+    publish_last(a, list_base + a.st[a.w_new]);
+    tl_mark(TL_FINAL);
+  }
   // this thread's first edge: fetched now, beside the tile counts
   const i64 p_first = (i64)blockIdx.x * NT + threadIdx.x;
   u32 er_first = 0, sl_first = 0;
@@ -1099,13 +1113,7 @@ __global__ void __launch_bounds__(NT) k_assign_s(const PassArgs a) {
     __syncthreads();
   }
   if (blockIdx.x == 0) {
-    if (threadIdx.x == 0) {
-      a.st[a.w_list_out] = list_base + nnew;
-      if (a.pub_words) {   // last pass of the run: that was the last counter (the rest went out with k_sample_s)
-        publish_last(a, a.w_list_out, list_base + nnew);
-        tl_mark(TL_FINAL);
-      }
-    }
+    if (threadIdx.x == 0) a.st[a.w_list_out] = list_base + nnew;
   }
   for (i64 p = p_first; p < E; p += (i64)gridDim.x * NT) {
     const u32 er = p == p_first ? er_first : a.erank[p];
@@ -1497,7 +1505,7 @@ Layout make_layout(int T, int R, int L) {
   l.o_rel = o; o += R; l.o_nph = o; o += T * (L + 1); l.o_eph = o; o += R * (L > 0 ? L : 1);
   l.o_mt = o; o += MT_N / 2;
   l.o_shard = o; o += MAX_SHARDS + 2;
-  l.o_ssa = o; o += 4 * R * (L > 0 ? L : 1);   // latency path: {E, cursor, relation total, dst list length} per pass
+  l.o_ssa = o; o += 5 * R * (L > 0 ? L : 1);   // latency path: {E, cursor, relation total, dst list length, new nodes} per pass
   l.words = (size_t)o;
   return l;
 }
@@ -2030,6 +2038,7 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
   i64* lk_colv = nullptr; const u64* lk_vals = nullptr; i64 lk_E = 0;
   s->run_serial += 1;
   bool published = false;
+  int pub_w_list = -1;   // latency path: the counter that arrives as the flag word's payload
   // latency path: the static schedule decides which write-once word holds what
   struct Wd { int w; i64 c; };
   std::vector<Wd> cur_list, sl_begin, sl_end, relcum, list_end;
@@ -2060,7 +2069,7 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
           a.pub_o_mt = lay.o_mt;
           published = true;
         }
-        const int base = lay.o_ssa + 4 * P++;
+        const int base = lay.o_ssa + 5 * P++;
         a.fanout = k;
         a.ssa = 1;
         a.w_begin = sl_begin[src_t].w; a.c_begin = sl_begin[src_t].c;
@@ -2068,7 +2077,8 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
         a.w_list_in = cur_list[dst_t].w; a.c_list_in = cur_list[dst_t].c;
         a.w_pbase = relcum[r].w;
         a.w_cur_in = cursor.w;
-        a.w_E = base; a.w_cur_out = base + 1; a.w_relcum_out = base + 2; a.w_list_out = base + 3;
+        a.w_E = base; a.w_cur_out = base + 1; a.w_relcum_out = base + 2; a.w_list_out = base + 3; a.w_new = base + 4;
+        if (a.pub_words) pub_w_list = base + 3;
         a.w_seed_list = lay.o_list + dst_t; a.w_seed_ids = lay.o_ids + dst_t;
         a.lk_colv = lk_colv; a.lk_vals = lk_vals; a.lk_w_E = lk_w_E; a.lk_w_pbase = lk_w_pbase;
         void* tk;
@@ -2240,11 +2250,12 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
   {  // wait for k_final's flag (spin on mapped memory; keep an eye on the stream in case the run died)
     volatile i64* flag = s->st_host + lay.words;
     unsigned long long spins = 0;
-    while (*flag != s->run_serial) {
+    auto done = [&]() { return (((u64)*flag) >> 40) == ((u64)s->run_serial & 0xffffffull); };
+    while (!done()) {
       if ((++spins & 0xfffff) == 0) {
         const cudaError_t q = cudaStreamQuery(st);
         if (q != cudaErrorNotReady) {
-          if (q == cudaSuccess && *flag == s->run_serial) break;
+          if (q == cudaSuccess && done()) break;
           set_error(std::string("sampler: run did not complete: ") + cudaGetErrorString(q == cudaSuccess ? cudaErrorUnknown : q));
           return PYGB200_ERR_CUDA;
         }
@@ -2256,6 +2267,7 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
     std::atomic_thread_fence(std::memory_order_acquire);
   }
   ht_lap(4);
+  if (pub_w_list >= 0) s->st_host[pub_w_list] = (i64)((u64)s->st_host[lay.words] & 0xffffffffffull);
   const i64* hs = s->st_host;
   PYGB_CHECK(hs[ST_ERROR] == 0, PYGB200_ERR_INTERNAL, "sampler: mt19937 stream buffer too small (internal bound violated)");
   s->dirty = false;
