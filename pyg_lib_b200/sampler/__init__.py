@@ -46,8 +46,9 @@ def neighbor_sample(
     :obj:`(rowptr, col)`.  Returns ``(row, col, node_id, edge_id, num_sampled_nodes_per_hop,
     num_sampled_edges_per_hop)`` exactly like the reference (pyg_lib/sampler/__init__.py:11-100).
 
-    Temporal (`node_time`/`edge_time`/`seed_time`) and biased (`edge_weight`) sampling raise: they are
-    not implemented on the B200 path and there is no CPU fallback."""
+    Node-/edge-level temporal sampling (`node_time`/`edge_time`/`seed_time`, strategies 'uniform' and 'last')
+    is supported; biased (`edge_weight`) sampling raises: it cannot be reproduced bit for bit on this path and
+    there is no CPU fallback."""
     return _neighbor_sample_op(rowptr, col, seed, num_neighbors, node_time, edge_time, seed_time, edge_weight, csc,
                                replace, directed, disjoint, temporal_strategy, return_edge_id)
 
