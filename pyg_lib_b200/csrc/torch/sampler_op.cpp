@@ -80,8 +80,13 @@ struct CpuEngine {
   }
 };
 
-// results of at most this many worst-case bytes are written in place (views of bound-sized tensors are returned)
-constexpr int64_t kDirectOutputBytes = 64ll << 20;
+// Results of at most this many worst-case bytes are written in place (views of bound-sized tensors are returned,
+// so a caller that keeps a result keeps the bound alive: C2 returns 76 % of its bound, a sparse hetero graph may
+// return 7 %).  PYGB200_DIRECT_OUTPUT_MB overrides the 64 MiB default (0 = always export into exact-size tensors).
+static const int64_t kDirectOutputBytes = [] {
+  const char* e = getenv("PYGB200_DIRECT_OUTPUT_MB");
+  return (e ? (int64_t)atoll(e) : 64ll) << 20;
+}();
 
 void check_index_tensor(const at::Tensor& t, const char* name, at::ScalarType st, const at::Device& dev) {
   TORCH_CHECK(t.is_contiguous(), "Non-contiguous '", name, "'");  // neighbor_kernel.cpp:361-363
@@ -258,6 +263,7 @@ hetero_neighbor_sample_cuda(const std::vector<node_type>& node_types, const std:
   pygb200_sampler* s = get_sampler(dev.index(), stream);
   unsigned flags = (replace ? PYGB200_S_REPLACE : 0u) | (disjoint ? PYGB200_S_DISJOINT : 0u) | (idx32 ? PYGB200_S_INDEX32 : 0u);
   std::vector<int64_t> nph((size_t)T * (L + 1), 0), eph((size_t)R * std::max<size_t>(L, 1), 0), n_nodes(T, 0), n_edges(std::max(R, 1), 0);
+  std::vector<at::Tensor> d_row, d_col, d_eid, d_node;   // bound-sized results (latency path)
   {
     std::vector<const int64_t*> nt(T, nullptr), et(std::max(R, 1), nullptr), stt(T, nullptr);
     bool any = false;
@@ -273,6 +279,27 @@ hetero_neighbor_sample_cuda(const std::vector<node_type>& node_types, const std:
       for (const auto& kv : *seed_time_dict)
         if (tix.count(kv.key())) stt[tix[kv.key()]] = time_ptr(kv.value(), "seed_time", dev);
     pygb200_temporal tmp{nt.data(), et.data(), stt.data(), temporal_strategy == "last" ? 1 : 0};
+    // Latency path (as in neighbor_sample_cuda): bound-sized result tensors the sampling kernels write themselves
+    std::vector<int64_t> ncap(T, 0), ecap(R, 0);
+    if (!idx32 && !disjoint && L > 0 && R > 0 &&
+        pygb200_sampler_bounds(T, R, (int)L, rels.data(), n_seeds.data(), nn.data(), ncap.data(), ecap.data()) == PYGB200_OK) {
+      int64_t total = 0;
+      bool ok = true;
+      for (int t = 0; t < T; ++t) { total += ncap[t]; ok = ok && ncap[t] > 0; }
+      for (int r = 0; r < R; ++r) { total += 3 * ecap[r]; ok = ok && ecap[r] > 0; }
+      if (ok && total * 8 <= kDirectOutputBytes) {
+        const auto opt0 = first_seed.options();
+        std::vector<void*> rp(R), cp(R), ep(R, nullptr), np(T);
+        d_row.resize(R); d_col.resize(R); d_eid.resize(R); d_node.resize(T);
+        for (int t = 0; t < T; ++t) { d_node[t] = at::empty({ncap[t]}, opt0); np[t] = d_node[t].data_ptr(); }
+        for (int r = 0; r < R; ++r) {
+          d_row[r] = at::empty({ecap[r]}, opt0); d_col[r] = at::empty({ecap[r]}, opt0);
+          rp[r] = d_row[r].data_ptr(); cp[r] = d_col[r].data_ptr();
+          if (return_edge_id) { d_eid[r] = at::empty({ecap[r]}, opt0); ep[r] = d_eid[r].data_ptr(); }
+        }
+        PYGB_TORCH_CALL(pygb200_sampler_bind_outputs(s, T, R, rp.data(), cp.data(), ep.data(), np.data(), ecap.data(), ncap.data()));
+      }
+    }
     CpuEngine eng;
     PYGB_TORCH_CALL(pygb200_sampler_run_temporal(s, T, R, (int)L, rels.data(), seeds.data(), n_seeds.data(), nn.data(), flags,
                                                  &eng.mt, nph.data(), eph.data(), n_nodes.data(), n_edges.data(), stream,
@@ -288,19 +315,31 @@ hetero_neighbor_sample_cuda(const std::vector<node_type>& node_types, const std:
   if (return_edge_id) out_eid = c10::Dict<rel_type, at::Tensor>();
   c10::Dict<node_type, std::vector<int64_t>> out_nph;
   c10::Dict<rel_type, std::vector<int64_t>> out_eph;
+  const bool direct_out = pygb200_sampler_outputs_direct(s) != 0;
   for (const auto& t : node_types) {
     const int i = tix[t];
-    at::Tensor node = disjoint ? at::empty({n_nodes[i], 2}, opt) : at::empty({n_nodes[i]}, opt);
-    PYGB_TORCH_CALL(pygb200_sampler_export_nodes(s, i, node.data_ptr(), idx32, stream));
+    at::Tensor node;
+    if (direct_out) {
+      node = d_node[i].narrow(0, 0, n_nodes[i]);
+    } else {
+      node = disjoint ? at::empty({n_nodes[i], 2}, opt) : at::empty({n_nodes[i]}, opt);
+      PYGB_TORCH_CALL(pygb200_sampler_export_nodes(s, i, node.data_ptr(), idx32, stream));
+    }
     out_node.insert(t, node);
     out_nph.insert(t, std::vector<int64_t>(nph.begin() + (size_t)i * (L + 1), nph.begin() + (size_t)(i + 1) * (L + 1)));
   }
   for (int r = 0; r < R; ++r) {
     const rel_type rk = to_rel_type(edge_types[r]);
-    at::Tensor row = at::empty({n_edges[r]}, opt), colv = at::empty({n_edges[r]}, opt), eid;
-    if (return_edge_id) eid = at::empty({n_edges[r]}, opt);
-    PYGB_TORCH_CALL(pygb200_sampler_export_edges(s, r, row.data_ptr(), colv.data_ptr(),
-                                                 return_edge_id ? eid.data_ptr() : nullptr, idx32, stream));
+    at::Tensor row, colv, eid;
+    if (direct_out) {
+      row = d_row[r].narrow(0, 0, n_edges[r]); colv = d_col[r].narrow(0, 0, n_edges[r]);
+      if (return_edge_id) eid = d_eid[r].narrow(0, 0, n_edges[r]);
+    } else {
+      row = at::empty({n_edges[r]}, opt); colv = at::empty({n_edges[r]}, opt);
+      if (return_edge_id) eid = at::empty({n_edges[r]}, opt);
+      PYGB_TORCH_CALL(pygb200_sampler_export_edges(s, r, row.data_ptr(), colv.data_ptr(),
+                                                   return_edge_id ? eid.data_ptr() : nullptr, idx32, stream));
+    }
     if (csc) std::swap(row, colv);
     out_row.insert(rk, row);
     out_col.insert(rk, colv);

@@ -398,3 +398,48 @@ def test_temporal_kat_and_hetero(lib):
             assert torch.equal(out[3][k].cpu(), exp[3][k]) and out[5][k] == exp[5][k]
         for t in nt:
             assert torch.equal(out[2][t].cpu(), exp[2][t]) and out[4][t] == exp[4][t]
+
+
+def test_throughput_path_and_export_path_subprocess():
+    """Small inputs take the latency path with in-place results by default; the same golden cases must also hold
+    on the throughput path (PYGB200_NO_LATENCY_PATH) and with exported, exact-size results
+    (PYGB200_DIRECT_OUTPUT_MB=0)."""
+    import os, subprocess, sys
+    ROOT = osp.dirname(osp.dirname(osp.abspath(__file__)))
+    code = r'''
+import os, sys, numpy as np, torch
+sys.path.insert(0, os.path.join(%r, 'tests')); sys.path.insert(0, %r)
+import pyg_lib_b200 as P
+from graphs import HOMO_CASES, HETERO_CASES, build_homo, build_hetero
+G = np.load(os.path.join(%r, 'tests', 'golden', 'reference_outputs.npz'))
+dev = 'cuda:0'
+n = 0
+for name, case in HOMO_CASES.items():
+    if 'temporal' in case: continue
+    rowptr, col, seed = build_homo(case)
+    torch.manual_seed(case['rng_seed'])
+    r = P.sampler.neighbor_sample(rowptr.to(dev), col.to(dev), seed.to(dev), case['num_neighbors'], csc=case.get('csc', False),
+                                  replace=case.get('replace', False), disjoint=case.get('disjoint', False))
+    for k, t in zip(('row', 'col', 'node', 'eid'), r[:4]):
+        assert np.array_equal(t.cpu().numpy(), G[f'homo/{name}/{k}']), (name, k)
+    assert list(r[4]) == list(G[f'homo/{name}/nph']) and list(r[5]) == list(G[f'homo/{name}/eph']), name
+    assert np.array_equal(torch.get_rng_state().numpy()[:24 + 624 * 8], G[f'homo/{name}/rng_after']), name
+    n += 1
+for name, case in HETERO_CASES.items():
+    node_types, edge_types, rowptr_d, col_d, seed_d, nn_d = build_hetero(case)
+    torch.manual_seed(case['rng_seed'])
+    r = torch.ops.pyg.hetero_neighbor_sample(node_types, edge_types, {k: v.to(dev) for k, v in rowptr_d.items()},
+                                             {k: v.to(dev) for k, v in col_d.items()}, {k: v.to(dev) for k, v in seed_d.items()},
+                                             nn_d, None, None, None, None, case.get('csc', False), case.get('replace', False), True,
+                                             case.get('disjoint', False), 'uniform', True)
+    for i, key in enumerate(('row', 'col', 'node', 'eid')):
+        for k, v in r[i].items():
+            assert np.array_equal(v.cpu().numpy(), G[f'hetero/{name}/{key}/{k}']), (name, key, k)
+    n += 1
+print('OK', n)
+''' % (ROOT, ROOT, ROOT)
+    for extra in ({'PYGB200_NO_LATENCY_PATH': '1'}, {'PYGB200_DIRECT_OUTPUT_MB': '0'},
+                  {'PYGB200_NO_LATENCY_PATH': '1', 'PYGB200_DIRECT_OUTPUT_MB': '0'}):
+        env = dict(os.environ, **extra)
+        out = subprocess.run([sys.executable, '-c', code], env=env, capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0 and 'OK' in out.stdout, (extra, out.stdout[-2000:], out.stderr[-4000:])
