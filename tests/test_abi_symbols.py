@@ -80,3 +80,59 @@ def test_product_never_imports_oracle():
         if osp.isfile(f) and f.endswith(('.py', '.cu', '.cuh', '.cpp', '.h')):
             txt = open(f, errors='ignore').read()
             assert 'import oracle' not in txt and 'from oracle' not in txt and 'liboracle' not in txt, f
+
+
+def test_sampler_bounds_host_only(built):
+    """pygb200_sampler_bounds is pure host arithmetic (no CUDA call): the static frontier/edge recurrence of
+    neighbor_kernel.cpp:430-475,718-812 — every frontier node emits <= k edges, every edge <= one new node of the
+    relation's dst type — checked against the oracle's actual counts on a hetero case."""
+    import sys
+    sys.path.insert(0, osp.join(ROOT, 'tests'))
+    from graphs import HETERO_CASES, build_hetero
+    from oracle import oracle as O
+    lib = C.CDLL(osp.join(built, 'libpyg_b200.so'))
+    lib.pygb200_last_error.restype = C.c_char_p
+
+    class REL(C.Structure):
+        _fields_ = [('rowptr', C.c_void_p), ('col', C.c_void_p), ('num_src_nodes', C.c_int64), ('num_edges', C.c_int64),
+                    ('src_type', C.c_int32), ('dst_type', C.c_int32)]
+
+    # homogeneous closed form
+    rel = REL(None, None, 100, 1000, 0, 0)
+    ns, nn = C.c_int64(7), (C.c_int64 * 3)(5, 4, 3)
+    ncap, ecap = C.c_int64(), C.c_int64()
+    assert lib.pygb200_sampler_bounds(1, 1, 3, C.byref(rel), C.byref(ns), nn, C.byref(ncap), C.byref(ecap)) == 0
+    assert ecap.value == 7 * 5 + 7 * 5 * 4 + 7 * 5 * 4 * 3 and ncap.value == 7 + ecap.value
+    nn_all = (C.c_int64 * 3)(5, -1, 3)
+    assert lib.pygb200_sampler_bounds(1, 1, 3, C.byref(rel), C.byref(ns), nn_all, C.byref(ncap), C.byref(ecap)) != 0
+    assert b'-1' in lib.pygb200_last_error()
+    bad = REL(None, None, 100, 1000, 0, 3)
+    assert lib.pygb200_sampler_bounds(1, 1, 3, C.byref(bad), C.byref(ns), nn, C.byref(ncap), C.byref(ecap)) != 0
+
+    # hetero: bounds dominate what the oracle (= the reference's algorithm) actually samples
+    name = next(iter(HETERO_CASES))
+    case = HETERO_CASES[name]
+    node_types, edge_types, rowptr_d, col_d, seed_d, nn_d = build_hetero(case)
+    types = list(seed_d.keys()) + [t for t in node_types if t not in seed_d]
+    tix = {t: i for i, t in enumerate(types)}
+    T, R, L = len(types), len(edge_types), len(next(iter(nn_d.values())))
+    rels = (REL * R)()
+    fan = (C.c_int64 * (R * L))()
+    for r, et in enumerate(edge_types):
+        k = '__'.join(et)
+        src, dst = (et[2], et[0]) if case.get('csc', False) else (et[0], et[2])
+        rels[r] = REL(None, None, rowptr_d[k].numel() - 1, col_d[k].numel(), tix[src], tix[dst])
+        for h in range(L):
+            fan[r * L + h] = nn_d[k][h]
+    n_seeds = (C.c_int64 * T)(*[seed_d[t].numel() if t in seed_d else 0 for t in types])
+    ncaps, ecaps = (C.c_int64 * T)(), (C.c_int64 * R)()
+    if any(v < 0 for v in fan):
+        pytest.skip('case uses full neighbourhoods')
+    assert lib.pygb200_sampler_bounds(T, R, L, rels, n_seeds, fan, ncaps, ecaps) == 0, lib.pygb200_last_error()
+    torch.manual_seed(case['rng_seed'])
+    exp = O.hetero_neighbor_sample(node_types, edge_types, rowptr_d, col_d, seed_d, nn_d, csc=case.get('csc', False),
+                                   replace=case.get('replace', False), disjoint=case.get('disjoint', False))
+    for r, et in enumerate(edge_types):
+        assert exp[0]['__'.join(et)].numel() <= ecaps[r]
+    for t in node_types:
+        assert exp[2][t].shape[0] <= ncaps[tix[t]]
