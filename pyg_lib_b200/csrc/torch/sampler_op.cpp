@@ -82,10 +82,10 @@ struct CpuEngine {
 
 // Results of at most this many worst-case bytes are written in place (views of bound-sized tensors are returned,
 // so a caller that keeps a result keeps the bound alive: C2 returns 76 % of its bound, a sparse hetero graph may
-// return 7 %).  PYGB200_DIRECT_OUTPUT_MB overrides the 64 MiB default (0 = always export into exact-size tensors).
+// return 7 %).  PYGB200_DIRECT_OUTPUT_MB overrides the 256 MiB default (0 = always export into exact-size tensors).
 static const int64_t kDirectOutputBytes = [] {
   const char* e = getenv("PYGB200_DIRECT_OUTPUT_MB");
-  return (e ? (int64_t)atoll(e) : 64ll) << 20;
+  return (e ? (int64_t)atoll(e) : 256ll) << 20;
 }();
 
 void check_index_tensor(const at::Tensor& t, const char* name, at::ScalarType st, const at::Device& dev) {
