@@ -89,9 +89,21 @@ __host__ __device__ __forceinline__ i64 rng_node_end(i64 pos, i64 n16, i64 n32, 
 }
 
 __device__ __forceinline__ u64 rng_draw(const u32* __restrict__ raw, i64 out0, i64 pos, int wu, u64 range) {
+  if (wu == 1) {
+    // 16-bit field `ph` of word W: it lies in one 32-bit half of the word, so only that engine output is loaded
+    // and tempered.  rng_word's two corrections still apply: v == 2^64-1 -> 0 (both halves all-ones after
+    // tempering; the other half is only looked at when this one is) and + 2^63 (flips the top bit of field 3).
+    const i64 W = pos >> 2;
+    const int ph = (int)(pos & 3);
+    const i64 o = out0 + ((W >> 7) << 8) + 2 * (127 - (int)(W & 127));
+    u32 t = mt_temper(raw[o + (ph < 2 ? 1 : 0)]);
+    if (t == 0xffffffffu && mt_temper(raw[o + (ph < 2 ? 0 : 1)]) == 0xffffffffu) t = 0;
+    if (ph >= 2) t ^= 0x80000000u;
+    const u32 field = (ph & 1) ? (t >> 16) : (t & 0xffffu);
+    return (u64)(field % (u32)range);
+  }
   const u64 w = rng_word(raw, out0, pos >> 2);
   const int sh = (int)(pos & 3) * 16;
-  if (wu == 1) return (u64)(((u32)(w >> sh) & 0xffffu) % (u32)range);
   if (wu == 2) return (u64)((u32)(w >> sh) % (u32)range);
   return w % range;
 }

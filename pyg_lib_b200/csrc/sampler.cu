@@ -180,19 +180,21 @@ __device__ __forceinline__ void pdl_enter(int id = 0) {
   if (id) tl_mark(id);
 }
 
-__device__ __forceinline__ u64 hash64(u64 x) {
-  x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33;
-  return x;
-}
-
 // open addressing, linear probing; returns the slot holding `key`
 __device__ __forceinline__ u32 table_insert(u64* keys, u64 mask, u64 key) {
-  u64 s = hash64(key) & mask;
+  // Fibonacci hashing: one multiply, top log2(capacity) bits (capacity = mask + 1 is a power of two >= 2)
+  u64 s = (key * 0x9E3779B97F4A7C15ull) >> (64 - __popcll(mask));
   while (true) {
     const u64 prev = atomicCAS(&keys[s], EMPTY, key);
     if (prev == EMPTY || prev == key) return (u32)s;
     s = (s + 1) & mask;
   }
+}
+
+// min-reduction without a return value, as one RED instruction: the addresses of a warp's inserts are almost
+// always distinct, so the match/elect/redux aggregation the compiler wraps around atomicMin only costs here
+__device__ __forceinline__ void red_min_u64(u64* addr, u64 v) {
+  asm volatile("red.global.min.u64 [%0], %1;" ::"l"(addr), "l"(v) : "memory");
 }
 
 __device__ __forceinline__ u64 make_key(i64 node, i64 batch, int disjoint) {
@@ -512,7 +514,7 @@ __global__ void __launch_bounds__(NT) k_count(const PassArgs a) {
 // when its random value was already CHOSEN by an earlier draw — but only through the chosen values: every lane
 // takes one draw and the conflicts are settled with g shuffles.  Fan-outs beyond 32 go in rounds of 32 and
 // re-read what earlier rounds emitted.
-template <typename idx_t>
+template <typename idx_t, bool PHASED>
 __device__ __forceinline__ void sample_node(const PassArgs& a, const NodeRec& r, i64 off, i64 pos0, i64 src_pos, i64 pbase,
                                             int g, int gl, int gbase, unsigned gmask) {
   const idx_t* __restrict__ col = (const idx_t*)a.col;
@@ -524,16 +526,16 @@ __device__ __forceinline__ void sample_node(const PassArgs& a, const NodeRec& r,
   const int mode = classify(deg, k, a.replace, &n_out, &n16, &n32, &n64);
   auto emit = [&](i64 j, i64 e) {
     const i64 p = off + j;
-    if (a.phase == 1) { a.eid[pbase + p] = e; return; }
+    if (PHASED && a.phase == 1) { a.eid[pbase + p] = e; return; }
     const i64 d = (i64)col[e];
     a.row[pbase + p] = src_pos;
     a.eid[pbase + p] = e;
     a.colv[pbase + p] = d;  // global id for now; the (deferred) lookup overwrites it with the local id
     const u32 s = table_insert(a.keys, a.mask, make_key(d, sbatch, a.disjoint));
-    atomicMin(&a.vals[s], POS_BASE + (u64)p);
+    red_min_u64(&a.vals[s], POS_BASE + (u64)p);
     a.eslot[p] = s;
   };
-  if (a.phase == 2) {
+  if (PHASED && a.phase == 2) {
     for (i64 j = gl; j < n_out; j += g) emit(j, a.eid[pbase + off + j]);
   } else if (mode == MODE_FULL) {
     for (i64 j = gl; j < deg; j += g) emit(j, rs + j);
@@ -544,27 +546,29 @@ __device__ __forceinline__ void sample_node(const PassArgs& a, const NodeRec& r,
       emit(j, rs + (i64)rng_draw(raw, out0, pos, wu, (u64)deg));
     }
   } else if (mode == MODE_FLOYD) {
-    const i64 lo = deg - k;  // draw j: range lo+1+j, fallback value lo+j
-    for (i64 c0 = 0; c0 < k; c0 += g) {
-      const i64 j = c0 + gl;
-      const bool act = j < k;
-      i64 rnd = -1, c = -1;
+    // (in-row offsets fit 32 bits: NodeRec::deg is u32, larger degrees are rejected by the host)
+    const u32 lo = (u32)(deg - k);  // draw j: range lo+1+j, fallback value lo+j
+    const u32 k32 = (u32)k;
+    for (u32 c0 = 0; c0 < k32; c0 += g) {
+      const u32 j = c0 + gl;
+      const bool act = j < k32;
+      u32 rnd = 0xffffffffu, c = 0xffffffffu;
       if (act) {
         int wu;
         const i64 pos = (n32 == 0 && n64 == 0) ? (wu = 1, pos0 + j) : rng_draw_start(pos0, n16, n32, j, &wu);
-        rnd = (i64)rng_draw(raw, out0, pos, wu, (u64)(lo + 1 + j));
+        rnd = (u32)rng_draw(raw, out0, pos, wu, (u64)lo + 1 + j);
         c = rnd;
         // already chosen in an earlier round of this node? (only when fanout > 32)
-        for (i64 t = 0; t < c0; ++t)
-          if (__ldcg(&a.eid[pbase + off + t]) - rs == rnd) { c = lo + j; break; }
+        for (u32 t = 0; t < c0; ++t)
+          if ((u32)(__ldcg(&a.eid[pbase + off + t]) - rs) == rnd) { c = lo + j; break; }
       }
-      const int lim = (int)((k - c0) < g ? (k - c0) : g);
+      const int lim = (int)((k32 - c0) < (u32)g ? (k32 - c0) : (u32)g);
       for (int jj = 0; jj < lim; ++jj) {
-        const i64 cj = __shfl_sync(gmask, c, gbase + jj);
+        const u32 cj = __shfl_sync(gmask, c, gbase + jj);
         if (act && gl > jj && rnd == cj) c = lo + j;
       }
       if (act) emit(j, rs + c);
-      if (c0 + g < k) __syncwarp(gmask);
+      if (c0 + g < k32) __syncwarp(gmask);
     }
   }
 }
@@ -605,7 +609,7 @@ __global__ void __launch_bounds__(NT, SAMPLE_MIN_BLOCKS) k_sample(const PassArgs
     const int ph = (int)(tpos & 3);
     const u32 pfv = ph == 0 ? r.pf[0] : (ph == 1 ? r.pf[1] : (ph == 2 ? r.pf[2] : r.pf[3]));
     // RNG position of the first draw; begin + i == local id of the source node (neighbor_kernel.cpp:453)
-    sample_node<idx_t>(a, r, off, tpos + pfv, begin + i, pbase, g, gl, gbase, gmask);
+    sample_node<idx_t, true>(a, r, off, tpos + pfv, begin + i, pbase, g, gl, gbase, gmask);
   }
   tl_mark(TL_SAMPLE | TL_END);
 }
@@ -635,7 +639,7 @@ __global__ void __launch_bounds__(NT) k_seed(const PassArgs a, const idx_t* __re
     a.dst_nodes[i] = v;
     if (a.disjoint) a.dst_batch[i] = batch0 + i;
     const u32 s = table_insert(a.keys, a.mask, make_key(v, batch0 + i, a.disjoint));
-    atomicMin(&a.vals[s], POS_BASE + (u64)i);
+    red_min_u64(&a.vals[s], POS_BASE + (u64)i);
     a.eslot[i] = s;
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -1044,7 +1048,7 @@ __global__ void __launch_bounds__(NT, SAMPLE_MIN_BLOCKS) k_sample_s(const PassAr
     const i64 off = (i64)s_off[tile] + r.loc_off;
     const int ph = (int)(tpos & 3);
     const u32 pfv = ph == 0 ? r.pf[0] : (ph == 1 ? r.pf[1] : (ph == 2 ? r.pf[2] : r.pf[3]));
-    sample_node<idx_t>(a, r, off, tpos + pfv, begin + i, pbase, g, gl, gbase, gmask);
+    sample_node<idx_t, false>(a, r, off, tpos + pfv, begin + i, pbase, g, gl, gbase, gmask);
   }
   tl_mark(TL_SAMPLE | TL_END);
 }
@@ -1230,7 +1234,7 @@ __global__ void __launch_bounds__(SEED_NT) k_seed_fused(const PassArgs a, const 
     a.dst_nodes[i] = v;
     if (a.disjoint) a.dst_batch[i] = batch0 + i;
     const u32 s = table_insert(a.keys, a.mask, make_key(v, batch0 + i, a.disjoint));
-    atomicMin(&a.vals[s], POS_BASE + (u64)i);
+    red_min_u64(&a.vals[s], POS_BASE + (u64)i);
     a.eslot[i] = s;
   }
   if (threadIdx.x == 0) s_carry = 0;
