@@ -286,7 +286,7 @@ def main():
         # the second-hop launch carries ~90% of the edges; report per-launch averages over both hops
         bytes_per_launch = BYTES_PER_EDGE * d_work / max(d_launches, 1)
         achieved = bytes_per_launch / (d_ms / max(d_launches, 1) * 1e-3) / 1e9 if d_ms > 0 else 0.0
-        line['roofline'] = {'bound': 'hbm', 'kernel': 'k_' + dom, 'achieved': achieved, 'peak': hbm_peak, 'unit': 'GB/s',
+        line['roofline'] = {'bound': 'hbm', 'kernel': 'k_' + dom + '_s' if dom != 'lookup' else 'k_lookup', 'achieved': achieved, 'peak': hbm_peak, 'unit': 'GB/s',
                             'frac': achieved / hbm_peak, 'traffic': traffic.get('k_' + dom), 'peak_source': peak_src,
                             'avg_launch_us': 1e3 * d_ms / max(d_launches, 1),
                             'bytes_per_launch': bytes_per_launch,
