@@ -231,6 +231,28 @@ int pygb200_neighbor_sample_run(pygb200_sampler* s, const void* rowptr, const vo
                                 int64_t* edges_per_hop, int64_t* n_nodes, int64_t* n_edges,
                                 void* stream);
 
+/* ---------------------------------------------------------------------------------- subgraph
+ * Induced subgraph of the CSR graph (rowptr, col) on `nodes` — replaces subgraph_kernel
+ * (pyg_lib/csrc/sampler/cpu/subgraph_kernel.cpp:13-89; schema pyg::subgraph, sampler/subgraph.cpp:28-32).
+ * `nodes` [n] (same index dtype as rowptr/col; may repeat, need not be sorted) are numbered in first-occurrence
+ * order like Mapper::fill (mapper.h:29-53); output row i lists, in CSR order, the neighbours of nodes[i] that are
+ * in the set, as those ids.  Two calls, because the caller allocates the result between them like the reference
+ * does (`:59-64`):
+ *   pygb200_subgraph_count  builds the id map, writes out_rowptr [n+1] (device, index dtype) and returns the
+ *                           number of kept edges (one host sync); PYGB200_ERR_ARG for a node outside
+ *                           [0, num_nodes);
+ *   pygb200_subgraph_fill   with the same rowptr/col/nodes: writes out_col [n_edges] and, unless NULL,
+ *                           out_edge_id [n_edges] (positions in `col`), then resets the map.
+ * A handle owns the map and scratch (device of the creating thread; one per stream; serialises its calls). */
+typedef struct pygb200_subgraph pygb200_subgraph;
+int pygb200_subgraph_create(pygb200_subgraph** out);
+void pygb200_subgraph_destroy(pygb200_subgraph* h);
+int pygb200_subgraph_count(pygb200_subgraph* h, const void* rowptr, const void* col, int64_t num_nodes,
+                           const void* nodes, int64_t n, int index32, void* out_rowptr, int64_t* n_edges_out,
+                           void* stream);
+int pygb200_subgraph_fill(pygb200_subgraph* h, const void* rowptr, const void* col, const void* nodes, int64_t n,
+                          int index32, void* out_col, void* out_edge_id, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -292,3 +292,34 @@ def grouped_matmul(inputs: List[torch.Tensor], others: List[torch.Tensor],
 
 def num_threads() -> int:
     return int(lib().oracle_num_threads())
+
+
+def subgraph(rowptr: torch.Tensor, col: torch.Tensor, nodes: torch.Tensor,
+             return_edge_id: bool = True) -> Tuple[torch.Tensor, torch.Tensor, Optional[torch.Tensor]]:
+    """Oracle for pyg_lib.sampler.subgraph (numpy restatement of pyg_lib/csrc/sampler/cpu/subgraph_kernel.cpp:13-89).
+
+    `nodes` are numbered by `Mapper::fill` (mapper.h:49-53,29-46): dense ids in first-occurrence order, a
+    repeated node keeps the id of its first occurrence but still gets its own output row.  Row i lists, in CSR
+    order, the neighbours of nodes[i] that are in the set (`:41-52,66-82`), mapped to those ids; `edge_id` is the
+    position of the kept edge in `col`."""
+    dt = nodes.dtype
+    rp, cl, nd = _i64(rowptr), _i64(col), _i64(nodes)
+    ids: Dict[int, int] = {}
+    for v in nd.tolist():
+        if v not in ids:
+            ids[v] = len(ids)
+    lut = np.full(int(rp.shape[0]) - 1, -1, dtype=np.int64)
+    for v, i in ids.items():
+        lut[v] = i
+    out_rowptr = np.zeros(nd.shape[0] + 1, dtype=np.int64)
+    cols, eids = [], []
+    for i, v in enumerate(nd.tolist()):
+        j = np.arange(rp[v], rp[v + 1], dtype=np.int64)
+        w = lut[cl[j]]
+        keep = w >= 0
+        cols.append(w[keep]); eids.append(j[keep])
+        out_rowptr[i + 1] = out_rowptr[i] + int(keep.sum())
+    out_col = np.concatenate(cols) if cols else np.zeros(0, dtype=np.int64)
+    out_eid = np.concatenate(eids) if eids else np.zeros(0, dtype=np.int64)
+    return (torch.from_numpy(out_rowptr).to(dt), torch.from_numpy(out_col).to(dt),
+            torch.from_numpy(out_eid).to(dt) if return_edge_id else None)

@@ -20,8 +20,8 @@ CUDA_HOME = os.environ.get('CUDA_HOME', '/usr/local/cuda')
 NVCC = osp.join(CUDA_HOME, 'bin', 'nvcc')
 CXX = '/usr/bin/g++' if osp.exists('/usr/bin/g++') else 'g++'
 
-CU_SOURCES = ['sampler.cu', 'matmul.cu', 'matmul_tcgen05.cu']
-TORCH_SOURCES = ['torch/library.cpp', 'torch/sampler_op.cpp', 'torch/matmul_op.cpp']
+CU_SOURCES = ['sampler.cu', 'subgraph.cu', 'matmul.cu', 'matmul_tcgen05.cu']
+TORCH_SOURCES = ['torch/library.cpp', 'torch/sampler_op.cpp', 'torch/subgraph_op.cpp', 'torch/matmul_op.cpp']
 HEADERS = ['common.cuh', 'mt19937.cuh', 'torch/common.h', '../../include/pyg_b200.h']
 
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',

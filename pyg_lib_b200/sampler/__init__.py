@@ -104,4 +104,21 @@ def hetero_neighbor_sample(
 
 from .dist import dist_neighbor_sample  # noqa: E402  (multi-GPU, frontier-sharded)
 
-__all__ = ['neighbor_sample', 'hetero_neighbor_sample', 'dist_neighbor_sample']
+__all__ = ['neighbor_sample', 'hetero_neighbor_sample', 'subgraph', 'dist_neighbor_sample']
+
+
+_subgraph_op = _LazyOp('subgraph')
+
+
+def subgraph(
+    rowptr: Tensor,
+    col: Tensor,
+    nodes: Tensor,
+    return_edge_id: bool = True,
+) -> Tuple[Tensor, Tensor, Optional[Tensor]]:
+    r"""Returns the induced subgraph of the graph given by :obj:`(rowptr, col)`, containing only the nodes in
+    :obj:`nodes` — same signature and result as the reference (pyg_lib/sampler/__init__.py:203-225): compressed row
+    pointers over :obj:`nodes` (in the given order), target ids relabelled by first occurrence in :obj:`nodes`, and
+    (optionally) the positions of the kept edges in :obj:`col`.  CUDA tensors only."""
+    return _subgraph_op(rowptr, col, nodes, return_edge_id)
+

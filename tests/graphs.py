@@ -226,3 +226,32 @@ def build_matmul(case: dict, device='cpu'):
     x = torch.randn(case['N'], case['K'], generator=g).to(dt)
     w = (torch.randn(B, case['K'], case['M'], generator=g) / case['K'] ** 0.5).to(dt)
     return x.to(device), ptr, w.to(device)
+
+
+# pyg::subgraph cases: (graph spec as in HOMO_CASES, how the node set is drawn)
+SUBGRAPH_CASES: Dict[str, dict] = {
+    # known-answer vector of test/csrc/sampler/test_subgraph.cpp:7-24 (cycle graph, nodes 1..4)
+    'cycle_kat': dict(graph=('cycle', 6), nodes=[1, 2, 3, 4]),
+    'cycle_dups_unsorted': dict(graph=('cycle', 6), nodes=[4, 1, 4, 2, 1]),
+    'empty_set': dict(graph=('cycle', 6), nodes=[]),
+    'rand_small': dict(graph=('rand', 2000, 20, 1), n_nodes=300, seed=5),
+    'rand_dense_set': dict(graph=('rand', 1500, 30, 2), n_nodes=1200, seed=6),
+    'rand_dups': dict(graph=('rand', 3000, 12, 3), n_nodes=500, seed=7, dup=200),
+    'bigdeg': dict(graph=('rand', 400, 10, 7, [(5, 70000), (77, 65540)]), n_nodes=150, seed=8, must=[5, 77]),
+}
+
+
+def build_subgraph(case):
+    """(rowptr, col, nodes) of a SUBGRAPH_CASES entry (int64 CPU tensors)."""
+    rowptr, col, _ = build_homo(dict(graph=case['graph'], seeds=[0], num_neighbors=[1], rng_seed=0))
+    n = rowptr.numel() - 1
+    if 'nodes' in case:
+        return rowptr, col, torch.tensor(case['nodes'], dtype=torch.int64)
+    g = torch.Generator().manual_seed(case['seed'])
+    nodes = torch.randperm(n, generator=g)[:case['n_nodes']]
+    if 'must' in case:
+        nodes = torch.cat([torch.tensor(case['must'], dtype=torch.int64), nodes[~torch.isin(nodes, torch.tensor(case['must']))]])
+    if case.get('dup', 0):
+        extra = nodes[torch.randint(0, nodes.numel(), (case['dup'],), generator=g)]
+        nodes = torch.cat([nodes, extra])[torch.randperm(nodes.numel() + case['dup'], generator=g)]
+    return rowptr, col, nodes.to(torch.int64)

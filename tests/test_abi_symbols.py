@@ -58,6 +58,8 @@ def test_schemas_match_reference(built):
     assert h.startswith('pyg::hetero_neighbor_sample(str[] node_types, (str, str, str)[] edge_types, Dict(str, Tensor) rowptr_dict')
     assert h.endswith('-> (Dict(str, Tensor), Dict(str, Tensor), Dict(str, Tensor), Dict(str, Tensor)?, Dict(str, int[]), Dict(str, int[]))')
     assert str(torch.ops.pyg.segment_matmul.default._schema) == 'pyg::segment_matmul(Tensor input, Tensor ptr, Tensor other) -> Tensor'
+    assert str(torch.ops.pyg.subgraph.default._schema) == ('pyg::subgraph(Tensor rowptr, Tensor col, Tensor nodes, bool return_edge_id) '
+                                                            '-> (Tensor, Tensor, Tensor?)')   # sampler/subgraph.cpp:28-32
     assert str(torch.ops.pyg.grouped_matmul.default._schema) == 'pyg::grouped_matmul(Tensor[] input, Tensor[] other) -> Tensor[]'
     assert torch.ops.pyg.cuda_version() >= 12000
 

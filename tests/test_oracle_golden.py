@@ -168,3 +168,30 @@ def test_kat_edge_temporal():
     out2 = O.neighbor_sample(rowptr, col, torch.arange(2, 4), [1, 1], edge_time=edge_time,
                              seed_time=torch.tensor([-1, -1]), disjoint=True, replace=True)
     assert out2[0].numel() == 0 and out2[2].flatten().tolist() == [0, 2, 1, 3]
+
+
+# ------------------------------------------------------------------------------------ subgraph
+import os.path as osp  # noqa: E402
+from graphs import SUBGRAPH_CASES, build_subgraph  # noqa: E402
+
+
+@pytest.fixture(scope='module')
+def subgraph_golden():
+    return np.load(osp.join(osp.dirname(osp.abspath(__file__)), 'golden', 'subgraph_outputs.npz'))
+
+
+def test_subgraph_kat():
+    """test/csrc/sampler/test_subgraph.cpp:7-24."""
+    rowptr, col, nodes = build_subgraph(SUBGRAPH_CASES['cycle_kat'])
+    r = O.subgraph(rowptr, col, nodes)
+    assert r[0].tolist() == [0, 1, 3, 5, 6] and r[1].tolist() == [1, 0, 2, 1, 3, 2] and r[2].tolist() == [3, 4, 5, 6, 7, 8]
+
+
+@pytest.mark.parametrize('name', list(SUBGRAPH_CASES))
+def test_subgraph_oracle_matches_reference_fixture(subgraph_golden, name):
+    rowptr, col, nodes = build_subgraph(SUBGRAPH_CASES[name])
+    r = O.subgraph(rowptr, col, nodes)
+    assert np.array_equal(r[0].numpy(), subgraph_golden[f'{name}/rowptr'])
+    assert np.array_equal(r[1].numpy(), subgraph_golden[f'{name}/col'])
+    assert np.array_equal(r[2].numpy(), subgraph_golden[f'{name}/eid'])
+    assert O.subgraph(rowptr, col, nodes, return_edge_id=False)[2] is None
