@@ -44,6 +44,11 @@ extern "C" {
 #define PYGB200_S_INDEX32 4u      /* rowptr/col/seed are int32 (else int64) */
 #define PYGB200_S_DEFER_CLEANUP 8u /* single node type only: the hash-table reset is done by the following
                                      pygb200_sampler_export_all (or by the next run) instead of its own launch */
+#define PYGB200_S_NO_DEDUP 16u     /* distributed one-hop sampling (dist_neighbor_sample_kernel, neighbor_kernel.cpp:957-978,
+                                     296-303): one node type / relation / hop; sampled neighbours are NOT mapped — after
+                                     the run `col` of pygb200_sampler_export_edges holds their GLOBAL ids in emission
+                                     order, `row` the index of the seed they came from, and
+                                     pygb200_sampler_export_cumsum gives cumsum_neighbors_per_node */
 
 const char* pygb200_last_error(void);
 int pygb200_cuda_version(void);          /* CUDA_VERSION the library was built with
@@ -207,6 +212,10 @@ int pygb200_sampler_bind_outputs(pygb200_sampler* s, int32_t T, int32_t R, void*
                                  void* const* edge_id, void* const* node, const int64_t* edge_cap,
                                  const int64_t* node_cap);
 int pygb200_sampler_outputs_direct(pygb200_sampler* s);
+
+/* After a PYGB200_S_NO_DEDUP run: out [n_seeds + 1] (int64, device) = n_seeds + number of edges emitted by seeds
+ * 0..i-1, i.e. the reference's cumsum_neighbors_per_node (neighbor_kernel.cpp:386-388,446-492). */
+int pygb200_sampler_export_cumsum(pygb200_sampler* s, int64_t* out, void* stream);
 
 /* Asynchronous copies (cast to int32 when index32 != 0) of the last run's results into caller
  * buffers of exactly n_edges[r] / n_nodes[t] elements.  row = local index of the source (frontier)

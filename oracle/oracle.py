@@ -323,3 +323,26 @@ def subgraph(rowptr: torch.Tensor, col: torch.Tensor, nodes: torch.Tensor,
     out_eid = np.concatenate(eids) if eids else np.zeros(0, dtype=np.int64)
     return (torch.from_numpy(out_rowptr).to(dt), torch.from_numpy(out_col).to(dt),
             torch.from_numpy(out_eid).to(dt) if return_edge_id else None)
+
+
+def dist_neighbor_sample(rowptr, col, seed, num_neighbors: int, node_time=None, edge_time=None, seed_time=None,
+                         edge_weight=None, csc: bool = False, replace: bool = False, directed: bool = True,
+                         disjoint: bool = False, temporal_strategy: str = 'uniform', mt: Optional[MTState] = None):
+    """Oracle for pyg::dist_neighbor_sample (dist_neighbor_sample_kernel, neighbor_kernel.cpp:957-978).
+
+    The distributed variant is the ordinary one-hop `sample<>` with `distributed=true`: same frontier order, same
+    draws, but `add` pushes every sampled neighbour unmapped (`:296-303`) and the loop records
+    cumsum_neighbors_per_node (`:386-388,446-492`).  So it is restated on top of the one-hop oracle: edges come out in
+    the same order, `col[edge_id[p]]` is the global id of edge p's neighbour, `row[p]` the seed it belongs to."""
+    r = neighbor_sample(rowptr, col, seed, [int(num_neighbors)], node_time, edge_time, seed_time, edge_weight, False, replace,
+                        directed, disjoint, temporal_strategy, True, mt)
+    row, eid = r[0], r[3]
+    S = int(seed.numel())
+    glob = col[eid.to(torch.int64)].to(seed.dtype)      # global id of every sampled neighbour (edge id = position in col)
+    if disjoint:                                        # (batch, node): a neighbour inherits the batch = index of its seed
+        nodes = torch.stack([torch.cat([torch.arange(S, dtype=seed.dtype), row.to(seed.dtype)]), torch.cat([seed, glob])], 1)
+    else:
+        nodes = torch.cat([seed, glob])
+    per_seed = torch.bincount(row.to(torch.int64), minlength=S)
+    cumsum = [S] + (S + torch.cumsum(per_seed, 0)).tolist()
+    return nodes, eid, cumsum

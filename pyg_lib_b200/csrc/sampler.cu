@@ -531,6 +531,7 @@ __device__ __forceinline__ void sample_node(const PassArgs& a, const NodeRec& r,
     a.row[pbase + p] = src_pos;
     a.eid[pbase + p] = e;
     a.colv[pbase + p] = d;  // global id for now; the (deferred) lookup overwrites it with the local id
+    if (PHASED && a.phase == 3) return;   // distributed one-hop sampling: no mapping at all (neighbor_kernel.cpp:296-303)
     const u32 s = table_insert(a.keys, a.mask, make_key(d, sbatch, a.disjoint));
     red_min_u64(&a.vals[s], POS_BASE + (u64)p);
     a.eslot[p] = s;
@@ -1279,6 +1280,14 @@ __global__ void __launch_bounds__(NT) k_cleanup(u64* keys, u64* vals, const u32*
   }
 }
 
+// pyg::dist_neighbor_sample: cumsum_neighbors_per_node = seeds, then seeds + edges emitted by seeds 0..i
+// (neighbor_kernel.cpp:386-388,446-492) from the records of the run's only pass
+__global__ void __launch_bounds__(NT) k_dist_cumsum(const NodeRec* __restrict__ rec, const i64* __restrict__ tile_off, i64 n_seeds, i64 n_edges,
+                                                     int have_pass, i64* __restrict__ out) {
+  for (i64 i = (i64)blockIdx.x * NT + threadIdx.x; i <= n_seeds; i += (i64)gridDim.x * NT)
+    out[i] = n_seeds + (i == n_seeds ? n_edges : (have_pass ? tile_off[i / NT] + (i64)rec[i].loc_off : 0));
+}
+
 // table growth (only the synced path): move every listed node's entry into the new table
 __global__ void __launch_bounds__(NT) k_rehash(const u64* __restrict__ old_keys, const u64* __restrict__ old_vals,
                                                u64* new_keys, u64* new_vals, u64 new_mask, u32* slots, i64 n) {
@@ -1378,6 +1387,8 @@ struct pygb200_sampler {
   // local cols / edge ids / node lists straight into them, so no export pass follows
   struct Bound { std::vector<i64*> row, col, eid, node; std::vector<i64> ecap, ncap; bool armed = false; } bound;
   bool last_direct = false;   // the last run wrote into the bound arrays (exports are refused)
+  bool last_nodedup = false;  // the last run was a PYGB200_S_NO_DEDUP run (pygb200_sampler_export_cumsum is valid)
+  i64 nd_seeds = 0;
   DevBuf eslot, erank, rec, tile_out, tile_func, tile_off, tile_pos, mtile, raw, st, gen;
   i64* st_host = nullptr;   // pinned + mapped mirror of the state buffer (k_final writes it directly)
   i64* st_host_dev = nullptr;   // device-side address of st_host
@@ -1776,6 +1787,10 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
                  PYGB200_ERR_ARG, "Seed time needs to be specified");
   }
   const bool sharded = shard != nullptr && shard->world > 1;
+  const bool nodedup = (flags & PYGB200_S_NO_DEDUP) != 0;
+  if (nodedup) PYGB_CHECK(T == 1 && R == 1 && L == 1 && !sharded, PYGB200_ERR_ARG,
+                          "PYGB200_S_NO_DEDUP (distributed one-hop sampling) takes one node type, one relation, one hop");
+  s->last_nodedup = false;
   if (sharded) {
     PYGB_CHECK(!synced, PYGB200_ERR_UNSUPPORTED, "frontier-sharded sampling needs bounded fan-outs (no -1, < 8 GiB worst case)");
     PYGB_CHECK(shard->world <= MAX_SHARDS && shard->rank >= 0 && shard->rank < shard->world && shard->allgather,
@@ -1783,7 +1798,7 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
   }
 
   // ---- results straight into the caller's arrays?  (bounded int64 non-disjoint runs only; the binding is one-shot)
-  bool direct = s->bound.armed && !synced && !sharded && !idx32 && !disjoint && (int)s->bound.node.size() == T &&
+  bool direct = s->bound.armed && !synced && !sharded && !nodedup && !idx32 && !disjoint && (int)s->bound.node.size() == T &&
                 (int)s->bound.row.size() == R;
   s->bound.armed = false;
   s->last_direct = false;
@@ -1979,7 +1994,7 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
   if (any_time) if (int e = s->seed_times.ensure((size_t)std::max<i64>(total_seeds, 1) * 8, 0, st)) return e;
   // ---- latency path?  (k_*_s kernels: write-once counters, no serial sections; see above k_count_s)
   static const bool no_lat = getenv("PYGB200_NO_LATENCY_PATH") != nullptr;
-  bool lat = !synced && !sharded && L > 0 && !no_lat;
+  bool lat = !synced && !sharded && !nodedup && L > 0 && !no_lat;
   for (int t = 0; t < T && lat; ++t) lat = n_seeds[t] <= SEED_FUSED_MAX;
   for (int h = 0; h < L && lat; ++h)
     for (int r = 0; r < R && lat; ++r) {
@@ -2147,6 +2162,12 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
         a.lk_colv = lk_colv; a.lk_vals = lk_vals;
         with_hop_end(a);
         if (int e = idx32 ? launch_count<int32_t>(s, a, Fb, lk_E, st) : launch_count<int64_t>(s, a, Fb, lk_E, st)) return e;
+        if (nodedup) {   // draw + gather only: global ids stay in `colv`, nothing is mapped, no lookup follows
+          PassArgs d = a;
+          d.phase = 3;
+          if (int e = idx32 ? launch_sample<int32_t>(s, d, Fb, Eb, st) : launch_sample<int64_t>(s, d, Fb, Eb, st)) return e;
+          continue;
+        }
         if (!sharded) {
           if (int e = idx32 ? launch_rest<int32_t>(s, a, Fb, Eb, false, st) : launch_rest<int64_t>(s, a, Fb, Eb, false, st)) return e;
         } else {
@@ -2204,6 +2225,11 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
         a = make_args(src_t, dst_t, r);  // pointers may have moved
         a.fanout = k;
         a.o_eph = lay.o_eph + r * L + h;
+        if (nodedup) {
+          a.phase = 3;
+          if (int e = idx32 ? launch_sample<int32_t>(s, a, F, E, st) : launch_sample<int64_t>(s, a, F, E, st)) return e;
+          continue;
+        }
         with_hop_end(a);
         if (int e = idx32 ? launch_rest<int32_t>(s, a, F, E, true, st) : launch_rest<int64_t>(s, a, F, E, true, st)) return e;
         if (r == last_r) hop_closed = true;
@@ -2231,6 +2257,8 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
   // PYGB200_S_DEFER_CLEANUP (homogeneous fast path) it rides along with pygb200_sampler_export_all instead.
   s->cleanup_pending = (flags & PYGB200_S_DEFER_CLEANUP) && T == 1 && !direct;
   s->last_direct = direct;
+  s->last_nodedup = nodedup;
+  s->nd_seeds = nodedup ? n_seeds[0] : 0;
   for (int t = 0; t < T && !s->cleanup_pending; ++t) {
     auto& tb = s->types[t];
     const i64 cap_nodes = (i64)(tb.slot.cap / 4);
@@ -2424,6 +2452,17 @@ extern "C" int pygb200_sampler_outputs_direct(pygb200_sampler* s) {
   if (!s) return 0;
   std::lock_guard<std::mutex> lock(s->mu);
   return s->last_direct ? 1 : 0;
+}
+
+extern "C" int pygb200_sampler_export_cumsum(pygb200_sampler* s, int64_t* out, void* stream) {
+  PYGB_CHECK(s && out, PYGB200_ERR_ARG, "export_cumsum: null argument");
+  PYGB_CHECK(s->last_nodedup, PYGB200_ERR_ARG, "export_cumsum: the last run was not a PYGB200_S_NO_DEDUP run");
+  cudaStream_t st = (cudaStream_t)stream;
+  const i64 ne = s->rels[0].n_edges;
+  k_dist_cumsum<<<grid_for(s->nd_seeds + 1, NT, s->sm_count), NT, 0, st>>>(s->rec.as<NodeRec>(), s->tile_off.as<i64>(), s->nd_seeds, ne,
+                                                                            ne > 0 ? 1 : 0, reinterpret_cast<i64*>(out));
+  PYGB_LAUNCH_CHECK();
+  return PYGB200_OK;
 }
 
 extern "C" int pygb200_sampler_export_edges(pygb200_sampler* s, int32_t rel, void* row_out, void* col_out,

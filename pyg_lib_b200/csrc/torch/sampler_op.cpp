@@ -192,6 +192,67 @@ neighbor_sample_cuda(const at::Tensor& rowptr, const at::Tensor& col, const at::
   return std::make_tuple(row, colv, node, eid, nph, eph);
 }
 
+// pyg::dist_neighbor_sample (dist_neighbor_sample_kernel, neighbor_kernel.cpp:957-978): ONE hop from `seed` with the
+// same draws as neighbor_sample, but nothing is mapped: node ids = the seeds followed by every sampled neighbour's
+// GLOBAL id in emission order ((batch, node) pairs if disjoint), their edge ids, and cumsum_neighbors_per_node.
+std::tuple<at::Tensor, at::Tensor, std::vector<int64_t>>
+dist_neighbor_sample_cuda(const at::Tensor& rowptr, const at::Tensor& col, const at::Tensor& seed, int64_t num_neighbors,
+                          const std::optional<at::Tensor>& node_time, const std::optional<at::Tensor>& edge_time,
+                          const std::optional<at::Tensor>& seed_time, const std::optional<at::Tensor>& edge_weight, bool csc,
+                          bool replace, bool directed, bool disjoint, std::string temporal_strategy) {
+  TORCH_CHECK(temporal_strategy == "uniform" || temporal_strategy == "last", "No valid temporal strategy found");
+  check_arguments(node_time.has_value(), edge_time.has_value(), seed_time.has_value(), edge_weight.has_value(), disjoint);
+  TORCH_CHECK(seed.is_cuda(), "pyg_lib_b200: dist_neighbor_sample expects CUDA tensors (no CPU fallback)");
+  const auto st = seed.scalar_type();
+  TORCH_CHECK(st == at::kLong || st == at::kInt, "dist_neighbor_sample: index tensors must be int64 or int32");
+  check_index_tensor(rowptr, "rowptr", st, seed.device());
+  check_index_tensor(col, "col", st, seed.device());
+  check_index_tensor(seed, "seed", st, seed.device());
+  TORCH_CHECK(rowptr.numel() >= 1, "'rowptr' must have at least one element");
+  (void)csc;  // no (row, col) pair is returned
+
+  c10::cuda::CUDAGuard guard(seed.device());
+  cudaStream_t stream = at::cuda::getCurrentCUDAStream();
+  pygb200_sampler* s = get_sampler(seed.device().index(), stream);
+  const bool idx32 = st == at::kInt;
+  const unsigned flags = (replace ? PYGB200_S_REPLACE : 0u) | (disjoint ? PYGB200_S_DISJOINT : 0u) | (idx32 ? PYGB200_S_INDEX32 : 0u) |
+                         PYGB200_S_NO_DEDUP;
+  const int64_t S = seed.numel();
+  int64_t nph[2] = {0, 0}, eph[1] = {0}, n_nodes = 0, n_edges = 0;
+  {
+    const int64_t* nt = node_time.has_value() ? time_ptr(*node_time, "node_time", seed.device()) : nullptr;
+    const int64_t* et = edge_time.has_value() ? time_ptr(*edge_time, "edge_time", seed.device()) : nullptr;
+    const int64_t* stt = seed_time.has_value() ? time_ptr(*seed_time, "seed_time", seed.device()) : nullptr;
+    if (stt) TORCH_CHECK(seed_time->numel() == S, "'seed_time' must have one entry per seed");
+    if (et) TORCH_CHECK(edge_time->numel() == col.numel(), "'edge_time' must have one entry per edge");
+    pygb200_temporal tmp{&nt, &et, &stt, temporal_strategy == "last" ? 1 : 0};
+    pygb200_relation rel{rowptr.data_ptr(), col.data_ptr(), rowptr.numel() - 1, col.numel(), 0, 0};
+    const void* seeds[1] = {seed.data_ptr()};
+    CpuEngine eng;
+    PYGB_TORCH_CALL(pygb200_sampler_run_temporal(s, 1, 1, 1, &rel, seeds, &S, &num_neighbors, flags, &eng.mt, nph, eph, &n_nodes,
+                                                 &n_edges, stream, (nt || et) ? &tmp : nullptr));
+    eng.commit();
+  }
+  TORCH_CHECK(directed, "Undirected subgraphs not yet supported");  // neighbor_kernel.cpp:501
+  const auto opt = seed.options();
+  at::Tensor eid = at::empty({n_edges}, opt);
+  at::Tensor cum = at::empty({S + 1}, opt.dtype(at::kLong));
+  at::Tensor node;
+  if (!disjoint) {
+    node = at::empty({S + n_edges}, opt);
+    node.narrow(0, 0, S).copy_(seed);
+    PYGB_TORCH_CALL(pygb200_sampler_export_edges(s, 0, nullptr, node.narrow(0, S, n_edges).data_ptr(), eid.data_ptr(), idx32, stream));
+  } else {   // (batch, node): a seed is its own batch; a neighbour inherits the batch (= index) of the seed it came from
+    at::Tensor row = at::empty({n_edges}, opt), dst = at::empty({n_edges}, opt);
+    PYGB_TORCH_CALL(pygb200_sampler_export_edges(s, 0, row.data_ptr(), dst.data_ptr(), eid.data_ptr(), idx32, stream));
+    node = at::stack({at::cat({at::arange(S, opt), row}), at::cat({seed, dst})}, 1);
+  }
+  PYGB_TORCH_CALL(pygb200_sampler_export_cumsum(s, cum.data_ptr<int64_t>(), stream));
+  const at::Tensor cum_host = cum.cpu();   // the API returns a host list (one more sync, as many values as seeds + 1)
+  const int64_t* cp = cum_host.data_ptr<int64_t>();
+  return std::make_tuple(node, eid, std::vector<int64_t>(cp, cp + S + 1));
+}
+
 std::tuple<c10::Dict<rel_type, at::Tensor>, c10::Dict<rel_type, at::Tensor>, c10::Dict<node_type, at::Tensor>,
            std::optional<c10::Dict<rel_type, at::Tensor>>, c10::Dict<node_type, std::vector<int64_t>>,
            c10::Dict<rel_type, std::vector<int64_t>>>
@@ -370,10 +431,17 @@ TORCH_LIBRARY_FRAGMENT(pyg, m) {
       "str temporal_strategy = 'uniform', bool return_edge_id = True) -> "
       "(Dict(str, Tensor), Dict(str, Tensor), Dict(str, Tensor), "
       "Dict(str, Tensor)?, Dict(str, int[]), Dict(str, int[]))"));
+  m.def(TORCH_SELECTIVE_SCHEMA(   // pyg_lib/csrc/sampler/neighbor.cpp:148-153
+      "pyg::dist_neighbor_sample(Tensor rowptr, Tensor col, Tensor seed, int "
+      "num_neighbors, Tensor? node_time = None, Tensor? edge_time = None, "
+      "Tensor? seed_time = None, Tensor? edge_weight = None, bool csc = False, "
+      "bool replace = False, bool directed = True, bool disjoint = False, "
+      "str temporal_strategy = 'uniform') -> (Tensor, Tensor, int[])"));
 }
 
 TORCH_LIBRARY_IMPL(pyg, CUDA, m) {
   m.impl(TORCH_SELECTIVE_NAME("pyg::neighbor_sample"), TORCH_FN(neighbor_sample_cuda));
+  m.impl(TORCH_SELECTIVE_NAME("pyg::dist_neighbor_sample"), TORCH_FN(dist_neighbor_sample_cuda));
 }
 
 TORCH_LIBRARY_IMPL(pyg, BackendSelect, m) {

@@ -255,3 +255,25 @@ def build_subgraph(case):
         extra = nodes[torch.randint(0, nodes.numel(), (case['dup'],), generator=g)]
         nodes = torch.cat([nodes, extra])[torch.randperm(nodes.numel() + case['dup'], generator=g)]
     return rowptr, col, nodes.to(torch.int64)
+
+
+# pyg::dist_neighbor_sample cases (one hop, no mapping); first four = test/csrc/sampler/test_dist_neighbor.cpp
+DIST_CASES: Dict[str, dict] = {
+    'cycle_full': dict(graph=('cycle', 6), seeds=[2, 3], k=-1, rng_seed=0),
+    'cycle_norep': dict(graph=('cycle', 6), seeds=[2, 3], k=1, rng_seed=123456),
+    'cycle_rep': dict(graph=('cycle', 6), seeds=[2, 3], k=2, rng_seed=123456, replace=True),
+    'cycle_disjoint': dict(graph=('cycle', 6), seeds=[2, 3], k=2, rng_seed=0, disjoint=True),
+    'rand_15': dict(graph=('rand', 2000, 20, 1), n_seeds=64, k=15, rng_seed=12345),
+    'rand_15_rep': dict(graph=('rand', 2000, 20, 1), n_seeds=64, k=15, rng_seed=12345, replace=True),
+    'rand_all': dict(graph=('rand', 1500, 6, 4), n_seeds=40, k=-1, rng_seed=5),
+    'rand_k40_disjoint': dict(graph=('rand', 1000, 60, 5), n_seeds=8, k=40, rng_seed=11, disjoint=True),
+    'rand_dupseeds': dict(graph=('rand', 2000, 20, 1), seeds=[4, 4, 9, 4, 9, 1, 1500, 4], k=5, rng_seed=1),
+    'rand_zero': dict(graph=('rand', 2000, 20, 1), n_seeds=16, k=0, rng_seed=3),
+    'bigdeg': dict(graph=('rand', 400, 10, 7, [(5, 70000), (77, 65540), (100, 65536), (101, 65535)]),
+                   seeds=[5, 3, 77, 100, 8, 101, 5], k=9, rng_seed=21),
+}
+
+
+def build_dist(case):
+    """(rowptr, col, seed) of a DIST_CASES entry."""
+    return build_homo(dict(case, num_neighbors=[case['k']]))

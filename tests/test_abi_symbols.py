@@ -60,6 +60,10 @@ def test_schemas_match_reference(built):
     assert str(torch.ops.pyg.segment_matmul.default._schema) == 'pyg::segment_matmul(Tensor input, Tensor ptr, Tensor other) -> Tensor'
     assert str(torch.ops.pyg.subgraph.default._schema) == ('pyg::subgraph(Tensor rowptr, Tensor col, Tensor nodes, bool return_edge_id) '
                                                             '-> (Tensor, Tensor, Tensor?)')   # sampler/subgraph.cpp:28-32
+    assert str(torch.ops.pyg.dist_neighbor_sample.default._schema) == (   # sampler/neighbor.cpp:148-153
+        'pyg::dist_neighbor_sample(Tensor rowptr, Tensor col, Tensor seed, int num_neighbors, Tensor? node_time=None, '
+        'Tensor? edge_time=None, Tensor? seed_time=None, Tensor? edge_weight=None, bool csc=False, bool replace=False, '
+        'bool directed=True, bool disjoint=False, str temporal_strategy="uniform") -> (Tensor, Tensor, int[])')
     assert str(torch.ops.pyg.grouped_matmul.default._schema) == 'pyg::grouped_matmul(Tensor[] input, Tensor[] other) -> Tensor[]'
     assert torch.ops.pyg.cuda_version() >= 12000
 

@@ -195,3 +195,37 @@ def test_subgraph_oracle_matches_reference_fixture(subgraph_golden, name):
     assert np.array_equal(r[1].numpy(), subgraph_golden[f'{name}/col'])
     assert np.array_equal(r[2].numpy(), subgraph_golden[f'{name}/eid'])
     assert O.subgraph(rowptr, col, nodes, return_edge_id=False)[2] is None
+
+
+# ------------------------------------------------------------------------------------ dist_neighbor_sample
+from graphs import DIST_CASES, build_dist  # noqa: E402
+
+
+@pytest.fixture(scope='module')
+def dist_golden():
+    return np.load(osp.join(osp.dirname(osp.abspath(__file__)), 'golden', 'dist_outputs.npz'))
+
+
+def test_dist_neighbor_sample_kats():
+    """test/csrc/sampler/test_dist_neighbor.cpp:8-77 (full, without / with replacement)."""
+    rowptr, col = cycle_graph(6)
+    r = O.dist_neighbor_sample(rowptr, col, torch.arange(2, 4), -1)
+    assert r[0].tolist() == [2, 3, 1, 3, 2, 4] and r[1].tolist() == [4, 5, 6, 7] and r[2] == [2, 4, 6]
+    torch.manual_seed(123456)
+    r = O.dist_neighbor_sample(rowptr, col, torch.arange(2, 4), 1)
+    assert r[0].tolist() == [2, 3, 1, 4] and r[1].tolist() == [4, 7] and r[2] == [2, 3, 4]
+    torch.manual_seed(123456)
+    r = O.dist_neighbor_sample(rowptr, col, torch.arange(2, 4), 2, replace=True)
+    assert r[0].tolist() == [2, 3, 1, 3, 4, 4] and r[1].tolist() == [4, 5, 7, 7] and r[2] == [2, 4, 6]
+
+
+@pytest.mark.parametrize('name', list(DIST_CASES))
+def test_dist_oracle_matches_reference_fixture(dist_golden, name):
+    case = DIST_CASES[name]
+    rowptr, col, seed = build_dist(case)
+    torch.manual_seed(case['rng_seed'])
+    r = O.dist_neighbor_sample(rowptr, col, seed, case['k'], replace=case.get('replace', False), disjoint=case.get('disjoint', False))
+    assert np.array_equal(r[0].numpy(), dist_golden[f'{name}/node'])
+    assert np.array_equal(r[1].numpy(), dist_golden[f'{name}/eid'])
+    assert list(r[2]) == dist_golden[f'{name}/cumsum'].tolist()
+    assert np.array_equal(torch.get_rng_state().numpy()[:24 + 624 * 8], dist_golden[f'{name}/rng_after'])

@@ -443,3 +443,49 @@ print('OK', n)
         env = dict(os.environ, **extra)
         out = subprocess.run([sys.executable, '-c', code], env=env, capture_output=True, text=True, timeout=600)
         assert out.returncode == 0 and 'OK' in out.stdout, (extra, out.stdout[-2000:], out.stderr[-4000:])
+
+
+# ------------------------------------------------------------------------------------ pyg::dist_neighbor_sample
+from graphs import DIST_CASES, build_dist  # noqa: E402
+
+
+@pytest.mark.parametrize('name', list(DIST_CASES))
+@pytest.mark.parametrize('dtype', [torch.int64, torch.int32])
+def test_dist_neighbor_sample_golden(lib, name, dtype):
+    """One hop without mapping (neighbor_kernel.cpp:957-978) vs fixtures made by the reference itself
+    (tests/golden/dist_outputs.npz), including the generator state afterwards."""
+    G = np.load(osp.join(osp.dirname(osp.abspath(__file__)), 'golden', 'dist_outputs.npz'))
+    case = DIST_CASES[name]
+    rowptr, col, seed = build_dist(case)
+    torch.manual_seed(case['rng_seed'])
+    out = torch.ops.pyg.dist_neighbor_sample(rowptr.to(DEV, dtype), col.to(DEV, dtype), seed.to(DEV, dtype), case['k'], None, None,
+                                             None, None, False, case.get('replace', False), True, case.get('disjoint', False),
+                                             'uniform')
+    assert out[0].dtype == dtype and out[1].dtype == dtype
+    assert np.array_equal(out[0].cpu().numpy(), G[f'{name}/node'])
+    assert np.array_equal(out[1].cpu().numpy(), G[f'{name}/eid'])
+    assert list(out[2]) == G[f'{name}/cumsum'].tolist()
+    assert np.array_equal(_rng_prefix(), G[f'{name}/rng_after'])
+
+
+def test_dist_neighbor_sample_then_neighbor_sample(lib):
+    """The no-mapping run shares the workspace and the persistent mt19937 stream with ordinary runs: interleave
+    both (larger than the fixtures: 4096 seeds on a 200k-node graph) and compare every call with the oracle."""
+    rowptr, col = lognormal_csr(200_000, 10_000_000, seed=2)
+    d_rowptr, d_col = rowptr.to(DEV), col.to(DEV)
+    g = torch.Generator().manual_seed(3)
+    seeds = [torch.randperm(200_000, generator=g)[:n] for n in (4096, 512, 20_000)]
+    torch.manual_seed(99)
+    exp = []
+    for i, sd in enumerate(seeds):
+        exp.append(O.dist_neighbor_sample(rowptr, col, sd, 10, replace=bool(i & 1)))
+        exp.append(O.neighbor_sample(rowptr, col, sd[:256], [5, 3]))
+    s_exp = _rng_prefix()
+    torch.manual_seed(99)
+    for i, sd in enumerate(seeds):
+        out = torch.ops.pyg.dist_neighbor_sample(d_rowptr, d_col, sd.to(DEV), 10, None, None, None, None, False, bool(i & 1), True,
+                                                 False, 'uniform')
+        e = exp[2 * i]
+        assert torch.equal(out[0].cpu(), e[0]) and torch.equal(out[1].cpu(), e[1]) and list(out[2]) == list(e[2])
+        _cmp(lib.sampler.neighbor_sample(d_rowptr, d_col, sd[:256].to(DEV), [5, 3]), exp[2 * i + 1])
+    assert np.array_equal(_rng_prefix(), s_exp)
