@@ -262,6 +262,17 @@ int pygb200_subgraph_count(pygb200_subgraph* h, const void* rowptr, const void* 
 int pygb200_subgraph_fill(pygb200_subgraph* h, const void* rowptr, const void* col, const void* nodes, int64_t n,
                           int index32, void* out_col, void* out_edge_id, void* stream);
 
+/* relabel_neighborhood (pyg_lib/csrc/sampler/cpu/dist_relabel_kernel.cpp:30-95; schema pyg::relabel_neighborhood,
+ * sampler/dist_relabel.cpp:71-76): local (row, col) of edges whose global endpoints were sampled without mapping
+ * (pyg::dist_neighbor_sample).  `sampled` [n_sampled] are the neighbours with duplicates, in source-node order;
+ * counts_host [n_counts] (HOST, like the reference's int[] argument) says how many belong to source node i, so
+ * out_row[j] = i; out_col[j] = id of sampled[j], ids numbering the first occurrences of [seed | sampled] — seeds
+ * first, exactly Mapper::fill + insert.  `batch` (NULL, or [n_sampled]) switches to disjoint keys (batch, node) with
+ * seed i in batch i.  Uses the map/scratch of a pygb200_subgraph handle; one host sync (error flag). */
+int pygb200_relabel_neighborhood(pygb200_subgraph* h, const void* seed, int64_t n_seed, const void* sampled,
+                                 const void* batch, int64_t n_sampled, const int64_t* counts_host, int64_t n_counts,
+                                 int index32, void* out_row, void* out_col, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -346,3 +346,29 @@ def dist_neighbor_sample(rowptr, col, seed, num_neighbors: int, node_time=None, 
     per_seed = torch.bincount(row.to(torch.int64), minlength=S)
     cumsum = [S] + (S + torch.cumsum(per_seed, 0)).tolist()
     return nodes, eid, cumsum
+
+
+def relabel_neighborhood(seed: torch.Tensor, sampled_nodes_with_duplicates: torch.Tensor, num_sampled_neighbors_per_node: List[int],
+                         num_nodes: int, batch: Optional[torch.Tensor] = None, csc: bool = False,
+                         disjoint: bool = False) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Oracle for pyg::relabel_neighborhood (relabel<disjoint>, pyg_lib/csrc/sampler/cpu/dist_relabel_kernel.cpp:30-95):
+    the mapper is filled with the seeds (`:67-74`; disjoint: key (i, seed_i)), then every sampled node is inserted in
+    order (`:76-92`); row = index of the source node the neighbour was counted for, col = the mapper's id."""
+    ids: Dict = {}
+    for i, v in enumerate(seed.tolist()):
+        k = (i, v) if disjoint else v
+        if k not in ids:
+            ids[k] = len(ids)
+    nodes = sampled_nodes_with_duplicates.tolist()
+    bt = batch.tolist() if disjoint else None
+    rows, cols = [], []
+    j = 0
+    for i, c in enumerate(num_sampled_neighbors_per_node):
+        for _ in range(int(c)):
+            k = (bt[j], nodes[j]) if disjoint else nodes[j]
+            if k not in ids:
+                ids[k] = len(ids)
+            rows.append(i); cols.append(ids[k])
+            j += 1
+    row = torch.tensor(rows, dtype=seed.dtype); col = torch.tensor(cols, dtype=seed.dtype)
+    return (col, row) if csc else (row, col)

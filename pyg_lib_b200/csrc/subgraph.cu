@@ -183,6 +183,39 @@ __global__ void __launch_bounds__(NT) k_sg_fill(const idx_t* __restrict__ rowptr
   }
 }
 
+// ---- relabel_neighborhood (dist_relabel_kernel.cpp:30-95): positions 0..S-1 are the seeds, S.. the sampled nodes
+// (with duplicates); a node's id is its rank among the first occurrences of that sequence.  Disjoint: the key is
+// (batch, node) — a seed is its own batch (`:70-73`), a sampled node brings its batch id.
+template <typename idx_t>
+__global__ void __launch_bounds__(NT) k_rl_insert(const idx_t* __restrict__ seed, i64 S, const idx_t* __restrict__ sampled,
+                                                   const idx_t* __restrict__ batch, i64 M, u64* keys, u64* vals, u64 mask, u32* slot, i64* err) {
+  for (i64 p = (i64)blockIdx.x * NT + threadIdx.x; p < S + M; p += (i64)gridDim.x * NT) {
+    const i64 v = p < S ? (i64)seed[p] : (i64)sampled[p - S];
+    const i64 b = batch ? (p < S ? p : (i64)batch[p - S]) : 0;
+    if (v < 0 || v >= ((i64)1 << 40) || b < 0 || b >= ((i64)1 << 23)) { *err = 1; slot[p] = 0; continue; }
+    const u32 s = table_insert(keys, mask, ((u64)b << 40) | (u64)v);
+    atomicMin(&vals[s], (u64)p);
+    slot[p] = s;
+  }
+}
+template <typename idx_t>
+__global__ void __launch_bounds__(NT) k_rl_cols(const u32* __restrict__ slot, const u64* __restrict__ vals, i64 S, i64 M, idx_t* __restrict__ out_col) {
+  for (i64 j = (i64)blockIdx.x * NT + threadIdx.x; j < M; j += (i64)gridDim.x * NT) out_col[j] = (idx_t)vals[slot[S + j]];
+}
+// row[j] = index of the source node whose run of sampled neighbours holds position j (`:76-88`): the last i with
+// offs[i] <= j (offs = exclusive prefix of the per-node counts; nodes without neighbours share an offset with their successor)
+template <typename idx_t>
+__global__ void __launch_bounds__(NT) k_rl_rows(const i64* __restrict__ offs, i64 n_counts, i64 M, idx_t* __restrict__ out_row) {
+  for (i64 j = (i64)blockIdx.x * NT + threadIdx.x; j < M; j += (i64)gridDim.x * NT) {
+    i64 lo = 0, hi = n_counts;   // first i with offs[i] > j
+    while (lo < hi) {
+      const i64 mid = lo + ((hi - lo) >> 1);
+      if (offs[mid] > j) hi = mid; else lo = mid + 1;
+    }
+    out_row[j] = (idx_t)(lo - 1);
+  }
+}
+
 }  // namespace
 }  // namespace pygb200
 
@@ -320,5 +353,74 @@ extern "C" int pygb200_subgraph_fill(pygb200_subgraph* h, const void* rowptr, co
   }
   k_sg_clean<<<g, NT, 0, st>>>(h->slot.as<u32>(), n, h->keys.as<u64>(), h->vals.as<u64>());
   PYGB_LAUNCH_CHECK();
+  return PYGB200_OK;
+}
+
+extern "C" int pygb200_relabel_neighborhood(pygb200_subgraph* h, const void* seed, int64_t n_seed, const void* sampled,
+                                            const void* batch, int64_t n_sampled, const int64_t* counts_host, int64_t n_counts,
+                                            int index32, void* out_row, void* out_col, void* stream) {
+  PYGB_CHECK(h && n_seed >= 0 && n_sampled >= 0 && n_counts >= 0 && (seed || n_seed == 0) && (sampled || n_sampled == 0) &&
+                 (counts_host || n_counts == 0) && ((out_row && out_col) || n_sampled == 0),
+             PYGB200_ERR_ARG, "pygb200_relabel_neighborhood: null / negative argument");
+  i64 total = 0;
+  for (i64 i = 0; i < n_counts; ++i) {
+    PYGB_CHECK(counts_host[i] >= 0, PYGB200_ERR_ARG, "relabel_neighborhood: negative neighbour count");
+    total += counts_host[i];
+  }
+  PYGB_CHECK(total == n_sampled, PYGB200_ERR_ARG, "relabel_neighborhood: the neighbour counts do not add up to the number of sampled nodes");
+  std::lock_guard<std::mutex> lock(h->mu);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (h->pending && h->n > 0) {   // an abandoned pygb200_subgraph_count still owns table entries
+    k_sg_clean<<<grid_for(h->n, NT, h->sm_count), NT, 0, st>>>(h->slot.as<u32>(), h->n, h->keys.as<u64>(), h->vals.as<u64>());
+    PYGB_LAUNCH_CHECK();
+  }
+  h->pending = false;
+  const i64 N = n_seed + n_sampled;
+  if (n_sampled == 0) return PYGB200_OK;
+  u64 cap = 2;
+  while (cap < 2 * (u64)N) cap <<= 1;
+  PYGB_CHECK(cap <= (1ull << 32), PYGB200_ERR_UNSUPPORTED, "relabel_neighborhood: too many nodes");
+  if (cap > h->tcap) {
+    if (int e = h->keys.ensure(cap * 8, 0, st)) return e;
+    if (int e = h->vals.ensure(cap * 8, 0, st)) return e;
+    PYGB_CUDA(cudaMemsetAsync(h->keys.p, 0xff, h->keys.cap, st));
+    PYGB_CUDA(cudaMemsetAsync(h->vals.p, 0xff, h->vals.cap, st));
+    h->tcap = cap;
+  }
+  const u64 mask = h->tcap - 1;
+  if (int e = h->slot.ensure((size_t)N * 4, 0, st)) return e;
+  if (int e = h->flag.ensure((size_t)N * 8, 0, st)) return e;
+  if (int e = h->ids.ensure((size_t)N * 8, 0, st)) return e;
+  if (int e = h->deg.ensure((size_t)std::max<i64>(n_counts, 1) * 8, 0, st)) return e;
+  if (int e = h->offs.ensure((size_t)std::max<i64>(n_counts, 1) * 8, 0, st)) return e;
+  if (int e = h->misc.ensure(64, 0, st)) return e;
+  i64* misc = h->misc.as<i64>();
+  PYGB_CUDA(cudaMemsetAsync(misc, 0, 64, st));
+  u64 *keys = h->keys.as<u64>(), *vals = h->vals.as<u64>();
+  u32* slot = h->slot.as<u32>();
+  const int g = grid_for(N, NT, h->sm_count), gm = grid_for(n_sampled, NT, h->sm_count);
+  if (index32) k_rl_insert<int32_t><<<g, NT, 0, st>>>((const int32_t*)seed, n_seed, (const int32_t*)sampled, (const int32_t*)batch, n_sampled, keys, vals, mask, slot, misc + 1);
+  else k_rl_insert<int64_t><<<g, NT, 0, st>>>((const int64_t*)seed, n_seed, (const int64_t*)sampled, (const int64_t*)batch, n_sampled, keys, vals, mask, slot, misc + 1);
+  PYGB_LAUNCH_CHECK();
+  k_sg_first<<<g, NT, 0, st>>>(slot, vals, N, h->flag.as<i64>());
+  PYGB_LAUNCH_CHECK();
+  if (int e = scan_i64(h, h->flag.as<i64>(), h->ids.as<i64>(), N, misc + 2, nullptr, 0, st)) return e;
+  k_sg_assign<<<g, NT, 0, st>>>(slot, h->flag.as<i64>(), h->ids.as<i64>(), N, vals);
+  PYGB_LAUNCH_CHECK();
+  if (index32) k_rl_cols<int32_t><<<gm, NT, 0, st>>>(slot, vals, n_seed, n_sampled, (int32_t*)out_col);
+  else k_rl_cols<int64_t><<<gm, NT, 0, st>>>(slot, vals, n_seed, n_sampled, (int64_t*)out_col);
+  PYGB_LAUNCH_CHECK();
+  // rows: per-node counts (a host list in the reference's API) -> offsets -> one binary search per edge
+  PYGB_CUDA(cudaMemcpyAsync(h->deg.p, counts_host, (size_t)n_counts * 8, cudaMemcpyHostToDevice, st));
+  if (int e = scan_i64(h, h->deg.as<i64>(), h->offs.as<i64>(), n_counts, misc, nullptr, 0, st)) return e;
+  if (index32) k_rl_rows<int32_t><<<gm, NT, 0, st>>>(h->offs.as<i64>(), n_counts, n_sampled, (int32_t*)out_row);
+  else k_rl_rows<int64_t><<<gm, NT, 0, st>>>(h->offs.as<i64>(), n_counts, n_sampled, (int64_t*)out_row);
+  PYGB_LAUNCH_CHECK();
+  k_sg_clean<<<g, NT, 0, st>>>(slot, N, keys, vals);
+  PYGB_LAUNCH_CHECK();
+  i64 err = 0;
+  PYGB_CUDA(cudaMemcpyAsync(&err, misc + 1, 8, cudaMemcpyDeviceToHost, st));
+  PYGB_CUDA(cudaStreamSynchronize(st));   // (also keeps `counts_host` alive until its copy is done)
+  PYGB_CHECK(err == 0, PYGB200_ERR_ARG, "relabel_neighborhood: node id outside [0, 2^40) or batch id outside [0, 2^23)");
   return PYGB200_OK;
 }

@@ -53,16 +53,61 @@ std::tuple<at::Tensor, at::Tensor, std::optional<at::Tensor>> subgraph_cuda(cons
   return std::make_tuple(out_rowptr, out_col, out_eid);
 }
 
+// pyg::relabel_neighborhood (relabel<disjoint>, cpu/dist_relabel_kernel.cpp:30-95) on CUDA tensors
+std::tuple<at::Tensor, at::Tensor> relabel_neighborhood_cuda(const at::Tensor& seed, const at::Tensor& sampled_nodes_with_duplicates,
+                                                             const std::vector<int64_t>& num_sampled_neighbors_per_node,
+                                                             int64_t num_nodes, const std::optional<at::Tensor>& batch, bool csc,
+                                                             bool disjoint) {
+  const at::Tensor& sampled = sampled_nodes_with_duplicates;
+  TORCH_CHECK(seed.is_cuda() && sampled.is_cuda(), "pyg_lib_b200: relabel_neighborhood expects CUDA tensors (no CPU fallback)");
+  const auto st = seed.scalar_type();
+  TORCH_CHECK(st == at::kLong || st == at::kInt, "relabel_neighborhood: index tensors must be int64 or int32");
+  TORCH_CHECK(sampled.scalar_type() == st, "relabel_neighborhood: expected 'seed' and 'sampled_nodes_with_duplicates' to have the same dtype");
+  if (disjoint) {   // dist_relabel_kernel.cpp:37-43
+    TORCH_CHECK(batch.has_value(), "Batch needs to be specified to create disjoint subgraphs");
+    TORCH_CHECK(batch->is_contiguous(), "Non-contiguous 'batch'");
+    TORCH_CHECK(batch->numel() == sampled.numel(), "Each node must belong to a subgraph");
+    TORCH_CHECK(batch->scalar_type() == st && batch->device() == seed.device(), "relabel_neighborhood: 'batch' must match 'seed' in dtype and device");
+  }
+  TORCH_CHECK(seed.is_contiguous(), "Non-contiguous 'seed'");
+  TORCH_CHECK(sampled.is_contiguous(), "Non-contiguous 'sampled_nodes_with_duplicates'");
+  TORCH_CHECK(sampled.device() == seed.device(), "relabel_neighborhood: tensors must live on one device");
+  (void)num_nodes;  // (the reference only sizes its mapper with it)
+  int64_t total = 0;
+  for (const int64_t c : num_sampled_neighbors_per_node) {
+    TORCH_CHECK(c >= 0, "relabel_neighborhood: negative neighbour count");
+    total += c;
+  }
+  TORCH_CHECK(total <= sampled.numel(), "relabel_neighborhood: more neighbours counted than sampled nodes given");
+
+  c10::cuda::CUDAGuard guard(seed.device());
+  cudaStream_t stream = at::cuda::getCurrentCUDAStream();
+  pygb200_subgraph* h = get_handle(seed.device().index(), stream);
+  at::Tensor row = at::empty({total}, seed.options()), colv = at::empty({total}, seed.options());
+  PYGB_TORCH_CALL(pygb200_relabel_neighborhood(h, seed.data_ptr(), seed.numel(), sampled.data_ptr(), disjoint ? batch->data_ptr() : nullptr,
+                                               total, num_sampled_neighbors_per_node.data(), (int64_t)num_sampled_neighbors_per_node.size(),
+                                               st == at::kInt, row.data_ptr(), colv.data_ptr(), stream));
+  if (csc) std::swap(row, colv);   // get_sampled_edges, dist_relabel_kernel.cpp:16-27
+  return std::make_tuple(row, colv);
+}
+
 }  // namespace
 
 TORCH_LIBRARY_FRAGMENT(pyg, m) {
   m.def(TORCH_SELECTIVE_SCHEMA(
       "pyg::subgraph(Tensor rowptr, Tensor col, Tensor "
       "nodes, bool return_edge_id) -> (Tensor, Tensor, Tensor?)"));
+  m.def(TORCH_SELECTIVE_SCHEMA(   // pyg_lib/csrc/sampler/dist_relabel.cpp:71-76
+      "pyg::relabel_neighborhood(Tensor seed, Tensor "
+      "sampled_nodes_with_duplicates, int[] num_sampled_neighbors_per_node, "
+      "int "
+      "num_nodes, Tensor? batch = None, bool csc = False, bool disjoint = "
+      "False) -> (Tensor, Tensor)"));
 }
 
 TORCH_LIBRARY_IMPL(pyg, CUDA, m) {
   m.impl(TORCH_SELECTIVE_NAME("pyg::subgraph"), TORCH_FN(subgraph_cuda));
+  m.impl(TORCH_SELECTIVE_NAME("pyg::relabel_neighborhood"), TORCH_FN(relabel_neighborhood_cuda));
 }
 
 }  // namespace sampler

@@ -277,3 +277,35 @@ DIST_CASES: Dict[str, dict] = {
 def build_dist(case):
     """(rowptr, col, seed) of a DIST_CASES entry."""
     return build_homo(dict(case, num_neighbors=[case['k']]))
+
+
+# pyg::relabel_neighborhood cases: inputs are what one hop of dist_neighbor_sample returns for a DIST_CASES entry
+# (seeds, the unmapped neighbours, neighbours per seed), plus hand-made ones
+RELABEL_CASES: Dict[str, dict] = {
+    # test/csrc/sampler/test_dist_relabel.cpp:9-36 and :38-60
+    'kat': dict(seed=[2, 3], sampled=[1, 3, 2, 4], counts=[2, 2], num_nodes=6),
+    'kat_disjoint': dict(seed=[2, 3], sampled=[1, 3, 2, 4], counts=[2, 2], num_nodes=6, batch=[0, 0, 1, 1]),
+    'zero_counts_dup_seeds': dict(seed=[5, 5, 1], sampled=[7, 5, 7, 9, 1], counts=[0, 3, 0, 2, 0], num_nodes=12),
+    'from_rand_15': dict(dist='rand_15'),
+    'from_rand_15_rep_csc': dict(dist='rand_15_rep', csc=True),
+    'from_rand_k40_disjoint': dict(dist='rand_k40_disjoint'),
+    'from_bigdeg': dict(dist='bigdeg'),
+}
+
+
+def build_relabel(case, oracle_dist):
+    """(seed, sampled, counts, num_nodes, batch, csc, disjoint); `oracle_dist(rowptr, col, seed, k, **kw)` supplies the
+    one-hop sample the derived cases relabel (tests pass oracle.dist_neighbor_sample, make_golden passes the reference)."""
+    if 'dist' not in case:
+        b = case.get('batch')
+        return (torch.tensor(case['seed']), torch.tensor(case['sampled']), list(case['counts']), case['num_nodes'],
+                None if b is None else torch.tensor(b), case.get('csc', False), b is not None)
+    dc = DIST_CASES[case['dist']]
+    rowptr, col, seed = build_dist(dc)
+    torch.manual_seed(dc['rng_seed'])
+    node, eid, cum = oracle_dist(rowptr, col, seed, dc['k'], replace=dc.get('replace', False), disjoint=dc.get('disjoint', False))
+    S = seed.numel()
+    counts = [int(cum[i + 1] - cum[i]) for i in range(S)]
+    if dc.get('disjoint', False):
+        return seed, node[S:, 1].contiguous(), counts, rowptr.numel() - 1, node[S:, 0].contiguous(), case.get('csc', False), True
+    return seed, node[S:].contiguous(), counts, rowptr.numel() - 1, None, case.get('csc', False), False

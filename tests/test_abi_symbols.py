@@ -64,6 +64,9 @@ def test_schemas_match_reference(built):
         'pyg::dist_neighbor_sample(Tensor rowptr, Tensor col, Tensor seed, int num_neighbors, Tensor? node_time=None, '
         'Tensor? edge_time=None, Tensor? seed_time=None, Tensor? edge_weight=None, bool csc=False, bool replace=False, '
         'bool directed=True, bool disjoint=False, str temporal_strategy="uniform") -> (Tensor, Tensor, int[])')
+    assert str(torch.ops.pyg.relabel_neighborhood.default._schema) == (   # sampler/dist_relabel.cpp:71-76
+        'pyg::relabel_neighborhood(Tensor seed, Tensor sampled_nodes_with_duplicates, int[] num_sampled_neighbors_per_node, '
+        'int num_nodes, Tensor? batch=None, bool csc=False, bool disjoint=False) -> (Tensor, Tensor)')
     assert str(torch.ops.pyg.grouped_matmul.default._schema) == 'pyg::grouped_matmul(Tensor[] input, Tensor[] other) -> Tensor[]'
     assert torch.ops.pyg.cuda_version() >= 12000
 

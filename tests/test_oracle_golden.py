@@ -229,3 +229,20 @@ def test_dist_oracle_matches_reference_fixture(dist_golden, name):
     assert np.array_equal(r[1].numpy(), dist_golden[f'{name}/eid'])
     assert list(r[2]) == dist_golden[f'{name}/cumsum'].tolist()
     assert np.array_equal(torch.get_rng_state().numpy()[:24 + 624 * 8], dist_golden[f'{name}/rng_after'])
+
+
+# ------------------------------------------------------------------------------------ relabel_neighborhood
+from graphs import RELABEL_CASES, build_relabel  # noqa: E402
+
+
+@pytest.mark.parametrize('name', list(RELABEL_CASES))
+def test_relabel_oracle_matches_reference_fixture(name):
+    """KATs test/csrc/sampler/test_dist_relabel.cpp:9-60 + cases derived from one-hop distributed samples."""
+    G = np.load(osp.join(osp.dirname(osp.abspath(__file__)), 'golden', 'relabel_outputs.npz'))
+    seed, sampled, counts, num_nodes, batch, csc, disjoint = build_relabel(RELABEL_CASES[name], O.dist_neighbor_sample)
+    r = O.relabel_neighborhood(seed, sampled, counts, num_nodes, batch, csc, disjoint)
+    assert np.array_equal(r[0].numpy(), G[f'{name}/row']) and np.array_equal(r[1].numpy(), G[f'{name}/col'])
+    if name == 'kat':
+        assert r[0].tolist() == [0, 0, 1, 1] and r[1].tolist() == [2, 1, 0, 3]
+    if name == 'kat_disjoint':
+        assert r[0].tolist() == [0, 0, 1, 1] and r[1].tolist() == [2, 3, 4, 5]

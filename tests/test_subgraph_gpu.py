@@ -101,3 +101,44 @@ def test_subgraph_c_abi(lib):
     torch.cuda.synchronize()
     assert torch.equal(out_rowptr.cpu(), exp[0]) and torch.equal(out_col.cpu(), exp[1]) and torch.equal(out_eid.cpu(), exp[2])
     abi.pygb200_subgraph_destroy(h)
+
+
+# ------------------------------------------------------------------------------------ pyg::relabel_neighborhood
+from graphs import RELABEL_CASES, build_relabel  # noqa: E402
+
+
+@pytest.mark.parametrize('name', list(RELABEL_CASES))
+@pytest.mark.parametrize('dtype', [torch.int64, torch.int32])
+def test_relabel_neighborhood_golden(lib, name, dtype):
+    G = np.load(osp.join(HERE, 'golden', 'relabel_outputs.npz'))
+    seed, sampled, counts, num_nodes, batch, csc, disjoint = build_relabel(RELABEL_CASES[name], O.dist_neighbor_sample)
+    out = torch.ops.pyg.relabel_neighborhood(seed.to(DEV, dtype), sampled.to(DEV, dtype), counts, num_nodes,
+                                             None if batch is None else batch.to(DEV, dtype), csc, disjoint)
+    assert out[0].dtype == dtype and out[1].dtype == dtype
+    assert np.array_equal(out[0].cpu().numpy(), G[f'{name}/row']) and np.array_equal(out[1].cpu().numpy(), G[f'{name}/col'])
+
+
+def test_dist_sample_then_relabel_equals_neighbor_sample(lib):
+    """The property the reference checks (test_dist_relabel.cpp:27-36): one distributed hop + relabel == the
+    ordinary one-hop sample, here on a 200k-node graph with 4096 seeds, all on the GPU."""
+    rowptr, col = lognormal_csr(200_000, 10_000_000, seed=4)
+    d_rowptr, d_col = rowptr.to(DEV), col.to(DEV)
+    seed = torch.randperm(200_000, generator=torch.Generator().manual_seed(5))[:4096].to(DEV)
+    torch.manual_seed(7)
+    node, eid, cum = torch.ops.pyg.dist_neighbor_sample(d_rowptr, d_col, seed, 10, None, None, None, None, False, False, True, False,
+                                                        'uniform')
+    counts = [cum[i + 1] - cum[i] for i in range(seed.numel())]
+    row, colv = torch.ops.pyg.relabel_neighborhood(seed, node[seed.numel():].contiguous(), counts, 200_000, None, False, False)
+    torch.manual_seed(7)
+    ref = lib.sampler.neighbor_sample(d_rowptr, d_col, seed, [10])
+    assert torch.equal(row, ref[0]) and torch.equal(colv, ref[1]) and torch.equal(eid, ref[3])
+
+
+def test_relabel_neighborhood_errors(lib):
+    seed = torch.tensor([2, 3], device=DEV)
+    with pytest.raises(RuntimeError, match='Batch needs to be specified'):
+        torch.ops.pyg.relabel_neighborhood(seed, torch.tensor([1, 3], device=DEV), [1, 1], 6, None, False, True)
+    with pytest.raises(RuntimeError, match='more neighbours counted'):
+        torch.ops.pyg.relabel_neighborhood(seed, torch.tensor([1, 3], device=DEV), [2, 2], 6, None, False, False)
+    out = torch.ops.pyg.relabel_neighborhood(seed, torch.tensor([1, 3, 2, 4], device=DEV), [2, 2], 6, None, False, False)
+    assert out[0].tolist() == [0, 0, 1, 1] and out[1].tolist() == [2, 1, 0, 3]
