@@ -5,18 +5,17 @@
 // them bit-for-bit, including the order in which the sequential RandintEngine stream
 // (pyg_lib/csrc/random/cpu/rand_engine.h:26-97) is consumed.
 //
-// One "pass" = (hop, relation).  Sizes never leave the device while a pass runs:
-//   k_count   thread per frontier node: degree -> #edges emitted and the node's RNG "advance
-//             function" (phase-in -> units consumed), block-local ordered scans, per-node records;
-//             the LAST block to finish scans the tile aggregates (edge offsets + absolute RNG
-//             positions) and extends the mt19937 raw stream to cover the pass.
-//   k_sample  one group of G lanes per frontier node: draws (Robert Floyd / with replacement / full
-//             row), coalesced writes of (row, global dst, edge id), hash insert keyed by global id
-//             with atomicMin of the flat emission position (first-occurrence order).
-//   k_mark    edge is "first" iff its position won the atomicMin; tile-local ranks; last block scans.
-//   k_assign  new local ids = ids_base + rank, appended to the dst type's node list.
-//   k_lookup  every edge reads its final local id.
-// Host work per call: bounds, launches, ONE stream sync at the end (the API returns host counts).
+// One "pass" = (hop, relation).  Sizes never leave the device while a pass runs.  Device bodies shared by both
+// schedules: count_tile (degree -> #edges + the node's RNG "advance function", phase-in -> units consumed),
+// sample_node (draws: Robert Floyd / with replacement / full row; coalesced writes of (row, global dst, edge id);
+// hash insert keyed by global id with a min-reduction of the flat emission position = first-occurrence order),
+// mark_tile (an edge is "first" iff its position won the reduction; tile-local ranks).
+//   latency path     k_seed_fused (+ the first pass's count) -> per pass k_count_s, k_sample_s, k_mark_s, k_assign_s
+//                    -> k_final: write-once counters, every block scans the <= 1024 tile aggregates itself, the run is
+//                    published to the host by its last pass.  Small bounded runs.
+//   throughput path  k_seed* -> per pass k_count, k_sample, k_mark, k_assign (last block scans, running counters)
+//                    -> k_final: any size, full neighbourhoods (host-synced sizing), frontier sharding, no-dedup hop.
+// Host work per call: bounds, launches, ONE wait on a mapped flag (the API returns host counts).
 #include <dlfcn.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -1889,21 +1888,21 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
     const int older = s->mt_ev_next, newer = s->mt_ev_next ^ 1;
     if (s->mt_gen_known >= need) {
       // covered by a launch this stream has already waited for; newer launches keep running beside us
-      g_ht.branch[0]++;
+      if (g_ht.on) g_ht.branch[0]++;
     } else if (s->mt_ev_pending[older] && s->mt_ev_target[older] >= need) {
-      g_ht.branch[1]++;
+      if (g_ht.on) g_ht.branch[1]++;
       PYGB_CUDA(cudaStreamWaitEvent(st, s->mt_ev[older], 0));
       s->mt_ev_pending[older] = false;
       s->mt_gen_known = std::max(s->mt_gen_known, s->mt_ev_target[older]);
     } else if (s->mt_ev_pending[newer] && s->mt_ev_target[newer] >= need) {
-      g_ht.branch[2]++;
+      if (g_ht.on) g_ht.branch[2]++;
       // same side stream: once the newer launch is complete so is the older one
       PYGB_CUDA(cudaStreamWaitEvent(st, s->mt_ev[newer], 0));
       s->mt_ev_pending[older] = s->mt_ev_pending[newer] = false;
       s->mt_gen_known = std::max(s->mt_gen_known, s->mt_ev_target[newer]);
     } else {
       // not covered ahead of time (first continued run, or a run larger than the previous one): extend here
-      g_ht.branch[3]++;
+      if (g_ht.on) g_ht.branch[3]++;
       if (int e = wait_all_pregen()) return e;
       if (int e = mt_request(s, st, need)) return e;
       s->mt_gen_known = need;
@@ -1912,7 +1911,7 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
       PYGB_CUDA(cudaStreamWaitEvent(s->mt_stream, s->mt_order_ev, 0));
     }
   } else {
-    g_ht.branch[4]++;
+    if (g_ht.on) g_ht.branch[4]++;
     if (int e = wait_all_pregen()) return e;
     static const i64 pref_cap = [] { const char* e = getenv("PYGB200_MT_CAP_WORDS"); return e ? (i64)atoll(e) : (i64)1 << 23; }();
     load_jump_table(s, st);
