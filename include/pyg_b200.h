@@ -273,6 +273,19 @@ int pygb200_relabel_neighborhood(pygb200_subgraph* h, const void* seed, int64_t 
                                  const void* batch, int64_t n_sampled, const int64_t* counts_host, int64_t n_counts,
                                  int index32, void* out_row, void* out_col, void* stream);
 
+/* The two halves of the heterogeneous version (hetero relabel<disjoint>, dist_relabel_kernel.cpp:97-273), where the
+ * schedule — which positions of a destination type's sampled list belong to which (layer, edge type, source node)
+ * — is host bookkeeping over the reference's int[][] count lists:
+ *   pygb200_relabel_ids     ids of one node type's `sampled` list among the first occurrences of [seed | sampled]
+ *                           (out_ids [n_sampled], index dtype); disjoint (batch != NULL): seed i has batch seed_batch0 + i;
+ *   pygb200_relabel_expand  one relation: HOST lists of n_seg source segments (count, source index, first position in
+ *                           the destination type's id list `ids` [n_ids]) -> out_row / out_col [sum of counts]. */
+int pygb200_relabel_ids(pygb200_subgraph* h, const void* seed, int64_t n_seed, int64_t seed_batch0, const void* sampled,
+                        const void* batch, int64_t n_sampled, int index32, void* out_ids, void* stream);
+int pygb200_relabel_expand(pygb200_subgraph* h, const int64_t* seg_count_host, const int64_t* seg_row_host,
+                           const int64_t* seg_pos_host, int64_t n_seg, const void* ids, int64_t n_ids, int index32,
+                           void* out_row, void* out_col, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

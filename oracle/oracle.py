@@ -372,3 +372,59 @@ def relabel_neighborhood(seed: torch.Tensor, sampled_nodes_with_duplicates: torc
             j += 1
     row = torch.tensor(rows, dtype=seed.dtype); col = torch.tensor(cols, dtype=seed.dtype)
     return (col, row) if csc else (row, col)
+
+
+def hetero_relabel_neighborhood(node_types: List[str], edge_types: List[Tuple[str, str, str]], seed_dict: Dict[str, torch.Tensor],
+                                sampled_dict: Dict[str, torch.Tensor], counts_dict: Dict[str, List[List[int]]],
+                                num_nodes_dict: Dict[str, int], batch_dict: Optional[Dict[str, torch.Tensor]] = None,
+                                csc: bool = False, disjoint: bool = False):
+    """Oracle for pyg::hetero_relabel_neighborhood (hetero relabel<disjoint>, dist_relabel_kernel.cpp:97-273), 1 thread.
+
+    One mapper per node type, filled with that type's seeds (disjoint: keys (batch, node), the batch counter running
+    over all seeds in seed_dict order, `:180-193`).  Layer by layer, edge type by edge type, source node by source
+    node, the next `count` entries of the DST type's sampled list are inserted (`:206-235`); row = the source node's
+    local index, which per edge type starts at 0 and continues after the largest index any edge type with the same
+    source node type used in the previous layer (`:240-258`)."""
+    dt = next(iter(seed_dict.values())).dtype
+    rel = lambda k: '__'.join(k)  # noqa: E731
+    ids = {t: {} for t in node_types}
+    cursor = {t: 0 for t in node_types}
+    b = 0
+    for t, sd in seed_dict.items():
+        for v in sd.tolist():
+            key = (b, v) if disjoint else v
+            if disjoint:
+                b += 1
+            if key not in ids[t]:
+                ids[t][key] = len(ids[t])
+    sampled = {t: sampled_dict[t].tolist() for t in node_types}
+    batches = {t: batch_dict[t].tolist() for t in node_types} if disjoint else None
+    rows = {k: [] for k in edge_types}
+    cols = {k: [] for k in edge_types}
+    L = len(counts_dict[rel(edge_types[0])])
+    src_slice = {k: (0, len(counts_dict[rel(k)][0])) for k in edge_types}
+    src_off = {t: 0 for t in node_types}
+    for ell in range(L):
+        for k in edge_types:
+            dst = k[0] if csc else k[2]
+            begin_i, end_i = src_slice[k]
+            for i in range(begin_i, end_i):
+                c = int(counts_dict[rel(k)][ell][i - begin_i])
+                for j in range(cursor[dst], cursor[dst] + c):
+                    key = (batches[dst][j], sampled[dst][j]) if disjoint else sampled[dst][j]
+                    if key not in ids[dst]:
+                        ids[dst][key] = len(ids[dst])
+                    rows[k].append(i); cols[k].append(ids[dst][key])
+                cursor[dst] += c
+        if ell < L - 1:
+            for k in edge_types:
+                src = k[2] if csc else k[0]
+                src_off[src] = max(src_off[src], src_slice[k][1])
+            for k in edge_types:
+                src = k[2] if csc else k[0]
+                src_slice[k] = (src_off[src], src_off[src] + len(counts_dict[rel(k)][ell + 1]))
+    out_row, out_col = {}, {}
+    for k in edge_types:
+        r, c = torch.tensor(rows[k], dtype=dt), torch.tensor(cols[k], dtype=dt)
+        out_row[rel(k)], out_col[rel(k)] = (c, r) if csc else (r, c)
+    return out_row, out_col

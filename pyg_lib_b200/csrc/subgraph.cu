@@ -187,11 +187,11 @@ __global__ void __launch_bounds__(NT) k_sg_fill(const idx_t* __restrict__ rowptr
 // (with duplicates); a node's id is its rank among the first occurrences of that sequence.  Disjoint: the key is
 // (batch, node) — a seed is its own batch (`:70-73`), a sampled node brings its batch id.
 template <typename idx_t>
-__global__ void __launch_bounds__(NT) k_rl_insert(const idx_t* __restrict__ seed, i64 S, const idx_t* __restrict__ sampled,
+__global__ void __launch_bounds__(NT) k_rl_insert(const idx_t* __restrict__ seed, i64 S, i64 seed_batch0, const idx_t* __restrict__ sampled,
                                                    const idx_t* __restrict__ batch, i64 M, u64* keys, u64* vals, u64 mask, u32* slot, i64* err) {
   for (i64 p = (i64)blockIdx.x * NT + threadIdx.x; p < S + M; p += (i64)gridDim.x * NT) {
     const i64 v = p < S ? (i64)seed[p] : (i64)sampled[p - S];
-    const i64 b = batch ? (p < S ? p : (i64)batch[p - S]) : 0;
+    const i64 b = batch ? (p < S ? seed_batch0 + p : (i64)batch[p - S]) : 0;
     if (v < 0 || v >= ((i64)1 << 40) || b < 0 || b >= ((i64)1 << 23)) { *err = 1; slot[p] = 0; continue; }
     const u32 s = table_insert(keys, mask, ((u64)b << 40) | (u64)v);
     atomicMin(&vals[s], (u64)p);
@@ -216,6 +216,24 @@ __global__ void __launch_bounds__(NT) k_rl_rows(const i64* __restrict__ offs, i6
   }
 }
 
+// hetero relabel: output edge j of a relation lies in source segment s (the last s with offs[s] <= j); its row is that
+// segment's source index and its col the id at the segment's position in the destination type's id list
+template <typename idx_t>
+__global__ void __launch_bounds__(NT) k_rl_expand(const i64* __restrict__ offs, i64 n_seg, i64 M, const i64* __restrict__ seg_row,
+                                                   const i64* __restrict__ seg_pos, const idx_t* __restrict__ ids, idx_t* __restrict__ out_row,
+                                                   idx_t* __restrict__ out_col) {
+  for (i64 j = (i64)blockIdx.x * NT + threadIdx.x; j < M; j += (i64)gridDim.x * NT) {
+    i64 lo = 0, hi = n_seg;
+    while (lo < hi) {
+      const i64 mid = lo + ((hi - lo) >> 1);
+      if (offs[mid] > j) hi = mid; else lo = mid + 1;
+    }
+    const i64 sgm = lo - 1;
+    out_row[j] = (idx_t)seg_row[sgm];
+    out_col[j] = ids[seg_pos[sgm] + (j - offs[sgm])];
+  }
+}
+
 }  // namespace
 }  // namespace pygb200
 
@@ -223,7 +241,7 @@ using namespace pygb200;
 
 struct pygb200_subgraph {
   int device = 0, sm_count = 148;
-  DevBuf keys, vals, slot, flag, ids, deg, offs, tiles, misc;   // misc: {total, err}
+  DevBuf keys, vals, slot, flag, ids, deg, offs, tiles, misc, segs;   // misc: {total, err}; segs: hetero relabel segment lists
   u64 tcap = 0;
   i64 n = 0;            // node count of the pending count() (fill() must follow with the same inputs)
   bool pending = false;
@@ -243,7 +261,7 @@ extern "C" int pygb200_subgraph_create(pygb200_subgraph** out) {
 
 extern "C" void pygb200_subgraph_destroy(pygb200_subgraph* h) {
   if (!h) return;
-  DevBuf* all[] = {&h->keys, &h->vals, &h->slot, &h->flag, &h->ids, &h->deg, &h->offs, &h->tiles, &h->misc};
+  DevBuf* all[] = {&h->keys, &h->vals, &h->slot, &h->flag, &h->ids, &h->deg, &h->offs, &h->tiles, &h->misc, &h->segs};
   for (DevBuf* b : all) b->release();
   delete h;
 }
@@ -356,27 +374,21 @@ extern "C" int pygb200_subgraph_fill(pygb200_subgraph* h, const void* rowptr, co
   return PYGB200_OK;
 }
 
-extern "C" int pygb200_relabel_neighborhood(pygb200_subgraph* h, const void* seed, int64_t n_seed, const void* sampled,
-                                            const void* batch, int64_t n_sampled, const int64_t* counts_host, int64_t n_counts,
-                                            int index32, void* out_row, void* out_col, void* stream) {
-  PYGB_CHECK(h && n_seed >= 0 && n_sampled >= 0 && n_counts >= 0 && (seed || n_seed == 0) && (sampled || n_sampled == 0) &&
-                 (counts_host || n_counts == 0) && ((out_row && out_col) || n_sampled == 0),
-             PYGB200_ERR_ARG, "pygb200_relabel_neighborhood: null / negative argument");
-  i64 total = 0;
-  for (i64 i = 0; i < n_counts; ++i) {
-    PYGB_CHECK(counts_host[i] >= 0, PYGB200_ERR_ARG, "relabel_neighborhood: negative neighbour count");
-    total += counts_host[i];
-  }
-  PYGB_CHECK(total == n_sampled, PYGB200_ERR_ARG, "relabel_neighborhood: the neighbour counts do not add up to the number of sampled nodes");
-  std::lock_guard<std::mutex> lock(h->mu);
-  cudaStream_t st = (cudaStream_t)stream;
+namespace {
+// ids of `sampled` [n_sampled] among the first occurrences of [seed | sampled] -> out_col (caller dtype); leaves the
+// map clean.  Caller holds h->mu.  The error flag (misc[1]) is read by the caller after its own sync.
+int relabel_ids_locked(pygb200_subgraph* h, const void* seed, i64 n_seed, i64 seed_batch0, const void* sampled, const void* batch,
+                       i64 n_sampled, int index32, void* out_col, cudaStream_t st) {
   if (h->pending && h->n > 0) {   // an abandoned pygb200_subgraph_count still owns table entries
     k_sg_clean<<<grid_for(h->n, NT, h->sm_count), NT, 0, st>>>(h->slot.as<u32>(), h->n, h->keys.as<u64>(), h->vals.as<u64>());
     PYGB_LAUNCH_CHECK();
   }
   h->pending = false;
-  const i64 N = n_seed + n_sampled;
+  if (int e = h->misc.ensure(64, 0, st)) return e;
+  i64* misc = h->misc.as<i64>();
+  PYGB_CUDA(cudaMemsetAsync(misc, 0, 64, st));
   if (n_sampled == 0) return PYGB200_OK;
+  const i64 N = n_seed + n_sampled;
   u64 cap = 2;
   while (cap < 2 * (u64)N) cap <<= 1;
   PYGB_CHECK(cap <= (1ull << 32), PYGB200_ERR_UNSUPPORTED, "relabel_neighborhood: too many nodes");
@@ -391,16 +403,11 @@ extern "C" int pygb200_relabel_neighborhood(pygb200_subgraph* h, const void* see
   if (int e = h->slot.ensure((size_t)N * 4, 0, st)) return e;
   if (int e = h->flag.ensure((size_t)N * 8, 0, st)) return e;
   if (int e = h->ids.ensure((size_t)N * 8, 0, st)) return e;
-  if (int e = h->deg.ensure((size_t)std::max<i64>(n_counts, 1) * 8, 0, st)) return e;
-  if (int e = h->offs.ensure((size_t)std::max<i64>(n_counts, 1) * 8, 0, st)) return e;
-  if (int e = h->misc.ensure(64, 0, st)) return e;
-  i64* misc = h->misc.as<i64>();
-  PYGB_CUDA(cudaMemsetAsync(misc, 0, 64, st));
   u64 *keys = h->keys.as<u64>(), *vals = h->vals.as<u64>();
   u32* slot = h->slot.as<u32>();
   const int g = grid_for(N, NT, h->sm_count), gm = grid_for(n_sampled, NT, h->sm_count);
-  if (index32) k_rl_insert<int32_t><<<g, NT, 0, st>>>((const int32_t*)seed, n_seed, (const int32_t*)sampled, (const int32_t*)batch, n_sampled, keys, vals, mask, slot, misc + 1);
-  else k_rl_insert<int64_t><<<g, NT, 0, st>>>((const int64_t*)seed, n_seed, (const int64_t*)sampled, (const int64_t*)batch, n_sampled, keys, vals, mask, slot, misc + 1);
+  if (index32) k_rl_insert<int32_t><<<g, NT, 0, st>>>((const int32_t*)seed, n_seed, seed_batch0, (const int32_t*)sampled, (const int32_t*)batch, n_sampled, keys, vals, mask, slot, misc + 1);
+  else k_rl_insert<int64_t><<<g, NT, 0, st>>>((const int64_t*)seed, n_seed, seed_batch0, (const int64_t*)sampled, (const int64_t*)batch, n_sampled, keys, vals, mask, slot, misc + 1);
   PYGB_LAUNCH_CHECK();
   k_sg_first<<<g, NT, 0, st>>>(slot, vals, N, h->flag.as<i64>());
   PYGB_LAUNCH_CHECK();
@@ -410,17 +417,87 @@ extern "C" int pygb200_relabel_neighborhood(pygb200_subgraph* h, const void* see
   if (index32) k_rl_cols<int32_t><<<gm, NT, 0, st>>>(slot, vals, n_seed, n_sampled, (int32_t*)out_col);
   else k_rl_cols<int64_t><<<gm, NT, 0, st>>>(slot, vals, n_seed, n_sampled, (int64_t*)out_col);
   PYGB_LAUNCH_CHECK();
+  k_sg_clean<<<g, NT, 0, st>>>(slot, N, keys, vals);
+  PYGB_LAUNCH_CHECK();
+  return PYGB200_OK;
+}
+int relabel_check_error(pygb200_subgraph* h, cudaStream_t st) {
+  i64 err = 0;
+  PYGB_CUDA(cudaMemcpyAsync(&err, h->misc.as<i64>() + 1, 8, cudaMemcpyDeviceToHost, st));
+  PYGB_CUDA(cudaStreamSynchronize(st));   // (also keeps host lists alive until their copies are done)
+  PYGB_CHECK(err == 0, PYGB200_ERR_ARG, "relabel_neighborhood: node id outside [0, 2^40) or batch id outside [0, 2^23)");
+  return PYGB200_OK;
+}
+}  // namespace
+
+extern "C" int pygb200_relabel_neighborhood(pygb200_subgraph* h, const void* seed, int64_t n_seed, const void* sampled,
+                                            const void* batch, int64_t n_sampled, const int64_t* counts_host, int64_t n_counts,
+                                            int index32, void* out_row, void* out_col, void* stream) {
+  PYGB_CHECK(h && n_seed >= 0 && n_sampled >= 0 && n_counts >= 0 && (seed || n_seed == 0) && (sampled || n_sampled == 0) &&
+                 (counts_host || n_counts == 0) && ((out_row && out_col) || n_sampled == 0),
+             PYGB200_ERR_ARG, "pygb200_relabel_neighborhood: null / negative argument");
+  i64 total = 0;
+  for (i64 i = 0; i < n_counts; ++i) {
+    PYGB_CHECK(counts_host[i] >= 0, PYGB200_ERR_ARG, "relabel_neighborhood: negative neighbour count");
+    total += counts_host[i];
+  }
+  PYGB_CHECK(total == n_sampled, PYGB200_ERR_ARG, "relabel_neighborhood: the neighbour counts do not add up to the number of sampled nodes");
+  std::lock_guard<std::mutex> lock(h->mu);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (int e = relabel_ids_locked(h, seed, n_seed, 0, sampled, batch, n_sampled, index32, out_col, st)) return e;
+  if (n_sampled == 0) return PYGB200_OK;
   // rows: per-node counts (a host list in the reference's API) -> offsets -> one binary search per edge
+  if (int e = h->deg.ensure((size_t)n_counts * 8, 0, st)) return e;
+  if (int e = h->offs.ensure((size_t)n_counts * 8, 0, st)) return e;
   PYGB_CUDA(cudaMemcpyAsync(h->deg.p, counts_host, (size_t)n_counts * 8, cudaMemcpyHostToDevice, st));
-  if (int e = scan_i64(h, h->deg.as<i64>(), h->offs.as<i64>(), n_counts, misc, nullptr, 0, st)) return e;
+  if (int e = scan_i64(h, h->deg.as<i64>(), h->offs.as<i64>(), n_counts, h->misc.as<i64>(), nullptr, 0, st)) return e;
+  const int gm = grid_for(n_sampled, NT, h->sm_count);
   if (index32) k_rl_rows<int32_t><<<gm, NT, 0, st>>>(h->offs.as<i64>(), n_counts, n_sampled, (int32_t*)out_row);
   else k_rl_rows<int64_t><<<gm, NT, 0, st>>>(h->offs.as<i64>(), n_counts, n_sampled, (int64_t*)out_row);
   PYGB_LAUNCH_CHECK();
-  k_sg_clean<<<g, NT, 0, st>>>(slot, N, keys, vals);
+  return relabel_check_error(h, st);
+}
+
+extern "C" int pygb200_relabel_ids(pygb200_subgraph* h, const void* seed, int64_t n_seed, int64_t seed_batch0, const void* sampled,
+                                   const void* batch, int64_t n_sampled, int index32, void* out_ids, void* stream) {
+  PYGB_CHECK(h && n_seed >= 0 && n_sampled >= 0 && seed_batch0 >= 0 && (seed || n_seed == 0) && (sampled || n_sampled == 0) &&
+                 (out_ids || n_sampled == 0),
+             PYGB200_ERR_ARG, "pygb200_relabel_ids: null / negative argument");
+  std::lock_guard<std::mutex> lock(h->mu);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (int e = relabel_ids_locked(h, seed, n_seed, seed_batch0, sampled, batch, n_sampled, index32, out_ids, st)) return e;
+  return relabel_check_error(h, st);
+}
+
+extern "C" int pygb200_relabel_expand(pygb200_subgraph* h, const int64_t* seg_count_host, const int64_t* seg_row_host,
+                                      const int64_t* seg_pos_host, int64_t n_seg, const void* ids, int64_t n_ids, int index32,
+                                      void* out_row, void* out_col, void* stream) {
+  PYGB_CHECK(h && n_seg >= 0 && n_ids >= 0 && ((seg_count_host && seg_row_host && seg_pos_host) || n_seg == 0), PYGB200_ERR_ARG,
+             "pygb200_relabel_expand: null / negative argument");
+  i64 total = 0;
+  for (i64 i = 0; i < n_seg; ++i) {
+    PYGB_CHECK(seg_count_host[i] >= 0 && seg_pos_host[i] >= 0 && seg_pos_host[i] + seg_count_host[i] <= n_ids, PYGB200_ERR_ARG,
+               "relabel_expand: segment outside the id list");
+    total += seg_count_host[i];
+  }
+  if (total == 0) return PYGB200_OK;
+  PYGB_CHECK(ids && out_row && out_col, PYGB200_ERR_ARG, "pygb200_relabel_expand: null output");
+  std::lock_guard<std::mutex> lock(h->mu);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (int e = h->deg.ensure((size_t)n_seg * 8, 0, st)) return e;
+  if (int e = h->offs.ensure((size_t)n_seg * 8, 0, st)) return e;
+  if (int e = h->segs.ensure((size_t)n_seg * 16, 0, st)) return e;
+  if (int e = h->misc.ensure(64, 0, st)) return e;
+  i64* seg_row = h->segs.as<i64>();
+  i64* seg_pos = seg_row + n_seg;
+  PYGB_CUDA(cudaMemcpyAsync(h->deg.p, seg_count_host, (size_t)n_seg * 8, cudaMemcpyHostToDevice, st));
+  PYGB_CUDA(cudaMemcpyAsync(seg_row, seg_row_host, (size_t)n_seg * 8, cudaMemcpyHostToDevice, st));
+  PYGB_CUDA(cudaMemcpyAsync(seg_pos, seg_pos_host, (size_t)n_seg * 8, cudaMemcpyHostToDevice, st));
+  if (int e = scan_i64(h, h->deg.as<i64>(), h->offs.as<i64>(), n_seg, h->misc.as<i64>(), nullptr, 0, st)) return e;
+  const int gm = grid_for(total, NT, h->sm_count);
+  if (index32) k_rl_expand<int32_t><<<gm, NT, 0, st>>>(h->offs.as<i64>(), n_seg, total, seg_row, seg_pos, (const int32_t*)ids, (int32_t*)out_row, (int32_t*)out_col);
+  else k_rl_expand<int64_t><<<gm, NT, 0, st>>>(h->offs.as<i64>(), n_seg, total, seg_row, seg_pos, (const int64_t*)ids, (int64_t*)out_row, (int64_t*)out_col);
   PYGB_LAUNCH_CHECK();
-  i64 err = 0;
-  PYGB_CUDA(cudaMemcpyAsync(&err, misc + 1, 8, cudaMemcpyDeviceToHost, st));
-  PYGB_CUDA(cudaStreamSynchronize(st));   // (also keeps `counts_host` alive until its copy is done)
-  PYGB_CHECK(err == 0, PYGB200_ERR_ARG, "relabel_neighborhood: node id outside [0, 2^40) or batch id outside [0, 2^23)");
+  PYGB_CUDA(cudaStreamSynchronize(st));   // the host lists may go away after the call
   return PYGB200_OK;
 }

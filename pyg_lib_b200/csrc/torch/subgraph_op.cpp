@@ -91,6 +91,132 @@ std::tuple<at::Tensor, at::Tensor> relabel_neighborhood_cuda(const at::Tensor& s
   return std::make_tuple(row, colv);
 }
 
+// pyg::hetero_relabel_neighborhood (hetero relabel<disjoint>, cpu/dist_relabel_kernel.cpp:97-273).
+// Every destination type's sampled list is consumed front to back (`slice_dict`, `:206-235`), so a node's id is its
+// rank among the first occurrences of [that type's seeds | that type's sampled list] — one pygb200_relabel_ids per
+// node type.  What remains is the schedule (which positions belong to which layer / edge type / source node, and the
+// source node's local index), pure bookkeeping over the int[][] count lists: done here on the host exactly in the
+// reference's loop order, then one pygb200_relabel_expand per edge type.
+typedef std::string node_type;
+typedef std::string rel_type;
+typedef std::tuple<std::string, std::string, std::string> edge_type;
+
+std::tuple<c10::Dict<rel_type, at::Tensor>, c10::Dict<rel_type, at::Tensor>> hetero_relabel_neighborhood_cuda(
+    const std::vector<node_type>& node_types, const std::vector<edge_type>& edge_types, const c10::Dict<node_type, at::Tensor>& seed_dict,
+    const c10::Dict<node_type, at::Tensor>& sampled_nodes_with_duplicates_dict,
+    const c10::Dict<rel_type, std::vector<std::vector<int64_t>>>& num_sampled_neighbors_per_node_dict,
+    const c10::Dict<node_type, int64_t>& num_nodes_dict, const std::optional<c10::Dict<node_type, at::Tensor>>& batch_dict, bool csc,
+    bool disjoint) {
+  TORCH_CHECK(seed_dict.size() > 0, "hetero_relabel_neighborhood: empty 'seed_dict'");
+  TORCH_CHECK(!edge_types.empty(), "hetero_relabel_neighborhood: empty 'edge_types'");
+  const at::Tensor& first = seed_dict.begin()->value();
+  TORCH_CHECK(first.is_cuda(), "pyg_lib_b200: hetero_relabel_neighborhood expects CUDA tensors (no CPU fallback)");
+  const auto st = first.scalar_type();
+  const auto dev = first.device();
+  TORCH_CHECK(st == at::kLong || st == at::kInt, "hetero_relabel_neighborhood: index tensors must be int64 or int32");
+  if (disjoint) TORCH_CHECK(batch_dict.has_value(), "Batch needs to be specified to create disjoint subgraphs");
+  (void)num_nodes_dict;
+  auto rel_of = [](const edge_type& k) { return std::get<0>(k) + "__" + std::get<1>(k) + "__" + std::get<2>(k); };
+  auto check = [&](const at::Tensor& t, const char* what) {
+    TORCH_CHECK(t.is_contiguous(), "Non-contiguous '", what, "'");
+    TORCH_CHECK(t.scalar_type() == st && t.device() == dev && t.dim() == 1, "hetero_relabel_neighborhood: '", what,
+                "' must be one-dimensional and match the seeds in dtype and device");
+  };
+
+  c10::cuda::CUDAGuard guard(dev);
+  cudaStream_t stream = at::cuda::getCurrentCUDAStream();
+  pygb200_subgraph* h = get_handle(dev.index(), stream);
+  const int idx32 = st == at::kInt;
+
+  // ---- ids per node type; disjoint batch ids of the seeds run over seed_dict in its order (`:180-193`)
+  std::map<node_type, int64_t> batch0;
+  int64_t nb = 0;
+  for (const auto& kv : seed_dict) { batch0[kv.key()] = nb; nb += kv.value().numel(); }
+  std::map<node_type, at::Tensor> ids;
+  for (const auto& t : node_types) {
+    TORCH_CHECK(sampled_nodes_with_duplicates_dict.contains(t), "hetero_relabel_neighborhood: no sampled nodes for node type '", t, "'");
+    const at::Tensor sampled = sampled_nodes_with_duplicates_dict.at(t);
+    check(sampled, "sampled_nodes_with_duplicates");
+    at::Tensor seed;
+    if (seed_dict.contains(t)) { seed = seed_dict.at(t); check(seed, "seed"); }
+    at::Tensor batch;
+    if (disjoint) {
+      TORCH_CHECK(batch_dict->contains(t), "hetero_relabel_neighborhood: no batch vector for node type '", t, "'");
+      batch = batch_dict->at(t);
+      check(batch, "batch");
+      TORCH_CHECK(batch.numel() == sampled.numel(), "Each node must belong to a subgraph");
+    }
+    at::Tensor out = at::empty({sampled.numel()}, sampled.options());
+    PYGB_TORCH_CALL(pygb200_relabel_ids(h, seed.defined() ? seed.data_ptr() : nullptr, seed.defined() ? seed.numel() : 0,
+                                        batch0.count(t) ? batch0[t] : 0, sampled.data_ptr(), disjoint ? batch.data_ptr() : nullptr,
+                                        sampled.numel(), idx32, out.data_ptr(), stream));
+    ids[t] = out;
+  }
+
+  // ---- the schedule (`:195-259`)
+  const size_t R = edge_types.size();
+  std::vector<const std::vector<std::vector<int64_t>>*> counts(R);
+  std::vector<std::vector<std::vector<int64_t>>> counts_store(R);
+  for (size_t r = 0; r < R; ++r) {
+    const rel_type rk = rel_of(edge_types[r]);
+    TORCH_CHECK(num_sampled_neighbors_per_node_dict.contains(rk), "hetero_relabel_neighborhood: no neighbour counts for '", rk, "'");
+    counts_store[r] = num_sampled_neighbors_per_node_dict.at(rk);
+    counts[r] = &counts_store[r];
+    TORCH_CHECK(!counts[r]->empty(), "hetero_relabel_neighborhood: empty layer list for '", rk, "'");
+  }
+  const size_t L = counts[0]->size();
+  for (size_t r = 0; r < R; ++r) TORCH_CHECK(counts[r]->size() >= L, "hetero_relabel_neighborhood: layer lists differ in length");
+  std::map<node_type, int64_t> cursor, src_off;
+  for (const auto& t : node_types) { cursor[t] = 0; src_off[t] = 0; }
+  std::vector<std::pair<int64_t, int64_t>> src_slice(R);
+  for (size_t r = 0; r < R; ++r) src_slice[r] = {0, (int64_t)(*counts[r])[0].size()};
+  std::vector<std::vector<int64_t>> seg_count(R), seg_row(R), seg_pos(R);
+  for (size_t ell = 0; ell < L; ++ell) {
+    for (size_t r = 0; r < R; ++r) {
+      const auto& k = edge_types[r];
+      const node_type& dst = !csc ? std::get<2>(k) : std::get<0>(k);
+      TORCH_CHECK(cursor.count(dst), "hetero_relabel_neighborhood: edge type with unknown node type '", dst, "'");
+      const auto& cl = (*counts[r])[ell];
+      const int64_t begin_i = src_slice[r].first, end_i = src_slice[r].second;
+      TORCH_CHECK((int64_t)cl.size() >= end_i - begin_i, "hetero_relabel_neighborhood: too few neighbour counts in a layer");
+      for (int64_t i = begin_i; i < end_i; ++i) {
+        const int64_t c = cl[(size_t)(i - begin_i)];
+        TORCH_CHECK(c >= 0, "hetero_relabel_neighborhood: negative neighbour count");
+        if (c > 0) { seg_count[r].push_back(c); seg_row[r].push_back(i); seg_pos[r].push_back(cursor[dst]); }
+        cursor[dst] += c;
+      }
+    }
+    if (ell + 1 < L) {
+      for (size_t r = 0; r < R; ++r) {
+        const node_type& src = !csc ? std::get<0>(edge_types[r]) : std::get<2>(edge_types[r]);
+        src_off[src] = std::max(src_off[src], src_slice[r].second);
+      }
+      for (size_t r = 0; r < R; ++r) {
+        const node_type& src = !csc ? std::get<0>(edge_types[r]) : std::get<2>(edge_types[r]);
+        src_slice[r] = {src_off[src], src_off[src] + (int64_t)(*counts[r])[ell + 1].size()};
+      }
+    }
+  }
+  for (const auto& t : node_types)
+    TORCH_CHECK(cursor[t] <= ids[t].numel(), "hetero_relabel_neighborhood: more neighbours counted than sampled nodes given for '", t, "'");
+
+  // ---- rows / cols per edge type
+  c10::Dict<rel_type, at::Tensor> out_row, out_col;
+  for (size_t r = 0; r < R; ++r) {
+    const auto& k = edge_types[r];
+    const node_type& dst = !csc ? std::get<2>(k) : std::get<0>(k);
+    int64_t total = 0;
+    for (const int64_t c : seg_count[r]) total += c;
+    at::Tensor row = at::empty({total}, first.options()), colv = at::empty({total}, first.options());
+    PYGB_TORCH_CALL(pygb200_relabel_expand(h, seg_count[r].data(), seg_row[r].data(), seg_pos[r].data(), (int64_t)seg_count[r].size(),
+                                           ids[dst].data_ptr(), ids[dst].numel(), idx32, row.data_ptr(), colv.data_ptr(), stream));
+    if (csc) std::swap(row, colv);   // get_sampled_edges, `:16-27`
+    out_row.insert(rel_of(k), row);
+    out_col.insert(rel_of(k), colv);
+  }
+  return std::make_tuple(out_row, out_col);
+}
+
 }  // namespace
 
 TORCH_LIBRARY_FRAGMENT(pyg, m) {
@@ -103,11 +229,23 @@ TORCH_LIBRARY_FRAGMENT(pyg, m) {
       "int "
       "num_nodes, Tensor? batch = None, bool csc = False, bool disjoint = "
       "False) -> (Tensor, Tensor)"));
+  m.def(TORCH_SELECTIVE_SCHEMA(   // pyg_lib/csrc/sampler/dist_relabel.cpp:77-83
+      "pyg::hetero_relabel_neighborhood(str[] node_types, (str, str, str)[] "
+      "edge_types, Dict(str, Tensor) seed_dict, Dict(str, Tensor) "
+      "sampled_nodes_with_duplicates_dict, Dict(str, int[][]) "
+      "num_sampled_neighbors_per_node_dict, Dict(str, int) num_nodes_dict, "
+      "Dict(str, Tensor)? batch_dict = None, bool csc = False, bool disjoint = "
+      "False) -> (Dict(str, Tensor), Dict(str, Tensor))"));
 }
 
 TORCH_LIBRARY_IMPL(pyg, CUDA, m) {
   m.impl(TORCH_SELECTIVE_NAME("pyg::subgraph"), TORCH_FN(subgraph_cuda));
   m.impl(TORCH_SELECTIVE_NAME("pyg::relabel_neighborhood"), TORCH_FN(relabel_neighborhood_cuda));
+}
+
+// dict arguments carry no backend key (as for hetero_neighbor_sample): BackendSelect, the kernel checks devices itself
+TORCH_LIBRARY_IMPL(pyg, BackendSelect, m) {
+  m.impl(TORCH_SELECTIVE_NAME("pyg::hetero_relabel_neighborhood"), TORCH_FN(hetero_relabel_neighborhood_cuda));
 }
 
 }  // namespace sampler

@@ -309,3 +309,43 @@ def build_relabel(case, oracle_dist):
     if dc.get('disjoint', False):
         return seed, node[S:, 1].contiguous(), counts, rowptr.numel() - 1, node[S:, 0].contiguous(), case.get('csc', False), True
     return seed, node[S:].contiguous(), counts, rowptr.numel() - 1, None, case.get('csc', False), False
+
+
+# pyg::hetero_relabel_neighborhood: synthetic inputs (the op does not need a graph): random seeds, random per-layer
+# neighbour counts per (edge type, source node) and random sampled ids per destination type
+HETERO_RELABEL_CASES: Dict[str, dict] = {
+    'two_types': dict(node_types=['a', 'b'], edge_types=[('a', 'x', 'b'), ('b', 'y', 'a'), ('a', 'z', 'a')],
+                      seeds={'a': 5, 'b': 3}, layers=[{'a': None, 'b': None}, {'a': 9, 'b': 7}], id_range=40, rng=1),
+    'two_types_csc': dict(node_types=['a', 'b'], edge_types=[('a', 'x', 'b'), ('b', 'y', 'a'), ('a', 'z', 'a')],
+                          seeds={'a': 5, 'b': 3}, layers=[{'a': None, 'b': None}, {'a': 9, 'b': 7}], id_range=40, rng=2, csc=True),
+    'one_seed_type_3_layers': dict(node_types=['p', 'q', 'r'], edge_types=[('p', 'w', 'q'), ('q', 'v', 'p'), ('q', 'u', 'r'), ('r', 't', 'q')],
+                                   seeds={'p': 16}, layers=[{'p': None, 'q': 0, 'r': 0}, {'p': 3, 'q': 30, 'r': 5}, {'p': 20, 'q': 11, 'r': 17}],
+                                   id_range=200, rng=3),
+    'disjoint': dict(node_types=['a', 'b'], edge_types=[('a', 'x', 'b'), ('b', 'y', 'a')], seeds={'a': 4, 'b': 6},
+                     layers=[{'a': None, 'b': None}, {'a': 8, 'b': 5}], id_range=12, rng=4, disjoint=True),
+}
+
+
+def build_hetero_relabel(case):
+    """(node_types, edge_types, seed_dict, sampled_dict, counts_dict {rel: [[...] per layer]}, num_nodes_dict, batch_dict|None,
+    csc, disjoint).  layers[l][t] = number of source nodes of type t in layer l (None: its seeds)."""
+    g = torch.Generator().manual_seed(case['rng'])
+    csc, disjoint = case.get('csc', False), case.get('disjoint', False)
+    nt, et = case['node_types'], case['edge_types']
+    R = case['id_range']
+    seed_dict = {t: torch.randint(0, R, (n,), generator=g) for t, n in case['seeds'].items()}
+    counts = {'__'.join(k): [] for k in et}
+    total = {t: 0 for t in nt}
+    n_batches = sum(case['seeds'].values())
+    for layer in case['layers']:
+        for k in et:
+            src, dst = (k[2], k[0]) if csc else (k[0], k[2])
+            n_src = layer[src]
+            if n_src is None:
+                n_src = case['seeds'].get(src, 0)
+            c = torch.randint(0, 4, (n_src,), generator=g).tolist()
+            counts['__'.join(k)].append(c)
+            total[dst] += sum(c)
+    sampled = {t: torch.randint(0, R, (total[t],), generator=g) for t in nt}
+    batch = {t: torch.randint(0, max(n_batches, 1), (total[t],), generator=g) for t in nt} if disjoint else None
+    return nt, et, seed_dict, sampled, counts, {t: R for t in nt}, batch, csc, disjoint

@@ -67,6 +67,11 @@ def test_schemas_match_reference(built):
     assert str(torch.ops.pyg.relabel_neighborhood.default._schema) == (   # sampler/dist_relabel.cpp:71-76
         'pyg::relabel_neighborhood(Tensor seed, Tensor sampled_nodes_with_duplicates, int[] num_sampled_neighbors_per_node, '
         'int num_nodes, Tensor? batch=None, bool csc=False, bool disjoint=False) -> (Tensor, Tensor)')
+    assert str(torch.ops.pyg.hetero_relabel_neighborhood.default._schema) == (   # sampler/dist_relabel.cpp:77-83
+        'pyg::hetero_relabel_neighborhood(str[] node_types, (str, str, str)[] edge_types, Dict(str, Tensor) seed_dict, '
+        'Dict(str, Tensor) sampled_nodes_with_duplicates_dict, Dict(str, int[][]) num_sampled_neighbors_per_node_dict, '
+        'Dict(str, int) num_nodes_dict, Dict(str, Tensor)? batch_dict=None, bool csc=False, bool disjoint=False) -> '
+        '(Dict(str, Tensor), Dict(str, Tensor))')
     assert str(torch.ops.pyg.grouped_matmul.default._schema) == 'pyg::grouped_matmul(Tensor[] input, Tensor[] other) -> Tensor[]'
     assert torch.ops.pyg.cuda_version() >= 12000
 

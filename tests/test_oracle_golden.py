@@ -246,3 +246,15 @@ def test_relabel_oracle_matches_reference_fixture(name):
         assert r[0].tolist() == [0, 0, 1, 1] and r[1].tolist() == [2, 1, 0, 3]
     if name == 'kat_disjoint':
         assert r[0].tolist() == [0, 0, 1, 1] and r[1].tolist() == [2, 3, 4, 5]
+
+
+# ------------------------------------------------------------------------------------ hetero_relabel_neighborhood
+from graphs import HETERO_RELABEL_CASES, build_hetero_relabel  # noqa: E402
+
+
+@pytest.mark.parametrize('name', list(HETERO_RELABEL_CASES))
+def test_hetero_relabel_oracle_matches_reference_fixture(name):
+    G = np.load(osp.join(osp.dirname(osp.abspath(__file__)), 'golden', 'hetero_relabel_outputs.npz'))
+    r = O.hetero_relabel_neighborhood(*build_hetero_relabel(HETERO_RELABEL_CASES[name]))
+    for k in r[0]:
+        assert np.array_equal(r[0][k].numpy(), G[f'{name}/row/{k}']) and np.array_equal(r[1][k].numpy(), G[f'{name}/col/{k}']), k

@@ -142,3 +142,21 @@ def test_relabel_neighborhood_errors(lib):
         torch.ops.pyg.relabel_neighborhood(seed, torch.tensor([1, 3], device=DEV), [2, 2], 6, None, False, False)
     out = torch.ops.pyg.relabel_neighborhood(seed, torch.tensor([1, 3, 2, 4], device=DEV), [2, 2], 6, None, False, False)
     assert out[0].tolist() == [0, 0, 1, 1] and out[1].tolist() == [2, 1, 0, 3]
+
+
+# ------------------------------------------------------------------------------------ pyg::hetero_relabel_neighborhood
+from graphs import HETERO_RELABEL_CASES, build_hetero_relabel  # noqa: E402
+
+
+@pytest.mark.parametrize('name', list(HETERO_RELABEL_CASES))
+@pytest.mark.parametrize('dtype', [torch.int64, torch.int32])
+def test_hetero_relabel_neighborhood_golden(lib, name, dtype):
+    G = np.load(osp.join(HERE, 'golden', 'hetero_relabel_outputs.npz'))
+    nt, et, seed_d, sampled_d, counts_d, nn_d, batch_d, csc, disjoint = build_hetero_relabel(HETERO_RELABEL_CASES[name])
+    dv = lambda d: None if d is None else {k: v.to(DEV, dtype) for k, v in d.items()}  # noqa: E731
+    out = torch.ops.pyg.hetero_relabel_neighborhood(nt, et, dv(seed_d), dv(sampled_d), counts_d, nn_d, dv(batch_d), csc, disjoint)
+    assert set(out[0].keys()) == {'__'.join(k) for k in et}
+    for k in out[0]:
+        assert out[0][k].dtype == dtype
+        assert np.array_equal(out[0][k].cpu().numpy(), G[f'{name}/row/{k}']), k
+        assert np.array_equal(out[1][k].cpu().numpy(), G[f'{name}/col/{k}']), k
