@@ -286,6 +286,24 @@ int pygb200_relabel_expand(pygb200_subgraph* h, const int64_t* seg_count_host, c
                            const int64_t* seg_pos_host, int64_t n_seg, const void* ids, int64_t n_ids, int index32,
                            void* out_row, void* out_col, void* stream);
 
+/* merge_sampler_outputs (pyg_lib/csrc/sampler/cpu/dist_merge_outputs_kernel.cpp:15-137): the per-partition outputs of
+ * pyg::dist_neighbor_sample are put back into the order of the seeds.  Seed j was sampled as the partition_orders[j]-th
+ * seed of partition partition_ids[j]; its neighbours are node_ids[p][c[o] : c[o+1]] and edge_ids[p][c[o]-c[0] : c[o+1]-c[0]]
+ * (c = that partition's cumsum_neighbors_per_node).
+ *   pygb200_merge_plan      HOST arithmetic only: cumsum lists flattened (list p = cumsum_flat[cumsum_off[p] : cumsum_off[p+1]])
+ *                           -> per seed the begin in its partition's node / edge ids and the neighbour count
+ *                           (= num_sampled_neighbors_per_node); validates against the arrays' lengths;
+ *   pygb200_segment_gather  out = concatenation of n_seg segments, segment s = seg_count[s] elements of device array
+ *                           src_ptrs[seg_src[s]] from seg_begin[s] (broadcast != 0: seg_count[s] copies of that one element,
+ *                           used for the batch vector).  Lists are HOST arrays; uses the scratch of a subgraph handle. */
+int pygb200_merge_plan(const int64_t* cumsum_flat, const int64_t* cumsum_off, int64_t num_partitions,
+                       const int64_t* partition_ids, const int64_t* partition_orders, int64_t p_size,
+                       const int64_t* node_numel, const int64_t* edge_numel, int64_t* seg_node_begin,
+                       int64_t* seg_edge_begin, int64_t* seg_count);
+int pygb200_segment_gather(pygb200_subgraph* h, const void* const* src_ptrs_host, int64_t n_src, const int64_t* seg_src_host,
+                           const int64_t* seg_begin_host, const int64_t* seg_count_host, int64_t n_seg, int broadcast,
+                           int index32, void* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

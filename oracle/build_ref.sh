@@ -7,8 +7,8 @@
 # file we supply is a 2-line stand-in for the cmake-generated pyg_lib/csrc/config.h
 # (config.h.in: WITH_MKL_BLAS()/NO_METIS() both 0 == the reference's default build).
 #
-# The reference's own build system (cmake + METIS + CUTLASS ...) is NOT run: g++ on the 12 files
-# below is enough for pyg::neighbor_sample, pyg::hetero_neighbor_sample, pyg::subgraph, pyg::relabel_neighborhood, pyg::segment_matmul,
+# The reference's own build system (cmake + METIS + CUTLASS ...) is NOT run: g++ on the 14 files
+# below is enough for pyg::neighbor_sample, pyg::hetero_neighbor_sample, pyg::subgraph, pyg::relabel_neighborhood, pyg::merge_sampler_outputs, pyg::segment_matmul,
 # pyg::grouped_matmul (CPU + Autograd keys).
 set -euo pipefail
 REF=${REF:-/root/reference}
@@ -33,6 +33,8 @@ pyg_lib/csrc/utils/check.cpp
 pyg_lib/csrc/utils/convert.cpp
 pyg_lib/csrc/sampler/neighbor.cpp
 pyg_lib/csrc/sampler/cpu/neighbor_kernel.cpp
+pyg_lib/csrc/sampler/dist_merge_outputs.cpp
+pyg_lib/csrc/sampler/cpu/dist_merge_outputs_kernel.cpp
 pyg_lib/csrc/sampler/dist_relabel.cpp
 pyg_lib/csrc/sampler/cpu/dist_relabel_kernel.cpp
 pyg_lib/csrc/sampler/subgraph.cpp

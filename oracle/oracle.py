@@ -428,3 +428,23 @@ def hetero_relabel_neighborhood(node_types: List[str], edge_types: List[Tuple[st
         r, c = torch.tensor(rows[k], dtype=dt), torch.tensor(cols[k], dtype=dt)
         out_row[rel(k)], out_col[rel(k)] = (c, r) if csc else (r, c)
     return out_row, out_col
+
+
+def merge_sampler_outputs(node_ids: List[torch.Tensor], edge_ids: List[torch.Tensor], cumsum_neighbors_per_node: List[List[int]],
+                          partition_ids: List[int], partition_orders: List[int], num_partitions: int, num_neighbors: int,
+                          batch: Optional[torch.Tensor] = None, disjoint: bool = False):
+    """Oracle for pyg::merge_sampler_outputs (merge_outputs<disjoint>, cpu/dist_merge_outputs_kernel.cpp:15-137): seed j's
+    neighbours are node_ids[p][c[o]:c[o+1]] and edge_ids[p][c[o]-c[0]:c[o+1]-c[0]] with p = partition_ids[j],
+    o = partition_orders[j], c = cumsum_neighbors_per_node[p] (`:79-92`); the outputs are their concatenation in seed
+    order (the reference pads every seed to `offset` entries with -1 and removes the -1 again, `:60-64,107-122`)."""
+    nodes, edges, batches, counts = [], [], [], []
+    for j, (p, o) in enumerate(zip(partition_ids, partition_orders)):
+        c = cumsum_neighbors_per_node[p]
+        b, e = c[o], c[o + 1]
+        nodes.append(node_ids[p][b:e]); edges.append(edge_ids[p][b - c[0]:e - c[0]])
+        if disjoint:
+            batches.append(batch[j].repeat(e - b))
+        counts.append(e - b)
+    dt = node_ids[0].dtype
+    cat = lambda xs: torch.cat(xs) if xs else torch.zeros(0, dtype=dt)  # noqa: E731
+    return cat(nodes), cat(edges), (cat(batches) if disjoint else None), counts

@@ -234,6 +234,23 @@ __global__ void __launch_bounds__(NT) k_rl_expand(const i64* __restrict__ offs, 
   }
 }
 
+// merge_sampler_outputs: output element i lies in segment s (the last s with offs[s] <= i) and is a copy of element
+// seg_begin[s] + (i - offs[s]) of source array seg_src[s] (broadcast: of element seg_begin[s] itself)
+template <typename idx_t>
+__global__ void __launch_bounds__(NT) k_seg_gather(const i64* __restrict__ offs, i64 n_seg, i64 M, const i64* __restrict__ seg_src,
+                                                    const i64* __restrict__ seg_begin, const idx_t* const* __restrict__ src_table, int broadcast,
+                                                    idx_t* __restrict__ out) {
+  for (i64 i = (i64)blockIdx.x * NT + threadIdx.x; i < M; i += (i64)gridDim.x * NT) {
+    i64 lo = 0, hi = n_seg;
+    while (lo < hi) {
+      const i64 mid = lo + ((hi - lo) >> 1);
+      if (offs[mid] > i) hi = mid; else lo = mid + 1;
+    }
+    const i64 sgm = lo - 1;
+    out[i] = src_table[seg_src[sgm]][seg_begin[sgm] + (broadcast ? 0 : i - offs[sgm])];
+  }
+}
+
 }  // namespace
 }  // namespace pygb200
 
@@ -497,6 +514,68 @@ extern "C" int pygb200_relabel_expand(pygb200_subgraph* h, const int64_t* seg_co
   const int gm = grid_for(total, NT, h->sm_count);
   if (index32) k_rl_expand<int32_t><<<gm, NT, 0, st>>>(h->offs.as<i64>(), n_seg, total, seg_row, seg_pos, (const int32_t*)ids, (int32_t*)out_row, (int32_t*)out_col);
   else k_rl_expand<int64_t><<<gm, NT, 0, st>>>(h->offs.as<i64>(), n_seg, total, seg_row, seg_pos, (const int64_t*)ids, (int64_t*)out_row, (int64_t*)out_col);
+  PYGB_LAUNCH_CHECK();
+  PYGB_CUDA(cudaStreamSynchronize(st));   // the host lists may go away after the call
+  return PYGB200_OK;
+}
+
+// ---- merge_sampler_outputs (pyg_lib/csrc/sampler/cpu/dist_merge_outputs_kernel.cpp:15-137)
+// Host arithmetic only (no CUDA call): where seed j's neighbours sit in the output of the partition that sampled it.
+extern "C" int pygb200_merge_plan(const int64_t* cumsum_flat, const int64_t* cumsum_off, int64_t num_partitions,
+                                  const int64_t* partition_ids, const int64_t* partition_orders, int64_t p_size,
+                                  const int64_t* node_numel, const int64_t* edge_numel, int64_t* seg_node_begin,
+                                  int64_t* seg_edge_begin, int64_t* seg_count) {
+  PYGB_CHECK(num_partitions >= 0 && p_size >= 0 && (p_size == 0 || (cumsum_flat && cumsum_off && partition_ids && partition_orders &&
+                                                                    node_numel && edge_numel && seg_node_begin && seg_edge_begin && seg_count)),
+             PYGB200_ERR_ARG, "pygb200_merge_plan: null / negative argument");
+  for (i64 j = 0; j < p_size; ++j) {
+    const i64 p = partition_ids[j], o = partition_orders[j];
+    PYGB_CHECK(p >= 0 && p < num_partitions, PYGB200_ERR_ARG, "merge_sampler_outputs: partition id out of range");
+    const int64_t* cs = cumsum_flat + cumsum_off[p];
+    const i64 len = cumsum_off[p + 1] - cumsum_off[p];
+    PYGB_CHECK(o >= 0 && o + 1 < len, PYGB200_ERR_ARG, "merge_sampler_outputs: sampling order outside the partition's cumulative counts");
+    // node ids start with the partition's seeds (cs[0] of them); edge ids have no such prefix (:85-92)
+    const i64 begin_node = cs[o], end_node = cs[o + 1], begin_edge = begin_node - cs[0];
+    PYGB_CHECK(end_node >= begin_node && begin_node >= 0 && end_node <= node_numel[p] && begin_edge >= 0 &&
+                   begin_edge + (end_node - begin_node) <= edge_numel[p],
+               PYGB200_ERR_ARG, "merge_sampler_outputs: cumulative counts do not fit the partition's outputs");
+    seg_node_begin[j] = begin_node;
+    seg_edge_begin[j] = begin_edge;
+    seg_count[j] = end_node - begin_node;
+  }
+  return PYGB200_OK;
+}
+
+extern "C" int pygb200_segment_gather(pygb200_subgraph* h, const void* const* src_ptrs_host, int64_t n_src, const int64_t* seg_src_host,
+                                      const int64_t* seg_begin_host, const int64_t* seg_count_host, int64_t n_seg, int broadcast,
+                                      int index32, void* out, void* stream) {
+  PYGB_CHECK(h && n_src >= 0 && n_seg >= 0 && (n_seg == 0 || (src_ptrs_host && seg_src_host && seg_begin_host && seg_count_host)),
+             PYGB200_ERR_ARG, "pygb200_segment_gather: null / negative argument");
+  i64 total = 0;
+  for (i64 i = 0; i < n_seg; ++i) {
+    PYGB_CHECK(seg_count_host[i] >= 0 && seg_begin_host[i] >= 0 && seg_src_host[i] >= 0 && seg_src_host[i] < n_src, PYGB200_ERR_ARG,
+               "segment_gather: bad segment");
+    total += seg_count_host[i];
+  }
+  if (total == 0) return PYGB200_OK;
+  PYGB_CHECK(out != nullptr, PYGB200_ERR_ARG, "pygb200_segment_gather: null output");
+  std::lock_guard<std::mutex> lock(h->mu);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (int e = h->deg.ensure((size_t)n_seg * 8, 0, st)) return e;
+  if (int e = h->offs.ensure((size_t)n_seg * 8, 0, st)) return e;
+  if (int e = h->segs.ensure((size_t)(2 * n_seg + n_src) * 8, 0, st)) return e;
+  if (int e = h->misc.ensure(64, 0, st)) return e;
+  i64* seg_src = h->segs.as<i64>();
+  i64* seg_begin = seg_src + n_seg;
+  void** table = reinterpret_cast<void**>(seg_begin + n_seg);
+  PYGB_CUDA(cudaMemcpyAsync(h->deg.p, seg_count_host, (size_t)n_seg * 8, cudaMemcpyHostToDevice, st));
+  PYGB_CUDA(cudaMemcpyAsync(seg_src, seg_src_host, (size_t)n_seg * 8, cudaMemcpyHostToDevice, st));
+  PYGB_CUDA(cudaMemcpyAsync(seg_begin, seg_begin_host, (size_t)n_seg * 8, cudaMemcpyHostToDevice, st));
+  PYGB_CUDA(cudaMemcpyAsync(table, src_ptrs_host, (size_t)n_src * 8, cudaMemcpyHostToDevice, st));
+  if (int e = scan_i64(h, h->deg.as<i64>(), h->offs.as<i64>(), n_seg, h->misc.as<i64>(), nullptr, 0, st)) return e;
+  const int g = grid_for(total, NT, h->sm_count);
+  if (index32) k_seg_gather<int32_t><<<g, NT, 0, st>>>(h->offs.as<i64>(), n_seg, total, seg_src, seg_begin, (const int32_t* const*)table, broadcast, (int32_t*)out);
+  else k_seg_gather<int64_t><<<g, NT, 0, st>>>(h->offs.as<i64>(), n_seg, total, seg_src, seg_begin, (const int64_t* const*)table, broadcast, (int64_t*)out);
   PYGB_LAUNCH_CHECK();
   PYGB_CUDA(cudaStreamSynchronize(st));   // the host lists may go away after the call
   return PYGB200_OK;

@@ -217,6 +217,65 @@ std::tuple<c10::Dict<rel_type, at::Tensor>, c10::Dict<rel_type, at::Tensor>> het
   return std::make_tuple(out_row, out_col);
 }
 
+// pyg::merge_sampler_outputs (merge_outputs<disjoint>, cpu/dist_merge_outputs_kernel.cpp:15-137) on CUDA tensors: the
+// plan is host arithmetic over the int[] / int[][] arguments (pygb200_merge_plan), the data moves in three segment
+// gathers (node ids, edge ids, batch broadcast).  The reference pads every seed's slot with -1 and strips all -1
+// afterwards; ids are never -1, so the result is the plain concatenation.
+std::tuple<at::Tensor, at::Tensor, std::optional<at::Tensor>, std::vector<int64_t>> merge_sampler_outputs_cuda(
+    const std::vector<at::Tensor>& node_ids, const std::vector<at::Tensor>& edge_ids,
+    const std::vector<std::vector<int64_t>>& cumsum_neighbors_per_node, const std::vector<int64_t>& partition_ids,
+    const std::vector<int64_t>& partition_orders, int64_t num_partitions, int64_t num_neighbors, const std::optional<at::Tensor>& batch,
+    bool disjoint) {
+  (void)num_neighbors;   // (only sizes the reference's padded scratch)
+  TORCH_CHECK(partition_ids.size() == partition_orders.size(), "Every partition ID must be assigned a sampling order");
+  if (disjoint) TORCH_CHECK(batch.has_value(), "Disjoint sampling requires 'batch' to be specified");
+  const int64_t P = num_partitions;
+  TORCH_CHECK(P >= 1 && (int64_t)node_ids.size() >= P && (int64_t)edge_ids.size() >= P && (int64_t)cumsum_neighbors_per_node.size() >= P,
+              "merge_sampler_outputs: expected one node / edge tensor and one cumulative count list per partition");
+  TORCH_CHECK(node_ids[0].is_cuda(), "pyg_lib_b200: merge_sampler_outputs expects CUDA tensors (no CPU fallback)");
+  const auto st = node_ids[0].scalar_type();
+  const auto dev = node_ids[0].device();
+  TORCH_CHECK(st == at::kLong || st == at::kInt, "merge_sampler_outputs: index tensors must be int64 or int32");
+  auto check = [&](const at::Tensor& t, const char* what) {
+    TORCH_CHECK(t.defined() && t.is_contiguous() && t.dim() == 1 && t.scalar_type() == st && t.device() == dev, "merge_sampler_outputs: '",
+                what, "' must be contiguous, one-dimensional, of one dtype and on one device");
+  };
+  const int64_t n = (int64_t)partition_ids.size();
+  std::vector<int64_t> flat, off(P + 1, 0), node_numel(P), edge_numel(P);
+  std::vector<const void*> node_ptrs(P), edge_ptrs(P);
+  for (int64_t p = 0; p < P; ++p) {
+    check(node_ids[p], "node_ids"); check(edge_ids[p], "edge_ids");
+    node_numel[p] = node_ids[p].numel(); edge_numel[p] = edge_ids[p].numel();
+    node_ptrs[p] = node_ids[p].data_ptr(); edge_ptrs[p] = edge_ids[p].data_ptr();
+    flat.insert(flat.end(), cumsum_neighbors_per_node[p].begin(), cumsum_neighbors_per_node[p].end());
+    off[p + 1] = (int64_t)flat.size();
+  }
+  std::vector<int64_t> nb(n), eb(n), cnt(n);
+  PYGB_TORCH_CALL(pygb200_merge_plan(flat.data(), off.data(), P, partition_ids.data(), partition_orders.data(), n, node_numel.data(),
+                                     edge_numel.data(), nb.data(), eb.data(), cnt.data()));
+  int64_t total = 0;
+  for (const int64_t c : cnt) total += c;
+
+  c10::cuda::CUDAGuard guard(dev);
+  cudaStream_t stream = at::cuda::getCurrentCUDAStream();
+  pygb200_subgraph* h = get_handle(dev.index(), stream);
+  const int idx32 = st == at::kInt;
+  at::Tensor out_node = at::empty({total}, node_ids[0].options()), out_edge = at::empty({total}, node_ids[0].options());
+  PYGB_TORCH_CALL(pygb200_segment_gather(h, node_ptrs.data(), P, partition_ids.data(), nb.data(), cnt.data(), n, 0, idx32, out_node.data_ptr(), stream));
+  PYGB_TORCH_CALL(pygb200_segment_gather(h, edge_ptrs.data(), P, partition_ids.data(), eb.data(), cnt.data(), n, 0, idx32, out_edge.data_ptr(), stream));
+  std::optional<at::Tensor> out_batch = std::nullopt;
+  if (disjoint) {
+    check(*batch, "batch");
+    TORCH_CHECK(batch->numel() >= n, "merge_sampler_outputs: 'batch' needs one entry per seed");
+    out_batch = at::empty({total}, node_ids[0].options());
+    std::vector<int64_t> zero(n, 0), pos(n);
+    for (int64_t j = 0; j < n; ++j) pos[j] = j;
+    const void* bp[1] = {batch->data_ptr()};
+    PYGB_TORCH_CALL(pygb200_segment_gather(h, bp, 1, zero.data(), pos.data(), cnt.data(), n, 1, idx32, out_batch->data_ptr(), stream));
+  }
+  return std::make_tuple(out_node, out_edge, out_batch, cnt);
+}
+
 }  // namespace
 
 TORCH_LIBRARY_FRAGMENT(pyg, m) {
@@ -236,6 +295,11 @@ TORCH_LIBRARY_FRAGMENT(pyg, m) {
       "num_sampled_neighbors_per_node_dict, Dict(str, int) num_nodes_dict, "
       "Dict(str, Tensor)? batch_dict = None, bool csc = False, bool disjoint = "
       "False) -> (Dict(str, Tensor), Dict(str, Tensor))"));
+  m.def(TORCH_SELECTIVE_SCHEMA(   // pyg_lib/csrc/sampler/dist_merge_outputs.cpp:51-55
+      "pyg::merge_sampler_outputs(Tensor[] node_ids, Tensor[] edge_ids, "
+      "int[][] cumsum_neighbors_per_node, int[] partition_ids, int[] "
+      "partition_orders, int num_partitions, int num_neighbors, Tensor? "
+      "batch, bool disjoint) -> (Tensor, Tensor, Tensor?, int[])"));
 }
 
 TORCH_LIBRARY_IMPL(pyg, CUDA, m) {
@@ -246,6 +310,7 @@ TORCH_LIBRARY_IMPL(pyg, CUDA, m) {
 // dict arguments carry no backend key (as for hetero_neighbor_sample): BackendSelect, the kernel checks devices itself
 TORCH_LIBRARY_IMPL(pyg, BackendSelect, m) {
   m.impl(TORCH_SELECTIVE_NAME("pyg::hetero_relabel_neighborhood"), TORCH_FN(hetero_relabel_neighborhood_cuda));
+  m.impl(TORCH_SELECTIVE_NAME("pyg::merge_sampler_outputs"), TORCH_FN(merge_sampler_outputs_cuda));
 }
 
 }  // namespace sampler

@@ -349,3 +349,41 @@ def build_hetero_relabel(case):
     sampled = {t: torch.randint(0, R, (total[t],), generator=g) for t in nt}
     batch = {t: torch.randint(0, max(n_batches, 1), (total[t],), generator=g) for t in nt} if disjoint else None
     return nt, et, seed_dict, sampled, counts, {t: R for t in nt}, batch, csc, disjoint
+
+
+# pyg::merge_sampler_outputs: the seeds of a DIST_CASES-like problem are dealt to P partitions, every partition
+# samples its own seeds with dist_neighbor_sample, merge restores the seed order
+MERGE_CASES: Dict[str, dict] = {
+    # test/csrc/sampler/test_dist_merge_outputs.cpp:7-48 and :50-91
+    'kat': dict(node_ids=[[2, 7, 8], [0, 1, 4, 5, 6], [3, 9, 10]], edge_ids=[[17, 18], [14, 15, 16], [19, 20]],
+                cumsum=[[1, 3], [2, 4, 5], [1, 3]], partition_ids=[1, 1, 0, 2], partition_orders=[0, 1, 0, 0], k=2),
+    'kat_all': dict(node_ids=[[2, 7, 8], [0, 1, 4, 5, 6], [3, 9, 10, 11]], edge_ids=[[17, 18], [14, 15, 16], [19, 20, 21]],
+                    cumsum=[[1, 3], [2, 4, 5], [1, 4]], partition_ids=[1, 1, 0, 2], partition_orders=[0, 1, 0, 0], k=-1),
+    'rand_3parts': dict(graph=('rand', 2000, 20, 1), n_seeds=200, k=7, parts=3, rng_seed=8),
+    'rand_5parts_rep_disjoint': dict(graph=('rand', 1500, 12, 2), n_seeds=97, k=4, parts=5, rng_seed=9, replace=True, disjoint=True),
+    'rand_all_neighbors': dict(graph=('rand', 1200, 6, 4), n_seeds=60, k=-1, parts=4, rng_seed=10),
+}
+
+
+def build_merge(case, oracle_dist):
+    """(node_ids, edge_ids, cumsum lists, partition_ids, partition_orders, num_partitions, num_neighbors, batch|None, disjoint)"""
+    if 'node_ids' in case:
+        t = lambda x: torch.tensor(x, dtype=torch.int64)  # noqa: E731
+        return ([t(x) for x in case['node_ids']], [t(x) for x in case['edge_ids']], [list(c) for c in case['cumsum']],
+                list(case['partition_ids']), list(case['partition_orders']), len(case['node_ids']), case['k'], None, False)
+    rowptr, col, seed = build_homo(dict(graph=case['graph'], n_seeds=case['n_seeds'], num_neighbors=[1], rng_seed=0))
+    g = torch.Generator().manual_seed(case['rng_seed'])
+    P = case['parts']
+    part = torch.randint(0, P, (seed.numel(),), generator=g)
+    disjoint = case.get('disjoint', False)
+    node_ids, edge_ids, cums, orders = [], [], [], [0] * seed.numel()
+    torch.manual_seed(case['rng_seed'])
+    for p in range(P):
+        idx = (part == p).nonzero().flatten()
+        for o, j in enumerate(idx.tolist()):
+            orders[j] = o
+        # (merge reads node ids as one flat list: the plain node column, also for disjoint sampling)
+        node, eid, cum = oracle_dist(rowptr, col, seed[idx], case['k'], replace=case.get('replace', False), disjoint=False)
+        node_ids.append(node.contiguous()); edge_ids.append(eid.contiguous()); cums.append([int(x) for x in cum])
+    batch = torch.arange(seed.numel(), dtype=torch.int64) if disjoint else None
+    return node_ids, edge_ids, cums, part.tolist(), orders, P, case['k'], batch, disjoint

@@ -72,6 +72,9 @@ def test_schemas_match_reference(built):
         'Dict(str, Tensor) sampled_nodes_with_duplicates_dict, Dict(str, int[][]) num_sampled_neighbors_per_node_dict, '
         'Dict(str, int) num_nodes_dict, Dict(str, Tensor)? batch_dict=None, bool csc=False, bool disjoint=False) -> '
         '(Dict(str, Tensor), Dict(str, Tensor))')
+    assert str(torch.ops.pyg.merge_sampler_outputs.default._schema) == (   # sampler/dist_merge_outputs.cpp:51-55
+        'pyg::merge_sampler_outputs(Tensor[] node_ids, Tensor[] edge_ids, int[][] cumsum_neighbors_per_node, int[] partition_ids, '
+        'int[] partition_orders, int num_partitions, int num_neighbors, Tensor? batch, bool disjoint) -> (Tensor, Tensor, Tensor?, int[])')
     assert str(torch.ops.pyg.grouped_matmul.default._schema) == 'pyg::grouped_matmul(Tensor[] input, Tensor[] other) -> Tensor[]'
     assert torch.ops.pyg.cuda_version() >= 12000
 

@@ -258,3 +258,43 @@ def test_hetero_relabel_oracle_matches_reference_fixture(name):
     r = O.hetero_relabel_neighborhood(*build_hetero_relabel(HETERO_RELABEL_CASES[name]))
     for k in r[0]:
         assert np.array_equal(r[0][k].numpy(), G[f'{name}/row/{k}']) and np.array_equal(r[1][k].numpy(), G[f'{name}/col/{k}']), k
+
+
+# ------------------------------------------------------------------------------------ merge_sampler_outputs
+from graphs import MERGE_CASES, build_merge  # noqa: E402
+
+
+@pytest.mark.parametrize('name', list(MERGE_CASES))
+def test_merge_oracle_and_host_plan_match_reference_fixture(name):
+    """The oracle restatement AND the product's host-side plan (pygb200_merge_plan: pure arithmetic, callable without a
+    GPU; the gathers it drives are emulated with numpy here) against fixtures made by the reference
+    (KATs test/csrc/sampler/test_dist_merge_outputs.cpp:7-91 + partitioned random cases)."""
+    import ctypes as C
+    G = np.load(osp.join(osp.dirname(osp.abspath(__file__)), 'golden', 'merge_outputs.npz'))
+    a = build_merge(MERGE_CASES[name], O.dist_neighbor_sample)
+    r = O.merge_sampler_outputs(*a)
+    assert np.array_equal(r[0].numpy(), G[f'{name}/node']) and np.array_equal(r[1].numpy(), G[f'{name}/edge'])
+    assert list(r[3]) == G[f'{name}/counts'].tolist()
+    if a[8]:
+        assert np.array_equal(r[2].numpy(), G[f'{name}/batch'])
+    # ---- host plan of the product
+    from pyg_lib_b200.build import build
+    build(verbose=False)
+    lib = C.CDLL(osp.join(osp.dirname(osp.dirname(osp.abspath(__file__))), 'pyg_lib_b200', 'libpyg_b200.so'))
+    lib.pygb200_last_error.restype = C.c_char_p
+    node_ids, edge_ids, cums, pids, pords, P = a[0], a[1], a[2], a[3], a[4], a[5]
+    flat = [x for c in cums for x in c]
+    off = np.cumsum([0] + [len(c) for c in cums]).astype(np.int64)
+    n = len(pids)
+    arr = lambda x: (C.c_int64 * max(len(x), 1))(*x)  # noqa: E731
+    nb, eb, cnt = (C.c_int64 * max(n, 1))(), (C.c_int64 * max(n, 1))(), (C.c_int64 * max(n, 1))()
+    rc = lib.pygb200_merge_plan(arr(flat), arr(off.tolist()), C.c_int64(P), arr(pids), arr(pords), C.c_int64(n),
+                                arr([t.numel() for t in node_ids]), arr([t.numel() for t in edge_ids]), nb, eb, cnt)
+    assert rc == 0, lib.pygb200_last_error()
+    assert list(cnt)[:n] == G[f'{name}/counts'].tolist()
+    nodes = np.concatenate([node_ids[pids[j]].numpy()[nb[j]:nb[j] + cnt[j]] for j in range(n)]) if n else np.zeros(0, np.int64)
+    edges = np.concatenate([edge_ids[pids[j]].numpy()[eb[j]:eb[j] + cnt[j]] for j in range(n)]) if n else np.zeros(0, np.int64)
+    assert np.array_equal(nodes, G[f'{name}/node']) and np.array_equal(edges, G[f'{name}/edge'])
+    bad = arr([p + 100 for p in pids])
+    assert lib.pygb200_merge_plan(arr(flat), arr(off.tolist()), C.c_int64(P), bad, arr(pords), C.c_int64(n),
+                                  arr([t.numel() for t in node_ids]), arr([t.numel() for t in edge_ids]), nb, eb, cnt) != 0
