@@ -26,10 +26,17 @@ def load_library(lib_name: str) -> None:
     torch.ops.load_library(spec.origin)
 
 
-load_library('libpyg')
+def _building() -> bool:
+    """`python -m pyg_lib_b200.build` / `__graft_entry__.build()` import this package before the library exists."""
+    import sys
+    argv = getattr(sys, 'orig_argv', sys.argv)
+    return bool(os.getenv('PYG_LIB_B200_BUILDING', '')) or any(a == 'pyg_lib_b200.build' for a in argv)
 
-from . import ops  # noqa: E402
-from . import sampler  # noqa: E402
+
+if not _building():
+    load_library('libpyg')
+    from . import ops  # noqa: E402,F401
+    from . import sampler  # noqa: E402,F401
 
 
 def cuda_version() -> int:

@@ -13,4 +13,21 @@ TORCH_LIBRARY_FRAGMENT(pyg, m) {
   m.def("b200_kernel_launches", &b200_kernel_launches);
 }
 
+// CPU tensors: the reference registers CPU kernels for every op (e.g. sampler/cpu/neighbor_kernel.cpp:980-983,
+// ops/cpu/matmul_kernel.cpp:255-262); this library is the CUDA path only (north_star: no CPU fallback).  Instead of the
+// dispatcher's generic "could not run ... with arguments from the 'CPU' backend", every pyg:: op called with CPU
+// tensors raises one clear message that says what to do.
+static void cpu_not_supported(const c10::OperatorHandle& op, c10::DispatchKeySet, torch::jit::Stack*) {
+  TORCH_CHECK(false, "pyg_lib_b200: '", op.schema().name(), "' was called with CPU tensors. This build implements the CUDA "
+              "(sm_100a) path only and has no CPU fallback: move the graph / feature tensors to a CUDA device, or use the "
+              "stock pyg-lib package for CPU sampling (set PYG_LIB_B200_NO_ALIAS=1 to keep `import pyg_lib` from "
+              "resolving to this package).");
+}
+
+TORCH_LIBRARY_IMPL(pyg, CPU, m) {   // (the dispatcher has no per-namespace fallback: one registration per CUDA-key op)
+  for (const char* name : {"pyg::segment_matmul", "pyg::segment_matmul_bias", "pyg::segment_matmul_wgrad", "pyg::grouped_matmul",
+                           "pyg::neighbor_sample", "pyg::dist_neighbor_sample", "pyg::subgraph", "pyg::relabel_neighborhood"})
+    m.impl(name, torch::CppFunction::makeFromBoxedFunction<&cpu_not_supported>());
+}
+
 }  // namespace pyg

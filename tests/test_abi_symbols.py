@@ -153,3 +153,26 @@ def test_sampler_bounds_host_only(built):
         assert exp[0]['__'.join(et)].numel() <= ecaps[r]
     for t in node_types:
         assert exp[2][t].shape[0] <= ncaps[tix[t]]
+
+
+def test_cpu_tensors_raise_clearly():
+    """PyG sends CPU tensors to pyg-lib from loader workers; this build has no CPU kernels, so every
+    CUDA-key op must fail with one clear message (not a generic dispatcher error, never a silent fallback)."""
+    import pytest
+    import torch
+    import pyg_lib_b200 as P
+    rowptr, col, seed = torch.tensor([0, 1, 2]), torch.tensor([1, 0]), torch.tensor([0])
+    calls = [
+        lambda: P.sampler.neighbor_sample(rowptr, col, seed, [1]),
+        lambda: P.sampler.subgraph(rowptr, col, seed),
+        lambda: torch.ops.pyg.dist_neighbor_sample(rowptr, col, seed, 1),
+        lambda: P.ops.segment_matmul(torch.randn(4, 4), torch.tensor([0, 4]), torch.randn(1, 4, 4)),
+        lambda: P.ops.segment_matmul(torch.randn(4, 4, requires_grad=True), torch.tensor([0, 4]), torch.randn(1, 4, 4)),
+        lambda: P.ops.segment_matmul(torch.randn(4, 4), torch.tensor([0, 4]), torch.randn(1, 4, 4), bias=torch.randn(1, 4)),
+        lambda: P.ops.grouped_matmul([torch.randn(4, 4)], [torch.randn(4, 4)]),
+    ]
+    for f in calls:
+        with pytest.raises(RuntimeError, match='no CPU fallback'):
+            f()
+    with pytest.raises(RuntimeError, match='no CPU fallback|CUDA tensors'):
+        P.sampler.hetero_neighbor_sample({('a', 'to', 'a'): rowptr}, {('a', 'to', 'a'): col}, {'a': seed}, {('a', 'to', 'a'): [1]})
