@@ -172,21 +172,31 @@ int pygb200_sampler_run_temporal(pygb200_sampler* s, int32_t T, int32_t R, int32
                                  const pygb200_temporal* temporal);
 
 /* Frontier-sharded run for multi-GPU sampling of ONE batch (the reference's own split of
- * the work is dist_neighbor_sample -> merge -> relabel, neighbor_kernel.cpp:296-303,957-978).
- * Every rank holds the full CSR and calls this with identical arguments and identical engine state.
- * Per pass each rank counts the whole frontier (edge offsets and bit-stream positions are global),
- * draws only its contiguous slice of frontier nodes, and the callback all-gathers the drawn EDGE IDS
- * in place:  on return buf[seg_begin[q] .. seg_begin[q+1]) must hold rank q's elements for every q
- * (int64 elements, offsets relative to buf; seg_begin is a HOST array of world+1 entries; the call is
- * made on `stream`'s timeline: enqueue the collective on / synchronise it with that stream).
- * Dedup / relabel then run replicated, so every rank ends with the identical, reference-exact result.
- * Restrictions: fan-outs >= 0, world <= 64. */
+ * the work is dist_neighbor_sample -> merge -> relabel, neighbor_kernel.cpp:296-303,957-978,
+ * dist_relabel_kernel.cpp:30-94).  One process per GPU; every rank holds the full CSR and calls this with
+ * identical arguments and identical engine state, and every rank ends with the identical, reference-exact
+ * result.  Per pass each rank counts the whole frontier (edge offsets and bit-stream positions are global)
+ * and draws only its contiguous slice of frontier nodes.  Two transports:
+ *
+ *  (a) peer memory (`exchange` != NULL; homogeneous, non-disjoint, fan-outs >= 0, node ids < 2^32-1, world <= 16):
+ *      the sampling kernel stores the (dst, edge id) of its edges straight into every rank's exchange region
+ *      over NVLink (the all-gather of sampled edges is fused into the kernel), dedup is partitioned by key hash,
+ *      the per-edge refs are reduced slice-wise with coalesced peer loads/stores, and cross-GPU ordering uses
+ *      flag words in peer memory — no host sync and no collective call per hop.  `exchange` is a HOST
+ *      all-gather of small blobs (out[q*bytes .. (q+1)*bytes) = rank q's `mine`), called only when the exchange
+ *      regions are (re)allocated, to swap cudaIpcMemHandle_t's; it doubles as a host barrier.
+ *  (b) callback all-gather (`exchange` == NULL): the callback all-gathers the drawn EDGE IDS in place: on return
+ *      buf[seg_begin[q] .. seg_begin[q+1]) must hold rank q's elements for every q (int64 elements, offsets
+ *      relative to buf; seg_begin is a HOST array of world+1 entries; the call is made on `stream`'s timeline).
+ *      Dedup / relabel then run replicated.  Also covers disjoint runs; world <= 64. */
 typedef int (*pygb200_allgather_fn)(void* user, void* buf_dev, const int64_t* seg_begin, int32_t world,
                                     void* stream);
+typedef int (*pygb200_exchange_fn)(void* user, const void* mine_host, void* all_host, int64_t bytes);
 typedef struct {
   int32_t rank, world;
   pygb200_allgather_fn allgather;
   void* user;
+  pygb200_exchange_fn exchange;
 } pygb200_shard;
 int pygb200_sampler_run_sharded(pygb200_sampler* s, int32_t T, int32_t R, int32_t L,
                                 const pygb200_relation* rels_host, const void* const* seeds,

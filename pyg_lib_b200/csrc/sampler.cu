@@ -149,6 +149,13 @@ struct PassArgs {
   // publication of the run's counters + final engine state to the host (publish_run): by k_final, or — latency
   // path — already by the last pass's k_assign_s, as soon as the last counter is known
   i64* pub_host; i64* pub_zero; i64 pub_serial; int pub_words, pub_o_mt;
+  // ---- v2 schedule (sampler_v2.cuh): packed 32-bit table of the dst type, refs, optional peer-memory sharding
+  u64* pk; int pk_bits;            // slot = node id << 32 | value
+  u32* fref;                       // ref of every edge of the running pass
+  int xw, xr, x_eid64;             // world size (1 = single GPU), rank, wire type of edge ids
+  int v2_writeback, o_shard;
+  i64 x_off_bar, x_off_dst, x_off_eid, x_off_pref, x_off_fref;   // byte offsets inside an exchange region
+  unsigned char* xpeer[16];        // exchange region of every rank (own one included), peer-mapped
 };
 __device__ __forceinline__ i64 ldw(const i64* st, int w, i64 c) { return w >= 0 ? st[w] : c; }
 
@@ -513,31 +520,18 @@ __global__ void __launch_bounds__(NT) k_count(const PassArgs a) {
 // when its random value was already CHOSEN by an earlier draw — but only through the chosen values: every lane
 // takes one draw and the conflicts are settled with g shuffles.  Fan-outs beyond 32 go in rounds of 32 and
 // re-read what earlier rounds emitted.
-template <typename idx_t, bool PHASED>
-__device__ __forceinline__ void sample_node(const PassArgs& a, const NodeRec& r, i64 off, i64 pos0, i64 src_pos, i64 pbase,
-                                            int g, int gl, int gbase, unsigned gmask) {
-  const idx_t* __restrict__ col = (const idx_t*)a.col;
+// The draws of one node, with the emission left to the caller: emit(j, e) receives the index of the draw within the
+// node and the chosen edge position; prev(t) must return the edge position emitted as draw t of this node in an
+// earlier round (only called for fan-outs beyond the group width).
+template <typename EmitF, typename PrevF>
+__device__ __forceinline__ void sample_draws(const PassArgs& a, const NodeRec& r, i64 pos0, int g, int gl, int gbase, unsigned gmask,
+                                             EmitF emit, PrevF prev) {
   const u32* __restrict__ raw = a.raw;
   const i64 out0 = a.out0;
   const i64 deg = r.deg, rs = r.rs, k = a.fanout;
-  const i64 sbatch = a.disjoint ? a.src_batch[src_pos] : 0;
   i64 n_out, n16, n32, n64;
   const int mode = classify(deg, k, a.replace, &n_out, &n16, &n32, &n64);
-  auto emit = [&](i64 j, i64 e) {
-    const i64 p = off + j;
-    if (PHASED && a.phase == 1) { a.eid[pbase + p] = e; return; }
-    const i64 d = (i64)col[e];
-    a.row[pbase + p] = src_pos;
-    a.eid[pbase + p] = e;
-    a.colv[pbase + p] = d;  // global id for now; the (deferred) lookup overwrites it with the local id
-    if (PHASED && a.phase == 3) return;   // distributed one-hop sampling: no mapping at all (neighbor_kernel.cpp:296-303)
-    const u32 s = table_insert(a.keys, a.mask, make_key(d, sbatch, a.disjoint));
-    red_min_u64(&a.vals[s], POS_BASE + (u64)p);
-    a.eslot[p] = s;
-  };
-  if (PHASED && a.phase == 2) {
-    for (i64 j = gl; j < n_out; j += g) emit(j, a.eid[pbase + off + j]);
-  } else if (mode == MODE_FULL) {
+  if (mode == MODE_FULL) {
     for (i64 j = gl; j < deg; j += g) emit(j, rs + j);
   } else if (mode == MODE_REPLACE) {
     const int wu = rng_width_units((u64)deg);
@@ -560,7 +554,7 @@ __device__ __forceinline__ void sample_node(const PassArgs& a, const NodeRec& r,
         c = rnd;
         // already chosen in an earlier round of this node? (only when fanout > 32)
         for (u32 t = 0; t < c0; ++t)
-          if ((u32)(__ldcg(&a.eid[pbase + off + t]) - rs) == rnd) { c = lo + j; break; }
+          if ((u32)(prev(t) - rs) == rnd) { c = lo + j; break; }
       }
       const int lim = (int)((k32 - c0) < (u32)g ? (k32 - c0) : (u32)g);
       for (int jj = 0; jj < lim; ++jj) {
@@ -570,6 +564,33 @@ __device__ __forceinline__ void sample_node(const PassArgs& a, const NodeRec& r,
       if (act) emit(j, rs + c);
       if (c0 + g < k32) __syncwarp(gmask);
     }
+  }
+}
+
+template <typename idx_t, bool PHASED>
+__device__ __forceinline__ void sample_node(const PassArgs& a, const NodeRec& r, i64 off, i64 pos0, i64 src_pos, i64 pbase,
+                                            int g, int gl, int gbase, unsigned gmask) {
+  const idx_t* __restrict__ col = (const idx_t*)a.col;
+  const i64 sbatch = a.disjoint ? a.src_batch[src_pos] : 0;
+  auto emit = [&](i64 j, i64 e) {
+    const i64 p = off + j;
+    if (PHASED && a.phase == 1) { a.eid[pbase + p] = e; return; }
+    const i64 d = (i64)col[e];
+    a.row[pbase + p] = src_pos;
+    a.eid[pbase + p] = e;
+    a.colv[pbase + p] = d;  // global id for now; the (deferred) lookup overwrites it with the local id
+    if (PHASED && a.phase == 3) return;   // distributed one-hop sampling: no mapping at all (neighbor_kernel.cpp:296-303)
+    const u32 s = table_insert(a.keys, a.mask, make_key(d, sbatch, a.disjoint));
+    red_min_u64(&a.vals[s], POS_BASE + (u64)p);
+    a.eslot[p] = s;
+  };
+  auto prev = [&](u32 t) { return __ldcg(&a.eid[pbase + off + t]); };
+  if (PHASED && a.phase == 2) {
+    i64 n_out, n16, n32, n64;
+    classify((i64)r.deg, a.fanout, a.replace, &n_out, &n16, &n32, &n64);
+    for (i64 j = gl; j < n_out; j += g) emit(j, a.eid[pbase + off + j]);
+  } else {
+    sample_draws(a, r, pos0, g, gl, gbase, gmask, emit, prev);
   }
 }
 
@@ -648,6 +669,8 @@ __global__ void __launch_bounds__(NT) k_seed(const PassArgs a, const idx_t* __re
   }
 }
 
+#include "sampler_v2.cuh"
+
 // first occurrences of the running pass + tile-local ranks; last block scans the tile counts and
 // updates the dst type's counters.
 // one 1024-edge tile: first-occurrence flags + tile-local ranks, count of firsts -> mtile[tile]
@@ -688,58 +711,11 @@ __global__ void __launch_bounds__(NT) k_mark(const PassArgs a) {
   pdl_enter(TL_MARK);
   const i64 E = a.st[ST_PASS_E];
   const i64 ntiles = ceil_div(E, ETILE);
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   for (i64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) mark_tile(a, E, tile, s_w);
   tl_mark(TL_MARK | TL_END);
   if (last_block(&a.st[ST_TICKET_B])) {
     tl_mark_any(TL_MARK | TL_LAST);
-    // ordered exclusive scan of tile counts by one block
-    __shared__ i64 s_s[NT / 32];
-    __shared__ i64 carry;
-    if (threadIdx.x == 0) carry = 0;
-    __syncthreads();
-    for (i64 base = 0; base < ntiles; base += NT) {
-      const i64 t = base + threadIdx.x;
-      const i64 v = t < ntiles ? __ldcg(&a.mtile[t]) : 0;
-      i64 inc = v;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const i64 o = __shfl_up_sync(0xffffffffu, inc, d);
-        if (lane >= d) inc += o;
-      }
-      if (lane == 31) s_s[wid] = inc;
-      __syncthreads();
-      i64 pre = 0, tot = 0;
-      for (int w = 0; w < NT / 32; ++w) { if (w < wid) pre += s_s[w]; tot += s_s[w]; }
-      const i64 c0 = carry;
-      if (t < ntiles) a.mtile[t] = c0 + pre + inc - v;
-      __syncthreads();
-      if (threadIdx.x == 0) carry = c0 + tot;
-      __syncthreads();
-    }
-    if (threadIdx.x == 0) {
-      const i64 nnew = carry;
-      a.st[ST_PASS_NEW] = nnew;
-      if (a.seed_mode) {
-        a.st[ST_LIST_BASE] = 0;
-        a.st[ST_IDS_BASE] = 0;
-        a.st[a.o_dst_list] = E;      // every seed is listed, duplicates included (neighbor_kernel.cpp:410)
-        a.st[a.o_dst_ids] = nnew;    // ... but ids only count distinct ones (mapper.h:29-46)
-      } else {
-        a.st[ST_LIST_BASE] = a.st[a.o_dst_list];
-        a.st[ST_IDS_BASE] = a.st[a.o_dst_ids];
-        a.st[a.o_dst_list] += nnew;
-        a.st[a.o_dst_ids] += nnew;
-      }
-    }
-    __syncthreads();
-    // last pass of the hop: advance every type's frontier slice (neighbor_kernel.cpp:807-812)
-    for (int t = threadIdx.x; t < a.he_T; t += NT) {
-      const i64 n = a.st[a.he_list + t], e = a.st[a.he_end + t];
-      a.st[a.he_nph + t * (a.he_L + 1) + a.he_hop + 1] = n - e;
-      a.st[a.he_begin + t] = e;
-      a.st[a.he_end + t] = n;
-    }
+    mark_finish(a, E, ntiles);   // ordered exclusive scan of the tile counts by one block + the pass's counters
     tl_mark_any(TL_MARK | TL_LAST | TL_END);
   }
 }
@@ -1376,6 +1352,8 @@ struct pygb200_sampler {
   int sm_count = 148;
   struct TypeBuf {
     DevBuf nodes, batch, slot, keys, vals;
+    DevBuf pk;          // v2: packed table (node id << 32 | value), all-EMPTY between runs
+    int pk_bits = 0;    // log2 of its capacity (0 = not allocated)
     u64 tcap = 0;       // table capacity (slots, power of two); table is all-EMPTY between runs
     i64 n_nodes = 0;    // result of the last run
   };
@@ -1389,6 +1367,18 @@ struct pygb200_sampler {
   bool last_nodedup = false;  // the last run was a PYGB200_S_NO_DEDUP run (pygb200_sampler_export_cumsum is valid)
   i64 nd_seeds = 0;
   DevBuf eslot, erank, rec, tile_out, tile_func, tile_off, tile_pos, mtile, raw, st, gen;
+  DevBuf fref;              // v2, single GPU: ref of every edge of the running pass
+  // v2, frontier sharding over peer memory: this rank's exchange region and the peer mappings of the others'
+  struct XRegion {
+    unsigned char* base = nullptr;
+    size_t bytes = 0;
+    i64 cap = 0;            // edges per pass the region is laid out for
+    int world = 0, rank = 0;
+    unsigned char* peer[16] = {nullptr};
+    u64 epoch = 0;          // barrier count (flag words only grow)
+    u64 passes = 0;         // sharded passes so far: parity picks the (dst, edge id) buffer
+    i64 off_bar = 0, off_dst[2] = {0, 0}, off_eid[2] = {0, 0}, off_pref = 0, off_fref = 0;
+  } x;
   i64* st_host = nullptr;   // pinned + mapped mirror of the state buffer (k_final writes it directly)
   i64* st_host_dev = nullptr;   // device-side address of st_host
   i64 run_serial = 0;       // completion flag value of the current run
@@ -1496,7 +1486,10 @@ extern "C" int pygb200_sampler_create(pygb200_sampler** out) {
 
 extern "C" void pygb200_sampler_destroy(pygb200_sampler* s) {
   if (!s) return;
-  for (auto& t : s->types) { t.nodes.release(); t.batch.release(); t.slot.release(); t.keys.release(); t.vals.release(); }
+  for (auto& t : s->types) { t.nodes.release(); t.batch.release(); t.slot.release(); t.keys.release(); t.vals.release(); t.pk.release(); }
+  s->fref.release();
+  for (int q = 0; q < s->x.world; ++q) if (q != s->x.rank && s->x.peer[q]) cudaIpcCloseMemHandle(s->x.peer[q]);
+  if (s->x.base) cudaFree(s->x.base);
   for (auto& r : s->rels) { r.row.release(); r.colv.release(); r.eid.release(); }
   if (s->mt_stream) { cudaStreamSynchronize(s->mt_stream); cudaStreamDestroy(s->mt_stream); }
   for (int i = 0; i < 2; ++i) if (s->mt_ev[i]) cudaEventDestroy(s->mt_ev[i]);
@@ -1559,6 +1552,62 @@ int ensure_table(pygb200_sampler* s, int t, i64 need_nodes, i64 listed, cudaStre
     tb.keys = nk; tb.vals = nv;
   }
   tb.tcap = cap;
+  return PYGB200_OK;
+}
+
+// v2: packed table of one type with room for `need_nodes` distinct keys at load factor <= 0.5
+int ensure_table_v2(pygb200_sampler* s, int t, i64 need_nodes, cudaStream_t st) {
+  auto& tb = s->types[t];
+  int bits = 10;
+  while ((1ull << bits) < 2 * (u64)(need_nodes > 0 ? need_nodes : 1)) ++bits;
+  if (bits <= tb.pk_bits) return PYGB200_OK;
+  PYGB_CHECK(bits <= 32, PYGB200_ERR_UNSUPPORTED, "sampler hash table would exceed 2^32 slots");
+  if (int e = tb.pk.ensure((size_t)8 << bits, 0, st)) return e;
+  PYGB_CUDA(cudaMemsetAsync(tb.pk.p, 0xff, (size_t)8 << bits, st));
+  tb.pk_bits = bits;
+  return PYGB200_OK;
+}
+
+// v2 sharding: exchange region for passes of up to `cap` edges, mapped into every rank.  Collective: all ranks get
+// here together (identical call sequences), `exchange` swaps the IPC handles and orders the remapping.
+int ensure_xregion(pygb200_sampler* s, i64 cap, const pygb200_shard* shard, cudaStream_t st) {
+  auto& x = s->x;
+  const int W = shard->world;
+  if (x.base && x.cap >= cap && x.world == W && x.rank == shard->rank) return PYGB200_OK;
+  PYGB_CUDA(cudaStreamSynchronize(st));
+  for (int q = 0; q < x.world; ++q)
+    if (q != x.rank && x.peer[q]) { cudaIpcCloseMemHandle(x.peer[q]); x.peer[q] = nullptr; }
+  i64 ncap = x.world == W ? std::max<i64>(x.cap, 1 << 16) : (1 << 16);
+  while (ncap < cap) ncap *= 2;
+  auto al = [](i64 b) { return (b + 255) / 256 * 256; };
+  i64 o = 256;
+  const i64 off_bar = 0;
+  i64 off_dst[2], off_eid[2];
+  for (int i = 0; i < 2; ++i) { off_dst[i] = o; o += al(ncap * 4); }
+  for (int i = 0; i < 2; ++i) { off_eid[i] = o; o += al(ncap * 8); }
+  const i64 off_pref = o; o += al(ncap * 4);
+  const i64 off_fref = o; o += al(ncap * 4);
+  unsigned char* nb = nullptr;
+  PYGB_CUDA(cudaMalloc((void**)&nb, (size_t)o));
+  PYGB_CUDA(cudaMemset(nb, 0, 256));
+  PYGB_CUDA(cudaDeviceSynchronize());
+  cudaIpcMemHandle_t mine;
+  PYGB_CUDA(cudaIpcGetMemHandle(&mine, nb));
+  std::vector<cudaIpcMemHandle_t> all((size_t)W);
+  const int rc = shard->exchange(shard->user, &mine, all.data(), (int64_t)sizeof(mine));
+  if (rc != 0) { cudaFree(nb); set_error("frontier-sharded sampling: handle exchange callback failed"); return PYGB200_ERR_INTERNAL; }
+  // every rank closed its mappings of the old regions before it entered the exchange
+  if (x.base) cudaFree(x.base);
+  x.base = nb; x.bytes = (size_t)o; x.cap = ncap; x.world = W; x.rank = shard->rank;
+  x.off_bar = off_bar; x.off_dst[0] = off_dst[0]; x.off_dst[1] = off_dst[1]; x.off_eid[0] = off_eid[0]; x.off_eid[1] = off_eid[1];
+  x.off_pref = off_pref; x.off_fref = off_fref;
+  x.epoch = 0; x.passes = 0;
+  for (int q = 0; q < W; ++q) {
+    if (q == x.rank) { x.peer[q] = nb; continue; }
+    void* pp = nullptr;
+    PYGB_CUDA(cudaIpcOpenMemHandle(&pp, all[(size_t)q], cudaIpcMemLazyEnablePeerAccess));
+    x.peer[q] = (unsigned char*)pp;
+  }
   return PYGB200_OK;
 }
 
@@ -1792,9 +1841,31 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
   s->last_nodedup = false;
   if (sharded) {
     PYGB_CHECK(!synced, PYGB200_ERR_UNSUPPORTED, "frontier-sharded sampling needs bounded fan-outs (no -1, < 8 GiB worst case)");
-    PYGB_CHECK(shard->world <= MAX_SHARDS && shard->rank >= 0 && shard->rank < shard->world && shard->allgather,
+    PYGB_CHECK(shard->world <= MAX_SHARDS && shard->rank >= 0 && shard->rank < shard->world && (shard->allgather || shard->exchange),
                PYGB200_ERR_ARG, "bad shard descriptor");
   }
+  // ---- which schedule?  latency path (k_*_s: write-once counters, no serial sections) for small bounded runs,
+  // v2 (sampler_v2.cuh: packed table, refs, peer-memory sharding) for the other bounded non-disjoint runs whose node
+  // ids provably fit 32 bits, the wide-table throughput path for everything else.
+  static const bool no_lat = getenv("PYGB200_NO_LATENCY_PATH") != nullptr;
+  static const bool no_v2 = getenv("PYGB200_NO_V2") != nullptr;
+  bool lat = !synced && !sharded && !nodedup && L > 0 && !no_lat;
+  for (int t = 0; t < T && lat; ++t) lat = n_seeds[t] <= SEED_FUSED_MAX;
+  for (int h = 0; h < L && lat; ++h)
+    for (int r = 0; r < R && lat; ++r) {
+      if (num_neighbors[(size_t)r * L + h] == 0) continue;
+      lat = fb[(size_t)rels[r].src_type * (L + 1) + h] <= (i64)LAT_TILES * NT && eb[(size_t)r * L + h] <= (i64)LAT_TILES * ETILE;
+    }
+  const bool p2p = sharded && shard->exchange != nullptr;
+  bool v2 = !lat && !synced && !nodedup && !disjoint && !any_time && L > 0 && (!no_v2 || p2p) && (!sharded || p2p);
+  if (v2) {   // every node type's id range must be known and fit the packed key (a type that is never a source has no bound)
+    std::vector<i64> type_nodes((size_t)T, -1);
+    for (int r = 0; r < R; ++r) type_nodes[rels[r].src_type] = std::max(type_nodes[rels[r].src_type], (i64)rels[r].num_src_nodes);
+    for (int t = 0; t < T && v2; ++t) v2 = idx32 || (type_nodes[t] >= 0 && type_nodes[t] < 0xffffffffll);
+  }
+  if (p2p) PYGB_CHECK(v2 && T == 1 && R == 1 && shard->world <= V2_MAX_W, PYGB200_ERR_UNSUPPORTED,
+                      "peer-memory frontier sharding: homogeneous, non-disjoint, bounded fan-outs, node ids < 2^32-1, world <= 16");
+  const int XW = p2p ? shard->world : 1, XR = p2p ? shard->rank : 0;
 
   // ---- results straight into the caller's arrays?  (bounded int64 non-disjoint runs only; the binding is one-shot)
   bool direct = s->bound.armed && !synced && !sharded && !nodedup && !idx32 && !disjoint && (int)s->bound.node.size() == T &&
@@ -1837,11 +1908,23 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
       PYGB_CUDA(cudaMemsetAsync(tb.keys.p, 0xff, tb.tcap * 8, st));
       PYGB_CUDA(cudaMemsetAsync(tb.vals.p, 0xff, tb.tcap * 8, st));
     }
+    for (auto& tb : s->types) if (tb.pk_bits) PYGB_CUDA(cudaMemsetAsync(tb.pk.p, 0xff, (size_t)8 << tb.pk_bits, st));
     s->mt_valid = false;
     s->st_dev_words = 0;
   }
   s->dirty = true;
-  if (!synced) {
+  if (v2) {
+    for (int t = 0; t < T; ++t) {
+      if (int e = ensure_type(s, t, node_cap[t], 0, false, st)) return e;
+      // a rank's table holds the keys it owns: 1/W of them (+25 % for imbalance)
+      if (int e = ensure_table_v2(s, t, XW == 1 ? node_cap[t] : node_cap[t] / XW + node_cap[t] / (4 * XW) + 1024, st)) return e;
+    }
+    for (int r = 0; r < R; ++r) if (int e = ensure_rel(s, r, rel_cap[r], 0, st)) return e;
+    if (int e = ensure_frontier_scratch(s, max_F, st)) return e;
+    if (int e = ensure_edge_scratch(s, max_E, st)) return e;
+    if (p2p) { if (int e = ensure_xregion(s, max_E, shard, st)) return e; }
+    else if (int e = s->fref.ensure((size_t)max_E * 4, 0, st)) return e;
+  } else if (!synced) {
     for (int t = 0; t < T; ++t) {
       if (int e = ensure_type(s, t, node_cap[t], 0, disjoint, st)) return e;
       if (int e = ensure_table(s, t, node_cap[t], 0, st)) return e;
@@ -1974,6 +2057,19 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
     a.o_dst_list = lay.o_list + dst_t; a.o_dst_ids = lay.o_ids + dst_t;
     a.raw = s->raw.as<u32>(); a.gen = s->gen.as<i64>(); a.out0 = out0; a.raw_cap = raw_cap;
     a.replace = replace; a.disjoint = disjoint;
+    if (v2) {
+      a.pk = td.pk.as<u64>(); a.pk_bits = td.pk_bits;
+      a.xw = XW; a.xr = XR; a.o_shard = lay.o_shard;
+      a.fref = s->fref.as<u32>();
+      if (p2p) {
+        const auto& x = s->x;
+        for (int q = 0; q < XW; ++q) a.xpeer[q] = x.peer[q];
+        a.x_off_bar = x.off_bar; a.x_off_pref = x.off_pref; a.x_off_fref = x.off_fref;
+        a.x_off_dst = x.off_dst[x.passes & 1]; a.x_off_eid = x.off_eid[x.passes & 1];
+        a.fref = reinterpret_cast<u32*>(x.base + x.off_fref);
+        a.x_eid64 = (rel >= 0 && rels[rel].num_edges > 0xffffffffll) ? 1 : 0;
+      }
+    }
     if (any_time && rel >= 0) {  // edge time of the relation wins over node time of its dst type (:742-787)
       if (temporal->edge_time && temporal->edge_time[rel]) { a.time_mode = 2; a.time = reinterpret_cast<const i64*>(temporal->edge_time[rel]); }
       else if (temporal->node_time && temporal->node_time[dst_t]) { a.time_mode = 1; a.time = reinterpret_cast<const i64*>(temporal->node_time[dst_t]); }
@@ -1988,18 +2084,43 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
     return PYGB200_OK;
   };
 
+  // v2: from the inserts of a pass (or of the seeds) to ids.  Single GPU: mark reads the refs from the table.
+  // Sharded: refs of owned positions -> barrier -> slice-wise reduction over the peers, result stored to all ->
+  // barrier -> the same mark on the full ref array.  Then ids (replicated, streaming).
+  static const u64 xbar_timeout_ns = [] { const char* e = getenv("PYGB200_XBARRIER_TIMEOUT_MS"); return (u64)(e ? atoll(e) : 20000) * 1000000ull; }();
+  auto xbarrier = [&](const PassArgs& a) -> int {
+    launch_pdl(k_xbarrier, 1, 32, st, a, (u64)(++s->x.epoch), xbar_timeout_ns);
+    PYGB_LAUNCH_CHECK();
+    return PYGB200_OK;
+  };
+  auto v2_ids = [&](const PassArgs& a, i64 Eb) -> int {
+    void* tk;
+    if (p2p) {
+      launch_pdl(k_v2_pref, grid_for(Eb, NT, s->sm_count), NT, st, a);
+      PYGB_LAUNCH_CHECK();
+      if (int e = xbarrier(a)) return e;
+      launch_pdl(k_v2_reduce, grid_for(ceil_div(Eb, XW), NT, s->sm_count), NT, st, a);
+      PYGB_LAUNCH_CHECK();
+      if (int e = xbarrier(a)) return e;
+      tk = prof_begin(st);
+      launch_pdl(k_v2_mark<false>, grid_for(Eb, ETILE, s->sm_count), NT, st, a);
+    } else {
+      tk = prof_begin(st);
+      launch_pdl(k_v2_mark<true>, grid_for(Eb, ETILE, s->sm_count), NT, st, a);
+    }
+    prof_end(tk, "mark", st, Eb);
+    PYGB_LAUNCH_CHECK();
+    tk = prof_begin(st);
+    if (p2p) launch_pdl(k_v2_assign<true>, grid_for(Eb, NT, s->sm_count), NT, st, a);
+    else launch_pdl(k_v2_assign<false>, grid_for(Eb, NT, s->sm_count), NT, st, a);
+    prof_end(tk, "assign", st, Eb);
+    PYGB_LAUNCH_CHECK();
+    return PYGB200_OK;
+  };
+
   ht_lap(1);
   // ---- seeds (neighbor_kernel.cpp:409-416, :669-704)
   if (any_time) if (int e = s->seed_times.ensure((size_t)std::max<i64>(total_seeds, 1) * 8, 0, st)) return e;
-  // ---- latency path?  (k_*_s kernels: write-once counters, no serial sections; see above k_count_s)
-  static const bool no_lat = getenv("PYGB200_NO_LATENCY_PATH") != nullptr;
-  bool lat = !synced && !sharded && !nodedup && L > 0 && !no_lat;
-  for (int t = 0; t < T && lat; ++t) lat = n_seeds[t] <= SEED_FUSED_MAX;
-  for (int h = 0; h < L && lat; ++h)
-    for (int r = 0; r < R && lat; ++r) {
-      if (num_neighbors[(size_t)r * L + h] == 0) continue;
-      lat = fb[(size_t)rels[r].src_type * (L + 1) + h] <= (i64)LAT_TILES * NT && eb[(size_t)r * L + h] <= (i64)LAT_TILES * ETILE;
-    }
   // The first pass that will run (hop 0) is counted inside the seed launch of its source type (extra blocks)
   int fuse_r = -1, fuse_t = -1;
   if (lat) {
@@ -2030,6 +2151,17 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
       if (idx32) k_seed_times<int32_t><<<g, NT, 0, st>>>(s->seed_times.as<i64>(), (const int32_t*)seeds[t], n_seeds[t], batch0, stt, ntt);
       else k_seed_times<int64_t><<<g, NT, 0, st>>>(s->seed_times.as<i64>(), (const int64_t*)seeds[t], n_seeds[t], batch0, stt, ntt);
       PYGB_LAUNCH_CHECK();
+    }
+    if (v2) {
+      if (n_seeds[t] == 0) continue;   // the zeroed state already says "empty list, empty slice"
+      const int g = grid_for(n_seeds[t], NT, s->sm_count);
+      if (idx32) launch_pdl(k_v2_seed<int32_t>, g, NT, st, a, (const int32_t*)seeds[t], (i64)n_seeds[t]);
+      else launch_pdl(k_v2_seed<int64_t>, g, NT, st, a, (const int64_t*)seeds[t], (i64)n_seeds[t]);
+      PYGB_LAUNCH_CHECK();
+      if (int e = v2_ids(a, n_seeds[t])) return e;
+      k_seed_end<<<1, 1, 0, st>>>(dst, t, L, lay.o_list, lay.o_begin, lay.o_end, lay.o_nph);
+      PYGB_LAUNCH_CHECK();
+      continue;
     }
     if (n_seeds[t] > 0 && n_seeds[t] <= SEED_FUSED_MAX) {
       if (idx32) launch_pdl(k_seed_fused<int32_t>, 1 + count_blocks, SEED_NT, st, a, (const int32_t*)seeds[t], (int)n_seeds[t], batch0, (int)L,
@@ -2161,6 +2293,35 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
         a.lk_colv = lk_colv; a.lk_vals = lk_vals;
         with_hop_end(a);
         if (int e = idx32 ? launch_count<int32_t>(s, a, Fb, lk_E, st) : launch_count<int64_t>(s, a, Fb, lk_E, st)) return e;
+        if (v2) {
+          // does any later pass insert into this dst type's table?  (else the ids need not be written back)
+          a.v2_writeback = 0;
+          for (int h2 = h; h2 < L && !a.v2_writeback; ++h2)
+            for (int r2 = (h2 == h ? r + 1 : 0); r2 < R && !a.v2_writeback; ++r2)
+              a.v2_writeback = rels[r2].dst_type == dst_t && num_neighbors[(size_t)r2 * L + h2] != 0 &&
+                               fb[(size_t)rels[r2].src_type * (L + 1) + h2] != 0 && eb[(size_t)r2 * L + h2] != 0;
+          a.group = sample_group_lanes(k);
+          const int gs = grid_for(Fb, sample_nodes_per_block(a.group), s->sm_count);
+          void* tk = prof_begin(st);
+          if (p2p) {
+            k_shard_bounds<<<1, 128, 0, st>>>(a, XW, lay.o_shard);   // position slices of the ref reduction
+            PYGB_LAUNCH_CHECK();
+            if (idx32) launch_pdl(k_v2_sample<int32_t, true>, gs, NT, st, a); else launch_pdl(k_v2_sample<int64_t, true>, gs, NT, st, a);
+          } else {
+            if (idx32) launch_pdl(k_v2_sample<int32_t, false>, gs, NT, st, a); else launch_pdl(k_v2_sample<int64_t, false>, gs, NT, st, a);
+          }
+          prof_end(tk, "sample", st, Eb);
+          PYGB_LAUNCH_CHECK();
+          if (p2p) {
+            if (int e = xbarrier(a)) return e;   // everybody's (dst, edge id) have arrived
+            launch_pdl(k_v2_insert, grid_for(Eb, NT, s->sm_count), NT, st, a);
+            PYGB_LAUNCH_CHECK();
+          }
+          if (int e = v2_ids(a, Eb)) return e;
+          if (p2p) s->x.passes += 1;
+          if (r == last_r) hop_closed = true;
+          continue;
+        }
         if (nodedup) {   // draw + gather only: global ids stay in `colv`, nothing is mapped, no lookup follows
           PassArgs d = a;
           d.phase = 3;
@@ -2254,11 +2415,16 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
   }
   // table cleanup is stream-ordered after k_final; the host does not wait for it.  With
   // PYGB200_S_DEFER_CLEANUP (homogeneous fast path) it rides along with pygb200_sampler_export_all instead.
-  s->cleanup_pending = (flags & PYGB200_S_DEFER_CLEANUP) && T == 1 && !direct;
+  s->cleanup_pending = (flags & PYGB200_S_DEFER_CLEANUP) && T == 1 && !direct && !v2;
   s->last_direct = direct;
   s->last_nodedup = nodedup;
   s->nd_seeds = nodedup ? n_seeds[0] : 0;
-  for (int t = 0; t < T && !s->cleanup_pending; ++t) {
+  for (int t = 0; t < T && v2; ++t) {
+    auto& tb = s->types[t];
+    launch_pdl(k_v2_cleanup, grid_for(node_cap[t], NT, s->sm_count), NT, st, tb.pk.as<u64>(), (const u32*)tb.slot.as<u32>(), (const i64*)(dst + lay.o_list + t));
+    PYGB_LAUNCH_CHECK();
+  }
+  for (int t = 0; t < T && !s->cleanup_pending && !v2; ++t) {
     auto& tb = s->types[t];
     const i64 cap_nodes = (i64)(tb.slot.cap / 4);
     launch_pdl(k_cleanup, grid_for(synced ? cap_nodes : node_cap[t], NT, s->sm_count), NT, st, tb.keys.as<u64>(), tb.vals.as<u64>(),
@@ -2300,6 +2466,7 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
   ht_lap(4);
   if (pub_w_list >= 0) s->st_host[pub_w_list] = (i64)((u64)s->st_host[lay.words] & 0xffffffffffull);
   const i64* hs = s->st_host;
+  PYGB_CHECK(hs[ST_ERROR] != 2, PYGB200_ERR_INTERNAL, "sampler: a peer rank did not reach a cross-GPU barrier in time (frontier-sharded run; PYGB200_XBARRIER_TIMEOUT_MS)");
   PYGB_CHECK(hs[ST_ERROR] == 0, PYGB200_ERR_INTERNAL, "sampler: mt19937 stream buffer too small (internal bound violated)");
   s->dirty = false;
   if (lat) {   // counters from the write-once words of the schedule

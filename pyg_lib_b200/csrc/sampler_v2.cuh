@@ -1,0 +1,347 @@
+// pyg_lib_b200/csrc/sampler_v2.cuh — throughput schedule of the sampler ("v2"), included by sampler.cu inside its
+// anonymous namespace (it uses PassArgs, NodeRec, sample_draws, pdl_enter, last_block, ... from there).
+//
+// Same results as the other schedules (bit-exact vs neighbor_kernel.cpp:337-514 / 529-841), different data path, built
+// from what tools/p2p_microbench.cu measured on B200: random 8-byte atomics on a table larger than L2 run at ~30 G/s
+// when an insert is ONE atomic and at ~12 G/s when it is CAS(keys) + min(vals) on two arrays; random 8-byte loads
+// at ~65 G/s; a peer GPU takes ~9 G CAS/s and ~700 GB/s of coalesced stores over NVLink.  So:
+//   * packed table: one u64 slot = (node id : 32 | value : 32); value = V2_POS | flat position of the running pass
+//     until ids are assigned, else the node's local id.  Insert = one CAS (+ one min only when the key was already
+//     there with a larger position).  Needs node ids < 2^32 - 1, pass positions and local ids < 2^31 (checked by
+//     the host; disjoint / temporal / unbounded runs keep the wide-table schedules).
+//   * "ref" instead of a lookup pass: after all inserts of a pass, mark reads each edge's slot once: ref = value.
+//     first occurrence <=> ref == V2_POS | p.  Ranks of the firsts come from per-tile counts + in-tile ranks
+//     (erank[], 4 B per edge, L2-resident), so an edge's local id is ids_base + tile_prefix[q >> 10] + erank[q] with
+//     q = ref's position — no second and third random pass over the table (assign's id write-back is skipped for
+//     passes whose dst table is not inserted into again; the old lookup pass is gone).
+//   * frontier sharding over peer memory (W ranks, one process per GPU, CSR replicated): every rank counts
+//     the whole frontier (offsets / RNG positions are global), draws only its slice of frontier nodes and STORES the
+//     (dst, edge id) of its edges straight into every rank's exchange region over NVLink — the all-gather of sampled
+//     edges is fused into the sampling kernel.  Dedup is partitioned by key: a rank inserts only the dst ids it owns
+//     (hash of the id), so the random atomics are divided by W; it publishes the refs of owned positions, each rank
+//     sums its position slice over the peers (coalesced peer loads) and stores the result to everybody.  From the
+//     full ref array all ranks derive identical ids with streaming work only.  Cross-GPU ordering = flag words in
+//     the exchange regions (k_xbarrier), no host involvement, no NCCL call on the data path.
+#pragma once
+
+constexpr u32 V2_POS = 0x80000000u;
+constexpr int V2_MAX_W = 16;
+
+__device__ __forceinline__ int v2_owner(u32 key, int W) {
+  u32 h = key * 0x85ebca6bu; h ^= h >> 13; h *= 0xc2b2ae35u; h ^= h >> 16;   // independent of the slot hash
+  return (int)(((u64)h * (u32)W) >> 32);
+}
+
+// insert (key, position p of the running pass); returns the slot.  The slot's value ends up as the minimum position
+// of the key in this pass, or stays the local id the key got in an earlier pass (ids < V2_POS <= positions).
+__device__ __forceinline__ u32 v2_insert(u64* __restrict__ pk, int bits, u32 key, u32 p) {
+  const u64 mask = (1ull << bits) - 1;
+  u64 s = ((u64)key * 0x9E3779B97F4A7C15ull) >> (64 - bits);
+  const u64 mine = ((u64)key << 32) | (u64)(V2_POS | p);
+  while (true) {
+    const u64 prev = atomicCAS(&pk[s], EMPTY, mine);
+    if (prev == EMPTY) return (u32)s;
+    if ((u32)(prev >> 32) == key) {
+      if ((u32)prev > (V2_POS | p)) red_min_u64(&pk[s], mine);
+      return (u32)s;
+    }
+    s = (s + 1) & mask;
+  }
+}
+
+template <typename T>
+__device__ __forceinline__ T* x_ptr(const PassArgs& a, int q, i64 off) { return reinterpret_cast<T*>(a.xpeer[q] + off); }
+
+// ---- cross-GPU barrier on flag words in the exchange regions.  Stream order puts it behind the kernel whose peer
+// stores it publishes (a completed kernel's stores are performed system-wide); thread q tells rank q "rank xr has
+// reached epoch" and waits for rank q's word in its own region.  A peer that never arrives is reported, not waited
+// for forever.
+__global__ void k_xbarrier(const PassArgs a, u64 epoch, u64 timeout_ns) {
+  pdl_enter();
+  const int q = threadIdx.x;
+  if (q >= a.xw) return;
+  __threadfence_system();
+  u64* mine = x_ptr<u64>(a, a.xr, a.x_off_bar);
+  if (q != a.xr) {
+    u64* theirs = x_ptr<u64>(a, q, a.x_off_bar);
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(theirs + a.xr), "l"(epoch) : "memory");
+    u64 t0, t1, v;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    while (true) {
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine + q) : "memory");
+      if (v >= epoch) break;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      if (t1 - t0 > timeout_ns) { a.st[ST_ERROR] = 2; break; }
+      __nanosleep(200);
+    }
+  }
+  __threadfence_system();
+}
+
+// ---- seeds: list them; the owner of a seed inserts it at position i (first-occurrence order == seed order)
+template <typename idx_t>
+__global__ void __launch_bounds__(NT) k_v2_seed(const PassArgs a, const idx_t* __restrict__ seeds, i64 n) {
+  pdl_enter(TL_SEED);
+  for (i64 i = (i64)blockIdx.x * NT + threadIdx.x; i < n; i += (i64)gridDim.x * NT) {
+    const i64 v = (i64)seeds[i];
+    a.dst_nodes[i] = v;
+    const u32 key = (u32)v;
+    const bool own = a.xw == 1 || v2_owner(key, a.xw) == a.xr;
+    a.eslot[i] = own ? v2_insert(a.pk, a.pk_bits, key, (u32)i) : NO_SLOT;
+  }
+  if (blockIdx.x == 0) {
+    if (threadIdx.x == 0) { a.st[ST_PASS_E] = n; a.st[ST_PASS_BASE] = 0; }
+    if (a.xw > 1 && threadIdx.x <= a.xw) a.st[a.o_shard + threadIdx.x] = (i64)((__int128)n * threadIdx.x / a.xw);   // position slices
+  }
+}
+
+// ---- one pass's sampling.  SH = false: draw, gather, rows / edge ids / global dst into the result arrays, insert.
+// SH = true: every node writes its rows (cheap, replicated); a node of this rank's slice draws, gathers and stores
+// (dst : u32, edge id : u32 | u64) at the edge's flat position into EVERY rank's exchange region.
+template <typename idx_t, bool SH>
+__global__ void __launch_bounds__(NT, SAMPLE_MIN_BLOCKS) k_v2_sample(const PassArgs a) {
+  pdl_enter(TL_SAMPLE);
+  const i64 F = a.st[ST_PASS_F];
+  const i64 begin = a.st[a.o_src_begin];
+  const i64 pbase = a.st[ST_PASS_BASE];
+  const int g = a.group, lane = threadIdx.x & 31, per_warp = 32 / g;
+  const int gi = lane / g, gl = lane - gi * g, gbase = gi * g;
+  const unsigned gmask = (g == 32) ? 0xffffffffu : (((1u << g) - 1u) << gbase);
+  const int npb = (NT / 32) * per_warp;
+  const idx_t* __restrict__ col = (const idx_t*)a.col;
+  const i64 own_lo = SH ? (i64)((__int128)F * a.xr / a.xw) : 0;
+  const i64 own_hi = SH ? (i64)((__int128)F * (a.xr + 1) / a.xw) : F;
+  if (gi >= per_warp) return;   // (lanes beyond the last whole group of the warp)
+  for (i64 i = (i64)blockIdx.x * npb + (threadIdx.x >> 5) * per_warp + gi; i < F; i += (i64)gridDim.x * npb) {
+    const NodeRec r = a.rec[i];
+    const i64 tile = i / NT;
+    const i64 off = a.tile_off[tile] + r.loc_off;    // pass-local flat position of the node's first edge
+    const i64 src_pos = begin + i;                   // local id of the source node (neighbor_kernel.cpp:453)
+    if (SH && (i < own_lo || i >= own_hi)) {         // somebody else's node: rows only
+      i64 n_out, n16, n32, n64;
+      classify((i64)r.deg, a.fanout, a.replace, &n_out, &n16, &n32, &n64);
+      for (i64 j = gl; j < n_out; j += g) a.row[pbase + off + j] = src_pos;
+      continue;
+    }
+    const i64 tpos = a.tile_pos[tile];
+    const int ph = (int)(tpos & 3);
+    const u32 pfv = ph == 0 ? r.pf[0] : (ph == 1 ? r.pf[1] : (ph == 2 ? r.pf[2] : r.pf[3]));
+    auto emit = [&](i64 j, i64 e) {
+      const i64 p = off + j;
+      const i64 d = (i64)col[e];
+      a.row[pbase + p] = src_pos;
+      if (!SH) {
+        a.eid[pbase + p] = e;
+        a.colv[pbase + p] = d;   // global id until k_v2_assign replaces it with the local id
+        a.eslot[p] = v2_insert(a.pk, a.pk_bits, (u32)d, (u32)p);
+      } else {
+        for (int q = 0; q < a.xw; ++q) {
+          x_ptr<u32>(a, q, a.x_off_dst)[p] = (u32)d;
+          if (a.x_eid64) x_ptr<u64>(a, q, a.x_off_eid)[p] = (u64)e; else x_ptr<u32>(a, q, a.x_off_eid)[p] = (u32)e;
+        }
+      }
+    };
+    auto prev = [&](u32 t) -> i64 {
+      if (!SH) return __ldcg(&a.eid[pbase + off + t]);
+      return a.x_eid64 ? (i64)__ldcg(x_ptr<u64>(a, a.xr, a.x_off_eid) + off + t) : (i64)__ldcg(x_ptr<u32>(a, a.xr, a.x_off_eid) + off + t);
+    };
+    sample_draws(a, r, tpos + pfv, g, gl, gbase, gmask, emit, prev);
+  }
+  tl_mark(TL_SAMPLE | TL_END);
+}
+
+// ---- sharded: the owner of a dst id inserts it (all positions of the pass are streamed, 1/W of them hit the table)
+__global__ void __launch_bounds__(NT) k_v2_insert(const PassArgs a) {
+  pdl_enter();
+  const i64 E = a.st[ST_PASS_E];
+  const u32* __restrict__ xdst = x_ptr<u32>(a, a.xr, a.x_off_dst);
+  for (i64 p = (i64)blockIdx.x * NT + threadIdx.x; p < E; p += (i64)gridDim.x * NT) {
+    const u32 key = xdst[p];
+    a.eslot[p] = v2_owner(key, a.xw) == a.xr ? v2_insert(a.pk, a.pk_bits, key, (u32)p) : NO_SLOT;
+  }
+}
+
+// ---- sharded: refs of the positions this rank owns (0 elsewhere: exactly one rank owns a position)
+__global__ void __launch_bounds__(NT) k_v2_pref(const PassArgs a) {
+  pdl_enter();
+  const i64 E = a.st[ST_PASS_E];
+  u32* __restrict__ pref = x_ptr<u32>(a, a.xr, a.x_off_pref);
+  for (i64 p = (i64)blockIdx.x * NT + threadIdx.x; p < E; p += (i64)gridDim.x * NT) {
+    const u32 s = a.eslot[p];
+    pref[p] = s == NO_SLOT ? 0u : (u32)a.pk[s];
+  }
+}
+
+// ---- sharded: this rank's position slice of the refs = sum over the ranks' partial refs (coalesced peer loads),
+// stored to every rank (coalesced peer stores)
+__global__ void __launch_bounds__(NT) k_v2_reduce(const PassArgs a) {
+  pdl_enter();
+  const i64 lo = a.st[a.o_shard + a.xr], hi = a.st[a.o_shard + a.xr + 1];
+  for (i64 p = lo + (i64)blockIdx.x * NT + threadIdx.x; p < hi; p += (i64)gridDim.x * NT) {
+    u32 v = 0;
+    for (int q = 0; q < a.xw; ++q) v += x_ptr<u32>(a, q, a.x_off_pref)[p];
+    for (int q = 0; q < a.xw; ++q) x_ptr<u32>(a, q, a.x_off_fref)[p] = v;
+  }
+}
+
+// counters of a pass once the per-tile counts of first occurrences are known: ordered exclusive scan of the counts by
+// the calling (last) block, dst list / id counters, end-of-hop bookkeeping (shared with k_mark)
+__device__ void mark_finish(const PassArgs& a, i64 E, i64 ntiles) {
+  __shared__ i64 s_s[NT / 32];
+  __shared__ i64 carry;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (i64 base = 0; base < ntiles; base += NT) {
+    const i64 t = base + threadIdx.x;
+    const i64 v = t < ntiles ? __ldcg(&a.mtile[t]) : 0;
+    i64 inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const i64 o = __shfl_up_sync(0xffffffffu, inc, d);
+      if (lane >= d) inc += o;
+    }
+    if (lane == 31) s_s[wid] = inc;
+    __syncthreads();
+    i64 pre = 0, tot = 0;
+    for (int w = 0; w < NT / 32; ++w) { if (w < wid) pre += s_s[w]; tot += s_s[w]; }
+    const i64 c0 = carry;
+    if (t < ntiles) a.mtile[t] = c0 + pre + inc - v;
+    __syncthreads();
+    if (threadIdx.x == 0) carry = c0 + tot;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const i64 nnew = carry;
+    a.st[ST_PASS_NEW] = nnew;
+    if (a.seed_mode) {
+      a.st[ST_LIST_BASE] = 0;
+      a.st[ST_IDS_BASE] = 0;
+      a.st[a.o_dst_list] = E;      // every seed is listed, duplicates included (neighbor_kernel.cpp:410)
+      a.st[a.o_dst_ids] = nnew;    // ... but ids only count distinct ones (mapper.h:29-46)
+    } else {
+      a.st[ST_LIST_BASE] = a.st[a.o_dst_list];
+      a.st[ST_IDS_BASE] = a.st[a.o_dst_ids];
+      a.st[a.o_dst_list] += nnew;
+      a.st[a.o_dst_ids] += nnew;
+    }
+  }
+  __syncthreads();
+  // last pass of the hop: advance every type's frontier slice (neighbor_kernel.cpp:807-812)
+  for (int t = threadIdx.x; t < a.he_T; t += NT) {
+    const i64 n = a.st[a.he_list + t], e = a.st[a.he_end + t];
+    a.st[a.he_nph + t * (a.he_L + 1) + a.he_hop + 1] = n - e;
+    a.st[a.he_begin + t] = e;
+    a.st[a.he_end + t] = n;
+  }
+}
+
+// ---- refs -> first-occurrence flags, in-tile ranks, per-tile counts; last block: scan + counters.
+// TABLE = true (single GPU): the ref of an edge is read from its slot here and kept in fref[].
+template <bool TABLE>
+__global__ void __launch_bounds__(NT) k_v2_mark(const PassArgs a) {
+  __shared__ u32 s_w[NT / 32];
+  pdl_enter(TL_MARK);
+  const i64 E = a.st[ST_PASS_E];
+  const i64 ntiles = ceil_div(E, ETILE);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (i64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const i64 p0 = tile * ETILE + threadIdx.x * 4;
+    u32 fl[4]; u32 cnt = 0;
+    if (p0 + 3 < E) {
+      uint4 rv;
+      if (TABLE) {
+        const uint4 sl = *reinterpret_cast<const uint4*>(a.eslot + p0);
+        rv.x = (u32)a.pk[sl.x]; rv.y = (u32)a.pk[sl.y]; rv.z = (u32)a.pk[sl.z]; rv.w = (u32)a.pk[sl.w];
+        *reinterpret_cast<uint4*>(a.fref + p0) = rv;
+      } else {
+        rv = *reinterpret_cast<const uint4*>(a.fref + p0);
+      }
+      fl[0] = rv.x == (V2_POS | (u32)p0); fl[1] = rv.y == (V2_POS | (u32)(p0 + 1));
+      fl[2] = rv.z == (V2_POS | (u32)(p0 + 2)); fl[3] = rv.w == (V2_POS | (u32)(p0 + 3));
+    } else {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const i64 p = p0 + q;
+        fl[q] = 0;
+        if (p < E) {
+          u32 rv;
+          if (TABLE) { rv = (u32)a.pk[a.eslot[p]]; a.fref[p] = rv; } else rv = a.fref[p];
+          fl[q] = rv == (V2_POS | (u32)p);
+        }
+      }
+    }
+    cnt = fl[0] + fl[1] + fl[2] + fl[3];
+    u32 inc = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const u32 o = __shfl_up_sync(0xffffffffu, inc, d);
+      if (lane >= d) inc += o;
+    }
+    if (lane == 31) s_w[wid] = inc;
+    __syncthreads();
+    u32 pre = 0, tot = 0;
+    for (int w = 0; w < NT / 32; ++w) { if (w < wid) pre += s_w[w]; tot += s_w[w]; }
+    u32 ex = pre + inc - cnt;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const i64 p = p0 + q;
+      if (p < E) a.erank[p] = ex;     // rank of p among the tile's firsts (only read for firsts)
+      ex += fl[q];
+    }
+    if (threadIdx.x == 0) a.mtile[tile] = tot;
+    __syncthreads();
+  }
+  tl_mark(TL_MARK | TL_END);
+  if (last_block(&a.st[ST_TICKET_B])) mark_finish(a, E, ntiles);
+}
+
+// ---- ids.  An edge's dst id = its ref if the node is older than this pass, else ids_base + rank of the node's first
+// position.  Firsts append their node to the dst list; the owner of the slot writes the id back unless no later pass
+// inserts into this table (then nobody will read it).
+template <bool SH>
+__global__ void __launch_bounds__(NT) k_v2_assign(const PassArgs a) {
+  pdl_enter(TL_ASSIGN);
+  const i64 E = a.st[ST_PASS_E];
+  const i64 pbase = a.st[ST_PASS_BASE];
+  const i64 list_base = a.st[ST_LIST_BASE], ids_base = a.st[ST_IDS_BASE];
+  const u32* __restrict__ xdst = SH ? x_ptr<u32>(a, a.xr, a.x_off_dst) : nullptr;
+  for (i64 p = (i64)blockIdx.x * NT + threadIdx.x; p < E; p += (i64)gridDim.x * NT) {
+    const u32 r = a.fref[p];
+    if (a.seed_mode) {
+      const bool first = r == (V2_POS | (u32)p);
+      const u32 s = a.eslot[p];
+      if (first && s != NO_SLOT) a.pk[s] = ((u64)(u32)a.dst_nodes[p] << 32) | (u64)(a.mtile[p / ETILE] + a.erank[p]);
+      a.dst_slot[p] = first ? s : NO_SLOT;
+      continue;
+    }
+    i64 id; bool first = false; i64 rank = 0;
+    if (r & V2_POS) {
+      const u32 q = r & ~V2_POS;
+      rank = a.mtile[q / ETILE] + a.erank[q];
+      id = ids_base + rank;
+      first = q == (u32)p;
+    } else {
+      id = r;
+    }
+    if (SH) a.eid[pbase + p] = a.x_eid64 ? (i64)x_ptr<u64>(a, a.xr, a.x_off_eid)[p] : (i64)x_ptr<u32>(a, a.xr, a.x_off_eid)[p];
+    if (!first) { a.colv[pbase + p] = id; continue; }
+    {
+      const i64 d = SH ? (i64)xdst[p] : a.colv[pbase + p];   // (global id, about to be replaced)
+      a.colv[pbase + p] = id;
+      const u32 s = a.eslot[p];
+      a.dst_nodes[list_base + rank] = d;
+      a.dst_slot[list_base + rank] = s;
+      if (a.v2_writeback && s != NO_SLOT) a.pk[s] = ((u64)(u32)d << 32) | (u64)id;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(NT) k_v2_cleanup(u64* pk, const u32* __restrict__ slots, const i64* n_ptr) {
+  pdl_enter();
+  const i64 n = *n_ptr;
+  for (i64 i = (i64)blockIdx.x * NT + threadIdx.x; i < n; i += (i64)gridDim.x * NT) {
+    const u32 s = slots[i];
+    if (s != NO_SLOT) pk[s] = EMPTY;
+  }
+}

@@ -3,8 +3,15 @@ configs[4]).  The reference has no multi-GPU sampler; its own decomposition of d
 `dist_neighbor_sample` (sample without relabel, neighbor_kernel.cpp:296-303,957-978) + merge + relabel.
 Here: the CSR is replicated, every rank calls `dist_neighbor_sample` with the same arguments and the
 same CPU generator state (`torch.manual_seed(s)` on every rank); per hop each rank draws the edges of
-its slice of the frontier, the drawn edge ids are all-gathered over NCCL (NVLink), and dedup / relabel
-run replicated, so every rank returns the SAME tensors as the single-GPU op (and as the reference).
+its slice of the frontier and every rank returns the SAME tensors as the single-GPU op (and as the
+reference).  Two transports (include/pyg_b200.h, `pygb200_sampler_run_sharded`):
+
+  * peer memory (default): the sampling kernel stores its edges straight into every rank's exchange
+    region over NVLink, dedup is partitioned by key hash, refs are reduced slice-wise over the peers —
+    no host sync, no collective call per hop (csrc/sampler_v2.cuh).  torch.distributed is only used to
+    swap the CUDA IPC handles of the regions when they are (re)allocated.
+  * `transport='collective'` (and always for disjoint runs): the drawn edge ids are all-gathered with
+    torch.distributed broadcasts (NCCL over NVLink) and dedup / relabel run replicated.
 
 Plumbing is torch.distributed; the sampling itself is `pygb200_sampler_run_sharded` of the C ABI.
 """
@@ -19,10 +26,25 @@ from torch import Tensor
 from .._rng import MT19937, read_default_cpu_engine, write_default_cpu_engine
 
 _ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_int64), C.c_int32, C.c_void_p)
+_EXCHANGE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64)
 
 
 class _Shard(C.Structure):
-    _fields_ = [('rank', C.c_int32), ('world', C.c_int32), ('allgather', _ALLGATHER_FN), ('user', C.c_void_p)]
+    _fields_ = [('rank', C.c_int32), ('world', C.c_int32), ('allgather', _ALLGATHER_FN), ('user', C.c_void_p),
+                ('exchange', _EXCHANGE_FN)]
+
+
+def allgather_blobs(mine: bytes, device: torch.device, group=None) -> bytes:
+    """Host all-gather of equally sized blobs in rank order (used to swap CUDA IPC handles)."""
+    world = dist.get_world_size(group)
+    backend = dist.get_backend(group)
+    t = torch.frombuffer(bytearray(mine), dtype=torch.uint8)
+    if backend == 'nccl':
+        t = t.to(device)
+    out = torch.empty(world * t.numel(), dtype=torch.uint8, device=t.device)
+    dist.all_gather_into_tensor(out, t, group=group) if backend == 'nccl' else \
+        dist.all_gather(list(out.view(world, -1).unbind(0)), t, group=group)
+    return bytes(out.cpu().numpy().tobytes())
 
 
 class _Relation(C.Structure):
@@ -81,8 +103,11 @@ def _handle(device: torch.device, stream: int):
 
 def dist_neighbor_sample(rowptr: Tensor, col: Tensor, seed: Tensor, num_neighbors: List[int], csc: bool = False,
                          replace: bool = False, disjoint: bool = False, return_edge_id: bool = True,
-                         group=None) -> Tuple[Tensor, Tensor, Tensor, Optional[Tensor], List[int], List[int]]:
-    """Same contract as `neighbor_sample` (uniform sampling, fan-outs >= 0); collective over `group`."""
+                         group=None, transport: str = 'peer') -> Tuple[Tensor, Tensor, Tensor, Optional[Tensor], List[int], List[int]]:
+    """Same contract as `neighbor_sample` (uniform sampling, fan-outs >= 0); collective over `group`.
+    `transport`: 'peer' (peer-memory stores + key-partitioned dedup; non-disjoint runs, <= 16 ranks) or 'collective'
+    (edge ids all-gathered with torch.distributed, replicated dedup)."""
+    assert transport in ('peer', 'collective')
     assert rowptr.is_cuda and col.is_cuda and seed.is_cuda, 'dist_neighbor_sample expects CUDA tensors'
     assert rowptr.dtype == col.dtype == seed.dtype and seed.dtype in (torch.int64, torch.int32)
     assert rowptr.is_contiguous() and col.is_contiguous() and seed.is_contiguous()
@@ -114,7 +139,18 @@ def dist_neighbor_sample(rowptr: Tensor, col: Tensor, seed: Tensor, num_neighbor
                 err.append(ex)
                 return 1
 
-        shard = _Shard(rank, world, _ALLGATHER_FN(_cb), None)
+        def _xcb(user, mine, out, nbytes):
+            try:
+                blob = C.string_at(mine, nbytes)
+                C.memmove(out, allgather_blobs(blob, dev, group), nbytes * world)
+                return 0
+            except Exception as ex:  # noqa
+                err.append(ex)
+                return 1
+
+        peer = transport == 'peer' and not disjoint and world <= 16 and len(num_neighbors) > 0 and \
+            min(num_neighbors) >= 0 and rowptr.numel() - 1 < 0xffffffff
+        shard = _Shard(rank, world, _ALLGATHER_FN(_cb), None, _EXCHANGE_FN(_xcb) if peer else _EXCHANGE_FN())
         mt = read_default_cpu_engine()
         rc = lib.pygb200_sampler_run_sharded(h, 1, 1, L, C.byref(rel), seeds, n_seeds, nn, flags, C.byref(mt), nph, eph,
                                              n_nodes, n_edges, C.c_void_p(stream), C.byref(shard))

@@ -27,6 +27,11 @@ def main():
             allgather_segments(buf, seg)
             exp = torch.cat([torch.arange(seg[q], seg[q + 1]) * 10 + q for q in range(world)]) if total else buf
             assert torch.equal(buf, exp), (rank, total)
+        # host all-gather of equally sized blobs (swaps the CUDA IPC handles of the peer-memory transport)
+        from pyg_lib_b200.sampler.dist import allgather_blobs
+        blob = bytes([(rank * 7 + i) % 256 for i in range(64)])
+        got = allgather_blobs(blob, torch.device('cpu'))
+        assert got == b''.join(bytes([(q * 7 + i) % 256 for i in range(64)]) for q in range(world)), rank
         # uneven, with empty segments
         seg = [0, 0, 5][:world + 1] if world == 2 else segment_bounds(9, world)
         buf = torch.zeros(seg[-1], dtype=torch.int64)
@@ -45,10 +50,13 @@ def main():
         seed = torch.randperm(20000, generator=torch.Generator().manual_seed(5))[:512]
         seed[3], seed[9] = 5, 77
         d = [t.to(dev) for t in (rowptr, col, seed)]
-        for kw in (dict(), dict(replace=True), dict(csc=True, return_edge_id=False), dict(disjoint=True)):
+        # both transports: peer memory (IPC-mapped exchange regions, key-partitioned dedup) and collective
+        # (edge ids all-gathered by torch.distributed, replicated dedup); disjoint runs always take the latter
+        for kw in (dict(), dict(replace=True), dict(csc=True, return_edge_id=False), dict(disjoint=True),
+                   dict(transport='collective'), dict(transport='collective', replace=True)):
             for nn in ([15, 10], [4, 3, 2], [40]):
                 torch.manual_seed(11)
-                exp = [O.neighbor_sample(rowptr, col, seed, nn, **kw) for _ in range(2)]
+                exp = [O.neighbor_sample(rowptr, col, seed, nn, **{k: v for k, v in kw.items() if k != 'transport'}) for _ in range(2)]
                 s_exp = torch.get_rng_state()
                 torch.manual_seed(11)
                 for i in range(2):

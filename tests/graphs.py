@@ -387,3 +387,32 @@ def build_merge(case, oracle_dist):
         node_ids.append(node.contiguous()); edge_ids.append(eid.contiguous()); cums.append([int(x) for x in cum])
     batch = torch.arange(seed.numel(), dtype=torch.int64) if disjoint else None
     return node_ids, edge_ids, cums, part.tolist(), orders, P, case['k'], batch, disjoint
+
+
+# ------------------------------------------------------------------------------------- config-size generators
+MAG240M_NODES = {'paper': 121_751_666, 'author': 122_383_112, 'institution': 25_721}
+MAG240M_EDGES = {('paper', 'cites', 'paper'): 1_297_748_926, ('author', 'writes', 'paper'): 386_022_720,
+                 ('author', 'affiliated_with', 'institution'): 44_592_586, ('paper', 'rev_writes', 'author'): 386_022_720,
+                 ('institution', 'rev_affiliated_with', 'author'): 44_592_586, ('paper', 'rev_cites', 'paper'): 1_297_748_926}
+
+
+def mag240m_shaped(scale: float, device='cpu', seed0: int = 10):
+    """BASELINE.json configs[3]: 3 node types / 6 edge types with MAG240M's node and edge counts times `scale`
+    (SURVEY.md 8d C4), log-normal degrees per relation, uniform targets.  Returns (sizes, rowptr_dict, col_dict) keyed by
+    edge-type tuples.  Generated with `device`'s generator: bit-identical across runs on the same device type."""
+    sizes = {k: max(int(v * scale), 64) for k, v in MAG240M_NODES.items()}
+    rowptr_d, col_d = {}, {}
+    for i, (k, e) in enumerate(MAG240M_EDGES.items()):
+        e = int(e * scale)
+        g = torch.Generator(device=device).manual_seed(seed0 + i)
+        w = torch.empty(sizes[k[0]], device=device, dtype=torch.float32).log_normal_(3.0, 1.2, generator=g)
+        deg = torch.floor(w.double() * (e / float(w.double().sum()))).to(torch.int64)
+        del w
+        rem = e - int(deg.sum())
+        deg[:rem] += 1
+        rowptr = torch.zeros(sizes[k[0]] + 1, dtype=torch.int64, device=device)
+        torch.cumsum(deg, 0, out=rowptr[1:])
+        del deg
+        col_d[k] = torch.randint(0, sizes[k[2]], (e,), generator=g, device=device, dtype=torch.int64)
+        rowptr_d[k] = rowptr
+    return sizes, rowptr_d, col_d

@@ -438,8 +438,12 @@ for name, case in HETERO_CASES.items():
     n += 1
 print('OK', n)
 ''' % (ROOT, ROOT, ROOT)
+    # (without the latency path bounded non-disjoint runs take the v2 schedule — packed table, refs — and the rest
+    #  the wide-table throughput path; PYGB200_NO_V2 sends everything to the latter)
     for extra in ({'PYGB200_NO_LATENCY_PATH': '1'}, {'PYGB200_DIRECT_OUTPUT_MB': '0'},
-                  {'PYGB200_NO_LATENCY_PATH': '1', 'PYGB200_DIRECT_OUTPUT_MB': '0'}):
+                  {'PYGB200_NO_LATENCY_PATH': '1', 'PYGB200_DIRECT_OUTPUT_MB': '0'},
+                  {'PYGB200_NO_LATENCY_PATH': '1', 'PYGB200_NO_V2': '1'},
+                  {'PYGB200_NO_LATENCY_PATH': '1', 'PYGB200_NO_V2': '1', 'PYGB200_DIRECT_OUTPUT_MB': '0'}):
         env = dict(os.environ, **extra)
         out = subprocess.run([sys.executable, '-c', code], env=env, capture_output=True, text=True, timeout=600)
         assert out.returncode == 0 and 'OK' in out.stdout, (extra, out.stdout[-2000:], out.stderr[-4000:])
