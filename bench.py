@@ -1,25 +1,31 @@
-"""bench.py — headline benchmark of the B200 hot paths (contract: see the task statement / DESIGN.md).
+"""bench.py — headline benchmark of the B200 hot paths (contract: see the task statement / DESIGN.md §5).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
-metric  : sampled edges/s of pyg_lib.sampler.neighbor_sample on BASELINE.json configs[1]
-          (ogbn-products-shaped CSR, 2,449,029 nodes / 123,718,280 edges, int64, fan-out [15,10],
-          1024 seeds per step, no replacement, return_edge_id).  One step = one call on one batch.
-value   : whole-job edges/s with the graph AND the seeds resident in HBM (each call still ends with the
-          API's own host sync, because the op returns Python lists).
-e2e     : same metric through the public API with HOST buffers: pinned seeds -> device every step and
-          the sampled (row, col, node_id, edge_id) copied back to pinned host memory every step.
-The same JSON line carries `roofline` (dominant kernel, device-timed), `cpu_baseline` (the reference's
-CPU implementation timed on this box's host cores, bounded sample) and `segment_matmul` (BASELINE.json
-configs[2]: 64 relations, N=2^20 ragged rows, 128->128 bf16, TFLOP/s + roofline fractions).
-N>1: every rank holds a replica of the CSR and samples its own disjoint seed batches (weak scaling;
-no data-path collective) — the frontier-sharded all-gather variant is pyg_lib_b200.sampler.dist.
+metric  : sampled edges/s of pyg_lib.sampler.neighbor_sample.
+N = 1   : BASELINE.json configs[1] — ogbn-products-shaped CSR (2,449,029 nodes / 123,718,280 edges, int64), fan-out
+          [15,10], 1024 seeds per step, no replacement, return_edge_id.  One step = one call on one batch.
+          `value` = graph AND seeds resident in HBM (each call still ends with the API's own host sync, because the op
+          returns Python lists); `e2e` = the same through the public API with HOST buffers: pinned seeds -> device
+          every step, sampled (row, col, node_id, edge_id) -> pinned host memory every step.
+          Same JSON line: `parity` (gates run BEFORE timing, against the reference's CPU implementation in a
+          subprocess: C2 bit-exact incl. generator state, C3 bf16 <= 1e-3 rel. Frobenius and <= 1 ulp), `roofline`
+          (dominant sampler kernel, device-timed, actual edges), `cpu_baseline`, `segment_matmul` (configs[2]: 64
+          relations, N = 2^20 ragged rows, 128 -> 128 bf16: TFLOP/s, roofline, its own e2e), `c5_single_gpu`
+          (configs[4]'s graph and batch on one GPU: the strong-scaling baseline of the N > 1 lines).
+N > 1   : BASELINE.json configs[4] — papers100M-shaped CSR (111,059,956 nodes / 1,615,685,872 edges) replicated on
+          every GPU, ONE batch of 65,536 seeds per step, frontier-sharded over the ranks: each rank draws its slice of
+          every hop's frontier, the sampled edges are all-gathered over NVLink (peer-memory stores fused into the
+          sampling kernel), dedup is partitioned by key; every rank returns the full, reference-exact result.
+          `scaling` = "strong" (work per step is fixed as N grows); `c5.single_gpu_edges_per_s` is measured in the
+          same run, `replicas` keeps the collective-free weak-scaling number of round 1 as a secondary key.
 """
 import argparse
 import ctypes as C
 import json
 import os
 import os.path as osp
+import queue
 import statistics
 import subprocess
 import sys
@@ -31,8 +37,9 @@ for p in (ROOT, osp.join(ROOT, 'tests')):
     if p not in sys.path:
         sys.path.insert(0, p)
 
-N_NODES, N_EDGES = 2_449_029, 123_718_280
+N_NODES, N_EDGES = 2_449_029, 123_718_280            # C2
 BATCH, FANOUT = 1024, [15, 10]
+C5_NODES, C5_EDGES, C5_BATCH = 111_059_956, 1_615_685_872, 65_536
 BYTES_PER_EDGE = 41.0  # algorithmic bytes per sampled edge at fan-out [15,10], int64
 
 
@@ -95,42 +102,240 @@ class ClockMonitor:
                 'reasons': sorted(reasons), 'samples': len(sm)}
 
 
-def run_ref_bench(args):
+def run_ref_bench(args, timeout=3000):
     out = subprocess.run([sys.executable, osp.join(ROOT, 'oracle', 'ref_bench.py')] + args, stdout=subprocess.PIPE,
-                         stderr=subprocess.PIPE, text=True, timeout=3000)
+                         stderr=subprocess.PIPE, text=True, timeout=timeout)
     for ln in out.stdout.splitlines():
         if ln.startswith('REFBENCH '):
             return json.loads(ln[len('REFBENCH '):])
     raise RuntimeError('ref_bench failed: ' + out.stderr[-2000:])
 
 
+def host_cores():
+    """Cores this process may run on (the cgroup's share of the box), not os.cpu_count()."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:  # noqa
+        return os.cpu_count() or 1
+
+
+def config_dict(n_gpus):
+    if n_gpus == 1:
+        return {'workload': 'neighbor_sample ogbn-products-shaped CSR (2,449,029 nodes / 123,718,280 edges, int64, '
+                            'log-normal degrees), fanout [15,10], 1024 seeds/step, replace=False, return_edge_id=True',
+                'batch_seeds': BATCH, 'fanout': FANOUT, 'index_dtype': 'int64', 'parallelism': 'single GPU',
+                'l2': 'inputs_larger_than_L2 (col = 990 MB, new random seeds every step)'}
+    return {'workload': 'neighbor_sample papers100M-shaped CSR (111,059,956 nodes / 1,615,685,872 edges, int64, log-normal '
+                        'degrees), fanout [15,10], ONE batch of 65,536 seeds per step, replace=False, return_edge_id=True',
+            'batch_seeds': C5_BATCH, 'fanout': FANOUT, 'index_dtype': 'int64',
+            'parallelism': 'frontier-sharded x%d: CSR replicated, each rank draws 1/%d of every frontier, sampled edges '
+                           'all-gathered by peer-memory stores over NVLink, dedup partitioned by key hash, identical full '
+                           'result on every rank' % (n_gpus, n_gpus),
+            'l2': 'inputs_larger_than_L2 (col = 12.9 GB, new random seeds every step)'}
+
+
 def reference_arm(a):
-    """--impl reference: the reference's CPU implementation on the host cores, same metric/config."""
+    """--impl reference: the reference's CPU implementation on the host cores, same metric/config as our arm at this N:
+    one single-threaded worker process per core of the cgroup (how PyG deploys CPU sampling), each step a bounded
+    sample; median over three repeats."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
-    workers = max(1, cores)  # every host thread: one single-threaded worker process per core (how PyG deploys it)
-    per_step_calls = 2  # each "step" = a bounded sample: `workers` processes x 2 calls of 1024 seeds
-    total_calls = per_step_calls * (a.steps + a.warmup)
-    total_calls = max(2, min(total_calls, 40))  # keep the whole run within a few minutes
-    r = run_ref_bench(['sampler', '--workers', str(workers), '--calls', str(total_calls)])
+    workers = host_cores()
+    if a.gpus == 1:
+        calls = max(2, min(2 * (a.steps + a.warmup), 40))
+        reps = [run_ref_bench(['sampler', '--workers', str(workers), '--calls', str(calls)]) for _ in range(3)]
+    else:   # configs[4]: papers100M-shaped graph, 65,536-seed batches (a call is ~1 s of one core)
+        reps = [run_ref_bench(['sampler', '--workers', str(workers), '--calls', '2', '--graph', 'papers', '--batch', str(C5_BATCH)])]
+    reps.sort(key=lambda r: r['edges_per_s'])
+    r = reps[len(reps) // 2]
     line = {'impl': 'reference', 'metric': 'sampled_edges_per_s', 'value': r['edges_per_s'], 'unit': 'edges/s',
             'n_gpus': a.gpus, 'steps': a.steps, 'warmup': a.warmup,
             'ms_per_step': 1e3 * r['seconds'] / max(r['calls'] / workers, 1), 'higher_is_better': True,
-            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'int64', 'data': 'synthetic', 'config': config_dict(a.gpus),
+            'scaling': 'weak' if a.gpus == 1 else 'strong', 'vs_baseline': None, 'dtype': 'int64', 'data': 'synthetic',
+            'config': config_dict(a.gpus),
             'cpu_baseline': {'value': r['edges_per_s'], 'unit': 'edges/s', 'cores': r['cores'], 'kind': r['kind'],
-                             'sample': r['sample']},
+                             'sample': r['sample'], 'repeats': [x['edges_per_s'] for x in reps]},
             'e2e': {'value': r['edges_per_s'], 'unit': 'edges/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
     print(json.dumps(line), flush=True)
 
 
-def config_dict(n_gpus):
-    return {'workload': 'neighbor_sample ogbn-products-shaped CSR (2,449,029 nodes / 123,718,280 edges, int64, '
-                        'log-normal degrees), fanout [15,10], 1024 seeds/step, replace=False, return_edge_id=True',
-            'batch_seeds': BATCH, 'fanout': FANOUT, 'index_dtype': 'int64',
-            'parallelism': 'replicas x%d (disjoint seed batches per rank, CSR replicated)' % n_gpus,
-            'l2': 'inputs_larger_than_L2 (col = 990 MB, new random seeds every step)'}
+# ------------------------------------------------------------------------------------------------ parity gates
+def parity_gates(P, dev, rowptr_c, col_c, rowptr, col, perm, with_matmul=True):
+    """parity before timing, at config size, against the reference in a subprocess."""
+    import torch
+    from graphs import ragged_ptr
+    from refproc import RefSession, compare_homo, lowp_ulp_excess, rng_prefix
+    res = {}
+    seeds = [perm[b * BATCH:(b + 1) * BATCH].clone() for b in (0, 1)]
+    with RefSession() as rs:
+        ref = rs.run(dict(kind='homo', rowptr=rs.share(rowptr_c), col=rs.share(col_c), seeds=seeds, num_neighbors=FANOUT, rng_seed=777))
+        saved = torch.get_rng_state()
+        torch.manual_seed(777)
+        cmp = [compare_homo(P.sampler.neighbor_sample(rowptr, col, s.to(dev), FANOUT), c) for s, c in zip(seeds, ref['calls'])]
+        rng_ok = bool(torch.equal(rng_prefix(), ref['rng_after']))
+        torch.set_rng_state(saved)
+        res['c2_neighbor_sample'] = {'against': ref['kind'], 'calls': len(cmp), 'edges': sum(c['edges'] for c in cmp),
+                                     'bit_exact': all(c['bit_exact'] for c in cmp), 'generator_state_equal': rng_ok,
+                                     'mismatch': sum((c['mismatch'] for c in cmp), [])}
+        ok = res['c2_neighbor_sample']['bit_exact'] and rng_ok
+        if with_matmul:
+            Nn, K, M, B = 1 << 20, 128, 128, 64
+            g = torch.Generator().manual_seed(0)
+            x = torch.randn(Nn, K, generator=g).to(torch.bfloat16)
+            w = (torch.randn(B, K, M, generator=g) / K ** 0.5).to(torch.bfloat16)
+            ptr = ragged_ptr(Nn, B, 100)
+            y_path = rs.out_file(Nn * M, torch.bfloat16)
+            refm = rs.run(dict(kind='matmul', x=rs.share(x), w=rs.share(w), ptr=ptr, y_path=y_path))
+            y_ref = torch.from_file(y_path, shared=False, size=Nn * M, dtype=torch.bfloat16).view(Nn, M)
+            y = P.ops.segment_matmul(x.to(dev), ptr.to(dev), w.to(dev)).cpu()
+            rel = float((y.float() - y_ref.float()).norm() / y_ref.float().norm())
+            ulp = lowp_ulp_excess(y, y_ref)
+            res['c3_segment_matmul'] = {'against': refm['kind'], 'rel_frobenius': rel, 'max_ulp': ulp, 'tolerance': '<= 1e-3 and <= 1 bf16 ulp',
+                                        'pass': rel <= 1e-3 and ulp <= 1.0}
+            ok = ok and res['c3_segment_matmul']['pass']
+            del y_ref
+    res['pass'] = bool(ok)
+    return res
+
+
+# ------------------------------------------------------------------------------------------------ helpers
+class Timer:
+    def __init__(self, torch, dist, dev, world, mon, P):
+        self.torch, self.dist, self.dev, self.world, self.mon, self.P = torch, dist, dev, world, mon, P
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def run(self, step_fn, steps, warmup, finish=None, first=0):
+        """`warmup` untimed calls, then exactly `steps` timed ones between barrier + synchronize; CUDA events on the
+        current stream; max over ranks; edges summed over ranks unless the step is collective (same result everywhere)."""
+        torch = self.torch
+        for i in range(warmup):
+            step_fn(first + i)
+        if finish is not None:
+            finish()
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = self.P.kernel_launches()
+        edges = 0
+        with self.mon:
+            e0.record()
+            for i in range(warmup, warmup + steps):
+                edges += step_fn(first + i)
+            if finish is not None:
+                finish()   # e.g. make the timed stream wait for outstanding result copies
+            e1.record()
+            torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        launches = self.P.kernel_launches() - l0
+        t = torch.tensor([ms, float(edges), float(launches)], dtype=torch.float64, device=self.dev)
+        if self.world > 1:
+            tmax = t.clone(); self.dist.all_reduce(tmax, op=self.dist.ReduceOp.MAX)
+            tsum = t.clone(); self.dist.all_reduce(tsum, op=self.dist.ReduceOp.SUM)
+            ms, edges_sum, launches = float(tmax[0]), float(tsum[1]), float(tsum[2])
+        else:
+            edges_sum = float(edges)
+        self.barrier()
+        return ms, float(edges), edges_sum, int(launches), self.mon.summary()
+
+
+class HostCopier:
+    """The loader side of the e2e leg: a second host thread queues the device -> pinned-host copies of step i on a copy
+    stream while the main thread is already inside the next sampling call (the op releases the GIL while it waits
+    for the GPU).  Four rotating sets of pinned buffers."""
+    def __init__(self, torch, dev, caps, n_slots=4):
+        self.torch, self.dev = torch, dev
+        self.bufs = [[torch.empty(c, dtype=torch.int64).pin_memory() for c in caps] for _ in range(n_slots)]
+        self.done = [torch.cuda.Event() for _ in range(n_slots)]
+        self.stream = torch.cuda.Stream(device=dev)
+        self.q = queue.Queue()
+        self.bytes = 0
+        self.n = 0
+        self.t = threading.Thread(target=self._loop, daemon=True)
+        self.t.start()
+
+    def _loop(self):
+        torch = self.torch
+        torch.cuda.set_device(self.dev)
+        while True:
+            item = self.q.get()
+            if item is None:
+                self.q.task_done()
+                return
+            outs, ready = item
+            slot = self.n % len(self.bufs)
+            self.n += 1
+            self.done[slot].synchronize()           # the buffers of step i - n_slots are free again
+            with torch.cuda.stream(self.stream):
+                self.stream.wait_event(ready)
+                for h, t in zip(self.bufs[slot], outs):
+                    t.record_stream(self.stream)
+                    h[:t.numel()].copy_(t.reshape(-1), non_blocking=True)
+                self.done[slot].record()
+            self.bytes += 8 * sum(t.numel() for t in outs)
+            self.q.task_done()
+
+    def submit(self, outs):
+        ready = self.torch.cuda.Event()
+        ready.record()
+        self.q.put((outs, ready))
+
+    def drain(self):
+        self.q.join()
+        self.torch.cuda.current_stream().wait_stream(self.stream)
+
+    def close(self):
+        self.q.put(None)
+        self.t.join(timeout=5)
+
+
+def sampler_roofline(abi, step_dev, first, n_prof, torch, peaks, hbm_peak, peak_src, traffic):
+    """CUDA events on the launching stream around every launch of the sampler's kernels (pygb200_profile_*);
+    `work` = edges the timed calls actually emitted (not the static bound)."""
+    abi.pygb200_profile_enable(1)
+    edges = 0
+    for i in range(first, first + n_prof):
+        edges += step_dev(i)
+    torch.cuda.synchronize()
+    abi.pygb200_profile_enable(0)
+    prof = {}
+    for name in ('count', 'sample', 'mark', 'assign', 'lookup'):
+        msv, ln, wk = C.c_double(), C.c_int64(), C.c_int64()
+        abi.pygb200_profile_read(name.encode(), C.byref(msv), C.byref(ln), C.byref(wk))
+        prof[name] = (msv.value, ln.value, wk.value)
+    dom = max(prof, key=lambda k: prof[k][0])
+    d_ms, d_launches, _ = prof[dom]
+    launches_per_call = max(d_launches, 1) / max(n_prof, 1)
+    # every edge of a call passes through exactly one launch of the kernel: bytes per launch = 41 B x edges per launch
+    bytes_per_launch = BYTES_PER_EDGE * edges / max(d_launches, 1)
+    avg_s = d_ms / max(d_launches, 1) * 1e-3
+    achieved = bytes_per_launch / avg_s / 1e9 if d_ms > 0 else 0.0
+    return {'bound': 'hbm', 'kernel': 'k_' + dom, 'achieved': achieved, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': achieved / hbm_peak,
+            'traffic': traffic, 'peak_source': peak_src, 'avg_launch_us': 1e6 * avg_s, 'bytes_per_launch': bytes_per_launch,
+            'launches_per_call': launches_per_call, 'edges_per_call': edges / max(n_prof, 1),
+            'kernel_ms_share': {k: v[0] for k, v in prof.items()}}
+
+
+def load_traffic():
+    """DRAM bytes per launch of the dominant kernels from the committed `ncu --set full` captures (profiles/)."""
+    out = {}
+    for fn in ('ncu_summary_r2.json', 'ncu_summary_r1.json'):
+        try:
+            summ = json.load(open(osp.join(ROOT, 'profiles', fn)))
+        except Exception:  # noqa
+            continue
+        for grp in summ.values():
+            for d in grp:
+                for nm in ('k_v2_sample', 'k_sample_s', 'k_sample', 'k_segment_matmul_tc'):
+                    if nm in d['Kernel Name']:
+                        out.setdefault(nm, []).append(1e6 * (float(d['dram__bytes_read.sum']) + float(d['dram__bytes_write.sum'])))
+                        break
+        if out:
+            break
+    return {k: sum(v) / len(v) for k, v in out.items()}
 
 
 def main():
@@ -141,7 +346,10 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-matmul', action='store_true')
+    ap.add_argument('--no-parity', action='store_true')
+    ap.add_argument('--no-c5', action='store_true', help='N=1: skip the papers100M-shaped single-GPU leg')
     a = ap.parse_args()
+    a.warmup = max(a.warmup, 3)
     if a.impl == 'reference':
         return reference_arm(a)
 
@@ -157,148 +365,82 @@ def main():
         dist.init_process_group('nccl', device_id=dev)
     import pyg_lib_b200 as P
     abi = C.CDLL(osp.join(osp.dirname(P.__file__), 'libpyg_b200.so'))
+    peaks = {}
+    try:
+        peaks = json.load(open(osp.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:  # noqa
+        pass
+    hbm_peak = float(peaks.get('hbm_gbs', 6650.0))
+    peak_src = 'measured (MEASURED_PEAKS.json)' if 'hbm_gbs' in peaks else 'fallback 6.65 TB/s (B200_PROFILING.md)'
+    traffic = load_traffic()
+    mon = ClockMonitor(local).start()
+    T = Timer(torch, dist, dev, world, mon, P)
 
-    # ---- synthetic inputs (deterministic; CPU-generated so the CPU baseline sees the same graph)
+    # ---- C2 inputs (deterministic; CPU-generated so that the reference process sees the same graph)
     rowptr_c, col_c = lognormal_csr(N_NODES, N_EDGES, seed=1)
     rowptr, col = rowptr_c.to(dev), col_c.to(dev)
-    del col_c
     perm = torch.randperm(N_NODES, generator=torch.Generator().manual_seed(2))
     n_batches = N_NODES // BATCH
-    my_batches = [(rank + i * world) % n_batches for i in range(a.steps + a.warmup)]
-    seeds_host = [perm[b * BATCH:(b + 1) * BATCH].clone().pin_memory() for b in my_batches]
-    seeds_dev = [s.to(dev) for s in seeds_host]
-    torch.manual_seed(12345 + rank)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    line = {}
+    if world == 1:
+        # ================================================================ N = 1: configs[1] (+ configs[2], configs[4] on one GPU)
+        parity = None
+        if not a.no_parity:
+            parity = parity_gates(P, dev, rowptr_c, col_c, rowptr, col, perm, with_matmul=not a.no_matmul)
+            if not parity['pass']:
+                print(json.dumps({'metric': 'sampled_edges_per_s', 'value': None, 'parity': parity,
+                                  'error': 'parity gate failed: nothing was timed'}), flush=True)
+                mon.stop()
+                sys.exit(1)
+        del col_c
+        my_batches = [i % n_batches for i in range(a.steps + a.warmup + 64)]
+        seeds_host = [perm[b * BATCH:(b + 1) * BATCH].clone().pin_memory() for b in my_batches]
+        seeds_dev = [s.to(dev) for s in seeds_host]
+        torch.manual_seed(12345)
 
-    mon = ClockMonitor(local).start()
+        def step_dev(i):
+            return P.sampler.neighbor_sample(rowptr, col, seeds_dev[i], FANOUT)[0].numel()
+        ms, edges, _, launches, clocks = T.run(step_dev, a.steps, a.warmup)
+        value = edges / (ms * 1e-3)
 
-    def timed(step_fn, finish=None):
-        for i in range(a.warmup):
-            step_fn(i)
-        if finish is not None:
-            finish()
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        l0 = P.kernel_launches()
-        edges = 0
-        with mon:
-            e0.record()
-            for i in range(a.warmup, a.warmup + a.steps):
-                edges += step_fn(i)
-            if finish is not None:
-                finish()   # e.g. make the timed stream wait for outstanding result copies
-            e1.record()
-            torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1)
-        launches = P.kernel_launches() - l0
-        t = torch.tensor([ms, float(edges), float(launches)], dtype=torch.float64, device=dev)
-        if world > 1:
-            tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-            tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-            ms, edges, launches = float(tmax[0]), float(tsum[1]), float(tsum[2])
-        barrier()
-        return ms, edges, int(launches), mon.summary()
+        # e2e: pinned seeds -> device and (row, col, node, eid) -> pinned host EVERY step, through the public API.  The
+        # calls themselves cannot overlap (each consumes the CPU generator where the previous one left it); the result
+        # copies are queued by a loader thread and run on a copy stream beside the next call.
+        cap = BATCH * (FANOUT[0] + FANOUT[0] * FANOUT[1])
+        copier = HostCopier(torch, dev, [cap, cap, cap + BATCH, cap])
 
-    # ---- value: inputs resident in HBM
-    def step_dev(i):
-        out = P.sampler.neighbor_sample(rowptr, col, seeds_dev[i], FANOUT)
-        return out[0].numel()
-    ms, edges, launches, clocks = timed(step_dev)
-    value = edges / (ms * 1e-3)
+        def step_e2e(i):
+            s = seeds_host[i].to(dev, non_blocking=True)
+            outs = P.sampler.neighbor_sample(rowptr, col, s, FANOUT)[:4]
+            copier.submit(outs)
+            return outs[0].numel()
+        b0 = copier.bytes
+        ms_e, edges_e, _, _, _ = T.run(step_e2e, a.steps, a.warmup, finish=copier.drain)
+        e2e = {'value': edges_e / (ms_e * 1e-3), 'unit': 'edges/s', 'h2d_bytes_per_step': BATCH * 8,
+               'd2h_bytes_per_step': int((copier.bytes - b0) / max(a.steps + a.warmup, 1)), 'ms_per_step': ms_e / a.steps,
+               'how': 'pinned seeds H2D + 4 result tensors D2H (pinned) every step; copies queued by a loader thread on a copy stream'}
+        copier.close()
 
-    # ---- e2e: host seeds in (pinned -> device) and host results out (device -> pinned) EVERY step, through the
-    # public API.  Like a double-buffered loader, the result copy of step i runs on a copy stream while step
-    # i+1 samples (the calls themselves cannot overlap: each consumes the CPU generator where the previous one
-    # left it); the timed region ends only after the last copy has landed.
-    cap = BATCH * (FANOUT[0] + FANOUT[0] * FANOUT[1]) + BATCH
-    host_out = [[torch.empty(cap, dtype=torch.int64).pin_memory() for _ in range(4)] for _ in range(2)]
-    copy_stream = torch.cuda.Stream(device=dev)
-    copied = [torch.cuda.Event(), torch.cuda.Event()]
-    d2h = [0]
+        line = {'metric': 'sampled_edges_per_s', 'value': value, 'unit': 'edges/s', 'n_gpus': 1, 'steps': a.steps,
+                'warmup': a.warmup, 'ms_per_step': ms / a.steps, 'higher_is_better': True, 'scaling': 'weak',
+                'vs_baseline': None, 'dtype': 'int64', 'data': 'synthetic', 'config': config_dict(1), 'clocks': clocks,
+                'e2e': e2e, 'gpu_launches': launches, 'edges_per_step': edges / a.steps}
+        if parity is not None:
+            line['parity'] = parity
+        rf = sampler_roofline(abi, step_dev, a.warmup, min(50, a.steps), torch, peaks, hbm_peak, peak_src, None)
+        rf['traffic'] = traffic.get(rf['kernel'] + '_s') or traffic.get(rf['kernel'])
+        rf['kernel'] += '_s'   # C2 runs the latency-path kernels (k_sample_s, ...)
+        rf['note'] = 'C2 is latency-bound (~5 MB per call): the HBM fraction is reported, the binding limit is the ' \
+                     'per-call chain of dependent launches + one host round trip'
+        line['roofline'] = rf
 
-    def step_e2e(i):
-        s = seeds_host[i].to(dev, non_blocking=True)
-        outs = P.sampler.neighbor_sample(rowptr, col, s, FANOUT)[:4]
-        ready = torch.cuda.Event()
-        ready.record()
-        slot = i & 1
-        copied[slot].synchronize()          # host buffers of step i-2 are free again
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(ready)
-            for h, t in zip(host_out[slot], outs):
-                t.record_stream(copy_stream)
-                h[:t.numel()].copy_(t, non_blocking=True)
-            copied[slot].record()
-        d2h[0] += 8 * sum(t.numel() for t in outs)
-        return outs[0].numel()
-
-    def finish_e2e():
-        torch.cuda.current_stream().wait_stream(copy_stream)
-    ms_e, edges_e, _, _ = timed(step_e2e, finish_e2e)
-    # (d2h counter also ran during warm-up; per-step figure from the timed steps only)
-    e2e = {'value': edges_e / (ms_e * 1e-3), 'unit': 'edges/s', 'h2d_bytes_per_step': BATCH * 8,
-           'd2h_bytes_per_step': int(d2h[0] / max(a.steps + a.warmup, 1))}
-
-    line = {'metric': 'sampled_edges_per_s', 'value': value, 'unit': 'edges/s', 'n_gpus': world, 'steps': a.steps,
-            'warmup': a.warmup, 'ms_per_step': ms / a.steps, 'higher_is_better': True, 'scaling': 'weak',
-            'vs_baseline': None, 'dtype': 'int64', 'data': 'synthetic', 'config': config_dict(world), 'clocks': clocks,
-            'e2e': e2e, 'gpu_launches': launches, 'edges_per_step': edges / a.steps / world}
-
-    if rank == 0:
-        # ---- roofline of the dominant sampler kernel: CUDA events on the launching stream around every launch
-        peaks = {}
-        try:
-            peaks = json.load(open(osp.join(ROOT, 'MEASURED_PEAKS.json')))
-        except Exception:  # noqa
-            pass
-        # DRAM traffic per launch of the dominant kernels, from the committed `ncu --set full` capture
-        # (profiles/ncu_summary_r1.json: dram__bytes_read.sum + dram__bytes_write.sum, MB)
-        traffic = {}
-        try:
-            summ = json.load(open(osp.join(ROOT, 'profiles', 'ncu_summary_r1.json')))
-            for grp in summ.values():
-                for d in grp:
-                    nm = 'k_sample' if 'k_sample' in d['Kernel Name'] else ('k_segment_matmul_tc' if 'k_segment_matmul_tc' in d['Kernel Name'] else None)
-                    if nm:
-                        traffic.setdefault(nm, []).append(1e6 * (float(d['dram__bytes_read.sum']) + float(d['dram__bytes_write.sum'])))
-            traffic = {k: sum(v) / len(v) for k, v in traffic.items()}
-        except Exception:  # noqa
-            traffic = {}
-        hbm_peak = float(peaks.get('hbm_gbs', 6650.0))
-        peak_src = 'measured (MEASURED_PEAKS.json)' if 'hbm_gbs' in peaks else 'fallback 6.65 TB/s'
-        abi.pygb200_profile_enable(1)
-        n_prof = min(50, a.steps)
-        for i in range(a.warmup, a.warmup + n_prof):
-            step_dev(i)
-        torch.cuda.synchronize()
-        abi.pygb200_profile_enable(0)
-        prof = {}
-        for name in ('count', 'sample', 'mark', 'assign', 'lookup'):
-            msv, ln, wk = C.c_double(), C.c_int64(), C.c_int64()
-            abi.pygb200_profile_read(name.encode(), C.byref(msv), C.byref(ln), C.byref(wk))
-            prof[name] = (msv.value, ln.value, wk.value)
-        dom = max(prof, key=lambda k: prof[k][0])
-        d_ms, d_launches, d_work = prof[dom]
-        # the second-hop launch carries ~90% of the edges; report per-launch averages over both hops
-        bytes_per_launch = BYTES_PER_EDGE * d_work / max(d_launches, 1)
-        achieved = bytes_per_launch / (d_ms / max(d_launches, 1) * 1e-3) / 1e9 if d_ms > 0 else 0.0
-        line['roofline'] = {'bound': 'hbm', 'kernel': 'k_' + dom + '_s' if dom != 'lookup' else 'k_lookup', 'achieved': achieved, 'peak': hbm_peak, 'unit': 'GB/s',
-                            'frac': achieved / hbm_peak, 'traffic': traffic.get('k_' + dom), 'peak_source': peak_src,
-                            'avg_launch_us': 1e3 * d_ms / max(d_launches, 1),
-                            'bytes_per_launch': bytes_per_launch,
-                            'kernel_ms_share': {k: v[0] for k, v in prof.items()},
-                            'note': 'C2 is latency-bound (5 MB/call): the fraction is reported, the binding limit is '
-                                    'the per-call critical path (launches + one D2H)'}
-
-        # ---- segment_matmul (BASELINE configs[2]); single GPU
+        # ---- segment_matmul (BASELINE configs[2])
         if not a.no_matmul:
             Nn, K, M, B = 1 << 20, 128, 128, 64
             g = torch.Generator().manual_seed(0)
-            x = torch.randn(Nn, K, generator=g).to(torch.bfloat16).to(dev)
+            xh = torch.randn(Nn, K, generator=g).to(torch.bfloat16).pin_memory()
+            x = xh.to(dev)
             w = (torch.randn(B, K, M, generator=g) / K ** 0.5).to(torch.bfloat16).to(dev)
             ptr = ragged_ptr(Nn, B, 100).to(dev)
             for _ in range(5):
@@ -311,6 +453,16 @@ def main():
                 y = P.ops.segment_matmul(x, ptr, w)
             e1.record(); torch.cuda.synchronize()
             mm_ms = e0.elapsed_time(e1) / iters
+            # e2e: features from pinned host memory in, result back to pinned host memory, every call
+            yh = torch.empty(Nn, M, dtype=torch.bfloat16).pin_memory()
+            for _ in range(2):
+                yh.copy_(P.ops.segment_matmul(xh.to(dev, non_blocking=True), ptr, w), non_blocking=True)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(10):
+                yh.copy_(P.ops.segment_matmul(xh.to(dev, non_blocking=True), ptr, w), non_blocking=True)
+            e1.record(); torch.cuda.synchronize()
+            mm_e2e_ms = e0.elapsed_time(e1) / 10
             flops, byts = 2.0 * Nn * K * M, Nn * K * 2 + Nn * M * 2 + B * K * M * 2 + (B + 1) * 8
             tf_peak = float(peaks.get('bf16_tflops', 1590.0))
             line['segment_matmul'] = {
@@ -319,25 +471,154 @@ def main():
                 'roofline': {'bound': 'hbm', 'achieved': byts / (mm_ms * 1e-3) / 1e9, 'peak': hbm_peak, 'unit': 'GB/s',
                              'frac': byts / (mm_ms * 1e-3) / 1e9 / hbm_peak, 'traffic': traffic.get('k_segment_matmul_tc'),
                              'tensor_frac_of_bf16_peak': flops / (mm_ms * 1e-3) / 1e12 / tf_peak},
+                'e2e': {'value': flops / (mm_e2e_ms * 1e-3) / 1e12, 'unit': 'TFLOP/s', 'ms': mm_e2e_ms,
+                        'h2d_bytes_per_step': Nn * K * 2, 'd2h_bytes_per_step': Nn * M * 2,
+                        'note': '512 MiB over PCIe per call: the link, not the kernel, is the bound'},
                 'note': 'x (256 MiB) + out (256 MiB) > L2; arithmetic intensity 63.75 FLOP/B => HBM-bound'}
-            del x, w, y
+            del x, w, y, xh, yh
+
+        # ---- configs[4] on one GPU: the strong-scaling baseline of the N > 1 lines, and the throughput schedule's roofline
+        if not a.no_c5:
+            del rowptr, col
+            torch.cuda.empty_cache()
+            line['c5_single_gpu'] = c5_leg(a, P, abi, T, torch, dev, 1, 0, peaks, hbm_peak, peak_src, traffic, None)
 
         # ---- CPU baseline: the reference's own CPU path on this box's host cores (bounded sample)
-        if world == 1 and not a.no_cpu_baseline:
+        if not a.no_cpu_baseline:
             try:
                 r = run_ref_bench(['sampler', '--workers', '1', '--calls', '200'])
                 line['cpu_baseline'] = {'value': r['edges_per_s'], 'unit': 'edges/s', 'cores': r['cores'], 'kind': r['kind'],
-                                        'sample': r['sample'], 'host_cores_available': os.cpu_count()}
+                                        'sample': r['sample'], 'host_cores_available': host_cores()}
                 if not a.no_matmul:
-                    rm = run_ref_bench(['matmul', '--calls', '3'])
-                    line['segment_matmul']['cpu_baseline'] = {'value': rm['tflops'], 'unit': 'TFLOP/s', 'cores': rm['cores'],
-                                                              'kind': rm['kind'], 'sample': rm['sample']}
+                    best = None
+                    for th in (8, 16, 32, 64):   # an oversubscribed thread pool is not a baseline: keep the best
+                        if th > host_cores():
+                            break
+                        rm = run_ref_bench(['matmul', '--calls', '3', '--workers', str(th)])
+                        if best is None or rm['tflops'] > best['tflops']:
+                            best = rm
+                    if best is not None:
+                        line['segment_matmul']['cpu_baseline'] = {'value': best['tflops'], 'unit': 'TFLOP/s', 'cores': best['cores'],
+                                                                  'kind': best['kind'], 'sample': best['sample']}
             except Exception as ex:  # noqa
                 line['cpu_baseline'] = {'value': None, 'unit': 'edges/s', 'cores': 0, 'kind': 'failed', 'sample': str(ex)[:300]}
         print(json.dumps(line), flush=True)
+    else:
+        # ================================================================ N > 1: configs[4], frontier-sharded
+        del col_c
+        # secondary: round 1's replicas (every rank its own 1024-seed batches on its own CSR replica, no collective)
+        rep_steps = min(a.steps, 200)
+        my_batches = [(rank + i * world) % n_batches for i in range(rep_steps + a.warmup)]
+        seeds_dev = [perm[b * BATCH:(b + 1) * BATCH].to(dev) for b in my_batches]
+        torch.manual_seed(12345 + rank)
+
+        def step_rep(i):
+            return P.sampler.neighbor_sample(rowptr, col, seeds_dev[i], FANOUT)[0].numel()
+        ms_r, _, edges_r, _, _ = T.run(step_rep, rep_steps, a.warmup)
+        replicas = {'value': edges_r / (ms_r * 1e-3), 'unit': 'edges/s', 'ms_per_step': ms_r / rep_steps, 'steps': rep_steps,
+                    'workload': 'configs[1] on every rank (CSR replicated, disjoint 1024-seed batches, no data-path collective)'}
+        del rowptr, col, seeds_dev
+        torch.cuda.empty_cache()
+        c5 = c5_leg(a, P, abi, T, torch, dev, world, rank, peaks, hbm_peak, peak_src, traffic, dist)
+        if rank == 0:
+            line = {'metric': 'sampled_edges_per_s', 'value': c5['value'], 'unit': 'edges/s', 'n_gpus': world, 'steps': a.steps,
+                    'warmup': a.warmup, 'ms_per_step': c5['ms_per_step'], 'higher_is_better': True, 'scaling': 'strong',
+                    'vs_baseline': None, 'dtype': 'int64', 'data': 'synthetic', 'config': config_dict(world),
+                    'clocks': c5.pop('clocks'), 'e2e': c5.pop('e2e'), 'gpu_launches': c5.pop('gpu_launches'),
+                    'edges_per_step': c5['edges_per_step'], 'parity': c5.pop('parity'), 'roofline': c5.pop('roofline'),
+                    'c5': c5, 'replicas': replicas}
+            print(json.dumps(line), flush=True)
     mon.stop()
     if world > 1:
         dist.destroy_process_group()
+
+
+def c5_leg(a, P, abi, T, torch, dev, world, rank, peaks, hbm_peak, peak_src, traffic, dist):
+    """configs[4]: papers100M-shaped CSR generated on the device (same CUDA generator seed on every rank -> identical
+    replicas), one 65,536-seed batch per step.  world == 1: the single-GPU op.  world > 1: the frontier-sharded op, gated
+    on being bit-identical to the single-GPU op on every rank, with the single-GPU time measured beside it."""
+    from graphs import lognormal_csr
+    t0 = time.time()
+    rowptr, col = lognormal_csr(C5_NODES, C5_EDGES, seed=1, device=dev)
+    torch.cuda.synchronize()
+    gen_s = time.time() - t0
+    steps = min(a.steps, 100)
+    perm = torch.randperm(C5_NODES, generator=torch.Generator().manual_seed(2))
+    n_b = C5_NODES // C5_BATCH
+    seeds_host = [perm[(i % n_b) * C5_BATCH:((i % n_b) + 1) * C5_BATCH].clone().pin_memory() for i in range(steps + a.warmup + 8)]
+    seeds_dev = [s.to(dev) for s in seeds_host]
+    del perm
+
+    def single(i):
+        return P.sampler.neighbor_sample(rowptr, col, seeds_dev[i], FANOUT)
+
+    def sharded(i):
+        return P.sampler.dist_neighbor_sample(rowptr, col, seeds_dev[i], FANOUT)
+    op = single if world == 1 else sharded
+    out = {'graph_gen_s': gen_s, 'steps': steps}
+    if world > 1:
+        # gate: the sharded result equals the single-GPU result (which tests/test_config_parity.py pins to the reference at
+        # this size) — same generator state, every tensor and count, on every rank
+        torch.manual_seed(4321)
+        o1 = [single(i) for i in (0, 1)]
+        s1 = torch.get_rng_state()
+        torch.manual_seed(4321)
+        oN = [sharded(i) for i in (0, 1)]
+        same = all(torch.equal(x, y) for p, q in zip(o1, oN) for x, y in zip(p[:4], q[:4])) and \
+            all(p[4] == q[4] and p[5] == q[5] for p, q in zip(o1, oN)) and bool(torch.equal(s1, torch.get_rng_state()))
+        flag = torch.tensor([1 if same else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        out['parity'] = {'c5_sharded_equals_single_gpu_on_every_rank': bool(int(flag[0])), 'calls': 2, 'edges': int(sum(o[0].numel() for o in oN)),
+                         'pass': bool(int(flag[0])), 'note': 'the single-GPU op is pinned to the reference at this size by tests/test_config_parity.py'}
+        del o1, oN
+        if not out['parity']['pass']:
+            if rank == 0:
+                print(json.dumps({'metric': 'sampled_edges_per_s', 'value': None, 'parity': out['parity'],
+                                  'error': 'parity gate failed: nothing was timed'}), flush=True)
+            sys.exit(1)
+    torch.manual_seed(999)
+    ms, edges, _, launches, clocks = T.run(lambda i: op(i)[0].numel(), steps, a.warmup)
+    out.update({'value': edges / (ms * 1e-3), 'unit': 'edges/s', 'ms_per_step': ms / steps, 'edges_per_step': edges / steps,
+                'clocks': clocks, 'gpu_launches': launches})
+    # e2e: seeds from pinned host memory, the full result back to pinned host memory on every rank
+    cap = C5_BATCH * (FANOUT[0] + FANOUT[0] * FANOUT[1])
+    copier = HostCopier(torch, dev, [cap, cap, cap + C5_BATCH, cap], n_slots=2)
+
+    def step_e2e(i):
+        s = seeds_host[i].to(dev, non_blocking=True)
+        o = (P.sampler.neighbor_sample(rowptr, col, s, FANOUT) if world == 1 else P.sampler.dist_neighbor_sample(rowptr, col, s, FANOUT))[:4]
+        copier.submit(o)
+        return o[0].numel()
+    e_steps = min(steps, 20)
+    b0 = copier.bytes
+    ms_e, edges_e, _, _, _ = T.run(step_e2e, e_steps, 3, finish=copier.drain)
+    out['e2e'] = {'value': edges_e / (ms_e * 1e-3), 'unit': 'edges/s', 'h2d_bytes_per_step': C5_BATCH * 8,
+                  'd2h_bytes_per_step': int((copier.bytes - b0) / (e_steps + 3)), 'ms_per_step': ms_e / e_steps, 'steps': e_steps,
+                  'how': 'pinned seeds H2D + 4 result tensors D2H (pinned) every step on every rank; copies on a copy stream'}
+    copier.close()
+    if rank == 0 or world == 1:
+        pass
+    # roofline of the dominant kernel of the throughput schedule (rank 0's launches)
+    if rank == 0:
+        rf = sampler_roofline(abi, lambda i: op(i)[0].numel(), a.warmup, min(10, steps), torch, peaks, hbm_peak, peak_src, None)
+        rf['kernel'] = {'k_sample': 'k_v2_sample', 'k_mark': 'k_v2_mark', 'k_assign': 'k_v2_assign'}.get(rf['kernel'], rf['kernel'])
+        rf['traffic'] = traffic.get(rf['kernel'])
+        if world > 1:
+            rf['note'] = 'per-launch bytes count all edges of the pass (every rank streams all of them); the draws and table atomics are 1/N of that'
+        out['roofline'] = rf
+    elif world > 1:
+        for i in range(a.warmup, a.warmup + min(10, steps)):   # keep the collective in step with rank 0's profiling calls
+            op(i)
+    if world > 1:
+        # the same batches on ONE GPU, measured on every rank at once (they do not interact), for the speed-up
+        torch.manual_seed(999)
+        ms1, ed1, _, _, _ = T.run(lambda i: single(i)[0].numel(), min(steps, 20), 3)
+        out['single_gpu_edges_per_s'] = ed1 / (ms1 * 1e-3)
+        out['single_gpu_ms_per_step'] = ms1 / min(steps, 20)
+        out['speedup_vs_1gpu'] = out['value'] / out['single_gpu_edges_per_s']
+        out['strong_scaling_efficiency'] = out['speedup_vs_1gpu'] / world
+    del rowptr, col
+    return out
 
 
 if __name__ == '__main__':

@@ -56,13 +56,45 @@ def _worker(args):
     return edges, time.perf_counter() - t0
 
 
+def papers_shaped_csr(n: int, e: int):
+    """Same recipe as tests/graphs.py lognormal_csr (log-normal degrees scaled to sum e, uniform targets), with the 12.9 GB
+    of targets drawn in parallel chunks (one CPU generator per chunk): a timing workload of BASELINE configs[4]'s shape —
+    not bit-identical to the device-generated graph of our arm, which no CPU generator can reproduce."""
+    from concurrent.futures import ThreadPoolExecutor
+    g = torch.Generator().manual_seed(1)
+    w = torch.empty(n, dtype=torch.float64).log_normal_(3.0, 1.2, generator=g)
+    deg = torch.floor(w * (e / w.sum())).to(torch.int64)
+    del w
+    rem = int(e - int(deg.sum()))
+    if rem > 0:
+        deg[:rem] += 1
+    rowptr = torch.zeros(n + 1, dtype=torch.int64)
+    torch.cumsum(deg, 0, out=rowptr[1:])
+    del deg
+    col = torch.empty(e, dtype=torch.int64)
+    chunk = 1 << 25
+
+    def fill(i):
+        gi = torch.Generator().manual_seed(1000 + i)
+        lo = i * chunk
+        col[lo:min(lo + chunk, e)].random_(0, n, generator=gi)
+    with ThreadPoolExecutor(max_workers=min(32, os.cpu_count() or 1)) as ex:
+        list(ex.map(fill, range((e + chunk - 1) // chunk)))
+    return rowptr, col
+
+
 def bench_sampler(workers: int, calls: int, graph: str, batch: int, nn):
     from graphs import lognormal_csr
     if graph == 'products':
         n, e = 2_449_029, 123_718_280
+    elif graph == 'papers':
+        n, e = 111_059_956, 1_615_685_872
     else:
         n, e = 200_000, 10_000_000
-    rowptr, col = lognormal_csr(n, e, seed=1)
+    if graph == 'papers':
+        rowptr, col = papers_shaped_csr(n, e)
+    else:
+        rowptr, col = lognormal_csr(n, e, seed=1)
     perm = torch.randperm(n, generator=torch.Generator().manual_seed(2))
     rowptr.share_memory_(); col.share_memory_(); perm.share_memory_()
     jobs = [(w, rowptr, col, perm, batch, nn, calls, workers) for w in range(workers)]

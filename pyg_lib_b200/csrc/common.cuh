@@ -75,6 +75,21 @@ struct DevBuf {
   T* as() const { return reinterpret_cast<T*>(p); }
 };
 
+// Stream-ordered scratch that is returned to the pool on every exit path (the PYGB_* macros return early on errors).
+struct AsyncScratch {
+  void* p = nullptr;
+  cudaStream_t st = nullptr;
+  int alloc(size_t bytes, cudaStream_t stream) {
+    st = stream;
+    PYGB_CUDA(cudaMallocAsync(&p, bytes, stream));
+    return PYGB200_OK;
+  }
+  ~AsyncScratch() { if (p) cudaFreeAsync(p, st); }
+  AsyncScratch() = default;
+  AsyncScratch(const AsyncScratch&) = delete;
+  AsyncScratch& operator=(const AsyncScratch&) = delete;
+};
+
 __host__ __device__ inline i64 ceil_div(i64 a, i64 b) { return (a + b - 1) / b; }
 
 }  // namespace pygb200

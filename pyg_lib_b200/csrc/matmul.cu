@@ -30,6 +30,34 @@ bool wgrad_tcgen05_supported(i64 N, i64 K, i64 M, i64 B, int dtype, const void* 
 int segment_matmul_tf32(const void* x, const i64* ptr_dev, const void* w, const void* bias, void* out, i64 N, i64 K, i64 M,
                         i64 B, cudaStream_t st);
 bool tf32_supported(i64 N, i64 K, i64 M, i64 B, const void* x, const void* w, const void* out);
+// matmul_grouped_tc.cu: general tensor-core grouped GEMM (any K / M multiple of 8, transposed views, many problems)
+bool grouped_tc_supported(const pygb200_gemm_problem* ps, i64 count, int dtype);
+int grouped_matmul_tc(const pygb200_gemm_problem* ps, i64 count, int dtype, cudaStream_t st);
+bool segment_tc_general_supported(i64 N, i64 K, i64 M, i64 B, int dtype, const void* x, const void* w, const void* out);
+int segment_matmul_tc_general(const void* x, const i64* ptr_dev, const void* w, const void* bias, void* out, i64 N, i64 K, i64 M,
+                              i64 B, int dtype, cudaStream_t st);
+
+// "invalid ptr" flag of the segment kernels: one int in pinned, mapped, portable host memory.  The kernels validate
+// `ptr` while they read it (ptr[0] == 0, non-decreasing, ptr[B] == N — what the reference's split_with_sizes checks on
+// the host after its D2H copy, matmul_kernel.cu:307) and raise the flag instead of touching memory; the NEXT matmul
+// call on this process reports it (like CUDA's own asynchronous errors), so a device-resident ptr still costs no sync.
+static int* g_mm_err_host = nullptr;
+static int* g_mm_err_dev = nullptr;
+int* mm_error_flag_dev() {
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    if (cudaHostAlloc((void**)&g_mm_err_host, sizeof(int), cudaHostAllocMapped | cudaHostAllocPortable) == cudaSuccess) {
+      *g_mm_err_host = 0;
+      if (cudaHostGetDevicePointer((void**)&g_mm_err_dev, g_mm_err_host, 0) != cudaSuccess) g_mm_err_dev = nullptr;
+    }
+  }
+  return g_mm_err_dev;
+}
+static bool mm_take_async_error() {
+  if (g_mm_err_host && *reinterpret_cast<volatile int*>(g_mm_err_host)) { *g_mm_err_host = 0; return true; }
+  return false;
+}
 
 namespace {
 
@@ -65,10 +93,18 @@ __host__ __device__ inline i64 work_items(i64 n, i64 m, i64 k, i64 kchunk) {
 //   mode 1: wgrad     dW[b] = X_b^T @ dY_b                      (n=K, k=len, m=M), split over K chunks
 __global__ void k_build_segments(Problem* probs, i64* total_tiles, const i64* __restrict__ ptr, const char* x,
                                  const char* w, const char* bias, char* out, float* acc, i64 K, i64 M, i64 B, int esize,
-                                 int mode) {
+                                 int mode, i64 N, int* err) {
   __shared__ i64 s_carry;
   __shared__ i64 s_w[32];
   if (threadIdx.x == 0) s_carry = 0;
+  {   // a ptr that is not a segment pointer over [0, N] leaves the launch without work and raises the flag
+    int bad = 0;
+    for (i64 b = threadIdx.x; b < B; b += blockDim.x) bad |= (ptr[b + 1] < ptr[b]) | (b == 0 && ptr[0] != 0) | (b == B - 1 && ptr[B] != N);
+    if (__syncthreads_or(bad)) {
+      if (threadIdx.x == 0) { *total_tiles = 0; if (err) *err = 1; }
+      return;
+    }
+  }
   __syncthreads();
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   for (i64 base = 0; base < B; base += blockDim.x) {
@@ -264,18 +300,19 @@ int segment_generic(const void* x, const i64* ptr_dev, const void* w, const void
                     i64 B, int dtype, int mode, cudaStream_t st) {
   if (B == 0) return PYGB200_OK;
   keep_pool_memory();
-  char* scratch = nullptr;
   const size_t prob_bytes = (((size_t)B * sizeof(Problem) + 16) + 255) & ~(size_t)255;
   // weight gradient: fp32 accumulators for segments that are split over K chunks
   const bool split = mode == 1 && N > WGRAD_KCHUNK;
   const size_t acc_bytes = split ? (size_t)B * K * M * sizeof(float) : 0;
-  PYGB_CUDA(cudaMallocAsync((void**)&scratch, prob_bytes + acc_bytes, st));
+  AsyncScratch sc;   // (freed on every return path)
+  if (int e = sc.alloc(prob_bytes + acc_bytes, st)) return e;
+  char* scratch = (char*)sc.p;
   Problem* probs = (Problem*)(scratch + 16);
   i64* total = (i64*)scratch;
   float* acc = split ? (float*)(scratch + prob_bytes) : nullptr;
   if (split) PYGB_CUDA(cudaMemsetAsync(acc, 0, acc_bytes, st));
   k_build_segments<<<1, 1024, 0, st>>>(probs, total, ptr_dev, (const char*)x, (const char*)w, (const char*)bias,
-                                       (char*)out, acc, K, M, B, esize_of(dtype), mode);
+                                       (char*)out, acc, K, M, B, esize_of(dtype), mode, N, mm_error_flag_dev());
   PYGB_LAUNCH_CHECK();
   const i64 bound = mode == 0 ? (ceil_div(N, (i64)BM) + B) * ceil_div(M, (i64)BN)
                               : (ceil_div(N, WGRAD_KCHUNK) + B) * ceil_div(K, (i64)BM) * ceil_div(M, (i64)BN);
@@ -290,7 +327,6 @@ int segment_generic(const void* x, const i64* ptr_dev, const void* w, const void
     count_launch();
     if (cudaGetLastError() != cudaSuccess) rc = PYGB200_ERR_CUDA;
   }
-  cudaFreeAsync(scratch, st);
   return rc;
 }
 
@@ -306,18 +342,27 @@ extern "C" int pygb200_segment_matmul(const void* x, const int64_t* ptr_dev, con
   PYGB_CHECK(dtype == PYGB200_F32 || dtype == PYGB200_BF16 || dtype == PYGB200_F16, PYGB200_ERR_ARG,
              "segment_matmul: dtype must be f32, bf16 or f16");
   if (N == 0 || M == 0 || B == 0) return PYGB200_OK;
-  PYGB_CHECK(x && ptr_dev && w && out, PYGB200_ERR_ARG, "segment_matmul: null pointer");
+  PYGB_CHECK(ptr_dev && out && (K == 0 || (x && w)), PYGB200_ERR_ARG, "segment_matmul: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
-  if (K == 0) {
-    PYGB_CHECK(bias == nullptr, PYGB200_ERR_UNSUPPORTED, "segment_matmul: K == 0 with bias");
+  mm_error_flag_dev();
+  PYGB_CHECK(!mm_take_async_error(), PYGB200_ERR_ARG,
+             "segment_matmul: an EARLIER segment_matmul / wgrad call received an invalid ptr (it must start at 0, be non-decreasing "
+             "and end at the number of rows); that call's output is undefined");
+  if (K == 0 && bias == nullptr) {
     PYGB_CUDA(cudaMemsetAsync(out, 0, (size_t)N * M * (dtype == PYGB200_F32 ? 4 : 2), st));
     return PYGB200_OK;
   }
+  if (K == 0)   // empty contraction: every row of segment b is bias[b] (the generic kernel runs zero K steps and adds the bias)
+    return segment_generic(x, (const i64*)ptr_dev, w, bias, out, N, K, M, B, dtype, 0, st);
   if (!(flags & PYGB200_MM_FORCE_SIMT) && tcgen05_supported(N, K, M, B, dtype, x, w, out))
     return segment_matmul_tcgen05(x, (const i64*)ptr_dev, w, bias, out, N, K, M, B, dtype, st);
   if (!(flags & PYGB200_MM_FORCE_SIMT) && (flags & PYGB200_MM_ALLOW_TF32) && dtype == PYGB200_F32 &&
       tf32_supported(N, K, M, B, x, w, out))
     return segment_matmul_tf32(x, (const i64*)ptr_dev, w, bias, out, N, K, M, B, st);
+  if (!(flags & PYGB200_MM_FORCE_SIMT) && segment_tc_general_supported(N, K, M, B, dtype, x, w, out)) {
+    keep_pool_memory();
+    return segment_matmul_tc_general(x, (const i64*)ptr_dev, w, bias, out, N, K, M, B, dtype, st);
+  }
   return segment_generic(x, (const i64*)ptr_dev, w, bias, out, N, K, M, B, dtype, 0, st);
 }
 
@@ -328,6 +373,9 @@ extern "C" int pygb200_segment_matmul_wgrad(const void* x, const int64_t* ptr_de
              "segment_matmul_wgrad: dtype must be f32, bf16 or f16");
   if (K == 0 || M == 0 || B == 0) return PYGB200_OK;
   PYGB_CHECK(ptr_dev && dw && (N == 0 || (x && dy)), PYGB200_ERR_ARG, "segment_matmul_wgrad: null pointer");
+  mm_error_flag_dev();
+  PYGB_CHECK(!mm_take_async_error(), PYGB200_ERR_ARG,
+             "segment_matmul_wgrad: an EARLIER segment_matmul / wgrad call received an invalid ptr; that call's output is undefined");
   keep_pool_memory();
   if (!(flags & PYGB200_MM_FORCE_SIMT) && N > 0 && wgrad_tcgen05_supported(N, K, M, B, dtype, x, dy, dw))
     return segment_wgrad_tcgen05(x, (const i64*)ptr_dev, dy, dw, N, K, M, B, dtype, (cudaStream_t)stream);
@@ -337,12 +385,18 @@ extern "C" int pygb200_segment_matmul_wgrad(const void* x, const int64_t* ptr_de
 
 extern "C" int pygb200_grouped_matmul(const pygb200_gemm_problem* ps, int64_t count, int dtype, unsigned flags,
                                       void* stream) {
-  (void)flags;
   PYGB_CHECK(count >= 0 && (ps || count == 0), PYGB200_ERR_ARG, "grouped_matmul: bad arguments");
   PYGB_CHECK(dtype == PYGB200_F32 || dtype == PYGB200_BF16 || dtype == PYGB200_F16, PYGB200_ERR_ARG,
              "grouped_matmul: dtype must be f32, bf16 or f16");
   if (count == 0) return PYGB200_OK;
   cudaStream_t st = (cudaStream_t)stream;
+  // bf16 / fp16 problems whose operands satisfy the TMA alignment rules run on the tensor cores (the reference runs
+  // grouped_matmul through the same TensorOp grouped GEMM as segment_matmul, matmul_kernel.cu:289-302)
+  if (!(flags & PYGB200_MM_FORCE_SIMT) && grouped_tc_supported(ps, count, dtype)) {
+    for (i64 i = 0; i < count; ++i) PYGB_CHECK(ps[i].n >= 0 && ps[i].k >= 0 && ps[i].m >= 0, PYGB200_ERR_ARG, "grouped_matmul: negative size");
+    keep_pool_memory();
+    return grouped_matmul_tc(ps, count, dtype, st);
+  }
   std::vector<Problem> h((size_t)count);
   i64 tiles = 0;
   for (i64 i = 0; i < count; ++i) {
@@ -361,13 +415,12 @@ extern "C" int pygb200_grouped_matmul(const pygb200_gemm_problem* ps, int64_t co
   }
   if (tiles == 0) return PYGB200_OK;
   keep_pool_memory();
-  char* scratch = nullptr;
   const size_t bytes = (size_t)count * sizeof(Problem) + 16;
-  PYGB_CUDA(cudaMallocAsync((void**)&scratch, bytes, st));
+  AsyncScratch sc;
+  if (int e = sc.alloc(bytes, st)) return e;
+  char* scratch = (char*)sc.p;
   // pageable source: the copy is staged by the driver before the call returns, so `h` may die here
   PYGB_CUDA(cudaMemcpyAsync(scratch, &tiles, 8, cudaMemcpyHostToDevice, st));
   PYGB_CUDA(cudaMemcpyAsync(scratch + 16, h.data(), (size_t)count * sizeof(Problem), cudaMemcpyHostToDevice, st));
-  int rc = launch_grouped((const Problem*)(scratch + 16), count, (const i64*)scratch, tiles, dtype, st);
-  cudaFreeAsync(scratch, st);
-  return rc;
+  return launch_grouped((const Problem*)(scratch + 16), count, (const i64*)scratch, tiles, dtype, st);
 }

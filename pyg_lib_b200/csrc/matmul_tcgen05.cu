@@ -28,107 +28,14 @@
 #include "common.cuh"
 
 namespace pygb200 {
+int* mm_error_flag_dev();   // matmul.cu: device address of the mapped "invalid ptr" flag
 namespace {
 
 constexpr int TM = 128;            // rows per tile == UMMA M == TMEM lanes
 constexpr int MAX_SEG = 1024;      // segments handled by the in-kernel tile prefix (else generic path)
 constexpr int NTHREADS = 256;
 
-// ---------------------------------------------------------------------------------- PTX helpers
-__device__ __forceinline__ u32 smem_u32(const void* p) { return (u32)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(u32 bar, u32 count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(u32 bar, u32 bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(u32 bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(u32 bar, u32 parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra DONE;\n"
-      "bra WAIT_LOOP;\n"
-      "DONE:\n"
-      "}\n" ::"r"(bar), "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(u32 dst, const CUtensorMap* map, int c0, int c1, u32 bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
-      "l"(map), "r"(c0), "r"(c1), "r"(bar)
-      : "memory");
-}
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, u32 src, int c0, int c1) {
-  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src), "r"(c0),
-               "r"(c1)
-               : "memory");
-}
-__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(u32 bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_mma_f16(u32 tmem_d, u64 adesc, u64 bdesc, u32 idesc, u32 accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void tc_ld_32x32(u32 taddr, u32* v) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp SmemDescriptor bit layout):
-// [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version=1 | [61,64) layout (2 = SWIZZLE_128B)
-__device__ __forceinline__ u64 make_desc(u32 saddr, u32 lbo_bytes, u32 sbo_bytes) {
-  u64 d = 0;
-  d |= (u64)((saddr & 0x3ffffu) >> 4);
-  d |= (u64)((lbo_bytes >> 4) & 0x3fffu) << 16;
-  d |= (u64)((sbo_bytes >> 4) & 0x3fffu) << 32;
-  d |= (u64)1 << 46;
-  d |= (u64)2 << 61;
-  return d;
-}
-
-template <bool BF16>
-__device__ __forceinline__ u32 pack2(float a, float b) {
-  if (BF16) {
-    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-    return *reinterpret_cast<u32*>(&h);
-  } else {
-    __half2 h = __floats2half2_rn(a, b);
-    return *reinterpret_cast<u32*>(&h);
-  }
-}
-template <bool BF16>
-__device__ __forceinline__ float ld_bias(const void* bias, i64 idx) {
-  if (BF16) return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(bias)[idx]);
-  return __half2float(reinterpret_cast<const __half*>(bias)[idx]);
-}
+#include "tcgen05_ptx.cuh"
 
 struct SegParams {
   const i64* ptr;
@@ -137,6 +44,7 @@ struct SegParams {
   i64 N;
   int K, M, B;
   int G;              // tiles per scheduling chunk (chunks are dealt round-robin to CTAs); 0 = one chunk per CTA
+  int* err;           // mapped host flag: raised when `ptr` is not a valid segment pointer
 };
 
 // Tile order of one CTA: chunks of G consecutive tiles, chunk c -> CTA c % gridDim.  All CTAs therefore
@@ -157,6 +65,45 @@ struct TileIter {
     if (++t >= end) { chunk += grid; const long long n = (long long)chunk * G; t = n < total ? (int)n : total; end = min(total, t + G); }
   }
 };
+
+// Prologue shared by the three segment kernels: tile_pre[b] = number of 128-row tiles of the segments before b
+// (tile_pre[B] = total), from `ptr` on the device — the reference does size_from_ptr(ptr).cpu() here
+// (matmul_kernel.cu:307).  All NTHREADS threads; a later __syncthreads() of the caller publishes the result.  `ptr` is
+// validated on the way (ptr[0] == 0, non-decreasing, ptr[B] == N — what the reference's split_with_sizes enforces on the
+// host): a bad ptr leaves the kernel without work and raises the mapped flag `err`, which the next matmul call reports.
+__device__ __forceinline__ void build_tile_prefix(const i64* __restrict__ ptr, int B, i64 N, int* tile_pre, int* err) {
+  __shared__ int s_part[NTHREADS];
+  const int per = (B + NTHREADS - 1) / NTHREADS;
+  int loc = 0, bad = 0;
+  for (int j = 0; j < per; ++j) {
+    const int b = threadIdx.x * per + j;
+    if (b < B) {
+      const i64 lo = ptr[b], hi = ptr[b + 1];
+      bad |= (hi < lo) | (b == 0 && lo != 0) | (b == B - 1 && hi != N);
+      loc += (int)((hi - lo + TM - 1) / TM);
+    }
+  }
+  s_part[threadIdx.x] = loc;
+  if (__syncthreads_or(bad)) {   // (also the barrier that publishes s_part)
+    for (int b = threadIdx.x; b <= B; b += NTHREADS) tile_pre[b] = 0;
+    if (threadIdx.x == 0 && blockIdx.x == 0 && err) *err = 1;
+    return;
+  }
+  int pre = 0;
+  for (int t = 0; t < (int)threadIdx.x; ++t) pre += s_part[t];
+  for (int j = 0; j < per; ++j) {
+    const int b = threadIdx.x * per + j;
+    if (b < B) {
+      tile_pre[b] = pre;
+      pre += (int)((ptr[b + 1] - ptr[b] + TM - 1) / TM);
+    }
+  }
+  if (threadIdx.x == 0) {
+    int tot = 0;
+    for (int t = 0; t < NTHREADS; ++t) tot += s_part[t];
+    tile_pre[B] = tot;
+  }
+}
 
 // dynamic smem layout (1024-aligned): A ring | W double buffer | out staging | barriers | tile prefix
 template <bool BF16, int A_STAGES, int W_BUFS, int O_BUFS>
@@ -187,32 +134,7 @@ k_segment_matmul_tc(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   const u32 tmem_cols = (2 * M <= 32) ? 32 : (2 * M <= 64) ? 64 : (2 * M <= 128) ? 128 : (2 * M <= 256) ? 256 : 512;
 
   // ---- prologue: tile prefix over segments (all threads), barriers, TMEM
-  {
-    // serial-in-chunks prefix: B <= MAX_SEG, 256 threads
-    __shared__ int s_part[NTHREADS];
-    const int per = (P.B + NTHREADS - 1) / NTHREADS;
-    int loc = 0;
-    for (int j = 0; j < per; ++j) {
-      const int b = threadIdx.x * per + j;
-      if (b < P.B) loc += (int)((P.ptr[b + 1] - P.ptr[b] + TM - 1) / TM);
-    }
-    s_part[threadIdx.x] = loc;
-    __syncthreads();
-    int pre = 0;
-    for (int t = 0; t < (int)threadIdx.x; ++t) pre += s_part[t];
-    for (int j = 0; j < per; ++j) {
-      const int b = threadIdx.x * per + j;
-      if (b < P.B) {
-        tile_pre[b] = pre;
-        pre += (int)((P.ptr[b + 1] - P.ptr[b] + TM - 1) / TM);
-      }
-    }
-    if (threadIdx.x == 0) {
-      int tot = 0;
-      for (int t = 0; t < NTHREADS; ++t) tot += s_part[t];
-      tile_pre[P.B] = tot;
-    }
-  }
+  build_tile_prefix(P.ptr, P.B, P.N, tile_pre, P.err);
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < A_STAGES; ++s) { mbar_init(A_FULL(s), 1); mbar_init(A_EMPTY(s), 1); }
     for (int s = 0; s < 2; ++s) {
@@ -506,6 +428,7 @@ struct WgradParams {
   float* acc;    // [B, K, M] fp32, zero-initialised
   i64 N;
   int K, M, B;
+  int* err;
 };
 
 template <bool BF16>
@@ -530,31 +453,7 @@ k_segment_wgrad_tc(const __grid_constant__ CUtensorMap map_x, const __grid_const
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const u32 tmem_cols = (2 * M <= 32) ? 32 : (2 * M <= 64) ? 64 : (2 * M <= 128) ? 128 : (2 * M <= 256) ? 256 : 512;
-  {
-    __shared__ int s_part[NTHREADS];
-    const int per = (P.B + NTHREADS - 1) / NTHREADS;
-    int loc = 0;
-    for (int j = 0; j < per; ++j) {
-      const int b = threadIdx.x * per + j;
-      if (b < P.B) loc += (int)((P.ptr[b + 1] - P.ptr[b] + TM - 1) / TM);
-    }
-    s_part[threadIdx.x] = loc;
-    __syncthreads();
-    int pre = 0;
-    for (int t = 0; t < (int)threadIdx.x; ++t) pre += s_part[t];
-    for (int j = 0; j < per; ++j) {
-      const int b = threadIdx.x * per + j;
-      if (b < P.B) {
-        tile_pre[b] = pre;
-        pre += (int)((P.ptr[b + 1] - P.ptr[b] + TM - 1) / TM);
-      }
-    }
-    if (threadIdx.x == 0) {
-      int tot = 0;
-      for (int t = 0; t < NTHREADS; ++t) tot += s_part[t];
-      tile_pre[P.B] = tot;
-    }
-  }
+  build_tile_prefix(P.ptr, P.B, P.N, tile_pre, P.err);
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < WG_STAGES; ++s) { mbar_init(FULL(s), 1); mbar_init(EMPTY(s), 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(T_FULL(s), 1); mbar_init(T_EMPTY(s), 128); }
@@ -725,7 +624,7 @@ int segment_matmul_tcgen05(const void* x, const i64* ptr_dev, const void* w, con
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const i64 max_tiles = N / TM + B;
   SegParams P;
-  P.ptr = ptr_dev; P.bias = bias; P.out = out; P.N = N; P.K = (int)K; P.M = (int)M; P.B = (int)B;
+  P.ptr = ptr_dev; P.bias = bias; P.out = out; P.N = N; P.K = (int)K; P.M = (int)M; P.B = (int)B; P.err = mm_error_flag_dev();
   {
     // Scheduling chunk: ~4 consecutive tiles per chunk, chunks dealt round-robin, sized so that every CTA
     // gets (nearly) the same whole number of chunks.  Measured: 96 us vs 103-110 us for one contiguous
@@ -779,6 +678,7 @@ struct Tf32Params {
   float* out;
   i64 N;
   int K, M, B, G;
+  int* err;
 };
 
 __global__ void __launch_bounds__(NTHREADS, 1)
@@ -803,31 +703,7 @@ k_segment_matmul_tf32(const __grid_constant__ CUtensorMap map_a, const __grid_co
   int* tile_pre = reinterpret_cast<int*>(tmem_slot + 2);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const u32 tmem_cols = (2 * M <= 32) ? 32 : (2 * M <= 64) ? 64 : (2 * M <= 128) ? 128 : (2 * M <= 256) ? 256 : 512;
-  {
-    __shared__ int s_part[NTHREADS];
-    const int per = (P.B + NTHREADS - 1) / NTHREADS;
-    int loc = 0;
-    for (int j = 0; j < per; ++j) {
-      const int b = threadIdx.x * per + j;
-      if (b < P.B) loc += (int)((P.ptr[b + 1] - P.ptr[b] + TM - 1) / TM);
-    }
-    s_part[threadIdx.x] = loc;
-    __syncthreads();
-    int pre = 0;
-    for (int t = 0; t < (int)threadIdx.x; ++t) pre += s_part[t];
-    for (int j = 0; j < per; ++j) {
-      const int b = threadIdx.x * per + j;
-      if (b < P.B) {
-        tile_pre[b] = pre;
-        pre += (int)((P.ptr[b + 1] - P.ptr[b] + TM - 1) / TM);
-      }
-    }
-    if (threadIdx.x == 0) {
-      int tot = 0;
-      for (int t = 0; t < NTHREADS; ++t) tot += s_part[t];
-      tile_pre[P.B] = tot;
-    }
-  }
+  build_tile_prefix(P.ptr, P.B, P.N, tile_pre, P.err);
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < TF_A_STAGES; ++s) { mbar_init(A_FULL(s), 1); mbar_init(A_EMPTY(s), 1); }
     mbar_init(W_FULL, 1); mbar_init(W_EMPTY, 1);
@@ -1043,8 +919,9 @@ bool tf32_supported(i64 N, i64 K, i64 M, i64 B, const void* x, const void* w, co
 
 int segment_matmul_tf32(const void* x, const i64* ptr_dev, const void* w, const void* bias, void* out, i64 N, i64 K, i64 M,
                         i64 B, cudaStream_t st) {
-  float* wt = nullptr;
-  PYGB_CUDA(cudaMallocAsync((void**)&wt, (size_t)B * K * M * 4, st));
+  AsyncScratch sc;   // (freed on every return path)
+  if (int e = sc.alloc((size_t)B * K * M * 4, st)) return e;
+  float* wt = (float*)sc.p;
   k_transpose_w_f32<<<dim3((unsigned)((M + 31) / 32), (unsigned)((K + 31) / 32), (unsigned)B), dim3(32, 8), 0, st>>>(
       (const float*)w, wt, (int)K, (int)M);
   PYGB_LAUNCH_CHECK();
@@ -1057,7 +934,7 @@ int segment_matmul_tf32(const void* x, const i64* ptr_dev, const void* w, const 
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const i64 max_tiles = N / TM + B;
   Tf32Params P;
-  P.ptr = ptr_dev; P.bias = (const float*)bias; P.out = (float*)out; P.N = N; P.K = (int)K; P.M = (int)M; P.B = (int)B;
+  P.ptr = ptr_dev; P.bias = (const float*)bias; P.out = (float*)out; P.N = N; P.K = (int)K; P.M = (int)M; P.B = (int)B; P.err = mm_error_flag_dev();
   {
     const i64 per_cta = (max_tiles + sms - 1) / sms;
     const i64 rounds = std::max<i64>(1, (per_cta + 2) / 4);
@@ -1070,7 +947,6 @@ int segment_matmul_tf32(const void* x, const i64* ptr_dev, const void* w, const 
   k_segment_matmul_tf32<<<grid, NTHREADS, smem, st>>>(ma, mw, mo, P);
   prof_end(tk, "segment_matmul", st, N);
   PYGB_LAUNCH_CHECK();
-  cudaFreeAsync(wt, st);
   return PYGB200_OK;
 }
 
@@ -1090,12 +966,13 @@ int segment_wgrad_tcgen05(const void* x, const i64* ptr_dev, const void* dy, voi
   CUtensorMap mx, my;
   if (int e = make_map(&mx, x, N, K, TM, bf16)) return e;
   if (int e = make_map(&my, dy, N, M, TM, bf16)) return e;
-  float* acc = nullptr;
   const size_t acc_bytes = (size_t)B * K * M * sizeof(float);
-  PYGB_CUDA(cudaMallocAsync((void**)&acc, acc_bytes, st));
+  AsyncScratch sc;   // (freed on every return path)
+  if (int e = sc.alloc(acc_bytes, st)) return e;
+  float* acc = (float*)sc.p;
   PYGB_CUDA(cudaMemsetAsync(acc, 0, acc_bytes, st));
   WgradParams P;
-  P.ptr = ptr_dev; P.acc = acc; P.N = N; P.K = (int)K; P.M = (int)M; P.B = (int)B;
+  P.ptr = ptr_dev; P.acc = acc; P.N = N; P.K = (int)K; P.M = (int)M; P.B = (int)B; P.err = mm_error_flag_dev();
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -1117,7 +994,6 @@ int segment_wgrad_tcgen05(const void* x, const i64* ptr_dev, const void* dy, voi
   if (bf16) k_wgrad_finish<true><<<fg, 256, 0, st>>>(acc, dw, n);
   else k_wgrad_finish<false><<<fg, 256, 0, st>>>(acc, dw, n);
   PYGB_LAUNCH_CHECK();
-  cudaFreeAsync(acc, st);
   return PYGB200_OK;
 }
 

@@ -194,12 +194,18 @@ __global__ void __launch_bounds__(640) k_mt_jump_prestep(u32* __restrict__ raw, 
 
 // CTA p generates raw[b0 + p*S + 624 .. b0 + (p+1)*S + 624), b0 = jump_base - 624 (CTA 0 continues after the
 // pre-step).  The last CTA to finish publishes the new length.
+// The jump itself is ~10 k XORs of history words per thread: the history the polynomial reads (MT_JUMP_HIST words,
+// 85 KB) is staged in shared memory first — read from L2 inside the bit loop, every XOR waited for one L2 round trip
+// (a while(bits) loop is not unrolled, so the loads did not overlap) and a 131 072-word chunk took 2.0 ms, of which the
+// generation proper is ~25 us (ncu launch list, profiles/launches_big_r2.csv).
+constexpr int MT_JUMP_HIST = 19938 + MT_N + 62;   // highest history index read: deg(g) <= 19937, + 623; rounded to 20 624
 template <int KL>
 __global__ void __launch_bounds__(640) k_mt_jump_generate(u32* __restrict__ raw, i64* generated, const i64* jump_base,
                                                            const u32* __restrict__ polys, int S, i64 cap_words,
                                                            unsigned long long* ticket) {
   __shared__ u32 win[MT_WIN];
   __shared__ int s_last;
+  extern __shared__ u32 s_hist[];   // MT_JUMP_HIST words
   const i64 b0 = *jump_base - MT_N;
   const int p = blockIdx.x, P = gridDim.x;
   i64 end_all = b0 + (i64)P * S + MT_N;
@@ -214,14 +220,18 @@ __global__ void __launch_bounds__(640) k_mt_jump_generate(u32* __restrict__ raw,
     if (w0 + MT_N <= end_all) {
       const u32* __restrict__ g = polys + (size_t)(p - 1) * MT_POLY_WORDS;
       const u32* src = raw + b0;
+      for (int i = threadIdx.x; i < MT_JUMP_HIST; i += blockDim.x) s_hist[i] = __ldcg(&src[i]);
+      __syncthreads();
       if (threadIdx.x < MT_N) {
         u32 acc = 0;
+        const u32* h = s_hist + threadIdx.x;
         for (int w = 0; w < MT_POLY_WORDS; ++w) {
-          u32 bits = g[w];
+          u32 bits = __ldg(&g[w]);
+          const u32* hw = h + w * 32;
           while (bits) {
-            const int i = w * 32 + __ffs(bits) - 1;
+            const int i = __ffs(bits) - 1;
             bits &= bits - 1;
-            acc ^= __ldcg(&src[i + threadIdx.x]);
+            acc ^= hw[i];
           }
         }
         raw[w0 + threadIdx.x] = acc;

@@ -208,18 +208,23 @@ __device__ __forceinline__ u64 make_key(i64 node, i64 batch, int disjoint) {
 }
 
 struct Func4 { u32 d[4]; };
+// (entry selected with a chain of selects: a run-time index into d[] would put the struct in local memory)
+template <typename F>
+__device__ __forceinline__ auto sel4(const F& f, unsigned ph) -> decltype(f.d[0] + 0) {
+  return ph == 0 ? f.d[0] : (ph == 1 ? f.d[1] : (ph == 2 ? f.d[2] : f.d[3]));
+}
 // apply a first, then b
 __device__ __forceinline__ Func4 compose(const Func4& a, const Func4& b) {
   Func4 c;
 #pragma unroll
-  for (int p = 0; p < 4; ++p) c.d[p] = a.d[p] + b.d[(p + a.d[p]) & 3];
+  for (int p = 0; p < 4; ++p) c.d[p] = a.d[p] + sel4(b, (p + a.d[p]) & 3u);
   return c;
 }
 struct Func4L { u64 d[4]; };
 __device__ __forceinline__ Func4L composeL(const Func4L& a, const Func4L& b) {
   Func4L c;
 #pragma unroll
-  for (int p = 0; p < 4; ++p) c.d[p] = a.d[p] + b.d[(p + a.d[p]) & 3];
+  for (int p = 0; p < 4; ++p) c.d[p] = a.d[p] + sel4(b, (unsigned)((p + a.d[p]) & 3u));
   return c;
 }
 
@@ -353,12 +358,12 @@ __device__ void scan_frontier_tiles(const PassArgs& a, i64 ntiles) {
     const i64 off0 = c_off, pos0 = c_pos;
     if (t < ntiles) {
       a.tile_off[t] = off0 + pv + ev;
-      a.tile_pos[t] = pos0 + (i64)exf.d[pos0 & 3];
+      a.tile_pos[t] = pos0 + (i64)sel4(exf, (unsigned)(pos0 & 3));
     }
     i64 tv = 0; Func4L tf = {{0, 0, 0, 0}};
     for (int w = 0; w < NT / 32; ++w) { tv += s_sum[w]; tf = composeL(tf, s_fun[w]); }
     __syncthreads();
-    if (threadIdx.x == 0) { c_off = off0 + tv; c_pos = pos0 + (i64)tf.d[pos0 & 3]; }
+    if (threadIdx.x == 0) { c_off = off0 + tv; c_pos = pos0 + (i64)sel4(tf, (unsigned)(pos0 & 3)); }
     __syncthreads();
   }
   if (threadIdx.x == 0) {
@@ -953,8 +958,9 @@ __global__ void __launch_bounds__(NT, SAMPLE_MIN_BLOCKS) k_sample_s(const PassAr
   const int npb = (NT / 32) * per_warp;
   // this group's first node: its record is fetched now, beside the tile aggregates (rec[] is sized for the bound)
   const i64 i_first = (i64)blockIdx.x * npb + (threadIdx.x >> 5) * per_warp + (gi < per_warp ? gi : 0);
-  NodeRec r_first = {};
-  if (i_first < F) r_first = a.rec[i_first];
+  // (a record = two 16-byte loads kept as eight scalars: selecting between whole NodeRec structs put pf[] in local memory)
+  uint4 ra_first = make_uint4(0, 0, 0, 0), rb_first = make_uint4(0, 0, 0, 0);
+  if (i_first < F) { const uint4* rp = reinterpret_cast<const uint4*>(a.rec + i_first); ra_first = rp[0]; rb_first = rp[1]; }
   // ---- every block: exclusive scan of the tile aggregates (edge offsets, RNG positions relative to cur_in)
   u32 E, adv;
   {
@@ -1018,12 +1024,16 @@ __global__ void __launch_bounds__(NT, SAMPLE_MIN_BLOCKS) k_sample_s(const PassAr
   // ---- one group of g lanes per frontier node
   if (gi >= per_warp) return;   // (lanes beyond the last whole group of the warp; no block-wide sync below)
   for (i64 i = i_first; i < F; i += (i64)gridDim.x * npb) {
-    const NodeRec r = i == i_first ? r_first : a.rec[i];
+    uint4 ra = ra_first, rb = rb_first;
+    if (i != i_first) { const uint4* rp = reinterpret_cast<const uint4*>(a.rec + i); ra = rp[0]; rb = rp[1]; }
+    NodeRec r;
+    r.rs = (i64)(((u64)ra.y << 32) | (u64)ra.x); r.deg = ra.z; r.loc_off = ra.w;
+    r.pf[0] = r.pf[1] = r.pf[2] = r.pf[3] = 0;   // (the advance is picked from the scalars below)
     const int tile = (int)(i / NT);
     const i64 tpos = cur_in + s_pos[tile];
     const i64 off = (i64)s_off[tile] + r.loc_off;
     const int ph = (int)(tpos & 3);
-    const u32 pfv = ph == 0 ? r.pf[0] : (ph == 1 ? r.pf[1] : (ph == 2 ? r.pf[2] : r.pf[3]));
+    const u32 pfv = ph == 0 ? rb.x : (ph == 1 ? rb.y : (ph == 2 ? rb.z : rb.w));
     sample_node<idx_t, false>(a, r, off, tpos + pfv, begin + i, pbase, g, gl, gbase, gmask);
   }
   tl_mark(TL_SAMPLE | TL_END);
@@ -1693,8 +1703,10 @@ int mt_request(pygb200_sampler* s, cudaStream_t st, i64 target) {
       i64* jb = s->jump_scratch.as<i64>();
       k_mt_jump_prestep<3><<<1, 640, 0, st>>>(s->raw.as<u32>(), s->gen.as<i64>(), jb, s->raw_cap_words);
       PYGB_LAUNCH_CHECK();
-      k_mt_jump_generate<3><<<P_used, 640, 0, st>>>(s->raw.as<u32>(), s->gen.as<i64>(), jb, s->jump_polys.as<u32>(), s->jump_S,
-                                                   s->raw_cap_words, reinterpret_cast<unsigned long long*>(jb + 1));
+      static const bool smem_ok = cudaFuncSetAttribute(k_mt_jump_generate<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, MT_JUMP_HIST * 4) == cudaSuccess;
+      PYGB_CHECK(smem_ok, PYGB200_ERR_CUDA, "k_mt_jump_generate: cannot reserve shared memory for the jump history");
+      k_mt_jump_generate<3><<<P_used, 640, MT_JUMP_HIST * 4, st>>>(s->raw.as<u32>(), s->gen.as<i64>(), jb, s->jump_polys.as<u32>(), s->jump_S,
+                                                                  s->raw_cap_words, reinterpret_cast<unsigned long long*>(jb + 1));
       PYGB_LAUNCH_CHECK();
       s->mt_requested += (i64)P_used * s->jump_S;
       if (s->mt_requested > s->raw_cap_words - MT_N) { s->mt_requested = s->raw_cap_words - MT_N; break; }
@@ -1766,6 +1778,11 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
                      int64_t* n_nodes_out, int64_t* n_edges_out, cudaStream_t st, const pygb200_shard* shard,
                      const pygb200_temporal* temporal) {
   const bool replace = flags & PYGB200_S_REPLACE, disjoint = flags & PYGB200_S_DISJOINT, idx32 = flags & PYGB200_S_INDEX32;
+  // the output binding is one-shot: it is consumed here, before any check can return early, so that a failed run
+  // never leaves pointers to arrays its caller is about to free
+  const bool bound_armed = s->bound.armed;
+  s->bound.armed = false;
+  s->last_direct = false;
   double ht_last = g_ht.on ? HostTimes::now() : 0;
   auto ht_lap = [&](int seg) { if (g_ht.on) { const double t = HostTimes::now(); g_ht.acc[seg] += t - ht_last; ht_last = t; } };
   i64 total_seeds = 0;
@@ -1868,10 +1885,8 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
   const int XW = p2p ? shard->world : 1, XR = p2p ? shard->rank : 0;
 
   // ---- results straight into the caller's arrays?  (bounded int64 non-disjoint runs only; the binding is one-shot)
-  bool direct = s->bound.armed && !synced && !sharded && !nodedup && !idx32 && !disjoint && (int)s->bound.node.size() == T &&
+  bool direct = bound_armed && !synced && !sharded && !nodedup && !idx32 && !disjoint && (int)s->bound.node.size() == T &&
                 (int)s->bound.row.size() == R;
-  s->bound.armed = false;
-  s->last_direct = false;
   for (int t = 0; t < T && direct; ++t) direct = s->bound.node[t] != nullptr && s->bound.ncap[t] >= node_cap[t];
   for (int r = 0; r < R && direct; ++r)
     direct = s->bound.row[r] != nullptr && s->bound.col[r] != nullptr && s->bound.ecap[r] >= rel_cap[r];

@@ -23,9 +23,19 @@ unsigned mm_flags() {
   return at::globalContext().float32MatmulPrecision() != at::Float32MatmulPrecision::HIGHEST ? PYGB200_MM_ALLOW_TF32 : 0u;
 }
 
-at::Tensor ptr_on_device(const at::Tensor& ptr, const at::Device& dev) {
+// `ptr` must be a segment pointer over the rows of the input: ptr[0] == 0, non-decreasing, ptr[-1] == N (the reference
+// raises through split_with_sizes on the host sizes, matmul_kernel.cu:307-313).  A host ptr is checked here; a device ptr
+// is checked by the kernels while they read it and reported by the next matmul call (no sync on the way).
+at::Tensor ptr_on_device(const at::Tensor& ptr, const at::Device& dev, int64_t N) {
   // int64 only, like the reference ("expected scalar type Long", matmul_kernel.cu:308-309)
   TORCH_CHECK(ptr.scalar_type() == at::kLong, "expected scalar type Long but found ", ptr.scalar_type());
+  if (ptr.device().is_cpu() && ptr.numel() > 0) {
+    const at::Tensor pc = ptr.contiguous();
+    const int64_t* v = pc.data_ptr<int64_t>();
+    bool ok = v[0] == 0 && v[pc.numel() - 1] == N;
+    for (int64_t i = 1; i < pc.numel() && ok; ++i) ok = v[i] >= v[i - 1];
+    TORCH_CHECK(ok, "segment_matmul: 'ptr' must start at 0, be non-decreasing and end at input.size(0) = ", N);
+  }
   return ptr.device() == dev ? ptr.contiguous() : ptr.contiguous().to(dev, /*non_blocking=*/true);
 }
 
@@ -37,7 +47,7 @@ at::Tensor segment_matmul_cuda(const at::Tensor& input, const at::Tensor& ptr, c
   TORCH_CHECK(ptr.numel() == other.size(0) + 1, "segment_matmul: ptr.numel() must equal other.size(0) + 1");
   c10::cuda::CUDAGuard guard(input.device());
   const at::Tensor x = input.contiguous(), w = other.contiguous();
-  const at::Tensor p = ptr_on_device(ptr, input.device());
+  const at::Tensor p = ptr_on_device(ptr, input.device(), input.size(0));
   at::Tensor out = input.new_empty({x.size(0), w.size(2)});
   PYGB_TORCH_CALL(pygb200_segment_matmul(x.data_ptr(), p.data_ptr<int64_t>(), w.data_ptr(), nullptr, out.data_ptr(),
                                          x.size(0), x.size(1), w.size(2), w.size(0), dtype_code(x.scalar_type()),
@@ -56,7 +66,7 @@ at::Tensor segment_matmul_bias_cuda(const at::Tensor& input, const at::Tensor& p
                   bias.size(1) == other.size(2), "segment_matmul_bias: shape mismatch");
   c10::cuda::CUDAGuard guard(input.device());
   const at::Tensor x = input.contiguous(), w = other.contiguous(), b = bias.contiguous();
-  const at::Tensor p = ptr_on_device(ptr, input.device());
+  const at::Tensor p = ptr_on_device(ptr, input.device(), input.size(0));
   at::Tensor out = input.new_empty({x.size(0), w.size(2)});
   PYGB_TORCH_CALL(pygb200_segment_matmul(x.data_ptr(), p.data_ptr<int64_t>(), w.data_ptr(), b.data_ptr(), out.data_ptr(),
                                          x.size(0), x.size(1), w.size(2), w.size(0), dtype_code(x.scalar_type()),
@@ -71,7 +81,7 @@ at::Tensor segment_matmul_wgrad_cuda(const at::Tensor& input, const at::Tensor& 
   TORCH_CHECK(input.scalar_type() == grad_out.scalar_type(), "segment_matmul_wgrad: dtype mismatch");
   c10::cuda::CUDAGuard guard(input.device());
   const at::Tensor x = input.contiguous(), dy = grad_out.contiguous();
-  const at::Tensor p = ptr_on_device(ptr, input.device());
+  const at::Tensor p = ptr_on_device(ptr, input.device(), input.size(0));
   const int64_t B = ptr.numel() - 1;
   at::Tensor dw = input.new_empty({B, x.size(1), dy.size(1)});
   PYGB_TORCH_CALL(pygb200_segment_matmul_wgrad(x.data_ptr(), p.data_ptr<int64_t>(), dy.data_ptr(), dw.data_ptr(),

@@ -9,6 +9,7 @@
 #include <ATen/CPUGeneratorImpl.h>
 
 #include <map>
+#include <memory>
 #include <mutex>
 
 #include <chrono>
@@ -40,18 +41,22 @@ struct OpTimes {
 };
 static OpTimes g_ot;
 
-// one persistent workspace per (device, stream)
-pygb200_sampler* get_sampler(int device, cudaStream_t stream) {
+// one persistent workspace per (device, stream).  An op binds outputs, runs and exports in separate ABI calls, and torch
+// drops the GIL inside ops: `op_mu` is held across the whole op body so that two host threads sampling on the same
+// stream cannot interleave (the reference op is reentrant).
+struct SamplerSlot { pygb200_sampler* s = nullptr; std::mutex op_mu; };
+SamplerSlot& get_slot(int device, cudaStream_t stream) {
   static std::mutex mu;
-  static std::map<std::pair<int, cudaStream_t>, pygb200_sampler*> cache;
+  static std::map<std::pair<int, cudaStream_t>, std::unique_ptr<SamplerSlot>> cache;
   std::lock_guard<std::mutex> lock(mu);
   auto key = std::make_pair(device, stream);
   auto it = cache.find(key);
-  if (it != cache.end()) return it->second;
-  pygb200_sampler* s = nullptr;
-  PYGB_TORCH_CALL(pygb200_sampler_create(&s));
-  cache[key] = s;
-  return s;
+  if (it != cache.end()) return *it->second;
+  auto slot = std::make_unique<SamplerSlot>();
+  PYGB_TORCH_CALL(pygb200_sampler_create(&slot->s));
+  auto& ref = *slot;
+  cache[key] = std::move(slot);
+  return ref;
 }
 
 // RAII view of torch's default CPU generator as the ABI's engine struct.  The reference draws its
@@ -86,6 +91,13 @@ struct CpuEngine {
 static const int64_t kDirectOutputBytes = [] {
   const char* e = getenv("PYGB200_DIRECT_OUTPUT_MB");
   return (e ? (int64_t)atoll(e) : 256ll) << 20;
+}();
+// ... and a view is only handed out when the result fills at least this fraction of its bound-sized buffer (default
+// 0.5); emptier results are copied into exact-size tensors so that a caller who queues batches (or pickles one: a
+// view serialises its whole storage) never holds more than 2x the payload.  PYGB200_DIRECT_MIN_FILL overrides.
+static const double kDirectMinFill = [] {
+  const char* e = getenv("PYGB200_DIRECT_MIN_FILL");
+  return e ? atof(e) : 0.5;
 }();
 
 void check_index_tensor(const at::Tensor& t, const char* name, at::ScalarType st, const at::Device& dev) {
@@ -132,7 +144,9 @@ neighbor_sample_cuda(const at::Tensor& rowptr, const at::Tensor& col, const at::
 
   c10::cuda::CUDAGuard guard(seed.device());
   cudaStream_t stream = at::cuda::getCurrentCUDAStream();
-  pygb200_sampler* s = get_sampler(seed.device().index(), stream);
+  SamplerSlot& slot = get_slot(seed.device().index(), stream);
+  std::lock_guard<std::mutex> op_lock(slot.op_mu);
+  pygb200_sampler* s = slot.s;
   const int L = (int)num_neighbors.size();
   const bool idx32 = st == at::kInt;
   unsigned flags = (replace ? PYGB200_S_REPLACE : 0u) | (disjoint ? PYGB200_S_DISJOINT : 0u) | (idx32 ? PYGB200_S_INDEX32 : 0u) |
@@ -158,8 +172,11 @@ neighbor_sample_cuda(const at::Tensor& rowptr, const at::Tensor& col, const at::
     if (!idx32 && !disjoint && L > 0 &&
         pygb200_sampler_bounds(1, 1, L, &rel, &n_seed, num_neighbors.data(), &ncap, &ecap) == PYGB200_OK && ecap > 0 &&
         (3 * ecap + ncap) * 8 <= kDirectOutputBytes) {
-      row = at::empty({ecap}, opt); colv = at::empty({ecap}, opt); node = at::empty({ncap}, opt);
-      if (return_edge_id) eid = at::empty({ecap}, opt);
+      // ONE allocation for the four results (row | col | edge_id | node_id): one allocator call per sampling call
+      const at::Tensor buf = at::empty({(return_edge_id ? 3 : 2) * ecap + ncap}, opt);
+      row = buf.narrow(0, 0, ecap); colv = buf.narrow(0, ecap, ecap);
+      if (return_edge_id) eid = buf.narrow(0, 2 * ecap, ecap);
+      node = buf.narrow(0, (return_edge_id ? 3 : 2) * ecap, ncap);
       void* rp = row.data_ptr(); void* cp = colv.data_ptr(); void* np = node.data_ptr();
       void* ep = return_edge_id ? eid->data_ptr() : nullptr;
       PYGB_TORCH_CALL(pygb200_sampler_bind_outputs(s, 1, 1, &rp, &cp, &ep, &np, &ecap, &ncap));
@@ -176,6 +193,11 @@ neighbor_sample_cuda(const at::Tensor& rowptr, const at::Tensor& col, const at::
   if (pygb200_sampler_outputs_direct(s)) {
     row = row.narrow(0, 0, n_edges); colv = colv.narrow(0, 0, n_edges); node = node.narrow(0, 0, n_nodes);
     if (return_edge_id) eid = eid->narrow(0, 0, n_edges);
+    const int64_t cap_total = row.storage().nbytes() / 8, used = (return_edge_id ? 3 : 2) * n_edges + n_nodes;
+    if ((double)used < kDirectMinFill * (double)cap_total) {   // sparse result: do not pin the bound-sized storage
+      row = row.clone(); colv = colv.clone(); node = node.clone();
+      if (return_edge_id) eid = eid->clone();
+    }
   } else {
     row = at::empty({n_edges}, opt); colv = at::empty({n_edges}, opt);
     node = disjoint ? at::empty({n_nodes, 2}, opt) : at::empty({n_nodes}, opt);
@@ -213,7 +235,9 @@ dist_neighbor_sample_cuda(const at::Tensor& rowptr, const at::Tensor& col, const
 
   c10::cuda::CUDAGuard guard(seed.device());
   cudaStream_t stream = at::cuda::getCurrentCUDAStream();
-  pygb200_sampler* s = get_sampler(seed.device().index(), stream);
+  SamplerSlot& slot = get_slot(seed.device().index(), stream);
+  std::lock_guard<std::mutex> op_lock(slot.op_mu);
+  pygb200_sampler* s = slot.s;
   const bool idx32 = st == at::kInt;
   const unsigned flags = (replace ? PYGB200_S_REPLACE : 0u) | (disjoint ? PYGB200_S_DISJOINT : 0u) | (idx32 ? PYGB200_S_INDEX32 : 0u) |
                          PYGB200_S_NO_DEDUP;
@@ -321,7 +345,9 @@ hetero_neighbor_sample_cuda(const std::vector<node_type>& node_types, const std:
 
   c10::cuda::CUDAGuard guard(dev);
   cudaStream_t stream = at::cuda::getCurrentCUDAStream();
-  pygb200_sampler* s = get_sampler(dev.index(), stream);
+  SamplerSlot& slot = get_slot(dev.index(), stream);
+  std::lock_guard<std::mutex> op_lock(slot.op_mu);
+  pygb200_sampler* s = slot.s;
   unsigned flags = (replace ? PYGB200_S_REPLACE : 0u) | (disjoint ? PYGB200_S_DISJOINT : 0u) | (idx32 ? PYGB200_S_INDEX32 : 0u);
   std::vector<int64_t> nph((size_t)T * (L + 1), 0), eph((size_t)R * std::max<size_t>(L, 1), 0), n_nodes(T, 0), n_edges(std::max(R, 1), 0);
   std::vector<at::Tensor> d_row, d_col, d_eid, d_node;   // bound-sized results (latency path)
@@ -382,6 +408,7 @@ hetero_neighbor_sample_cuda(const std::vector<node_type>& node_types, const std:
     at::Tensor node;
     if (direct_out) {
       node = d_node[i].narrow(0, 0, n_nodes[i]);
+      if ((double)n_nodes[i] < kDirectMinFill * (double)d_node[i].numel()) node = node.clone();
     } else {
       node = disjoint ? at::empty({n_nodes[i], 2}, opt) : at::empty({n_nodes[i]}, opt);
       PYGB_TORCH_CALL(pygb200_sampler_export_nodes(s, i, node.data_ptr(), idx32, stream));
@@ -395,6 +422,10 @@ hetero_neighbor_sample_cuda(const std::vector<node_type>& node_types, const std:
     if (direct_out) {
       row = d_row[r].narrow(0, 0, n_edges[r]); colv = d_col[r].narrow(0, 0, n_edges[r]);
       if (return_edge_id) eid = d_eid[r].narrow(0, 0, n_edges[r]);
+      if ((double)n_edges[r] < kDirectMinFill * (double)d_row[r].numel()) {
+        row = row.clone(); colv = colv.clone();
+        if (return_edge_id) eid = eid.clone();
+      }
     } else {
       row = at::empty({n_edges[r]}, opt); colv = at::empty({n_edges[r]}, opt);
       if (return_edge_id) eid = at::empty({n_edges[r]}, opt);

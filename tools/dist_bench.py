@@ -21,6 +21,7 @@ def main():
     ap.add_argument('--graph', default='products')
     ap.add_argument('--seeds', type=int, default=65536)
     ap.add_argument('--iters', type=int, default=10)
+    ap.add_argument('--collective', action='store_true', help='also time the NCCL-broadcast transport with replicated dedup')
     a = ap.parse_args()
     rank, world = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1))
     dev = torch.device('cuda', int(os.environ.get('LOCAL_RANK', 0)))
@@ -55,6 +56,7 @@ def main():
 
     ms1, ed1, _ = timed(lambda: P.sampler.neighbor_sample(rowptr, col, seed, nn))
     msN, edN, _ = timed(lambda: P.sampler.dist_neighbor_sample(rowptr, col, seed, nn))
+    msC, _, _ = timed(lambda: P.sampler.dist_neighbor_sample(rowptr, col, seed, nn, transport='collective')) if a.collective else (None, None, None)
     # identical results: same seed, one call each
     torch.manual_seed(7); o1 = P.sampler.neighbor_sample(rowptr, col, seed, nn)
     torch.manual_seed(7); oN = P.sampler.dist_neighbor_sample(rowptr, col, seed, nn)
@@ -64,7 +66,7 @@ def main():
     dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
     if rank == 0:
         print(json.dumps({'graph': a.graph, 'n_gpus': world, 'seeds': a.seeds, 'fanout': nn, 'graph_gen_s': gen_s,
-                          'single_gpu_ms': ms1, 'single_gpu_edges_per_s': ed1 / (ms1 * 1e-3), 'sharded_ms': msN,
+                          'single_gpu_ms': ms1, 'single_gpu_edges_per_s': ed1 / (ms1 * 1e-3), 'sharded_ms': msN, 'sharded_collective_ms': msC,
                           'sharded_edges_per_s': edN / (msN * 1e-3), 'edges_per_call': edN,
                           'sharded_equals_single_gpu': bool(same), 'all_ranks_identical': bool(torch.equal(lo, hi))}))
     dist.destroy_process_group()
