@@ -1875,11 +1875,10 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
     }
   const bool p2p = sharded && shard->exchange != nullptr;
   bool v2 = !lat && !synced && !nodedup && !disjoint && !any_time && L > 0 && (!no_v2 || p2p) && (!sharded || p2p);
-  if (v2) {   // every node type's id range must be known and fit the packed key (a type that is never a source has no bound)
-    std::vector<i64> type_nodes((size_t)T, -1);
-    for (int r = 0; r < R; ++r) type_nodes[rels[r].src_type] = std::max(type_nodes[rels[r].src_type], (i64)rels[r].num_src_nodes);
+  std::vector<i64> type_nodes((size_t)T, -1);   // nodes of each type, where a relation with that source type tells us
+  for (int r = 0; r < R; ++r) type_nodes[rels[r].src_type] = std::max(type_nodes[rels[r].src_type], (i64)rels[r].num_src_nodes);
+  if (v2)   // every node type's id range must be known and fit the packed key (a type that is never a source has no bound)
     for (int t = 0; t < T && v2; ++t) v2 = idx32 || (type_nodes[t] >= 0 && type_nodes[t] < 0xffffffffll);
-  }
   if (p2p) PYGB_CHECK(v2 && T == 1 && R == 1 && shard->world <= V2_MAX_W, PYGB200_ERR_UNSUPPORTED,
                       "peer-memory frontier sharding: homogeneous, non-disjoint, bounded fan-outs, node ids < 2^32-1, world <= 16");
   const int XW = p2p ? shard->world : 1, XR = p2p ? shard->rank : 0;
@@ -1931,8 +1930,10 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
   if (v2) {
     for (int t = 0; t < T; ++t) {
       if (int e = ensure_type(s, t, node_cap[t], 0, false, st)) return e;
-      // a rank's table holds the keys it owns: 1/W of them (+25 % for imbalance)
-      if (int e = ensure_table_v2(s, t, XW == 1 ? node_cap[t] : node_cap[t] / XW + node_cap[t] / (4 * XW) + 1024, st)) return e;
+      // distinct keys <= min(static bound, nodes of the type): a products-sized graph (2.4 M nodes) keeps its table
+      // L2-resident (64 MB) whatever the batch; a rank's table holds the keys it owns: 1/W of them (+25 % for imbalance)
+      const i64 keys = type_nodes[t] >= 0 ? std::min(node_cap[t], type_nodes[t]) : node_cap[t];
+      if (int e = ensure_table_v2(s, t, XW == 1 ? keys : keys / XW + keys / (4 * XW) + 1024, st)) return e;
     }
     for (int r = 0; r < R; ++r) if (int e = ensure_rel(s, r, rel_cap[r], 0, st)) return e;
     if (int e = ensure_frontier_scratch(s, max_F, st)) return e;
@@ -2111,10 +2112,10 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
   auto v2_ids = [&](const PassArgs& a, i64 Eb) -> int {
     void* tk;
     if (p2p) {
-      launch_pdl(k_v2_pref, grid_for(Eb, NT, s->sm_count), NT, st, a);
+      launch_pdl(k_v2_pref, grid_for(Eb, 4 * NT, s->sm_count), NT, st, a);
       PYGB_LAUNCH_CHECK();
       if (int e = xbarrier(a)) return e;
-      launch_pdl(k_v2_reduce, grid_for(ceil_div(Eb, XW), NT, s->sm_count), NT, st, a);
+      launch_pdl(k_v2_reduce, grid_for(ceil_div(Eb, XW), 4 * NT, s->sm_count), NT, st, a);
       PYGB_LAUNCH_CHECK();
       if (int e = xbarrier(a)) return e;
       tk = prof_begin(st);
@@ -2126,8 +2127,8 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
     prof_end(tk, "mark", st, Eb);
     PYGB_LAUNCH_CHECK();
     tk = prof_begin(st);
-    if (p2p) launch_pdl(k_v2_assign<true>, grid_for(Eb, NT, s->sm_count), NT, st, a);
-    else launch_pdl(k_v2_assign<false>, grid_for(Eb, NT, s->sm_count), NT, st, a);
+    if (p2p) launch_pdl(k_v2_assign<true>, grid_for(Eb, 4 * NT, s->sm_count), NT, st, a);
+    else launch_pdl(k_v2_assign<false>, grid_for(Eb, 4 * NT, s->sm_count), NT, st, a);
     prof_end(tk, "assign", st, Eb);
     PYGB_LAUNCH_CHECK();
     return PYGB200_OK;
@@ -2329,7 +2330,7 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
           PYGB_LAUNCH_CHECK();
           if (p2p) {
             if (int e = xbarrier(a)) return e;   // everybody's (dst, edge id) have arrived
-            launch_pdl(k_v2_insert, grid_for(Eb, NT, s->sm_count), NT, st, a);
+            launch_pdl(k_v2_insert, grid_for(Eb, 4 * NT, s->sm_count), NT, st, a);
             PYGB_LAUNCH_CHECK();
           }
           if (int e = v2_ids(a, Eb)) return e;

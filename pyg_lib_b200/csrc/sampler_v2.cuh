@@ -150,14 +150,46 @@ __global__ void __launch_bounds__(NT, SAMPLE_MIN_BLOCKS) k_v2_sample(const PassA
   tl_mark(TL_SAMPLE | TL_END);
 }
 
-// ---- sharded: the owner of a dst id inserts it (all positions of the pass are streamed, 1/W of them hit the table)
+// ---- sharded: the owner of a dst id inserts it (all positions of the pass are streamed, 1/W of them hit the table).
+// Four positions per thread (coalesced, strided by the block) with their first CAS issued back to back: the kernel is
+// bound by the round trips of independent atomics, not by their number.
 __global__ void __launch_bounds__(NT) k_v2_insert(const PassArgs a) {
   pdl_enter();
   const i64 E = a.st[ST_PASS_E];
   const u32* __restrict__ xdst = x_ptr<u32>(a, a.xr, a.x_off_dst);
-  for (i64 p = (i64)blockIdx.x * NT + threadIdx.x; p < E; p += (i64)gridDim.x * NT) {
-    const u32 key = xdst[p];
-    a.eslot[p] = v2_owner(key, a.xw) == a.xr ? v2_insert(a.pk, a.pk_bits, key, (u32)p) : NO_SLOT;
+  const u64 mask = (1ull << a.pk_bits) - 1;
+  for (i64 base = (i64)blockIdx.x * (4 * NT); base < E; base += (i64)gridDim.x * (4 * NT)) {
+    u32 key[4]; u64 slot[4], prev[4]; bool own[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const i64 p = base + j * NT + threadIdx.x;
+      key[j] = p < E ? xdst[p] : 0u;
+      own[j] = p < E && v2_owner(key[j], a.xw) == a.xr;
+      slot[j] = ((u64)key[j] * 0x9E3779B97F4A7C15ull) >> (64 - a.pk_bits);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const i64 p = base + j * NT + threadIdx.x;
+      prev[j] = own[j] ? atomicCAS(&a.pk[slot[j]], EMPTY, ((u64)key[j] << 32) | (u64)(V2_POS | (u32)p)) : EMPTY;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const i64 p = base + j * NT + threadIdx.x;
+      if (p >= E) break;
+      u32 res = NO_SLOT;
+      if (own[j]) {
+        const u64 mine = ((u64)key[j] << 32) | (u64)(V2_POS | (u32)p);
+        u64 sl = slot[j], pv = prev[j];
+        while (true) {   // (same decisions as v2_insert, continuing from the CAS already made)
+          if (pv == EMPTY) break;
+          if ((u32)(pv >> 32) == key[j]) { if ((u32)pv > (V2_POS | (u32)p)) red_min_u64(&a.pk[sl], mine); break; }
+          sl = (sl + 1) & mask;
+          pv = atomicCAS(&a.pk[sl], EMPTY, mine);
+        }
+        res = (u32)sl;
+      }
+      a.eslot[p] = res;
+    }
   }
 }
 
@@ -166,21 +198,34 @@ __global__ void __launch_bounds__(NT) k_v2_pref(const PassArgs a) {
   pdl_enter();
   const i64 E = a.st[ST_PASS_E];
   u32* __restrict__ pref = x_ptr<u32>(a, a.xr, a.x_off_pref);
-  for (i64 p = (i64)blockIdx.x * NT + threadIdx.x; p < E; p += (i64)gridDim.x * NT) {
-    const u32 s = a.eslot[p];
-    pref[p] = s == NO_SLOT ? 0u : (u32)a.pk[s];
+  for (i64 base = (i64)blockIdx.x * (4 * NT); base < E; base += (i64)gridDim.x * (4 * NT)) {
+    u32 s[4], v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { const i64 p = base + j * NT + threadIdx.x; s[j] = p < E ? __ldg(&a.eslot[p]) : NO_SLOT; }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = s[j] == NO_SLOT ? 0u : (u32)a.pk[s[j]];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { const i64 p = base + j * NT + threadIdx.x; if (p < E) pref[p] = v[j]; }
   }
 }
 
 // ---- sharded: this rank's position slice of the refs = sum over the ranks' partial refs (coalesced peer loads),
-// stored to every rank (coalesced peer stores)
+// stored to every rank (coalesced peer stores); 4 positions per thread so that 4 x W loads are in flight
 __global__ void __launch_bounds__(NT) k_v2_reduce(const PassArgs a) {
   pdl_enter();
   const i64 lo = a.st[a.o_shard + a.xr], hi = a.st[a.o_shard + a.xr + 1];
-  for (i64 p = lo + (i64)blockIdx.x * NT + threadIdx.x; p < hi; p += (i64)gridDim.x * NT) {
-    u32 v = 0;
-    for (int q = 0; q < a.xw; ++q) v += x_ptr<u32>(a, q, a.x_off_pref)[p];
-    for (int q = 0; q < a.xw; ++q) x_ptr<u32>(a, q, a.x_off_fref)[p] = v;
+  for (i64 base = lo + (i64)blockIdx.x * (4 * NT); base < hi; base += (i64)gridDim.x * (4 * NT)) {
+    u32 v[4] = {0, 0, 0, 0};
+    for (int q = 0; q < a.xw; ++q) {
+      const u32* __restrict__ src = x_ptr<u32>(a, q, a.x_off_pref);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { const i64 p = base + j * NT + threadIdx.x; if (p < hi) v[j] += src[p]; }
+    }
+    for (int q = 0; q < a.xw; ++q) {
+      u32* __restrict__ dst = x_ptr<u32>(a, q, a.x_off_fref);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { const i64 p = base + j * NT + threadIdx.x; if (p < hi) dst[p] = v[j]; }
+    }
   }
 }
 
@@ -299,6 +344,14 @@ __global__ void __launch_bounds__(NT) k_v2_mark(const PassArgs a) {
 // ---- ids.  An edge's dst id = its ref if the node is older than this pass, else ids_base + rank of the node's first
 // position.  Firsts append their node to the dst list; the owner of the slot writes the id back unless no later pass
 // inserts into this table (then nobody will read it).
+// Four edges per thread: the kernel is a chain of dependent loads per edge (ref -> rank of the ref's position ->
+// store), and with one edge per thread in flight — the loads of an unrolled iteration could not move above the stores
+// of the previous one — it ran at 3.5 % issue utilisation: 357 us for 6 M edges (profiles/ncu_summary_r2.json, first
+// capture).  Now the four refs and their four rank lookups are issued together through the read-only path (nothing
+// this kernel writes is read by it, except colv by the same thread).
+__device__ __forceinline__ i64 v2_rank_of(const PassArgs& a, u32 q) {
+  return __ldg(&a.mtile[q / ETILE]) + (i64)__ldg(&a.erank[q]);
+}
 template <bool SH>
 __global__ void __launch_bounds__(NT) k_v2_assign(const PassArgs a) {
   pdl_enter(TL_ASSIGN);
@@ -306,33 +359,47 @@ __global__ void __launch_bounds__(NT) k_v2_assign(const PassArgs a) {
   const i64 pbase = a.st[ST_PASS_BASE];
   const i64 list_base = a.st[ST_LIST_BASE], ids_base = a.st[ST_IDS_BASE];
   const u32* __restrict__ xdst = SH ? x_ptr<u32>(a, a.xr, a.x_off_dst) : nullptr;
-  for (i64 p = (i64)blockIdx.x * NT + threadIdx.x; p < E; p += (i64)gridDim.x * NT) {
-    const u32 r = a.fref[p];
+  // a block takes 1024 consecutive edges per step, thread t the edges base + t + 256 j: every access is coalesced and
+  // the four chains of a thread are independent
+  for (i64 base = (i64)blockIdx.x * (4 * NT); base < E; base += (i64)gridDim.x * (4 * NT)) {
+    u32 r[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const i64 p = base + j * NT + threadIdx.x;
+      r[j] = p < E ? __ldg(&a.fref[p]) : 0u;
+    }
     if (a.seed_mode) {
-      const bool first = r == (V2_POS | (u32)p);
-      const u32 s = a.eslot[p];
-      if (first && s != NO_SLOT) a.pk[s] = ((u64)(u32)a.dst_nodes[p] << 32) | (u64)(a.mtile[p / ETILE] + a.erank[p]);
-      a.dst_slot[p] = first ? s : NO_SLOT;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const i64 p = base + j * NT + threadIdx.x;
+        if (p >= E) break;
+        const bool first = r[j] == (V2_POS | (u32)p);
+        const u32 s = a.eslot[p];
+        if (first && s != NO_SLOT) a.pk[s] = ((u64)(u32)a.dst_nodes[p] << 32) | (u64)v2_rank_of(a, (u32)p);
+        a.dst_slot[p] = first ? s : NO_SLOT;
+      }
       continue;
     }
-    i64 id; bool first = false; i64 rank = 0;
-    if (r & V2_POS) {
-      const u32 q = r & ~V2_POS;
-      rank = a.mtile[q / ETILE] + a.erank[q];
-      id = ids_base + rank;
-      first = q == (u32)p;
-    } else {
-      id = r;
+    i64 id[4], rank[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {   // four independent lookups in flight
+      rank[j] = (r[j] & V2_POS) ? v2_rank_of(a, r[j] & ~V2_POS) : 0;
+      id[j] = (r[j] & V2_POS) ? ids_base + rank[j] : (i64)r[j];
     }
-    if (SH) a.eid[pbase + p] = a.x_eid64 ? (i64)x_ptr<u64>(a, a.xr, a.x_off_eid)[p] : (i64)x_ptr<u32>(a, a.xr, a.x_off_eid)[p];
-    if (!first) { a.colv[pbase + p] = id; continue; }
-    {
-      const i64 d = SH ? (i64)xdst[p] : a.colv[pbase + p];   // (global id, about to be replaced)
-      a.colv[pbase + p] = id;
-      const u32 s = a.eslot[p];
-      a.dst_nodes[list_base + rank] = d;
-      a.dst_slot[list_base + rank] = s;
-      if (a.v2_writeback && s != NO_SLOT) a.pk[s] = ((u64)(u32)d << 32) | (u64)id;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const i64 p = base + j * NT + threadIdx.x;
+      if (p >= E) break;
+      if (SH) a.eid[pbase + p] = a.x_eid64 ? (i64)x_ptr<u64>(a, a.xr, a.x_off_eid)[p] : (i64)x_ptr<u32>(a, a.xr, a.x_off_eid)[p];
+      const bool first = r[j] == (V2_POS | (u32)p);
+      if (first) {
+        const i64 d = SH ? (i64)xdst[p] : a.colv[pbase + p];   // (global id, about to be replaced)
+        const u32 s = a.eslot[p];
+        a.dst_nodes[list_base + rank[j]] = d;
+        a.dst_slot[list_base + rank[j]] = s;
+        if (a.v2_writeback && s != NO_SLOT) a.pk[s] = ((u64)(u32)d << 32) | (u64)id[j];
+      }
+      a.colv[pbase + p] = id[j];
     }
   }
 }
