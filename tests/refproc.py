@@ -77,15 +77,32 @@ def rng_prefix():
     return torch.get_rng_state()[:24 + 624 * 8].clone()
 
 
-def lowp_ulp_excess(out: torch.Tensor, ref: torch.Tensor, floor: float = 2.0 ** -10) -> float:
-    """max |out - ref| in units of one storage ulp of the reference value: ulp(v) = 2^-7 |v| for bf16, 2^-10 |v| for
-    fp16 (an upper bound of the true spacing, within 2x), with |v| floored at `floor` — results that cancel to almost
-    zero carry the fp32 accumulation-order noise of a K-term dot product (~1e-6 here), which no rounding argument
-    bounds in ulps of a tiny result.  SURVEY.md 8(c): parity holds when this is <= 1."""
+def accumulation_bound(x: torch.Tensor, ptr: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
+    """Rigorous bound on how far two fp32-accumulated K-term dot products of the same inputs can be apart because of
+    their summation ORDER (Higham, gamma_K): 2 K 2^-24 sum_k |x_ik| |w_kj|, per output element [N, M] (fp32, on x's
+    device).  It only matters for results that cancel to almost zero, where an error in ulps of the RESULT says nothing."""
+    K = x.size(1)
+    out = torch.empty(x.size(0), w.size(2), dtype=torch.float32, device=x.device)
+    p = ptr.tolist()
+    for b in range(len(p) - 1):
+        if p[b + 1] > p[b]:
+            out[p[b]:p[b + 1]] = x[p[b]:p[b + 1]].float().abs() @ w[b].float().abs()
+    return out * (2.0 * K * 2.0 ** -24)
+
+
+def lowp_ulp_excess(out: torch.Tensor, ref: torch.Tensor, abs_tol=None) -> float:
+    """max (|out - ref| - abs_tol) in units of one storage ulp of the reference value: ulp(v) = 2^-7 |v| for bf16,
+    2^-10 |v| for fp16 (an upper bound of the true spacing, within 2x).  `abs_tol` (tensor like out, or None) is the
+    fp32 accumulation-order allowance of `accumulation_bound`.  SURVEY.md 8(c): parity holds when the result is <= 1."""
     rel = 2.0 ** -7 if out.dtype == torch.bfloat16 else 2.0 ** -10
-    o, r = out.float(), ref.float()
     worst = 0.0
-    for i in range(0, o.size(0), 1 << 16):   # chunked: full-size outputs are 134 M elements
-        oc, rc = o[i:i + (1 << 16)], r[i:i + (1 << 16)]
-        worst = max(worst, float(((oc - rc).abs() / (rel * rc.abs().clamp_min(floor))).max())) if oc.numel() else worst
+    step = 1 << 16
+    for i in range(0, out.size(0), step):   # chunked: full-size outputs are 134 M elements
+        oc, rc = out[i:i + step].float(), ref[i:i + step].float()
+        if not oc.numel():
+            continue
+        d = (oc - rc).abs()
+        if abs_tol is not None:
+            d = (d - abs_tol[i:i + step].to(d.device)).clamp_min(0)
+        worst = max(worst, float((d / (rel * rc.abs().clamp_min(1e-30))).max()))
     return worst
