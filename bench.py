@@ -303,7 +303,7 @@ def sampler_roofline(abi, step_dev, first, n_prof, torch, peaks, hbm_peak, peak_
     torch.cuda.synchronize()
     abi.pygb200_profile_enable(0)
     prof = {}
-    for name in ('count', 'sample', 'mark', 'assign', 'lookup'):
+    for name in ('count', 'sample', 'mark', 'assign', 'lookup', 'seed', 'insert', 'pref', 'reduce', 'xbarrier', 'final', 'cleanup', 'export'):
         msv, ln, wk = C.c_double(), C.c_int64(), C.c_int64()
         abi.pygb200_profile_read(name.encode(), C.byref(msv), C.byref(ln), C.byref(wk))
         prof[name] = (msv.value, ln.value, wk.value)
@@ -317,7 +317,7 @@ def sampler_roofline(abi, step_dev, first, n_prof, torch, peaks, hbm_peak, peak_
     return {'bound': 'hbm', 'kernel': 'k_' + dom, 'achieved': achieved, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': achieved / hbm_peak,
             'traffic': traffic, 'peak_source': peak_src, 'avg_launch_us': 1e6 * avg_s, 'bytes_per_launch': bytes_per_launch,
             'launches_per_call': launches_per_call, 'edges_per_call': edges / max(n_prof, 1),
-            'kernel_ms_share': {k: v[0] for k, v in prof.items()}}
+            'kernel_ms_per_call': {k: v[0] / max(n_prof, 1) for k, v in prof.items() if v[1]}}
 
 
 def load_traffic():

@@ -59,8 +59,8 @@ int pygb200_kernel_launches(void);       /* number of kernels this library launc
 /* Per-kernel device timing for bench.py's roofline: when enabled, selected kernels are bracketed with
  * CUDA events on their launching stream.  `pygb200_profile_read` synchronises the pending events and
  * returns accumulated milliseconds, launch count and work units (sampler kernels: edges; matmul: rows)
- * for `name` in {"sample","count","mark","assign","lookup","segment_matmul","grouped_gemm"}, then
- * resets that accumulator.  Returns 0, or PYGB200_ERR_ARG for an unknown name. */
+ * for `name` in {"sample","count","mark","assign","lookup","segment_matmul","grouped_gemm"} and, for the throughput /
+ * sharded schedule, {"seed","insert","pref","reduce","xbarrier","final","cleanup","export"}, then resets that accumulator.  Returns 0, or PYGB200_ERR_ARG for an unknown name. */
 void pygb200_profile_enable(int on);
 int pygb200_profile_read(const char* name, double* ms, int64_t* launches, int64_t* work);
 

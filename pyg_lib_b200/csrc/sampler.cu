@@ -46,7 +46,9 @@ std::mutex g_prof_mu;
 std::atomic<bool> g_prof_on{false};
 std::vector<ProfPending> g_prof_pending;
 ProfAcc g_prof_acc[] = {{"sample", 0, 0, 0}, {"count", 0, 0, 0}, {"mark", 0, 0, 0}, {"assign", 0, 0, 0},
-                        {"lookup", 0, 0, 0}, {"segment_matmul", 0, 0, 0}, {"grouped_gemm", 0, 0, 0}};
+                        {"lookup", 0, 0, 0}, {"segment_matmul", 0, 0, 0}, {"grouped_gemm", 0, 0, 0},
+                        {"insert", 0, 0, 0}, {"pref", 0, 0, 0}, {"reduce", 0, 0, 0}, {"xbarrier", 0, 0, 0},
+                        {"seed", 0, 0, 0}, {"final", 0, 0, 0}, {"cleanup", 0, 0, 0}, {"export", 0, 0, 0}};
 constexpr int N_PROF = sizeof(g_prof_acc) / sizeof(g_prof_acc[0]);
 int prof_slot(const char* name) {
   for (int i = 0; i < N_PROF; ++i) if (strcmp(g_prof_acc[i].name, name) == 0) return i;
@@ -320,56 +322,57 @@ __device__ __forceinline__ void block_scan_nodes(u32 v, Func4 f, u32* ex_v, Func
 }
 
 // Single-block ordered scan of the frontier tile aggregates: edge offsets and absolute RNG positions.
-// Runs in the last block of k_count.  blockDim.x == NT.
+// Runs in the last block of k_count.  blockDim.x == NT.  Every thread takes a contiguous chunk of ceil(ntiles / NT)
+// tiles: serial reduction of the chunk, ONE block-wide scan of the NT chunk totals, serial scan of the chunk — a
+// 983 k-node frontier (3840 tiles) used to cost 15 rounds of block-wide scans here, in a section nothing overlaps.
 __device__ void scan_frontier_tiles(const PassArgs& a, i64 ntiles) {
   __shared__ i64 s_sum[NT / 32];
   __shared__ Func4L s_fun[NT / 32];
-  __shared__ i64 c_off, c_pos;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  if (threadIdx.x == 0) { c_off = 0; c_pos = a.st[ST_CURSOR]; }
-  __syncthreads();
-  for (i64 base = 0; base < ntiles; base += NT) {
-    const i64 t = base + threadIdx.x;
-    i64 v = 0; Func4L f = {{0, 0, 0, 0}};
-    if (t < ntiles) {
-      v = __ldcg(&a.tile_out[t]);
+  const i64 per = ceil_div(ntiles, NT);
+  const i64 t0 = (i64)threadIdx.x * per, t1 = t0 + per < ntiles ? t0 + per : ntiles;
+  const i64 cur0 = a.st[ST_CURSOR];
+  i64 v = 0; Func4L f = {{0, 0, 0, 0}};
+  for (i64 t = t0; t < t1; ++t) {
+    v += __ldcg(&a.tile_out[t]);
+    Func4L g;
 #pragma unroll
-      for (int p = 0; p < 4; ++p) f.d[p] = __ldcg(&a.tile_func[4 * t + p]);
-    }
-    i64 iv = v; Func4L iff = f;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const i64 ov = __shfl_up_sync(0xffffffffu, iv, d);
-      Func4L of;
-#pragma unroll
-      for (int p = 0; p < 4; ++p) of.d[p] = __shfl_up_sync(0xffffffffu, iff.d[p], d);
-      if (lane >= d) { iv += ov; iff = composeL(of, iff); }
-    }
-    if (lane == 31) { s_sum[wid] = iv; s_fun[wid] = iff; }
-    __syncthreads();
-    i64 pv = 0; Func4L pfx = {{0, 0, 0, 0}};
-    for (int w = 0; w < wid; ++w) { pv += s_sum[w]; pfx = composeL(pfx, s_fun[w]); }
-    i64 ev = __shfl_up_sync(0xffffffffu, iv, 1);
-    Func4L ef;
-#pragma unroll
-    for (int p = 0; p < 4; ++p) ef.d[p] = __shfl_up_sync(0xffffffffu, iff.d[p], 1);
-    if (lane == 0) { ev = 0; ef = {{0, 0, 0, 0}}; }
-    const Func4L exf = composeL(pfx, ef);
-    const i64 off0 = c_off, pos0 = c_pos;
-    if (t < ntiles) {
-      a.tile_off[t] = off0 + pv + ev;
-      a.tile_pos[t] = pos0 + (i64)sel4(exf, (unsigned)(pos0 & 3));
-    }
-    i64 tv = 0; Func4L tf = {{0, 0, 0, 0}};
-    for (int w = 0; w < NT / 32; ++w) { tv += s_sum[w]; tf = composeL(tf, s_fun[w]); }
-    __syncthreads();
-    if (threadIdx.x == 0) { c_off = off0 + tv; c_pos = pos0 + (i64)sel4(tf, (unsigned)(pos0 & 3)); }
-    __syncthreads();
+    for (int p = 0; p < 4; ++p) g.d[p] = __ldcg(&a.tile_func[4 * t + p]);
+    f = composeL(f, g);
   }
-  if (threadIdx.x == 0) {
-    const i64 E = c_off;
+  i64 iv = v; Func4L iff = f;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const i64 ov = __shfl_up_sync(0xffffffffu, iv, d);
+    Func4L of;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) of.d[p] = __shfl_up_sync(0xffffffffu, iff.d[p], d);
+    if (lane >= d) { iv += ov; iff = composeL(of, iff); }
+  }
+  if (lane == 31) { s_sum[wid] = iv; s_fun[wid] = iff; }
+  __syncthreads();
+  i64 pv = 0; Func4L pfx = {{0, 0, 0, 0}};
+  for (int w = 0; w < wid; ++w) { pv += s_sum[w]; pfx = composeL(pfx, s_fun[w]); }
+  i64 ev = __shfl_up_sync(0xffffffffu, iv, 1);
+  Func4L ef;
+#pragma unroll
+  for (int p = 0; p < 4; ++p) ef.d[p] = __shfl_up_sync(0xffffffffu, iff.d[p], 1);
+  if (lane == 0) { ev = 0; ef = {{0, 0, 0, 0}}; }
+  i64 off = pv + ev;                  // edges emitted before this thread's chunk
+  Func4L adv = composeL(pfx, ef);     // RNG advance (per entry phase) before this thread's chunk
+  for (i64 t = t0; t < t1; ++t) {
+    a.tile_off[t] = off;
+    a.tile_pos[t] = cur0 + (i64)sel4(adv, (unsigned)(cur0 & 3));
+    off += __ldcg(&a.tile_out[t]);
+    Func4L g;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) g.d[p] = __ldcg(&a.tile_func[4 * t + p]);
+    adv = composeL(adv, g);
+  }
+  if (threadIdx.x == NT - 1) {        // (the last thread's running values are the totals)
+    const i64 E = off;
     a.st[ST_PASS_E] = E;
-    a.st[ST_CURSOR] = c_pos;
+    a.st[ST_CURSOR] = cur0 + (i64)sel4(adv, (unsigned)(cur0 & 3));
     if (!a.seed_mode) {
       a.st[ST_PASS_BASE] = a.st[a.o_rel_edges];
       a.st[a.o_rel_edges] += E;
@@ -2105,17 +2108,23 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
   // barrier -> the same mark on the full ref array.  Then ids (replicated, streaming).
   static const u64 xbar_timeout_ns = [] { const char* e = getenv("PYGB200_XBARRIER_TIMEOUT_MS"); return (u64)(e ? atoll(e) : 20000) * 1000000ull; }();
   auto xbarrier = [&](const PassArgs& a) -> int {
+    void* tkb = prof_begin(st);
     launch_pdl(k_xbarrier, 1, 32, st, a, (u64)(++s->x.epoch), xbar_timeout_ns);
+    prof_end(tkb, "xbarrier", st, 1);
     PYGB_LAUNCH_CHECK();
     return PYGB200_OK;
   };
   auto v2_ids = [&](const PassArgs& a, i64 Eb) -> int {
     void* tk;
     if (p2p) {
+      tk = prof_begin(st);
       launch_pdl(k_v2_pref, grid_for(Eb, 4 * NT, s->sm_count), NT, st, a);
+      prof_end(tk, "pref", st, Eb);
       PYGB_LAUNCH_CHECK();
       if (int e = xbarrier(a)) return e;
+      tk = prof_begin(st);
       launch_pdl(k_v2_reduce, grid_for(ceil_div(Eb, XW), 4 * NT, s->sm_count), NT, st, a);
+      prof_end(tk, "reduce", st, Eb);
       PYGB_LAUNCH_CHECK();
       if (int e = xbarrier(a)) return e;
       tk = prof_begin(st);
@@ -2171,8 +2180,10 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
     if (v2) {
       if (n_seeds[t] == 0) continue;   // the zeroed state already says "empty list, empty slice"
       const int g = grid_for(n_seeds[t], NT, s->sm_count);
+      void* tks = prof_begin(st);
       if (idx32) launch_pdl(k_v2_seed<int32_t>, g, NT, st, a, (const int32_t*)seeds[t], (i64)n_seeds[t]);
       else launch_pdl(k_v2_seed<int64_t>, g, NT, st, a, (const int64_t*)seeds[t], (i64)n_seeds[t]);
+      prof_end(tks, "seed", st, n_seeds[t]);
       PYGB_LAUNCH_CHECK();
       if (int e = v2_ids(a, n_seeds[t])) return e;
       k_seed_end<<<1, 1, 0, st>>>(dst, t, L, lay.o_list, lay.o_begin, lay.o_end, lay.o_nph);
@@ -2330,7 +2341,9 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
           PYGB_LAUNCH_CHECK();
           if (p2p) {
             if (int e = xbarrier(a)) return e;   // everybody's (dst, edge id) have arrived
+            void* tki = prof_begin(st);
             launch_pdl(k_v2_insert, grid_for(Eb, 4 * NT, s->sm_count), NT, st, a);
+            prof_end(tki, "insert", st, Eb);
             PYGB_LAUNCH_CHECK();
           }
           if (int e = v2_ids(a, Eb)) return e;
@@ -2426,7 +2439,9 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
       a.pub_host = s->st_host_dev; a.pub_zero = dst_other; a.pub_serial = s->run_serial; a.pub_words = (int)lay.words;
       a.pub_o_mt = lay.o_mt;
     }
+    void* tkf = prof_begin(st);
     launch_pdl(k_final, lk_colv ? grid_for(lk_E, NT, s->sm_count) : 1, NT, st, a);
+    prof_end(tkf, "final", st, 1);
     PYGB_LAUNCH_CHECK();
   }
   // table cleanup is stream-ordered after k_final; the host does not wait for it.  With
@@ -2437,7 +2452,9 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
   s->nd_seeds = nodedup ? n_seeds[0] : 0;
   for (int t = 0; t < T && v2; ++t) {
     auto& tb = s->types[t];
+    void* tkc = prof_begin(st);
     launch_pdl(k_v2_cleanup, grid_for(node_cap[t], NT, s->sm_count), NT, st, tb.pk.as<u64>(), (const u32*)tb.slot.as<u32>(), (const i64*)(dst + lay.o_list + t));
+    prof_end(tkc, "cleanup", st, node_cap[t]);
     PYGB_LAUNCH_CHECK();
   }
   for (int t = 0; t < T && !s->cleanup_pending && !v2; ++t) {
@@ -2656,8 +2673,10 @@ extern "C" int pygb200_sampler_export_edges(pygb200_sampler* s, int32_t rel, voi
   if (n == 0) return PYGB200_OK;
   const int g = grid_for(n, NT, s->sm_count);
   const i64 *s0 = s->rels[rel].row.as<i64>(), *s1 = s->rels[rel].colv.as<i64>(), *s2 = s->rels[rel].eid.as<i64>();
+  void* tk = prof_begin(st);
   if (index32) k_export3<int32_t><<<g, NT, 0, st>>>(s0, s1, s2, (int32_t*)row_out, (int32_t*)col_out, (int32_t*)edge_id_out, n);
   else k_export3<int64_t><<<g, NT, 0, st>>>(s0, s1, s2, (int64_t*)row_out, (int64_t*)col_out, (int64_t*)edge_id_out, n);
+  prof_end(tk, "export", st, n);
   PYGB_LAUNCH_CHECK();
   return PYGB200_OK;
 }

@@ -235,27 +235,29 @@ __device__ void mark_finish(const PassArgs& a, i64 E, i64 ntiles) {
   __shared__ i64 s_s[NT / 32];
   __shared__ i64 carry;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  if (threadIdx.x == 0) carry = 0;
-  __syncthreads();
-  for (i64 base = 0; base < ntiles; base += NT) {
-    const i64 t = base + threadIdx.x;
-    const i64 v = t < ntiles ? __ldcg(&a.mtile[t]) : 0;
-    i64 inc = v;
+  // a contiguous chunk of tiles per thread: serial sum, one block-wide scan of the chunk totals, serial exclusive scan
+  const i64 per = ceil_div(ntiles, NT);
+  const i64 t0 = (i64)threadIdx.x * per, t1 = t0 + per < ntiles ? t0 + per : ntiles;
+  i64 v = 0;
+  for (i64 t = t0; t < t1; ++t) v += __ldcg(&a.mtile[t]);
+  i64 inc = v;
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const i64 o = __shfl_up_sync(0xffffffffu, inc, d);
-      if (lane >= d) inc += o;
-    }
-    if (lane == 31) s_s[wid] = inc;
-    __syncthreads();
-    i64 pre = 0, tot = 0;
-    for (int w = 0; w < NT / 32; ++w) { if (w < wid) pre += s_s[w]; tot += s_s[w]; }
-    const i64 c0 = carry;
-    if (t < ntiles) a.mtile[t] = c0 + pre + inc - v;
-    __syncthreads();
-    if (threadIdx.x == 0) carry = c0 + tot;
-    __syncthreads();
+  for (int d = 1; d < 32; d <<= 1) {
+    const i64 o = __shfl_up_sync(0xffffffffu, inc, d);
+    if (lane >= d) inc += o;
   }
+  if (lane == 31) s_s[wid] = inc;
+  __syncthreads();
+  i64 pre = 0, tot = 0;
+  for (int w = 0; w < NT / 32; ++w) { if (w < wid) pre += s_s[w]; tot += s_s[w]; }
+  i64 run = pre + inc - v;
+  for (i64 t = t0; t < t1; ++t) {
+    const i64 c = __ldcg(&a.mtile[t]);
+    a.mtile[t] = run;
+    run += c;
+  }
+  if (threadIdx.x == 0) carry = tot;
+  __syncthreads();
   if (threadIdx.x == 0) {
     const i64 nnew = carry;
     a.st[ST_PASS_NEW] = nnew;
