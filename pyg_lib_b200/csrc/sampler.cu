@@ -48,7 +48,7 @@ std::vector<ProfPending> g_prof_pending;
 ProfAcc g_prof_acc[] = {{"sample", 0, 0, 0}, {"count", 0, 0, 0}, {"mark", 0, 0, 0}, {"assign", 0, 0, 0},
                         {"lookup", 0, 0, 0}, {"segment_matmul", 0, 0, 0}, {"grouped_gemm", 0, 0, 0},
                         {"insert", 0, 0, 0}, {"pref", 0, 0, 0}, {"reduce", 0, 0, 0}, {"xbarrier", 0, 0, 0},
-                        {"seed", 0, 0, 0}, {"final", 0, 0, 0}, {"cleanup", 0, 0, 0}, {"export", 0, 0, 0}};
+                        {"seed", 0, 0, 0}, {"final", 0, 0, 0}, {"cleanup", 0, 0, 0}, {"export", 0, 0, 0}, {"rows", 0, 0, 0}};
 constexpr int N_PROF = sizeof(g_prof_acc) / sizeof(g_prof_acc[0]);
 int prof_slot(const char* name) {
   for (int i = 0; i < N_PROF; ++i) if (strcmp(g_prof_acc[i].name, name) == 0) return i;
@@ -153,6 +153,7 @@ struct PassArgs {
   i64* pub_host; i64* pub_zero; i64 pub_serial; int pub_words, pub_o_mt;
   // ---- v2 schedule (sampler_v2.cuh): packed 32-bit table of the dst type, refs, optional peer-memory sharding
   u64* pk; int pk_bits;            // slot = node id << 32 | value
+  u64* pk_main; int pk_main_bits;  // sharded seeds: `pk` is the replicated seed scratch table, ids go into this one
   u32* fref;                       // ref of every edge of the running pass
   int xw, xr, x_eid64;             // world size (1 = single GPU), rank, wire type of edge ids
   int v2_writeback, o_shard;
@@ -1381,6 +1382,8 @@ struct pygb200_sampler {
   i64 nd_seeds = 0;
   DevBuf eslot, erank, rec, tile_out, tile_func, tile_off, tile_pos, mtile, raw, st, gen;
   DevBuf fref;              // v2, single GPU: ref of every edge of the running pass
+  DevBuf seedpk;            // v2, sharded: scratch table for the replicated dedup of the seeds (all-EMPTY between runs)
+  int seedpk_bits = 0;
   // v2, frontier sharding over peer memory: this rank's exchange region and the peer mappings of the others'
   struct XRegion {
     unsigned char* base = nullptr;
@@ -1500,7 +1503,7 @@ extern "C" int pygb200_sampler_create(pygb200_sampler** out) {
 extern "C" void pygb200_sampler_destroy(pygb200_sampler* s) {
   if (!s) return;
   for (auto& t : s->types) { t.nodes.release(); t.batch.release(); t.slot.release(); t.keys.release(); t.vals.release(); t.pk.release(); }
-  s->fref.release();
+  s->fref.release(); s->seedpk.release();
   for (int q = 0; q < s->x.world; ++q) if (q != s->x.rank && s->x.peer[q]) cudaIpcCloseMemHandle(s->x.peer[q]);
   if (s->x.base) cudaFree(s->x.base);
   for (auto& r : s->rels) { r.row.release(); r.colv.release(); r.eid.release(); }
@@ -1887,8 +1890,8 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
   const int XW = p2p ? shard->world : 1, XR = p2p ? shard->rank : 0;
 
   // ---- results straight into the caller's arrays?  (bounded int64 non-disjoint runs only; the binding is one-shot)
-  bool direct = bound_armed && !synced && !sharded && !nodedup && !idx32 && !disjoint && (int)s->bound.node.size() == T &&
-                (int)s->bound.row.size() == R;
+  bool direct = bound_armed && !synced && (!sharded || shard->exchange != nullptr) && !nodedup && !idx32 && !disjoint &&
+                (int)s->bound.node.size() == T && (int)s->bound.row.size() == R;
   for (int t = 0; t < T && direct; ++t) direct = s->bound.node[t] != nullptr && s->bound.ncap[t] >= node_cap[t];
   for (int r = 0; r < R && direct; ++r)
     direct = s->bound.row[r] != nullptr && s->bound.col[r] != nullptr && s->bound.ecap[r] >= rel_cap[r];
@@ -1926,6 +1929,7 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
       PYGB_CUDA(cudaMemsetAsync(tb.vals.p, 0xff, tb.tcap * 8, st));
     }
     for (auto& tb : s->types) if (tb.pk_bits) PYGB_CUDA(cudaMemsetAsync(tb.pk.p, 0xff, (size_t)8 << tb.pk_bits, st));
+    if (s->seedpk_bits) PYGB_CUDA(cudaMemsetAsync(s->seedpk.p, 0xff, (size_t)8 << s->seedpk_bits, st));
     s->mt_valid = false;
     s->st_dev_words = 0;
   }
@@ -1941,8 +1945,16 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
     for (int r = 0; r < R; ++r) if (int e = ensure_rel(s, r, rel_cap[r], 0, st)) return e;
     if (int e = ensure_frontier_scratch(s, max_F, st)) return e;
     if (int e = ensure_edge_scratch(s, max_E, st)) return e;
-    if (p2p) { if (int e = ensure_xregion(s, max_E, shard, st)) return e; }
-    else if (int e = s->fref.ensure((size_t)max_E * 4, 0, st)) return e;
+    if (p2p) {
+      if (int e = ensure_xregion(s, max_E, shard, st)) return e;
+      int bits = 10;
+      while ((1ull << bits) < 2 * (u64)std::max<i64>(total_seeds, 1)) ++bits;
+      if (bits > s->seedpk_bits) {
+        if (int e = s->seedpk.ensure((size_t)8 << bits, 0, st)) return e;
+        PYGB_CUDA(cudaMemsetAsync(s->seedpk.p, 0xff, (size_t)8 << bits, st));
+        s->seedpk_bits = bits;
+      }
+    } else if (int e = s->fref.ensure((size_t)max_E * 4, 0, st)) return e;
   } else if (!synced) {
     for (int t = 0; t < T; ++t) {
       if (int e = ensure_type(s, t, node_cap[t], 0, disjoint, st)) return e;
@@ -2179,13 +2191,26 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
     }
     if (v2) {
       if (n_seeds[t] == 0) continue;   // the zeroed state already says "empty list, empty slice"
+      if (p2p) { a.pk_main = a.pk; a.pk_main_bits = a.pk_bits; a.pk = s->seedpk.as<u64>(); a.pk_bits = s->seedpk_bits; }
       const int g = grid_for(n_seeds[t], NT, s->sm_count);
       void* tks = prof_begin(st);
       if (idx32) launch_pdl(k_v2_seed<int32_t>, g, NT, st, a, (const int32_t*)seeds[t], (i64)n_seeds[t]);
       else launch_pdl(k_v2_seed<int64_t>, g, NT, st, a, (const int64_t*)seeds[t], (i64)n_seeds[t]);
       prof_end(tks, "seed", st, n_seeds[t]);
       PYGB_LAUNCH_CHECK();
-      if (int e = v2_ids(a, n_seeds[t])) return e;
+      if (p2p) {
+        // seeds: every rank dedups ALL of them in a scratch table of its own (65 k CAS, L2-resident) — no exchange, no
+        // barrier; only the ids of the seeds a rank owns go into its partition of the real table (k_v2_assign)
+        tks = prof_begin(st);
+        launch_pdl(k_v2_mark<true>, grid_for(n_seeds[t], ETILE, s->sm_count), NT, st, a);
+        prof_end(tks, "mark", st, n_seeds[t]);
+        PYGB_LAUNCH_CHECK();
+        tks = prof_begin(st);
+        launch_pdl(k_v2_assign<true>, grid_for(n_seeds[t], 4 * NT, s->sm_count), NT, st, a);
+        prof_end(tks, "assign", st, n_seeds[t]);
+        PYGB_LAUNCH_CHECK();
+        PYGB_CUDA(cudaMemsetAsync(s->seedpk.p, 0xff, (size_t)8 << s->seedpk_bits, st));   // scratch table clean for the next run
+      } else if (int e = v2_ids(a, n_seeds[t])) return e;
       k_seed_end<<<1, 1, 0, st>>>(dst, t, L, lay.o_list, lay.o_begin, lay.o_end, lay.o_nph);
       PYGB_LAUNCH_CHECK();
       continue;
@@ -2328,17 +2353,23 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
               a.v2_writeback = rels[r2].dst_type == dst_t && num_neighbors[(size_t)r2 * L + h2] != 0 &&
                                fb[(size_t)rels[r2].src_type * (L + 1) + h2] != 0 && eb[(size_t)r2 * L + h2] != 0;
           a.group = sample_group_lanes(k);
-          const int gs = grid_for(Fb, sample_nodes_per_block(a.group), s->sm_count);
+          const int gs = grid_for(p2p ? ceil_div(Fb, XW) + 1 : Fb, sample_nodes_per_block(a.group), s->sm_count);
           void* tk = prof_begin(st);
           if (p2p) {
             k_shard_bounds<<<1, 128, 0, st>>>(a, XW, lay.o_shard);   // position slices of the ref reduction
             PYGB_LAUNCH_CHECK();
             if (idx32) launch_pdl(k_v2_sample<int32_t, true>, gs, NT, st, a); else launch_pdl(k_v2_sample<int64_t, true>, gs, NT, st, a);
+            prof_end(tk, "sample", st, Eb);
+            PYGB_LAUNCH_CHECK();
+            tk = prof_begin(st);
+            launch_pdl(k_v2_rows, grid_for(Fb, NT, s->sm_count), NT, st, a);   // (overlaps the tail of the peer stores)
+            prof_end(tk, "rows", st, Eb);
+            PYGB_LAUNCH_CHECK();
           } else {
             if (idx32) launch_pdl(k_v2_sample<int32_t, false>, gs, NT, st, a); else launch_pdl(k_v2_sample<int64_t, false>, gs, NT, st, a);
+            prof_end(tk, "sample", st, Eb);
+            PYGB_LAUNCH_CHECK();
           }
-          prof_end(tk, "sample", st, Eb);
-          PYGB_LAUNCH_CHECK();
           if (p2p) {
             if (int e = xbarrier(a)) return e;   // everybody's (dst, edge id) have arrived
             void* tki = prof_begin(st);

@@ -78,26 +78,41 @@ __global__ void k_xbarrier(const PassArgs a, u64 epoch, u64 timeout_ns) {
   __threadfence_system();
 }
 
-// ---- seeds: list them; the owner of a seed inserts it at position i (first-occurrence order == seed order)
+// ---- seeds: list them and insert them at position i (first-occurrence order == seed order)
 template <typename idx_t>
 __global__ void __launch_bounds__(NT) k_v2_seed(const PassArgs a, const idx_t* __restrict__ seeds, i64 n) {
   pdl_enter(TL_SEED);
   for (i64 i = (i64)blockIdx.x * NT + threadIdx.x; i < n; i += (i64)gridDim.x * NT) {
     const i64 v = (i64)seeds[i];
     a.dst_nodes[i] = v;
-    const u32 key = (u32)v;
-    const bool own = a.xw == 1 || v2_owner(key, a.xw) == a.xr;
-    a.eslot[i] = own ? v2_insert(a.pk, a.pk_bits, key, (u32)i) : NO_SLOT;
+    // (sharded: `pk` is this rank's scratch table and takes ALL seeds — see k_v2_assign)
+    a.eslot[i] = v2_insert(a.pk, a.pk_bits, (u32)v, (u32)i);
   }
-  if (blockIdx.x == 0) {
-    if (threadIdx.x == 0) { a.st[ST_PASS_E] = n; a.st[ST_PASS_BASE] = 0; }
-    if (a.xw > 1 && threadIdx.x <= a.xw) a.st[a.o_shard + threadIdx.x] = (i64)((__int128)n * threadIdx.x / a.xw);   // position slices
+  if (blockIdx.x == 0 && threadIdx.x == 0) { a.st[ST_PASS_E] = n; a.st[ST_PASS_BASE] = 0; }
+}
+
+// ---- sharded: the row (source-node index) of EVERY edge of the pass, one thread per frontier node — replicated on
+// all ranks and cheap (F records in, E coalescable 8-byte stores out).  It used to ride inside the sampling kernel as
+// "rows only" iterations of the node groups, 52 dependent iterations per group at 8 ranks: 176 us where the draws
+// themselves need 25 (bench r2h, kernel_ms_per_call).
+__global__ void __launch_bounds__(NT) k_v2_rows(const PassArgs a) {
+  pdl_enter();
+  const i64 F = a.st[ST_PASS_F];
+  const i64 begin = a.st[a.o_src_begin];
+  const i64 pbase = a.st[ST_PASS_BASE];
+  for (i64 i = (i64)blockIdx.x * NT + threadIdx.x; i < F; i += (i64)gridDim.x * NT) {
+    const uint4 ra = __ldg(reinterpret_cast<const uint4*>(a.rec + i));   // {rs lo, rs hi, deg, loc_off}
+    i64 n_out, n16, n32, n64;
+    classify((i64)ra.z, a.fanout, a.replace, &n_out, &n16, &n32, &n64);
+    i64* dst = a.row + pbase + __ldg(&a.tile_off[i / NT]) + ra.w;
+    const i64 src_pos = begin + i;
+    for (i64 j = 0; j < n_out; ++j) dst[j] = src_pos;
   }
 }
 
 // ---- one pass's sampling.  SH = false: draw, gather, rows / edge ids / global dst into the result arrays, insert.
-// SH = true: every node writes its rows (cheap, replicated); a node of this rank's slice draws, gathers and stores
-// (dst : u32, edge id : u32 | u64) at the edge's flat position into EVERY rank's exchange region.
+// SH = true: the nodes of this rank's frontier slice draw, gather and store (dst : u32, edge id : u32 | u64) at the
+// edge's flat position into EVERY rank's exchange region (rows: k_v2_rows).
 template <typename idx_t, bool SH>
 __global__ void __launch_bounds__(NT, SAMPLE_MIN_BLOCKS) k_v2_sample(const PassArgs a) {
   pdl_enter(TL_SAMPLE);
@@ -112,25 +127,19 @@ __global__ void __launch_bounds__(NT, SAMPLE_MIN_BLOCKS) k_v2_sample(const PassA
   const i64 own_lo = SH ? (i64)((__int128)F * a.xr / a.xw) : 0;
   const i64 own_hi = SH ? (i64)((__int128)F * (a.xr + 1) / a.xw) : F;
   if (gi >= per_warp) return;   // (lanes beyond the last whole group of the warp)
-  for (i64 i = (i64)blockIdx.x * npb + (threadIdx.x >> 5) * per_warp + gi; i < F; i += (i64)gridDim.x * npb) {
+  for (i64 i = own_lo + (i64)blockIdx.x * npb + (threadIdx.x >> 5) * per_warp + gi; i < own_hi; i += (i64)gridDim.x * npb) {
     const NodeRec r = a.rec[i];
     const i64 tile = i / NT;
     const i64 off = a.tile_off[tile] + r.loc_off;    // pass-local flat position of the node's first edge
     const i64 src_pos = begin + i;                   // local id of the source node (neighbor_kernel.cpp:453)
-    if (SH && (i < own_lo || i >= own_hi)) {         // somebody else's node: rows only
-      i64 n_out, n16, n32, n64;
-      classify((i64)r.deg, a.fanout, a.replace, &n_out, &n16, &n32, &n64);
-      for (i64 j = gl; j < n_out; j += g) a.row[pbase + off + j] = src_pos;
-      continue;
-    }
     const i64 tpos = a.tile_pos[tile];
     const int ph = (int)(tpos & 3);
     const u32 pfv = ph == 0 ? r.pf[0] : (ph == 1 ? r.pf[1] : (ph == 2 ? r.pf[2] : r.pf[3]));
     auto emit = [&](i64 j, i64 e) {
       const i64 p = off + j;
       const i64 d = (i64)col[e];
-      a.row[pbase + p] = src_pos;
       if (!SH) {
+        a.row[pbase + p] = src_pos;
         a.eid[pbase + p] = e;
         a.colv[pbase + p] = d;   // global id until k_v2_assign replaces it with the local id
         a.eslot[p] = v2_insert(a.pk, a.pk_bits, (u32)d, (u32)p);
@@ -376,8 +385,21 @@ __global__ void __launch_bounds__(NT) k_v2_assign(const PassArgs a) {
         const i64 p = base + j * NT + threadIdx.x;
         if (p >= E) break;
         const bool first = r[j] == (V2_POS | (u32)p);
-        const u32 s = a.eslot[p];
-        if (first && s != NO_SLOT) a.pk[s] = ((u64)(u32)a.dst_nodes[p] << 32) | (u64)v2_rank_of(a, (u32)p);
+        u32 s = a.eslot[p];
+        if (first && a.pk_main == nullptr) {
+          a.pk[s] = ((u64)(u32)a.dst_nodes[p] << 32) | (u64)v2_rank_of(a, (u32)p);
+        } else if (first) {
+          // sharded: the dedup ran in the scratch table; the id of a seed this rank owns goes into its partition of the
+          // real table (empty of this key: first occurrences are distinct), the others leave no slot to clean up
+          const u32 key = (u32)a.dst_nodes[p];
+          s = NO_SLOT;
+          if (v2_owner(key, a.xw) == a.xr) {
+            const u64 mask = (1ull << a.pk_main_bits) - 1, mine = ((u64)key << 32) | (u64)v2_rank_of(a, (u32)p);
+            u64 sl = ((u64)key * 0x9E3779B97F4A7C15ull) >> (64 - a.pk_main_bits);
+            while (atomicCAS(&a.pk_main[sl], EMPTY, mine) != EMPTY) sl = (sl + 1) & mask;
+            s = (u32)sl;
+          }
+        }
         a.dst_slot[p] = first ? s : NO_SLOT;
       }
       continue;
