@@ -63,7 +63,8 @@ namespace {
 
 struct Problem {       // C[n,m] = A[n,k] @ B[k,m] (+ bias[m]);  element strides
   const void* a; const void* b; void* c; const void* bias;
-  float* acc;          // non-null: this problem is split over K; partial tiles are atomically added here ([n,m] fp32, ld = m)
+  float* acc;          // non-null: this problem is split over K; K chunk c stores its partial product to acc + c*n*m
+                       // ([n,m] fp32 each, ld = m) and k_finish_split adds the chunks in order (deterministic, no atomics)
   i64 n, k, m;
   i64 sa0, sa1, sb0, sb1, ldc;
   i64 kchunk;          // K extent of one work item (== k when not split)
@@ -93,7 +94,7 @@ __host__ __device__ inline i64 work_items(i64 n, i64 m, i64 k, i64 kchunk) {
 //   mode 1: wgrad     dW[b] = X_b^T @ dY_b                      (n=K, k=len, m=M), split over K chunks
 __global__ void k_build_segments(Problem* probs, i64* total_tiles, const i64* __restrict__ ptr, const char* x,
                                  const char* w, const char* bias, char* out, float* acc, i64 K, i64 M, i64 B, int esize,
-                                 int mode, i64 N, int* err) {
+                                 int mode, i64 N, int* err, i64 wgrad_kchunk) {
   __shared__ i64 s_carry;
   __shared__ i64 s_w[32];
   if (threadIdx.x == 0) s_carry = 0;
@@ -120,8 +121,8 @@ __global__ void k_build_segments(Problem* probs, i64* total_tiles, const i64* __
       } else {
         p.a = x + r0 * K * esize; p.b = w + r0 * M * esize; p.c = out + b * K * M * esize; p.bias = nullptr;
         p.n = K; p.k = len; p.m = M; p.sa0 = 1; p.sa1 = K; p.sb0 = M; p.sb1 = 1; p.ldc = M;
-        p.kchunk = WGRAD_KCHUNK;
-        p.acc = (acc != nullptr && len > WGRAD_KCHUNK) ? acc + b * K * M : nullptr;
+        p.kchunk = wgrad_kchunk;
+        p.acc = (acc != nullptr && len > wgrad_kchunk) ? acc : nullptr;   // (offset by the chunks before this segment, below)
         if (p.acc == nullptr) p.kchunk = len > 0 ? len : 1;   // short segment: one item, direct store
       }
       tiles = work_items(p.n, p.m, p.k, p.kchunk);
@@ -137,7 +138,13 @@ __global__ void k_build_segments(Problem* probs, i64* total_tiles, const i64* __
     i64 pre = 0, tot = 0;
     for (int q = 0; q < (int)(blockDim.x >> 5); ++q) { if (q < wid) pre += s_w[q]; tot += s_w[q]; }
     const i64 c0 = s_carry;
-    if (b < B) { p.tile0 = c0 + pre + inc - tiles; probs[b] = p; }
+    if (b < B) {
+      p.tile0 = c0 + pre + inc - tiles;
+      // weight gradient: every segment has the same K x M tile grid, so tile0 / (tiles per chunk) numbers the K chunks of
+      // all segments consecutively — chunk c of this segment owns the partial buffer tile0 / tiles_mn + c
+      if (p.acc) p.acc += (p.tile0 / (ceil_div(p.n, (i64)BM) * ceil_div(p.m, (i64)BN))) * p.n * p.m;
+      probs[b] = p;
+    }
     __syncthreads();
     if (threadIdx.x == 0) s_carry = c0 + tot;
     __syncthreads();
@@ -237,7 +244,7 @@ __global__ void __launch_bounds__(MM_NT) k_grouped_gemm(const Problem* __restric
         const i64 gc = col0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
         if (gc >= pm) continue;
         if (p.acc) {
-          atomicAdd(&p.acc[gr * p.m + gc], acc[i][j]);
+          p.acc[(kc * pn + gr) * p.m + gc] = acc[i][j];
         } else {
           float v = acc[i][j];
           if (bias) v += to_f<T>(bias[gc]);
@@ -255,9 +262,12 @@ __global__ void k_finish_split(const Problem* __restrict__ probs, i64 P) {
     const Problem p = probs[b];
     if (!p.acc) continue;
     T* C = (T*)p.c;
-    const i64 n = p.n * p.m;
-    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x)
-      C[(i / p.m) * p.ldc + (i % p.m)] = from_f<T>(p.acc[i]);
+    const i64 n = p.n * p.m, chunks = ceil_div(p.k, p.kchunk);
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) {
+      float v = 0.f;
+      for (i64 c = 0; c < chunks; ++c) v += p.acc[c * n + i];   // fixed order: bit-reproducible
+      C[(i / p.m) * p.ldc + (i % p.m)] = from_f<T>(v);
+    }
   }
 }
 
@@ -301,21 +311,28 @@ int segment_generic(const void* x, const i64* ptr_dev, const void* w, const void
   if (B == 0) return PYGB200_OK;
   keep_pool_memory();
   const size_t prob_bytes = (((size_t)B * sizeof(Problem) + 16) + 255) & ~(size_t)255;
-  // weight gradient: fp32 accumulators for segments that are split over K chunks
-  const bool split = mode == 1 && N > WGRAD_KCHUNK;
-  const size_t acc_bytes = split ? (size_t)B * K * M * sizeof(float) : 0;
+  // weight gradient: one fp32 partial [K, M] per K chunk of every split segment (<= N / kchunk + B of them), added up in
+  // order afterwards.  The chunk grows until the partials fit 256 MB; if even B of them do not, segments are not split.
+  i64 kchunk = WGRAD_KCHUNK;
+  bool split = mode == 1 && N > WGRAD_KCHUNK;
+  if (split) {
+    const i64 slots = ((i64)256 << 20) / std::max<i64>(K * M * 4, 1);
+    if (slots < 2 * B + 2) split = false;
+    else kchunk = std::max<i64>(WGRAD_KCHUNK, ceil_div(N, slots - B - 1));
+  }
+  if (!split) kchunk = std::max<i64>(N, 1);
+  const size_t acc_bytes = split ? (size_t)(ceil_div(N, kchunk) + B + 1) * K * M * sizeof(float) : 0;
   AsyncScratch sc;   // (freed on every return path)
   if (int e = sc.alloc(prob_bytes + acc_bytes, st)) return e;
   char* scratch = (char*)sc.p;
   Problem* probs = (Problem*)(scratch + 16);
   i64* total = (i64*)scratch;
   float* acc = split ? (float*)(scratch + prob_bytes) : nullptr;
-  if (split) PYGB_CUDA(cudaMemsetAsync(acc, 0, acc_bytes, st));
   k_build_segments<<<1, 1024, 0, st>>>(probs, total, ptr_dev, (const char*)x, (const char*)w, (const char*)bias,
-                                       (char*)out, acc, K, M, B, esize_of(dtype), mode, N, mm_error_flag_dev());
+                                       (char*)out, acc, K, M, B, esize_of(dtype), mode, N, mm_error_flag_dev(), kchunk);
   PYGB_LAUNCH_CHECK();
   const i64 bound = mode == 0 ? (ceil_div(N, (i64)BM) + B) * ceil_div(M, (i64)BN)
-                              : (ceil_div(N, WGRAD_KCHUNK) + B) * ceil_div(K, (i64)BM) * ceil_div(M, (i64)BN);
+                              : (ceil_div(N, kchunk) + B) * ceil_div(K, (i64)BM) * ceil_div(M, (i64)BN);
   int rc = launch_grouped(probs, B, total, bound, dtype, st);
   if (rc == PYGB200_OK && split) {
     const dim3 grid((unsigned)std::min<i64>(64, ceil_div(K * M, (i64)256)), (unsigned)std::min<i64>(B, 4096));

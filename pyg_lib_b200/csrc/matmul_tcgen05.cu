@@ -425,7 +425,9 @@ constexpr int WG_STAGES = 3;
 
 struct WgradParams {
   const i64* ptr;
-  float* acc;    // [B, K, M] fp32, zero-initialised
+  float* acc;    // [B, K, M] fp32: segments whose row tiles all belong to one CTA are stored here directly
+  float* part;   // [grid, 2, K, M] fp32: a CTA's partial sums of the (at most two) segments it shares with its neighbours
+  int* tile_pre_out;   // [B + 1] tile prefix for k_wgrad_finish (written by block 0)
   i64 N;
   int K, M, B;
   int* err;
@@ -478,6 +480,7 @@ k_segment_wgrad_tc(const __grid_constant__ CUtensorMap map_x, const __grid_const
   const int per_cta = (total_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
   const int t_begin = (int)blockIdx.x * per_cta;
   const int t_end = min(total_tiles, t_begin + per_cta);
+  if (blockIdx.x == 0) for (int b = threadIdx.x; b <= P.B; b += NTHREADS) P.tile_pre_out[b] = tile_pre[b];
   auto seg_of = [&](int t) {
     int lo = 0, hi = P.B - 1;
     while (lo < hi) {
@@ -567,13 +570,22 @@ k_segment_wgrad_tc(const __grid_constant__ CUtensorMap map_x, const __grid_const
         mbar_wait(T_FULL(acc), (t_phase >> acc) & 1u);
         t_phase ^= 1u << acc;
         tc_fence_after();
-        float* dst = P.acc + ((i64)seg * K + r) * M;
+        // Deterministic reduction (the reference's per-segment torch::matmul is deterministic,
+        // ops/autograd/matmul_kernel.cpp:92-107): no atomics.  A segment whose tiles all lie inside this CTA's range
+        // is stored to acc[seg]; otherwise this run is one of the CTA's at most two partial sums — slot 0 if the run
+        // begins at the CTA's first tile, slot 1 if it is a later run that continues past its last tile — and
+        // k_wgrad_finish adds the partials of a segment in CTA order.
+        const bool exclusive = tile_pre[seg] >= t_begin && tile_pre[seg + 1] <= t_end;
+        const int run_begin = max(tile_pre[seg], t_begin);
+        float* dst = exclusive ? P.acc + ((i64)seg * K + r) * M
+                               : P.part + (((i64)blockIdx.x * 2 + (run_begin == t_begin ? 0 : 1)) * K + r) * M;
         for (int c0 = 0; c0 < M; c0 += 32) {
           u32 v[32];
           tc_ld_32x32(tmem_base + (u32)(acc * M + c0) + ((u32)(q * 32) << 16), v);
           tc_wait_ld();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) atomicAdd(dst + c0 + j, __uint_as_float(v[j]));
+          for (int j = 0; j < 8; ++j)
+            reinterpret_cast<uint4*>(dst + c0)[j] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         }
         tc_fence_before();
         mbar_arrive(T_EMPTY(acc));
@@ -590,10 +602,29 @@ k_segment_wgrad_tc(const __grid_constant__ CUtensorMap map_x, const __grid_const
   }
 }
 
+// dW[b] in the storage type: 0 for an empty segment, acc[b] for a segment one CTA had to itself, else the sum of the
+// CTAs' partial sums in CTA order (fixed order => bit-reproducible).  blockIdx.y = segment.
 template <bool BF16>
-__global__ void k_wgrad_finish(const float* __restrict__ acc, void* __restrict__ dw, i64 n) {
-  for (i64 i = ((i64)blockIdx.x * blockDim.x + threadIdx.x) * 2; i < n; i += (i64)gridDim.x * blockDim.x * 2)
-    reinterpret_cast<u32*>(dw)[i >> 1] = pack2<BF16>(acc[i], acc[i + 1]);
+__global__ void k_wgrad_finish(const float* __restrict__ acc, const float* __restrict__ part, const int* __restrict__ tile_pre,
+                               void* __restrict__ dw, int KM, int grid_main) {
+  const int b = blockIdx.y;
+  const int t0 = tile_pre[b], t1 = tile_pre[b + 1], total = tile_pre[gridDim.y];
+  const int per_cta = (total + grid_main - 1) / grid_main;
+  const int c0 = t1 > t0 ? t0 / per_cta : 0, c1 = t1 > t0 ? (t1 - 1) / per_cta : -1;
+  u32* out = reinterpret_cast<u32*>(dw) + (i64)b * (KM / 2);
+  for (int i = (blockIdx.x * blockDim.x + threadIdx.x) * 2; i < KM; i += gridDim.x * blockDim.x * 2) {
+    float2 v = make_float2(0.f, 0.f);
+    if (c1 == c0) {
+      v = *reinterpret_cast<const float2*>(acc + (i64)b * KM + i);
+    } else {
+      for (int c = c0; c <= c1; ++c) {
+        const int slot = t0 <= c * per_cta ? 0 : 1;
+        const float2 p = *reinterpret_cast<const float2*>(part + ((i64)c * 2 + slot) * KM + i);
+        v.x += p.x; v.y += p.y;
+      }
+    }
+    out[i >> 1] = pack2<BF16>(v.x, v.y);
+  }
 }
 
 size_t wgrad_smem(i64 K, i64 M, i64 B) {
@@ -966,18 +997,19 @@ int segment_wgrad_tcgen05(const void* x, const i64* ptr_dev, const void* dy, voi
   CUtensorMap mx, my;
   if (int e = make_map(&mx, x, N, K, TM, bf16)) return e;
   if (int e = make_map(&my, dy, N, M, TM, bf16)) return e;
-  const size_t acc_bytes = (size_t)B * K * M * sizeof(float);
-  AsyncScratch sc;   // (freed on every return path)
-  if (int e = sc.alloc(acc_bytes, st)) return e;
-  float* acc = (float*)sc.p;
-  PYGB_CUDA(cudaMemsetAsync(acc, 0, acc_bytes, st));
-  WgradParams P;
-  P.ptr = ptr_dev; P.acc = acc; P.N = N; P.K = (int)K; P.M = (int)M; P.B = (int)B; P.err = mm_error_flag_dev();
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const i64 max_tiles = N / TM + B;
   const int grid = (int)(max_tiles < sms ? (max_tiles < 1 ? 1 : max_tiles) : sms);
+  // scratch: acc [B,K,M] | part [grid,2,K,M] | tile prefix [B+1]   (nothing needs zeroing: every word that is read was stored)
+  const size_t acc_bytes = (size_t)B * K * M * sizeof(float), part_bytes = (size_t)grid * 2 * K * M * sizeof(float);
+  AsyncScratch sc;   // (freed on every return path)
+  if (int e = sc.alloc(acc_bytes + part_bytes + ((size_t)B + 1) * sizeof(int), st)) return e;
+  float* acc = (float*)sc.p;
+  WgradParams P;
+  P.ptr = ptr_dev; P.acc = acc; P.part = acc + (size_t)B * K * M; P.tile_pre_out = reinterpret_cast<int*>(P.part + (size_t)grid * 2 * K * M);
+  P.N = N; P.K = (int)K; P.M = (int)M; P.B = (int)B; P.err = mm_error_flag_dev();
   const size_t smem = wgrad_smem(K, M, B);
   void* tk = prof_begin(st);
   if (bf16) {
@@ -989,10 +1021,10 @@ int segment_wgrad_tcgen05(const void* x, const i64* ptr_dev, const void* dy, voi
   }
   prof_end(tk, "segment_matmul", st, N);
   PYGB_LAUNCH_CHECK();
-  const i64 n = B * K * M;
-  const int fg = (int)std::min<i64>((n / 2 + 255) / 256, (i64)sms * 8);
-  if (bf16) k_wgrad_finish<true><<<fg, 256, 0, st>>>(acc, dw, n);
-  else k_wgrad_finish<false><<<fg, 256, 0, st>>>(acc, dw, n);
+  const int KM = (int)(K * M);
+  const dim3 fgrid((unsigned)std::min<i64>((KM / 2 + 255) / 256, 64), (unsigned)B);
+  if (bf16) k_wgrad_finish<true><<<fgrid, 256, 0, st>>>(acc, P.part, P.tile_pre_out, dw, KM, grid);
+  else k_wgrad_finish<false><<<fgrid, 256, 0, st>>>(acc, P.part, P.tile_pre_out, dw, KM, grid);
   PYGB_LAUNCH_CHECK();
   return PYGB200_OK;
 }

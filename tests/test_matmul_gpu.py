@@ -174,6 +174,9 @@ def test_wgrad_tcgen05(lib, dtype, M):
     dw = torch.ops.pyg.segment_matmul_wgrad(x.to(DEV), ptr.to(DEV), gy.to(DEV)).float().cpu()
     ref = torch.stack([x[ptr[i]:ptr[i + 1]].float().t() @ gy[ptr[i]:ptr[i + 1]].float() for i in range(B)])
     assert dw.shape == (B, K, M)
+    # deterministic: segments that span several CTAs are reduced in a fixed order, no fp32 atomics
+    for _ in range(3):
+        assert torch.equal(dw, torch.ops.pyg.segment_matmul_wgrad(x.to(DEV), ptr.to(DEV), gy.to(DEV)).float().cpu())
     for i in range(B):
         if lens[i] == 0:
             assert torch.count_nonzero(dw[i]) == 0
@@ -315,3 +318,23 @@ def test_segment_matmul_invalid_ptr_is_reported(lib):
     b = torch.randn(2, 128, device=DEV).bfloat16()
     out = lib.ops.segment_matmul(x[:, :0], torch.tensor([0, 100, 300]), w[:, :0], bias=b)
     assert torch.equal(out[:100], b[0].expand(100, 128)) and torch.equal(out[100:], b[1].expand(200, 128))
+
+
+@pytest.mark.parametrize('dtype,K,M', [(torch.float32, 48, 40), (torch.float32, 128, 128), (torch.bfloat16, 96, 72)])
+def test_wgrad_split_k_is_deterministic(lib, dtype, K, M):
+    """The SIMT weight gradient splits long segments over K chunks; the chunks' partial products are added in a fixed
+    order (no fp32 atomics), so repeated calls are bit-identical like the reference's per-segment torch::matmul
+    (ops/autograd/matmul_kernel.cpp:92-107) — and still correct."""
+    g = torch.Generator().manual_seed(3)
+    lens = [0, 5000, 1, 2049, 30000, 2048, 700]
+    ptr = torch.tensor([0] + lens).cumsum(0)
+    N, B = int(ptr[-1]), len(lens)
+    x = torch.randn(N, K, generator=g).to(dtype).to(DEV)
+    gy = torch.randn(N, M, generator=g).to(dtype).to(DEV)
+    dw = torch.ops.pyg.segment_matmul_wgrad(x, ptr.to(DEV), gy)
+    for _ in range(3):
+        assert torch.equal(dw, torch.ops.pyg.segment_matmul_wgrad(x, ptr.to(DEV), gy))
+    ref = torch.stack([x[ptr[i]:ptr[i + 1]].double().t() @ gy[ptr[i]:ptr[i + 1]].double() for i in range(B)])
+    tol = 1e-5 if dtype == torch.float32 else 4e-3
+    assert (dw.double() - ref).norm() <= tol * ref.norm()
+    assert torch.count_nonzero(dw[0]) == 0
