@@ -54,6 +54,8 @@ struct GProb {
   int a_mn, b_k;               // operand stored transposed
   int c_vec;                   // rows of C are 16-byte aligned
   int tile0, tiles_n;          // first flat tile of the problem; number of column tiles
+  int ksplit, ksteps_chunk;    // split-K: number of K chunks (1 = none) and K steps (of 64) per chunk
+  float* part;                 // split-K: [ksplit][n, m] fp32 partial products, added in chunk order by k_gt_finish
 };
 
 __device__ __forceinline__ void tma_load_3d(u32 dst, const CUtensorMap* map, int c0, int c1, int c2, u32 bar) {
@@ -68,15 +70,16 @@ __device__ __forceinline__ void fence_tensormap(const CUtensorMap* map) {
   asm volatile("fence.proxy.tensormap::generic.acquire.sys [%0], 128;" ::"l"(map) : "memory");
 }
 
-struct TileRef { int p, i, j; };
+struct TileRef { int p, i, j, kc; };
 __device__ __forceinline__ TileRef find_tile(const GProb* __restrict__ probs, int P, int t) {
   int lo = 0, hi = P - 1;
   while (lo < hi) {   // largest p with tile0 <= t (empty problems share their successor's tile0 and are skipped)
     const int mid = (lo + hi + 1) >> 1;
     if (probs[mid].tile0 <= t) lo = mid; else hi = mid - 1;
   }
-  const int local = t - probs[lo].tile0, tn = probs[lo].tiles_n;
-  return {lo, local / tn, local % tn};
+  const int local = t - probs[lo].tile0, tn = probs[lo].tiles_n, tm = (probs[lo].n + GT_TM - 1) / GT_TM;
+  const int mn = local % (tm * tn);   // K chunks outermost: the chunks of one output tile run on different CTAs
+  return {lo, mn / tn, mn % tn, local / (tm * tn)};
 }
 
 template <bool BF16>
@@ -121,8 +124,8 @@ __global__ void __launch_bounds__(GT_NT, 1) k_grouped_tc(const GProb* __restrict
         const GProb& pb = probs[tr.p];
         if (tr.p != last_p) { fence_tensormap(pb.map_a); fence_tensormap(pb.map_b); last_p = tr.p; }
         const int cols = min(GT_BN, pb.m - tr.j * GT_BN), groups = (cols + 63) >> 6;
-        const int ksteps = (pb.k + GT_BK - 1) / GT_BK;
-        for (int ks = 0; ks < ksteps; ++ks) {
+        const int ks0 = tr.kc * pb.ksteps_chunk, ks1 = min((pb.k + GT_BK - 1) / GT_BK, ks0 + pb.ksteps_chunk);
+        for (int ks = ks0; ks < ks1; ++ks) {
           mbar_wait(EMPTY(stage), phase ^ 1);
           const u32 a_dst = base + stage * GT_STAGE_BYTES, b_dst = a_dst + GT_A_BYTES;
           mbar_expect_tx(FULL(stage), GT_A_BYTES + groups * GT_B_GROUP);
@@ -153,10 +156,10 @@ __global__ void __launch_bounds__(GT_NT, 1) k_grouped_tc(const GProb* __restrict
       // D = f32 (bit 4), A/B format (bits 7-9 / 10-12), A major (bit 15), B major (bit 16; 1 = MN-major), N >> 3, M >> 4
       const u32 idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((u32)(pb.a_mn ? 1 : 0) << 15) | ((u32)(pb.b_k ? 0 : 1) << 16) |
                         ((un >> 3) << 17) | ((u32)(GT_TM >> 4) << 24);
-      const int ksteps = (pb.k + GT_BK - 1) / GT_BK;
+      const int ks0 = tr.kc * pb.ksteps_chunk, ksteps = min((pb.k + GT_BK - 1) / GT_BK, ks0 + pb.ksteps_chunk);
       mbar_wait(T_EMPTY(acc), ((t_phase >> acc) & 1u) ^ 1u);
       const u32 d_tmem = tmem_base + (u32)(acc * GT_BN);
-      for (int ks = 0; ks < ksteps; ++ks) {
+      for (int ks = ks0; ks < ksteps; ++ks) {
         mbar_wait(FULL(stage), phase);
         tc_fence_after();
         if (lane == 0) {
@@ -165,7 +168,7 @@ __global__ void __launch_bounds__(GT_NT, 1) k_grouped_tc(const GProb* __restrict
           for (int kk = 0; kk < kk_n; ++kk) {
             const u64 adesc = pb.a_mn ? make_desc(a_base + kk * 2048, 8192, 1024) : make_desc(a_base + kk * 32, 16, 1024);
             const u64 bdesc = pb.b_k ? make_desc(b_base + kk * 32, 16, 1024) : make_desc(b_base + kk * 2048, GT_B_GROUP, 1024);
-            tc_mma_f16(d_tmem, adesc, bdesc, idesc, (ks > 0 || kk > 0) ? 1u : 0u);
+            tc_mma_f16(d_tmem, adesc, bdesc, idesc, (ks > ks0 || kk > 0) ? 1u : 0u);
           }
           tc_commit(EMPTY(stage));
           if (ks == ksteps - 1) tc_commit(T_FULL(acc));
@@ -197,6 +200,17 @@ __global__ void __launch_bounds__(GT_NT, 1) k_grouped_tc(const GProb* __restrict
         tc_wait_ld();
         if (!row_ok) continue;
         const int nc = min(32, cols - c);
+        if (pb.ksplit > 1) {   // fp32 partial of this K chunk; bias / rounding happen in k_gt_finish
+          float* dst = pb.part + ((i64)tr.kc * pb.n + grow) * pb.m + col0 + c;
+          if (nc == 32 && (pb.m & 3) == 0) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) reinterpret_cast<uint4*>(dst)[j] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (j < nc) dst[j] = __uint_as_float(v[j]);
+          }
+          continue;
+        }
         if (pb.bias) {
 #pragma unroll
           for (int j = 0; j < 32; ++j)
@@ -256,7 +270,7 @@ __global__ void k_gt_build_segments(GProb* probs, int* total, const i64* __restr
       const i64 r0 = ptr[b], len = ptr[b + 1] - r0;
       p.map_a = map_a; p.map_b = map_b; p.c = out + r0 * M * 2; p.bias = bias ? bias + (i64)b * M * 2 : nullptr;
       p.ldc = M; p.n = (int)len; p.k = K; p.m = M; p.a_row0 = (int)r0; p.b_z = b; p.a_mn = 0; p.b_k = 0; p.c_vec = c_vec;
-      p.tiles_n = tiles_n;
+      p.tiles_n = tiles_n; p.ksplit = 1; p.ksteps_chunk = (K + GT_BK - 1) / GT_BK; p.part = nullptr;
       tiles = (int)((len + GT_TM - 1) / GT_TM) * tiles_n;
     }
     int inc = tiles;
@@ -276,6 +290,23 @@ __global__ void k_gt_build_segments(GProb* probs, int* total, const i64* __restr
     __syncthreads();
   }
   if (threadIdx.x == 0) *total = s_carry;
+}
+
+// split-K epilogue: C = sum over the K chunks' partials, in chunk order (bit-reproducible), rounded to the storage type
+template <bool BF16>
+__global__ void k_gt_finish(const GProb* __restrict__ probs, int P) {
+  for (int b = blockIdx.y; b < P; b += gridDim.y) {
+    const GProb pb = probs[b];
+    if (pb.ksplit <= 1) continue;
+    const i64 nm = (i64)pb.n * pb.m;
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < nm; i += (i64)gridDim.x * blockDim.x) {
+      float v = 0.f;
+      for (int c = 0; c < pb.ksplit; ++c) v += pb.part[(i64)c * nm + i];
+      const i64 r = i / pb.m, col = i - r * pb.m;
+      if (pb.bias) v += ld_bias<BF16>(pb.bias, col);
+      reinterpret_cast<unsigned short*>(pb.c)[r * pb.ldc + col] = (unsigned short)(pack2<BF16>(v, 0.f) & 0xffffu);
+    }
+  }
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -340,7 +371,8 @@ bool grouped_tc_supported(const pygb200_gemm_problem* ps, i64 count, int dtype) 
   for (i64 i = 0; i < count; ++i) {
     const auto& q = ps[i];
     if (q.n == 0 || q.m == 0) continue;
-    if (q.k < 1 || q.n >= ((i64)1 << 31) || q.k >= ((i64)1 << 31) || q.m >= ((i64)1 << 31)) return false;
+    if (q.n >= ((i64)1 << 31) || q.k >= ((i64)1 << 31) || q.m >= ((i64)1 << 31)) return false;
+    if (q.k == 0) continue;   // empty contraction: the output is zeroed by a memset, no tile is scheduled
     if (!al16(q.a) || !al16(q.b) || q.lda % 8 != 0 || q.ldb % 8 != 0) return false;
     // the extent along the contiguous dimension must fit the pitch
     if (q.lda < (q.a_colmajor ? q.n : q.k) || q.ldb < (q.b_colmajor ? q.k : q.m) || q.ldc < q.m) return false;
@@ -351,25 +383,51 @@ bool grouped_tc_supported(const pygb200_gemm_problem* ps, i64 count, int dtype) 
 
 int grouped_matmul_tc(const pygb200_gemm_problem* ps, i64 count, int dtype, cudaStream_t st) {
   const bool bf16 = dtype == PYGB200_BF16;
-  // one upload: [tensor maps: 2 per problem | problem list | tile total]
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  // Split-K plan: a weight-gradient-shaped list (few output tiles, very long K: dW = X^T dY of a HeteroDictLinear) would
+  // keep a handful of CTAs busy for thousands of K steps.  When the output tiles do not fill the machine twice, every
+  // problem's K steps are cut into chunks (>= 8 steps = 512 of K each) that become work items of their own; chunk c
+  // stores an fp32 partial and k_gt_finish adds the partials in order.  256 MB of partials at most.
+  i64 base_tiles = 0;
+  for (i64 i = 0; i < count; ++i)
+    if (ps[i].n > 0 && ps[i].m > 0 && ps[i].k > 0) base_tiles += ((ps[i].n + GT_TM - 1) / GT_TM) * ((ps[i].m + GT_BN - 1) / GT_BN);
+  const i64 want = base_tiles > 0 && base_tiles < 2 * (i64)sms ? (2 * (i64)sms + base_tiles - 1) / base_tiles : 1;
+  std::vector<int> ksplit((size_t)count, 1);
+  size_t part_bytes = 0;
+  for (i64 i = 0; i < count && want > 1; ++i) {
+    const auto& q = ps[i];
+    if (q.n <= 0 || q.m <= 0 || q.k <= 0) continue;
+    const i64 ksteps = (q.k + GT_BK - 1) / GT_BK;
+    const i64 sp = std::max<i64>(1, std::min<i64>(want, ksteps / 8));
+    const size_t bytes = (size_t)sp * q.n * q.m * 4;
+    if (sp > 1 && part_bytes + bytes <= ((size_t)256 << 20)) { ksplit[(size_t)i] = (int)sp; part_bytes += (bytes + 255) & ~(size_t)255; }
+  }
+  // one upload: [tensor maps: 2 per problem | problem list | tile total]; partials behind it
   const size_t map_bytes = (size_t)count * 2 * sizeof(CUtensorMap);
   const size_t prob_off = (map_bytes + 255) & ~(size_t)255, total_off = prob_off + (((size_t)count * sizeof(GProb) + 15) & ~(size_t)15);
+  const size_t part_off = (total_off + 16 + 255) & ~(size_t)255;
   std::vector<unsigned char> h(total_off + 16, 0);
   AsyncScratch sc;   // (freed on every return path)
-  if (int e = sc.alloc(h.size(), st)) return e;
+  if (int e = sc.alloc(part_off + part_bytes, st)) return e;
   unsigned char* dbuf = (unsigned char*)sc.p;
   CUtensorMap* hmaps = reinterpret_cast<CUtensorMap*>(h.data());
   GProb* hp = reinterpret_cast<GProb*>(h.data() + prob_off);
   const CUtensorMap* dmaps = reinterpret_cast<const CUtensorMap*>(dbuf);
   i64 tiles = 0;
+  size_t part_used = 0;
+  bool any_split = false;
   int rc = PYGB200_OK;
   for (i64 i = 0; i < count && rc == PYGB200_OK; ++i) {
     const auto& q = ps[i];
     GProb p;
     memset(&p, 0, sizeof(p));
-    p.tile0 = (int)tiles; p.tiles_n = 1;
+    p.tile0 = (int)tiles; p.tiles_n = 1; p.ksplit = 1; p.ksteps_chunk = 1;
     p.n = (int)q.n; p.k = (int)q.k; p.m = (int)q.m;
-    if (q.n > 0 && q.m > 0) {
+    if (q.n > 0 && q.m > 0 && q.k == 0) {   // empty contraction: zeros
+      if (cudaMemset2DAsync(q.c, (size_t)q.ldc * 2, 0, (size_t)q.m * 2, (size_t)q.n, st) != cudaSuccess) rc = PYGB200_ERR_CUDA;
+    } else if (q.n > 0 && q.m > 0) {
       CUtensorMap ma, mb;
       cuuint64_t d[3], s[2]; cuuint32_t box[3];
       if (!q.a_colmajor) { d[0] = (cuuint64_t)q.k; d[1] = (cuuint64_t)q.n; s[0] = (cuuint64_t)q.lda * 2; box[0] = 64; box[1] = GT_TM; }
@@ -387,16 +445,32 @@ int grouped_matmul_tc(const pygb200_gemm_problem* ps, i64 count, int dtype, cuda
       p.a_mn = q.a_colmajor ? 1 : 0; p.b_k = q.b_colmajor ? 1 : 0;
       p.c_vec = (al16(q.c) && q.ldc % 8 == 0) ? 1 : 0;
       p.tiles_n = (int)((q.m + GT_BN - 1) / GT_BN);
-      tiles += ((q.n + GT_TM - 1) / GT_TM) * p.tiles_n;
+      const int ksteps = (int)((q.k + GT_BK - 1) / GT_BK);
+      p.ksplit = ksplit[(size_t)i];
+      p.ksteps_chunk = (ksteps + p.ksplit - 1) / p.ksplit;
+      p.ksplit = (ksteps + p.ksteps_chunk - 1) / p.ksteps_chunk;   // (no empty chunk)
+      if (p.ksplit > 1) {
+        p.part = reinterpret_cast<float*>(dbuf + part_off + part_used);
+        part_used += ((size_t)p.ksplit * q.n * q.m * 4 + 255) & ~(size_t)255;
+        any_split = true;
+      }
+      tiles += ((q.n + GT_TM - 1) / GT_TM) * p.tiles_n * p.ksplit;
     }
     hp[i] = p;
   }
-  if (rc == PYGB200_OK) {
+  if (rc == PYGB200_OK && tiles > 0) {
     *reinterpret_cast<int*>(h.data() + total_off) = (int)tiles;
     // pageable source: the copy is staged by the driver before the call returns, so `h` may die at the end of the scope
     if (cudaMemcpyAsync(dbuf, h.data(), h.size(), cudaMemcpyHostToDevice, st) != cudaSuccess) rc = PYGB200_ERR_CUDA;
+    if (rc == PYGB200_OK) rc = gt_launch(reinterpret_cast<const GProb*>(dbuf + prob_off), (int)count, reinterpret_cast<const int*>(dbuf + total_off), tiles, bf16, st);
+    if (rc == PYGB200_OK && any_split) {
+      const dim3 grid(64, (unsigned)std::min<i64>(count, 4096));
+      if (bf16) k_gt_finish<true><<<grid, 256, 0, st>>>(reinterpret_cast<const GProb*>(dbuf + prob_off), (int)count);
+      else k_gt_finish<false><<<grid, 256, 0, st>>>(reinterpret_cast<const GProb*>(dbuf + prob_off), (int)count);
+      count_launch();
+      if (cudaGetLastError() != cudaSuccess) rc = PYGB200_ERR_CUDA;
+    }
   }
-  if (rc == PYGB200_OK) rc = gt_launch(reinterpret_cast<const GProb*>(dbuf + prob_off), (int)count, reinterpret_cast<const int*>(dbuf + total_off), tiles, bf16, st);
   return rc;
 }
 
