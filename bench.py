@@ -483,6 +483,32 @@ def main():
             del rowptr, col
             torch.cuda.empty_cache()
             line['c5_single_gpu'] = c5_leg(a, P, abi, T, torch, dev, 1, 0, peaks, hbm_peak, peak_src, traffic, None)
+            torch.cuda.empty_cache()
+            # ---- configs[3]: hetero_neighbor_sample on the MAG240M-shaped graph at FULL size (3 node types / 6 edge types,
+            # 3.46 G edges = 27.7 GB of col), fan-out [25,15] for every relation, 1024 paper seeds per call.  Parity at 0.1
+            # scale against the 1-thread reference: tests/test_config_parity.py.
+            try:
+                from graphs import mag240m_shaped
+                t0 = time.time()
+                sizes, rp_d, col_d = mag240m_shaped(1.0, device=dev)
+                torch.cuda.synchronize()
+                gen_s = time.time() - t0
+                nn_d = {k: [25, 15] for k in rp_d}
+                permp = torch.randperm(sizes['paper'], device=dev)
+                torch.manual_seed(12345)
+                h_steps = min(a.steps, 100)
+                ms_h, edges_h, _, launches_h, _ = T.run(
+                    lambda i: sum(v.numel() for v in P.sampler.hetero_neighbor_sample(rp_d, col_d, {'paper': permp[i * 1024:(i + 1) * 1024]}, nn_d)[0].values()),
+                    h_steps, a.warmup)
+                line['c4_hetero'] = {'workload': 'hetero_neighbor_sample, MAG240M-shaped (121.7 M papers / 122.4 M authors / 25.7 k institutions, 6 relations, '
+                                                 '3.46 G edges), fanout [25,15] per relation, 1024 paper seeds per call',
+                                     'value': edges_h / (ms_h * 1e-3), 'unit': 'edges/s', 'ms_per_step': ms_h / h_steps, 'steps': h_steps,
+                                     'edges_per_step': edges_h / h_steps, 'gpu_launches_per_step': launches_h / h_steps, 'graph_gen_s': gen_s,
+                                     'graph_bytes': int(sum(v.numel() for v in col_d.values()) * 8)}
+                del rp_d, col_d, permp
+                torch.cuda.empty_cache()
+            except Exception as ex:  # noqa  (e.g. a smaller GPU: the leg is informative, not the headline)
+                line['c4_hetero'] = {'error': str(ex)[:300]}
 
         # ---- CPU baseline: the reference's own CPU path on this box's host cores (bounded sample)
         if not a.no_cpu_baseline:

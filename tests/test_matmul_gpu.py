@@ -259,7 +259,7 @@ def test_grouped_matmul_tensor_cores_forward_backward(lib, dtype):
     inputs = [torch.randn(n, k, generator=g).to(dtype).to(DEV).requires_grad_() for n, k, m in shapes]
     others = [(torch.randn(k, m, generator=g) / k ** 0.5).to(dtype).to(DEV).requires_grad_() for n, k, m in shapes]
     outs, launches = _launch_delta(lib, lambda: lib.ops.grouped_matmul(inputs, others))
-    assert launches == 1, launches     # one grouped launch for all problems (the SIMT fallback would also be 1: check values below)
+    assert launches <= 2, launches     # one grouped launch for all problems (+ the split-K finish when few output tiles carry a long K)
     for (n, k, m), x, w, o in zip(shapes, inputs, others, outs):
         ref = x.detach().float() @ w.detach().float()
         assert o.shape == (n, m) and o.dtype == dtype
