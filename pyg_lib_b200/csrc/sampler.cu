@@ -323,57 +323,82 @@ __device__ __forceinline__ void block_scan_nodes(u32 v, Func4 f, u32* ex_v, Func
 }
 
 // Single-block ordered scan of the frontier tile aggregates: edge offsets and absolute RNG positions.
-// Runs in the last block of k_count.  blockDim.x == NT.  Every thread takes a contiguous chunk of ceil(ntiles / NT)
-// tiles: serial reduction of the chunk, ONE block-wide scan of the NT chunk totals, serial scan of the chunk — a
-// 983 k-node frontier (3840 tiles) used to cost 15 rounds of block-wide scans here, in a section nothing overlaps.
+// Runs in the last block of k_count, a section nothing overlaps (device timeline r2k: 26 us for the 3840 tiles of a
+// 983 k-node frontier when every thread walked its tiles in global memory, 12 us even for 256 tiles).  The aggregates
+// are staged in shared memory with coalesced loads, SCAN_CHUNK tiles per round; a thread scans 4 consecutive staged
+// tiles, one block-wide scan orders the threads.  Uniform advance functions (every pass unless a node has >= 2^16
+// candidates) are plain sums; the general case composes the 4-entry functions in the same order.
+constexpr int SCAN_PER = 4, SCAN_CHUNK = NT * SCAN_PER;   // (5 staged words per tile + k_count's 16 KB RNG window fit 48 KB)
+constexpr int MSCAN_PER = 16, MSCAN_CHUNK = NT * MSCAN_PER;
 __device__ void scan_frontier_tiles(const PassArgs& a, i64 ntiles) {
+  __shared__ u32 s_out[SCAN_CHUNK];
+  __shared__ u32 s_f[4][SCAN_CHUNK];
   __shared__ i64 s_sum[NT / 32];
   __shared__ Func4L s_fun[NT / 32];
+  __shared__ i64 c_off, c_pos;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const i64 per = ceil_div(ntiles, NT);
-  const i64 t0 = (i64)threadIdx.x * per, t1 = t0 + per < ntiles ? t0 + per : ntiles;
-  const i64 cur0 = a.st[ST_CURSOR];
-  i64 v = 0; Func4L f = {{0, 0, 0, 0}};
-  for (i64 t = t0; t < t1; ++t) {
-    v += __ldcg(&a.tile_out[t]);
-    Func4L g;
+  if (threadIdx.x == 0) { c_off = 0; c_pos = a.st[ST_CURSOR]; }
+  for (i64 base = 0; base < ntiles; base += SCAN_CHUNK) {
+    const int n = (int)(ntiles - base < SCAN_CHUNK ? ntiles - base : SCAN_CHUNK);
+    int uni = 1;
+    for (int j = threadIdx.x; j < n; j += NT) {   // coalesced staging
+      s_out[j] = (u32)__ldcg(&a.tile_out[base + j]);
+      const uint4 w = __ldcg(reinterpret_cast<const uint4*>(a.tile_func + 4 * (base + j)));
+      s_f[0][j] = w.x; s_f[1][j] = w.y; s_f[2][j] = w.z; s_f[3][j] = w.w;
+      uni &= w.x == w.y && w.y == w.z && w.z == w.w;
+    }
+    uni = __syncthreads_and(uni);   // (also publishes the staged tiles and c_off / c_pos)
+    const int j0 = threadIdx.x * SCAN_PER, j1 = j0 + SCAN_PER < n ? j0 + SCAN_PER : n;
+    i64 v = 0; Func4L f = {{0, 0, 0, 0}};
+    if (uni) {
+      u64 u = 0;
+      for (int j = j0; j < j1; ++j) { v += s_out[j]; u += s_f[0][j]; }
+      f.d[0] = f.d[1] = f.d[2] = f.d[3] = u;
+    } else {
+      for (int j = j0; j < j1; ++j) {
+        v += s_out[j];
+        Func4L g; g.d[0] = s_f[0][j]; g.d[1] = s_f[1][j]; g.d[2] = s_f[2][j]; g.d[3] = s_f[3][j];
+        f = composeL(f, g);
+      }
+    }
+    i64 iv = v; Func4L iff = f;
 #pragma unroll
-    for (int p = 0; p < 4; ++p) g.d[p] = __ldcg(&a.tile_func[4 * t + p]);
-    f = composeL(f, g);
+    for (int d = 1; d < 32; d <<= 1) {
+      const i64 ov = __shfl_up_sync(0xffffffffu, iv, d);
+      Func4L of;
+#pragma unroll
+      for (int p = 0; p < 4; ++p) of.d[p] = __shfl_up_sync(0xffffffffu, iff.d[p], d);
+      if (lane >= d) { iv += ov; iff = composeL(of, iff); }
+    }
+    if (lane == 31) { s_sum[wid] = iv; s_fun[wid] = iff; }
+    __syncthreads();
+    i64 pv = 0; Func4L pfx = {{0, 0, 0, 0}};
+    for (int w = 0; w < wid; ++w) { pv += s_sum[w]; pfx = composeL(pfx, s_fun[w]); }
+    i64 ev = __shfl_up_sync(0xffffffffu, iv, 1);
+    Func4L ef;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) ef.d[p] = __shfl_up_sync(0xffffffffu, iff.d[p], 1);
+    if (lane == 0) { ev = 0; ef = {{0, 0, 0, 0}}; }
+    const i64 off0 = c_off, pos0 = c_pos;
+    i64 off = off0 + pv + ev;              // edges emitted before this thread's tiles
+    Func4L adv = composeL(pfx, ef);        // RNG advance (per entry phase) of this round's tiles before them
+    for (int j = j0; j < j1; ++j) {
+      a.tile_off[base + j] = off;
+      a.tile_pos[base + j] = pos0 + (i64)sel4(adv, (unsigned)(pos0 & 3));
+      off += s_out[j];
+      Func4L g; g.d[0] = s_f[0][j]; g.d[1] = s_f[1][j]; g.d[2] = s_f[2][j]; g.d[3] = s_f[3][j];
+      adv = composeL(adv, g);
+    }
+    i64 tv = 0; Func4L tf = {{0, 0, 0, 0}};
+    for (int w = 0; w < NT / 32; ++w) { tv += s_sum[w]; tf = composeL(tf, s_fun[w]); }
+    __syncthreads();                        // everybody has read c_off / c_pos and the staged tiles
+    if (threadIdx.x == 0) { c_off = off0 + tv; c_pos = pos0 + (i64)sel4(tf, (unsigned)(pos0 & 3)); }
   }
-  i64 iv = v; Func4L iff = f;
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    const i64 ov = __shfl_up_sync(0xffffffffu, iv, d);
-    Func4L of;
-#pragma unroll
-    for (int p = 0; p < 4; ++p) of.d[p] = __shfl_up_sync(0xffffffffu, iff.d[p], d);
-    if (lane >= d) { iv += ov; iff = composeL(of, iff); }
-  }
-  if (lane == 31) { s_sum[wid] = iv; s_fun[wid] = iff; }
   __syncthreads();
-  i64 pv = 0; Func4L pfx = {{0, 0, 0, 0}};
-  for (int w = 0; w < wid; ++w) { pv += s_sum[w]; pfx = composeL(pfx, s_fun[w]); }
-  i64 ev = __shfl_up_sync(0xffffffffu, iv, 1);
-  Func4L ef;
-#pragma unroll
-  for (int p = 0; p < 4; ++p) ef.d[p] = __shfl_up_sync(0xffffffffu, iff.d[p], 1);
-  if (lane == 0) { ev = 0; ef = {{0, 0, 0, 0}}; }
-  i64 off = pv + ev;                  // edges emitted before this thread's chunk
-  Func4L adv = composeL(pfx, ef);     // RNG advance (per entry phase) before this thread's chunk
-  for (i64 t = t0; t < t1; ++t) {
-    a.tile_off[t] = off;
-    a.tile_pos[t] = cur0 + (i64)sel4(adv, (unsigned)(cur0 & 3));
-    off += __ldcg(&a.tile_out[t]);
-    Func4L g;
-#pragma unroll
-    for (int p = 0; p < 4; ++p) g.d[p] = __ldcg(&a.tile_func[4 * t + p]);
-    adv = composeL(adv, g);
-  }
-  if (threadIdx.x == NT - 1) {        // (the last thread's running values are the totals)
-    const i64 E = off;
+  if (threadIdx.x == 0) {
+    const i64 E = c_off;
     a.st[ST_PASS_E] = E;
-    a.st[ST_CURSOR] = cur0 + (i64)sel4(adv, (unsigned)(cur0 & 3));
+    a.st[ST_CURSOR] = c_pos;
     if (!a.seed_mode) {
       a.st[ST_PASS_BASE] = a.st[a.o_rel_edges];
       a.st[a.o_rel_edges] += E;

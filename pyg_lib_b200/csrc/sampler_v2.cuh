@@ -241,31 +241,36 @@ __global__ void __launch_bounds__(NT) k_v2_reduce(const PassArgs a) {
 // counters of a pass once the per-tile counts of first occurrences are known: ordered exclusive scan of the counts by
 // the calling (last) block, dst list / id counters, end-of-hop bookkeeping (shared with k_mark)
 __device__ void mark_finish(const PassArgs& a, i64 E, i64 ntiles) {
+  // (staged in shared memory like scan_frontier_tiles: coalesced loads, 16 consecutive tiles per thread, one block-wide
+  //  scan per round of 4096 tiles; a tile holds at most 1024 firsts, so the counts fit 32 bits)
+  __shared__ u32 s_cnt[MSCAN_CHUNK];
   __shared__ i64 s_s[NT / 32];
   __shared__ i64 carry;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  // a contiguous chunk of tiles per thread: serial sum, one block-wide scan of the chunk totals, serial exclusive scan
-  const i64 per = ceil_div(ntiles, NT);
-  const i64 t0 = (i64)threadIdx.x * per, t1 = t0 + per < ntiles ? t0 + per : ntiles;
-  i64 v = 0;
-  for (i64 t = t0; t < t1; ++t) v += __ldcg(&a.mtile[t]);
-  i64 inc = v;
+  if (threadIdx.x == 0) carry = 0;
+  for (i64 base = 0; base < ntiles; base += MSCAN_CHUNK) {
+    const int n = (int)(ntiles - base < MSCAN_CHUNK ? ntiles - base : MSCAN_CHUNK);
+    for (int j = threadIdx.x; j < n; j += NT) s_cnt[j] = (u32)__ldcg(&a.mtile[base + j]);
+    __syncthreads();
+    const int j0 = threadIdx.x * MSCAN_PER, j1 = j0 + MSCAN_PER < n ? j0 + MSCAN_PER : n;
+    i64 v = 0;
+    for (int j = j0; j < j1; ++j) v += s_cnt[j];
+    i64 inc = v;
 #pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    const i64 o = __shfl_up_sync(0xffffffffu, inc, d);
-    if (lane >= d) inc += o;
+    for (int d = 1; d < 32; d <<= 1) {
+      const i64 o = __shfl_up_sync(0xffffffffu, inc, d);
+      if (lane >= d) inc += o;
+    }
+    if (lane == 31) s_s[wid] = inc;
+    __syncthreads();
+    i64 pre = 0, tot = 0;
+    for (int w = 0; w < NT / 32; ++w) { if (w < wid) pre += s_s[w]; tot += s_s[w]; }
+    const i64 c0 = carry;
+    i64 run = c0 + pre + inc - v;
+    for (int j = j0; j < j1; ++j) { a.mtile[base + j] = run; run += s_cnt[j]; }
+    __syncthreads();
+    if (threadIdx.x == 0) carry = c0 + tot;
   }
-  if (lane == 31) s_s[wid] = inc;
-  __syncthreads();
-  i64 pre = 0, tot = 0;
-  for (int w = 0; w < NT / 32; ++w) { if (w < wid) pre += s_s[w]; tot += s_s[w]; }
-  i64 run = pre + inc - v;
-  for (i64 t = t0; t < t1; ++t) {
-    const i64 c = __ldcg(&a.mtile[t]);
-    a.mtile[t] = run;
-    run += c;
-  }
-  if (threadIdx.x == 0) carry = tot;
   __syncthreads();
   if (threadIdx.x == 0) {
     const i64 nnew = carry;
