@@ -48,7 +48,7 @@ std::vector<ProfPending> g_prof_pending;
 ProfAcc g_prof_acc[] = {{"sample", 0, 0, 0}, {"count", 0, 0, 0}, {"mark", 0, 0, 0}, {"assign", 0, 0, 0},
                         {"lookup", 0, 0, 0}, {"segment_matmul", 0, 0, 0}, {"grouped_gemm", 0, 0, 0},
                         {"insert", 0, 0, 0}, {"pref", 0, 0, 0}, {"reduce", 0, 0, 0}, {"xbarrier", 0, 0, 0},
-                        {"seed", 0, 0, 0}, {"final", 0, 0, 0}, {"cleanup", 0, 0, 0}, {"export", 0, 0, 0}, {"rows", 0, 0, 0}};
+                        {"seed", 0, 0, 0}, {"final", 0, 0, 0}, {"cleanup", 0, 0, 0}, {"export", 0, 0, 0}, {"scan", 0, 0, 0}};
 constexpr int N_PROF = sizeof(g_prof_acc) / sizeof(g_prof_acc[0]);
 int prof_slot(const char* name) {
   for (int i = 0; i < N_PROF; ++i) if (strcmp(g_prof_acc[i].name, name) == 0) return i;
@@ -158,6 +158,7 @@ struct PassArgs {
   int xw, xr, x_eid64;             // world size (1 = single GPU), rank, wire type of edge ids
   int v2_writeback, o_shard;
   i64 x_off_bar, x_off_dst, x_off_eid, x_off_pref, x_off_fref;   // byte offsets inside an exchange region
+  i64 x_off_row, x_off_tout, x_off_tfunc;                        // sharded count: rows of the edges, per-tile aggregates
   unsigned char* xpeer[16];        // exchange region of every rank (own one included), peer-mapped
 };
 __device__ __forceinline__ i64 ldw(const i64* st, int w, i64 c) { return w >= 0 ? st[w] : c; }
@@ -521,9 +522,16 @@ __device__ __forceinline__ void count_tile(const PassArgs& a, i64 begin, i64 F, 
     a.rec[i] = r;
   }
   if (threadIdx.x == 0) {
-    a.tile_out[tile] = tot_v;
+    if (a.xw > 1 && a.x_off_tout) {   // sharded count (k_v2_count): the aggregate goes to every rank's copy
+      for (int q = 0; q < a.xw; ++q) {
+        reinterpret_cast<i64*>(a.xpeer[q] + a.x_off_tout)[tile] = tot_v;
+        *reinterpret_cast<uint4*>(a.xpeer[q] + a.x_off_tfunc + 16 * tile) = make_uint4(tot_f.d[0], tot_f.d[1], tot_f.d[2], tot_f.d[3]);
+      }
+    } else {
+      a.tile_out[tile] = tot_v;
 #pragma unroll
-    for (int p = 0; p < 4; ++p) a.tile_func[4 * tile + p] = tot_f.d[p];
+      for (int p = 0; p < 4; ++p) a.tile_func[4 * tile + p] = tot_f.d[p];
+    }
   }
 }
 
@@ -544,6 +552,36 @@ __global__ void __launch_bounds__(NT) k_count(const PassArgs a) {
     mt_extend_block<3>(a.raw, a.gen, a.out0 + 256 * rng_blocks_for_units(a.st[ST_CURSOR]), a.raw_cap, a.st, s_win);
     tl_mark_any(TL_COUNT | TL_LAST | TL_END);
   }
+}
+
+// Sharded count (peer-memory frontier sharding): a rank counts only its own tiles of the frontier — tile-aligned
+// slices [T r / W, T (r+1) / W) — and stores their aggregates into every rank's copy; after a cross-GPU barrier
+// k_v2_scan (one block, every rank) turns the full list of aggregates into offsets / RNG positions exactly like the last
+// block of k_count does on one GPU.  The records stay local: only the owner samples a node.
+template <typename idx_t>
+__global__ void __launch_bounds__(NT) k_v2_count(const PassArgs a) {
+  pdl_enter(TL_COUNT);
+  const i64 begin = a.st[a.o_src_begin], end = a.st[a.o_src_end];
+  const i64 F = end - begin;
+  const i64 ntiles = ceil_div(F, NT);
+  const i64 t_lo = (i64)((__int128)ntiles * a.xr / a.xw), t_hi = (i64)((__int128)ntiles * (a.xr + 1) / a.xw);
+  for (i64 tile = t_lo + blockIdx.x; tile < t_hi; tile += gridDim.x) count_tile<idx_t>(a, begin, F, tile);
+  tl_mark(TL_COUNT | TL_END);
+}
+__global__ void __launch_bounds__(NT) k_v2_scan(const PassArgs a) {
+  __shared__ u32 s_win[MT_WIN];
+  pdl_enter();
+  const i64 begin = a.st[a.o_src_begin], end = a.st[a.o_src_end];
+  const i64 F = end - begin;
+  const i64 ntiles = ceil_div(F, NT);
+  if (threadIdx.x == 0) a.st[ST_PASS_F] = F;
+  scan_frontier_tiles(a, ntiles);
+  // position slices of the ref reduction = the edges of each rank's tiles
+  if ((int)threadIdx.x <= a.xw) {
+    const i64 t = (i64)((__int128)ntiles * threadIdx.x / a.xw);
+    a.st[a.o_shard + threadIdx.x] = t < ntiles ? a.tile_off[t] : a.st[ST_PASS_E];
+  }
+  mt_extend_block<3>(a.raw, a.gen, a.out0 + 256 * rng_blocks_for_units(a.st[ST_CURSOR]), a.raw_cap, a.st, s_win);
 }
 
 // Sampling of ONE frontier node by a group of `g` consecutive lanes of a warp (g = min(fan-out, 32): a warp
@@ -1391,8 +1429,11 @@ struct pygb200_sampler {
   int sm_count = 148;
   struct TypeBuf {
     DevBuf nodes, batch, slot, keys, vals;
-    DevBuf pk;          // v2: packed table (node id << 32 | value), all-EMPTY between runs
-    int pk_bits = 0;    // log2 of its capacity (0 = not allocated)
+    // v2: packed tables (node id << 32 | value) and the slot lists that say which entries a run touched, TWO of each:
+    // consecutive runs alternate, so that the reset of run i's table (random 8-byte stores: 144 us per 65,536-seed call on
+    // the papers100M-shaped graph, bench r2l) runs on a side stream beside run i+1 instead of in front of it
+    DevBuf pk[2], vslot[2];
+    int pk_bits[2] = {0, 0};   // log2 of the capacities (0 = not allocated)
     u64 tcap = 0;       // table capacity (slots, power of two); table is all-EMPTY between runs
     i64 n_nodes = 0;    // result of the last run
   };
@@ -1409,6 +1450,10 @@ struct pygb200_sampler {
   DevBuf fref;              // v2, single GPU: ref of every edge of the running pass
   DevBuf seedpk;            // v2, sharded: scratch table for the replicated dedup of the seeds (all-EMPTY between runs)
   int seedpk_bits = 0;
+  int v2_side = 0;          // which of the two packed tables the current / last v2 run uses
+  cudaStream_t clean_stream = nullptr;
+  cudaEvent_t clean_done[2] = {nullptr, nullptr}, final_ev = nullptr;
+  bool clean_pending[2] = {false, false};
   // v2, frontier sharding over peer memory: this rank's exchange region and the peer mappings of the others'
   struct XRegion {
     unsigned char* base = nullptr;
@@ -1418,7 +1463,7 @@ struct pygb200_sampler {
     unsigned char* peer[16] = {nullptr};
     u64 epoch = 0;          // barrier count (flag words only grow)
     u64 passes = 0;         // sharded passes so far: parity picks the (dst, edge id) buffer
-    i64 off_bar = 0, off_dst[2] = {0, 0}, off_eid[2] = {0, 0}, off_pref = 0, off_fref = 0;
+    i64 off_bar = 0, off_dst[2] = {0, 0}, off_eid[2] = {0, 0}, off_row[2] = {0, 0}, off_pref = 0, off_fref = 0, off_tout = 0, off_tfunc = 0;
   } x;
   i64* st_host = nullptr;   // pinned + mapped mirror of the state buffer (k_final writes it directly)
   i64* st_host_dev = nullptr;   // device-side address of st_host
@@ -1461,6 +1506,7 @@ struct pygb200_sampler {
 struct HostTimes {
   bool on = getenv("PYGB200_HOST_TIMING") != nullptr;
   double acc[6] = {0, 0, 0, 0, 0, 0};
+  double sub[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // finer laps inside "setup" (debug)
   long runs = 0;
   long branch[5] = {0, 0, 0, 0, 0};   // stream coverage at run start: known / older event / newer event / extend here / restart
   static double now() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
@@ -1468,6 +1514,9 @@ struct HostTimes {
     if (on && runs)
       fprintf(stderr, "[pygb200 host us/run over %ld runs] setup %.2f  mt+memset %.2f  seeds %.2f  hops+final %.2f  spin %.2f  post %.2f\n",
               runs, acc[0] / runs, acc[1] / runs, acc[2] / runs, acc[3] / runs, acc[4] / runs, acc[5] / runs);
+    if (on && runs)
+      fprintf(stderr, "[pygb200 setup laps us/run] checks+bounds %.2f  schedule %.2f  direct+cleanup %.2f  layout+state %.2f  workspace %.2f\n",
+              sub[0] / runs, sub[1] / runs, sub[2] / runs, sub[3] / runs, sub[4] / runs);
     if (on && runs)
       fprintf(stderr, "[pygb200 mt19937 stream at run start] covered %ld  older event %ld  newer event %ld  extended here %ld  restarted %ld\n",
               branch[0], branch[1], branch[2], branch[3], branch[4]);
@@ -1527,7 +1576,13 @@ extern "C" int pygb200_sampler_create(pygb200_sampler** out) {
 
 extern "C" void pygb200_sampler_destroy(pygb200_sampler* s) {
   if (!s) return;
-  for (auto& t : s->types) { t.nodes.release(); t.batch.release(); t.slot.release(); t.keys.release(); t.vals.release(); t.pk.release(); }
+  if (s->clean_stream) { cudaStreamSynchronize(s->clean_stream); cudaStreamDestroy(s->clean_stream); }
+  for (int i = 0; i < 2; ++i) if (s->clean_done[i]) cudaEventDestroy(s->clean_done[i]);
+  if (s->final_ev) cudaEventDestroy(s->final_ev);
+  for (auto& t : s->types) {
+    t.nodes.release(); t.batch.release(); t.slot.release(); t.keys.release(); t.vals.release();
+    for (int i = 0; i < 2; ++i) { t.pk[i].release(); t.vslot[i].release(); }
+  }
   s->fref.release(); s->seedpk.release();
   for (int q = 0; q < s->x.world; ++q) if (q != s->x.rank && s->x.peer[q]) cudaIpcCloseMemHandle(s->x.peer[q]);
   if (s->x.base) cudaFree(s->x.base);
@@ -1597,15 +1652,16 @@ int ensure_table(pygb200_sampler* s, int t, i64 need_nodes, i64 listed, cudaStre
 }
 
 // v2: packed table of one type with room for `need_nodes` distinct keys at load factor <= 0.5
-int ensure_table_v2(pygb200_sampler* s, int t, i64 need_nodes, cudaStream_t st) {
+int ensure_table_v2(pygb200_sampler* s, int t, int side, i64 need_nodes, i64 list_cap, cudaStream_t st) {
   auto& tb = s->types[t];
+  if (int e = tb.vslot[side].ensure((size_t)std::max<i64>(list_cap, 1) * 4, 0, st)) return e;
   int bits = 10;
   while ((1ull << bits) < 2 * (u64)(need_nodes > 0 ? need_nodes : 1)) ++bits;
-  if (bits <= tb.pk_bits) return PYGB200_OK;
+  if (bits <= tb.pk_bits[side]) return PYGB200_OK;
   PYGB_CHECK(bits <= 32, PYGB200_ERR_UNSUPPORTED, "sampler hash table would exceed 2^32 slots");
-  if (int e = tb.pk.ensure((size_t)8 << bits, 0, st)) return e;
-  PYGB_CUDA(cudaMemsetAsync(tb.pk.p, 0xff, (size_t)8 << bits, st));
-  tb.pk_bits = bits;
+  if (int e = tb.pk[side].ensure((size_t)8 << bits, 0, st)) return e;
+  PYGB_CUDA(cudaMemsetAsync(tb.pk[side].p, 0xff, (size_t)8 << bits, st));
+  tb.pk_bits[side] = bits;
   return PYGB200_OK;
 }
 
@@ -1623,11 +1679,15 @@ int ensure_xregion(pygb200_sampler* s, i64 cap, const pygb200_shard* shard, cuda
   auto al = [](i64 b) { return (b + 255) / 256 * 256; };
   i64 o = 256;
   const i64 off_bar = 0;
-  i64 off_dst[2], off_eid[2];
+  i64 off_dst[2], off_eid[2], off_row[2];
   for (int i = 0; i < 2; ++i) { off_dst[i] = o; o += al(ncap * 4); }
   for (int i = 0; i < 2; ++i) { off_eid[i] = o; o += al(ncap * 8); }
+  for (int i = 0; i < 2; ++i) { off_row[i] = o; o += al(ncap * 4); }
   const i64 off_pref = o; o += al(ncap * 4);
   const i64 off_fref = o; o += al(ncap * 4);
+  const i64 tcap = ncap / NT + 2;   // frontier tiles: a frontier is never longer than a pass's edge bound... (+ the seed list, <= ncap)
+  const i64 off_tout = o; o += al(tcap * 8);
+  const i64 off_tfunc = o; o += al(tcap * 16);
   unsigned char* nb = nullptr;
   PYGB_CUDA(cudaMalloc((void**)&nb, (size_t)o));
   PYGB_CUDA(cudaMemset(nb, 0, 256));
@@ -1641,7 +1701,8 @@ int ensure_xregion(pygb200_sampler* s, i64 cap, const pygb200_shard* shard, cuda
   if (x.base) cudaFree(x.base);
   x.base = nb; x.bytes = (size_t)o; x.cap = ncap; x.world = W; x.rank = shard->rank;
   x.off_bar = off_bar; x.off_dst[0] = off_dst[0]; x.off_dst[1] = off_dst[1]; x.off_eid[0] = off_eid[0]; x.off_eid[1] = off_eid[1];
-  x.off_pref = off_pref; x.off_fref = off_fref;
+  x.off_row[0] = off_row[0]; x.off_row[1] = off_row[1];
+  x.off_pref = off_pref; x.off_fref = off_fref; x.off_tout = off_tout; x.off_tfunc = off_tfunc;
   x.epoch = 0; x.passes = 0;
   for (int q = 0; q < W; ++q) {
     if (q == x.rank) { x.peer[q] = nb; continue; }
@@ -1816,6 +1877,8 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
   s->last_direct = false;
   double ht_last = g_ht.on ? HostTimes::now() : 0;
   auto ht_lap = [&](int seg) { if (g_ht.on) { const double t = HostTimes::now(); g_ht.acc[seg] += t - ht_last; ht_last = t; } };
+  double ht_sub = ht_last;
+  auto sub_lap = [&](int seg) { if (g_ht.on) { const double t = HostTimes::now(); g_ht.sub[seg] += t - ht_sub; ht_sub = t; } };
   i64 total_seeds = 0;
   for (int t = 0; t < T; ++t) {
     PYGB_CHECK(n_seeds[t] >= 0, PYGB200_ERR_ARG, "negative seed count");
@@ -1882,6 +1945,7 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
       PYGB_CHECK(n_seeds[t] == 0 || (temporal->seed_time && temporal->seed_time[t]) || (temporal->node_time && temporal->node_time[t]),
                  PYGB200_ERR_ARG, "Seed time needs to be specified");
   }
+  sub_lap(0);
   const bool sharded = shard != nullptr && shard->world > 1;
   const bool nodedup = (flags & PYGB200_S_NO_DEDUP) != 0;
   if (nodedup) PYGB_CHECK(T == 1 && R == 1 && L == 1 && !sharded, PYGB200_ERR_ARG,
@@ -1914,6 +1978,7 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
                       "peer-memory frontier sharding: homogeneous, non-disjoint, bounded fan-outs, node ids < 2^32-1, world <= 16");
   const int XW = p2p ? shard->world : 1, XR = p2p ? shard->rank : 0;
 
+  sub_lap(1);
   // ---- results straight into the caller's arrays?  (bounded int64 non-disjoint runs only; the binding is one-shot)
   bool direct = bound_armed && !synced && (!sharded || shard->exchange != nullptr) && !nodedup && !idx32 && !disjoint &&
                 (int)s->bound.node.size() == T && (int)s->bound.row.size() == R;
@@ -1929,6 +1994,7 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
     PYGB_LAUNCH_CHECK();
     s->cleanup_pending = false;
   }
+  sub_lap(2);
   if ((int)s->types.size() < T) s->types.resize(T);
   if ((int)s->rels.size() < R) s->rels.resize(R);
   s->T = T; s->R = R; s->L = L; s->disjoint = disjoint;
@@ -1948,30 +2014,40 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
     for (int i = 0; i < 2; ++i) PYGB_CUDA(cudaEventCreateWithFlags(&s->mt_ev[i], cudaEventDisableTiming));
     PYGB_CUDA(cudaEventCreateWithFlags(&s->mt_order_ev, cudaEventDisableTiming));
   }
+  sub_lap(3);
   if (s->dirty) {  // previous run aborted: wipe tables, forget the stream
     for (auto& tb : s->types) if (tb.tcap) {
       PYGB_CUDA(cudaMemsetAsync(tb.keys.p, 0xff, tb.tcap * 8, st));
       PYGB_CUDA(cudaMemsetAsync(tb.vals.p, 0xff, tb.tcap * 8, st));
     }
-    for (auto& tb : s->types) if (tb.pk_bits) PYGB_CUDA(cudaMemsetAsync(tb.pk.p, 0xff, (size_t)8 << tb.pk_bits, st));
+    for (int i = 0; i < 2; ++i) if (s->clean_pending[i]) { PYGB_CUDA(cudaStreamWaitEvent(st, s->clean_done[i], 0)); s->clean_pending[i] = false; }
+    for (auto& tb : s->types)
+      for (int i = 0; i < 2; ++i) if (tb.pk_bits[i]) PYGB_CUDA(cudaMemsetAsync(tb.pk[i].p, 0xff, (size_t)8 << tb.pk_bits[i], st));
     if (s->seedpk_bits) PYGB_CUDA(cudaMemsetAsync(s->seedpk.p, 0xff, (size_t)8 << s->seedpk_bits, st));
     s->mt_valid = false;
     s->st_dev_words = 0;
   }
   s->dirty = true;
   if (v2) {
+    if (!s->clean_stream) {
+      PYGB_CUDA(cudaStreamCreateWithFlags(&s->clean_stream, cudaStreamNonBlocking));
+      for (int i = 0; i < 2; ++i) PYGB_CUDA(cudaEventCreateWithFlags(&s->clean_done[i], cudaEventDisableTiming));
+      PYGB_CUDA(cudaEventCreateWithFlags(&s->final_ev, cudaEventDisableTiming));
+    }
+    s->v2_side ^= 1;   // the other table: the previous v2 run's one may still be resetting on the side stream
+    if (s->clean_pending[s->v2_side]) { PYGB_CUDA(cudaStreamWaitEvent(st, s->clean_done[s->v2_side], 0)); s->clean_pending[s->v2_side] = false; }
     for (int t = 0; t < T; ++t) {
       if (int e = ensure_type(s, t, node_cap[t], 0, false, st)) return e;
       // distinct keys <= min(static bound, nodes of the type): a products-sized graph (2.4 M nodes) keeps its table
       // L2-resident (64 MB) whatever the batch; a rank's table holds the keys it owns: 1/W of them (+25 % for imbalance)
       const i64 keys = type_nodes[t] >= 0 ? std::min(node_cap[t], type_nodes[t]) : node_cap[t];
-      if (int e = ensure_table_v2(s, t, XW == 1 ? keys : keys / XW + keys / (4 * XW) + 1024, st)) return e;
+      if (int e = ensure_table_v2(s, t, s->v2_side, XW == 1 ? keys : keys / XW + keys / (4 * XW) + 1024, node_cap[t], st)) return e;
     }
     for (int r = 0; r < R; ++r) if (int e = ensure_rel(s, r, rel_cap[r], 0, st)) return e;
     if (int e = ensure_frontier_scratch(s, max_F, st)) return e;
     if (int e = ensure_edge_scratch(s, max_E, st)) return e;
     if (p2p) {
-      if (int e = ensure_xregion(s, max_E, shard, st)) return e;
+      if (int e = ensure_xregion(s, std::max(max_E, max_F), shard, st)) return e;
       int bits = 10;
       while ((1ull << bits) < 2 * (u64)std::max<i64>(total_seeds, 1)) ++bits;
       if (bits > s->seedpk_bits) {
@@ -1997,6 +2073,7 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
     if (int e = ensure_edge_scratch(s, total_seeds, st)) return e;
   }
 
+  sub_lap(4);
   ht_lap(0);
   // ---- mt19937 raw stream: continue the persistent one or (re)start from the caller's engine state.
   // Pre-generation runs TWO runs ahead on the side stream: the launch made at the end of run i-1 already
@@ -2114,14 +2191,17 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
     a.raw = s->raw.as<u32>(); a.gen = s->gen.as<i64>(); a.out0 = out0; a.raw_cap = raw_cap;
     a.replace = replace; a.disjoint = disjoint;
     if (v2) {
-      a.pk = td.pk.as<u64>(); a.pk_bits = td.pk_bits;
+      a.pk = td.pk[s->v2_side].as<u64>(); a.pk_bits = td.pk_bits[s->v2_side];
+      a.dst_slot = td.vslot[s->v2_side].as<u32>();
       a.xw = XW; a.xr = XR; a.o_shard = lay.o_shard;
       a.fref = s->fref.as<u32>();
       if (p2p) {
         const auto& x = s->x;
         for (int q = 0; q < XW; ++q) a.xpeer[q] = x.peer[q];
         a.x_off_bar = x.off_bar; a.x_off_pref = x.off_pref; a.x_off_fref = x.off_fref;
-        a.x_off_dst = x.off_dst[x.passes & 1]; a.x_off_eid = x.off_eid[x.passes & 1];
+        a.x_off_dst = x.off_dst[x.passes & 1]; a.x_off_eid = x.off_eid[x.passes & 1]; a.x_off_row = x.off_row[x.passes & 1];
+        a.x_off_tout = x.off_tout; a.x_off_tfunc = x.off_tfunc;
+        a.tile_out = reinterpret_cast<i64*>(x.base + x.off_tout); a.tile_func = reinterpret_cast<u32*>(x.base + x.off_tfunc);
         a.fref = reinterpret_cast<u32*>(x.base + x.off_fref);
         a.x_eid64 = (rel >= 0 && rels[rel].num_edges > 0xffffffffll) ? 1 : 0;
       }
@@ -2369,7 +2449,18 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
         a.o_eph = lay.o_eph + r * L + h;
         a.lk_colv = lk_colv; a.lk_vals = lk_vals;
         with_hop_end(a);
-        if (int e = idx32 ? launch_count<int32_t>(s, a, Fb, lk_E, st) : launch_count<int64_t>(s, a, Fb, lk_E, st)) return e;
+        if (p2p) {   // sharded count: own tiles -> aggregates to every rank -> barrier -> scan
+          void* tkq = prof_begin(st);
+          const int gq = grid_for(ceil_div(Fb, XW) + NT, NT, s->sm_count);
+          if (idx32) launch_pdl(k_v2_count<int32_t>, gq, NT, st, a); else launch_pdl(k_v2_count<int64_t>, gq, NT, st, a);
+          prof_end(tkq, "count", st, Fb);
+          PYGB_LAUNCH_CHECK();
+          if (int e = xbarrier(a)) return e;
+          tkq = prof_begin(st);
+          launch_pdl(k_v2_scan, 1, NT, st, a);
+          prof_end(tkq, "scan", st, Fb);
+          PYGB_LAUNCH_CHECK();
+        } else if (int e = idx32 ? launch_count<int32_t>(s, a, Fb, lk_E, st) : launch_count<int64_t>(s, a, Fb, lk_E, st)) return e;
         if (v2) {
           // does any later pass insert into this dst type's table?  (else the ids need not be written back)
           a.v2_writeback = 0;
@@ -2381,24 +2472,29 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
           const int gs = grid_for(p2p ? ceil_div(Fb, XW) + 1 : Fb, sample_nodes_per_block(a.group), s->sm_count);
           void* tk = prof_begin(st);
           if (p2p) {
-            k_shard_bounds<<<1, 128, 0, st>>>(a, XW, lay.o_shard);   // position slices of the ref reduction
-            PYGB_LAUNCH_CHECK();
             if (idx32) launch_pdl(k_v2_sample<int32_t, true>, gs, NT, st, a); else launch_pdl(k_v2_sample<int64_t, true>, gs, NT, st, a);
             prof_end(tk, "sample", st, Eb);
             PYGB_LAUNCH_CHECK();
-            tk = prof_begin(st);
-            launch_pdl(k_v2_rows, grid_for(Fb, NT, s->sm_count), NT, st, a);   // (overlaps the tail of the peer stores)
-            prof_end(tk, "rows", st, Eb);
-            PYGB_LAUNCH_CHECK();
           } else {
+            // A/B switch: draws and table inserts in one kernel (default) or the inserts in an edge-parallel kernel of their
+            // own with four CAS in flight per thread (PYGB200_V2_SPLIT_INSERT=1)
+            static const bool split_insert = getenv("PYGB200_V2_SPLIT_INSERT") != nullptr;
+            if (split_insert) a.phase = 4;
             if (idx32) launch_pdl(k_v2_sample<int32_t, false>, gs, NT, st, a); else launch_pdl(k_v2_sample<int64_t, false>, gs, NT, st, a);
             prof_end(tk, "sample", st, Eb);
             PYGB_LAUNCH_CHECK();
+            if (split_insert) {
+              void* tki = prof_begin(st);
+              launch_pdl(k_v2_insert<false>, grid_for(Eb, 4 * NT, s->sm_count), NT, st, a);
+              prof_end(tki, "insert", st, Eb);
+              PYGB_LAUNCH_CHECK();
+              a.phase = 0;
+            }
           }
           if (p2p) {
             if (int e = xbarrier(a)) return e;   // everybody's (dst, edge id) have arrived
             void* tki = prof_begin(st);
-            launch_pdl(k_v2_insert, grid_for(Eb, 4 * NT, s->sm_count), NT, st, a);
+            launch_pdl(k_v2_insert<true>, grid_for(Eb, 4 * NT, s->sm_count), NT, st, a);
             prof_end(tki, "insert", st, Eb);
             PYGB_LAUNCH_CHECK();
           }
@@ -2506,13 +2602,7 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
   s->last_direct = direct;
   s->last_nodedup = nodedup;
   s->nd_seeds = nodedup ? n_seeds[0] : 0;
-  for (int t = 0; t < T && v2; ++t) {
-    auto& tb = s->types[t];
-    void* tkc = prof_begin(st);
-    launch_pdl(k_v2_cleanup, grid_for(node_cap[t], NT, s->sm_count), NT, st, tb.pk.as<u64>(), (const u32*)tb.slot.as<u32>(), (const i64*)(dst + lay.o_list + t));
-    prof_end(tkc, "cleanup", st, node_cap[t]);
-    PYGB_LAUNCH_CHECK();
-  }
+  if (v2) PYGB_CUDA(cudaEventRecord(s->final_ev, st));   // the table reset of this run waits for it on the side stream (below)
   for (int t = 0; t < T && !s->cleanup_pending && !v2; ++t) {
     auto& tb = s->types[t];
     const i64 cap_nodes = (i64)(tb.slot.cap / 4);
@@ -2587,6 +2677,22 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
       if (n_edges_out) n_edges_out[r] = hs[lay.o_rel + r];
       if (edges_per_hop) for (int j = 0; j < L; ++j) edges_per_hop[(size_t)r * L + j] = hs[lay.o_eph + r * L + j];
     }
+  }
+  if (v2) {
+    // reset the entries this run touched, on the side stream, behind k_final: the next run uses the other table and does
+    // not wait for it (the one after that does: clean_pending).  List lengths are host values by now.
+    PYGB_CUDA(cudaStreamWaitEvent(s->clean_stream, s->final_ev, 0));
+    for (int t = 0; t < T; ++t) {
+      auto& tb = s->types[t];
+      const i64 n = s->types[t].n_nodes;
+      if (n == 0) continue;
+      void* tkc = prof_begin(s->clean_stream);
+      k_v2_cleanup<<<grid_for(n, NT, s->sm_count), NT, 0, s->clean_stream>>>(tb.pk[s->v2_side].as<u64>(), (const u32*)tb.vslot[s->v2_side].as<u32>(), n);
+      prof_end(tkc, "cleanup", s->clean_stream, n);
+      PYGB_LAUNCH_CHECK();
+    }
+    PYGB_CUDA(cudaEventRecord(s->clean_done[s->v2_side], s->clean_stream));
+    s->clean_pending[s->v2_side] = true;
   }
   memcpy(mt->state, hs + lay.o_mt, sizeof(mt->state));
   mt->next = (int32_t)hs[ST_MT_NEXT];

@@ -91,28 +91,9 @@ __global__ void __launch_bounds__(NT) k_v2_seed(const PassArgs a, const idx_t* _
   if (blockIdx.x == 0 && threadIdx.x == 0) { a.st[ST_PASS_E] = n; a.st[ST_PASS_BASE] = 0; }
 }
 
-// ---- sharded: the row (source-node index) of EVERY edge of the pass, one thread per frontier node — replicated on
-// all ranks and cheap (F records in, E coalescable 8-byte stores out).  It used to ride inside the sampling kernel as
-// "rows only" iterations of the node groups, 52 dependent iterations per group at 8 ranks: 176 us where the draws
-// themselves need 25 (bench r2h, kernel_ms_per_call).
-__global__ void __launch_bounds__(NT) k_v2_rows(const PassArgs a) {
-  pdl_enter();
-  const i64 F = a.st[ST_PASS_F];
-  const i64 begin = a.st[a.o_src_begin];
-  const i64 pbase = a.st[ST_PASS_BASE];
-  for (i64 i = (i64)blockIdx.x * NT + threadIdx.x; i < F; i += (i64)gridDim.x * NT) {
-    const uint4 ra = __ldg(reinterpret_cast<const uint4*>(a.rec + i));   // {rs lo, rs hi, deg, loc_off}
-    i64 n_out, n16, n32, n64;
-    classify((i64)ra.z, a.fanout, a.replace, &n_out, &n16, &n32, &n64);
-    i64* dst = a.row + pbase + __ldg(&a.tile_off[i / NT]) + ra.w;
-    const i64 src_pos = begin + i;
-    for (i64 j = 0; j < n_out; ++j) dst[j] = src_pos;
-  }
-}
-
 // ---- one pass's sampling.  SH = false: draw, gather, rows / edge ids / global dst into the result arrays, insert.
-// SH = true: the nodes of this rank's frontier slice draw, gather and store (dst : u32, edge id : u32 | u64) at the
-// edge's flat position into EVERY rank's exchange region (rows: k_v2_rows).
+// SH = true: the nodes of this rank's frontier slice draw, gather and store (dst : u32, source index : u32, edge id :
+// u32 | u64) at the edge's flat position into EVERY rank's exchange region.
 template <typename idx_t, bool SH>
 __global__ void __launch_bounds__(NT, SAMPLE_MIN_BLOCKS) k_v2_sample(const PassArgs a) {
   pdl_enter(TL_SAMPLE);
@@ -124,8 +105,11 @@ __global__ void __launch_bounds__(NT, SAMPLE_MIN_BLOCKS) k_v2_sample(const PassA
   const unsigned gmask = (g == 32) ? 0xffffffffu : (((1u << g) - 1u) << gbase);
   const int npb = (NT / 32) * per_warp;
   const idx_t* __restrict__ col = (const idx_t*)a.col;
-  const i64 own_lo = SH ? (i64)((__int128)F * a.xr / a.xw) : 0;
-  const i64 own_hi = SH ? (i64)((__int128)F * (a.xr + 1) / a.xw) : F;
+  // sharded: this rank's nodes are those of its tiles (tile-aligned slices, the same ones k_v2_count counted)
+  const i64 ntiles = ceil_div(F, NT);
+  const i64 own_lo = SH ? NT * (i64)((__int128)ntiles * a.xr / a.xw) : 0;
+  const i64 own_hi_t = SH ? NT * (i64)((__int128)ntiles * (a.xr + 1) / a.xw) : F;
+  const i64 own_hi = own_hi_t < F ? own_hi_t : F;
   if (gi >= per_warp) return;   // (lanes beyond the last whole group of the warp)
   for (i64 i = own_lo + (i64)blockIdx.x * npb + (threadIdx.x >> 5) * per_warp + gi; i < own_hi; i += (i64)gridDim.x * npb) {
     const NodeRec r = a.rec[i];
@@ -142,10 +126,11 @@ __global__ void __launch_bounds__(NT, SAMPLE_MIN_BLOCKS) k_v2_sample(const PassA
         a.row[pbase + p] = src_pos;
         a.eid[pbase + p] = e;
         a.colv[pbase + p] = d;   // global id until k_v2_assign replaces it with the local id
-        a.eslot[p] = v2_insert(a.pk, a.pk_bits, (u32)d, (u32)p);
+        if (a.phase != 4) a.eslot[p] = v2_insert(a.pk, a.pk_bits, (u32)d, (u32)p);   // (phase 4: k_v2_insert<false> follows)
       } else {
         for (int q = 0; q < a.xw; ++q) {
           x_ptr<u32>(a, q, a.x_off_dst)[p] = (u32)d;
+          x_ptr<u32>(a, q, a.x_off_row)[p] = (u32)src_pos;
           if (a.x_eid64) x_ptr<u64>(a, q, a.x_off_eid)[p] = (u64)e; else x_ptr<u32>(a, q, a.x_off_eid)[p] = (u32)e;
         }
       }
@@ -162,18 +147,20 @@ __global__ void __launch_bounds__(NT, SAMPLE_MIN_BLOCKS) k_v2_sample(const PassA
 // ---- sharded: the owner of a dst id inserts it (all positions of the pass are streamed, 1/W of them hit the table).
 // Four positions per thread (coalesced, strided by the block) with their first CAS issued back to back: the kernel is
 // bound by the round trips of independent atomics, not by their number.
+template <bool SH>   // SH = false: single GPU with the insert split from the draws (keys = the global ids in colv)
 __global__ void __launch_bounds__(NT) k_v2_insert(const PassArgs a) {
   pdl_enter();
   const i64 E = a.st[ST_PASS_E];
-  const u32* __restrict__ xdst = x_ptr<u32>(a, a.xr, a.x_off_dst);
+  const i64 pbase = a.st[ST_PASS_BASE];
+  const u32* __restrict__ xdst = SH ? x_ptr<u32>(a, a.xr, a.x_off_dst) : nullptr;
   const u64 mask = (1ull << a.pk_bits) - 1;
   for (i64 base = (i64)blockIdx.x * (4 * NT); base < E; base += (i64)gridDim.x * (4 * NT)) {
     u32 key[4]; u64 slot[4], prev[4]; bool own[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const i64 p = base + j * NT + threadIdx.x;
-      key[j] = p < E ? xdst[p] : 0u;
-      own[j] = p < E && v2_owner(key[j], a.xw) == a.xr;
+      key[j] = p < E ? (SH ? xdst[p] : (u32)a.colv[pbase + p]) : 0u;
+      own[j] = p < E && (!SH || v2_owner(key[j], a.xw) == a.xr);
       slot[j] = ((u64)key[j] * 0x9E3779B97F4A7C15ull) >> (64 - a.pk_bits);
     }
 #pragma unroll
@@ -419,7 +406,10 @@ __global__ void __launch_bounds__(NT) k_v2_assign(const PassArgs a) {
     for (int j = 0; j < 4; ++j) {
       const i64 p = base + j * NT + threadIdx.x;
       if (p >= E) break;
-      if (SH) a.eid[pbase + p] = a.x_eid64 ? (i64)x_ptr<u64>(a, a.xr, a.x_off_eid)[p] : (i64)x_ptr<u32>(a, a.xr, a.x_off_eid)[p];
+      if (SH) {
+        a.eid[pbase + p] = a.x_eid64 ? (i64)x_ptr<u64>(a, a.xr, a.x_off_eid)[p] : (i64)x_ptr<u32>(a, a.xr, a.x_off_eid)[p];
+        a.row[pbase + p] = (i64)x_ptr<u32>(a, a.xr, a.x_off_row)[p];
+      }
       const bool first = r[j] == (V2_POS | (u32)p);
       if (first) {
         const i64 d = SH ? (i64)xdst[p] : a.colv[pbase + p];   // (global id, about to be replaced)
@@ -433,9 +423,7 @@ __global__ void __launch_bounds__(NT) k_v2_assign(const PassArgs a) {
   }
 }
 
-__global__ void __launch_bounds__(NT) k_v2_cleanup(u64* pk, const u32* __restrict__ slots, const i64* n_ptr) {
-  pdl_enter();
-  const i64 n = *n_ptr;
+__global__ void __launch_bounds__(NT) k_v2_cleanup(u64* pk, const u32* __restrict__ slots, i64 n) {
   for (i64 i = (i64)blockIdx.x * NT + threadIdx.x; i < n; i += (i64)gridDim.x * NT) {
     const u32 s = slots[i];
     if (s != NO_SLOT) pk[s] = EMPTY;

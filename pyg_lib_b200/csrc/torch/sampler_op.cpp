@@ -154,7 +154,8 @@ neighbor_sample_cuda(const at::Tensor& rowptr, const at::Tensor& col, const at::
   std::vector<int64_t> nph(L + 1, 0), eph(L, 0);
   int64_t n_nodes = 0, n_edges = 0;
   const auto opt = seed.options();
-  at::Tensor row, colv, node;
+  at::Tensor row, colv, node, direct_buf;
+  int64_t direct_ecap = 0;
   std::optional<at::Tensor> eid = std::nullopt;
   {
     const int64_t* nt = node_time.has_value() ? time_ptr(*node_time, "node_time", seed.device()) : nullptr;
@@ -173,12 +174,12 @@ neighbor_sample_cuda(const at::Tensor& rowptr, const at::Tensor& col, const at::
         pygb200_sampler_bounds(1, 1, L, &rel, &n_seed, num_neighbors.data(), &ncap, &ecap) == PYGB200_OK && ecap > 0 &&
         (3 * ecap + ncap) * 8 <= kDirectOutputBytes) {
       // ONE allocation for the four results (row | col | edge_id | node_id): one allocator call per sampling call
-      const at::Tensor buf = at::empty({(return_edge_id ? 3 : 2) * ecap + ncap}, opt);
-      row = buf.narrow(0, 0, ecap); colv = buf.narrow(0, ecap, ecap);
-      if (return_edge_id) eid = buf.narrow(0, 2 * ecap, ecap);
-      node = buf.narrow(0, (return_edge_id ? 3 : 2) * ecap, ncap);
-      void* rp = row.data_ptr(); void* cp = colv.data_ptr(); void* np = node.data_ptr();
-      void* ep = return_edge_id ? eid->data_ptr() : nullptr;
+      // (views are only made once, after the run, with the final sizes: every narrow() is a dispatcher call)
+      direct_buf = at::empty({(return_edge_id ? 3 : 2) * ecap + ncap}, opt);
+      direct_ecap = ecap;
+      int64_t* base = direct_buf.data_ptr<int64_t>();
+      void* rp = base; void* cp = base + ecap; void* ep = return_edge_id ? base + 2 * ecap : nullptr;
+      void* np = base + (return_edge_id ? 3 : 2) * ecap;
       PYGB_TORCH_CALL(pygb200_sampler_bind_outputs(s, 1, 1, &rp, &cp, &ep, &np, &ecap, &ncap));
     }
     CpuEngine eng;
@@ -191,9 +192,10 @@ neighbor_sample_cuda(const at::Tensor& rowptr, const at::Tensor& col, const at::
   }
   TORCH_CHECK(directed, "Undirected subgraphs not yet supported");  // raised after sampling, neighbor_kernel.cpp:501
   if (pygb200_sampler_outputs_direct(s)) {
-    row = row.narrow(0, 0, n_edges); colv = colv.narrow(0, 0, n_edges); node = node.narrow(0, 0, n_nodes);
-    if (return_edge_id) eid = eid->narrow(0, 0, n_edges);
-    const int64_t cap_total = row.storage().nbytes() / 8, used = (return_edge_id ? 3 : 2) * n_edges + n_nodes;
+    row = direct_buf.narrow(0, 0, n_edges); colv = direct_buf.narrow(0, direct_ecap, n_edges);
+    if (return_edge_id) eid = direct_buf.narrow(0, 2 * direct_ecap, n_edges);
+    node = direct_buf.narrow(0, (return_edge_id ? 3 : 2) * direct_ecap, n_nodes);
+    const int64_t cap_total = direct_buf.numel(), used = (return_edge_id ? 3 : 2) * n_edges + n_nodes;
     if ((double)used < kDirectMinFill * (double)cap_total) {   // sparse result: do not pin the bound-sized storage
       row = row.clone(); colv = colv.clone(); node = node.clone();
       if (return_edge_id) eid = eid->clone();
