@@ -303,7 +303,7 @@ def sampler_roofline(abi, step_dev, first, n_prof, torch, peaks, hbm_peak, peak_
     torch.cuda.synchronize()
     abi.pygb200_profile_enable(0)
     prof = {}
-    for name in ('count', 'sample', 'mark', 'assign', 'lookup', 'seed', 'insert', 'scan', 'pref', 'reduce', 'xbarrier', 'final', 'cleanup', 'export'):
+    for name in ('count', 'sample', 'mark', 'assign', 'lookup', 'seed', 'insert', 'rows', 'push', 'pref', 'reduce', 'xbarrier', 'final', 'cleanup', 'export'):
         msv, ln, wk = C.c_double(), C.c_int64(), C.c_int64()
         abi.pygb200_profile_read(name.encode(), C.byref(msv), C.byref(ln), C.byref(wk))
         prof[name] = (msv.value, ln.value, wk.value)

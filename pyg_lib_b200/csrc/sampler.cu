@@ -48,7 +48,7 @@ std::vector<ProfPending> g_prof_pending;
 ProfAcc g_prof_acc[] = {{"sample", 0, 0, 0}, {"count", 0, 0, 0}, {"mark", 0, 0, 0}, {"assign", 0, 0, 0},
                         {"lookup", 0, 0, 0}, {"segment_matmul", 0, 0, 0}, {"grouped_gemm", 0, 0, 0},
                         {"insert", 0, 0, 0}, {"pref", 0, 0, 0}, {"reduce", 0, 0, 0}, {"xbarrier", 0, 0, 0},
-                        {"seed", 0, 0, 0}, {"final", 0, 0, 0}, {"cleanup", 0, 0, 0}, {"export", 0, 0, 0}, {"scan", 0, 0, 0}};
+                        {"seed", 0, 0, 0}, {"final", 0, 0, 0}, {"cleanup", 0, 0, 0}, {"export", 0, 0, 0}, {"rows", 0, 0, 0}, {"push", 0, 0, 0}};
 constexpr int N_PROF = sizeof(g_prof_acc) / sizeof(g_prof_acc[0]);
 int prof_slot(const char* name) {
   for (int i = 0; i < N_PROF; ++i) if (strcmp(g_prof_acc[i].name, name) == 0) return i;
@@ -157,8 +157,8 @@ struct PassArgs {
   u32* fref;                       // ref of every edge of the running pass
   int xw, xr, x_eid64;             // world size (1 = single GPU), rank, wire type of edge ids
   int v2_writeback, o_shard;
-  i64 x_off_bar, x_off_dst, x_off_eid, x_off_pref, x_off_fref;   // byte offsets inside an exchange region
-  i64 x_off_row, x_off_tout, x_off_tfunc;                        // sharded count: rows of the edges, per-tile aggregates
+  i64 x_off_bar, x_off_dst, x_off_eid, x_off_fref;               // byte offsets inside an exchange region
+  i64 x_off_exc, x_off_exc_n, x_off_xcnt, x_exc_cap;             // ref exceptions: W lists of (position, ref), their lengths, my counter
   unsigned char* xpeer[16];        // exchange region of every rank (own one included), peer-mapped
 };
 __device__ __forceinline__ i64 ldw(const i64* st, int w, i64 c) { return w >= 0 ? st[w] : c; }
@@ -522,16 +522,9 @@ __device__ __forceinline__ void count_tile(const PassArgs& a, i64 begin, i64 F, 
     a.rec[i] = r;
   }
   if (threadIdx.x == 0) {
-    if (a.xw > 1 && a.x_off_tout) {   // sharded count (k_v2_count): the aggregate goes to every rank's copy
-      for (int q = 0; q < a.xw; ++q) {
-        reinterpret_cast<i64*>(a.xpeer[q] + a.x_off_tout)[tile] = tot_v;
-        *reinterpret_cast<uint4*>(a.xpeer[q] + a.x_off_tfunc + 16 * tile) = make_uint4(tot_f.d[0], tot_f.d[1], tot_f.d[2], tot_f.d[3]);
-      }
-    } else {
-      a.tile_out[tile] = tot_v;
+    a.tile_out[tile] = tot_v;
 #pragma unroll
-      for (int p = 0; p < 4; ++p) a.tile_func[4 * tile + p] = tot_f.d[p];
-    }
+    for (int p = 0; p < 4; ++p) a.tile_func[4 * tile + p] = tot_f.d[p];
   }
 }
 
@@ -552,36 +545,6 @@ __global__ void __launch_bounds__(NT) k_count(const PassArgs a) {
     mt_extend_block<3>(a.raw, a.gen, a.out0 + 256 * rng_blocks_for_units(a.st[ST_CURSOR]), a.raw_cap, a.st, s_win);
     tl_mark_any(TL_COUNT | TL_LAST | TL_END);
   }
-}
-
-// Sharded count (peer-memory frontier sharding): a rank counts only its own tiles of the frontier — tile-aligned
-// slices [T r / W, T (r+1) / W) — and stores their aggregates into every rank's copy; after a cross-GPU barrier
-// k_v2_scan (one block, every rank) turns the full list of aggregates into offsets / RNG positions exactly like the last
-// block of k_count does on one GPU.  The records stay local: only the owner samples a node.
-template <typename idx_t>
-__global__ void __launch_bounds__(NT) k_v2_count(const PassArgs a) {
-  pdl_enter(TL_COUNT);
-  const i64 begin = a.st[a.o_src_begin], end = a.st[a.o_src_end];
-  const i64 F = end - begin;
-  const i64 ntiles = ceil_div(F, NT);
-  const i64 t_lo = (i64)((__int128)ntiles * a.xr / a.xw), t_hi = (i64)((__int128)ntiles * (a.xr + 1) / a.xw);
-  for (i64 tile = t_lo + blockIdx.x; tile < t_hi; tile += gridDim.x) count_tile<idx_t>(a, begin, F, tile);
-  tl_mark(TL_COUNT | TL_END);
-}
-__global__ void __launch_bounds__(NT) k_v2_scan(const PassArgs a) {
-  __shared__ u32 s_win[MT_WIN];
-  pdl_enter();
-  const i64 begin = a.st[a.o_src_begin], end = a.st[a.o_src_end];
-  const i64 F = end - begin;
-  const i64 ntiles = ceil_div(F, NT);
-  if (threadIdx.x == 0) a.st[ST_PASS_F] = F;
-  scan_frontier_tiles(a, ntiles);
-  // position slices of the ref reduction = the edges of each rank's tiles
-  if ((int)threadIdx.x <= a.xw) {
-    const i64 t = (i64)((__int128)ntiles * threadIdx.x / a.xw);
-    a.st[a.o_shard + threadIdx.x] = t < ntiles ? a.tile_off[t] : a.st[ST_PASS_E];
-  }
-  mt_extend_block<3>(a.raw, a.gen, a.out0 + 256 * rng_blocks_for_units(a.st[ST_CURSOR]), a.raw_cap, a.st, s_win);
 }
 
 // Sampling of ONE frontier node by a group of `g` consecutive lanes of a warp (g = min(fan-out, 32): a warp
@@ -1463,7 +1426,8 @@ struct pygb200_sampler {
     unsigned char* peer[16] = {nullptr};
     u64 epoch = 0;          // barrier count (flag words only grow)
     u64 passes = 0;         // sharded passes so far: parity picks the (dst, edge id) buffer
-    i64 off_bar = 0, off_dst[2] = {0, 0}, off_eid[2] = {0, 0}, off_row[2] = {0, 0}, off_pref = 0, off_fref = 0, off_tout = 0, off_tfunc = 0;
+    i64 off_bar = 0, off_dst[2] = {0, 0}, off_eid[2] = {0, 0}, off_fref = 0;
+    i64 off_exc = 0, off_exc_n = 0, off_xcnt = 0;
   } x;
   i64* st_host = nullptr;   // pinned + mapped mirror of the state buffer (k_final writes it directly)
   i64* st_host_dev = nullptr;   // device-side address of st_host
@@ -1679,15 +1643,14 @@ int ensure_xregion(pygb200_sampler* s, i64 cap, const pygb200_shard* shard, cuda
   auto al = [](i64 b) { return (b + 255) / 256 * 256; };
   i64 o = 256;
   const i64 off_bar = 0;
-  i64 off_dst[2], off_eid[2], off_row[2];
+  i64 off_dst[2], off_eid[2];
   for (int i = 0; i < 2; ++i) { off_dst[i] = o; o += al(ncap * 4); }
   for (int i = 0; i < 2; ++i) { off_eid[i] = o; o += al(ncap * 8); }
-  for (int i = 0; i < 2; ++i) { off_row[i] = o; o += al(ncap * 4); }
-  const i64 off_pref = o; o += al(ncap * 4);
   const i64 off_fref = o; o += al(ncap * 4);
-  const i64 tcap = ncap / NT + 2;   // frontier tiles: a frontier is never longer than a pass's edge bound... (+ the seed list, <= ncap)
-  const i64 off_tout = o; o += al(tcap * 8);
-  const i64 off_tfunc = o; o += al(tcap * 16);
+  const i64 off_exc_n = o; o += 256;                 // W list lengths (written by the source ranks)
+  const i64 off_xcnt = o; o += 256;                  // this rank's running exception count
+  const i64 off_exc = o; o += al((i64)W * ncap * 8); // W lists of up to ncap (position, ref) pairs
+
   unsigned char* nb = nullptr;
   PYGB_CUDA(cudaMalloc((void**)&nb, (size_t)o));
   PYGB_CUDA(cudaMemset(nb, 0, 256));
@@ -1701,8 +1664,8 @@ int ensure_xregion(pygb200_sampler* s, i64 cap, const pygb200_shard* shard, cuda
   if (x.base) cudaFree(x.base);
   x.base = nb; x.bytes = (size_t)o; x.cap = ncap; x.world = W; x.rank = shard->rank;
   x.off_bar = off_bar; x.off_dst[0] = off_dst[0]; x.off_dst[1] = off_dst[1]; x.off_eid[0] = off_eid[0]; x.off_eid[1] = off_eid[1];
-  x.off_row[0] = off_row[0]; x.off_row[1] = off_row[1];
-  x.off_pref = off_pref; x.off_fref = off_fref; x.off_tout = off_tout; x.off_tfunc = off_tfunc;
+  x.off_fref = off_fref;
+  x.off_exc = off_exc; x.off_exc_n = off_exc_n; x.off_xcnt = off_xcnt;
   x.epoch = 0; x.passes = 0;
   for (int q = 0; q < W; ++q) {
     if (q == x.rank) { x.peer[q] = nb; continue; }
@@ -2047,7 +2010,7 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
     if (int e = ensure_frontier_scratch(s, max_F, st)) return e;
     if (int e = ensure_edge_scratch(s, max_E, st)) return e;
     if (p2p) {
-      if (int e = ensure_xregion(s, std::max(max_E, max_F), shard, st)) return e;
+      if (int e = ensure_xregion(s, max_E, shard, st)) return e;
       int bits = 10;
       while ((1ull << bits) < 2 * (u64)std::max<i64>(total_seeds, 1)) ++bits;
       if (bits > s->seedpk_bits) {
@@ -2198,10 +2161,9 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
       if (p2p) {
         const auto& x = s->x;
         for (int q = 0; q < XW; ++q) a.xpeer[q] = x.peer[q];
-        a.x_off_bar = x.off_bar; a.x_off_pref = x.off_pref; a.x_off_fref = x.off_fref;
-        a.x_off_dst = x.off_dst[x.passes & 1]; a.x_off_eid = x.off_eid[x.passes & 1]; a.x_off_row = x.off_row[x.passes & 1];
-        a.x_off_tout = x.off_tout; a.x_off_tfunc = x.off_tfunc;
-        a.tile_out = reinterpret_cast<i64*>(x.base + x.off_tout); a.tile_func = reinterpret_cast<u32*>(x.base + x.off_tfunc);
+        a.x_off_bar = x.off_bar; a.x_off_fref = x.off_fref;
+        a.x_off_exc = x.off_exc; a.x_off_exc_n = x.off_exc_n; a.x_off_xcnt = x.off_xcnt; a.x_exc_cap = x.cap;
+        a.x_off_dst = x.off_dst[x.passes & 1]; a.x_off_eid = x.off_eid[x.passes & 1];
         a.fref = reinterpret_cast<u32*>(x.base + x.off_fref);
         a.x_eid64 = (rel >= 0 && rels[rel].num_edges > 0xffffffffll) ? 1 : 0;
       }
@@ -2235,15 +2197,22 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
     void* tk;
     if (p2p) {
       tk = prof_begin(st);
-      launch_pdl(k_v2_pref, grid_for(Eb, 4 * NT, s->sm_count), NT, st, a);
+      launch_pdl(k_v2_exc, grid_for(Eb, 4 * NT, s->sm_count), NT, st, a);
       prof_end(tk, "pref", st, Eb);
       PYGB_LAUNCH_CHECK();
       if (int e = xbarrier(a)) return e;
       tk = prof_begin(st);
-      launch_pdl(k_v2_reduce, grid_for(ceil_div(Eb, XW), 4 * NT, s->sm_count), NT, st, a);
+      {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)grid_for(ceil_div(Eb, XW), NT, s->sm_count), (unsigned)XW); cfg.blockDim = dim3(NT); cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        PYGB_CUDA(cudaLaunchKernelEx(&cfg, k_v2_scatter, a));
+      }
       prof_end(tk, "reduce", st, Eb);
       PYGB_LAUNCH_CHECK();
-      if (int e = xbarrier(a)) return e;
       tk = prof_begin(st);
       launch_pdl(k_v2_mark<false>, grid_for(Eb, ETILE, s->sm_count), NT, st, a);
     } else {
@@ -2449,18 +2418,7 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
         a.o_eph = lay.o_eph + r * L + h;
         a.lk_colv = lk_colv; a.lk_vals = lk_vals;
         with_hop_end(a);
-        if (p2p) {   // sharded count: own tiles -> aggregates to every rank -> barrier -> scan
-          void* tkq = prof_begin(st);
-          const int gq = grid_for(ceil_div(Fb, XW) + NT, NT, s->sm_count);
-          if (idx32) launch_pdl(k_v2_count<int32_t>, gq, NT, st, a); else launch_pdl(k_v2_count<int64_t>, gq, NT, st, a);
-          prof_end(tkq, "count", st, Fb);
-          PYGB_LAUNCH_CHECK();
-          if (int e = xbarrier(a)) return e;
-          tkq = prof_begin(st);
-          launch_pdl(k_v2_scan, 1, NT, st, a);
-          prof_end(tkq, "scan", st, Fb);
-          PYGB_LAUNCH_CHECK();
-        } else if (int e = idx32 ? launch_count<int32_t>(s, a, Fb, lk_E, st) : launch_count<int64_t>(s, a, Fb, lk_E, st)) return e;
+        if (int e = idx32 ? launch_count<int32_t>(s, a, Fb, lk_E, st) : launch_count<int64_t>(s, a, Fb, lk_E, st)) return e;
         if (v2) {
           // does any later pass insert into this dst type's table?  (else the ids need not be written back)
           a.v2_writeback = 0;
@@ -2472,8 +2430,18 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
           const int gs = grid_for(p2p ? ceil_div(Fb, XW) + 1 : Fb, sample_nodes_per_block(a.group), s->sm_count);
           void* tk = prof_begin(st);
           if (p2p) {
+            k_shard_bounds<<<1, 128, 0, st>>>(a, XW, lay.o_shard);   // positions of the ranks' frontier slices
+            PYGB_LAUNCH_CHECK();
             if (idx32) launch_pdl(k_v2_sample<int32_t, true>, gs, NT, st, a); else launch_pdl(k_v2_sample<int64_t, true>, gs, NT, st, a);
             prof_end(tk, "sample", st, Eb);
+            PYGB_LAUNCH_CHECK();
+            tk = prof_begin(st);
+            launch_pdl(k_v2_push, grid_for(ceil_div(Eb, XW) + 1, 4 * NT, s->sm_count), NT, st, a);   // own slice -> every peer, 16-byte stores
+            prof_end(tk, "push", st, Eb);
+            PYGB_LAUNCH_CHECK();
+            tk = prof_begin(st);
+            launch_pdl(k_v2_rows, grid_for(Fb, NT, s->sm_count), NT, st, a);   // (overlaps the tail of the peer stores)
+            prof_end(tk, "rows", st, Eb);
             PYGB_LAUNCH_CHECK();
           } else {
             // A/B switch: draws and table inserts in one kernel (default) or the inserts in an edge-parallel kernel of their

@@ -91,9 +91,63 @@ __global__ void __launch_bounds__(NT) k_v2_seed(const PassArgs a, const idx_t* _
   if (blockIdx.x == 0 && threadIdx.x == 0) { a.st[ST_PASS_E] = n; a.st[ST_PASS_BASE] = 0; }
 }
 
+// ---- sharded: the row (source-node index) of EVERY edge of the pass, one thread per frontier node — replicated on
+// all ranks and cheap (F records in, E 8-byte stores out).
+__global__ void __launch_bounds__(NT) k_v2_rows(const PassArgs a) {
+  pdl_enter();
+  const i64 F = a.st[ST_PASS_F];
+  const i64 begin = a.st[a.o_src_begin];
+  const i64 pbase = a.st[ST_PASS_BASE];
+  for (i64 i = (i64)blockIdx.x * NT + threadIdx.x; i < F; i += (i64)gridDim.x * NT) {
+    const uint4 ra = __ldg(reinterpret_cast<const uint4*>(a.rec + i));   // {rs lo, rs hi, deg, loc_off}
+    i64 n_out, n16, n32, n64;
+    classify((i64)ra.z, a.fanout, a.replace, &n_out, &n16, &n32, &n64);
+    i64* dst = a.row + pbase + __ldg(&a.tile_off[i / NT]) + ra.w;
+    const i64 src_pos = begin + i;
+    for (i64 j = 0; j < n_out; ++j) dst[j] = src_pos;
+  }
+}
+
+// ---- sharded: this rank's slice of (dst, edge id) — contiguous flat positions [st[o_shard + r], st[o_shard + r + 1]) —
+// from its own exchange region to every peer's: the all-gather of the sampled edges as 16-byte coalesced peer stores
+// (the access pattern tools/p2p_microbench.cu measured at 690 GB/s).
+__global__ void __launch_bounds__(NT) k_v2_push(const PassArgs a) {
+  pdl_enter();
+  const i64 lo = a.st[a.o_shard + a.xr], hi = a.st[a.o_shard + a.xr + 1];
+  auto push_bytes = [&](i64 off, int esz) {
+    // byte range of the slice inside the array: the 16-byte-aligned middle goes as uint4, the unaligned head and tail
+    // (< 16 bytes each; they share their 16-byte lines with the neighbouring ranks' slices) as 4-byte stores
+    const i64 b0 = lo * esz, b1 = hi * esz;
+    const i64 v0 = (b0 + 15) & ~(i64)15, v1 = b1 & ~(i64)15;
+    const unsigned char* src = a.xpeer[a.xr] + off;
+    if (v1 > v0) {
+      const i64 nv = (v1 - v0) >> 4;
+      for (i64 i = (i64)blockIdx.x * NT + threadIdx.x; i < nv; i += (i64)gridDim.x * NT) {
+        const uint4 w = *reinterpret_cast<const uint4*>(src + v0 + (i << 4));
+        for (int q = 0; q < a.xw; ++q)
+          if (q != a.xr) *reinterpret_cast<uint4*>(a.xpeer[q] + off + v0 + (i << 4)) = w;
+      }
+    }
+    // unaligned head and tail (< 16 bytes each), 4 bytes at a time, by block 0
+    if (blockIdx.x == 0) {
+      const i64 h1 = v1 > v0 ? v0 : b1, t0 = v1 > v0 ? v1 : b1;
+      for (i64 b = b0 + 4 * threadIdx.x; b < h1; b += 4 * NT) {
+        const u32 w = *reinterpret_cast<const u32*>(src + b);
+        for (int q = 0; q < a.xw; ++q) if (q != a.xr) *reinterpret_cast<u32*>(a.xpeer[q] + off + b) = w;
+      }
+      for (i64 b = t0 + 4 * threadIdx.x; b < b1; b += 4 * NT) {
+        const u32 w = *reinterpret_cast<const u32*>(src + b);
+        for (int q = 0; q < a.xw; ++q) if (q != a.xr) *reinterpret_cast<u32*>(a.xpeer[q] + off + b) = w;
+      }
+    }
+  };
+  push_bytes(a.x_off_dst, 4);
+  push_bytes(a.x_off_eid, a.x_eid64 ? 8 : 4);
+}
+
 // ---- one pass's sampling.  SH = false: draw, gather, rows / edge ids / global dst into the result arrays, insert.
-// SH = true: the nodes of this rank's frontier slice draw, gather and store (dst : u32, source index : u32, edge id :
-// u32 | u64) at the edge's flat position into EVERY rank's exchange region.
+// SH = true: the nodes of this rank's frontier slice draw, gather and store (dst : u32, edge id : u32 | u64) at the
+// edge's flat position into this rank's exchange region; k_v2_push sends the slice to every peer, k_v2_rows writes the rows.
 template <typename idx_t, bool SH>
 __global__ void __launch_bounds__(NT, SAMPLE_MIN_BLOCKS) k_v2_sample(const PassArgs a) {
   pdl_enter(TL_SAMPLE);
@@ -105,11 +159,8 @@ __global__ void __launch_bounds__(NT, SAMPLE_MIN_BLOCKS) k_v2_sample(const PassA
   const unsigned gmask = (g == 32) ? 0xffffffffu : (((1u << g) - 1u) << gbase);
   const int npb = (NT / 32) * per_warp;
   const idx_t* __restrict__ col = (const idx_t*)a.col;
-  // sharded: this rank's nodes are those of its tiles (tile-aligned slices, the same ones k_v2_count counted)
-  const i64 ntiles = ceil_div(F, NT);
-  const i64 own_lo = SH ? NT * (i64)((__int128)ntiles * a.xr / a.xw) : 0;
-  const i64 own_hi_t = SH ? NT * (i64)((__int128)ntiles * (a.xr + 1) / a.xw) : F;
-  const i64 own_hi = own_hi_t < F ? own_hi_t : F;
+  const i64 own_lo = SH ? (i64)((__int128)F * a.xr / a.xw) : 0;
+  const i64 own_hi = SH ? (i64)((__int128)F * (a.xr + 1) / a.xw) : F;
   if (gi >= per_warp) return;   // (lanes beyond the last whole group of the warp)
   for (i64 i = own_lo + (i64)blockIdx.x * npb + (threadIdx.x >> 5) * per_warp + gi; i < own_hi; i += (i64)gridDim.x * npb) {
     const NodeRec r = a.rec[i];
@@ -128,11 +179,10 @@ __global__ void __launch_bounds__(NT, SAMPLE_MIN_BLOCKS) k_v2_sample(const PassA
         a.colv[pbase + p] = d;   // global id until k_v2_assign replaces it with the local id
         if (a.phase != 4) a.eslot[p] = v2_insert(a.pk, a.pk_bits, (u32)d, (u32)p);   // (phase 4: k_v2_insert<false> follows)
       } else {
-        for (int q = 0; q < a.xw; ++q) {
-          x_ptr<u32>(a, q, a.x_off_dst)[p] = (u32)d;
-          x_ptr<u32>(a, q, a.x_off_row)[p] = (u32)src_pos;
-          if (a.x_eid64) x_ptr<u64>(a, q, a.x_off_eid)[p] = (u64)e; else x_ptr<u32>(a, q, a.x_off_eid)[p] = (u32)e;
-        }
+        // into this rank's OWN exchange region; k_v2_push forwards the slice to the peers with wide, fully coalesced
+        // stores — 4-byte lane stores straight to 7 peers made this kernel 227 us at 8 ranks for 1/8 of the draws
+        x_ptr<u32>(a, a.xr, a.x_off_dst)[p] = (u32)d;
+        if (a.x_eid64) x_ptr<u64>(a, a.xr, a.x_off_eid)[p] = (u64)e; else x_ptr<u32>(a, a.xr, a.x_off_eid)[p] = (u32)e;
       }
     };
     auto prev = [&](u32 t) -> i64 {
@@ -154,6 +204,7 @@ __global__ void __launch_bounds__(NT) k_v2_insert(const PassArgs a) {
   const i64 pbase = a.st[ST_PASS_BASE];
   const u32* __restrict__ xdst = SH ? x_ptr<u32>(a, a.xr, a.x_off_dst) : nullptr;
   const u64 mask = (1ull << a.pk_bits) - 1;
+  if (SH && blockIdx.x == 0 && threadIdx.x == 0) *x_ptr<u64>(a, a.xr, a.x_off_xcnt) = 0;   // this pass's exception count (k_v2_exc)
   for (i64 base = (i64)blockIdx.x * (4 * NT); base < E; base += (i64)gridDim.x * (4 * NT)) {
     u32 key[4]; u64 slot[4], prev[4]; bool own[4];
 #pragma unroll
@@ -185,15 +236,22 @@ __global__ void __launch_bounds__(NT) k_v2_insert(const PassArgs a) {
         res = (u32)sl;
       }
       a.eslot[p] = res;
+      if (SH) a.fref[p] = V2_POS | (u32)p;   // default ref "first occurrence"; the owners send the exceptions (k_v2_exc)
     }
   }
 }
 
-// ---- sharded: refs of the positions this rank owns (0 elsewhere: exactly one rank owns a position)
-__global__ void __launch_bounds__(NT) k_v2_pref(const PassArgs a) {
+// ---- sharded: the refs every rank needs.  A position's ref is "first occurrence" (V2_POS | p, what k_v2_insert wrote
+// as the default) unless its key was seen earlier — in this pass at a smaller position, or in an earlier pass.  Only
+// the owner of the key knows, and only those EXCEPTIONS travel: (position, ref) pairs appended to a list in every
+// rank's exchange region (on the papers100M-shaped graph ~5 % of the positions, on a duplicate-heavy graph at most
+// all of them).  One barrier later k_v2_scatter applies the W lists to the local ref array.  This replaced a
+// zero-padded partial-ref array + slice-wise pull / reduce / push (two kernels, two barriers, 8 B/edge on the link).
+__global__ void __launch_bounds__(NT) k_v2_exc(const PassArgs a) {
   pdl_enter();
   const i64 E = a.st[ST_PASS_E];
-  u32* __restrict__ pref = x_ptr<u32>(a, a.xr, a.x_off_pref);
+  u64* cnt = x_ptr<u64>(a, a.xr, a.x_off_xcnt);
+  const int lane = threadIdx.x & 31;
   for (i64 base = (i64)blockIdx.x * (4 * NT); base < E; base += (i64)gridDim.x * (4 * NT)) {
     u32 s[4], v[4];
 #pragma unroll
@@ -201,27 +259,35 @@ __global__ void __launch_bounds__(NT) k_v2_pref(const PassArgs a) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) v[j] = s[j] == NO_SLOT ? 0u : (u32)a.pk[s[j]];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) { const i64 p = base + j * NT + threadIdx.x; if (p < E) pref[p] = v[j]; }
+    for (int j = 0; j < 4; ++j) {
+      const i64 p = base + j * NT + threadIdx.x;
+      const bool exc = s[j] != NO_SLOT && v[j] != (V2_POS | (u32)p);
+      const unsigned m = __ballot_sync(0xffffffffu, exc);   // (the loop bounds are block-uniform: all lanes are here)
+      if (m == 0) continue;
+      u64 pos0 = 0;
+      if (lane == __ffs(m) - 1) pos0 = atomicAdd(cnt, (u64)__popc(m));   // one counter bump per warp
+      pos0 = __shfl_sync(0xffffffffu, pos0, __ffs(m) - 1);
+      if (exc) {
+        const u64 idx = pos0 + __popc(m & ((1u << lane) - 1u)), pair = ((u64)(u32)p << 32) | (u64)v[j];
+        for (int q = 0; q < a.xw; ++q) x_ptr<u64>(a, q, a.x_off_exc)[(i64)a.xr * a.x_exc_cap + idx] = pair;
+      }
+    }
+  }
+  // the list length goes to every rank once all blocks are done
+  if (last_block(&a.st[ST_TICKET_A])) {
+    if (threadIdx.x < a.xw) x_ptr<u64>(a, threadIdx.x, a.x_off_exc_n)[a.xr] = *reinterpret_cast<volatile u64*>(cnt);
   }
 }
 
-// ---- sharded: this rank's position slice of the refs = sum over the ranks' partial refs (coalesced peer loads),
-// stored to every rank (coalesced peer stores); 4 positions per thread so that 4 x W loads are in flight
-__global__ void __launch_bounds__(NT) k_v2_reduce(const PassArgs a) {
+// blockIdx.y = source rank
+__global__ void __launch_bounds__(NT) k_v2_scatter(const PassArgs a) {
   pdl_enter();
-  const i64 lo = a.st[a.o_shard + a.xr], hi = a.st[a.o_shard + a.xr + 1];
-  for (i64 base = lo + (i64)blockIdx.x * (4 * NT); base < hi; base += (i64)gridDim.x * (4 * NT)) {
-    u32 v[4] = {0, 0, 0, 0};
-    for (int q = 0; q < a.xw; ++q) {
-      const u32* __restrict__ src = x_ptr<u32>(a, q, a.x_off_pref);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) { const i64 p = base + j * NT + threadIdx.x; if (p < hi) v[j] += src[p]; }
-    }
-    for (int q = 0; q < a.xw; ++q) {
-      u32* __restrict__ dst = x_ptr<u32>(a, q, a.x_off_fref);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) { const i64 p = base + j * NT + threadIdx.x; if (p < hi) dst[p] = v[j]; }
-    }
+  const int sr = blockIdx.y;
+  const i64 n = (i64)x_ptr<u64>(a, a.xr, a.x_off_exc_n)[sr];
+  const u64* __restrict__ list = x_ptr<u64>(a, a.xr, a.x_off_exc) + (i64)sr * a.x_exc_cap;
+  for (i64 i = (i64)blockIdx.x * NT + threadIdx.x; i < n; i += (i64)gridDim.x * NT) {
+    const u64 pair = list[i];
+    a.fref[pair >> 32] = (u32)pair;
   }
 }
 
@@ -406,10 +472,7 @@ __global__ void __launch_bounds__(NT) k_v2_assign(const PassArgs a) {
     for (int j = 0; j < 4; ++j) {
       const i64 p = base + j * NT + threadIdx.x;
       if (p >= E) break;
-      if (SH) {
-        a.eid[pbase + p] = a.x_eid64 ? (i64)x_ptr<u64>(a, a.xr, a.x_off_eid)[p] : (i64)x_ptr<u32>(a, a.xr, a.x_off_eid)[p];
-        a.row[pbase + p] = (i64)x_ptr<u32>(a, a.xr, a.x_off_row)[p];
-      }
+      if (SH) a.eid[pbase + p] = a.x_eid64 ? (i64)x_ptr<u64>(a, a.xr, a.x_off_eid)[p] : (i64)x_ptr<u32>(a, a.xr, a.x_off_eid)[p];
       const bool first = r[j] == (V2_POS | (u32)p);
       if (first) {
         const i64 d = SH ? (i64)xdst[p] : a.colv[pbase + p];   // (global id, about to be replaced)
