@@ -159,6 +159,8 @@ struct PassArgs {
   int v2_writeback, o_shard;
   i64 x_off_bar, x_off_dst, x_off_eid, x_off_fref;               // byte offsets inside an exchange region
   i64 x_off_exc, x_off_exc_n, x_off_xcnt, x_exc_cap;             // ref exceptions: W lists of (position, ref), their lengths, my counter
+  u64 x_sig_epoch, x_wait_epoch, x_timeout_ns;                   // cross-GPU flags raised at the end / awaited at the start of a kernel (0 = none)
+  int sd_begin, sd_end, sd_nph;                                  // seed pass: frontier-slice words its mark kernel sets (k_seed_end folded in; 0 = not)
   unsigned char* xpeer[16];        // exchange region of every rank (own one included), peer-mapped
 };
 __device__ __forceinline__ i64 ldw(const i64* st, int w, i64 c) { return w >= 0 ? st[w] : c; }
@@ -463,6 +465,21 @@ __device__ __forceinline__ bool last_block(i64* ticket) {
   return s_last != 0;
 }
 
+// same, for kernels that stored to PEER memory: the fence in front of the ticket is system-wide
+__device__ __forceinline__ bool last_block_sys(i64* ticket) {
+  __shared__ int s_last;
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const u64 t = atomicAdd((u64*)ticket, 1ull);
+    s_last = (t == (u64)gridDim.x - 1);
+    if (s_last) *ticket = 0;
+  }
+  __syncthreads();
+  if (s_last) __threadfence_system();
+  return s_last != 0;
+}
+
 // ------------------------------------------------------------------------------------ kernels
 // local ids of the previous pass's edges (its k_assign has completed: kernel boundary)
 __device__ __forceinline__ void deferred_lookup(const PassArgs& a) {
@@ -542,6 +559,10 @@ __global__ void __launch_bounds__(NT) k_count(const PassArgs a) {
     tl_mark_any(TL_COUNT | TL_LAST);
     if (threadIdx.x == 0) a.st[ST_PASS_F] = F;
     scan_frontier_tiles(a, ntiles);
+    if (a.xw > 1 && (int)threadIdx.x <= a.xw) {   // sharded: flat position of the first edge of every rank's frontier slice
+      const i64 i = (i64)((__int128)F * threadIdx.x / a.xw);
+      a.st[a.o_shard + threadIdx.x] = i < F ? a.tile_off[i / NT] + (i64)a.rec[i].loc_off : a.st[ST_PASS_E];
+    }
     mt_extend_block<3>(a.raw, a.gen, a.out0 + 256 * rng_blocks_for_units(a.st[ST_CURSOR]), a.raw_cap, a.st, s_win);
     tl_mark_any(TL_COUNT | TL_LAST | TL_END);
   }
@@ -1411,8 +1432,8 @@ struct pygb200_sampler {
   i64 nd_seeds = 0;
   DevBuf eslot, erank, rec, tile_out, tile_func, tile_off, tile_pos, mtile, raw, st, gen;
   DevBuf fref;              // v2, single GPU: ref of every edge of the running pass
-  DevBuf seedpk;            // v2, sharded: scratch table for the replicated dedup of the seeds (all-EMPTY between runs)
-  int seedpk_bits = 0;
+  DevBuf seedpk[2];         // v2, sharded: scratch tables for the replicated dedup of the seeds (all-EMPTY between runs; one per side)
+  int seedpk_bits[2] = {0, 0};
   int v2_side = 0;          // which of the two packed tables the current / last v2 run uses
   cudaStream_t clean_stream = nullptr;
   cudaEvent_t clean_done[2] = {nullptr, nullptr}, final_ev = nullptr;
@@ -1547,7 +1568,7 @@ extern "C" void pygb200_sampler_destroy(pygb200_sampler* s) {
     t.nodes.release(); t.batch.release(); t.slot.release(); t.keys.release(); t.vals.release();
     for (int i = 0; i < 2; ++i) { t.pk[i].release(); t.vslot[i].release(); }
   }
-  s->fref.release(); s->seedpk.release();
+  s->fref.release(); s->seedpk[0].release(); s->seedpk[1].release();
   for (int q = 0; q < s->x.world; ++q) if (q != s->x.rank && s->x.peer[q]) cudaIpcCloseMemHandle(s->x.peer[q]);
   if (s->x.base) cudaFree(s->x.base);
   for (auto& r : s->rels) { r.row.release(); r.colv.release(); r.eid.release(); }
@@ -1986,7 +2007,7 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
     for (int i = 0; i < 2; ++i) if (s->clean_pending[i]) { PYGB_CUDA(cudaStreamWaitEvent(st, s->clean_done[i], 0)); s->clean_pending[i] = false; }
     for (auto& tb : s->types)
       for (int i = 0; i < 2; ++i) if (tb.pk_bits[i]) PYGB_CUDA(cudaMemsetAsync(tb.pk[i].p, 0xff, (size_t)8 << tb.pk_bits[i], st));
-    if (s->seedpk_bits) PYGB_CUDA(cudaMemsetAsync(s->seedpk.p, 0xff, (size_t)8 << s->seedpk_bits, st));
+    for (int i = 0; i < 2; ++i) if (s->seedpk_bits[i]) PYGB_CUDA(cudaMemsetAsync(s->seedpk[i].p, 0xff, (size_t)8 << s->seedpk_bits[i], st));
     s->mt_valid = false;
     s->st_dev_words = 0;
   }
@@ -2013,10 +2034,10 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
       if (int e = ensure_xregion(s, max_E, shard, st)) return e;
       int bits = 10;
       while ((1ull << bits) < 2 * (u64)std::max<i64>(total_seeds, 1)) ++bits;
-      if (bits > s->seedpk_bits) {
-        if (int e = s->seedpk.ensure((size_t)8 << bits, 0, st)) return e;
-        PYGB_CUDA(cudaMemsetAsync(s->seedpk.p, 0xff, (size_t)8 << bits, st));
-        s->seedpk_bits = bits;
+      if (bits > s->seedpk_bits[s->v2_side]) {
+        if (int e = s->seedpk[s->v2_side].ensure((size_t)8 << bits, 0, st)) return e;
+        PYGB_CUDA(cudaMemsetAsync(s->seedpk[s->v2_side].p, 0xff, (size_t)8 << bits, st));
+        s->seedpk_bits[s->v2_side] = bits;
       }
     } else if (int e = s->fref.ensure((size_t)max_E * 4, 0, st)) return e;
   } else if (!synced) {
@@ -2186,9 +2207,10 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
   // Sharded: refs of owned positions -> barrier -> slice-wise reduction over the peers, result stored to all ->
   // barrier -> the same mark on the full ref array.  Then ids (replicated, streaming).
   static const u64 xbar_timeout_ns = [] { const char* e = getenv("PYGB200_XBARRIER_TIMEOUT_MS"); return (u64)(e ? atoll(e) : 20000) * 1000000ull; }();
-  auto xbarrier = [&](const PassArgs& a) -> int {
+  auto xbarrier = [&](const PassArgs& a, int mode = 3) -> int {   // 1 = signal (opens a new epoch), 2 = wait for it, 3 = both
+    if (mode & 1) ++s->x.epoch;
     void* tkb = prof_begin(st);
-    launch_pdl(k_xbarrier, 1, 32, st, a, (u64)(++s->x.epoch), xbar_timeout_ns);
+    launch_pdl(k_xbarrier, 1, 32, st, a, (u64)s->x.epoch, xbar_timeout_ns, mode);
     prof_end(tkb, "xbarrier", st, 1);
     PYGB_LAUNCH_CHECK();
     return PYGB200_OK;
@@ -2196,11 +2218,13 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
   auto v2_ids = [&](const PassArgs& a, i64 Eb) -> int {
     void* tk;
     if (p2p) {
+      PassArgs b = a;
+      b.x_sig_epoch = ++s->x.epoch; b.x_timeout_ns = xbar_timeout_ns;   // the last block of k_v2_exc raises the flags ...
       tk = prof_begin(st);
-      launch_pdl(k_v2_exc, grid_for(Eb, 4 * NT, s->sm_count), NT, st, a);
+      launch_pdl(k_v2_exc, grid_for(Eb, 4 * NT, s->sm_count), NT, st, b);
       prof_end(tk, "pref", st, Eb);
       PYGB_LAUNCH_CHECK();
-      if (int e = xbarrier(a)) return e;
+      b.x_sig_epoch = 0; b.x_wait_epoch = s->x.epoch;                    // ... k_v2_scatter waits for everybody's
       tk = prof_begin(st);
       {
         cudaLaunchConfig_t cfg = {};
@@ -2209,7 +2233,7 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
         attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
-        PYGB_CUDA(cudaLaunchKernelEx(&cfg, k_v2_scatter, a));
+        PYGB_CUDA(cudaLaunchKernelEx(&cfg, k_v2_scatter, b));
       }
       prof_end(tk, "reduce", st, Eb);
       PYGB_LAUNCH_CHECK();
@@ -2265,7 +2289,8 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
     }
     if (v2) {
       if (n_seeds[t] == 0) continue;   // the zeroed state already says "empty list, empty slice"
-      if (p2p) { a.pk_main = a.pk; a.pk_main_bits = a.pk_bits; a.pk = s->seedpk.as<u64>(); a.pk_bits = s->seedpk_bits; }
+      if (p2p) { a.pk_main = a.pk; a.pk_main_bits = a.pk_bits; a.pk = s->seedpk[s->v2_side].as<u64>(); a.pk_bits = s->seedpk_bits[s->v2_side]; }
+      a.sd_begin = lay.o_begin + t; a.sd_end = lay.o_end + t; a.sd_nph = lay.o_nph + t * (L + 1);   // (k_seed_end folded into the mark kernel)
       const int g = grid_for(n_seeds[t], NT, s->sm_count);
       void* tks = prof_begin(st);
       if (idx32) launch_pdl(k_v2_seed<int32_t>, g, NT, st, a, (const int32_t*)seeds[t], (i64)n_seeds[t]);
@@ -2283,10 +2308,8 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
         launch_pdl(k_v2_assign<true>, grid_for(n_seeds[t], 4 * NT, s->sm_count), NT, st, a);
         prof_end(tks, "assign", st, n_seeds[t]);
         PYGB_LAUNCH_CHECK();
-        PYGB_CUDA(cudaMemsetAsync(s->seedpk.p, 0xff, (size_t)8 << s->seedpk_bits, st));   // scratch table clean for the next run
+        // (the scratch table is wiped on the side stream with this side's table reset, behind the run)
       } else if (int e = v2_ids(a, n_seeds[t])) return e;
-      k_seed_end<<<1, 1, 0, st>>>(dst, t, L, lay.o_list, lay.o_begin, lay.o_end, lay.o_nph);
-      PYGB_LAUNCH_CHECK();
       continue;
     }
     if (n_seeds[t] > 0 && n_seeds[t] <= SEED_FUSED_MAX) {
@@ -2430,17 +2453,20 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
           const int gs = grid_for(p2p ? ceil_div(Fb, XW) + 1 : Fb, sample_nodes_per_block(a.group), s->sm_count);
           void* tk = prof_begin(st);
           if (p2p) {
-            k_shard_bounds<<<1, 128, 0, st>>>(a, XW, lay.o_shard);   // positions of the ranks' frontier slices
-            PYGB_LAUNCH_CHECK();
+            // (the positions of the ranks' frontier slices were written by the last block of k_count)
             if (idx32) launch_pdl(k_v2_sample<int32_t, true>, gs, NT, st, a); else launch_pdl(k_v2_sample<int64_t, true>, gs, NT, st, a);
             prof_end(tk, "sample", st, Eb);
             PYGB_LAUNCH_CHECK();
+            // own slice -> every peer with 16-byte stores; its last block raises this rank's flag at the peers ("my slice
+            // has been delivered"), so the peers' flags arrive while the rows are written and k_v2_insert only has to look
+            a.x_sig_epoch = ++s->x.epoch; a.x_timeout_ns = xbar_timeout_ns;
             tk = prof_begin(st);
-            launch_pdl(k_v2_push, grid_for(ceil_div(Eb, XW) + 1, 4 * NT, s->sm_count), NT, st, a);   // own slice -> every peer, 16-byte stores
+            launch_pdl(k_v2_push, grid_for(ceil_div(Eb, XW) + 1, 4 * NT, s->sm_count), NT, st, a);
             prof_end(tk, "push", st, Eb);
             PYGB_LAUNCH_CHECK();
+            a.x_sig_epoch = 0;
             tk = prof_begin(st);
-            launch_pdl(k_v2_rows, grid_for(Fb, NT, s->sm_count), NT, st, a);   // (overlaps the tail of the peer stores)
+            launch_pdl(k_v2_rows, grid_for(Fb, NT, s->sm_count), NT, st, a);
             prof_end(tk, "rows", st, Eb);
             PYGB_LAUNCH_CHECK();
           } else {
@@ -2460,11 +2486,12 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
             }
           }
           if (p2p) {
-            if (int e = xbarrier(a)) return e;   // everybody's (dst, edge id) have arrived
+            a.x_wait_epoch = s->x.epoch;   // every block first waits until everybody's (dst, edge id) have arrived
             void* tki = prof_begin(st);
             launch_pdl(k_v2_insert<true>, grid_for(Eb, 4 * NT, s->sm_count), NT, st, a);
             prof_end(tki, "insert", st, Eb);
             PYGB_LAUNCH_CHECK();
+            a.x_wait_epoch = 0;
           }
           if (int e = v2_ids(a, Eb)) return e;
           if (p2p) s->x.passes += 1;
@@ -2659,6 +2686,8 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
       prof_end(tkc, "cleanup", s->clean_stream, n);
       PYGB_LAUNCH_CHECK();
     }
+    if (p2p && s->seedpk_bits[s->v2_side])
+      PYGB_CUDA(cudaMemsetAsync(s->seedpk[s->v2_side].p, 0xff, (size_t)8 << s->seedpk_bits[s->v2_side], s->clean_stream));
     PYGB_CUDA(cudaEventRecord(s->clean_done[s->v2_side], s->clean_stream));
     s->clean_pending[s->v2_side] = true;
   }

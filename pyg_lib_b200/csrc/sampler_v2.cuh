@@ -56,7 +56,9 @@ __device__ __forceinline__ T* x_ptr(const PassArgs& a, int q, i64 off) { return 
 // stores it publishes (a completed kernel's stores are performed system-wide); thread q tells rank q "rank xr has
 // reached epoch" and waits for rank q's word in its own region.  A peer that never arrives is reported, not waited
 // for forever.
-__global__ void k_xbarrier(const PassArgs a, u64 epoch, u64 timeout_ns) {
+// `mode`: 1 = signal only, 2 = wait only, 3 = both — a signal right behind the kernel that stored to the peers and the
+// wait after a kernel that needs nothing remote (k_v2_rows) hide the peers' skew behind local work.
+__global__ void k_xbarrier(const PassArgs a, u64 epoch, u64 timeout_ns, int mode) {
   pdl_enter();
   const int q = threadIdx.x;
   if (q >= a.xw) return;
@@ -64,7 +66,8 @@ __global__ void k_xbarrier(const PassArgs a, u64 epoch, u64 timeout_ns) {
   u64* mine = x_ptr<u64>(a, a.xr, a.x_off_bar);
   if (q != a.xr) {
     u64* theirs = x_ptr<u64>(a, q, a.x_off_bar);
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(theirs + a.xr), "l"(epoch) : "memory");
+    if (mode & 1) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(theirs + a.xr), "l"(epoch) : "memory");
+    if (!(mode & 2)) return;
     u64 t0, t1, v;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
     while (true) {
@@ -76,6 +79,28 @@ __global__ void k_xbarrier(const PassArgs a, u64 epoch, u64 timeout_ns) {
     }
   }
   __threadfence_system();
+}
+
+// the same flags, raised by the last block of a kernel that stored to the peers (x_signal after last_block_sys) and
+// awaited by every block of the kernel that consumes what arrived (x_wait at its start): no barrier launches at all
+__device__ __forceinline__ void x_signal(const PassArgs& a) {
+  if ((int)threadIdx.x < a.xw && (int)threadIdx.x != a.xr)
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(x_ptr<u64>(a, threadIdx.x, a.x_off_bar) + a.xr), "l"(a.x_sig_epoch) : "memory");
+}
+__device__ __forceinline__ void x_wait(const PassArgs& a) {
+  if ((int)threadIdx.x < a.xw && (int)threadIdx.x != a.xr) {
+    const u64* mine = x_ptr<u64>(a, a.xr, a.x_off_bar) + threadIdx.x;
+    u64 t0, t1, v;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    while (true) {
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine) : "memory");
+      if (v >= a.x_wait_epoch) break;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      if (t1 - t0 > a.x_timeout_ns) { a.st[ST_ERROR] = 2; break; }
+      __nanosleep(100);
+    }
+  }
+  __syncthreads();
 }
 
 // ---- seeds: list them and insert them at position i (first-occurrence order == seed order)
@@ -143,6 +168,7 @@ __global__ void __launch_bounds__(NT) k_v2_push(const PassArgs a) {
   };
   push_bytes(a.x_off_dst, 4);
   push_bytes(a.x_off_eid, a.x_eid64 ? 8 : 4);
+  if (a.x_sig_epoch && last_block_sys(&a.st[ST_TICKET_B])) x_signal(a);
 }
 
 // ---- one pass's sampling.  SH = false: draw, gather, rows / edge ids / global dst into the result arrays, insert.
@@ -204,6 +230,7 @@ __global__ void __launch_bounds__(NT) k_v2_insert(const PassArgs a) {
   const i64 pbase = a.st[ST_PASS_BASE];
   const u32* __restrict__ xdst = SH ? x_ptr<u32>(a, a.xr, a.x_off_dst) : nullptr;
   const u64 mask = (1ull << a.pk_bits) - 1;
+  if (SH && a.x_wait_epoch) x_wait(a);
   if (SH && blockIdx.x == 0 && threadIdx.x == 0) *x_ptr<u64>(a, a.xr, a.x_off_xcnt) = 0;   // this pass's exception count (k_v2_exc)
   for (i64 base = (i64)blockIdx.x * (4 * NT); base < E; base += (i64)gridDim.x * (4 * NT)) {
     u32 key[4]; u64 slot[4], prev[4]; bool own[4];
@@ -274,14 +301,18 @@ __global__ void __launch_bounds__(NT) k_v2_exc(const PassArgs a) {
     }
   }
   // the list length goes to every rank once all blocks are done
-  if (last_block(&a.st[ST_TICKET_A])) {
+  if (last_block_sys(&a.st[ST_TICKET_A])) {
     if (threadIdx.x < a.xw) x_ptr<u64>(a, threadIdx.x, a.x_off_exc_n)[a.xr] = *reinterpret_cast<volatile u64*>(cnt);
+    __threadfence_system();
+    __syncthreads();
+    if (a.x_sig_epoch) x_signal(a);
   }
 }
 
 // blockIdx.y = source rank
 __global__ void __launch_bounds__(NT) k_v2_scatter(const PassArgs a) {
   pdl_enter();
+  if (a.x_wait_epoch) x_wait(a);
   const int sr = blockIdx.y;
   const i64 n = (i64)x_ptr<u64>(a, a.xr, a.x_off_exc_n)[sr];
   const u64* __restrict__ list = x_ptr<u64>(a, a.xr, a.x_off_exc) + (i64)sr * a.x_exc_cap;
@@ -333,6 +364,7 @@ __device__ void mark_finish(const PassArgs& a, i64 E, i64 ntiles) {
       a.st[ST_IDS_BASE] = 0;
       a.st[a.o_dst_list] = E;      // every seed is listed, duplicates included (neighbor_kernel.cpp:410)
       a.st[a.o_dst_ids] = nnew;    // ... but ids only count distinct ones (mapper.h:29-46)
+      if (a.sd_end) { a.st[a.sd_begin] = 0; a.st[a.sd_end] = E; a.st[a.sd_nph] = E; }   // first frontier = the seed list (k_seed_end)
     } else {
       a.st[ST_LIST_BASE] = a.st[a.o_dst_list];
       a.st[ST_IDS_BASE] = a.st[a.o_dst_ids];
