@@ -171,6 +171,23 @@ int pygb200_sampler_run_temporal(pygb200_sampler* s, int32_t T, int32_t R, int32
                                  int64_t* edges_per_hop, int64_t* n_nodes, int64_t* n_edges, void* stream,
                                  const pygb200_temporal* temporal);
 
+/* Biased sampling (edge_weight; _biased_sample, neighbor_kernel.cpp:245-285): per frontier node the whole neighbourhood
+ * (fan-out >= degree without replacement), at::multinomial with replacement, or the `fan-out` largest keys
+ * log(u) / weight without — reproducing the reference bit for bit INCLUDING the CPU generator stream it consumes
+ * (uniform_/random64 outputs), torch's CPU float32 log (MKL; table of its deviations from the correctly rounded log)
+ * and at::topk's libstdc++ tie behaviour.  edge_weight[r]: device pointer to relation r's weights (one per edge,
+ * weight_dtype = PYGB200_F32), for EVERY relation.  Limits of this path (PYGB200_ERR_UNSUPPORTED otherwise): bounded
+ * fan-outs (no -1), not disjoint, not temporal (the reference refuses that too), node ids < 2^32 - 1, one GPU, and with
+ * replacement no fan-out of 1 (at::multinomial(n_sample=1) samples from an MKL VSL stream).  Invalid weights under
+ * replacement (negative, NaN/inf, zero row sum) return PYGB200_ERR_ARG with at::multinomial's message.  One host
+ * synchronisation per (hop, relation): the number of engine outputs a pass consumes is data dependent. */
+int pygb200_sampler_run_weighted(pygb200_sampler* s, int32_t T, int32_t R, int32_t L,
+                                 const pygb200_relation* rels_host, const void* const* seeds,
+                                 const int64_t* n_seeds, const int64_t* num_neighbors, unsigned flags,
+                                 pygb200_mt19937* mt_inout, int64_t* nodes_per_hop,
+                                 int64_t* edges_per_hop, int64_t* n_nodes, int64_t* n_edges, void* stream,
+                                 const void* const* edge_weight, int32_t weight_dtype);
+
 /* Frontier-sharded run for multi-GPU sampling of ONE batch (the reference's own split of
  * the work is dist_neighbor_sample -> merge -> relabel, neighbor_kernel.cpp:296-303,957-978,
  * dist_relabel_kernel.cpp:30-94).  One process per GPU; every rank holds the full CSR and calls this with

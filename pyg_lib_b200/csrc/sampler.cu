@@ -104,6 +104,7 @@ enum {
   ST_ERROR = 8,
   ST_MT_NEXT = 9, ST_MT_LEFT = 10, ST_BLOCKS = 11,
   ST_TICKET_A = 12, ST_TICKET_B = 13,
+  ST_W_WORDS = 14, ST_W_SCR = 15,   // biased pass: engine words it consumes, scratch entries it needs (k_w_count)
   ST_HDR = 16
 };
 
@@ -151,6 +152,7 @@ struct PassArgs {
   // publication of the run's counters + final engine state to the host (publish_run): by k_final, or — latency
   // path — already by the last pass's k_assign_s, as soon as the last counter is known
   i64* pub_host; i64* pub_zero; i64 pub_serial; int pub_words, pub_o_mt;
+  i64 pub_wwords;                                         // engine outputs consumed by biased passes (beside the RandintEngine's blocks)
   // ---- v2 schedule (sampler_v2.cuh): packed 32-bit table of the dst type, refs, optional peer-memory sharding
   u64* pk; int pk_bits;            // slot = node id << 32 | value
   u64* pk_main; int pk_main_bits;  // sharded seeds: `pk` is the replicated seed scratch table, ids go into this one
@@ -726,6 +728,11 @@ __global__ void __launch_bounds__(NT) k_seed(const PassArgs a, const idx_t* __re
 }
 
 #include "sampler_v2.cuh"
+#include "sampler_weighted.cuh"
+const u32 kMklLogfTable[] = {
+#include "mkl_logf_table.inc"
+};
+constexpr int kMklLogfTableN = (int)(sizeof(kMklLogfTable) / sizeof(u32));
 
 // first occurrences of the running pass + tile-local ranks; last block scans the tile counts and
 // updates the dst type's counters.
@@ -947,7 +954,7 @@ __device__ void publish_run(const PassArgs& a, i64 cursor, bool with_flag) {
   // the state buffer is double-buffered: the half the NEXT run uses is cleared here (nobody reads it any more)
   if (a.pub_zero) for (int i = threadIdx.x; i < n_words; i += blockDim.x) a.pub_zero[i] = 0;
   const i64 blocks = rng_blocks_for_units(cursor);
-  const i64 q = a.out0 + 256 * blocks;
+  const i64 q = a.out0 + 256 * blocks + a.pub_wwords;
   const i64 g = (q - 1) / MT_N;
   u32* hout = reinterpret_cast<u32*>(host_st + o_mt);
   for (int i = threadIdx.x; i < MT_N; i += blockDim.x) hout[i] = __ldcg(&a.raw[g * MT_N + i]);
@@ -1432,6 +1439,8 @@ struct pygb200_sampler {
   i64 nd_seeds = 0;
   DevBuf eslot, erank, rec, tile_out, tile_func, tile_off, tile_pos, mtile, raw, st, gen;
   DevBuf fref;              // v2, single GPU: ref of every edge of the running pass
+  DevBuf wkey, widx, wl_bits, wl_tab;   // biased sampling: key / index scratch, MKL logf deviations (bitmap + sorted list)
+  bool wl_ready = false;
   DevBuf seedpk[2];         // v2, sharded: scratch tables for the replicated dedup of the seeds (all-EMPTY between runs; one per side)
   int seedpk_bits[2] = {0, 0};
   int v2_side = 0;          // which of the two packed tables the current / last v2 run uses
@@ -1569,6 +1578,7 @@ extern "C" void pygb200_sampler_destroy(pygb200_sampler* s) {
     for (int i = 0; i < 2; ++i) { t.pk[i].release(); t.vslot[i].release(); }
   }
   s->fref.release(); s->seedpk[0].release(); s->seedpk[1].release();
+  s->wkey.release(); s->widx.release(); s->wl_bits.release(); s->wl_tab.release();
   for (int q = 0; q < s->x.world; ++q) if (q != s->x.rank && s->x.peer[q]) cudaIpcCloseMemHandle(s->x.peer[q]);
   if (s->x.base) cudaFree(s->x.base);
   for (auto& r : s->rels) { r.row.release(); r.colv.release(); r.eid.release(); }
@@ -1852,7 +1862,7 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
                      const void* const* seeds, const int64_t* n_seeds, const int64_t* num_neighbors,
                      unsigned flags, pygb200_mt19937* mt, int64_t* nodes_per_hop, int64_t* edges_per_hop,
                      int64_t* n_nodes_out, int64_t* n_edges_out, cudaStream_t st, const pygb200_shard* shard,
-                     const pygb200_temporal* temporal) {
+                     const pygb200_temporal* temporal, const void* const* edge_weight = nullptr) {
   const bool replace = flags & PYGB200_S_REPLACE, disjoint = flags & PYGB200_S_DISJOINT, idx32 = flags & PYGB200_S_INDEX32;
   // the output binding is one-shot: it is consumed here, before any check can return early, so that a failed run
   // never leaves pointers to arrays its caller is about to free
@@ -1929,6 +1939,22 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
       PYGB_CHECK(n_seeds[t] == 0 || (temporal->seed_time && temporal->seed_time[t]) || (temporal->node_time && temporal->node_time[t]),
                  PYGB200_ERR_ARG, "Seed time needs to be specified");
   }
+  // biased sampling (edge_weight): every relation or none — the reference lets relations without weights draw from its
+  // RandintEngine in between, which interleaves two consumers of one engine stream (not reproduced here)
+  bool weighted = false;
+  if (edge_weight) {
+    int nw = 0;
+    for (int r = 0; r < R; ++r) nw += edge_weight[r] != nullptr;
+    weighted = nw > 0;
+    PYGB_CHECK(nw == 0 || nw == R, PYGB200_ERR_UNSUPPORTED,
+               "biased sampling: edge weights must be given for every relation or for none on this path");
+    PYGB_CHECK(!weighted || !any_time, PYGB200_ERR_ARG, "Biased temporal sampling not yet supported");   // neighbor_kernel.cpp:377-380
+    if (weighted && replace)
+      for (size_t i = 0; i < (size_t)R * L; ++i)
+        PYGB_CHECK(num_neighbors[i] != 1, PYGB200_ERR_UNSUPPORTED,
+                   "biased sampling with replacement and a fan-out of 1: at::multinomial(n_sample=1) draws from an MKL VSL stream "
+                   "(exponential_), which this path does not reproduce");
+  }
   sub_lap(0);
   const bool sharded = shard != nullptr && shard->world > 1;
   const bool nodedup = (flags & PYGB200_S_NO_DEDUP) != 0;
@@ -1945,7 +1971,7 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
   // ids provably fit 32 bits, the wide-table throughput path for everything else.
   static const bool no_lat = getenv("PYGB200_NO_LATENCY_PATH") != nullptr;
   static const bool no_v2 = getenv("PYGB200_NO_V2") != nullptr;
-  bool lat = !synced && !sharded && !nodedup && L > 0 && !no_lat;
+  bool lat = !synced && !sharded && !nodedup && L > 0 && !no_lat && !weighted;
   for (int t = 0; t < T && lat; ++t) lat = n_seeds[t] <= SEED_FUSED_MAX;
   for (int h = 0; h < L && lat; ++h)
     for (int r = 0; r < R && lat; ++r) {
@@ -1953,13 +1979,15 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
       lat = fb[(size_t)rels[r].src_type * (L + 1) + h] <= (i64)LAT_TILES * NT && eb[(size_t)r * L + h] <= (i64)LAT_TILES * ETILE;
     }
   const bool p2p = sharded && shard->exchange != nullptr;
-  bool v2 = !lat && !synced && !nodedup && !disjoint && !any_time && L > 0 && (!no_v2 || p2p) && (!sharded || p2p);
+  bool v2 = !lat && !synced && !nodedup && !disjoint && !any_time && L > 0 && (!no_v2 || p2p || weighted) && (!sharded || p2p);
   std::vector<i64> type_nodes((size_t)T, -1);   // nodes of each type, where a relation with that source type tells us
   for (int r = 0; r < R; ++r) type_nodes[rels[r].src_type] = std::max(type_nodes[rels[r].src_type], (i64)rels[r].num_src_nodes);
   if (v2)   // every node type's id range must be known and fit the packed key (a type that is never a source has no bound)
     for (int t = 0; t < T && v2; ++t) v2 = idx32 || (type_nodes[t] >= 0 && type_nodes[t] < 0xffffffffll);
   if (p2p) PYGB_CHECK(v2 && T == 1 && R == 1 && shard->world <= V2_MAX_W, PYGB200_ERR_UNSUPPORTED,
                       "peer-memory frontier sharding: homogeneous, non-disjoint, bounded fan-outs, node ids < 2^32-1, world <= 16");
+  if (weighted) PYGB_CHECK(v2 && !sharded, PYGB200_ERR_UNSUPPORTED,
+                           "biased sampling on this path: bounded fan-outs (no -1), not disjoint, node ids < 2^32 - 1, one GPU");
   const int XW = p2p ? shard->world : 1, XR = p2p ? shard->rank : 0;
 
   sub_lap(1);
@@ -2076,11 +2104,11 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
   i64 out0;
   bool cont = s->mt_valid && memcmp(&s->mt_expected, mt, sizeof(*mt)) == 0 &&
               s->mt_q + run_outputs_max + run_outputs + 6 * MT_N <= s->raw_cap_words;
-  if (synced) {  // synced runs extend the stream from inside k_count: nothing may run beside them
+  if (synced || weighted) {  // these runs extend the stream themselves (k_count / between passes): nothing may run beside them
     if (int e = wait_all_pregen()) return e;
     s->mt_gen_known = 0;
   }
-  if (!cont || synced) s->mt_defer_target = 0;
+  if (!cont || synced || weighted) s->mt_defer_target = 0;
   if (cont) {
     out0 = s->mt_q;
     const i64 need = out0 + run_outputs + MT_N;
@@ -2256,6 +2284,68 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
     prof_end(tk, "assign", st, Eb);
     PYGB_LAUNCH_CHECK();
     return PYGB200_OK;
+  };
+
+  // ---- biased (edge_weight) pass: count -> the host reads the totals (one synchronisation) -> the raw stream and the key
+  // scratch are sized -> draws -> inserts -> ids.  The engine outputs of biased passes follow the RandintEngine's first
+  // (and, on this path, only) block of 256.
+  i64 wwords = 0;
+  auto biased_error = [&](i64 code) -> int {
+    PYGB_CHECK(code != W_ERR_NEG, PYGB200_ERR_ARG, "invalid multinomial distribution (encountering probability entry < 0)");
+    PYGB_CHECK(code != W_ERR_INF, PYGB200_ERR_ARG, "invalid multinomial distribution (encountering probability entry = infinity or NaN)");
+    PYGB_CHECK(code != W_ERR_SUM, PYGB200_ERR_ARG, "invalid multinomial distribution (sum of probabilities <= 0)");
+    PYGB_CHECK(code != W_ERR_CATEGORIES, PYGB200_ERR_ARG, "number of categories cannot exceed 2^24");
+    return PYGB200_OK;
+  };
+  if (weighted && !s->wl_ready) {
+    if (int e = s->wl_tab.ensure(sizeof(kMklLogfTable), 0, st)) return e;
+    if (int e = s->wl_bits.ensure((size_t)1 << 21, 0, st)) return e;
+    PYGB_CUDA(cudaMemcpyAsync(s->wl_tab.p, kMklLogfTable, sizeof(kMklLogfTable), cudaMemcpyHostToDevice, st));
+    PYGB_CUDA(cudaMemsetAsync(s->wl_bits.p, 0, (size_t)1 << 21, st));
+    k_w_log_bitmap<<<ceil_div(kMklLogfTableN, NT), NT, 0, st>>>(s->wl_tab.as<u32>(), kMklLogfTableN, s->wl_bits.as<u32>());
+    PYGB_LAUNCH_CHECK();
+    s->wl_ready = true;
+  }
+  auto biased_pass = [&](PassArgs& a, int r, i64 Fb) -> int {
+    void* tk = prof_begin(st);
+    if (idx32) launch_pdl(k_w_count<int32_t>, grid_for(Fb, NT, s->sm_count), NT, st, a);
+    else launch_pdl(k_w_count<int64_t>, grid_for(Fb, NT, s->sm_count), NT, st, a);
+    prof_end(tk, "count", st, Fb);
+    PYGB_LAUNCH_CHECK();
+    if (int e = read_state()) return e;
+    const i64 F = s->st_host[ST_PASS_F], E = s->st_host[ST_PASS_E], W = s->st_host[ST_W_WORDS], S = s->st_host[ST_W_SCR];
+    if (int e = biased_error(s->st_host[ST_ERROR])) return e;
+    if (int e = s->wkey.ensure((size_t)std::max<i64>(S, 1) * 4, 0, st)) return e;
+    if (int e = s->widx.ensure((size_t)std::max<i64>(S, 1) * 4, 0, st)) return e;
+    const i64 need = out0 + 256 + wwords + W + 2 * MT_N;
+    const i64 cap_need = need + 2 * (i64)s->jump_S + 8 * MT_N;
+    if (cap_need > raw_cap) {
+      PYGB_CHECK(cap_need < ((i64)1 << 33), PYGB200_ERR_UNSUPPORTED, "biased sampling: a run may consume at most 2^33 engine outputs");
+      i64 gen_now = 0;
+      PYGB_CUDA(cudaMemcpyAsync(&gen_now, s->gen.p, 8, cudaMemcpyDeviceToHost, st));
+      PYGB_CUDA(cudaStreamSynchronize(st));
+      if (int e = s->raw.ensure((size_t)cap_need * 4, (size_t)gen_now * 4, st)) return e;
+      raw_cap = s->raw_cap_words = (i64)(s->raw.cap / 4);
+    }
+    if (int e = mt_request(s, st, need)) return e;
+    a.raw = s->raw.as<u32>(); a.raw_cap = raw_cap;
+    WArgs wa;
+    wa.weight = reinterpret_cast<const float*>(edge_weight[r]);
+    wa.skey = s->wkey.as<float>(); wa.sidx = s->widx.as<u32>();
+    wa.lbits = s->wl_bits.as<u32>(); wa.ltab = s->wl_tab.as<u32>(); wa.ltab_n = kMklLogfTableN;
+    wa.wbase = out0 + 256 + wwords;
+    wwords += W;
+    tk = prof_begin(st);
+    const int gw = (int)std::min<i64>(std::max<i64>(ceil_div(F, NT / 32), 1), (i64)s->sm_count * 16);
+    if (idx32) launch_pdl(k_w_sample<int32_t>, gw, NT, st, a, wa); else launch_pdl(k_w_sample<int64_t>, gw, NT, st, a, wa);
+    prof_end(tk, "sample", st, E);
+    PYGB_LAUNCH_CHECK();
+    const i64 Eg = std::max<i64>(E, 1);
+    tk = prof_begin(st);
+    launch_pdl(k_v2_insert<false>, grid_for(Eg, 4 * NT, s->sm_count), NT, st, a);
+    prof_end(tk, "insert", st, E);
+    PYGB_LAUNCH_CHECK();
+    return v2_ids(a, Eg);
   };
 
   ht_lap(1);
@@ -2446,7 +2536,7 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
         a.o_eph = lay.o_eph + r * L + h;
         a.lk_colv = lk_colv; a.lk_vals = lk_vals;
         with_hop_end(a);
-        if (int e = idx32 ? launch_count<int32_t>(s, a, Fb, lk_E, st) : launch_count<int64_t>(s, a, Fb, lk_E, st)) return e;
+        if (!weighted) if (int e = idx32 ? launch_count<int32_t>(s, a, Fb, lk_E, st) : launch_count<int64_t>(s, a, Fb, lk_E, st)) return e;
         if (v2) {
           // does any later pass insert into this dst type's table?  (else the ids need not be written back)
           a.v2_writeback = 0;
@@ -2454,6 +2544,11 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
             for (int r2 = (h2 == h ? r + 1 : 0); r2 < R && !a.v2_writeback; ++r2)
               a.v2_writeback = rels[r2].dst_type == dst_t && num_neighbors[(size_t)r2 * L + h2] != 0 &&
                                fb[(size_t)rels[r2].src_type * (L + 1) + h2] != 0 && eb[(size_t)r2 * L + h2] != 0;
+          if (weighted) {
+            if (int e = biased_pass(a, r, Fb)) return e;
+            if (r == last_r) hop_closed = true;
+            continue;
+          }
           a.group = sample_group_lanes(k);
           const int gs = grid_for(p2p ? ceil_div(Fb, XW) + 1 : Fb, sample_nodes_per_block(a.group), s->sm_count);
           void* tk = prof_begin(st);
@@ -2594,6 +2689,7 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
       a.pub_host = s->st_host_dev; a.pub_zero = dst_other; a.pub_serial = s->run_serial; a.pub_words = (int)lay.words;
       a.pub_o_mt = lay.o_mt;
     }
+    a.pub_wwords = wwords;
     void* tkf = prof_begin(st);
     launch_pdl(k_final, lk_colv ? grid_for(lk_E, NT, s->sm_count) : 1, NT, st, a);
     prof_end(tkf, "final", st, 1);
@@ -2649,6 +2745,7 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
   if (pub_w_list >= 0) s->st_host[pub_w_list] = (i64)((u64)s->st_host[lay.words] & 0xffffffffffull);
   const i64* hs = s->st_host;
   PYGB_CHECK(hs[ST_ERROR] != 2, PYGB200_ERR_INTERNAL, "sampler: a peer rank did not reach a cross-GPU barrier in time (frontier-sharded run; PYGB200_XBARRIER_TIMEOUT_MS)");
+  if (int e = biased_error(hs[ST_ERROR])) return e;
   PYGB_CHECK(hs[ST_ERROR] == 0, PYGB200_ERR_INTERNAL, "sampler: mt19937 stream buffer too small (internal bound violated)");
   s->dirty = false;
   if (lat) {   // counters from the write-once words of the schedule
@@ -2706,9 +2803,9 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
   // on the side stream (one CTA, overlaps the caller's work and the next run's first kernels)
   s->st_o_list = lat && cur_list[0].w >= 0 ? cur_list[0].w : lay.o_list;
   s->mt_expected = *mt;
-  s->mt_q = out0 + 256 * hs[ST_BLOCKS];
+  s->mt_q = out0 + 256 * hs[ST_BLOCKS] + wwords;
   s->mt_valid = true;
-  if (!synced) {
+  if (!synced && !weighted) {
     const i64 target = std::min<i64>(s->raw_cap_words - 2 * MT_N, s->mt_q + 2 * run_outputs + 2 * MT_N);
     // this run's kernels (which may extend the stream themselves) are done; the launch itself is left to the
     // next run (see above) so that it costs no host time between two runs
@@ -2746,6 +2843,22 @@ extern "C" int pygb200_sampler_run_temporal(pygb200_sampler* s, int32_t T, int32
   std::lock_guard<std::mutex> lock(s->mu);
   return sampler_run_impl(s, T, R, L, rels, seeds, n_seeds, num_neighbors, flags, mt, nodes_per_hop, edges_per_hop,
                           n_nodes_out, n_edges_out, (cudaStream_t)stream, nullptr, temporal);
+}
+
+extern "C" int pygb200_sampler_run_weighted(pygb200_sampler* s, int32_t T, int32_t R, int32_t L,
+                                            const pygb200_relation* rels, const void* const* seeds,
+                                            const int64_t* n_seeds, const int64_t* num_neighbors, unsigned flags,
+                                            pygb200_mt19937* mt, int64_t* nodes_per_hop, int64_t* edges_per_hop,
+                                            int64_t* n_nodes_out, int64_t* n_edges_out, void* stream,
+                                            const void* const* edge_weight, int32_t weight_dtype) {
+  PYGB_CHECK(s && seeds && n_seeds && mt && (rels || R == 0) && (num_neighbors || L == 0 || R == 0), PYGB200_ERR_ARG,
+             "pygb200_sampler_run_weighted: null argument");
+  PYGB_CHECK(T >= 1 && T <= 1024 && R >= 0 && L >= 0, PYGB200_ERR_ARG, "pygb200_sampler_run_weighted: bad T/R/L");
+  PYGB_CHECK(weight_dtype == PYGB200_F32, PYGB200_ERR_UNSUPPORTED,
+             "biased sampling: float32 edge weights only (the reference's random stream and key arithmetic depend on the weight dtype)");
+  std::lock_guard<std::mutex> lock(s->mu);
+  return sampler_run_impl(s, T, R, L, rels, seeds, n_seeds, num_neighbors, flags, mt, nodes_per_hop, edges_per_hop,
+                          n_nodes_out, n_edges_out, (cudaStream_t)stream, nullptr, nullptr, edge_weight);
 }
 
 extern "C" int pygb200_sampler_run_sharded(pygb200_sampler* s, int32_t T, int32_t R, int32_t L,

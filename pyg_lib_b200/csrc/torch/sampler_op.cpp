@@ -8,6 +8,7 @@
 // There is no CPU kernel: CPU tensors raise.
 #include <ATen/CPUGeneratorImpl.h>
 
+#include <algorithm>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -113,7 +114,19 @@ void check_arguments(bool has_node_time, bool has_edge_time, bool has_seed_time,
   TORCH_CHECK(!has_edge_time || disjoint, "Temporal sampling needs to create disjoint subgraphs");
   TORCH_CHECK(!(has_node_time && has_edge_time), "Only one of node-level or edge-level sampling is supported ");
   TORCH_CHECK(!has_edge_time || has_seed_time, "Seed time needs to be specified");
-  TORCH_CHECK(!has_weight, "pyg_lib_b200: biased (edge_weight) neighbor sampling is not implemented on the B200 path");
+  TORCH_CHECK(!(has_node_time && has_weight), "Biased node temporal sampling not yet supported");   // neighbor_kernel.cpp:377-380
+  TORCH_CHECK(!(has_edge_time && has_weight), "Biased edge temporal sampling not yet supported");
+}
+
+// edge weights of one relation for the biased path: float32, one per edge, on the sampler's device
+const void* weight_ptr(const at::Tensor& w, const at::Tensor& col, const at::Device& dev) {
+  TORCH_CHECK(w.device() == dev, "'edge_weight' must live on ", dev, " (pyg_lib_b200 has no CPU fallback)");
+  TORCH_CHECK(w.scalar_type() == at::kFloat,
+              "pyg_lib_b200: biased sampling takes float32 edge weights (the reference's random stream and key arithmetic "
+              "depend on the weight dtype; only float32 is reproduced), got ", w.scalar_type());
+  TORCH_CHECK(w.is_contiguous() && w.dim() == 1, "'edge_weight' must be a contiguous one-dimensional tensor");
+  TORCH_CHECK(w.numel() == col.numel(), "'edge_weight' must have one entry per edge");
+  return w.data_ptr();
 }
 
 const int64_t* time_ptr(const at::Tensor& t, const char* name, const at::Device& dev) {
@@ -182,8 +195,17 @@ neighbor_sample_cuda(const at::Tensor& rowptr, const at::Tensor& col, const at::
       void* np = base + (return_edge_id ? 3 : 2) * ecap;
       PYGB_TORCH_CALL(pygb200_sampler_bind_outputs(s, 1, 1, &rp, &cp, &ep, &np, &ecap, &ncap));
     }
+    // biased sampling; with only "all neighbours" fan-outs the weights are never looked at (neighbor_kernel.cpp:259-265)
+    const void* wp = nullptr;
+    if (edge_weight.has_value() && std::any_of(num_neighbors.begin(), num_neighbors.end(), [](int64_t k) { return k >= 0; }))
+      wp = weight_ptr(*edge_weight, col, seed.device());
     CpuEngine eng;
     if (g_ot.on) ot1 = OpTimes::now();
+    if (wp) {
+      TORCH_CHECK(!disjoint, "pyg_lib_b200: biased sampling of disjoint subgraphs is not implemented on the B200 path");
+      PYGB_TORCH_CALL(pygb200_sampler_run_weighted(s, 1, 1, L, &rel, seeds, &n_seed, num_neighbors.data(), flags, &eng.mt,
+                                                   nph.data(), eph.data(), &n_nodes, &n_edges, stream, &wp, PYGB200_F32));
+    } else
     PYGB_TORCH_CALL(pygb200_sampler_run_temporal(s, 1, 1, L, &rel, seeds, &n_seed, num_neighbors.data(), flags, &eng.mt,
                                                  nph.data(), eph.data(), &n_nodes, &n_edges, stream,
                                                  (nt || et) ? &tmp : nullptr));
@@ -226,6 +248,7 @@ dist_neighbor_sample_cuda(const at::Tensor& rowptr, const at::Tensor& col, const
                           bool replace, bool directed, bool disjoint, std::string temporal_strategy) {
   TORCH_CHECK(temporal_strategy == "uniform" || temporal_strategy == "last", "No valid temporal strategy found");
   check_arguments(node_time.has_value(), edge_time.has_value(), seed_time.has_value(), edge_weight.has_value(), disjoint);
+  TORCH_CHECK(!edge_weight.has_value(), "pyg_lib_b200: biased (edge_weight) dist_neighbor_sample is not implemented on the B200 path");
   TORCH_CHECK(seed.is_cuda(), "pyg_lib_b200: dist_neighbor_sample expects CUDA tensors (no CPU fallback)");
   const auto st = seed.scalar_type();
   TORCH_CHECK(st == at::kLong || st == at::kInt, "dist_neighbor_sample: index tensors must be int64 or int32");
@@ -389,7 +412,27 @@ hetero_neighbor_sample_cuda(const std::vector<node_type>& node_types, const std:
         PYGB_TORCH_CALL(pygb200_sampler_bind_outputs(s, T, R, rp.data(), cp.data(), ep.data(), np.data(), ecap.data(), ncap.data()));
       }
     }
+    // biased sampling: every relation must come with weights on this path (the reference lets weighted and unweighted
+    // relations share one engine stream; that interleaving is not reproduced)
+    std::vector<const void*> wp(std::max(R, 1), nullptr);
+    bool biased = false;
+    if (edge_weight_dict.has_value() && edge_weight_dict->size() > 0 &&
+        std::any_of(nn.begin(), nn.end(), [](int64_t k) { return k >= 0; })) {
+      biased = true;
+      for (int r = 0; r < R; ++r) {
+        const rel_type rk = to_rel_type(edge_types[r]);
+        TORCH_CHECK(edge_weight_dict->contains(rk), "pyg_lib_b200: 'edge_weight_dict' must hold weights for every edge type (missing '", rk,
+                    "'): mixing biased and uniform relations in one call is not implemented on the B200 path");
+        wp[r] = weight_ptr(edge_weight_dict->at(rk), col_dict.at(rk), dev);
+      }
+      TORCH_CHECK(!disjoint, "pyg_lib_b200: biased sampling of disjoint subgraphs is not implemented on the B200 path");
+    }
     CpuEngine eng;
+    if (biased)
+      PYGB_TORCH_CALL(pygb200_sampler_run_weighted(s, T, R, (int)L, rels.data(), seeds.data(), n_seeds.data(), nn.data(), flags,
+                                                   &eng.mt, nph.data(), eph.data(), n_nodes.data(), n_edges.data(), stream,
+                                                   wp.data(), PYGB200_F32));
+    else
     PYGB_TORCH_CALL(pygb200_sampler_run_temporal(s, T, R, (int)L, rels.data(), seeds.data(), n_seeds.data(), nn.data(), flags,
                                                  &eng.mt, nph.data(), eph.data(), n_nodes.data(), n_edges.data(), stream,
                                                  any ? &tmp : nullptr));

@@ -46,9 +46,10 @@ def neighbor_sample(
     :obj:`(rowptr, col)`.  Returns ``(row, col, node_id, edge_id, num_sampled_nodes_per_hop,
     num_sampled_edges_per_hop)`` exactly like the reference (pyg_lib/sampler/__init__.py:11-100).
 
-    Node-/edge-level temporal sampling (`node_time`/`edge_time`/`seed_time`, strategies 'uniform' and 'last')
-    is supported; biased (`edge_weight`) sampling raises: it cannot be reproduced bit for bit on this path and
-    there is no CPU fallback."""
+    Node-/edge-level temporal sampling (`node_time`/`edge_time`/`seed_time`, strategies 'uniform' and 'last') and biased
+    sampling (`edge_weight`: float32, one weight per edge; neighbor_kernel.cpp:245-285) are supported, both bit-identical
+    to the reference including the state of the CPU generator afterwards.  Biased sampling on this path: bounded fan-outs,
+    not disjoint, and with `replace=True` no fan-out of 1 (`DESIGN.md` §3.8); it costs one host synchronisation per hop."""
     return _neighbor_sample_op(rowptr, col, seed, num_neighbors, node_time, edge_time, seed_time, edge_weight, csc,
                                replace, directed, disjoint, temporal_strategy, return_edge_id)
 

@@ -416,3 +416,70 @@ def mag240m_shaped(scale: float, device='cpu', seed0: int = 10):
         col_d[k] = torch.randint(0, sizes[k[2]], (e,), generator=g, device=device, dtype=torch.int64)
         rowptr_d[k] = rowptr
     return sizes, rowptr_d, col_d
+
+
+# ------------------------------------------------------------------------------------- biased (edge_weight) sampling
+# graph / seeds as in HOMO_CASES; `weights`: how the float32 edge weights are drawn (build_weights)
+WEIGHTED_CASES: Dict[str, dict] = {
+    # known-answer vector of test/csrc/sampler/test_neighbor.cpp:300-329 (cycle graph, only even edges have weight)
+    'kat_cycle': dict(graph=('cycle', 6), seeds=[0, 1], num_neighbors=[1], rng_seed=0, weights='even_edges'),
+    'rand_float': dict(graph=('rand', 2000, 20, 1), n_seeds=64, num_neighbors=[10, 5], rng_seed=11, weights='uniform'),
+    'rand_float_rep': dict(graph=('rand', 2000, 20, 1), n_seeds=64, num_neighbors=[10, 5], rng_seed=12, weights='uniform', replace=True),
+    # masked neighbours (weight 0 -> key -inf): fan-out > number of positive weights -> at::topk's tie order decides
+    'masked': dict(graph=('rand', 1500, 16, 2), n_seeds=48, num_neighbors=[8, 4], rng_seed=13, weights='masked'),
+    'masked_rep': dict(graph=('rand', 1500, 16, 2), n_seeds=48, num_neighbors=[8, 4], rng_seed=14, weights='masked_pos', replace=True),
+    'ones': dict(graph=('rand', 2500, 24, 3), n_seeds=40, num_neighbors=[15, 10], rng_seed=15, weights='ones'),
+    'quantized': dict(graph=('rand', 1200, 18, 4), n_seeds=40, num_neighbors=[6, 6], rng_seed=16, weights='quantized'),
+    'three_hops_csc': dict(graph=('rand', 3000, 8, 5), n_seeds=16, num_neighbors=[4, 4, 4], rng_seed=17, weights='uniform', csc=True),
+    # hubs: 70,000 neighbours -> std::partial_sort branch of at::topk (k * 64 <= n), long running sums under replacement
+    'hub': dict(graph=('rand', 400, 10, 7, [(5, 70000), (77, 65540)]), seeds=[5, 77, 3, 9, 200], num_neighbors=[10, 5], rng_seed=18,
+                weights='uniform'),
+    'hub_masked': dict(graph=('rand', 400, 10, 7, [(5, 70000), (77, 65540)]), seeds=[5, 77, 3, 9, 200], num_neighbors=[12, 3], rng_seed=19,
+                       weights='masked_heavy'),
+    'hub_rep': dict(graph=('rand', 400, 10, 7, [(5, 70000), (77, 65540)]), seeds=[5, 77, 3, 9, 200], num_neighbors=[10, 5], rng_seed=20,
+                    weights='uniform', replace=True),
+    'zero_fanout_mix': dict(graph=('rand', 800, 12, 8), n_seeds=20, num_neighbors=[5, 0, 3], rng_seed=21, weights='uniform'),
+    'dup_seeds': dict(graph=('rand', 600, 12, 9), seeds=[7, 7, 3, 7, 11, 3], num_neighbors=[4, 4], rng_seed=22, weights='uniform'),
+}
+HETERO_WEIGHTED_CASES: Dict[str, dict] = {
+    'kat_cycle': dict(kind='cycle', num_neighbors=[1], rng_seed=0, weights='even_edges', seeds=[0, 1]),   # test_neighbor.cpp:331-378
+    'mag_w': dict(kind='mag', sizes=dict(paper=600, author=400, institution=20), avg_deg=6, n_seeds=dict(paper=16),
+                  num_neighbors=[5, 3], rng_seed=31, gseed=31, weights='uniform'),
+    'mag_w_rep': dict(kind='mag', sizes=dict(paper=600, author=400, institution=20), avg_deg=6, n_seeds=dict(paper=8, author=8),
+                      num_neighbors=[4, 4], rng_seed=32, gseed=33, weights='uniform', replace=True),
+    'mag_w_masked_csc': dict(kind='mag', sizes=dict(paper=600, author=400, institution=20), avg_deg=6, n_seeds=dict(paper=16),
+                             num_neighbors=[6, 3], rng_seed=33, gseed=31, weights='masked', csc=True),
+}
+
+
+def build_weights(kind: str, rowptr: torch.Tensor, seed: int) -> torch.Tensor:
+    E = int(rowptr[-1])
+    g = torch.Generator().manual_seed(77000 + seed)
+    if kind == 'even_edges':
+        return torch.stack([torch.ones(E // 2), torch.zeros(E // 2)], -1).view(-1)
+    if kind == 'uniform':
+        return torch.rand(E, generator=g)
+    if kind == 'ones':
+        return torch.ones(E)
+    if kind == 'quantized':
+        return torch.randint(0, 3, (E,), generator=g).float()
+    if kind in ('masked', 'masked_heavy', 'masked_pos'):
+        w = torch.rand(E, generator=g) * (torch.rand(E, generator=g) < (0.03 if kind == 'masked_heavy' else 0.4))
+        if kind == 'masked_pos':   # at::multinomial wants a positive sum in every sampled row
+            first = rowptr[:-1][rowptr[:-1] < rowptr[1:]]
+            w[first] += 0.25
+        return w
+    raise ValueError(kind)
+
+
+def build_weighted(case: dict):
+    rowptr, col, seed = build_homo(case)
+    return rowptr, col, seed, build_weights(case['weights'], rowptr, case['rng_seed'])
+
+
+def build_hetero_weighted(case: dict):
+    node_types, edge_types, rowptr_d, col_d, seed_d, nn_d = build_hetero(case)
+    if 'seeds' in case:
+        seed_d = {'paper': torch.tensor(case['seeds'])}
+    w_d = {k: build_weights(case['weights'], rowptr_d[k], case['rng_seed'] + i) for i, k in enumerate(rowptr_d)}
+    return node_types, edge_types, rowptr_d, col_d, seed_d, nn_d, w_d
