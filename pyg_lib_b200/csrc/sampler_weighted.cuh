@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(NT) k_w_count(const PassArgs a) {
 // LARGEST 64-bit code is the next pick
 __device__ __forceinline__ u64 w_code(float x, u32 idx) {
   const u32 b = __float_as_uint(x);
-  const u32 o = (x != x) ? 0xffffffffu : ((b & 0x80000000u) ? ~b : (b | 0x80000000u));
+  const u32 o = (x != x) ? 0xfffffffeu : ((b & 0x80000000u) ? ~b : (b | 0x80000000u));   // (+inf is 0xff800000; ~0 stays free: "before the first pick")
   return ((u64)o << 32) | (u64)(0xffffffffu - idx);
 }
 
@@ -196,7 +196,11 @@ __global__ void __launch_bounds__(NT) k_w_sample(const PassArgs a, const WArgs w
         if (!err && !(sum > 0.f)) err = W_ERR_SUM;
       }
       err = __shfl_sync(0xffffffffu, err, 0); sum = __shfl_sync(0xffffffffu, sum, 0);
-      if (err) { if (lane == 0) a.st[ST_ERROR] = err; continue; }
+      if (err) {   // reported by the host when the run ends; the node's slots still get valid edges so that the rest of the pass stays in bounds
+        if (lane == 0) a.st[ST_ERROR] = err;
+        for (i64 t = lane; t < k; t += 32) emit(t, r.rs);
+        continue;
+      }
       __syncwarp();
       for (int j = lane; j < n; j += 32) key[j] = __fdiv_rn(key[j], sum);
       __syncwarp();

@@ -190,6 +190,7 @@ def test_errors(lib):
     _cmp(out, W.neighbor_sample(rowptr, col, seed.cpu(), [3, 2], w))
     # negative / NaN weights without replacement flow through the key arithmetic like in the reference
     wodd = w.clone(); wodd[::5] = -wodd[::5]; wodd[3::11] = float('nan'); wodd[7::13] = float('inf')
+    wodd[rowptr[:-1][(rowptr[:-1] < rowptr[1:]) & (torch.arange(300) % 3 == 0)]] = float('nan')   # NaN key at in-row index 0
     torch.manual_seed(4)
     out = lib.sampler.neighbor_sample(rp, cl, seed, [3, 2], edge_weight=wodd.to(DEV))
     torch.manual_seed(4)
