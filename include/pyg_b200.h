@@ -176,11 +176,12 @@ int pygb200_sampler_run_temporal(pygb200_sampler* s, int32_t T, int32_t R, int32
  * log(u) / weight without — reproducing the reference bit for bit INCLUDING the CPU generator stream it consumes
  * (uniform_/random64 outputs), torch's CPU float32 log (MKL; table of its deviations from the correctly rounded log)
  * and at::topk's libstdc++ tie behaviour.  edge_weight[r]: device pointer to relation r's weights (one per edge,
- * weight_dtype = PYGB200_F32), for EVERY relation.  Limits of this path (PYGB200_ERR_UNSUPPORTED otherwise): bounded
- * fan-outs (no -1), not disjoint, not temporal (the reference refuses that too), node ids < 2^32 - 1, one GPU, and with
- * replacement no fan-out of 1 (at::multinomial(n_sample=1) samples from an MKL VSL stream).  Invalid weights under
- * replacement (negative, NaN/inf, zero row sum) return PYGB200_ERR_ARG with at::multinomial's message.  One host
- * synchronisation per (hop, relation): the number of engine outputs a pass consumes is data dependent. */
+ * weight_dtype = PYGB200_F32), for EVERY relation.  All flags of pygb200_sampler_run apply (PYGB200_S_DISJOINT,
+ * PYGB200_S_REPLACE, PYGB200_S_NO_DEDUP = the reference's distributed one-hop sampling, -1 fan-outs).  Limits
+ * (PYGB200_ERR_UNSUPPORTED): weights for every relation or none; with replacement no fan-out of 1 (at::multinomial(n_sample=1)
+ * samples from an MKL VSL stream); one GPU; not temporal (the reference refuses that too).  Invalid weights under replacement
+ * (negative, NaN/inf, zero row sum) return PYGB200_ERR_ARG with at::multinomial's message.  One host synchronisation per
+ * (hop, relation): the number of engine outputs a pass consumes is data dependent. */
 int pygb200_sampler_run_weighted(pygb200_sampler* s, int32_t T, int32_t R, int32_t L,
                                  const pygb200_relation* rels_host, const void* const* seeds,
                                  const int64_t* n_seeds, const int64_t* num_neighbors, unsigned flags,

@@ -1986,8 +1986,7 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
     for (int t = 0; t < T && v2; ++t) v2 = idx32 || (type_nodes[t] >= 0 && type_nodes[t] < 0xffffffffll);
   if (p2p) PYGB_CHECK(v2 && T == 1 && R == 1 && shard->world <= V2_MAX_W, PYGB200_ERR_UNSUPPORTED,
                       "peer-memory frontier sharding: homogeneous, non-disjoint, bounded fan-outs, node ids < 2^32-1, world <= 16");
-  if (weighted) PYGB_CHECK(v2 && !sharded, PYGB200_ERR_UNSUPPORTED,
-                           "biased sampling on this path: bounded fan-outs (no -1), not disjoint, node ids < 2^32 - 1, one GPU");
+  if (weighted) PYGB_CHECK(!sharded, PYGB200_ERR_UNSUPPORTED, "biased sampling is not frontier-sharded: one GPU per batch");
   const int XW = p2p ? shard->world : 1, XR = p2p ? shard->rank : 0;
 
   sub_lap(1);
@@ -2306,15 +2305,20 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
     PYGB_LAUNCH_CHECK();
     s->wl_ready = true;
   }
-  auto biased_pass = [&](PassArgs& a, int r, i64 Fb) -> int {
+  // step 1: degrees -> per-node edge / engine-word / scratch offsets; the host reads the pass's totals (st_host)
+  auto biased_count = [&](const PassArgs& a, i64 F_grid, i64 E_prev) -> int {
+    const int g = std::max(grid_for(F_grid, NT, s->sm_count), a.lk_colv ? grid_for(E_prev, NT, s->sm_count) : 1);
     void* tk = prof_begin(st);
-    if (idx32) launch_pdl(k_w_count<int32_t>, grid_for(Fb, NT, s->sm_count), NT, st, a);
-    else launch_pdl(k_w_count<int64_t>, grid_for(Fb, NT, s->sm_count), NT, st, a);
-    prof_end(tk, "count", st, Fb);
+    if (idx32) launch_pdl(k_w_count<int32_t>, g, NT, st, a); else launch_pdl(k_w_count<int64_t>, g, NT, st, a);
+    prof_end(tk, "count", st, F_grid);
     PYGB_LAUNCH_CHECK();
     if (int e = read_state()) return e;
+    return biased_error(s->st_host[ST_ERROR]);
+  };
+  // step 2: size the key scratch and the raw stream from those totals, then draw: row / edge id / global dst id of every
+  // sampled edge at its final position (what the schedules' insert stages start from)
+  auto biased_draws = [&](PassArgs& a, int r) -> int {
     const i64 F = s->st_host[ST_PASS_F], E = s->st_host[ST_PASS_E], W = s->st_host[ST_W_WORDS], S = s->st_host[ST_W_SCR];
-    if (int e = biased_error(s->st_host[ST_ERROR])) return e;
     if (int e = s->wkey.ensure((size_t)std::max<i64>(S, 1) * 4, 0, st)) return e;
     if (int e = s->widx.ensure((size_t)std::max<i64>(S, 1) * 4, 0, st)) return e;
     const i64 need = out0 + 256 + wwords + W + 2 * MT_N;
@@ -2335,15 +2339,21 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
     wa.lbits = s->wl_bits.as<u32>(); wa.ltab = s->wl_tab.as<u32>(); wa.ltab_n = kMklLogfTableN;
     wa.wbase = out0 + 256 + wwords;
     wwords += W;
-    tk = prof_begin(st);
+    void* tk = prof_begin(st);
     const int gw = (int)std::min<i64>(std::max<i64>(ceil_div(F, NT / 32), 1), (i64)s->sm_count * 16);
     if (idx32) launch_pdl(k_w_sample<int32_t>, gw, NT, st, a, wa); else launch_pdl(k_w_sample<int64_t>, gw, NT, st, a, wa);
     prof_end(tk, "sample", st, E);
     PYGB_LAUNCH_CHECK();
-    const i64 Eg = std::max<i64>(E, 1);
-    tk = prof_begin(st);
+    return PYGB200_OK;
+  };
+  // v2 schedule: count -> draws -> inserts -> ids
+  auto biased_pass = [&](PassArgs& a, int r, i64 Fb) -> int {
+    if (int e = biased_count(a, Fb, 0)) return e;
+    if (int e = biased_draws(a, r)) return e;
+    const i64 Eg = std::max<i64>(s->st_host[ST_PASS_E], 1);
+    void* tk = prof_begin(st);
     launch_pdl(k_v2_insert<false>, grid_for(Eg, 4 * NT, s->sm_count), NT, st, a);
-    prof_end(tk, "insert", st, E);
+    prof_end(tk, "insert", st, Eg);
     PYGB_LAUNCH_CHECK();
     return v2_ids(a, Eg);
   };
@@ -2601,6 +2611,18 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
           if (r == last_r) hop_closed = true;
           continue;
         }
+        if (weighted) {   // wide table (disjoint / 64-bit ids): biased draws, then the expand-from-edge-ids stage the sharded path uses
+          if (int e = biased_count(a, Fb, lk_E)) return e;
+          if (int e = biased_draws(a, r)) return e;
+          if (nodedup) continue;   // (row / edge id / global id are already what a distributed hop returns)
+          PassArgs d = a;
+          d.phase = 2;
+          if (int e = idx32 ? launch_sample<int32_t>(s, d, Fb, Eb, st) : launch_sample<int64_t>(s, d, Fb, Eb, st)) return e;
+          if (int e = idx32 ? launch_rest<int32_t>(s, a, Fb, Eb, false, st, false) : launch_rest<int64_t>(s, a, Fb, Eb, false, st, false)) return e;
+          lk_colv = a.colv; lk_vals = a.vals; lk_E = Eb;
+          if (r == last_r) hop_closed = true;
+          continue;
+        }
         if (nodedup) {   // draw + gather only: global ids stay in `colv`, nothing is mapped, no lookup follows
           PassArgs d = a;
           d.phase = 3;
@@ -2637,7 +2659,7 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
         const i64 F = s->st_host[lay.o_end + src_t] - s->st_host[lay.o_begin + src_t];
         if (F == 0) continue;
         if (int e = ensure_frontier_scratch(s, F, st)) return e;
-        if (k > 0) {  // draws possible: make sure the raw stream buffer can hold this pass
+        if (k > 0 && !weighted) {  // draws possible: make sure the raw stream buffer can hold this pass
           const i64 upu = rels[r].num_edges < 65536 ? 1 : (rels[r].num_edges < ((i64)1 << 32) ? 3 : 7);
           if (int e = read_state()) return e;
           const i64 need = out0 + 256 * (rng_blocks_for_units(s->st_host[ST_CURSOR] + sat_mul(sat_mul(F, k), upu)) + 1) + 3 * MT_N;
@@ -2652,8 +2674,12 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
         PassArgs a = make_args(src_t, dst_t, r);
         a.fanout = k;
         a.o_eph = lay.o_eph + r * L + h;
-        if (int e = idx32 ? launch_count<int32_t>(s, a, F, 0, st) : launch_count<int64_t>(s, a, F, 0, st)) return e;
-        if (int e = read_state()) return e;
+        if (weighted) {
+          if (int e = biased_count(a, F, 0)) return e;
+        } else {
+          if (int e = idx32 ? launch_count<int32_t>(s, a, F, 0, st) : launch_count<int64_t>(s, a, F, 0, st)) return e;
+          if (int e = read_state()) return e;
+        }
         const i64 E = s->st_host[ST_PASS_E];
         if (E == 0) continue;  // (a hop whose last pass emits nothing is closed by the standalone kernel below)
         const i64 rel_before = s->st_host[ST_PASS_BASE], list_now = s->st_host[lay.o_list + dst_t];
@@ -2664,13 +2690,20 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
         a = make_args(src_t, dst_t, r);  // pointers may have moved
         a.fanout = k;
         a.o_eph = lay.o_eph + r * L + h;
+        if (weighted) if (int e = biased_draws(a, r)) return e;   // (row / edge id / global dst id of every sampled edge)
         if (nodedup) {
+          if (weighted) continue;
           a.phase = 3;
           if (int e = idx32 ? launch_sample<int32_t>(s, a, F, E, st) : launch_sample<int64_t>(s, a, F, E, st)) return e;
           continue;
         }
         with_hop_end(a);
-        if (int e = idx32 ? launch_rest<int32_t>(s, a, F, E, true, st) : launch_rest<int64_t>(s, a, F, E, true, st)) return e;
+        if (weighted) {
+          PassArgs d = a;
+          d.phase = 2;   // expand from the edge ids: gather, hash insert
+          if (int e = idx32 ? launch_sample<int32_t>(s, d, F, E, st) : launch_sample<int64_t>(s, d, F, E, st)) return e;
+          if (int e = idx32 ? launch_rest<int32_t>(s, a, F, E, true, st, false) : launch_rest<int64_t>(s, a, F, E, true, st, false)) return e;
+        } else if (int e = idx32 ? launch_rest<int32_t>(s, a, F, E, true, st) : launch_rest<int64_t>(s, a, F, E, true, st)) return e;
         if (r == last_r) hop_closed = true;
       }
     }

@@ -94,6 +94,7 @@ __device__ __forceinline__ W3 w_classify(i64 deg, i64 k, int replace) {
 template <typename idx_t>
 __global__ void __launch_bounds__(NT) k_w_count(const PassArgs a) {
   pdl_enter();
+  deferred_lookup(a);   // (wide-table schedule: local ids of the previous pass; must precede the ticket, like in k_count)
   const i64 begin = a.st[a.o_src_begin], end = a.st[a.o_src_end];
   const i64 F = end - begin;
   const i64 ntiles = ceil_div(F, NT);

@@ -202,7 +202,6 @@ neighbor_sample_cuda(const at::Tensor& rowptr, const at::Tensor& col, const at::
     CpuEngine eng;
     if (g_ot.on) ot1 = OpTimes::now();
     if (wp) {
-      TORCH_CHECK(!disjoint, "pyg_lib_b200: biased sampling of disjoint subgraphs is not implemented on the B200 path");
       PYGB_TORCH_CALL(pygb200_sampler_run_weighted(s, 1, 1, L, &rel, seeds, &n_seed, num_neighbors.data(), flags, &eng.mt,
                                                    nph.data(), eph.data(), &n_nodes, &n_edges, stream, &wp, PYGB200_F32));
     } else
@@ -248,7 +247,6 @@ dist_neighbor_sample_cuda(const at::Tensor& rowptr, const at::Tensor& col, const
                           bool replace, bool directed, bool disjoint, std::string temporal_strategy) {
   TORCH_CHECK(temporal_strategy == "uniform" || temporal_strategy == "last", "No valid temporal strategy found");
   check_arguments(node_time.has_value(), edge_time.has_value(), seed_time.has_value(), edge_weight.has_value(), disjoint);
-  TORCH_CHECK(!edge_weight.has_value(), "pyg_lib_b200: biased (edge_weight) dist_neighbor_sample is not implemented on the B200 path");
   TORCH_CHECK(seed.is_cuda(), "pyg_lib_b200: dist_neighbor_sample expects CUDA tensors (no CPU fallback)");
   const auto st = seed.scalar_type();
   TORCH_CHECK(st == at::kLong || st == at::kInt, "dist_neighbor_sample: index tensors must be int64 or int32");
@@ -277,7 +275,12 @@ dist_neighbor_sample_cuda(const at::Tensor& rowptr, const at::Tensor& col, const
     pygb200_temporal tmp{&nt, &et, &stt, temporal_strategy == "last" ? 1 : 0};
     pygb200_relation rel{rowptr.data_ptr(), col.data_ptr(), rowptr.numel() - 1, col.numel(), 0, 0};
     const void* seeds[1] = {seed.data_ptr()};
+    const void* wp = (edge_weight.has_value() && num_neighbors >= 0) ? weight_ptr(*edge_weight, col, seed.device()) : nullptr;
     CpuEngine eng;
+    if (wp)
+      PYGB_TORCH_CALL(pygb200_sampler_run_weighted(s, 1, 1, 1, &rel, seeds, &S, &num_neighbors, flags, &eng.mt, nph, eph, &n_nodes,
+                                                   &n_edges, stream, &wp, PYGB200_F32));
+    else
     PYGB_TORCH_CALL(pygb200_sampler_run_temporal(s, 1, 1, 1, &rel, seeds, &S, &num_neighbors, flags, &eng.mt, nph, eph, &n_nodes,
                                                  &n_edges, stream, (nt || et) ? &tmp : nullptr));
     eng.commit();
@@ -425,7 +428,6 @@ hetero_neighbor_sample_cuda(const std::vector<node_type>& node_types, const std:
                     "'): mixing biased and uniform relations in one call is not implemented on the B200 path");
         wp[r] = weight_ptr(edge_weight_dict->at(rk), col_dict.at(rk), dev);
       }
-      TORCH_CHECK(!disjoint, "pyg_lib_b200: biased sampling of disjoint subgraphs is not implemented on the B200 path");
     }
     CpuEngine eng;
     if (biased)

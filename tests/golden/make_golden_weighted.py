@@ -33,7 +33,7 @@ def main():
         rowptr, col, seed, w = build_weighted(case)
         torch.manual_seed(case['rng_seed'])
         r = torch.ops.pyg.neighbor_sample(rowptr, col, seed, case['num_neighbors'], None, None, None, w, case.get('csc', False),
-                                          case.get('replace', False), True, False, 'uniform', True)
+                                          case.get('replace', False), True, case.get('disjoint', False), 'uniform', True)
         for k, v in zip(('row', 'col', 'node', 'eid', 'nph', 'eph'), r):
             out[f'homo/{name}/{k}'] = np_(v)
         out[f'homo/{name}/rng_after'] = torch.get_rng_state().numpy()[:24 + 624 * 8].copy()
@@ -42,7 +42,7 @@ def main():
         nt, et, rp, cl, sd, nn, wd = build_hetero_weighted(case)
         torch.manual_seed(case['rng_seed'])
         r = torch.ops.pyg.hetero_neighbor_sample(nt, et, rp, cl, sd, nn, None, None, None, wd, case.get('csc', False),
-                                                 case.get('replace', False), True, False, 'uniform', True)
+                                                 case.get('replace', False), True, case.get('disjoint', False), 'uniform', True)
         for i, key in enumerate(('row', 'col', 'node', 'eid', 'nph', 'eph')):
             for k, v in r[i].items():
                 out[f'hetero/{name}/{key}/{k}'] = np_(v)

@@ -440,6 +440,12 @@ WEIGHTED_CASES: Dict[str, dict] = {
                     weights='uniform', replace=True),
     'zero_fanout_mix': dict(graph=('rand', 800, 12, 8), n_seeds=20, num_neighbors=[5, 0, 3], rng_seed=21, weights='uniform'),
     'dup_seeds': dict(graph=('rand', 600, 12, 9), seeds=[7, 7, 3, 7, 11, 3], num_neighbors=[4, 4], rng_seed=22, weights='uniform'),
+    # disjoint subgraphs ((batch, node) keys) and "all neighbours" hops mixed with biased ones
+    'disjoint': dict(graph=('rand', 1500, 14, 41), n_seeds=40, num_neighbors=[5, 4], rng_seed=23, weights='uniform', disjoint=True),
+    'disjoint_masked_rep': dict(graph=('rand', 1500, 14, 41), n_seeds=40, num_neighbors=[5, 4], rng_seed=24, weights='masked_pos',
+                                disjoint=True, replace=True),
+    'full_then_k': dict(graph=('rand', 900, 6, 42), n_seeds=12, num_neighbors=[-1, 4], rng_seed=25, weights='masked'),
+    'k_then_full_rep': dict(graph=('rand', 900, 6, 42), n_seeds=12, num_neighbors=[6, -1], rng_seed=26, weights='masked_pos', replace=True),
 }
 HETERO_WEIGHTED_CASES: Dict[str, dict] = {
     'kat_cycle': dict(kind='cycle', num_neighbors=[1], rng_seed=0, weights='even_edges', seeds=[0, 1]),   # test_neighbor.cpp:331-378
@@ -449,6 +455,8 @@ HETERO_WEIGHTED_CASES: Dict[str, dict] = {
                       num_neighbors=[4, 4], rng_seed=32, gseed=33, weights='uniform', replace=True),
     'mag_w_masked_csc': dict(kind='mag', sizes=dict(paper=600, author=400, institution=20), avg_deg=6, n_seeds=dict(paper=16),
                              num_neighbors=[6, 3], rng_seed=33, gseed=31, weights='masked', csc=True),
+    'mag_w_disjoint': dict(kind='mag', sizes=dict(paper=600, author=400, institution=20), avg_deg=6, n_seeds=dict(paper=6, author=5),
+                           num_neighbors=[4, 3], rng_seed=34, gseed=34, weights='uniform', disjoint=True),
 }
 
 

@@ -40,7 +40,8 @@ def test_weighted_golden(lib, name, dtype):
     rowptr, col, seed, w = build_weighted(case)
     torch.manual_seed(case['rng_seed'])
     out = lib.sampler.neighbor_sample(rowptr.to(DEV, dtype), col.to(DEV, dtype), seed.to(DEV, dtype), case['num_neighbors'],
-                                      edge_weight=w.to(DEV), csc=case.get('csc', False), replace=case.get('replace', False))
+                                      edge_weight=w.to(DEV), csc=case.get('csc', False), replace=case.get('replace', False),
+                                      disjoint=case.get('disjoint', False))
     p = f'homo/{name}/'
     assert out[0].dtype == dtype and out[2].dtype == dtype
     assert out[4] == GOLD[p + 'nph'].tolist() and out[5] == GOLD[p + 'eph'].tolist()
@@ -56,7 +57,7 @@ def test_hetero_weighted_golden(lib, name):
     dv = lambda d: {k: v.to(DEV) for k, v in d.items()}  # noqa: E731
     torch.manual_seed(case['rng_seed'])
     out = torch.ops.pyg.hetero_neighbor_sample(nt, et, dv(rp), dv(cl), dv(sd), nn, None, None, None, dv(wd), case.get('csc', False),
-                                               case.get('replace', False), True, False, 'uniform', True)
+                                               case.get('replace', False), True, case.get('disjoint', False), 'uniform', True)
     p = f'hetero/{name}/'
     for i, key in enumerate(('row', 'col', 'node', 'eid')):
         for k, v in out[i].items():
@@ -167,12 +168,8 @@ def test_errors(lib):
         lib.sampler.neighbor_sample(rp, cl, seed, [3, 2], edge_weight=w[:-1].to(DEV))
     with pytest.raises(RuntimeError, match='no CPU fallback'):
         lib.sampler.neighbor_sample(rp, cl, seed, [3, 2], edge_weight=w)
-    with pytest.raises(RuntimeError, match='disjoint'):
-        lib.sampler.neighbor_sample(rp, cl, seed, [3, 2], edge_weight=w.to(DEV), disjoint=True)
     with pytest.raises(RuntimeError, match='fan-out of 1'):
         lib.sampler.neighbor_sample(rp, cl, seed, [3, 1], edge_weight=w.to(DEV), replace=True)
-    with pytest.raises(RuntimeError, match='bounded fan-outs'):
-        lib.sampler.neighbor_sample(rp, cl, seed, [3, -1], edge_weight=w.to(DEV))
     with pytest.raises(RuntimeError, match='Biased node temporal'):
         lib.sampler.neighbor_sample(rp, cl, seed, [3, 2], node_time=torch.zeros(300, dtype=torch.long, device=DEV), edge_weight=w.to(DEV),
                                     disjoint=True)
@@ -205,3 +202,30 @@ def test_hetero_needs_weights_for_every_relation(lib):
     with pytest.raises(RuntimeError, match='every edge type'):
         torch.ops.pyg.hetero_neighbor_sample(nt, et, dv(rp), dv(cl), dv(sd), nn, None, None, None, dv(some), False, False, True, False,
                                              'uniform', True)
+
+
+@pytest.mark.parametrize('replace', [False, True])
+@pytest.mark.parametrize('disjoint', [False, True])
+def test_weighted_dist_neighbor_sample_is_one_hop_of_neighbor_sample(lib, replace, disjoint):
+    """pyg::dist_neighbor_sample with edge_weight (biased_sample with distributed = true, neighbor_kernel.cpp:296-303,436-448): the
+    same draws as the first hop of neighbor_sample, nothing mapped — global ids, edge ids, cumulative counts per seed."""
+    rowptr, col = random_csr(4000, 18, 12, big=[(3, 9000)])
+    w = build_weights('masked_pos' if replace else 'masked', rowptr, 5)
+    seed = torch.cat([torch.tensor([3]), torch.randperm(4000, generator=torch.Generator().manual_seed(2))[:300]])
+    k = 7
+    torch.manual_seed(8)
+    node, eid, cum = torch.ops.pyg.dist_neighbor_sample(rowptr.to(DEV), col.to(DEV), seed.to(DEV), k, None, None, None, w.to(DEV), True,
+                                                        replace, True, disjoint, 'uniform')
+    after = _rng()
+    torch.manual_seed(8)
+    exp = W.neighbor_sample(rowptr, col, seed, [k], w, replace=replace, disjoint=disjoint)
+    assert np.array_equal(after, _rng())
+    assert torch.equal(eid.cpu(), exp[3])
+    S = seed.numel()
+    dst = col[exp[3]]
+    counts = torch.bincount(exp[0], minlength=S)
+    assert list(cum) == [S] + (S + torch.cumsum(counts, 0)).tolist()   # neighbor_kernel.cpp:386,447
+    if not disjoint:
+        assert torch.equal(node.cpu(), torch.cat([seed, dst]))
+    else:
+        assert torch.equal(node.cpu(), torch.stack([torch.cat([torch.arange(S), exp[0]]), torch.cat([seed, dst])], 1))
