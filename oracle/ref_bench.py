@@ -34,24 +34,27 @@ if KIND == 'port':
     from oracle import oracle as O
 
 
-def sample_call(rowptr, col, seed, nn):
+def sample_call(rowptr, col, seed, nn, weight=None):
     if KIND == 'reference':
-        return torch.ops.pyg.neighbor_sample(rowptr, col, seed, nn, None, None, None, None, False, False, True, False,
+        return torch.ops.pyg.neighbor_sample(rowptr, col, seed, nn, None, None, None, weight, False, False, True, False,
                                              'uniform', True)
+    if weight is not None:
+        from oracle import weighted as WO
+        return WO.neighbor_sample(rowptr, col, seed, nn, weight)
     return O.neighbor_sample(rowptr, col, seed, nn)
 
 
 def _worker(args):
-    wid, rowptr, col, perm, batch, nn, calls, n_workers = args
+    wid, rowptr, col, perm, batch, nn, calls, n_workers, weight = args
     torch.set_num_threads(1)
     torch.manual_seed(12345 + wid)
     n_batches = perm.numel() // batch
     edges = 0
-    sample_call(rowptr, col, perm[:batch], nn)  # warm-up
+    sample_call(rowptr, col, perm[:batch], nn, weight)  # warm-up
     t0 = time.perf_counter()
     for i in range(calls):
         b = (wid + i * n_workers) % n_batches
-        out = sample_call(rowptr, col, perm[b * batch:(b + 1) * batch], nn)
+        out = sample_call(rowptr, col, perm[b * batch:(b + 1) * batch], nn, weight)
         edges += out[0].numel()
     return edges, time.perf_counter() - t0
 
@@ -83,7 +86,7 @@ def papers_shaped_csr(n: int, e: int):
     return rowptr, col
 
 
-def bench_sampler(workers: int, calls: int, graph: str, batch: int, nn):
+def bench_sampler(workers: int, calls: int, graph: str, batch: int, nn, weighted: bool = False):
     from graphs import lognormal_csr
     if graph == 'products':
         n, e = 2_449_029, 123_718_280
@@ -97,7 +100,11 @@ def bench_sampler(workers: int, calls: int, graph: str, batch: int, nn):
         rowptr, col = lognormal_csr(n, e, seed=1)
     perm = torch.randperm(n, generator=torch.Generator().manual_seed(2))
     rowptr.share_memory_(); col.share_memory_(); perm.share_memory_()
-    jobs = [(w, rowptr, col, perm, batch, nn, calls, workers) for w in range(workers)]
+    weight = None
+    if weighted:   # biased sampling (edge_weight): uniform float32 weights
+        weight = torch.rand(col.numel(), generator=torch.Generator().manual_seed(3))
+        weight.share_memory_()
+    jobs = [(w, rowptr, col, perm, batch, nn, calls, workers, weight) for w in range(workers)]
     t0 = time.perf_counter()
     if workers == 1:
         res = [_worker(jobs[0])]
@@ -109,7 +116,7 @@ def bench_sampler(workers: int, calls: int, graph: str, batch: int, nn):
     busy = max(r[1] for r in res)
     return dict(kind=KIND, cores=workers, edges=edges, seconds=busy, wall_seconds=wall,
                 edges_per_s=edges / busy, calls=calls * workers,
-                sample=f'{calls * workers} calls of {batch} seeds {nn} on the {graph}-shaped CSR '
+                sample=f'{calls * workers} {"biased " if weighted else ""}calls of {batch} seeds {nn} on the {graph}-shaped CSR '
                        f'({workers} single-threaded worker process(es), disjoint seed batches)')
 
 
@@ -142,9 +149,10 @@ if __name__ == '__main__':
     ap.add_argument('--graph', default='products')
     ap.add_argument('--batch', type=int, default=1024)
     ap.add_argument('--fanout', default='15,10')
+    ap.add_argument('--weighted', action='store_true', help='biased sampling with uniform float32 edge weights')
     a = ap.parse_args()
     if a.what == 'sampler':
-        r = bench_sampler(a.workers, a.calls, a.graph, a.batch, [int(v) for v in a.fanout.split(',')])
+        r = bench_sampler(a.workers, a.calls, a.graph, a.batch, [int(v) for v in a.fanout.split(',')], a.weighted)
     else:
         r = bench_matmul(a.calls, a.workers if a.workers > 1 else (os.cpu_count() or 1))
     print('REFBENCH ' + json.dumps(r))
