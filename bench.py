@@ -405,46 +405,74 @@ def main():
         ms, edges, _, launches, clocks = T.run(step_dev, a.steps, a.warmup)
         value = edges / (ms * 1e-3)
 
-        # e2e: pinned seeds -> device and (row, col, node, eid) -> pinned host EVERY step, through the public API.  The
-        # calls themselves cannot overlap (each consumes the CPU generator where the previous one left it); the result
-        # copies are queued by a loader thread and run on a copy stream beside the next call.
-        # The op hands out its four results as views of ONE bound-sized buffer (row | col | edge_id | node_id), so the
-        # consumer moves them with a single async copy on a copy stream (5.4 MB incl. the unused tail of each part; four
-        # exact copies are 4.1 MB but cost four times the host time, which is what bounds a 78 us step).
+        # e2e: pinned seeds -> device and (row, col, edge_id, node_id) -> pinned host EVERY step, through the public API.  The
+        # calls themselves cannot overlap (each consumes the CPU generator where the previous one left it, and returns its
+        # counts as host integers); the result copies run on a copy stream beside the next call.  The consumer is what a C++
+        # loader would be: cudaMemcpyAsync of exactly the four results (the op hands them out as views of one allocation, so
+        # holding the views keeps the storage alive until the copy is done) — 3.9 MB per step instead of the 5.4 MB of the
+        # bound-sized buffer, which at this link's ~55 GB/s is the difference between a copy-bound and a call-bound step.
+        import ctypes
+        rt = ctypes.CDLL('libcudart.so.12')
+        rt.cudaMemcpyAsync.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p]
+        rt.cudaMemcpyAsync.restype = ctypes.c_int
         cap = BATCH * (FANOUT[0] + FANOUT[0] * FANOUT[1])
         n_slots = 4
         host_bufs = [torch.empty(4 * cap + BATCH, dtype=torch.int64).pin_memory() for _ in range(n_slots)]
+        host_ptr = [b.data_ptr() for b in host_bufs]
+        seed_bufs = [torch.empty(BATCH, dtype=torch.int64, device=dev) for _ in range(n_slots)]
         copy_stream = torch.cuda.Stream(device=dev)
+        cs, ms_ = ctypes.c_void_p(copy_stream.cuda_stream), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        rt.cudaMemcpy2DAsync.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t,
+                                         ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p]
+        rt.cudaMemcpy2DAsync.restype = ctypes.c_int
         done = [torch.cuda.Event() for _ in range(n_slots)]
+        ready = [torch.cuda.Event() for _ in range(n_slots)]
+        held = [None] * n_slots
         d2h = [0]
+        use_2d = os.environ.get('PYGB200_BENCH_E2E_2D', '1') != '0'
 
         def step_e2e(i):
-            s = seeds_host[i].to(dev, non_blocking=True)
-            outs = P.sampler.neighbor_sample(rowptr, col, s, FANOUT)[:4]
-            base = outs[0]._base
-            srcs = [base] if base is not None and all(o._base is base for o in outs) else [o.reshape(-1) for o in outs]
-            ready = torch.cuda.Event()
-            ready.record()
             slot = i % n_slots
-            done[slot].synchronize()          # the host buffer of step i - 4 is free again
-            with torch.cuda.stream(copy_stream):
-                copy_stream.wait_event(ready)
-                off = 0
-                for t in srcs:
-                    t.record_stream(copy_stream)
-                    host_bufs[slot][off:off + t.numel()].copy_(t, non_blocking=True)
-                    off += t.numel()
-                done[slot].record()
-            d2h[0] += 8 * sum(t.numel() for t in srcs)
-            return outs[0].numel()
+            done[slot].synchronize()          # step i - 4's copies are done: its host buffer, seed buffer and results are free
+            rc = rt.cudaMemcpyAsync(seed_bufs[slot].data_ptr(), seeds_host[i].data_ptr(), BATCH * 8, 1, ms_)
+            row, colv, node, eid = outs = P.sampler.neighbor_sample(rowptr, col, seed_bufs[slot], FANOUT)[:4]
+            ready[slot].record()
+            copy_stream.wait_event(ready[slot])
+            E, nb_node = row.numel(), node.numel() * 8
+            pitch = colv.data_ptr() - row.data_ptr()
+            if use_2d and E and eid.data_ptr() - colv.data_ptr() == pitch:   # views of one allocation: row | col | edge_id at one pitch
+                rc |= rt.cudaMemcpy2DAsync(host_ptr[slot], E * 8, row.data_ptr(), pitch, E * 8, 3, 2, cs)
+            else:
+                for j, t in enumerate((row, colv, eid)):
+                    rc |= rt.cudaMemcpyAsync(host_ptr[slot] + j * E * 8, t.data_ptr(), E * 8, 2, cs)
+            rc |= rt.cudaMemcpyAsync(host_ptr[slot] + 3 * E * 8, node.data_ptr(), nb_node, 2, cs)
+            done[slot].record(copy_stream)
+            held[slot] = outs                  # the views keep the storage alive until the slot comes round again
+            if rc:
+                raise RuntimeError('cudaMemcpyAsync failed')
+            d2h[0] += 3 * E * 8 + nb_node
+            return E
 
         def finish_e2e():
             torch.cuda.current_stream().wait_stream(copy_stream)
         ms_e, edges_e, _, _, _ = T.run(step_e2e, a.steps, a.warmup, finish=finish_e2e)
+        # what the link gives a copy of that size (same pinned buffers, device-timed): the floor of a copy-bound step
+        nb_step = int(d2h[0] / max(a.steps + a.warmup, 1))
+        src_probe = torch.empty(nb_step // 8, dtype=torch.int64, device=dev)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for rep in range(3):
+            if rep == 1:
+                ev0.record()
+            rt.cudaMemcpyAsync(host_ptr[0], src_probe.data_ptr(), nb_step, 2, ms_)
+        ev1.record(); torch.cuda.synchronize()
+        d2h_us = ev0.elapsed_time(ev1) / 2 * 1e3
         e2e = {'value': edges_e / (ms_e * 1e-3), 'unit': 'edges/s', 'h2d_bytes_per_step': BATCH * 8,
-               'd2h_bytes_per_step': int(d2h[0] / max(a.steps + a.warmup, 1)), 'ms_per_step': ms_e / a.steps,
-               'how': 'pinned seeds H2D and the result buffer (row | col | edge_id | node_id, one allocation) D2H to pinned memory every '
-                      'step; the copy of step i runs on a copy stream beside step i+1'}
+               'd2h_bytes_per_step': nb_step, 'ms_per_step': ms_e / a.steps,
+               'd2h_alone_us': d2h_us, 'd2h_link_gbs': nb_step / d2h_us / 1e3,
+               'how': 'every step: pinned seeds H2D (cudaMemcpyAsync), neighbor_sample through the public API, its four results (row, col, '
+                      'edge_id, node_id; exact sizes) D2H to pinned memory on a copy stream beside the next call '
+                      '(cudaMemcpy2DAsync for row | col | edge_id, one copy for node_id)' if use_2d else 'every step: pinned seeds H2D, '
+                      'neighbor_sample through the public API, four exact-size cudaMemcpyAsync D2H on a copy stream beside the next call'}
 
         line = {'metric': 'sampled_edges_per_s', 'value': value, 'unit': 'edges/s', 'n_gpus': 1, 'steps': a.steps,
                 'warmup': a.warmup, 'ms_per_step': ms / a.steps, 'higher_is_better': True, 'scaling': 'weak',
