@@ -150,8 +150,8 @@ def test_errors(lib):
         lib.sampler.neighbor_sample(r, c, s, [2], directed=False)
     with pytest.raises(RuntimeError, match='disjoint'):
         lib.sampler.neighbor_sample(r, c, s, [2], node_time=torch.zeros(100, dtype=torch.long, device=DEV))
-    with pytest.raises(RuntimeError, match='not implemented on the B200 path'):   # (biased sampling itself: tests/test_weighted_gpu.py)
-        lib.sampler.neighbor_sample(r, c, s, [2], edge_weight=torch.ones(col.numel(), device=DEV), disjoint=True)
+    with pytest.raises(RuntimeError, match='float32'):   # (biased sampling itself: tests/test_weighted_gpu.py)
+        lib.sampler.neighbor_sample(r, c, s, [2], edge_weight=torch.ones(col.numel(), device=DEV, dtype=torch.float64))
     with pytest.raises(RuntimeError, match='Seed time needs to be specified'):
         lib.sampler.neighbor_sample(r, c, s, [2], edge_time=torch.zeros(col.numel(), dtype=torch.long, device=DEV), disjoint=True)
     with pytest.raises(RuntimeError, match='Non-contiguous'):
