@@ -48,7 +48,8 @@ std::vector<ProfPending> g_prof_pending;
 ProfAcc g_prof_acc[] = {{"sample", 0, 0, 0}, {"count", 0, 0, 0}, {"mark", 0, 0, 0}, {"assign", 0, 0, 0},
                         {"lookup", 0, 0, 0}, {"segment_matmul", 0, 0, 0}, {"grouped_gemm", 0, 0, 0},
                         {"insert", 0, 0, 0}, {"pref", 0, 0, 0}, {"reduce", 0, 0, 0}, {"xbarrier", 0, 0, 0},
-                        {"seed", 0, 0, 0}, {"final", 0, 0, 0}, {"cleanup", 0, 0, 0}, {"export", 0, 0, 0}, {"rows", 0, 0, 0}, {"push", 0, 0, 0}};
+                        {"seed", 0, 0, 0}, {"final", 0, 0, 0}, {"cleanup", 0, 0, 0}, {"export", 0, 0, 0}, {"rows", 0, 0, 0}, {"push", 0, 0, 0},
+                        {"mtgen", 0, 0, 0}};
 constexpr int N_PROF = sizeof(g_prof_acc) / sizeof(g_prof_acc[0]);
 int prof_slot(const char* name) {
   for (int i = 0; i < N_PROF; ++i) if (strcmp(g_prof_acc[i].name, name) == 0) return i;
@@ -1784,7 +1785,10 @@ int mt_request(pygb200_sampler* s, cudaStream_t st, i64 target) {
   target = std::min<i64>(target, s->raw_cap_words - MT_N);
   while (target > s->mt_requested) {
     const i64 amount = target - s->mt_requested;
-    if (s->jump_P >= 2 && amount >= 2 * (i64)s->jump_S) {
+    // jump-ahead has a fixed cost (~0.6 ms: serial pre-step + one polynomial pass per chunk); the one-CTA generator makes 2 G words/s
+    // (measured with biased sampling, which asks for 10^5..10^8 words at a time): the crossover is at ~1.2 M words
+    static const i64 jump_min = [] { const char* e = getenv("PYGB200_MT_JUMP_MIN_WORDS"); return e ? (i64)atoll(e) : (i64)1250000; }();
+    if (s->jump_P >= 2 && amount >= std::max<i64>(2 * (i64)s->jump_S, jump_min)) {
       const int P_used = (int)std::min<i64>(s->jump_P, (amount + s->jump_S - 1) / s->jump_S);
       i64* jb = s->jump_scratch.as<i64>();
       k_mt_jump_prestep<3><<<1, 640, 0, st>>>(s->raw.as<u32>(), s->gen.as<i64>(), jb, s->raw_cap_words);
@@ -2331,7 +2335,9 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
       if (int e = s->raw.ensure((size_t)cap_need * 4, (size_t)gen_now * 4, st)) return e;
       raw_cap = s->raw_cap_words = (i64)(s->raw.cap / 4);
     }
+    void* tkm = prof_begin(st);
     if (int e = mt_request(s, st, need)) return e;
+    prof_end(tkm, "mtgen", st, W);   // (raw mt19937 words of this pass: jump-ahead generation when there are many)
     a.raw = s->raw.as<u32>(); a.raw_cap = raw_cap;
     WArgs wa;
     wa.weight = reinterpret_cast<const float*>(edge_weight[r]);
@@ -2341,7 +2347,20 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
     wwords += W;
     void* tk = prof_begin(st);
     const int gw = (int)std::min<i64>(std::max<i64>(ceil_div(F, NT / 32), 1), (i64)s->sm_count * 16);
-    if (idx32) launch_pdl(k_w_sample<int32_t>, gw, NT, st, a, wa); else launch_pdl(k_w_sample<int64_t>, gw, NT, st, a, wa);
+    {
+      static const bool smem_ok = cudaFuncSetAttribute(k_w_sample<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, W_LIST_MAX * 2048) == cudaSuccess &&
+                                  cudaFuncSetAttribute(k_w_sample<int64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, W_LIST_MAX * 2048) == cudaSuccess;
+      PYGB_CHECK(smem_ok, PYGB200_ERR_CUDA, "k_w_sample: cannot reserve shared memory for the candidate lists");
+      const i64 kf = a.fanout;
+      const size_t smem = (!a.replace && kf >= 0 && kf + 1 <= W_LIST_MAX) ? (size_t)(kf + 1) * (NT / 32) * 32 * 8 : 0;
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3((unsigned)gw); cfg.blockDim = dim3(NT); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[0].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = attr; cfg.numAttrs = 1;
+      if (idx32) PYGB_CUDA(cudaLaunchKernelEx(&cfg, k_w_sample<int32_t>, a, wa)); else PYGB_CUDA(cudaLaunchKernelEx(&cfg, k_w_sample<int64_t>, a, wa));
+    }
     prof_end(tk, "sample", st, E);
     PYGB_LAUNCH_CHECK();
     return PYGB200_OK;

@@ -157,8 +157,15 @@ __device__ __forceinline__ u64 w_code(float x, u32 idx) {
   return ((u64)o << 32) | (u64)(0xffffffffu - idx);
 }
 
+// comp-equivalent keys (neither goes before the other), from the value part of two codes: equal, or +0 / -0
+__device__ __forceinline__ bool w_same_key(u32 o1, u32 o2) {
+  return o1 == o2 || (o1 == 0x80000000u && o2 == 0x7fffffffu) || (o1 == 0x7fffffffu && o2 == 0x80000000u);
+}
+constexpr int W_LIST_MAX = 32;   // fan-out + 1 candidates per lane live in shared memory; beyond that the keys are re-scanned per pick
+
 template <typename idx_t>
 __global__ void __launch_bounds__(NT) k_w_sample(const PassArgs a, const WArgs w) {
+  extern __shared__ u64 w_lists[];   // [warp][M][32 lanes]: every lane's M best codes so far
   pdl_enter();
   const i64 F = a.st[ST_PASS_F], begin = a.st[a.o_src_begin], pbase = a.st[ST_PASS_BASE];
   const int lane = threadIdx.x & 31;
@@ -166,6 +173,8 @@ __global__ void __launch_bounds__(NT) k_w_sample(const PassArgs a, const WArgs w
   const idx_t* __restrict__ col = (const idx_t*)a.col;
   const i64* tile_scr = reinterpret_cast<const i64*>(a.tile_func);
   const i64 k = a.fanout;
+  const int M = (!a.replace && k >= 0 && k + 1 <= W_LIST_MAX) ? (int)k + 1 : 0;
+  u64* L = w_lists + (size_t)(threadIdx.x >> 5) * M * 32 + lane;   // entry m at L[m * 32]
   for (i64 i = (i64)blockIdx.x * (NT / 32) + (threadIdx.x >> 5); i < F; i += nwarps) {
     const NodeRec r = a.rec[i];
     const i64 deg = r.deg;
@@ -184,19 +193,25 @@ __global__ void __launch_bounds__(NT) k_w_sample(const PassArgs a, const WArgs w
     const float* __restrict__ wt = w.weight + r.rs;
     const int n = (int)deg;
     if (a.replace) {
-      // ---- at::multinomial with replacement: sequential float32 running sum (that IS its definition), normalised
+      // ---- at::multinomial with replacement: a float32 running sum IN ROW ORDER (that is its definition), normalised.
+      // 32 weights per coalesced load; every lane replays the 32 additions from shuffles (same chain, same roundings)
+      // and keeps the prefix that ends at its element.
       int err = 0; float sum = 0.f;
-      if (lane == 0) {
-        for (int j = 0; j < n; ++j) {
-          const float v = wt[j];
-          if (!(v >= 0.f)) err = W_ERR_NEG;                       // "probability entry < 0" (NaN fails the same check)
-          else if (isinf(v) && !err) err = W_ERR_INF;
-          sum = __fadd_rn(sum, v);
-          key[j] = sum;
+      for (int base = 0; base < n; base += 32) {
+        const int j = base + lane;
+        const float v = j < n ? wt[j] : 0.f;
+        const int bad = j < n ? (!(v >= 0.f) ? W_ERR_NEG : (isinf(v) ? W_ERR_INF : 0)) : 0;   // "entry < 0" (NaN fails it too), "inf or NaN"
+        const unsigned bm = __ballot_sync(0xffffffffu, bad != 0);
+        if (bm && !err) err = __shfl_sync(0xffffffffu, bad, __ffs(bm) - 1);   // the first offending entry decides, like the reference's loop
+        const int m = n - base < 32 ? n - base : 32;
+        float mine = 0.f;
+        for (int q = 0; q < m; ++q) {
+          sum = __fadd_rn(sum, __shfl_sync(0xffffffffu, v, q));
+          if (lane == q) mine = sum;
         }
-        if (!err && !(sum > 0.f)) err = W_ERR_SUM;
+        if (j < n) key[j] = mine;
       }
-      err = __shfl_sync(0xffffffffu, err, 0); sum = __shfl_sync(0xffffffffu, sum, 0);
+      if (!err && !(sum > 0.f)) err = W_ERR_SUM;
       if (err) {   // reported by the host when the run ends; the node's slots still get valid edges so that the rest of the pass stays in bounds
         if (lane == 0) a.st[ST_ERROR] = err;
         for (i64 t = lane; t < k; t += 32) emit(t, r.rs);
@@ -219,29 +234,59 @@ __global__ void __launch_bounds__(NT) k_w_sample(const PassArgs a, const WArgs w
       }
       continue;
     }
-    // ---- weighted reservoir keys, the k largest in descending order
-    for (int j = lane; j < n; j += 32) {
-      const u32 k24 = mt_temper(a.raw[wpos + j]) & 0xffffffu;
-      key[j] = __fdiv_rn(w_mkl_logf(k24, w), wt[j]);
+    // ---- weighted reservoir keys (kept in `key` for the libstdc++ replay), the k largest in descending order.
+    // One pass: four independent elements per lane in flight (engine word, weight, log-table bit), every lane keeps its own
+    // k + 1 best codes in shared memory — the k + 1 best of the row are among them.
+    int cnt = 0, mnpos = 0;
+    u64 mn = ~0ull;
+    for (int jb = lane; jb < n; jb += 128) {
+      u32 wd[4]; float ww[4], kv[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int j = jb + 32 * q;
+        wd[q] = j < n ? a.raw[wpos + j] : 0u;
+        ww[q] = j < n ? wt[j] : 1.f;
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) kv[q] = __fdiv_rn(w_mkl_logf(mt_temper(wd[q]) & 0xffffffu, w), ww[q]);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int j = jb + 32 * q;
+        if (j < n) {
+          key[j] = kv[q];
+          if (M) {
+            const u64 c = w_code(kv[q], (u32)j);
+            if (cnt < M) {
+              L[cnt * 32] = c;
+              if (c < mn) { mn = c; mnpos = cnt; }
+              ++cnt;
+            } else if (c > mn) {
+              L[mnpos * 32] = c;
+              mn = ~0ull;
+              for (int m = 0; m < M; ++m) { const u64 v = L[m * 32]; if (v < mn) { mn = v; mnpos = m; } }
+            }
+          }
+        }
+      }
     }
     __syncwarp();
     u64 prev = ~0ull;
-    float prev_v = 0.f;
+    u32 prev_o = 0;
     bool tie = false;
     const int rounds = (int)k + 1;   // (n > k here)
     for (int t = 0; t < rounds; ++t) {
       u64 best = 0;   // (every real code is > 0: the index part alone is >= 2^32 - n)
-      for (int j = lane; j < n; j += 32) {
-        const u64 c = w_code(key[j], (u32)j);
-        if (c < prev && c > best) best = c;
+      if (M) {
+        for (int m = 0; m < cnt; ++m) { const u64 c = L[m * 32]; if (c < prev && c > best) best = c; }
+      } else {
+        for (int j = lane; j < n; j += 32) { const u64 c = w_code(key[j], (u32)j); if (c < prev && c > best) best = c; }
       }
 #pragma unroll
       for (int d = 16; d > 0; d >>= 1) { const u64 o = __shfl_xor_sync(0xffffffffu, best, d); best = o > best ? o : best; }
-      const u32 idx = 0xffffffffu - (u32)best;
-      const float v = key[idx];
-      if (t > 0 && (((v != v) && (prev_v != prev_v)) || v == prev_v)) tie = true;
+      const u32 idx = 0xffffffffu - (u32)best, o = (u32)(best >> 32);
+      if (t > 0 && w_same_key(o, prev_o)) tie = true;
       if (t < k && lane == (t & 31)) emit(t, r.rs + idx);
-      prev = best; prev_v = v;
+      prev = best; prev_o = o;
     }
     if (tie) {   // two of the k + 1 largest keys are equal: libstdc++ decides (one lane; rare outside masked rows)
       u32* sidx = w.sidx + spos;
@@ -251,5 +296,6 @@ __global__ void __launch_bounds__(NT) k_w_sample(const PassArgs a, const WArgs w
       __syncwarp();
       for (i64 t = lane; t < k; t += 32) emit(t, r.rs + sidx[t]);
     }
+    __syncwarp();   // (the lists are reused by this warp's next node)
   }
 }

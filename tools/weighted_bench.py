@@ -47,7 +47,21 @@ def main():
             for i in range(iters):
                 un += P.sampler.neighbor_sample(rowptr, col, perm[(3 + i) * batch:(4 + i) * batch], [15, 10], replace=replace)[0].numel()
             e1.record(); torch.cuda.synchronize()
-            res['gpu'][f'{batch} seeds [15,10] replace={replace}'] = dict(ms_per_call=ms, edges_per_call=edges / iters, edges_per_s=edges / iters / ms * 1e3,
+            import ctypes as C
+            abi = C.CDLL(os.path.join(os.path.dirname(P.__file__), 'libpyg_b200.so'))
+            abi.pygb200_profile_read.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p]
+            abi.pygb200_profile_enable(1)
+            for i in range(iters):
+                P.sampler.neighbor_sample(rowptr, col, perm[(3 + i) * batch:(4 + i) * batch], [15, 10], edge_weight=w, replace=replace)
+            torch.cuda.synchronize()
+            abi.pygb200_profile_enable(0)
+            prof = {}
+            for name in ('count', 'mtgen', 'sample', 'insert', 'mark', 'assign', 'seed', 'final', 'cleanup'):
+                msv, ln, wk = C.c_double(), C.c_int64(), C.c_int64()
+                abi.pygb200_profile_read(name.encode(), C.byref(msv), C.byref(ln), C.byref(wk))
+                if ln.value:
+                    prof[name] = round(msv.value / iters * 1e3, 1)
+            res['gpu'][f'{batch} seeds [15,10] replace={replace}'] = dict(kernel_us_per_call=prof, ms_per_call=ms, edges_per_call=edges / iters, edges_per_s=edges / iters / ms * 1e3,
                                                                       uniform_ms_per_call=e0.elapsed_time(e1) / iters)
     del rowptr, col, w
     torch.cuda.empty_cache()
