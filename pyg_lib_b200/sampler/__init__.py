@@ -48,8 +48,8 @@ def neighbor_sample(
 
     Node-/edge-level temporal sampling (`node_time`/`edge_time`/`seed_time`, strategies 'uniform' and 'last') and biased
     sampling (`edge_weight`: float32, one weight per edge; neighbor_kernel.cpp:245-285) are supported, both bit-identical
-    to the reference including the state of the CPU generator afterwards.  Biased sampling on this path: bounded fan-outs,
-    not disjoint, and with `replace=True` no fan-out of 1 (`DESIGN.md` §3.8); it costs one host synchronisation per hop."""
+    to the reference including the state of the CPU generator afterwards.  Biased sampling costs one host synchronisation
+    per hop; with `replace=True` a fan-out of exactly 1 is refused (`DESIGN.md` §4.5, §9)."""
     return _neighbor_sample_op(rowptr, col, seed, num_neighbors, node_time, edge_time, seed_time, edge_weight, csc,
                                replace, directed, disjoint, temporal_strategy, return_edge_id)
 
