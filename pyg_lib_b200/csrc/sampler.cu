@@ -626,7 +626,10 @@ __device__ __forceinline__ void sample_draws(const PassArgs& a, const NodeRec& r
   }
 }
 
-template <typename idx_t, bool PHASED>
+__device__ __forceinline__ u32 v2_insert(u64* __restrict__ pk, int bits, u32 key, u32 p);   // (sampler_v2.cuh: packed table)
+
+// PK: the dst type's table is the packed one (slot = node id : 32 | value : 32; sampler_v2.cuh) — one CAS per insert
+template <typename idx_t, bool PHASED, bool PK = false>
 __device__ __forceinline__ void sample_node(const PassArgs& a, const NodeRec& r, i64 off, i64 pos0, i64 src_pos, i64 pbase,
                                             int g, int gl, int gbase, unsigned gmask) {
   const idx_t* __restrict__ col = (const idx_t*)a.col;
@@ -639,6 +642,7 @@ __device__ __forceinline__ void sample_node(const PassArgs& a, const NodeRec& r,
     a.eid[pbase + p] = e;
     a.colv[pbase + p] = d;  // global id for now; the (deferred) lookup overwrites it with the local id
     if (PHASED && a.phase == 3) return;   // distributed one-hop sampling: no mapping at all (neighbor_kernel.cpp:296-303)
+    if (PK) { a.eslot[p] = v2_insert(a.pk, a.pk_bits, (u32)d, (u32)p); return; }
     const u32 s = table_insert(a.keys, a.mask, make_key(d, sbatch, a.disjoint));
     red_min_u64(&a.vals[s], POS_BASE + (u64)p);
     a.eslot[p] = s;
@@ -1000,7 +1004,7 @@ __global__ void __launch_bounds__(NT) k_count_s(const PassArgs a) {
   tl_mark(TL_COUNT | TL_END);
 }
 
-template <typename idx_t>
+template <typename idx_t, bool PK = false>
 __global__ void __launch_bounds__(NT, SAMPLE_MIN_BLOCKS) k_sample_s(const PassArgs a) {
   __shared__ u32 s_off[LAT_TILES], s_pos[LAT_TILES];
   __shared__ u32 s_win[MT_WIN];   // (block 0, stream shortfall only)
@@ -1093,7 +1097,7 @@ __global__ void __launch_bounds__(NT, SAMPLE_MIN_BLOCKS) k_sample_s(const PassAr
     const i64 off = (i64)s_off[tile] + r.loc_off;
     const int ph = (int)(tpos & 3);
     const u32 pfv = ph == 0 ? rb.x : (ph == 1 ? rb.y : (ph == 2 ? rb.z : rb.w));
-    sample_node<idx_t, false>(a, r, off, tpos + pfv, begin + i, pbase, g, gl, gbase, gmask);
+    sample_node<idx_t, false, PK>(a, r, off, tpos + pfv, begin + i, pbase, g, gl, gbase, gmask);
   }
   tl_mark(TL_SAMPLE | TL_END);
 }
@@ -1174,6 +1178,118 @@ __global__ void __launch_bounds__(NT) k_assign_s(const PassArgs a) {
       if (a.disjoint) a.dst_batch[list_base + rank] = a.src_batch[a.row[pbase + p]];
       a.dst_slot[list_base + rank] = s;
     }
+  }
+}
+
+// ---- latency schedule on the PACKED table (runs that qualify for it: not disjoint, not temporal, node ids < 2^32 - 1):
+// the same write-once counters and per-block rescans as k_mark_s / k_assign_s, with sampler_v2.cuh's data path — one CAS
+// per insert in k_sample_s<PK>, refs read once in the mark kernel, ids from rank lookups, so an edge's local id is final
+// when the assign kernel stores it and no lookup of a pass is deferred into the next kernel any more.
+__global__ void __launch_bounds__(NT) k_mark_p(const PassArgs a) {
+  __shared__ u32 s_w[NT / 32];
+  pdl_enter(TL_MARK);
+  const i64 E = a.st[a.w_E];
+  const i64 ntiles = ceil_div(E, ETILE);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  u32 mine = 0;
+  for (i64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const i64 p0 = tile * ETILE + threadIdx.x * 4;
+    u32 fl[4], rv[4], cnt = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { const i64 p = p0 + q; rv[q] = p < E ? (u32)a.pk[a.eslot[p]] : 0u; }   // four independent chains
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const i64 p = p0 + q;
+      fl[q] = (p < E && rv[q] == (V2_POS | (u32)p)) ? 1u : 0u;
+      if (p < E) a.fref[p] = rv[q];
+      cnt += fl[q];
+    }
+    u32 inc = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const u32 o = __shfl_up_sync(0xffffffffu, inc, d);
+      if (lane >= d) inc += o;
+    }
+    if (lane == 31) s_w[wid] = inc;
+    __syncthreads();
+    u32 pre = 0, tot = 0;
+    for (int w = 0; w < NT / 32; ++w) { if (w < wid) pre += s_w[w]; tot += s_w[w]; }
+    u32 ex = pre + inc - cnt;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const i64 p = p0 + q;
+      if (p < E) a.erank[p] = ex;     // rank of p among the tile's firsts (only read for firsts)
+      ex += fl[q];
+    }
+    if (threadIdx.x == 0) { a.mtile[tile] = tot; mine += tot; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0 && mine) atomicAdd(reinterpret_cast<unsigned long long*>(a.st + a.w_new), (unsigned long long)mine);
+  tl_mark(TL_MARK | TL_END);
+}
+
+__global__ void __launch_bounds__(NT) k_assign_p(const PassArgs a) {
+  __shared__ u32 s_excl[LAT_TILES];
+  __shared__ u32 s_w[NT / 32];
+  pdl_enter(TL_ASSIGN);
+  const i64 E = a.st[a.w_E];
+  const i64 pbase = ldw(a.st, a.w_pbase, 0);
+  const i64 list_base = ldw(a.st, a.w_list_in, a.c_list_in);
+  const i64 ids_base = list_base - (a.st[a.w_seed_list] - a.st[a.w_seed_ids]);   // duplicate seeds are listed, not numbered
+  const int ntiles = (int)ceil_div(E, ETILE);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (a.pub_words && blockIdx.x == 0 && threadIdx.x == 0) {   // last pass of the run: its dst list length was the last counter
+    publish_last(a, list_base + a.st[a.w_new]);
+    tl_mark(TL_FINAL);
+  }
+  const i64 p_first = (i64)blockIdx.x * NT + threadIdx.x;
+  u32 r_first = 0;
+  if (p_first < E) r_first = a.fref[p_first];
+  // ---- every block: exclusive scan of the per-tile counts of first occurrences
+  {
+    const int t0 = threadIdx.x * 4;
+    u32 pv[4]; u32 lv = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int t = t0 + q;
+      pv[q] = lv;
+      if (t < ntiles) lv += (u32)a.mtile[t];
+    }
+    u32 inc = lv;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const u32 o = __shfl_up_sync(0xffffffffu, inc, d);
+      if (lane >= d) inc += o;
+    }
+    if (lane == 31) s_w[wid] = inc;
+    __syncthreads();
+    u32 pre = 0, tot = 0;
+    for (int w = 0; w < NT / 32; ++w) { if (w < wid) pre += s_w[w]; tot += s_w[w]; }
+    const u32 ex = pre + inc - lv;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int t = t0 + q;
+      if (t < ntiles) s_excl[t] = ex + pv[q];
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) a.st[a.w_list_out] = list_base + tot;
+    __syncthreads();
+  }
+  for (i64 p = p_first; p < E; p += (i64)gridDim.x * NT) {
+    const u32 r = p == p_first ? r_first : a.fref[p];
+    i64 id = (i64)r;
+    if (r & V2_POS) {   // first seen in this pass, at position q: the rank of q among the pass's firsts
+      const u32 q = r & ~V2_POS;
+      const i64 rank = (i64)s_excl[q / ETILE] + (i64)__ldg(&a.erank[q]);
+      id = ids_base + rank;
+      if (q == (u32)p) {
+        const i64 d = a.colv[pbase + p];   // (global id, about to be replaced)
+        const u32 s = a.eslot[p];
+        a.dst_nodes[list_base + rank] = d;
+        a.dst_slot[list_base + rank] = s;
+        if (a.v2_writeback) a.pk[s] = ((u64)(u32)d << 32) | (u64)id;
+      }
+    }
+    a.colv[pbase + p] = id;
   }
 }
 
@@ -1274,10 +1390,12 @@ __global__ void __launch_bounds__(SEED_NT) k_seed_fused(const PassArgs a, const 
     }
     return;
   }
+  const bool packed = a.pk != nullptr;   // (latency schedule on the packed table: k_mark_p / k_assign_p)
   for (int i = threadIdx.x; i < n; i += SEED_NT) {
     const i64 v = (i64)seeds[i];
     a.dst_nodes[i] = v;
     if (a.disjoint) a.dst_batch[i] = batch0 + i;
+    if (packed) { a.eslot[i] = v2_insert(a.pk, a.pk_bits, (u32)v, (u32)i); continue; }
     const u32 s = table_insert(a.keys, a.mask, make_key(v, batch0 + i, a.disjoint));
     red_min_u64(&a.vals[s], POS_BASE + (u64)i);
     a.eslot[i] = s;
@@ -1287,7 +1405,10 @@ __global__ void __launch_bounds__(SEED_NT) k_seed_fused(const PassArgs a, const 
   for (int base = 0; base < n; base += SEED_NT) {
     const int i = base + threadIdx.x;
     u32 s = 0; int first = 0;
-    if (i < n) { s = a.eslot[i]; first = (a.vals[s] == POS_BASE + (u64)i) ? 1 : 0; }
+    if (i < n) {
+      s = a.eslot[i];
+      first = packed ? ((u32)a.pk[s] == (V2_POS | (u32)i) ? 1 : 0) : ((a.vals[s] == POS_BASE + (u64)i) ? 1 : 0);
+    }
     int inc = first;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -1301,7 +1422,8 @@ __global__ void __launch_bounds__(SEED_NT) k_seed_fused(const PassArgs a, const 
     const int c0 = s_carry;
     if (i < n) a.dst_slot[i] = first ? s : NO_SLOT;
     __syncthreads();   // every thread has read vals[] of this chunk before ranks overwrite them
-    if (first) a.vals[s] = (u64)(c0 + pre + inc - 1);
+    if (first && packed) a.pk[s] = ((u64)(u32)a.dst_nodes[i] << 32) | (u64)(u32)(c0 + pre + inc - 1);
+    else if (first) a.vals[s] = (u64)(c0 + pre + inc - 1);
     if (threadIdx.x == 0) s_carry = c0 + tot;
     __syncthreads();
   }
@@ -1983,7 +2105,13 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
       lat = fb[(size_t)rels[r].src_type * (L + 1) + h] <= (i64)LAT_TILES * NT && eb[(size_t)r * L + h] <= (i64)LAT_TILES * ETILE;
     }
   const bool p2p = sharded && shard->exchange != nullptr;
-  bool v2 = !lat && !synced && !nodedup && !disjoint && !any_time && L > 0 && (!no_v2 || p2p || weighted) && (!sharded || p2p);
+  // (PYGB200_LAT_PACKED=1: the latency schedule on the packed table — k_sample_s<PK> / k_mark_p / k_assign_p.  Measured on C2,
+  //  same box: 75.9-77.1 us per call against 73.8 on the wide table — at 1024 seeds the second-hop kernel is bound by its chain of
+  //  dependent loads, not by the two atomics per insert, and the side-stream table reset costs more host time than the lookup
+  //  it saves — so it stays opt-in)
+  static const bool no_lat_packed = getenv("PYGB200_LAT_PACKED") == nullptr;
+  bool v2 = !synced && !nodedup && !disjoint && !any_time && L > 0 && (!sharded || p2p) &&
+            (lat ? (!no_lat_packed && !no_v2) : (!no_v2 || p2p || weighted));
   std::vector<i64> type_nodes((size_t)T, -1);   // nodes of each type, where a relation with that source type tells us
   for (int r = 0; r < R; ++r) type_nodes[rels[r].src_type] = std::max(type_nodes[rels[r].src_type], (i64)rels[r].num_src_nodes);
   if (v2)   // every node type's id range must be known and fit the packed key (a type that is never a source has no bound)
@@ -2411,7 +2539,7 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
       else k_seed_times<int64_t><<<g, NT, 0, st>>>(s->seed_times.as<i64>(), (const int64_t*)seeds[t], n_seeds[t], batch0, stt, ntt);
       PYGB_LAUNCH_CHECK();
     }
-    if (v2) {
+    if (v2 && !lat) {
       if (n_seeds[t] == 0) continue;   // the zeroed state already says "empty list, empty slice"
       if (p2p) { a.pk_main = a.pk; a.pk_main_bits = a.pk_bits; a.pk = s->seedpk[s->v2_side].as<u64>(); a.pk_bits = s->seedpk_bits[s->v2_side]; }
       a.sd_begin = lay.o_begin + t; a.sd_end = lay.o_end + t; a.sd_nph = lay.o_nph + t * (L + 1);   // (k_seed_end folded into the mark kernel)
@@ -2514,19 +2642,29 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
         }
         a.group = sample_group_lanes(k);
         const int gs = grid_for(Fb, sample_nodes_per_block(a.group), s->sm_count);
+        if (v2) {   // does any later pass insert into this dst type's table?  (else the ids need not be written back)
+          a.v2_writeback = 0;
+          for (int h2 = h; h2 < L && !a.v2_writeback; ++h2)
+            for (int r2 = (h2 == h ? r + 1 : 0); r2 < R && !a.v2_writeback; ++r2)
+              a.v2_writeback = rels[r2].dst_type == dst_t && num_neighbors[(size_t)r2 * L + h2] != 0 &&
+                               fb[(size_t)rels[r2].src_type * (L + 1) + h2] != 0 && eb[(size_t)r2 * L + h2] != 0;
+        }
         tk = prof_begin(st);
-        if (idx32) launch_pdl(k_sample_s<int32_t>, gs, NT, st, a); else launch_pdl(k_sample_s<int64_t>, gs, NT, st, a);
+        if (v2) { if (idx32) launch_pdl(k_sample_s<int32_t, true>, gs, NT, st, a); else launch_pdl(k_sample_s<int64_t, true>, gs, NT, st, a); }
+        else if (idx32) launch_pdl(k_sample_s<int32_t>, gs, NT, st, a); else launch_pdl(k_sample_s<int64_t>, gs, NT, st, a);
         prof_end(tk, "sample", st, Eb);
         PYGB_LAUNCH_CHECK();
         tk = prof_begin(st);
-        launch_pdl(k_mark_s, grid_for(Eb, ETILE, s->sm_count), NT, st, a);
+        if (v2) launch_pdl(k_mark_p, grid_for(Eb, ETILE, s->sm_count), NT, st, a);
+        else launch_pdl(k_mark_s, grid_for(Eb, ETILE, s->sm_count), NT, st, a);
         prof_end(tk, "mark", st, Eb);
         PYGB_LAUNCH_CHECK();
         tk = prof_begin(st);
-        launch_pdl(k_assign_s, grid_for(Eb, NT, s->sm_count), NT, st, a);
+        if (v2) launch_pdl(k_assign_p, grid_for(Eb, NT, s->sm_count), NT, st, a);
+        else launch_pdl(k_assign_s, grid_for(Eb, NT, s->sm_count), NT, st, a);
         prof_end(tk, "assign", st, Eb);
         PYGB_LAUNCH_CHECK();
-        lk_colv = a.colv; lk_vals = a.vals; lk_E = Eb; lk_w_E = base; lk_w_pbase = relcum[r].w;
+        if (!v2) { lk_colv = a.colv; lk_vals = a.vals; lk_E = Eb; lk_w_E = base; lk_w_pbase = relcum[r].w; }   // (packed: ids are final)
         cursor = Wd{base + 1, 0}; relcum[r] = Wd{base + 2, 0}; cur_list[dst_t] = Wd{base + 3, 0};
         eph_w[(size_t)r * L + h] = base;
       }
