@@ -1563,6 +1563,7 @@ struct pygb200_sampler {
   DevBuf eslot, erank, rec, tile_out, tile_func, tile_off, tile_pos, mtile, raw, st, gen;
   DevBuf fref;              // v2, single GPU: ref of every edge of the running pass
   DevBuf wkey, widx, wl_bits, wl_tab;   // biased sampling: key / index scratch, MKL logf deviations (bitmap + sorted list)
+  DevBuf eraw;              // mixed biased / uniform relations: the RandintEngine's blocks, compacted (see sampler_run_impl)
   bool wl_ready = false;
   DevBuf seedpk[2];         // v2, sharded: scratch tables for the replicated dedup of the seeds (all-EMPTY between runs; one per side)
   int seedpk_bits[2] = {0, 0};
@@ -1701,7 +1702,7 @@ extern "C" void pygb200_sampler_destroy(pygb200_sampler* s) {
     for (int i = 0; i < 2; ++i) { t.pk[i].release(); t.vslot[i].release(); }
   }
   s->fref.release(); s->seedpk[0].release(); s->seedpk[1].release();
-  s->wkey.release(); s->widx.release(); s->wl_bits.release(); s->wl_tab.release();
+  s->wkey.release(); s->widx.release(); s->wl_bits.release(); s->wl_tab.release(); s->eraw.release();
   for (int q = 0; q < s->x.world; ++q) if (q != s->x.rank && s->x.peer[q]) cudaIpcCloseMemHandle(s->x.peer[q]);
   if (s->x.base) cudaFree(s->x.base);
   for (auto& r : s->rels) { r.row.release(); r.colv.release(); r.eid.release(); }
@@ -2065,22 +2066,25 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
       PYGB_CHECK(n_seeds[t] == 0 || (temporal->seed_time && temporal->seed_time[t]) || (temporal->node_time && temporal->node_time[t]),
                  PYGB200_ERR_ARG, "Seed time needs to be specified");
   }
-  // biased sampling (edge_weight): every relation or none — the reference lets relations without weights draw from its
-  // RandintEngine in between, which interleaves two consumers of one engine stream (not reproduced here)
-  bool weighted = false;
+  // biased sampling (edge_weight): per relation (neighbor_kernel.cpp:732-745).  `mixed` = some relations with weights, some without:
+  // the weighted ones take engine outputs directly while the others draw from the RandintEngine, whose 256-output blocks then sit
+  // wherever the generator happened to be when a block ran out — see "mixed" below.
+  bool weighted = false, mixed = false;
+  std::vector<char> wrel((size_t)std::max(R, 1), 0);
   if (edge_weight) {
     int nw = 0;
-    for (int r = 0; r < R; ++r) nw += edge_weight[r] != nullptr;
+    for (int r = 0; r < R; ++r) { wrel[r] = edge_weight[r] != nullptr; nw += wrel[r]; }
     weighted = nw > 0;
-    PYGB_CHECK(nw == 0 || nw == R, PYGB200_ERR_UNSUPPORTED,
-               "biased sampling: edge weights must be given for every relation or for none on this path");
+    mixed = nw > 0 && nw < R;
     PYGB_CHECK(!weighted || !any_time, PYGB200_ERR_ARG, "Biased temporal sampling not yet supported");   // neighbor_kernel.cpp:377-380
     if (weighted && replace)
-      for (size_t i = 0; i < (size_t)R * L; ++i)
-        PYGB_CHECK(num_neighbors[i] != 1, PYGB200_ERR_UNSUPPORTED,
-                   "biased sampling with replacement and a fan-out of 1: at::multinomial(n_sample=1) draws from an MKL VSL stream "
-                   "(exponential_), which this path does not reproduce");
+      for (int r = 0; r < R; ++r)
+        for (int h = 0; h < L && wrel[r]; ++h)
+          PYGB_CHECK(num_neighbors[(size_t)r * L + h] != 1, PYGB200_ERR_UNSUPPORTED,
+                     "biased sampling with replacement and a fan-out of 1: at::multinomial(n_sample=1) draws from an MKL VSL stream "
+                     "(exponential_), which this path does not reproduce");
   }
+  if (mixed) synced = true;   // the host follows the engine's block count pass by pass
   sub_lap(0);
   const bool sharded = shard != nullptr && shard->world > 1;
   const bool nodedup = (flags & PYGB200_S_NO_DEDUP) != 0;
@@ -2293,6 +2297,11 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
   }
   s->mt_valid = false;  // until this run completes
   i64 raw_cap = s->raw_cap_words;
+  if (mixed) {   // the engine's first block (fetched by its constructor, before anything else draws) opens the compacted copy
+    if (int e = mt_request(s, st, out0 + 512 + MT_N)) return e;
+    if (int e = s->eraw.ensure(512 * 4, 0, st)) return e;
+    PYGB_CUDA(cudaMemcpyAsync(s->eraw.p, s->raw.as<u32>() + out0, 256 * 4, cudaMemcpyDeviceToDevice, st));
+  }
 
   // ---- init: zero state.  Two halves: the previous run's k_final already cleared the one this run uses.
   if (s->st_dev_words != lay.words) {
@@ -2421,6 +2430,7 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
   // scratch are sized -> draws -> inserts -> ids.  The engine outputs of biased passes follow the RandintEngine's first
   // (and, on this path, only) block of 256.
   i64 wwords = 0;
+  i64 eng_blocks_max = 1;   // mixed: upper bound of the RandintEngine blocks fetched so far
   auto biased_error = [&](i64 code) -> int {
     PYGB_CHECK(code != W_ERR_NEG, PYGB200_ERR_ARG, "invalid multinomial distribution (encountering probability entry < 0)");
     PYGB_CHECK(code != W_ERR_INF, PYGB200_ERR_ARG, "invalid multinomial distribution (encountering probability entry = infinity or NaN)");
@@ -2453,7 +2463,10 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
     const i64 F = s->st_host[ST_PASS_F], E = s->st_host[ST_PASS_E], W = s->st_host[ST_W_WORDS], S = s->st_host[ST_W_SCR];
     if (int e = s->wkey.ensure((size_t)std::max<i64>(S, 1) * 4, 0, st)) return e;
     if (int e = s->widx.ensure((size_t)std::max<i64>(S, 1) * 4, 0, st)) return e;
-    const i64 need = out0 + 256 + wwords + W + 2 * MT_N;
+    // the engine outputs of this pass follow whatever the generator has handed out so far: the RandintEngine's blocks (one,
+    // fetched by its constructor, unless uniform relations have drawn from it: `mixed`) and the earlier biased passes
+    const i64 eng_words = 256 * rng_blocks_for_units(s->st_host[ST_CURSOR]);
+    const i64 need = out0 + eng_words + wwords + W + 2 * MT_N;
     const i64 cap_need = need + 2 * (i64)s->jump_S + 8 * MT_N;
     if (cap_need > raw_cap) {
       PYGB_CHECK(cap_need < ((i64)1 << 33), PYGB200_ERR_UNSUPPORTED, "biased sampling: a run may consume at most 2^33 engine outputs");
@@ -2471,7 +2484,7 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
     wa.weight = reinterpret_cast<const float*>(edge_weight[r]);
     wa.skey = s->wkey.as<float>(); wa.sidx = s->widx.as<u32>();
     wa.lbits = s->wl_bits.as<u32>(); wa.ltab = s->wl_tab.as<u32>(); wa.ltab_n = kMklLogfTableN;
-    wa.wbase = out0 + 256 + wwords;
+    wa.wbase = out0 + eng_words + wwords;
     wwords += W;
     void* tk = prof_begin(st);
     const int gw = (int)std::min<i64>(std::max<i64>(ceil_div(F, NT / 32), 1), (i64)s->sm_count * 16);
@@ -2703,7 +2716,7 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
         a.o_eph = lay.o_eph + r * L + h;
         a.lk_colv = lk_colv; a.lk_vals = lk_vals;
         with_hop_end(a);
-        if (!weighted) if (int e = idx32 ? launch_count<int32_t>(s, a, Fb, lk_E, st) : launch_count<int64_t>(s, a, Fb, lk_E, st)) return e;
+        if (!wrel[r]) if (int e = idx32 ? launch_count<int32_t>(s, a, Fb, lk_E, st) : launch_count<int64_t>(s, a, Fb, lk_E, st)) return e;
         if (v2) {
           // does any later pass insert into this dst type's table?  (else the ids need not be written back)
           a.v2_writeback = 0;
@@ -2711,7 +2724,7 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
             for (int r2 = (h2 == h ? r + 1 : 0); r2 < R && !a.v2_writeback; ++r2)
               a.v2_writeback = rels[r2].dst_type == dst_t && num_neighbors[(size_t)r2 * L + h2] != 0 &&
                                fb[(size_t)rels[r2].src_type * (L + 1) + h2] != 0 && eb[(size_t)r2 * L + h2] != 0;
-          if (weighted) {
+          if (wrel[r]) {
             if (int e = biased_pass(a, r, Fb)) return e;
             if (r == last_r) hop_closed = true;
             continue;
@@ -2768,7 +2781,7 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
           if (r == last_r) hop_closed = true;
           continue;
         }
-        if (weighted) {   // wide table (disjoint / 64-bit ids): biased draws, then the expand-from-edge-ids stage the sharded path uses
+        if (wrel[r]) {   // wide table (disjoint / 64-bit ids): biased draws, then the expand-from-edge-ids stage the sharded path uses
           if (int e = biased_count(a, Fb, lk_E)) return e;
           if (int e = biased_draws(a, r)) return e;
           if (nodedup) continue;   // (row / edge id / global id are already what a distributed hop returns)
@@ -2816,22 +2829,39 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
         const i64 F = s->st_host[lay.o_end + src_t] - s->st_host[lay.o_begin + src_t];
         if (F == 0) continue;
         if (int e = ensure_frontier_scratch(s, F, st)) return e;
-        if (k > 0 && !weighted) {  // draws possible: make sure the raw stream buffer can hold this pass
+        i64 eng_blocks = 0;   // mixed: blocks of the RandintEngine this pass may touch
+        if (k > 0 && !wrel[r]) {  // draws possible: make sure the raw stream buffer can hold this pass
           const i64 upu = rels[r].num_edges < 65536 ? 1 : (rels[r].num_edges < ((i64)1 << 32) ? 3 : 7);
           if (int e = read_state()) return e;
-          const i64 need = out0 + 256 * (rng_blocks_for_units(s->st_host[ST_CURSOR] + sat_mul(sat_mul(F, k), upu)) + 1) + 3 * MT_N;
+          eng_blocks = rng_blocks_for_units(s->st_host[ST_CURSOR] + sat_mul(sat_mul(F, k), upu)) + 1;
+          const i64 need = out0 + 256 * eng_blocks + wwords + 3 * MT_N + (mixed ? 2 * (i64)s->jump_S + 8 * MT_N : 0);
           if (need > raw_cap) {
             i64 gen_now = 0;
             PYGB_CUDA(cudaMemcpyAsync(&gen_now, s->gen.p, 8, cudaMemcpyDeviceToHost, st));
             PYGB_CUDA(cudaStreamSynchronize(st));
             if (int e = s->raw.ensure((size_t)need * 4, (size_t)gen_now * 4, st)) return e;
-            raw_cap = need; s->raw_cap_words = need;
+            raw_cap = s->raw_cap_words = (i64)(s->raw.cap / 4);
+          }
+          if (mixed) {
+            // ---- mixed biased / uniform relations.  The reference's RandintEngine fetches a block of 256 engine outputs whenever it
+            // runs out (rand_engine.h:53-61,80-85); biased relations take outputs in between, so block b of the engine sits at
+            // out0 + 256 b + (outputs the biased passes had consumed when b was fetched).  The uniform kernels index a stream in
+            // which the blocks are contiguous: that stream is kept as a compacted copy (`eraw`).  Blocks the engine has already
+            // fetched (b < used) stay; every block it may fetch during this pass is (re)copied from where it would sit NOW.
+            const i64 used = rng_blocks_for_units(s->st_host[ST_CURSOR]);
+            if (int e = mt_request(s, st, out0 + 256 * eng_blocks + wwords + 2 * MT_N)) return e;
+            if (int e = s->eraw.ensure((size_t)eng_blocks * 256 * 4, (size_t)used * 256 * 4, st)) return e;
+            PYGB_CUDA(cudaMemcpyAsync(s->eraw.as<u32>() + 256 * used, s->raw.as<u32>() + out0 + 256 * used + wwords,
+                                      (size_t)(eng_blocks - used) * 256 * 4, cudaMemcpyDeviceToDevice, st));
+            eng_blocks_max = std::max(eng_blocks_max, eng_blocks);
           }
         }
         PassArgs a = make_args(src_t, dst_t, r);
         a.fanout = k;
         a.o_eph = lay.o_eph + r * L + h;
-        if (weighted) {
+        auto use_eraw = [&](PassArgs& x) { if (mixed && !wrel[r]) { x.raw = s->eraw.as<u32>(); x.out0 = 0; x.raw_cap = (i64)(s->eraw.cap / 4); } };
+        use_eraw(a);
+        if (wrel[r]) {
           if (int e = biased_count(a, F, 0)) return e;
         } else {
           if (int e = idx32 ? launch_count<int32_t>(s, a, F, 0, st) : launch_count<int64_t>(s, a, F, 0, st)) return e;
@@ -2847,15 +2877,16 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
         a = make_args(src_t, dst_t, r);  // pointers may have moved
         a.fanout = k;
         a.o_eph = lay.o_eph + r * L + h;
-        if (weighted) if (int e = biased_draws(a, r)) return e;   // (row / edge id / global dst id of every sampled edge)
+        use_eraw(a);
+        if (wrel[r]) if (int e = biased_draws(a, r)) return e;   // (row / edge id / global dst id of every sampled edge)
         if (nodedup) {
-          if (weighted) continue;
+          if (wrel[r]) continue;
           a.phase = 3;
           if (int e = idx32 ? launch_sample<int32_t>(s, a, F, E, st) : launch_sample<int64_t>(s, a, F, E, st)) return e;
           continue;
         }
         with_hop_end(a);
-        if (weighted) {
+        if (wrel[r]) {
           PassArgs d = a;
           d.phase = 2;   // expand from the edge ids: gather, hash insert
           if (int e = idx32 ? launch_sample<int32_t>(s, d, F, E, st) : launch_sample<int64_t>(s, d, F, E, st)) return e;
@@ -2870,6 +2901,7 @@ int sampler_run_impl(pygb200_sampler* s, int32_t T, int32_t R, int32_t L, const 
     }
   }
 
+  if (mixed) if (int e = mt_request(s, st, out0 + 256 * eng_blocks_max + wwords + 2 * MT_N)) return e;   // (the state k_final publishes)
   // ---- final kernel (deferred lookup of the last pass + engine state), counts to the host
   {
     PassArgs a = make_args(-1, 0, -1);

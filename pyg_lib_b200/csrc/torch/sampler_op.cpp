@@ -415,20 +415,17 @@ hetero_neighbor_sample_cuda(const std::vector<node_type>& node_types, const std:
         PYGB_TORCH_CALL(pygb200_sampler_bind_outputs(s, T, R, rp.data(), cp.data(), ep.data(), np.data(), ecap.data(), ncap.data()));
       }
     }
-    // biased sampling: every relation must come with weights on this path (the reference lets weighted and unweighted
-    // relations share one engine stream; that interleaving is not reproduced)
+    // biased sampling: relations that come with weights (neighbor_kernel.cpp:732-745); the others keep drawing uniformly
     std::vector<const void*> wp(std::max(R, 1), nullptr);
     bool biased = false;
-    if (edge_weight_dict.has_value() && edge_weight_dict->size() > 0 &&
-        std::any_of(nn.begin(), nn.end(), [](int64_t k) { return k >= 0; })) {
-      biased = true;
+    if (edge_weight_dict.has_value() && edge_weight_dict->size() > 0)
       for (int r = 0; r < R; ++r) {
         const rel_type rk = to_rel_type(edge_types[r]);
-        TORCH_CHECK(edge_weight_dict->contains(rk), "pyg_lib_b200: 'edge_weight_dict' must hold weights for every edge type (missing '", rk,
-                    "'): mixing biased and uniform relations in one call is not implemented on the B200 path");
+        const auto& v = num_neighbors_dict.at(rk);
+        if (!edge_weight_dict->contains(rk) || std::none_of(v.begin(), v.end(), [](int64_t k) { return k >= 0; })) continue;
         wp[r] = weight_ptr(edge_weight_dict->at(rk), col_dict.at(rk), dev);
+        biased = true;
       }
-    }
     CpuEngine eng;
     if (biased)
       PYGB_TORCH_CALL(pygb200_sampler_run_weighted(s, T, R, (int)L, rels.data(), seeds.data(), n_seeds.data(), nn.data(), flags,

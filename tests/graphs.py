@@ -457,6 +457,16 @@ HETERO_WEIGHTED_CASES: Dict[str, dict] = {
                              num_neighbors=[6, 3], rng_seed=33, gseed=31, weights='masked', csc=True),
     'mag_w_disjoint': dict(kind='mag', sizes=dict(paper=600, author=400, institution=20), avg_deg=6, n_seeds=dict(paper=6, author=5),
                            num_neighbors=[4, 3], rng_seed=34, gseed=34, weights='uniform', disjoint=True),
+    # weights for SOME relations (`weighted_rels`: indices into the edge type list): biased and uniform relations take turns on the
+    # engine stream, the RandintEngine refills (one block = 512 16-bit draws) land between the biased relations' outputs
+    'mag_mixed': dict(kind='mag', sizes=dict(paper=3000, author=2000, institution=40), avg_deg=30, n_seeds=dict(paper=8),
+                      num_neighbors=[10, 6], rng_seed=35, gseed=32, weights='uniform', weighted_rels=[0, 1, 4]),
+    'mag_mixed_rep': dict(kind='mag', sizes=dict(paper=3000, author=2000, institution=40), avg_deg=30, n_seeds=dict(paper=8, author=4),
+                          num_neighbors=[8, 5], rng_seed=36, gseed=32, weights='masked_pos', weighted_rels=[1, 3], replace=True),
+    'mag_mixed_disjoint_masked': dict(kind='mag', sizes=dict(paper=600, author=400, institution=20), avg_deg=6, n_seeds=dict(paper=6, author=5),
+                                      num_neighbors=[4, 3, 2], rng_seed=37, gseed=34, weights='masked', weighted_rels=[2, 3, 5], disjoint=True),
+    'mag_mixed_csc_one': dict(kind='mag', sizes=dict(paper=3000, author=2000, institution=40), avg_deg=30, n_seeds=dict(paper=16),
+                              num_neighbors=[12, 4], rng_seed=38, gseed=32, weights='uniform', weighted_rels=[5], csc=True),
 }
 
 
@@ -489,5 +499,6 @@ def build_hetero_weighted(case: dict):
     node_types, edge_types, rowptr_d, col_d, seed_d, nn_d = build_hetero(case)
     if 'seeds' in case:
         seed_d = {'paper': torch.tensor(case['seeds'])}
-    w_d = {k: build_weights(case['weights'], rowptr_d[k], case['rng_seed'] + i) for i, k in enumerate(rowptr_d)}
+    w_d = {k: build_weights(case['weights'], rowptr_d[k], case['rng_seed'] + i) for i, k in enumerate(rowptr_d)
+           if 'weighted_rels' not in case or i in case['weighted_rels']}
     return node_types, edge_types, rowptr_d, col_d, seed_d, nn_d, w_d

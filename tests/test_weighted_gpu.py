@@ -194,16 +194,6 @@ def test_errors(lib):
     _cmp(out, W.neighbor_sample(rowptr, col, seed.cpu(), [3, 2], wodd))
 
 
-def test_hetero_needs_weights_for_every_relation(lib):
-    case = HETERO_WEIGHTED_CASES['mag_w']
-    nt, et, rp, cl, sd, nn, wd = build_hetero_weighted(case)
-    dv = lambda d: {k: v.to(DEV) for k, v in d.items()}  # noqa: E731
-    some = dict(list(wd.items())[:2])
-    with pytest.raises(RuntimeError, match='every edge type'):
-        torch.ops.pyg.hetero_neighbor_sample(nt, et, dv(rp), dv(cl), dv(sd), nn, None, None, None, dv(some), False, False, True, False,
-                                             'uniform', True)
-
-
 @pytest.mark.parametrize('replace', [False, True])
 @pytest.mark.parametrize('disjoint', [False, True])
 def test_weighted_dist_neighbor_sample_is_one_hop_of_neighbor_sample(lib, replace, disjoint):
