@@ -176,9 +176,10 @@ int pygb200_sampler_run_temporal(pygb200_sampler* s, int32_t T, int32_t R, int32
  * log(u) / weight without — reproducing the reference bit for bit INCLUDING the CPU generator stream it consumes
  * (uniform_/random64 outputs), torch's CPU float32 log (MKL; table of its deviations from the correctly rounded log)
  * and at::topk's libstdc++ tie behaviour.  edge_weight[r]: device pointer to relation r's weights (one per edge,
- * weight_dtype = PYGB200_F32), for EVERY relation.  All flags of pygb200_sampler_run apply (PYGB200_S_DISJOINT,
+ * weight_dtype = PYGB200_F32) or NULL: that relation samples uniformly (the reference's interleaving of the two kinds of
+ * draws on one generator is reproduced; such runs synchronise with the host after every pass).  All flags of pygb200_sampler_run apply (PYGB200_S_DISJOINT,
  * PYGB200_S_REPLACE, PYGB200_S_NO_DEDUP = the reference's distributed one-hop sampling, -1 fan-outs).  Limits
- * (PYGB200_ERR_UNSUPPORTED): weights for every relation or none; with replacement no fan-out of 1 (at::multinomial(n_sample=1)
+ * (PYGB200_ERR_UNSUPPORTED): with replacement no fan-out of 1 (at::multinomial(n_sample=1)
  * samples from an MKL VSL stream); one GPU; not temporal (the reference refuses that too).  Invalid weights under replacement
  * (negative, NaN/inf, zero row sum) return PYGB200_ERR_ARG with at::multinomial's message.  One host synchronisation per
  * (hop, relation): the number of engine outputs a pass consumes is data dependent. */
