@@ -21,6 +21,7 @@ for f in *.sm_100a.cubin; do
   awk '/Function :/ {fn=$3} /UTCHMMA/ {n[fn]++} END {for (k in n) printf "  %-110s UTCHMMA x%d\n", k, n[k]}' "$f.sass" | c++filt | cut -c1-170
 done
 echo
-echo "# peer-memory stores of the sharded sampler (ld/st.global on IPC-mapped pointers, same kernel as the draws):"
-awk '/Function :/ {fn=$3} /STG/ {n[fn]++} END {for (k in n) if (k ~ /k_v2_sample.*Lb1/ || k ~ /k_v2_reduce/ || k ~ /k_xbarrier/) printf "  %-110s STG x%d\n", k, n[k]}' sampler.sm_100a.cubin.sass | c++filt | cut -c1-170
+echo "# stores of the sharded sampler's exchange kernels (st.global on IPC-mapped peer pointers: k_v2_push = the all-gather of sampled edges,"
+echo "# k_v2_exc = ref exceptions, k_xbarrier = flags; k_v2_sample<.., true> stores into the rank's own exchange region):"
+awk '/Function :/ {fn=$3} /STG/ {n[fn]++} END {for (k in n) if (k ~ /k_v2_sample.*Lb1/ || k ~ /k_v2_push/ || k ~ /k_v2_exc/ || k ~ /k_xbarrier/) printf "  %-110s STG x%d\n", k, n[k]}' sampler.sm_100a.cubin.sass | c++filt | cut -c1-170
 rm -rf "$T"
